@@ -1,0 +1,313 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_core.hpp header).
+// C interface for tests/ (ctypes), __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+#include <thread>
+#include <chrono>
+
+#include "oracle_build.hpp"
+#include "oracle_disk.hpp"
+#include "oracle_query.hpp"
+
+using namespace orc;
+
+extern "C" {
+
+// Shared by the oracle and (same layout) the product's pcv_location, so tests build one struct.
+struct orc_location {
+    int32_t kind;  // 0 all, 1 aabb, 2 frustum, 3 obb
+    int32_t pad;
+    double aabb_min[3], aabb_max[3];
+    double clip_from_query[16], query_from_clip[16];  // column-major (nalgebra)
+    double query_from_obb[7], obb_from_query[7];      // tx,ty,tz, qi,qj,qk,qw
+    double half_extent[3];
+};
+
+static Iso3 iso_from7(const double* v) {
+    Iso3 r;
+    r.t = {v[0], v[1], v[2]};
+    r.q[0] = v[3];
+    r.q[1] = v[4];
+    r.q[2] = v[5];
+    r.q[3] = v[6];
+    return r;
+}
+
+static Location to_loc(const orc_location* l) {
+    Location r;
+    r.kind = l->kind;
+    r.aabb = Aabb::make({l->aabb_min[0], l->aabb_min[1], l->aabb_min[2]}, {l->aabb_max[0], l->aabb_max[1], l->aabb_max[2]});
+    std::memcpy(r.frustum.clip_from_query.m, l->clip_from_query, sizeof(double) * 16);
+    std::memcpy(r.frustum.query_from_clip.m, l->query_from_clip, sizeof(double) * 16);
+    r.obb.query_from_obb = iso_from7(l->query_from_obb);
+    r.obb.obb_from_query = iso_from7(l->obb_from_query);
+    r.obb.half_extent = {l->half_extent[0], l->half_extent[1], l->half_extent[2]};
+    return r;
+}
+
+struct Handle {
+    Octree oct;
+    std::vector<NodeId> order;  // sorted meta ids
+    double build_seconds = 0;
+};
+
+void orc_bbox(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, double* out6) {
+    Aabb b = find_bounding_box((size_t)n, x, y, z, (size_t)stride);
+    out6[0] = b.mins.x;
+    out6[1] = b.mins.y;
+    out6[2] = b.mins.z;
+    out6[3] = b.maxs.x;
+    out6[4] = b.maxs.y;
+    out6[5] = b.maxs.z;
+}
+
+void* orc_build(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, const uint8_t* rgb,
+                const float* intensity, double resolution, const double* bbox_min, const double* bbox_max,
+                int64_t max_points_per_node, int num_threads) {
+    Builder b;
+    b.num_threads = num_threads > 0 ? num_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    b.P.resolution = resolution;
+    b.P.bbox = Aabb::make({bbox_min[0], bbox_min[1], bbox_min[2]}, {bbox_max[0], bbox_max[1], bbox_max[2]});
+    b.P.with_intensity = intensity != nullptr;
+    if (max_points_per_node > 0) b.P.max_points_per_node = max_points_per_node;
+    auto t0 = std::chrono::steady_clock::now();
+    Handle* h = new Handle();
+    h->oct = b.build((size_t)n, x, y, z, (size_t)stride, rgb, intensity);
+    h->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (auto& kv : h->oct.nodes) h->order.push_back(kv.first);
+    return h;
+}
+double orc_build_seconds(void* hp) { return ((Handle*)hp)->build_seconds; }
+int orc_max_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+void orc_free(void* hp) { delete (Handle*)hp; }
+
+uint64_t orc_num_nodes(void* hp) { return ((Handle*)hp)->order.size(); }
+
+void orc_node_info(void* hp, uint64_t i, uint64_t* hi, uint64_t* lo, int64_t* num_points, int32_t* enc, double* cube4) {
+    Handle* h = (Handle*)hp;
+    NodeId id = h->order[i];
+    const NodeMeta& m = h->oct.nodes[id];
+    *hi = id.high();
+    *lo = id.low();
+    *num_points = m.num_points;
+    *enc = (int32_t)m.enc;
+    cube4[0] = m.cube.min.x;
+    cube4[1] = m.cube.min.y;
+    cube4[2] = m.cube.min.z;
+    cube4[3] = m.cube.edge;
+}
+
+// Copies node content; any out pointer may be null. Returns number of points or -1 if unknown id.
+int64_t orc_node_data(void* hp, uint64_t hi, uint64_t lo, uint8_t* xyz, uint8_t* rgb, float* intensity, uint64_t* src) {
+    Handle* h = (Handle*)hp;
+    NodeId id = NodeId::from_high_low(hi, lo);
+    if (!h->oct.nodes.count(id)) return -1;
+    auto it = h->oct.files.find(id);
+    if (it == h->oct.files.end()) return 0;
+    const NodeFile& f = it->second;
+    if (xyz) std::memcpy(xyz, f.xyz.data(), f.xyz.size());
+    if (rgb) std::memcpy(rgb, f.rgb.data(), f.rgb.size());
+    if (intensity && !f.intensity.empty()) std::memcpy(intensity, f.intensity.data(), f.intensity.size() * 4);
+    if (src) std::memcpy(src, f.src.data(), f.src.size() * 8);
+    return f.num_points();
+}
+
+// ---- scalar codec / node-id vectors ----
+uint64_t orc_encode(double value, double min, double edge, int enc) { return encode_coord(value, min, edge, (Enc)enc); }
+double orc_decode(uint64_t bits, double min, double edge, int enc) { return decode_coord(bits, min, edge, (Enc)enc); }
+int orc_position_encoding(double edge, double resolution) { return (int)position_encoding(Cube{{0, 0, 0}, edge}, resolution); }
+void orc_find_bounding_cube(uint64_t hi, uint64_t lo, const double* root_min, double root_edge, double* out4) {
+    Cube c = find_bounding_cube(NodeId::from_high_low(hi, lo), Cube{{root_min[0], root_min[1], root_min[2]}, root_edge});
+    out4[0] = c.min.x;
+    out4[1] = c.min.y;
+    out4[2] = c.min.z;
+    out4[3] = c.edge;
+}
+void orc_cube_bounding(const double* mn, const double* mx, double* out4) {
+    Cube c = Cube::bounding(Aabb::make({mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]}));
+    out4[0] = c.min.x;
+    out4[1] = c.min.y;
+    out4[2] = c.min.z;
+    out4[3] = c.edge;
+}
+int orc_child_index(const double* cube4, const double* p) {
+    return (int)child_index_of(Cube{{cube4[0], cube4[1], cube4[2]}, cube4[3]}, {p[0], p[1], p[2]});
+}
+void orc_node_id_from_string(const char* s, uint64_t* hi, uint64_t* lo) {
+    NodeId id = NodeId::from_string(s);
+    *hi = id.high();
+    *lo = id.low();
+}
+void orc_node_id_to_string(uint64_t hi, uint64_t lo, char* out, int cap) {
+    std::string s = NodeId::from_high_low(hi, lo).to_string();
+    std::snprintf(out, (size_t)cap, "%s", s.c_str());
+}
+void orc_node_id_parent(uint64_t hi, uint64_t lo, uint64_t* phi, uint64_t* plo, int* child_index) {
+    NodeId id = NodeId::from_high_low(hi, lo);
+    *child_index = id.child_index();
+    NodeId p = id.has_parent() ? id.parent() : id;
+    *phi = p.high();
+    *plo = p.low();
+}
+void orc_node_id_child(uint64_t hi, uint64_t lo, int k, uint64_t* chi, uint64_t* clo) {
+    NodeId c = NodeId::from_high_low(hi, lo).child((unsigned)k);
+    *chi = c.high();
+    *clo = c.low();
+}
+
+// ---- SAT pins ----
+static Intersector mk_isec(const double* corners24, const double* edges, int ne, const double* faces, int nf) {
+    Intersector r;
+    for (int i = 0; i < 8; ++i) r.corners[i] = {corners24[3 * i], corners24[3 * i + 1], corners24[3 * i + 2]};
+    for (int i = 0; i < ne; ++i) r.edges.push_back({edges[3 * i], edges[3 * i + 1], edges[3 * i + 2]});
+    for (int i = 0; i < nf; ++i) r.face_normals.push_back({faces[3 * i], faces[3 * i + 1], faces[3 * i + 2]});
+    return r;
+}
+// Intersector::intersect (sat.rs:145-151)
+int orc_intersector_intersect(const double* ca, const double* ea, int nea, const double* fa, int nfa, const double* cb,
+                              const double* eb, int neb, const double* fb, int nfb) {
+    Intersector a = mk_isec(ca, ea, nea, fa, nfa), b = mk_isec(cb, eb, neb, fb, nfb);
+    return (int)sat(separating_axes(a, b.edges, b.face_normals), a.corners, 8, b.corners, 8);
+}
+static Intersector loc_intersector(const Location& l) {
+    if (l.kind == LOC_FRUSTUM) return l.frustum.intersector();
+    if (l.kind == LOC_OBB) return l.obb.intersector();
+    return aabb_intersector_generic(l.aabb);
+}
+// location.intersector().intersect(&aabb.intersector())   (math/mod.rs:212-215)
+int orc_location_intersect_aabb_generic(const orc_location* l, const double* mn, const double* mx) {
+    Location loc = to_loc(l);
+    Intersector a = loc_intersector(loc);
+    Intersector b = aabb_intersector_generic(Aabb::make({mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]}));
+    return (int)sat(separating_axes(a, b.edges, b.face_normals), a.corners, 8, b.corners, 8);
+}
+// location.intersector().cache_separating_axes_for_aabb(): number of axes + relation against an aabb
+int orc_cached_axes(const orc_location* l, double* axes_out, int cap) {
+    Location loc = to_loc(l);
+    CachedAxesIntersector c = cache_separating_axes_for_aabb(loc_intersector(loc));
+    for (int i = 0; i < (int)c.axes.size() && i < cap; ++i) {
+        axes_out[3 * i] = c.axes[i].x;
+        axes_out[3 * i + 1] = c.axes[i].y;
+        axes_out[3 * i + 2] = c.axes[i].z;
+    }
+    return (int)c.axes.size();
+}
+int orc_cached_intersect_aabb(const orc_location* l, const double* mn, const double* mx) {
+    Location loc = to_loc(l);
+    AabbIntersector isec = make_aabb_intersector(loc);
+    if (isec.all) return REL_IN;
+    Vec3 c[8];
+    Aabb::make({mn[0], mn[1], mn[2]}, {mx[0], mx[1], mx[2]}).corners(c);
+    return (int)isec.isec.intersect(c, 8);
+}
+int orc_location_contains(const orc_location* l, const double* p) { return to_loc(l).contains({p[0], p[1], p[2]}) ? 1 : 0; }
+void orc_location_corners(const orc_location* l, double* out24) {
+    Intersector a = loc_intersector(to_loc(l));
+    for (int i = 0; i < 8; ++i) {
+        out24[3 * i] = a.corners[i].x;
+        out24[3 * i + 1] = a.corners[i].y;
+        out24[3 * i + 2] = a.corners[i].z;
+    }
+}
+// contains via SAT with face normals only against a single point (point_cloud_test/tests/main.rs:104-127)
+int orc_location_contains_sat(const orc_location* l, const double* p) {
+    Intersector a = loc_intersector(to_loc(l));
+    Vec3 pt{p[0], p[1], p[2]};
+    return sat(a.face_normals, a.corners, 8, &pt, 1) == REL_IN ? 1 : 0;
+}
+int orc_try_inverse(const double* m16, double* out16) {
+    Mat4 a, b;
+    std::memcpy(a.m, m16, sizeof(a.m));
+    if (!try_inverse(a, b)) return 0;
+    std::memcpy(out16, b.m, sizeof(b.m));
+    return 1;
+}
+
+// ---- queries ----
+int64_t orc_nodes_in_location(void* hp, const orc_location* l, uint64_t* hi_lo_out, int64_t cap) {
+    Handle* h = (Handle*)hp;
+    std::vector<NodeId> ids = nodes_in_location(h->oct, to_loc(l));
+    for (int64_t i = 0; i < (int64_t)ids.size() && i < cap; ++i) {
+        hi_lo_out[2 * i] = ids[i].high();
+        hi_lo_out[2 * i + 1] = ids[i].low();
+    }
+    return (int64_t)ids.size();
+}
+
+int64_t orc_visible_nodes(void* hp, const double* m16, uint64_t* hi_lo_out, int64_t cap) {
+    Handle* h = (Handle*)hp;
+    Mat4 M;
+    std::memcpy(M.m, m16, sizeof(M.m));
+    std::vector<NodeId> ids;
+    if (!get_visible_nodes(h->oct, M, ids)) return -1;
+    for (int64_t i = 0; i < (int64_t)ids.size() && i < cap; ++i) {
+        hi_lo_out[2 * i] = ids[i].high();
+        hi_lo_out[2 * i + 1] = ids[i].low();
+    }
+    return (int64_t)ids.size();
+}
+
+// All points matching the query, nodes visited in nodes_in_location order (the reference's batch order
+// across nodes is unspecified; per node it is file order).  Two-call protocol: call with null outputs
+// to get the count.  `filters` = nfilt * {lo,hi} closed intervals on intensity.
+int64_t orc_query(void* hp, const orc_location* l, const double* filters, int nfilt, double* xyz, uint8_t* rgb, float* intensity,
+                  uint64_t* src, int64_t cap, int64_t* tested_points) {
+    Handle* h = (Handle*)hp;
+    Location loc = to_loc(l);
+    std::vector<Interval> fi;
+    for (int i = 0; i < nfilt; ++i) fi.push_back({0, filters[2 * i], filters[2 * i + 1]});
+    QueryOut out;
+    int64_t tested = 0;
+    for (NodeId id : nodes_in_location(h->oct, loc)) {
+        tested += h->oct.nodes[id].num_points;
+        query_node(h->oct, id, loc, fi, out);
+    }
+    if (tested_points) *tested_points = tested;
+    int64_t n = (int64_t)out.src.size();
+    if (xyz && n <= cap) {
+        std::memcpy(xyz, out.xyz.data(), out.xyz.size() * 8);
+        if (rgb) std::memcpy(rgb, out.rgb.data(), out.rgb.size());
+        if (intensity && !out.intensity.empty()) std::memcpy(intensity, out.intensity.data(), out.intensity.size() * 4);
+        if (src) std::memcpy(src, out.src.data(), out.src.size() * 8);
+    }
+    return n;
+}
+
+int orc_xray_tile(void* hp, const double* bbox_min, const double* bbox_max, uint32_t w, uint32_t hgt, const double* query_from_global7,
+                  uint8_t* rgba_out, uint32_t* zbits_out, uint8_t* zover_out) {
+    Handle* h = (Handle*)hp;
+    Aabb bb = Aabb::make({bbox_min[0], bbox_min[1], bbox_min[2]}, {bbox_max[0], bbox_max[1], bbox_max[2]});
+    Iso3 q{};
+    if (query_from_global7) q = iso_from7(query_from_global7);
+    std::vector<uint8_t> rgba, zover;
+    std::vector<uint32_t> zb;
+    bool any = xray_tile(h->oct, bb, w, hgt, query_from_global7 != nullptr, q, rgba, &zb, &zover);
+    std::memcpy(rgba_out, rgba.data(), rgba.size());
+    if (zbits_out && any) std::memcpy(zbits_out, zb.data(), zb.size() * 4);
+    if (zover_out && any) std::memcpy(zover_out, zover.data(), zover.size());
+    return any ? 1 : 0;
+}
+
+// ---- disk ----
+int orc_write_dir(void* hp, const char* dir) { return write_dir(((Handle*)hp)->oct, dir) ? 0 : -1; }
+void* orc_load_dir(const char* dir) {
+    Handle* h = new Handle();
+    if (!load_dir(dir, h->oct)) {
+        delete h;
+        return nullptr;
+    }
+    for (auto& kv : h->oct.nodes) h->order.push_back(kv.first);
+    return h;
+}
+void orc_octree_meta(void* hp, double* resolution, double* bbox6, int* with_intensity) {
+    Handle* h = (Handle*)hp;
+    *resolution = h->oct.resolution;
+    bbox6[0] = h->oct.bbox.mins.x;
+    bbox6[1] = h->oct.bbox.mins.y;
+    bbox6[2] = h->oct.bbox.mins.z;
+    bbox6[3] = h->oct.bbox.maxs.x;
+    bbox6[4] = h->oct.bbox.maxs.y;
+    bbox6[5] = h->oct.bbox.maxs.z;
+    *with_intensity = h->oct.with_intensity ? 1 : 0;
+}
+
+}  // extern "C"

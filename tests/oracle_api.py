@@ -1,0 +1,216 @@
+"""ctypes wrapper around oracle/_build/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+The oracle is the CPU restatement of the reference algorithm (see oracle/oracle_core.hpp).  Only
+tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_build", "liboracle.so")
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in os.listdir(os.path.join(_ROOT, "oracle")) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "-s"])
+    return _SO
+
+
+class Location(C.Structure):
+    """Same layout as pcv_location in include/pcv.h and orc_location in oracle_capi.cpp."""
+
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("pad", C.c_int32),
+        ("aabb_min", C.c_double * 3),
+        ("aabb_max", C.c_double * 3),
+        ("clip_from_query", C.c_double * 16),
+        ("query_from_clip", C.c_double * 16),
+        ("query_from_obb", C.c_double * 7),
+        ("obb_from_query", C.c_double * 7),
+        ("half_extent", C.c_double * 3),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(_SO)
+        dp, u8p, fp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint64)
+        L.orc_build.restype = C.c_void_p
+        L.orc_build.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, dp, dp, C.c_int64, C.c_int]
+        L.orc_build_seconds.restype = C.c_double
+        L.orc_build_seconds.argtypes = [C.c_void_p]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_num_nodes.restype = C.c_uint64
+        L.orc_num_nodes.argtypes = [C.c_void_p]
+        L.orc_node_info.argtypes = [C.c_void_p, C.c_uint64, u64p, u64p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp]
+        L.orc_node_data.restype = C.c_int64
+        L.orc_node_data.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_bbox.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, dp]
+        L.orc_encode.restype = C.c_uint64
+        L.orc_encode.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_decode.restype = C.c_double
+        L.orc_decode.argtypes = [C.c_uint64, C.c_double, C.c_double, C.c_int]
+        L.orc_position_encoding.argtypes = [C.c_double, C.c_double]
+        L.orc_find_bounding_cube.argtypes = [C.c_uint64, C.c_uint64, dp, C.c_double, dp]
+        L.orc_cube_bounding.argtypes = [dp, dp, dp]
+        L.orc_child_index.argtypes = [dp, dp]
+        L.orc_node_id_from_string.argtypes = [C.c_char_p, u64p, u64p]
+        L.orc_node_id_to_string.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_int]
+        L.orc_node_id_parent.argtypes = [C.c_uint64, C.c_uint64, u64p, u64p, C.POINTER(C.c_int)]
+        L.orc_node_id_child.argtypes = [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p]
+        L.orc_intersector_intersect.argtypes = [dp, dp, C.c_int, dp, C.c_int, dp, dp, C.c_int, dp, C.c_int]
+        LP = C.POINTER(Location)
+        L.orc_location_intersect_aabb_generic.argtypes = [LP, dp, dp]
+        L.orc_cached_axes.argtypes = [LP, dp, C.c_int]
+        L.orc_cached_intersect_aabb.argtypes = [LP, dp, dp]
+        L.orc_location_contains.argtypes = [LP, dp]
+        L.orc_location_contains_sat.argtypes = [LP, dp]
+        L.orc_location_corners.argtypes = [LP, dp]
+        L.orc_try_inverse.argtypes = [dp, dp]
+        L.orc_nodes_in_location.restype = C.c_int64
+        L.orc_nodes_in_location.argtypes = [C.c_void_p, LP, C.c_void_p, C.c_int64]
+        L.orc_visible_nodes.restype = C.c_int64
+        L.orc_visible_nodes.argtypes = [C.c_void_p, dp, C.c_void_p, C.c_int64]
+        L.orc_query.restype = C.c_int64
+        L.orc_query.argtypes = [C.c_void_p, LP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_xray_tile.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_write_dir.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_load_dir.restype = C.c_void_p
+        L.orc_load_dir.argtypes = [C.c_char_p]
+        L.orc_octree_meta.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return (C.c_double * len(a))(*[float(v) for v in a])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+ENC_BPC = {1: 1, 2: 2, 3: 4, 4: 8}
+
+
+def id_str(hi, lo):
+    buf = C.create_string_buffer(64)
+    lib().orc_node_id_to_string(int(hi), int(lo), buf, 64)
+    return buf.value.decode()
+
+
+def id_from_str(s):
+    hi, lo = C.c_uint64(), C.c_uint64()
+    lib().orc_node_id_from_string(s.encode(), C.byref(hi), C.byref(lo))
+    return hi.value, lo.value
+
+
+class OracleOctree:
+    def __init__(self, handle):
+        self.h = handle
+        L = lib()
+        n = L.orc_num_nodes(self.h)
+        self.nodes = {}  # "r012" -> dict(num_points, enc, cube, hi, lo)
+        self.order = []
+        hi, lo, npts, enc = C.c_uint64(), C.c_uint64(), C.c_int64(), C.c_int32()
+        cube = (C.c_double * 4)()
+        for i in range(n):
+            L.orc_node_info(self.h, i, C.byref(hi), C.byref(lo), C.byref(npts), C.byref(enc), cube)
+            name = id_str(hi.value, lo.value)
+            self.order.append(name)
+            self.nodes[name] = dict(num_points=npts.value, enc=enc.value, cube=tuple(cube), hi=hi.value, lo=lo.value)
+
+    def __del__(self):
+        try:
+            lib().orc_free(self.h)
+        except Exception:
+            pass
+
+    @property
+    def build_seconds(self):
+        return lib().orc_build_seconds(self.h)
+
+    def node_data(self, name, with_intensity=False):
+        m = self.nodes[name]
+        n = m["num_points"]
+        bpc = ENC_BPC[m["enc"]]
+        xyz = np.zeros(n * 3 * bpc, np.uint8)
+        rgb = np.zeros(n * 3, np.uint8)
+        inten = np.zeros(n, np.float32) if with_intensity else None
+        src = np.zeros(n, np.uint64)
+        got = lib().orc_node_data(self.h, m["hi"], m["lo"], _ptr(xyz), _ptr(rgb), _ptr(inten), _ptr(src))
+        assert got == n, (name, got, n)
+        return xyz, rgb, inten, src
+
+    def nodes_in_location(self, loc):
+        cap = len(self.nodes) + 1
+        out = np.zeros(2 * cap, np.uint64)
+        n = lib().orc_nodes_in_location(self.h, C.byref(loc), _ptr(out), cap)
+        return [id_str(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
+    def visible_nodes(self, m16):
+        cap = len(self.nodes) + 1
+        out = np.zeros(2 * cap, np.uint64)
+        n = lib().orc_visible_nodes(self.h, _d(m16), _ptr(out), cap)
+        if n < 0:
+            raise ValueError("Invalid projection matrix.")
+        return [id_str(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
+    def query(self, loc, filters=(), with_intensity=False):
+        f = np.asarray(filters, np.float64).reshape(-1)
+        nf = len(f) // 2
+        tested = C.c_int64()
+        n = lib().orc_query(self.h, C.byref(loc), _ptr(f) if nf else None, nf, None, None, None, None, 0, C.byref(tested))
+        xyz = np.zeros((n, 3), np.float64)
+        rgb = np.zeros((n, 3), np.uint8)
+        inten = np.zeros(n, np.float32) if with_intensity else None
+        src = np.zeros(n, np.uint64)
+        lib().orc_query(self.h, C.byref(loc), _ptr(f) if nf else None, nf, _ptr(xyz), _ptr(rgb), _ptr(inten), _ptr(src), n, C.byref(tested))
+        return dict(xyz=xyz, rgb=rgb, intensity=inten, src=src, tested=tested.value)
+
+    def xray_tile(self, bmin, bmax, w, h, query_from_global=None):
+        rgba = np.zeros((h, w, 4), np.uint8)
+        zbits = np.zeros((h, w, 32), np.uint32)
+        zover = np.zeros((h, w), np.uint8)
+        q = _d(query_from_global) if query_from_global is not None else None
+        any_ = lib().orc_xray_tile(self.h, _d(bmin), _d(bmax), w, h, q, _ptr(rgba), _ptr(zbits), _ptr(zover))
+        return bool(any_), rgba, zbits, zover
+
+    def write_dir(self, d):
+        assert lib().orc_write_dir(self.h, d.encode()) == 0
+
+    def meta(self):
+        res, bb, wi = C.c_double(), (C.c_double * 6)(), C.c_int()
+        lib().orc_octree_meta(self.h, C.byref(res), bb, C.byref(wi))
+        return res.value, tuple(bb), bool(wi.value)
+
+
+def build(x, y, z, rgb, resolution, bbox_min, bbox_max, intensity=None, max_points_per_node=100000, num_threads=0, stride=1):
+    n = len(rgb) // 3 if rgb.ndim == 1 else rgb.shape[0]
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    h = lib().orc_build(n, _ptr(x), _ptr(y), _ptr(z), stride, _ptr(rgb), _ptr(intensity), float(resolution), _d(bbox_min), _d(bbox_max), int(max_points_per_node), int(num_threads))
+    return OracleOctree(h)
+
+
+def load_dir(d):
+    h = lib().orc_load_dir(d.encode())
+    if not h:
+        raise IOError("oracle could not load " + d)
+    return OracleOctree(h)
+
+
+def bbox(x, y, z, stride=1):
+    out = (C.c_double * 6)()
+    n = len(x) if stride == 1 else len(x) // 1
+    lib().orc_bbox(n, _ptr(x), _ptr(y), _ptr(z), stride, out)
+    return tuple(out)
