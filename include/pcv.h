@@ -1,0 +1,191 @@
+/*
+ * pcv.h — C ABI of the B200-native octree builder / LOD + frustum point-query engine.
+ *
+ * This is the drop-in boundary for point_cloud_viewer's hot path: each entry point replaces a Rust
+ * function or trait method of crate `point_viewer` (citations = reference file:line).  The reference
+ * has no FFI of its own; INTEGRATION.md shows the Rust `extern "C"` block + shim a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 (PCV_OK) or a negative pcv_status and
+ *    never unwinds across the boundary; pcv_last_error() returns the text for the calling thread.
+ *  - "host" entry points take host memory (pinned or pageable) and copy inside the call; "_device"
+ *    entry points take device pointers already resident in HBM on the context's GPU.
+ *  - positions are f64; element i of a coordinate array is at ptr[i * stride] so both the SoA layout
+ *    (stride 1, three arrays) and the crate's AoS `Vec<Point3<f64>>` (stride 3, y = x+1, z = x+2) are
+ *    accepted without a host-side transpose.
+ *  - matrices are column-major like nalgebra::Matrix4<f64>; isometries are tx,ty,tz,qi,qj,qk,qw.
+ *  - NodeId is the crate's u128 (level << 120 | octal path index, src/octree/node.rs:52-111) passed
+ *    as (high, low) u64 halves exactly like proto::NodeId (node.rs:101-106).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    PCV_ERR_CUDA.
+ */
+#ifndef PCV_H
+#define PCV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcv_ctx pcv_ctx;       /* one per device; internally stream ordered              */
+typedef struct pcv_octree pcv_octree; /* a built / loaded octree, node data resident in HBM     */
+
+typedef enum pcv_status {
+    PCV_OK = 0,
+    PCV_ERR_INVALID = -1,     /* bad argument                                                    */
+    PCV_ERR_CUDA = -2,        /* CUDA runtime error or no device                                 */
+    PCV_ERR_IO = -3,          /* file system error (the reference unwrap()s these)               */
+    PCV_ERR_NOT_FOUND = -4,   /* ErrorKind::NodeNotFound (src/errors.rs)                         */
+    PCV_ERR_CANCELLED = -5,   /* callback returned non-zero == ErrorKind::Channel                */
+    PCV_ERR_UNSUPPORTED = -6, /* e.g. more than 2^32-1 points per context, depth > 40            */
+    PCV_ERR_SINGULAR = -7     /* get_visible_nodes: "Invalid projection matrix." (mod.rs:230)    */
+} pcv_status;
+
+/* PositionEncoding (src/read_write/codec.rs:22-28, proto.proto:78-84) */
+enum { PCV_ENC_UINT8 = 1, PCV_ENC_UINT16 = 2, PCV_ENC_FLOAT32 = 3, PCV_ENC_FLOAT64 = 4 };
+
+typedef struct pcv_config {
+    uint64_t max_points_per_node; /* MAX_POINTS_PER_NODE, generation.rs:37; 0 -> 100000          */
+    uint32_t levels_per_pass;     /* octree levels resolved per partition pass (1..3); 0 -> 3    */
+    uint32_t reserved;
+} pcv_config;
+
+typedef struct pcv_points {
+    const double* x; /* element i at x[i*stride]                                                 */
+    const double* y;
+    const double* z;
+    uint64_t stride;        /* 1 = SoA, 3 = AoS xyz                                              */
+    const uint8_t* rgb;     /* n * 3, "color" U8Vec3 (mandatory: on_disk.rs:23-33)               */
+    const float* intensity; /* n or NULL ("intensity" F32, octree/mod.rs:62-74)                  */
+    uint64_t n;
+} pcv_points;
+
+typedef struct pcv_node_meta {
+    uint64_t id_high, id_low; /* NodeId u128 halves                                              */
+    int64_t num_points;       /* may be 0: such nodes stay in meta.pb (generation.rs:241-243)    */
+    int32_t position_encoding;
+    int32_t level;
+    double cube_min[3]; /* NodeId::find_bounding_cube (node.rs:157-172)                          */
+    double cube_edge;
+    uint64_t point_offset;    /* first point of the node in the node-contiguous arrays           */
+    uint64_t xyz_byte_offset; /* first byte of the node's .xyz content                           */
+} pcv_node_meta;
+
+/* PointLocation (src/iterator.rs:13-20).  Same field layout as the oracle's orc_location. */
+enum { PCV_LOC_ALL = 0, PCV_LOC_AABB = 1, PCV_LOC_FRUSTUM = 2, PCV_LOC_OBB = 3 };
+typedef struct pcv_location {
+    int32_t kind;
+    int32_t pad;
+    double aabb_min[3], aabb_max[3];                 /* Aabb{mins,maxs}        aabb.rs:12-16     */
+    double clip_from_query[16], query_from_clip[16]; /* Frustum fields         frustum.rs:95-98  */
+    double query_from_obb[7], obb_from_query[7];     /* Obb fields             obb.rs:13-17      */
+    double half_extent[3];
+} pcv_location;
+
+typedef struct pcv_interval { /* ClosedInterval<f64> on "intensity" (math/mod.rs:65-89)          */
+    double lo, hi;
+} pcv_interval;
+
+/* A PointsBatch (src/lib.rs:102-107) delivered to the consumer: AoS positions + SoA attributes.  */
+typedef struct pcv_batch {
+    uint64_t n;
+    const double* xyz;         /* n * 3                                                          */
+    const uint8_t* rgb;        /* n * 3                                                          */
+    const float* intensity;    /* n or NULL                                                      */
+    const uint64_t* src_index; /* provenance: index of the point in the build input              */
+} pcv_batch;
+typedef int (*pcv_batch_cb)(void* user, const pcv_batch* batch); /* non-zero return cancels      */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pcv_create(int device, const pcv_config* cfg, pcv_ctx** out);
+void pcv_destroy(pcv_ctx* ctx);
+const char* pcv_last_error(void);
+int pcv_device_count(void);
+
+/* ---- a1: find_bounding_box (generation.rs:256-270, aabb.rs:41-44) -------------------------- */
+int pcv_bbox(pcv_ctx* ctx, const pcv_points* host_points, double out_min[3], double out_max[3]);
+int pcv_bbox_device(pcv_ctx* ctx, const pcv_points* dev_points, double out_min[3], double out_max[3]);
+
+/* ---- a2-a8: build_octree (generation.rs:289-403) -------------------------------------------- */
+int pcv_build_octree(pcv_ctx* ctx, const pcv_points* host_points, double resolution, const double bbox_min[3],
+                     const double bbox_max[3], pcv_octree** out);
+int pcv_build_octree_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
+                            const double bbox_max[3], pcv_octree** out);
+void pcv_octree_free(pcv_octree* o);
+
+/* ---- a8-a10: node table, node bytes, on-disk layout ----------------------------------------- */
+int pcv_octree_info(const pcv_octree* o, uint64_t* num_nodes, uint64_t* num_points, uint64_t* xyz_bytes, double* resolution,
+                    double bbox_min[3], double bbox_max[3], int* has_intensity);
+int pcv_octree_nodes(const pcv_octree* o, pcv_node_meta* out, uint64_t cap); /* sorted by NodeId   */
+/* Octree::get_node_data (octree/mod.rs:285-307): raw .xyz / .rgb bytes (+ intensity, provenance). */
+int pcv_octree_node_data(const pcv_octree* o, uint64_t id_high, uint64_t id_low, void* xyz_out, uint8_t* rgb_out,
+                         float* intensity_out, uint64_t* src_index_out);
+/* All nodes at once into caller (ideally pinned) buffers, node-contiguous in pcv_octree_nodes order. */
+int pcv_octree_download(const pcv_octree* o, void* xyz_out, uint8_t* rgb_out, float* intensity_out, uint64_t* src_index_out);
+/* Device views of the same arrays (valid until pcv_octree_free). */
+int pcv_octree_device_arrays(const pcv_octree* o, const void** xyz, const uint8_t** rgb, const float** intensity,
+                             const uint32_t** src_index);
+/* <dir>/<NodeId>.xyz|.rgb|.intensity + meta.pb (on_disk.rs:17-33, lib.rs:49,74-80, proto.proto:68-149). */
+int pcv_octree_write_dir(const pcv_octree* o, const char* dir);
+int pcv_octree_load_dir(pcv_ctx* ctx, const char* dir, pcv_octree** out); /* Octree::from_data_provider, mod.rs:156-215 */
+
+/* ---- a11-a14: nodes_in_location (octree/mod.rs:309-323, octree_iterator.rs:30-43) ---------- */
+int pcv_nodes_in_location(const pcv_octree* o, const pcv_location* loc, uint64_t* ids_hi_lo, uint64_t cap, uint64_t* n_out);
+
+/* ---- a17: Octree::get_visible_nodes (octree/mod.rs:228-283) --------------------------------- */
+int pcv_visible_nodes(const pcv_octree* o, const double clip_from_world[16], uint64_t* ids_hi_lo, uint64_t cap, uint64_t* n_out);
+
+/* ---- a15-a16: PointQuery streaming (iterator.rs:66-119,255-333) ----------------------------- */
+/* Streams every point of every node in `loc` that passes the culling + interval filters, re-chunked
+ * into batches of exactly batch_size points (last one short), on the caller's thread. */
+int pcv_query_points(const pcv_octree* o, const pcv_location* loc, const pcv_interval* filters, uint32_t nfilt,
+                     uint64_t batch_size, pcv_batch_cb cb, void* user);
+/* Throughput form: nloc locations in one call; survivors stay compacted in HBM.  counts_out[i] =
+ * survivors of location i, tested_out[i] = points decoded + tested for location i. */
+int pcv_query_batch_device(const pcv_octree* o, const pcv_location* locs, uint32_t nloc, const pcv_interval* filters,
+                           uint32_t nfilt, uint64_t* counts_out, uint64_t* tested_out);
+
+/* ---- a19: X-ray leaf tile (xray/src/generation.rs:108-127,159-198,464-513) ------------------ */
+/* query_from_global: 7 doubles or NULL.  rgba_out: w*h*4.  Returns any_points_out=0 for an empty tile
+ * (the reference returns None). zbits_out (optional): w*h*32 u32 z-bucket bitsets. */
+int pcv_xray_tile(const pcv_octree* o, const double tile_min[3], const double tile_max[3], uint32_t w, uint32_t h,
+                  const double* query_from_global, uint8_t* rgba_out, uint32_t* zbits_out, int* any_points_out);
+
+/* ---- multi-GPU helpers (points shard by level-k path prefix) ------------------ */
+/* Per-point level-k cell (first k steps of the re-quantising descent on the raw positions) ->
+ * 8^k histogram; then a stable pack of the points of each destination rank into contiguous send
+ * buffers.  The exchange itself is one NCCL all-to-all issued by the host layer. */
+int pcv_prefix_histogram_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
+                                const double bbox_max[3], uint32_t k, uint64_t* counts_out /* 8^k, host */);
+int pcv_prefix_pack_device(pcv_ctx* ctx, const pcv_points* dev_points, const uint64_t* dev_global_index, double resolution,
+                           const double bbox_min[3], const double bbox_max[3], uint32_t k,
+                           const int32_t* cell_to_rank /* 8^k, host */, uint32_t nranks, double* dev_xyz_out /* n*3 AoS */,
+                           uint8_t* dev_rgb_out, float* dev_intensity_out, uint64_t* dev_index_out,
+                           uint64_t* rank_counts_out /* nranks, host */);
+
+/* ---- synthetic inputs for benchmarks / parity tests (integer-only, counter based) ----------- */
+enum { PCV_SYNTH_SLAB_ECEF = 1, PCV_SYNTH_GAUSS_CLUSTERS = 2 };
+int pcv_synth_points_device(pcv_ctx* ctx, int kind, uint64_t seed, uint64_t first_index, uint64_t n, double* dev_x,
+                            double* dev_y, double* dev_z, uint8_t* dev_rgb);
+int pcv_synth_points_host(int kind, uint64_t seed, uint64_t first_index, uint64_t n, double* x, double* y, double* z, uint8_t* rgb);
+int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* resolution);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+typedef struct pcv_build_stats {
+    uint64_t kernel_launches; /* CUDA kernels launched by the last build on this context           */
+    uint32_t passes;
+    uint32_t deepest_level;
+    uint64_t num_nodes;
+    uint64_t algorithmic_bytes; /* 27*N + sum_nodes n*(3*bpc+3) (+8*N with intensity)             */
+    float ms_bbox, ms_partition, ms_place, ms_total; /* CUDA-event times on the context's stream   */
+    float ms_chain_kernels;                          /* hist + scatter kernels only                */
+} pcv_build_stats;
+int pcv_last_build_stats(pcv_ctx* ctx, pcv_build_stats* out);
+uint64_t pcv_kernel_launch_count(pcv_ctx* ctx); /* cumulative, all entry points                    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCV_H */

@@ -1,0 +1,518 @@
+// build_host.hpp — host orchestration of the GPU octree build (backend agnostic).
+//
+// Replaces src/octree/generation.rs:289-403 (build_octree) with a different algorithm that yields the
+// same tree, the same per-node point order and the same stored position codes:
+//
+//   split phase    the reference's recursive 8-way file split (generation.rs:58-193) becomes a
+//                  top-down, level-synchronous stable multi-way partition: each pass resolves G octree
+//                  levels for every point that still sits in a node with > MAX_POINTS_PER_NODE points
+//                  (`hist` -> per-tile digit histograms, `scan` -> per-digit prefix over tiles, host
+//                  decides leaf/split for the 8^1..8^G descendants, `scatter` -> stable partition
+//                  into the next pass's segments or into the leaf arena).  The per-point digits come
+//                  from the re-quantising descent in chain.h, so node membership is bit-identical.
+//   subsample      the level-by-level rewrite (generation.rs:195-253,335-387) is replaced by its closed
+//                  form: a point at rank j of a node X with parent P moves up iff j % 8 == 0, to rank
+//                  off(X in P) + j/8; otherwise it stays at slot j - j/8 - 1.  `place` walks each leaf
+//                  point up, re-encoding through every cube it passes (same DEC/ENC chain as the
+//                  reference's rewrites), and writes it to its final node-contiguous slot.
+//
+// The Backend interface is implemented by the CUDA kernels (kernels_build.cuh).  A second, test-only
+// implementation lives under tests/ to exercise this host logic without a GPU; the shipped library
+// contains only the CUDA one.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "chain.h"
+
+namespace pcv {
+
+typedef unsigned __int128 u128;
+
+struct PointsView {  // device pointers
+    const double* x;
+    const double* y;
+    const double* z;
+    uint64_t stride;
+    const uint8_t* rgb;
+    const float* intensity;
+    uint64_t n;
+};
+
+// ---- structures shared with the kernels ---------------------------------------------------------
+struct RecN {  // narrow partition record: codes of U8/U16/F32 levels
+    uint32_t c[3];
+    uint32_t idx;
+};
+struct RecW {  // wide record: used for the whole build when any level >= 1 is Float64 encoded
+    uint64_t c[3];
+    uint32_t idx;
+    uint32_t pad;
+};
+struct TileDesc {
+    uint64_t start;   // first record (or raw point) of the tile
+    uint32_t count;   // <= kTilePoints
+    uint32_t active;  // index into the pass's active-node array
+};
+struct ActiveDesc {
+    double m[3];
+    double e;
+    uint32_t chunk_begin, nchunks;
+    uint32_t pad0, pad1;
+};
+struct ChunkDesc {
+    uint32_t tile_begin, ntiles;
+    uint32_t active;
+    uint32_t first;  // 1 if first chunk of its node
+};
+struct BucketDesc {
+    uint64_t dest;    // first record of the bucket in its destination buffer
+    uint16_t b0, b1;  // digit range [b0,b1) it collects (contiguous: a whole sub-tree)
+    uint8_t keep;     // 1..G: which level's codes the destination stores
+    uint8_t kind;     // 0 = next pass segment, 1 = leaf arena
+    uint16_t pad;
+};
+struct DNode {
+    double m[3];
+    double e;
+    uint64_t off_in_parent;   // sum_{k'<k} ceil(n(P.k')/8)
+    uint64_t out_point_off;
+    uint64_t out_xyz_off;     // bytes
+    int32_t parent;           // -1 for the root
+    int32_t enc;
+};
+struct LeafTile {
+    uint64_t arena_start;
+    uint64_t j0;
+    uint32_t node;
+    uint32_t count;
+};
+
+constexpr uint32_t kTilePoints = 4096;   // partition tile (hist / scatter)
+constexpr uint32_t kChunkTiles = 256;    // tiles per scan chunk
+constexpr uint32_t kPlaceTile = 2048;    // place tile
+
+struct PassArgs {
+    int level, G, nbins;
+    bool root, wide;
+    PointsView pts;
+    const void* rec_in;
+    void* rec_next;
+    void* arena;
+    uint32_t ntiles, nactive, nchunks;
+    const TileDesc* d_tiles;
+    const ActiveDesc* d_active;
+    const ChunkDesc* d_chunks;
+    uint32_t* d_tile_counts;  // [ntiles][nbins]; after scan: exclusive prefix over the node's tiles
+    uint32_t* d_chunk_sums;   // [nchunks][nbins]
+    uint64_t* d_node_bins;    // [nactive][nbins]
+    const uint16_t* d_lut;    // [nactive][nbins] -> local bucket, 0xFFFF for empty digits
+    const BucketDesc* d_buckets;  // [nactive][nbins]
+    LevelTable lv;
+};
+
+struct PlaceArgs {
+    bool wide;
+    PointsView pts;
+    const void* arena;
+    const DNode* d_nodes;
+    const LeafTile* d_tiles;
+    uint32_t ntiles;
+    uint8_t* out_xyz;
+    uint8_t* out_rgb;
+    float* out_intensity;
+    uint32_t* out_src;
+};
+
+struct Backend {
+    virtual ~Backend() {}
+    virtual void* dmalloc(size_t bytes) = 0;
+    virtual void dfree(void* p) = 0;
+    virtual void h2d(void* d, const void* h, size_t bytes) = 0;
+    virtual void d2h(void* h, const void* d, size_t bytes) = 0;
+    virtual void hist(const PassArgs& a) = 0;
+    virtual void scan(const PassArgs& a) = 0;
+    virtual void scatter(const PassArgs& a) = 0;
+    virtual void place(const PlaceArgs& a) = 0;
+    virtual void mark(int what) {}  // timing hooks: 0 partition start, 1 partition end / place start, 2 place end
+};
+
+// ---- host-side node algebra (node.rs) -------------------------------------------------------------
+struct HNode {
+    u128 index;
+    int level;
+    int parent;
+    int child[8];
+    uint64_t count;  // points routed into the node by the split phase
+    bool leaf;
+    uint64_t arena_off;
+    uint64_t n_sub;  // size when the node is subsampled into its parent
+    uint64_t off_in_parent;
+    uint64_t final_count;
+    uint64_t out_point_off, out_xyz_off;
+    double m[3];
+    double e;
+    int enc;
+};
+
+inline uint32_t rust_as_u32(double v) {
+    if (!(v == v) || v <= 0.0) return 0u;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (uint32_t)v;
+}
+// PositionEncoding::new (codec.rs:31-40)
+inline int position_encoding_for(double edge, double resolution) {
+    uint32_t min_bits = rust_as_u32(std::log2(edge / resolution)) + 1u;
+    if (min_bits <= 8) return ENC_U8;
+    if (min_bits <= 16) return ENC_U16;
+    if (min_bits <= 24) return ENC_F32;
+    return ENC_F64;
+}
+
+inline LevelTable make_level_table(double root_edge, double resolution) {
+    LevelTable t;
+    double e = root_edge;
+    t.last_level = kMaxLevels - 1;
+    bool found = false;
+    for (int L = 0; L < kMaxLevels; ++L) {
+        t.edge[L] = e;
+        t.enc[L] = (int8_t)position_encoding_for(e, resolution);
+        // should_split_node (generation.rs:128-150): a node at level L >= 1 is split only if edge > resolution.
+        if (!found && L >= 1 && !(e > resolution)) {
+            t.last_level = L;
+            found = true;
+        }
+        e /= 2.;  // node.rs:161
+    }
+    return t;
+}
+
+struct BuildResult {
+    std::vector<HNode> nodes;     // creation order (parents before children)
+    std::vector<int> sorted;      // node indices sorted by NodeId
+    uint64_t n = 0;
+    uint64_t xyz_bytes = 0;
+    uint8_t* d_xyz = nullptr;
+    uint8_t* d_rgb = nullptr;
+    float* d_intensity = nullptr;
+    uint32_t* d_src = nullptr;
+    uint32_t passes = 0;
+    uint32_t deepest_level = 0;
+    uint64_t algorithmic_bytes = 0;
+    LevelTable lv;
+    double root_min[3];
+    double root_edge;
+};
+
+struct BuildError : std::runtime_error {
+    int code;
+    BuildError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+class BuildPlan {
+   public:
+    Backend& be;
+    uint64_t max_points;
+    int G;
+    BuildPlan(Backend& b, uint64_t max_points_per_node, int levels_per_pass)
+        : be(b), max_points(max_points_per_node ? max_points_per_node : 100000), G(levels_per_pass) {
+        if (G < 1 || G > 3) G = 3;
+    }
+
+    template <class T>
+    T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
+        if (v.empty()) return nullptr;
+        T* d = (T*)be.dmalloc(v.size() * sizeof(T));
+        owned.push_back(d);
+        be.h2d(d, v.data(), v.size() * sizeof(T));
+        return d;
+    }
+
+    BuildResult run(const PointsView& pts, double resolution, const double bmin[3], const double bmax[3]) {
+        if (!(resolution > 0.0)) throw BuildError(-1, "resolution must be > 0");
+        if (pts.n >= 0xFFFFFFFFull) throw BuildError(-6, "more than 2^32-2 points per context are not supported");
+        BuildResult R;
+        R.n = pts.n;
+        // Cube::bounding (aabb.rs:149-157)
+        double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
+        for (int a = 0; a < 3; ++a) R.root_min[a] = bmin[a];
+        R.root_edge = E;
+        R.lv = make_level_table(E, resolution);
+        const LevelTable& lv = R.lv;
+        if (pts.n == 0) return R;  // no leaves -> no nodes at all (generation.rs:325-397)
+
+        bool wide = false;
+        for (int L = 1; L <= lv.last_level; ++L) wide = wide || lv.enc[L] == ENC_F64;
+        const size_t rec_bytes = wide ? sizeof(RecW) : sizeof(RecN);
+
+        std::vector<HNode>& nodes = R.nodes;
+        {
+            HNode r{};
+            r.index = 0;
+            r.level = 0;
+            r.parent = -1;
+            for (int k = 0; k < 8; ++k) r.child[k] = -1;
+            r.count = pts.n;
+            r.leaf = false;
+            for (int a = 0; a < 3; ++a) r.m[a] = bmin[a];
+            r.e = E;
+            r.enc = lv.enc[0];
+            nodes.push_back(r);
+        }
+
+        struct Active {
+            int node;
+            uint64_t start, count;
+        };
+        std::vector<Active> active{{0, 0, pts.n}};
+        int L = 0;
+        void* bufs[2] = {nullptr, nullptr};
+        void* arena = be.dmalloc((size_t)pts.n * rec_bytes);
+        uint64_t arena_used = 0;
+        int cur = -1;  // -1: raw input
+        std::vector<void*> scratch;
+        auto free_scratch = [&]() {
+            for (void* p : scratch) be.dfree(p);
+            scratch.clear();
+        };
+        be.mark(0);
+        try {
+            while (!active.empty()) {
+                const int Gp = std::min(G, lv.last_level - L);
+                if (Gp < 1) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
+                const int nbins = 1 << (3 * Gp);
+                // ---- tiles / chunks ----
+                std::vector<TileDesc> tiles;
+                std::vector<ChunkDesc> chunks;
+                std::vector<ActiveDesc> adesc(active.size());
+                uint64_t active_points = 0;
+                for (size_t a = 0; a < active.size(); ++a) {
+                    const HNode& nd = nodes[active[a].node];
+                    for (int k = 0; k < 3; ++k) adesc[a].m[k] = nd.m[k];
+                    adesc[a].e = nd.e;
+                    uint64_t c = active[a].count, s = active[a].start;
+                    active_points += c;
+                    uint32_t t0 = (uint32_t)tiles.size();
+                    for (uint64_t o = 0; o < c; o += kTilePoints)
+                        tiles.push_back(TileDesc{s + o, (uint32_t)std::min<uint64_t>(kTilePoints, c - o), (uint32_t)a});
+                    uint32_t nt = (uint32_t)tiles.size() - t0;
+                    adesc[a].chunk_begin = (uint32_t)chunks.size();
+                    adesc[a].nchunks = (nt + kChunkTiles - 1) / kChunkTiles;
+                    for (uint32_t o = 0; o < nt; o += kChunkTiles)
+                        chunks.push_back(ChunkDesc{t0 + o, std::min(kChunkTiles, nt - o), (uint32_t)a, o == 0 ? 1u : 0u});
+                }
+                PassArgs pa{};
+                pa.level = L;
+                pa.G = Gp;
+                pa.nbins = nbins;
+                pa.root = cur < 0;
+                pa.wide = wide;
+                pa.pts = pts;
+                pa.rec_in = cur < 0 ? nullptr : bufs[cur];
+                int nxt = cur < 0 ? 0 : 1 - cur;
+                if (!bufs[nxt]) bufs[nxt] = be.dmalloc((size_t)pts.n * rec_bytes);
+                pa.rec_next = bufs[nxt];
+                pa.arena = arena;
+                pa.ntiles = (uint32_t)tiles.size();
+                pa.nactive = (uint32_t)active.size();
+                pa.nchunks = (uint32_t)chunks.size();
+                pa.d_tiles = upload(tiles, scratch);
+                pa.d_active = upload(adesc, scratch);
+                pa.d_chunks = upload(chunks, scratch);
+                pa.d_tile_counts = (uint32_t*)be.dmalloc((size_t)pa.ntiles * nbins * 4);
+                scratch.push_back(pa.d_tile_counts);
+                pa.d_chunk_sums = (uint32_t*)be.dmalloc((size_t)pa.nchunks * nbins * 4);
+                scratch.push_back(pa.d_chunk_sums);
+                pa.d_node_bins = (uint64_t*)be.dmalloc((size_t)pa.nactive * nbins * 8);
+                scratch.push_back(pa.d_node_bins);
+                pa.lv = lv;
+
+                be.hist(pa);
+                be.scan(pa);
+                std::vector<uint64_t> bins((size_t)pa.nactive * nbins);
+                be.d2h(bins.data(), pa.d_node_bins, bins.size() * 8);
+
+                // ---- decide leaf / split for every descendant within Gp levels ----
+                std::vector<uint16_t> lut((size_t)pa.nactive * nbins, 0xFFFF);
+                std::vector<BucketDesc> buckets((size_t)pa.nactive * nbins);
+                std::vector<Active> next_active;
+                uint64_t next_used = 0;
+                for (size_t a = 0; a < active.size(); ++a) {
+                    const uint64_t* nb = &bins[a * nbins];
+                    uint16_t nlocal = 0;
+                    uint64_t total = 0;
+                    for (int b = 0; b < nbins; ++b) total += nb[b];
+                    if (total != active[a].count) throw BuildError(-2, "internal: histogram total mismatch");
+                    // iterative expansion with an explicit stack: (node, sublevel j, b0, width)
+                    struct Fr {
+                        int node, j, b0, w;
+                    };
+                    std::vector<Fr> st{{active[a].node, 0, 0, nbins}};
+                    // children must be visited in digit order so that destinations are laid out in
+                    // node order; use recursion order via reversed pushes.
+                    while (!st.empty()) {
+                        Fr f = st.back();
+                        st.pop_back();
+                        int w = f.w / 8;
+                        std::vector<Fr> pend;
+                        for (int k = 0; k < 8; ++k) {
+                            int b0 = f.b0 + k * w;
+                            uint64_t cnt = 0;
+                            for (int b = b0; b < b0 + w; ++b) cnt += nb[b];
+                            if (cnt == 0) continue;
+                            HNode c{};
+                            const HNode& p = nodes[f.node];
+                            c.level = p.level + 1;
+                            c.index = (p.index << 3) + (u128)k;  // node.rs:120-125
+                            c.parent = f.node;
+                            for (int q = 0; q < 8; ++q) c.child[q] = -1;
+                            c.count = cnt;
+                            c.e = lv.edge[c.level];
+                            // node.rs:165-170: x = bit2, y = bit1, z = bit0
+                            c.m[0] = (k & 4) ? p.m[0] + c.e : p.m[0];
+                            c.m[1] = (k & 2) ? p.m[1] + c.e : p.m[1];
+                            c.m[2] = (k & 1) ? p.m[2] + c.e : p.m[2];
+                            c.enc = lv.enc[c.level];
+                            bool split = cnt > max_points && c.e > resolution;  // generation.rs:128-150
+                            if (split && c.level >= kMaxLevels - 1)
+                                throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
+                            c.leaf = !split;
+                            int ci = (int)nodes.size();
+                            nodes.push_back(c);
+                            nodes[f.node].child[k] = ci;
+                            int j = f.j + 1;
+                            if (split && j < Gp) {
+                                pend.push_back(Fr{ci, j, b0, w});
+                                continue;
+                            }
+                            BucketDesc bd{};
+                            bd.b0 = (uint16_t)b0;
+                            bd.b1 = (uint16_t)(b0 + w);
+                            bd.keep = (uint8_t)j;
+                            if (split) {
+                                bd.kind = 0;
+                                bd.dest = next_used;
+                                next_active.push_back(Active{ci, next_used, cnt});
+                                next_used += cnt;
+                            } else {
+                                bd.kind = 1;
+                                bd.dest = arena_used;
+                                nodes[ci].arena_off = arena_used;
+                                arena_used += cnt;
+                                R.deepest_level = std::max<uint32_t>(R.deepest_level, (uint32_t)c.level);
+                            }
+                            for (int b = b0; b < b0 + w; ++b) lut[a * nbins + b] = nlocal;
+                            buckets[a * nbins + nlocal] = bd;
+                            ++nlocal;
+                        }
+                        for (size_t i = pend.size(); i-- > 0;) st.push_back(pend[i]);
+                    }
+                }
+                pa.d_lut = upload(lut, scratch);
+                pa.d_buckets = upload(buckets, scratch);
+                be.scatter(pa);
+                free_scratch();
+                R.passes++;
+                active.swap(next_active);
+                cur = nxt;
+                L += Gp;
+            }
+        } catch (...) {
+            free_scratch();
+            be.dfree(arena);
+            for (void* b : bufs)
+                if (b) be.dfree(b);
+            throw;
+        }
+        for (void* b : bufs)
+            if (b) be.dfree(b);
+        be.mark(1);
+
+        // ---- subsample plan: closed form of generation.rs:195-253,335-387 ----
+        for (size_t i = nodes.size(); i-- > 0;) {
+            HNode& x = nodes[i];
+            if (x.leaf) {
+                x.n_sub = x.count;
+            } else {
+                uint64_t off = 0;
+                for (int k = 0; k < 8; ++k) {
+                    if (x.child[k] < 0) continue;
+                    HNode& c = nodes[x.child[k]];
+                    c.off_in_parent = off;
+                    off += (c.n_sub + 7) / 8;  // every 8th point by current index: ceil(n/8)
+                }
+                x.n_sub = off;
+            }
+        }
+        for (auto& x : nodes) x.final_count = x.parent < 0 ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
+
+        // ---- output layout: nodes sorted by NodeId (level << 120 | index) ----
+        R.sorted.resize(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) R.sorted[i] = (int)i;
+        std::sort(R.sorted.begin(), R.sorted.end(), [&](int a, int b) {
+            if (nodes[a].level != nodes[b].level) return nodes[a].level < nodes[b].level;
+            return nodes[a].index < nodes[b].index;
+        });
+        uint64_t poff = 0, boff = 0, algo_xyz = 0;
+        for (int i : R.sorted) {
+            HNode& x = nodes[i];
+            x.out_point_off = poff;
+            boff = (boff + 15) & ~15ull;  // node .xyz blocks are 16-byte aligned inside the device array
+            x.out_xyz_off = boff;
+            poff += x.final_count;
+            boff += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
+            algo_xyz += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
+        }
+        if (poff != pts.n) {
+            be.dfree(arena);
+            throw BuildError(-2, "internal: subsample plan does not conserve points");
+        }
+        R.xyz_bytes = boff;
+        R.algorithmic_bytes = 27ull * pts.n + algo_xyz + 3ull * pts.n + (pts.intensity ? 8ull * pts.n : 0ull);
+
+        // ---- place ----
+        std::vector<DNode> dn(nodes.size());
+        std::vector<LeafTile> lt;
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const HNode& x = nodes[i];
+            DNode& d = dn[i];
+            for (int a = 0; a < 3; ++a) d.m[a] = x.m[a];
+            d.e = x.e;
+            d.off_in_parent = x.off_in_parent;
+            d.out_point_off = x.out_point_off;
+            d.out_xyz_off = x.out_xyz_off;
+            d.parent = x.parent;
+            d.enc = x.enc;
+            if (x.leaf)
+                for (uint64_t o = 0; o < x.count; o += kPlaceTile)
+                    lt.push_back(LeafTile{x.arena_off + o, o, (uint32_t)i, (uint32_t)std::min<uint64_t>(kPlaceTile, x.count - o)});
+        }
+        R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
+        R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
+        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
+        R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
+        PlaceArgs pl{};
+        pl.wide = wide;
+        pl.pts = pts;
+        pl.arena = arena;
+        pl.d_nodes = upload(dn, scratch);
+        pl.d_tiles = upload(lt, scratch);
+        pl.ntiles = (uint32_t)lt.size();
+        pl.out_xyz = R.d_xyz;
+        pl.out_rgb = R.d_rgb;
+        pl.out_intensity = R.d_intensity;
+        pl.out_src = R.d_src;
+        be.place(pl);
+        be.mark(2);
+        free_scratch();
+        be.dfree(arena);
+        return R;
+    }
+};
+
+}  // namespace pcv

@@ -1,0 +1,137 @@
+// chain.h — the re-quantising descent ("chain") arithmetic, shared by the CUDA kernels and the host
+// orchestration.  Every operation is IEEE-754 binary64 in the reference's exact order; this header
+// must be compiled with FMA contraction OFF (nvcc -fmad=false, g++ -ffp-contract=off): the only fused
+// operations are the two explicit fma() calls that restate `mul_add` in the reference's decode.
+//
+// Reference semantics (file:line relative to the reference checkout):
+//   child index      src/octree/node.rs:34-42      strict `>` against Cube::center (aabb.rs:184-192)
+//   child cube       src/octree/node.rs:157-172    e /= 2; min += bit * e
+//   encode           src/read_write/codec.rs:102-121,142-148  clamp((v-min)/edge,0,1) * MAX -> `as` cast
+//   decode           src/read_write/codec.rs:124-139  (v / MAX).mul_add(edge, min)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PCV_HD __host__ __device__ __forceinline__
+#else
+#define PCV_HD inline
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace pcv {
+
+enum : int { ENC_U8 = 1, ENC_U16 = 2, ENC_F32 = 3, ENC_F64 = 4 };
+constexpr int kMaxLevels = 41;  // NodeId holds a 120-bit octal path: levels 0..40 (node.rs:152-154)
+
+PCV_HD int enc_bytes(int enc) { return enc == ENC_U8 ? 1 : enc == ENC_U16 ? 2 : enc == ENC_F32 ? 4 : 8; }
+
+PCV_HD double bits_to_f64(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+PCV_HD uint64_t f64_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+PCV_HD float bits_to_f32(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+PCV_HD uint32_t f32_to_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return b;
+#endif
+}
+
+// num::clamp (num 0.3.0): NaN passes through.
+PCV_HD double clamp01(double x) {
+    if (x < 0.0) return 0.0;
+    if (x > 1.0) return 1.0;
+    return x;
+}
+
+// Rust `f64 as u32` for s in [0, 65535] or NaN: truncate toward zero, NaN -> 0.
+PCV_HD uint32_t trunc_u32(double s) {
+#if defined(__CUDA_ARCH__)
+    return __double2uint_rz(s);  // cvt.rzi.u32.f64: saturating, NaN -> 0 (same as Rust `as`)
+#else
+    if (!(s == s)) return 0u;
+    if (s <= 0.0) return 0u;
+    if (s >= 4294967295.0) return 4294967295u;
+    return (uint32_t)s;
+#endif
+}
+
+// One coordinate -> code bits (u8/u16 value, f32 bits or f64 bits, in a u64).
+PCV_HD uint64_t encode1(double value, double mn, double edge, int enc) {
+    double t = clamp01((value - mn) / edge);
+    if (enc == ENC_U8) return (uint64_t)trunc_u32(255.0 * t);
+    if (enc == ENC_U16) return (uint64_t)trunc_u32(65535.0 * t);
+    if (enc == ENC_F32) return (uint64_t)f32_to_bits((float)t);
+    return f64_to_bits(t);
+}
+
+PCV_HD double decode1(uint64_t bits, double mn, double edge, int enc) {
+    if (enc == ENC_U8) return fma((double)(uint32_t)bits / 255.0, edge, mn);
+    if (enc == ENC_U16) return fma((double)(uint32_t)bits / 65535.0, edge, mn);
+    if (enc == ENC_F32) return fma((double)bits_to_f32((uint32_t)bits), edge, mn);
+    return fma(bits_to_f64(bits), edge, mn);
+}
+
+// Per-level constants, computed once on the host exactly like the reference does per node:
+// edge[L] by repeated `/= 2` from the root edge (node.rs:161), enc[L] = PositionEncoding::new
+// (codec.rs:31-40, log2 evaluated on the host only).
+struct LevelTable {
+    double edge[kMaxLevels];
+    int8_t enc[kMaxLevels];
+    int32_t last_level;  // deepest level a node can have (nodes there are never split)
+};
+
+// One descent step: point at decoded position q inside the cube (m, e_cur) of a node at level L.
+// Computes the child digit, advances m to the child's min, encodes q into the child cube and
+// replaces q by the decoded value — i.e. exactly what the child's node file would hand to the next
+// split (generation.rs:78-101 then raw.rs:127-216).
+struct Step {
+    uint64_t code[3];
+    unsigned digit;
+};
+PCV_HD Step descend(double q[3], double m[3], double e_cur, double e_half, int enc_child) {
+    Step s;
+    unsigned d = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a) {
+        double c = (m[a] + (m[a] + e_cur)) / 2.0;  // Cube::center
+        unsigned bit = q[a] > c ? 1u : 0u;
+        d = (d << 1) | bit;
+        if (bit) m[a] = m[a] + e_half;  // min += 1.0 * edge (bit 0 adds 0.0: unchanged)
+        uint64_t code = encode1(q[a], m[a], e_half, enc_child);
+        s.code[a] = code;
+        q[a] = decode1(code, m[a], e_half, enc_child);
+    }
+    s.digit = d;  // (x>cx)<<2 | (y>cy)<<1 | (z>cz)
+    return s;
+}
+
+}  // namespace pcv

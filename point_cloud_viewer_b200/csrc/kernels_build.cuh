@@ -1,0 +1,552 @@
+// kernels_build.cuh — sm_100a kernels of the octree build and the CUDA Backend that drives them.
+//
+//   k_bbox      a1  find_bounding_box (generation.rs:256-270): streaming min/max, warp-shuffle reduce
+//   k_hist      a3-a6  per tile: decode -> G descent steps (chain.h) -> digit histogram in shared memory
+//   k_scan_*    per-digit exclusive prefix over the tiles of each active node (+ node totals)
+//   k_scatter   a4  stable multi-way partition of a tile (warp match ranking), re-running the descent
+//   k_place     a7  closed-form LOD subsampling + up-chain re-encode + final node-contiguous store
+//
+// All of them stream SoA/record arrays once with coalesced accesses; none has a dense contraction,
+// so there is no tensor-core path here.  The descent is FP64 (IEEE divide + FMA) by definition of
+// the reference's codec, compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "build_host.hpp"
+
+namespace pcv {
+
+#define PCV_CUDA_CHECK(x)                                                                            \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) throw BuildError(-2, std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// bbox
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// partial[block][6] = min xyz, max xyz.  Grid-stride, 4 independent loads in flight per coordinate.
+__global__ void __launch_bounds__(256) k_bbox(PointsView p, double* __restrict__ partial) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t s = p.stride;
+    for (; i + 3 * step < p.n; i += 4 * step) {
+        double vx[4], vy[4], vz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            vx[u] = __ldg(p.x + (i + u * step) * s);
+            vy[u] = __ldg(p.y + (i + u * step) * s);
+            vz[u] = __ldg(p.z + (i + u * step) * s);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            mn[0] = fmin(mn[0], vx[u]);
+            mx[0] = fmax(mx[0], vx[u]);
+            mn[1] = fmin(mn[1], vy[u]);
+            mx[1] = fmax(mx[1], vy[u]);
+            mn[2] = fmin(mn[2], vz[u]);
+            mx[2] = fmax(mx[2], vz[u]);
+        }
+    }
+    for (; i < p.n; i += step) {
+        double x = __ldg(p.x + i * s), y = __ldg(p.y + i * s), z = __ldg(p.z + i * s);
+        mn[0] = fmin(mn[0], x);
+        mx[0] = fmax(mx[0], x);
+        mn[1] = fmin(mn[1], y);
+        mx[1] = fmax(mx[1], y);
+        mn[2] = fmin(mn[2], z);
+        mx[2] = fmax(mx[2], z);
+    }
+    __shared__ double sh[8][6];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double lo = warp_min(mn[a]), hi = warp_max(mx[a]);
+        if (l == 0) {
+            sh[w][a] = lo;
+            sh[w][3 + a] = hi;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sh[0][threadIdx.x];
+        for (int k = 1; k < 8; ++k) v = threadIdx.x < 3 ? fmin(v, sh[k][threadIdx.x]) : fmax(v, sh[k][threadIdx.x]);
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// record load / store helpers
+// ------------------------------------------------------------------------------------------------
+template <bool WIDE>
+struct RecT;
+template <>
+struct RecT<false> {
+    typedef RecN type;
+};
+template <>
+struct RecT<true> {
+    typedef RecW type;
+};
+
+template <bool WIDE>
+__device__ __forceinline__ void load_rec(const void* base, uint64_t i, uint64_t c[3], uint32_t& idx) {
+    if (WIDE) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(base) + 2 * i;  // 32-byte record
+        const ulonglong2 v0 = __ldg(p), v1 = __ldg(p + 1);
+        c[0] = v0.x;
+        c[1] = v0.y;
+        c[2] = v1.x;
+        idx = (uint32_t)v1.y;
+    } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base) + i);  // 16-byte record
+        c[0] = v.x;
+        c[1] = v.y;
+        c[2] = v.z;
+        idx = v.w;
+    }
+}
+template <bool WIDE>
+__device__ __forceinline__ void store_rec(void* base, uint64_t i, const uint64_t c[3], uint32_t idx) {
+    if (WIDE) {
+        ulonglong2 v0, v1;
+        v0.x = c[0];
+        v0.y = c[1];
+        v1.x = c[2];
+        v1.y = idx;
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(base) + 2 * i;
+        p[0] = v0;
+        p[1] = v1;
+    } else {
+        uint4 v;
+        v.x = (uint32_t)c[0];
+        v.y = (uint32_t)c[1];
+        v.z = (uint32_t)c[2];
+        v.w = idx;
+        reinterpret_cast<uint4*>(base)[i] = v;
+    }
+}
+
+// Position of item `i` of a tile as the node's file would hand it to split(): raw for the root,
+// decoded from the node's own encoding otherwise (raw.rs:127-216).
+template <bool ROOT, bool WIDE>
+__device__ __forceinline__ void load_position(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i,
+                                              double q[3], uint32_t& idx) {
+    const uint64_t g = t.start + i;
+    if (ROOT) {
+        q[0] = __ldg(a.pts.x + g * a.pts.stride);
+        q[1] = __ldg(a.pts.y + g * a.pts.stride);
+        q[2] = __ldg(a.pts.z + g * a.pts.stride);
+        idx = (uint32_t)g;
+    } else {
+        uint64_t c[3];
+        load_rec<WIDE>(a.rec_in, g, c, idx);
+        const int enc = a.lv.enc[a.level];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, enc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hist
+// ------------------------------------------------------------------------------------------------
+template <bool ROOT, bool WIDE>
+__global__ void __launch_bounds__(256) k_hist(const __grid_constant__ PassArgs a) {
+    extern __shared__ uint32_t sh_hist[];
+    const TileDesc t = a.d_tiles[blockIdx.x];
+    const ActiveDesc act = a.d_active[t.active];
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) sh_hist[b] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
+        double q[3], m[3] = {act.m[0], act.m[1], act.m[2]};
+        uint32_t idx;
+        load_position<ROOT, WIDE>(a, t, act, i, q, idx);
+        double e = act.e;
+        unsigned bin = 0;
+        for (int j = 1; j <= a.G; ++j) {
+            const double eh = a.lv.edge[a.level + j];
+            Step s = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+            bin = (bin << 3) | s.digit;
+            e = eh;
+        }
+        atomicAdd(&sh_hist[bin], 1u);
+    }
+    __syncthreads();
+    uint32_t* out = a.d_tile_counts + (size_t)blockIdx.x * a.nbins;
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) out[b] = sh_hist[b];
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan: per digit, exclusive prefix over the tiles of each active node
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scan_chunk_sums(const __grid_constant__ PassArgs a) {
+    const ChunkDesc c = a.d_chunks[blockIdx.x];
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+        uint32_t s = 0;
+        const uint32_t* p = a.d_tile_counts + (size_t)c.tile_begin * a.nbins + b;
+        for (uint32_t t = 0; t < c.ntiles; ++t) s += p[(size_t)t * a.nbins];
+        a.d_chunk_sums[(size_t)blockIdx.x * a.nbins + b] = s;
+    }
+}
+__global__ void k_scan_nodes(const __grid_constant__ PassArgs a) {
+    const ActiveDesc act = a.d_active[blockIdx.x];
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+        uint64_t run = 0;
+        uint32_t* p = a.d_chunk_sums + (size_t)act.chunk_begin * a.nbins + b;
+        for (uint32_t c = 0; c < act.nchunks; ++c) {
+            uint32_t v = p[(size_t)c * a.nbins];
+            p[(size_t)c * a.nbins] = (uint32_t)run;
+            run += v;
+        }
+        a.d_node_bins[(size_t)blockIdx.x * a.nbins + b] = run;
+    }
+}
+__global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
+    const ChunkDesc c = a.d_chunks[blockIdx.x];
+    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+        uint32_t run = a.d_chunk_sums[(size_t)blockIdx.x * a.nbins + b];
+        uint32_t* p = a.d_tile_counts + (size_t)c.tile_begin * a.nbins + b;
+        for (uint32_t t = 0; t < c.ntiles; ++t) {
+            uint32_t v = p[(size_t)t * a.nbins];
+            p[(size_t)t * a.nbins] = run;
+            run += v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scatter
+// ------------------------------------------------------------------------------------------------
+constexpr int kScatterThreads = 256;
+constexpr int kScatterWarps = kScatterThreads / 32;
+constexpr int kScatterItems = 4;                                   // items per thread per round
+constexpr int kRoundPoints = kScatterThreads * kScatterItems;      // 1024
+static_assert(kTilePoints % kRoundPoints == 0, "tile must be a whole number of rounds");
+
+template <bool ROOT, bool WIDE>
+__global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_constant__ PassArgs a) {
+    // shared: base[nbins] u32 | wc[8][nbins] u32 | lut[nbins] u16 | meta[nbins] u16
+    extern __shared__ uint32_t sh[];
+    const int nb = a.nbins;
+    uint32_t* base = sh;
+    uint32_t* wc = sh + nb;
+    uint16_t* lut = reinterpret_cast<uint16_t*>(wc + kScatterWarps * nb);
+    uint16_t* meta = lut + nb;
+
+    const TileDesc t = a.d_tiles[blockIdx.x];
+    const ActiveDesc act = a.d_active[t.active];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // (1) exclusive prefix of this node's earlier tiles, per digit -> inclusive scan over digits
+    const uint32_t* pfx = a.d_tile_counts + (size_t)blockIdx.x * nb;
+    for (int b = tid; b < nb; b += kScatterThreads) {
+        wc[b] = pfx[b];
+        lut[b] = a.d_lut[(size_t)t.active * nb + b];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int per = (nb + 31) / 32;
+        const int b0 = lane * per, b1 = min(nb, b0 + per);
+        uint32_t s = 0;
+        for (int b = b0; b < b1; ++b) s += wc[b];
+        uint32_t incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        uint32_t run = incl - s;
+        for (int b = b0; b < b1; ++b) {
+            run += wc[b];
+            wc[b] = run;  // inclusive over digits
+        }
+    }
+    __syncthreads();
+    // (2) per local bucket: destination of this tile's first record
+    for (int lb = tid; lb < nb; lb += kScatterThreads) {
+        const BucketDesc bd = a.d_buckets[(size_t)t.active * nb + lb];
+        uint32_t v = 0;
+        uint16_t mt = 0;
+        if (bd.b1 != 0) {
+            const uint32_t hi = wc[bd.b1 - 1], lo = bd.b0 ? wc[bd.b0 - 1] : 0u;
+            v = (uint32_t)bd.dest + (hi - lo);
+            mt = (uint16_t)(bd.keep | (bd.kind << 8));
+        }
+        base[lb] = v;
+        meta[lb] = mt;
+    }
+    __syncthreads();
+
+    const int enc_in = a.lv.enc[a.level];
+    (void)enc_in;
+    for (uint32_t r0 = 0; r0 < t.count; r0 += kRoundPoints) {
+        for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) wc[i] = 0;
+        __syncthreads();
+
+        uint64_t code[kScatterItems][3];
+        uint32_t idxs[kScatterItems];
+        uint32_t lbs[kScatterItems];
+        uint32_t rank[kScatterItems];
+        // phase 1: descent for this thread's items
+#pragma unroll
+        for (int s = 0; s < kScatterItems; ++s) {
+            const uint32_t i = r0 + warp * (32 * kScatterItems) + s * 32 + lane;
+            lbs[s] = 0xFFFFu;
+            if (i < t.count) {
+                double q[3], m[3] = {act.m[0], act.m[1], act.m[2]};
+                load_position<ROOT, WIDE>(a, t, act, i, q, idxs[s]);
+                double e = act.e;
+                unsigned bin = 0;
+                uint64_t cj[3][3];
+#pragma unroll
+                for (int j = 1; j <= 3; ++j) {
+                    if (j <= a.G) {
+                        const double eh = a.lv.edge[a.level + j];
+                        Step st = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+                        bin = (bin << 3) | st.digit;
+                        e = eh;
+                        cj[j - 1][0] = st.code[0];
+                        cj[j - 1][1] = st.code[1];
+                        cj[j - 1][2] = st.code[2];
+                    }
+                }
+                const uint32_t lb = lut[bin];
+                lbs[s] = lb;
+                const int keep = meta[lb] & 0xFF;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) code[s][k] = keep == 1 ? cj[0][k] : (keep == 2 ? cj[1][k] : cj[2][k]);
+            }
+        }
+        // phase 2: stable rank inside the warp, sub-round by sub-round
+#pragma unroll
+        for (int s = 0; s < kScatterItems; ++s) {
+            const uint32_t lb = lbs[s];
+            const unsigned mask = __match_any_sync(0xffffffffu, lb);
+            const int leader = __ffs(mask) - 1;
+            uint32_t old = 0;
+            if (lane == leader && lb != 0xFFFFu) {
+                old = wc[warp * nb + lb];
+                wc[warp * nb + lb] = old + __popc(mask);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[s] = old + __popc(mask & ((1u << lane) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+        // phase 3: exclusive scan over warps, advance the tile cursor
+        for (int lb = tid; lb < nb; lb += kScatterThreads) {
+            uint32_t run = base[lb];
+#pragma unroll
+            for (int w = 0; w < kScatterWarps; ++w) {
+                const uint32_t c = wc[w * nb + lb];
+                wc[w * nb + lb] = run;
+                run += c;
+            }
+            base[lb] = run;
+        }
+        __syncthreads();
+        // phase 4: write
+#pragma unroll
+        for (int s = 0; s < kScatterItems; ++s) {
+            const uint32_t lb = lbs[s];
+            if (lb != 0xFFFFu) {
+                const uint32_t dst = wc[warp * nb + lb] + rank[s];
+                void* buf = (meta[lb] >> 8) ? a.arena : a.rec_next;
+                store_rec<WIDE>(buf, dst, code[s], idxs[s]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// place
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_code(uint8_t* p, uint64_t c, int enc) {
+    if (enc == ENC_U8)
+        *p = (uint8_t)c;
+    else if (enc == ENC_U16)
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)c;
+    else if (enc == ENC_F32)
+        *reinterpret_cast<uint32_t*>(p) = (uint32_t)c;
+    else
+        *reinterpret_cast<uint64_t*>(p) = c;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
+    const LeafTile lt = a.d_tiles[blockIdx.x];
+    const DNode leaf = a.d_nodes[lt.node];
+    for (uint32_t i = threadIdx.x; i < lt.count; i += blockDim.x) {
+        uint64_t c[3];
+        uint32_t idx;
+        load_rec<WIDE>(a.arena, lt.arena_start + i, c, idx);
+        uint64_t j = lt.j0 + i;
+        DNode nd = leaf;
+        // every 8th point (by current rank) moves into the parent: generation.rs:224-238
+        while (nd.parent >= 0 && (j & 7) == 0) {
+            const DNode P = a.d_nodes[nd.parent];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
+                c[k] = encode1(q, P.m[k], P.e, P.enc);
+            }
+            j = nd.off_in_parent + (j >> 3);
+            nd = P;
+        }
+        uint64_t slot = j;
+        if (nd.parent >= 0) {
+            // the points that stay are rewritten once into the same cube (child_writer, generation.rs:234-238)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
+                c[k] = encode1(q, nd.m[k], nd.e, nd.enc);
+            }
+            slot = j - (j >> 3) - 1;
+        }
+        const uint64_t dp = nd.out_point_off + slot;
+        const int bpc = enc_bytes(nd.enc);
+        uint8_t* px = a.out_xyz + nd.out_xyz_off + slot * 3 * (uint64_t)bpc;
+        store_code(px, c[0], nd.enc);
+        store_code(px + bpc, c[1], nd.enc);
+        store_code(px + 2 * bpc, c[2], nd.enc);
+        const uint8_t* rs = a.pts.rgb + 3ull * idx;
+        uint8_t* rd = a.out_rgb + 3ull * dp;
+        rd[0] = __ldg(rs);
+        rd[1] = __ldg(rs + 1);
+        rd[2] = __ldg(rs + 2);
+        a.out_src[dp] = idx;
+        if (a.out_intensity) a.out_intensity[dp] = __ldg(a.pts.intensity + idx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA backend
+// ------------------------------------------------------------------------------------------------
+struct CudaBackend : Backend {
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms_chain = 0.f;
+    bool time_chain = false;
+
+    explicit CudaBackend(cudaStream_t s) : stream(s) {
+        for (auto& e : ev) PCV_CUDA_CHECK(cudaEventCreate(&e));
+    }
+    ~CudaBackend() override {
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    void* dmalloc(size_t bytes) override {
+        void* p = nullptr;
+        PCV_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+        return p;
+    }
+    void dfree(void* p) override {
+        if (p) cudaFreeAsync(p, stream);
+    }
+    void h2d(void* d, const void* h, size_t bytes) override {
+        // staging copies come from pageable std::vector storage: the copy is complete (w.r.t. the host
+        // buffer) when the call returns.
+        PCV_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
+        PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    void d2h(void* h, const void* d, size_t bytes) override {
+        PCV_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
+        PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    void mark(int what) override { cudaEventRecord(ev[what], stream); }
+
+    static size_t scatter_smem(int nbins) { return (size_t)nbins * 4 * (1 + kScatterWarps) + (size_t)nbins * 2 * 2; }
+
+    void hist(const PassArgs& a) override {
+        const size_t sm = (size_t)a.nbins * 4;
+        if (a.root) {
+            if (a.wide)
+                k_hist<true, true><<<a.ntiles, 256, sm, stream>>>(a);
+            else
+                k_hist<true, false><<<a.ntiles, 256, sm, stream>>>(a);
+        } else {
+            if (a.wide)
+                k_hist<false, true><<<a.ntiles, 256, sm, stream>>>(a);
+            else
+                k_hist<false, false><<<a.ntiles, 256, sm, stream>>>(a);
+        }
+        ++launches;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    void scan(const PassArgs& a) override {
+        const int th = a.nbins < 32 ? 32 : (a.nbins > 512 ? 512 : a.nbins);
+        k_scan_chunk_sums<<<a.nchunks, th, 0, stream>>>(a);
+        k_scan_nodes<<<a.nactive, th, 0, stream>>>(a);
+        k_scan_tiles<<<a.nchunks, th, 0, stream>>>(a);
+        launches += 3;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    void scatter(const PassArgs& a) override {
+        const size_t sm = scatter_smem(a.nbins);
+        if (a.root) {
+            if (a.wide)
+                k_scatter<true, true><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+            else
+                k_scatter<true, false><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+        } else {
+            if (a.wide)
+                k_scatter<false, true><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+            else
+                k_scatter<false, false><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+        }
+        ++launches;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    void place(const PlaceArgs& a) override {
+        if (a.ntiles == 0) return;
+        if (a.wide)
+            k_place<true><<<a.ntiles, 256, 0, stream>>>(a);
+        else
+            k_place<false><<<a.ntiles, 256, 0, stream>>>(a);
+        ++launches;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void bbox(const PointsView& p, double mn[3], double mx[3]) {
+        if (p.n == 0) {  // generation.rs:269: unwrap_or_else(Aabb::zero)
+            for (int a = 0; a < 3; ++a) mn[a] = mx[a] = 0.0;
+            return;
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int blocks = (int)std::min<uint64_t>((uint64_t)sms * 8, (p.n + 255) / 256);
+        double* d = (double*)dmalloc((size_t)blocks * 6 * 8);
+        k_bbox<<<blocks, 256, 0, stream>>>(p, d);
+        ++launches;
+        PCV_CUDA_CHECK(cudaGetLastError());
+        std::vector<double> h((size_t)blocks * 6);
+        d2h(h.data(), d, h.size() * 8);
+        dfree(d);
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = h[a];
+            mx[a] = h[3 + a];
+        }
+        for (int b = 1; b < blocks; ++b)
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = std::fmin(mn[a], h[(size_t)b * 6 + a]);
+                mx[a] = std::fmax(mx[a], h[(size_t)b * 6 + 3 + a]);
+            }
+    }
+};
+
+}  // namespace pcv

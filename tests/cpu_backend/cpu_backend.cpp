@@ -1,0 +1,243 @@
+// TEST-ONLY backend for csrc/build_host.hpp: runs the host orchestration (pass planning, bucket
+// tables, closed-form subsample plan, output layout) with the kernels replaced by sequential loops
+// that follow the CUDA kernels' index arithmetic line by line.  It lets `-m "not gpu"` tests compare
+// the product's *algorithm* with the oracle on a machine without a GPU.  It is NOT part of the
+// shipped library (libpcv_b200.so contains only the CUDA backend and has no CPU fallback).
+#include <cstdlib>
+#include <map>
+
+#include "../../include/pcv.h"
+#include "../../point_cloud_viewer_b200/csrc/build_host.hpp"
+
+using namespace pcv;
+
+namespace {
+
+struct CpuBackend : Backend {
+    void* dmalloc(size_t b) override { return std::malloc(b ? b : 16); }
+    void dfree(void* p) override { std::free(p); }
+    void h2d(void* d, const void* h, size_t b) override { std::memcpy(d, h, b); }
+    void d2h(void* h, const void* d, size_t b) override { std::memcpy(h, d, b); }
+
+    static void load_rec(const void* base, uint64_t i, bool wide, uint64_t c[3], uint32_t& idx) {
+        if (wide) {
+            const RecW& r = ((const RecW*)base)[i];
+            c[0] = r.c[0], c[1] = r.c[1], c[2] = r.c[2], idx = r.idx;
+        } else {
+            const RecN& r = ((const RecN*)base)[i];
+            c[0] = r.c[0], c[1] = r.c[1], c[2] = r.c[2], idx = r.idx;
+        }
+    }
+    static void store_rec(void* base, uint64_t i, bool wide, const uint64_t c[3], uint32_t idx) {
+        if (wide) {
+            RecW& r = ((RecW*)base)[i];
+            r.c[0] = c[0], r.c[1] = c[1], r.c[2] = c[2], r.idx = idx, r.pad = 0;
+        } else {
+            RecN& r = ((RecN*)base)[i];
+            r.c[0] = (uint32_t)c[0], r.c[1] = (uint32_t)c[1], r.c[2] = (uint32_t)c[2], r.idx = idx;
+        }
+    }
+    static void load_position(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i, double q[3], uint32_t& idx) {
+        const uint64_t g = t.start + i;
+        if (a.root) {
+            q[0] = a.pts.x[g * a.pts.stride];
+            q[1] = a.pts.y[g * a.pts.stride];
+            q[2] = a.pts.z[g * a.pts.stride];
+            idx = (uint32_t)g;
+        } else {
+            uint64_t c[3];
+            load_rec(a.rec_in, g, a.wide, c, idx);
+            for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, a.lv.enc[a.level]);
+        }
+    }
+    static unsigned run_chain(const PassArgs& a, const ActiveDesc& act, double q[3], uint64_t cj[3][3]) {
+        double m[3] = {act.m[0], act.m[1], act.m[2]}, e = act.e;
+        unsigned bin = 0;
+        for (int j = 1; j <= a.G; ++j) {
+            const double eh = a.lv.edge[a.level + j];
+            Step s = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+            bin = (bin << 3) | s.digit;
+            e = eh;
+            for (int k = 0; k < 3; ++k) cj[j - 1][k] = s.code[k];
+        }
+        return bin;
+    }
+
+    void hist(const PassArgs& a) override {
+        for (uint32_t b = 0; b < a.ntiles; ++b) {
+            const TileDesc t = a.d_tiles[b];
+            const ActiveDesc act = a.d_active[t.active];
+            uint32_t* out = a.d_tile_counts + (size_t)b * a.nbins;
+            for (int k = 0; k < a.nbins; ++k) out[k] = 0;
+            for (uint32_t i = 0; i < t.count; ++i) {
+                double q[3];
+                uint32_t idx;
+                uint64_t cj[3][3];
+                load_position(a, t, act, i, q, idx);
+                out[run_chain(a, act, q, cj)]++;
+            }
+        }
+    }
+    void scan(const PassArgs& a) override {
+        for (uint32_t ch = 0; ch < a.nchunks; ++ch) {
+            const ChunkDesc c = a.d_chunks[ch];
+            for (int b = 0; b < a.nbins; ++b) {
+                uint32_t s = 0;
+                for (uint32_t t = 0; t < c.ntiles; ++t) s += a.d_tile_counts[(size_t)(c.tile_begin + t) * a.nbins + b];
+                a.d_chunk_sums[(size_t)ch * a.nbins + b] = s;
+            }
+        }
+        for (uint32_t n = 0; n < a.nactive; ++n) {
+            const ActiveDesc act = a.d_active[n];
+            for (int b = 0; b < a.nbins; ++b) {
+                uint64_t run = 0;
+                for (uint32_t c = 0; c < act.nchunks; ++c) {
+                    uint32_t& v = a.d_chunk_sums[(size_t)(act.chunk_begin + c) * a.nbins + b];
+                    uint32_t old = v;
+                    v = (uint32_t)run;
+                    run += old;
+                }
+                a.d_node_bins[(size_t)n * a.nbins + b] = run;
+            }
+        }
+        for (uint32_t ch = 0; ch < a.nchunks; ++ch) {
+            const ChunkDesc c = a.d_chunks[ch];
+            for (int b = 0; b < a.nbins; ++b) {
+                uint32_t run = a.d_chunk_sums[(size_t)ch * a.nbins + b];
+                for (uint32_t t = 0; t < c.ntiles; ++t) {
+                    uint32_t& v = a.d_tile_counts[(size_t)(c.tile_begin + t) * a.nbins + b];
+                    uint32_t old = v;
+                    v = run;
+                    run += old;
+                }
+            }
+        }
+    }
+    void scatter(const PassArgs& a) override {
+        const int nb = a.nbins;
+        std::vector<uint32_t> incl(nb), base(nb);
+        std::vector<uint16_t> meta(nb);
+        for (uint32_t blk = 0; blk < a.ntiles; ++blk) {
+            const TileDesc t = a.d_tiles[blk];
+            const ActiveDesc act = a.d_active[t.active];
+            const uint32_t* pfx = a.d_tile_counts + (size_t)blk * nb;
+            uint32_t run = 0;
+            for (int b = 0; b < nb; ++b) {
+                run += pfx[b];
+                incl[b] = run;
+            }
+            for (int lb = 0; lb < nb; ++lb) {
+                const BucketDesc bd = a.d_buckets[(size_t)t.active * nb + lb];
+                base[lb] = 0;
+                meta[lb] = 0;
+                if (bd.b1 != 0) {
+                    const uint32_t hi = incl[bd.b1 - 1], lo = bd.b0 ? incl[bd.b0 - 1] : 0u;
+                    base[lb] = (uint32_t)bd.dest + (hi - lo);
+                    meta[lb] = (uint16_t)(bd.keep | (bd.kind << 8));
+                }
+            }
+            for (uint32_t i = 0; i < t.count; ++i) {  // tile order == stable order
+                double q[3];
+                uint32_t idx;
+                uint64_t cj[3][3];
+                load_position(a, t, act, i, q, idx);
+                const unsigned bin = run_chain(a, act, q, cj);
+                const uint32_t lb = a.d_lut[(size_t)t.active * nb + bin];
+                const int keep = meta[lb] & 0xFF;
+                void* buf = (meta[lb] >> 8) ? a.arena : a.rec_next;
+                store_rec(buf, base[lb]++, a.wide, cj[keep - 1], idx);
+            }
+        }
+    }
+    void place(const PlaceArgs& a) override {
+        for (uint32_t b = 0; b < a.ntiles; ++b) {
+            const LeafTile lt = a.d_tiles[b];
+            const DNode leaf = a.d_nodes[lt.node];
+            for (uint32_t i = 0; i < lt.count; ++i) {
+                uint64_t c[3];
+                uint32_t idx;
+                load_rec(a.arena, lt.arena_start + i, a.wide, c, idx);
+                uint64_t j = lt.j0 + i;
+                DNode nd = leaf;
+                while (nd.parent >= 0 && (j & 7) == 0) {
+                    const DNode P = a.d_nodes[nd.parent];
+                    for (int k = 0; k < 3; ++k) c[k] = encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), P.m[k], P.e, P.enc);
+                    j = nd.off_in_parent + (j >> 3);
+                    nd = P;
+                }
+                uint64_t slot = j;
+                if (nd.parent >= 0) {
+                    for (int k = 0; k < 3; ++k) c[k] = encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), nd.m[k], nd.e, nd.enc);
+                    slot = j - (j >> 3) - 1;
+                }
+                const uint64_t dp = nd.out_point_off + slot;
+                const int bpc = enc_bytes(nd.enc);
+                uint8_t* px = a.out_xyz + nd.out_xyz_off + slot * 3 * (uint64_t)bpc;
+                for (int k = 0; k < 3; ++k) std::memcpy(px + k * bpc, &c[k], (size_t)bpc);  // little-endian host
+                std::memcpy(a.out_rgb + 3 * dp, a.pts.rgb + 3ull * idx, 3);
+                a.out_src[dp] = idx;
+                if (a.out_intensity) a.out_intensity[dp] = a.pts.intensity[idx];
+            }
+        }
+    }
+};
+
+struct TbTree {
+    BuildResult R;
+    std::vector<pcv_node_meta> nodes;
+};
+
+}  // namespace
+
+extern "C" {
+
+void* tb_build(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, const uint8_t* rgb, const float* intensity,
+               double resolution, const double* bmin, const double* bmax, uint64_t max_points, int levels_per_pass, char* err, int errcap) {
+    CpuBackend be;
+    PointsView v{x, y, z, stride, rgb, intensity, n};
+    try {
+        BuildPlan plan(be, max_points, levels_per_pass);
+        TbTree* t = new TbTree();
+        t->R = plan.run(v, resolution, bmin, bmax);
+        for (int i : t->R.sorted) {
+            const HNode& h = t->R.nodes[i];
+            pcv_node_meta m{};
+            u128 id = ((u128)h.level << 120) | h.index;
+            m.id_high = (uint64_t)(id >> 64);
+            m.id_low = (uint64_t)id;
+            m.num_points = (int64_t)h.final_count;
+            m.position_encoding = h.enc;
+            m.level = h.level;
+            for (int a = 0; a < 3; ++a) m.cube_min[a] = h.m[a];
+            m.cube_edge = h.e;
+            m.point_offset = h.out_point_off;
+            m.xyz_byte_offset = h.out_xyz_off;
+            t->nodes.push_back(m);
+        }
+        return t;
+    } catch (const std::exception& e) {
+        if (err) snprintf(err, (size_t)errcap, "%s", e.what());
+        return nullptr;
+    }
+}
+uint64_t tb_num_nodes(void* h) { return ((TbTree*)h)->nodes.size(); }
+void tb_nodes(void* h, pcv_node_meta* out) { std::memcpy(out, ((TbTree*)h)->nodes.data(), ((TbTree*)h)->nodes.size() * sizeof(pcv_node_meta)); }
+uint64_t tb_xyz_bytes(void* h) { return ((TbTree*)h)->R.xyz_bytes; }
+uint32_t tb_passes(void* h) { return ((TbTree*)h)->R.passes; }
+void tb_download(void* h, uint8_t* xyz, uint8_t* rgb, float* intensity, uint32_t* src) {
+    BuildResult& R = ((TbTree*)h)->R;
+    if (R.n == 0) return;
+    std::memcpy(xyz, R.d_xyz, R.xyz_bytes);
+    std::memcpy(rgb, R.d_rgb, R.n * 3);
+    if (intensity && R.d_intensity) std::memcpy(intensity, R.d_intensity, R.n * 4);
+    std::memcpy(src, R.d_src, R.n * 4);
+}
+void tb_free(void* h) {
+    TbTree* t = (TbTree*)h;
+    std::free(t->R.d_xyz);
+    std::free(t->R.d_rgb);
+    std::free(t->R.d_intensity);
+    std::free(t->R.d_src);
+    delete t;
+}
+}
