@@ -1,0 +1,287 @@
+"""point_cloud_viewer_b200 — B200-native octree builder + LOD / frustum point-query engine.
+
+The product is the CUDA shared library behind include/pcv.h (csrc/).  This package is the thin host
+layer used by tests and bench.py: it mirrors the names of the reference's interface for this path
+(build_octree, Octree.get_visible_nodes / get_node_data / nodes_in_location, PointQuery streaming)
+and never computes on the CPU — every call goes through the C ABI and fails loudly without a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import geometry
+from ._native import PcvError, Location  # noqa: F401
+
+ENC_BYTES = {1: 1, 2: 2, 3: 4, 4: 8}
+SYNTH_SLAB_ECEF, SYNTH_GAUSS_CLUSTERS = 1, 2
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def node_name(hi, lo):
+    """NodeId Display: 'r' + octal path (src/octree/node.rs:73-86)."""
+    v = (int(hi) << 64) | int(lo)
+    level = v >> 120
+    return "r" + "".join(str((v >> (3 * i)) & 7) for i in range(level - 1, -1, -1))
+
+
+def node_id_from_name(name):
+    level = len(name) - 1
+    idx = int(name[1:], 8) if level else 0
+    v = (level << 120) | idx
+    return v >> 64, v & 0xFFFFFFFFFFFFFFFF
+
+
+def device_count():
+    return N.lib().pcv_device_count()
+
+
+class Context:
+    """One per GPU (pcv_ctx)."""
+
+    def __init__(self, device=0, max_points_per_node=0, levels_per_pass=0):
+        cfg = N.Config(max_points_per_node, levels_per_pass, 0)
+        h = C.c_void_p()
+        N.check(N.lib().pcv_create(device, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            N.lib().pcv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- a1
+    def bbox(self, x, y, z, stride=1, n=None, device=False):
+        n = int(n if n is not None else (len(x) if stride == 1 else len(x) // 1))
+        pts = N.Points(_p(x), _p(y), _p(z), stride, None, None, n)
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        fn = N.lib().pcv_bbox_device if device else N.lib().pcv_bbox
+        N.check(fn(self.h, C.byref(pts), mn, mx))
+        return np.array(mn), np.array(mx)
+
+    # -- build_octree (generation.rs:289-295): returns an Octree resident in HBM
+    def build_octree(self, x, y, z, rgb, resolution, bbox_min, bbox_max, intensity=None, stride=1, n=None, device=False):
+        if n is None:
+            n = len(rgb) // 3 if getattr(rgb, "ndim", 1) == 1 else rgb.shape[0]
+        keep = (x, y, z, rgb, intensity)  # keep host arrays alive during the call
+        pts = N.Points(_p(x), _p(y), _p(z), stride, _p(rgb), _p(intensity), int(n))
+        out = C.c_void_p()
+        fn = N.lib().pcv_build_octree_device if device else N.lib().pcv_build_octree
+        N.check(fn(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), C.byref(out)))
+        del keep
+        return Octree(self, out)
+
+    def load_dir(self, directory):
+        out = C.c_void_p()
+        N.check(N.lib().pcv_octree_load_dir(self.h, str(directory).encode(), C.byref(out)))
+        return Octree(self, out)
+
+    def last_build_stats(self):
+        s = N.BuildStats()
+        N.check(N.lib().pcv_last_build_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in N.BuildStats._fields_}
+
+    def kernel_launch_count(self):
+        return int(N.lib().pcv_kernel_launch_count(self.h))
+
+    def synth_points_device(self, kind, seed, first, n, x_ptr, y_ptr, z_ptr, rgb_ptr):
+        N.check(N.lib().pcv_synth_points_device(self.h, kind, seed, first, n, x_ptr, y_ptr, z_ptr, rgb_ptr))
+
+    def prefix_histogram_device(self, x, y, z, n, resolution, bbox_min, bbox_max, k, stride=1):
+        pts = N.Points(_p(x), _p(y), _p(z), stride, None, None, int(n))
+        counts = np.zeros(8 ** k, np.uint64)
+        N.check(N.lib().pcv_prefix_histogram_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(counts)))
+        return counts
+
+    def prefix_pack_device(self, x, y, z, rgb, intensity, gidx, n, resolution, bbox_min, bbox_max, k, cell_to_rank, nranks, out_xyz, out_rgb,
+                           out_intensity, out_idx, stride=1):
+        pts = N.Points(_p(x), _p(y), _p(z), stride, _p(rgb), _p(intensity), int(n))
+        c2r = np.ascontiguousarray(cell_to_rank, np.int32)
+        counts = np.zeros(nranks, np.uint64)
+        N.check(N.lib().pcv_prefix_pack_device(self.h, C.byref(pts), _p(gidx), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(c2r), nranks,
+                                               _p(out_xyz), _p(out_rgb), _p(out_intensity), _p(out_idx), _p(counts)))
+        return counts
+
+
+def synth_points_host(kind, seed, first, n):
+    x, y, z = np.empty(n), np.empty(n), np.empty(n)
+    rgb = np.empty(n * 3, np.uint8)
+    N.check(N.lib().pcv_synth_points_host(kind, seed, first, n, _p(x), _p(y), _p(z), _p(rgb)))
+    return x, y, z, rgb
+
+
+def synth_bbox(kind):
+    mn, mx, res = (C.c_double * 3)(), (C.c_double * 3)(), C.c_double()
+    N.check(N.lib().pcv_synth_bbox(kind, mn, mx, C.byref(res)))
+    return np.array(mn), np.array(mx), res.value
+
+
+class Octree:
+    """Mirror of point_viewer::octree::Octree (src/octree/mod.rs:141-358) over a pcv_octree."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+        nn, npts, xb, res = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
+        mn, mx, hi = (C.c_double * 3)(), (C.c_double * 3)(), C.c_int()
+        N.check(N.lib().pcv_octree_info(self.h, C.byref(nn), C.byref(npts), C.byref(xb), C.byref(res), mn, mx, C.byref(hi)))
+        self.num_points, self.xyz_bytes, self.resolution = npts.value, xb.value, res.value
+        self.bbox_min, self.bbox_max, self.has_intensity = np.array(mn), np.array(mx), bool(hi.value)
+        arr = (N.NodeMeta * max(nn.value, 1))()
+        N.check(N.lib().pcv_octree_nodes(self.h, arr, nn.value))
+        self.node_array = arr
+        self.order = []
+        self.nodes = {}
+        for i in range(nn.value):
+            m = arr[i]
+            name = node_name(m.id_high, m.id_low)
+            self.order.append(name)
+            self.nodes[name] = dict(
+                num_points=m.num_points,
+                enc=m.position_encoding,
+                level=m.level,
+                cube=(m.cube_min[0], m.cube_min[1], m.cube_min[2], m.cube_edge),
+                hi=m.id_high,
+                lo=m.id_low,
+                point_offset=m.point_offset,
+                xyz_byte_offset=m.xyz_byte_offset,
+            )
+
+    def free(self):
+        if self.h:
+            N.lib().pcv_octree_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # Octree::get_node_data (octree/mod.rs:285-307) (+ provenance)
+    def node_data(self, name):
+        m = self.nodes[name]
+        n, bpc = m["num_points"], ENC_BYTES[m["enc"]]
+        xyz, rgb = np.zeros(n * 3 * bpc, np.uint8), np.zeros(n * 3, np.uint8)
+        inten = np.zeros(n, np.float32) if self.has_intensity else None
+        src = np.zeros(n, np.uint64)
+        N.check(N.lib().pcv_octree_node_data(self.h, m["hi"], m["lo"], _p(xyz), _p(rgb), _p(inten), _p(src)))
+        return xyz, rgb, inten, src
+
+    def download(self, xyz=None, rgb=None, intensity=None, src=None):
+        xyz = np.zeros(max(self.xyz_bytes, 1), np.uint8) if xyz is None else xyz
+        rgb = np.zeros(max(self.num_points * 3, 1), np.uint8) if rgb is None else rgb
+        if intensity is None and self.has_intensity:
+            intensity = np.zeros(self.num_points, np.float32)
+        src = np.zeros(max(self.num_points, 1), np.uint64) if src is None else src
+        N.check(N.lib().pcv_octree_download(self.h, _p(xyz), _p(rgb), _p(intensity), _p(src)))
+        return xyz, rgb, intensity, src
+
+    def write_dir(self, directory):
+        N.check(N.lib().pcv_octree_write_dir(self.h, str(directory).encode()))
+
+    # PointCloud::nodes_in_location (octree/mod.rs:329-331)
+    def nodes_in_location(self, loc):
+        cap = len(self.nodes) + 1
+        out = np.zeros(2 * cap, np.uint64)
+        n = C.c_uint64()
+        N.check(N.lib().pcv_nodes_in_location(self.h, C.byref(loc), _p(out), cap, C.byref(n)))
+        return [node_name(out[2 * i], out[2 * i + 1]) for i in range(n.value)]
+
+    # Octree::get_visible_nodes (octree/mod.rs:228)
+    def get_visible_nodes(self, clip_from_world):
+        m = np.asarray(clip_from_world, np.float64)
+        flat = m.T.reshape(-1) if m.ndim == 2 else m
+        cap = len(self.nodes) + 1
+        out = np.zeros(2 * cap, np.uint64)
+        n = C.c_uint64()
+        N.check(N.lib().pcv_visible_nodes(self.h, (C.c_double * 16)(*[float(v) for v in flat]), _p(out), cap, C.byref(n)))
+        return [node_name(out[2 * i], out[2 * i + 1]) for i in range(n.value)]
+
+    # ParallelIterator::try_for_each_batch semantics (iterator.rs:255-333) on the caller's thread
+    def query_points(self, loc, callback=None, filters=(), batch_size=500000):
+        """Streams batches dict(xyz (n,3) f64, rgb (n,3), intensity, src).  A callback returning a truthy
+        value cancels the stream (ErrorKind::Channel); without a callback the batches are returned."""
+        f = np.asarray(filters, np.float64).reshape(-1)
+        nf = len(f) // 2
+        got = []
+
+        def tramp(_user, bp):
+            b = bp.contents
+            n = b.n
+            d = dict(
+                xyz=np.ctypeslib.as_array(C.cast(b.xyz, C.POINTER(C.c_double)), (n, 3)).copy() if n else np.zeros((0, 3)),
+                rgb=np.ctypeslib.as_array(C.cast(b.rgb, C.POINTER(C.c_uint8)), (n, 3)).copy() if n else np.zeros((0, 3), np.uint8),
+                intensity=np.ctypeslib.as_array(C.cast(b.intensity, C.POINTER(C.c_float)), (n,)).copy() if (n and b.intensity) else None,
+                src=np.ctypeslib.as_array(C.cast(b.src_index, C.POINTER(C.c_uint64)), (n,)).copy() if n else np.zeros(0, np.uint64),
+            )
+            if callback is None:
+                got.append(d)
+                return 0
+            return 1 if callback(d) else 0
+
+        cb = N.BATCH_CB(tramp)
+        rc = N.lib().pcv_query_points(self.h, C.byref(loc), _p(f) if nf else None, nf, int(batch_size), cb, None)
+        if rc == -5:
+            raise PcvError(rc, "cancelled by callback")
+        N.check(rc)
+        return got
+
+    def query_batch_device(self, locs, filters=()):
+        arr = (N.Location * len(locs))(*locs)
+        f = np.asarray(filters, np.float64).reshape(-1)
+        nf = len(f) // 2
+        counts, tested = np.zeros(len(locs), np.uint64), np.zeros(len(locs), np.uint64)
+        N.check(N.lib().pcv_query_batch_device(self.h, arr, len(locs), _p(f) if nf else None, nf, _p(counts), _p(tested)))
+        return counts, tested
+
+    def xray_tile(self, tile_min, tile_max, w, h, query_from_global=None, want_bits=False):
+        rgba = np.zeros((h, w, 4), np.uint8)
+        zb = np.zeros((h, w, 32), np.uint32) if want_bits else None
+        anyp = C.c_int()
+        q = (C.c_double * 7)(*[float(v) for v in query_from_global]) if query_from_global is not None else None
+        N.check(N.lib().pcv_xray_tile(self.h, _d3(tile_min), _d3(tile_max), w, h, q, _p(rgba), _p(zb), C.byref(anyp)))
+        return bool(anyp.value), rgba, zb
+
+
+def build_octree(output_directory, resolution, bounding_box, batches, attributes=("color",), device=0, ctx=None):
+    """Drop-in shape of point_viewer::octree::build_octree (src/octree/generation.rs:289-295):
+    drains `batches` (iterable of dict(position (n,3) f64, color (n,3) u8[, intensity (n,) f32])), builds on
+    the GPU, writes the reference's directory layout.  bounding_box = (min3, max3)."""
+    pos, col, inten = [], [], []
+    for b in batches:
+        pos.append(np.ascontiguousarray(b["position"], np.float64).reshape(-1, 3))
+        col.append(np.ascontiguousarray(b["color"], np.uint8).reshape(-1, 3))
+        if "intensity" in b and "intensity" in attributes:
+            inten.append(np.ascontiguousarray(b["intensity"], np.float32).reshape(-1))
+    P = np.concatenate(pos) if pos else np.zeros((0, 3))
+    Cc = np.concatenate(col) if col else np.zeros((0, 3), np.uint8)
+    I = np.concatenate(inten) if inten else None
+    own = ctx is None
+    ctx = ctx or Context(device)
+    flat = P.reshape(-1)
+    tree = ctx.build_octree(flat[0:], flat[1:], flat[2:], Cc.reshape(-1), resolution, bounding_box[0], bounding_box[1], intensity=I, stride=3, n=len(P))
+    tree.write_dir(output_directory)
+    if own:
+        tree.free()
+        ctx.close()
+        return None
+    return tree

@@ -1,0 +1,156 @@
+"""ctypes bindings of include/pcv.h (libpcv_b200.so).
+
+The shared library is the product; this module is plumbing.  It fails loudly when the CUDA extension
+has not been built (there is no CPU or pure-Python fallback)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcv_b200.so")
+
+PCV_OK = 0
+ERR_NAMES = {
+    -1: "PCV_ERR_INVALID",
+    -2: "PCV_ERR_CUDA",
+    -3: "PCV_ERR_IO",
+    -4: "PCV_ERR_NOT_FOUND",
+    -5: "PCV_ERR_CANCELLED",
+    -6: "PCV_ERR_UNSUPPORTED",
+    -7: "PCV_ERR_SINGULAR",
+}
+
+
+class PcvError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, code), msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("max_points_per_node", C.c_uint64), ("levels_per_pass", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Points(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("y", C.c_void_p),
+        ("z", C.c_void_p),
+        ("stride", C.c_uint64),
+        ("rgb", C.c_void_p),
+        ("intensity", C.c_void_p),
+        ("n", C.c_uint64),
+    ]
+
+
+class NodeMeta(C.Structure):
+    _fields_ = [
+        ("id_high", C.c_uint64),
+        ("id_low", C.c_uint64),
+        ("num_points", C.c_int64),
+        ("position_encoding", C.c_int32),
+        ("level", C.c_int32),
+        ("cube_min", C.c_double * 3),
+        ("cube_edge", C.c_double),
+        ("point_offset", C.c_uint64),
+        ("xyz_byte_offset", C.c_uint64),
+    ]
+
+
+class Location(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("pad", C.c_int32),
+        ("aabb_min", C.c_double * 3),
+        ("aabb_max", C.c_double * 3),
+        ("clip_from_query", C.c_double * 16),
+        ("query_from_clip", C.c_double * 16),
+        ("query_from_obb", C.c_double * 7),
+        ("obb_from_query", C.c_double * 7),
+        ("half_extent", C.c_double * 3),
+    ]
+
+
+class Interval(C.Structure):
+    _fields_ = [("lo", C.c_double), ("hi", C.c_double)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("xyz", C.c_void_p), ("rgb", C.c_void_p), ("intensity", C.c_void_p), ("src_index", C.c_void_p)]
+
+
+BATCH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Batch))
+
+
+class BuildStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64),
+        ("passes", C.c_uint32),
+        ("deepest_level", C.c_uint32),
+        ("num_nodes", C.c_uint64),
+        ("algorithmic_bytes", C.c_uint64),
+        ("ms_bbox", C.c_float),
+        ("ms_partition", C.c_float),
+        ("ms_place", C.c_float),
+        ("ms_total", C.c_float),
+        ("ms_chain_kernels", C.c_float),
+    ]
+
+
+# every symbol include/pcv.h declares: (name, restype, argtypes)
+_dp = C.POINTER(C.c_double)
+_u64p = C.POINTER(C.c_uint64)
+SYMBOLS = [
+    ("pcv_create", C.c_int, [C.c_int, C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    ("pcv_destroy", None, [C.c_void_p]),
+    ("pcv_last_error", C.c_char_p, []),
+    ("pcv_device_count", C.c_int, []),
+    ("pcv_bbox", C.c_int, [C.c_void_p, C.POINTER(Points), _dp, _dp]),
+    ("pcv_bbox_device", C.c_int, [C.c_void_p, C.POINTER(Points), _dp, _dp]),
+    ("pcv_build_octree", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.POINTER(C.c_void_p)]),
+    ("pcv_build_octree_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.POINTER(C.c_void_p)]),
+    ("pcv_octree_free", None, [C.c_void_p]),
+    ("pcv_octree_info", C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
+    ("pcv_octree_nodes", C.c_int, [C.c_void_p, C.POINTER(NodeMeta), C.c_uint64]),
+    ("pcv_octree_node_data", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_octree_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_octree_device_arrays", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("pcv_octree_write_dir", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("pcv_octree_load_dir", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("pcv_nodes_in_location", C.c_int, [C.c_void_p, C.POINTER(Location), C.c_void_p, C.c_uint64, _u64p]),
+    ("pcv_visible_nodes", C.c_int, [C.c_void_p, _dp, C.c_void_p, C.c_uint64, _u64p]),
+    ("pcv_query_points", C.c_int, [C.c_void_p, C.POINTER(Location), C.c_void_p, C.c_uint32, C.c_uint64, BATCH_CB, C.c_void_p]),
+    ("pcv_query_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    ("pcv_xray_tile", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    ("pcv_prefix_histogram_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p]),
+    ("pcv_prefix_pack_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_synth_points_device", C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_synth_points_host", C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_synth_bbox", C.c_int, [C.c_int, _dp, _dp, _dp]),
+    ("pcv_last_build_stats", C.c_int, [C.c_void_p, C.POINTER(BuildStats)]),
+    ("pcv_kernel_launch_count", C.c_uint64, [C.c_void_p]),
+]
+
+_lib = None
+
+
+def lib():
+    """Load libpcv_b200.so; raise (never fall back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "point_cloud_viewer_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != PCV_OK:
+        raise PcvError(rc, lib().pcv_last_error().decode("utf-8", "replace"))

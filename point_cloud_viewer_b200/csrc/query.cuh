@@ -1,2 +1,368 @@
-// query.cuh — placeholder, filled in below.
+// query.cuh — sm_100a kernels of the query side.
+//
+//   k_sat_nodes      a11-a12  batched separating-axis test: (location, node cube) -> Relation
+//   k_propagate      a11      BFS semantics of NodeIdsIterator: a node is visited iff all ancestors passed
+//   k_visible_eval   a17      per node: Relation vs the view frustum + relative_size_on_screen
+//   k_cull_count / k_cull_write   a13-a15  decode + PointCulling::contains + interval filters +
+//                                 order-preserving compaction (FilteredIterator, iterator.rs:96-119)
+//   k_xray_accum / k_xray_resolve a19  discretise + per-pixel 1024-bit z-bucket set + grey mapping
+//
+// All arithmetic is binary64 in the reference's operation order (compiled with -fmad=false).
 #pragma once
+#include <cuda_runtime.h>
+
+#include "chain.h"
+#include "geometry_host.hpp"
+
+namespace pcv {
+
+struct QNode {
+    double m[3];
+    double e;
+    uint64_t point_off;
+    uint64_t xyz_off;
+    uint32_t n;
+    int32_t enc;
+    int32_t parent;
+    int32_t level;
+};
+
+enum : uint8_t { REL_IN = 0, REL_CROSS = 1, REL_OUT = 2 };  // sat.rs:39-47
+
+// Project the 8 corners of the cube (min m, edge e) on an axis: Aabb corners order x fastest (aabb.rs:114-125),
+// max = min + edge (aabb.rs:175-181).
+__device__ __forceinline__ void project_cube(const double m[3], double e, const double ax[3], double& lo, double& hi) {
+    const double mx[3] = {m[0] + e, m[1] + e, m[2] + e};
+    lo = 1.7976931348623157e308;
+    hi = -1.7976931348623157e308;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double cx = (i & 1) ? mx[0] : m[0], cy = (i & 2) ? mx[1] : m[1], cz = (i & 4) ? mx[2] : m[2];
+        const double p = cx * ax[0] + cy * ax[1] + cz * ax[2];
+        lo = fmin(lo, p);
+        hi = fmax(hi, p);
+    }
+}
+
+// sat() of sat.rs:174-194 with A = the location (projections precomputed in aproj) and B = the node cube.
+__device__ __forceinline__ uint8_t sat_cube(const QueryGeom& g, const double (*aproj)[2], const double m[3], double e) {
+    uint8_t rel = REL_IN;
+    for (int k = 0; k < g.naxes; ++k) {
+        double bmin, bmax;
+        project_cube(m, e, g.axes[k], bmin, bmax);
+        const double amin = aproj[k][0], amax = aproj[k][1];
+        if (bmin > amax || bmax < amin) return REL_OUT;
+        if (amin > bmin || bmax > amax) rel = REL_CROSS;
+    }
+    return rel;
+}
+
+__device__ __forceinline__ void project_location(const QueryGeom& g, double (*aproj)[2]) {
+    for (int k = threadIdx.x; k < g.naxes; k += blockDim.x) {
+        double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
+        for (int i = 0; i < 8; ++i) {
+            const double p = g.corners[i][0] * g.axes[k][0] + g.corners[i][1] * g.axes[k][1] + g.corners[i][2] * g.axes[k][2];
+            lo = fmin(lo, p);
+            hi = fmax(hi, p);
+        }
+        aproj[k][0] = lo;
+        aproj[k][1] = hi;
+    }
+}
+
+// grid = (ceil(nnodes/256), nloc).  rel[loc * nnodes + node]
+__global__ void __launch_bounds__(256) k_sat_nodes(const QueryGeom* __restrict__ geoms, const QNode* __restrict__ nodes, uint32_t nnodes,
+                                                   uint8_t* __restrict__ rel) {
+    __shared__ double aproj[26][2];
+    const QueryGeom& g = geoms[blockIdx.y];
+    project_location(g, aproj);
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    uint8_t r = REL_IN;
+    if (g.kind != PCV_LOC_ALL) {
+        const QNode nd = nodes[i];
+        r = sat_cube(g, aproj, nd.m, nd.e);
+    }
+    rel[(size_t)blockIdx.y * nnodes + i] = r;
+}
+
+// One block per location; nodes are sorted by level so parents precede children.  pass = not Out && parent passed.
+__global__ void __launch_bounds__(1024) k_propagate(const QNode* __restrict__ nodes, const uint32_t* __restrict__ level_start, int nlevels,
+                                                    uint32_t nnodes, uint8_t* __restrict__ rel, uint8_t* __restrict__ pass) {
+    uint8_t* r = rel + (size_t)blockIdx.x * nnodes;
+    uint8_t* p = pass + (size_t)blockIdx.x * nnodes;
+    for (int L = 0; L < nlevels; ++L) {
+        for (uint32_t i = level_start[L] + threadIdx.x; i < level_start[L + 1]; i += blockDim.x) {
+            const int par = nodes[i].parent;
+            p[i] = (r[i] != REL_OUT && (par < 0 || p[par])) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// relative_size_on_screen (octree/mod.rs:103-139): project the 8 cube corners with the 4x4 (homogeneous divide),
+// clamp to [-1,1]^2 x [0,1], grow an Aabb, return diag.x * diag.y.  bad[0] is set if any w == 0 (reference panics).
+__device__ __forceinline__ double num_clamp_d(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__global__ void __launch_bounds__(256) k_visible_eval(const QueryGeom* __restrict__ geom, const double* __restrict__ M,
+                                                      const QNode* __restrict__ nodes, uint32_t nnodes, uint8_t* __restrict__ rel,
+                                                      double* __restrict__ size, int* __restrict__ bad) {
+    __shared__ double aproj[26][2];
+    const QueryGeom& g = geom[0];
+    project_location(g, aproj);
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    const QNode nd = nodes[i];
+    rel[i] = sat_cube(g, aproj, nd.m, nd.e);
+    const double mn[3] = {nd.m[0], nd.m[1], nd.m[2]}, mx[3] = {nd.m[0] + nd.e, nd.m[1] + nd.e, nd.m[2] + nd.e};
+    double lo[2] = {0, 0}, hi[2] = {0, 0};
+    // corner order of mod.rs:122-137: min, max, then 6 mixed corners (order is irrelevant for min/max)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double px = (c & 1) ? mx[0] : mn[0], py = (c & 2) ? mx[1] : mn[1], pz = (c & 4) ? mx[2] : mn[2];
+        double q[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double a = M[r] * px;
+            a = M[4 + r] * py + a;
+            a = M[8 + r] * pz + a;
+            a = M[12 + r] * 1.0 + a;
+            q[r] = a;
+        }
+        if (q[3] == 0.0) atomicExch(bad, 1);
+        const double x = num_clamp_d(q[0] / q[3], -1., 1.), y = num_clamp_d(q[1] / q[3], -1., 1.);
+        if (c == 0) {
+            lo[0] = hi[0] = x;
+            lo[1] = hi[1] = y;
+        } else {
+            lo[0] = fmin(lo[0], x);
+            hi[0] = fmax(hi[0], x);
+            lo[1] = fmin(lo[1], y);
+            hi[1] = fmax(hi[1], y);
+        }
+    }
+    size[i] = (hi[0] - lo[0]) * (hi[1] - lo[1]);
+}
+
+// ---- per-point culling -----------------------------------------------------------------------------
+__device__ __forceinline__ bool loc_contains(const QueryGeom& g, double x, double y, double z) {
+    if (g.kind == PCV_LOC_AABB) {  // aabb.rs:46-48
+        return g.aabb_min[0] <= x && g.aabb_min[1] <= y && g.aabb_min[2] <= z && x < g.aabb_max[0] && y < g.aabb_max[1] && z < g.aabb_max[2];
+    }
+    if (g.kind == PCV_LOC_FRUSTUM) {  // frustum.rs:120-125
+        const V3 c = mat4_transform_point(g.clip_from_query, V3{x, y, z});
+        const double mn = fmin(fmin(c.x, c.y), c.z), mx = fmax(fmax(c.x, c.y), c.z);
+        return mn > -1.0 && mx < 1.0;
+    }
+    if (g.kind == PCV_LOC_OBB) {  // obb.rs:83-90
+        const V3 q = iso_apply(g.obb_from_query, V3{x, y, z});
+        return fabs(q.x) <= g.half_extent[0] && fabs(q.y) <= g.half_extent[1] && fabs(q.z) <= g.half_extent[2];
+    }
+    return true;  // AllPoints, math/mod.rs:157-161
+}
+
+struct QTile {
+    uint32_t loc;
+    uint32_t node;
+    uint32_t first;   // first point of the tile inside the node
+    uint32_t count;
+};
+constexpr uint32_t kQueryTile = 2048;
+
+struct CullArgs {
+    const QueryGeom* geoms;
+    const QNode* nodes;
+    const QTile* tiles;
+    const uint8_t* xyz;
+    const uint8_t* rgb;
+    const float* intensity;
+    const uint32_t* src;
+    const pcv_interval* filters;
+    uint32_t nfilt;
+    uint32_t* tile_keep;     // count pass output, then (after the scan) exclusive offsets
+    double* out_xyz;         // write pass outputs (AoS)
+    uint8_t* out_rgb;
+    float* out_intensity;
+    uint32_t* out_src;
+};
+
+__device__ __forceinline__ uint64_t load_code(const uint8_t* p, int enc) {
+    if (enc == ENC_U8) return *p;
+    if (enc == ENC_U16) return *reinterpret_cast<const uint16_t*>(p);
+    if (enc == ENC_F32) return *reinterpret_cast<const uint32_t*>(p);
+    return *reinterpret_cast<const uint64_t*>(p);
+}
+
+__device__ __forceinline__ bool eval_point(const CullArgs& a, const QueryGeom& g, const QNode& nd, uint32_t i, double p[3]) {
+    const int bpc = enc_bytes(nd.enc);
+    const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)i * 3 * bpc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = decode1(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+    bool keep = loc_contains(g, p[0], p[1], p[2]);
+    if (a.nfilt) {
+        const double v = (double)a.intensity[nd.point_off + i];  // iterator.rs:82-91: attribute as f64, closed interval
+        for (uint32_t f = 0; f < a.nfilt; ++f) keep = keep && (a.filters[f].lo <= v && v <= a.filters[f].hi);
+    }
+    return keep;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_cull(const __grid_constant__ CullArgs a) {
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t running;
+    const QTile t = a.tiles[blockIdx.x];
+    const QueryGeom& g = a.geoms[t.loc];
+    const QNode nd = a.nodes[t.node];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = WRITE ? a.tile_keep[blockIdx.x] : 0u;
+    __syncthreads();
+    for (uint32_t r0 = 0; r0 < t.count; r0 += 256) {
+        const uint32_t i = r0 + threadIdx.x;
+        double p[3] = {0, 0, 0};
+        bool keep = false;
+        if (i < t.count) keep = eval_point(a, g, nd, t.first + i, p);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = warp_cnt[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        if (WRITE && keep) {
+            const uint64_t dst = (uint64_t)running + before + __popc(bal & ((1u << lane) - 1u));
+            const uint64_t sp = nd.point_off + t.first + i;
+            a.out_xyz[3 * dst] = p[0];
+            a.out_xyz[3 * dst + 1] = p[1];
+            a.out_xyz[3 * dst + 2] = p[2];
+            a.out_rgb[3 * dst] = a.rgb[3 * sp];
+            a.out_rgb[3 * dst + 1] = a.rgb[3 * sp + 1];
+            a.out_rgb[3 * dst + 2] = a.rgb[3 * sp + 2];
+            if (a.out_intensity) a.out_intensity[dst] = a.intensity[sp];
+            a.out_src[dst] = a.src[sp];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running += total;
+        __syncthreads();
+    }
+    if (!WRITE && threadIdx.x == 0) a.tile_keep[blockIdx.x] = running;
+}
+
+// Exclusive scan of n u32 values in place; total (u64) to *total_out.  Single block; n is at most a few million tiles.
+__global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* v, uint32_t n, unsigned long long* total_out) {
+    __shared__ uint32_t wsum[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < n ? v[i] : 0u;
+        uint32_t incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = wsum[lane], si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, si, o);
+                if (lane >= o) si += y;
+            }
+            wsum[lane] = si - s;  // exclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long c = carry;
+        if (i < n) v[i] = (uint32_t)(c + wsum[warp] + (incl - x));
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wsum[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+// per-location totals: kept[loc] += keep counts, tested[loc] += tile counts
+__global__ void k_tile_totals(const QTile* tiles, const uint32_t* keep_counts, uint32_t ntiles, unsigned long long* kept,
+                              unsigned long long* tested) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntiles) return;
+    atomicAdd(&kept[tiles[i].loc], (unsigned long long)keep_counts[i]);
+    atomicAdd(&tested[tiles[i].loc], (unsigned long long)tiles[i].count);
+}
+
+// ---- X-ray -----------------------------------------------------------------------------------------
+struct XrayArgs {
+    QueryGeom geom;
+    const QNode* nodes;
+    const QTile* tiles;
+    const uint8_t* xyz;
+    double tmin[3], tdiag[3];
+    double query_from_global[7];
+    int has_q;
+    uint32_t w, h;
+    uint32_t* zbits;   // w*h*32
+    uint8_t* zover;    // w*h
+    int* any;
+};
+
+__global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ XrayArgs a) {
+    const QTile t = a.tiles[blockIdx.x];
+    const QNode nd = a.nodes[t.node];
+    const int bpc = enc_bytes(nd.enc);
+    bool seen = false;
+    for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
+        const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)(t.first + i) * 3 * bpc;
+        double p[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = decode1(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+        if (!loc_contains(a.geom, p[0], p[1], p[2])) continue;
+        seen = true;
+        if (a.has_q) {  // generation.rs:493-497
+            const V3 q = iso_apply(a.query_from_global, V3{p[0], p[1], p[2]});
+            p[0] = q.x;
+            p[1] = q.y;
+            p[2] = q.z;
+        }
+        // process_point_data, generation.rs:108-127 (`as u32` saturates, NaN -> 0)
+        const uint32_t x = __double2uint_rz(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
+        const uint32_t y = __double2uint_rz((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
+        const uint32_t z = __double2uint_rz(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
+        if (x < a.w && y < a.h) {
+            const size_t px = (size_t)y * a.w + x;
+            if (z < 1024)
+                atomicOr(&a.zbits[px * 32 + (z >> 5)], 1u << (z & 31));
+            else
+                a.zover[px] = 1;
+        }
+    }
+    if (__syncthreads_or(seen) && threadIdx.x == 0) atomicExch(a.any, 1);
+}
+
+// grey[count] LUT is computed on the host with libm log (generation.rs:186-197) so the cast boundary matches.
+__global__ void __launch_bounds__(256) k_xray_resolve(const uint32_t* __restrict__ zbits, const uint8_t* __restrict__ zover,
+                                                      const uint8_t* __restrict__ grey, uint32_t npix, uint8_t* __restrict__ rgba) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npix) return;
+    uint32_t cnt = zover[px];
+    const uint4* b = reinterpret_cast<const uint4*>(zbits + (size_t)px * 32);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint4 v = b[k];
+        cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if (cnt) {
+        const uint8_t gval = grey[cnt];
+        o = make_uchar4(gval, gval, gval, 255);
+    }
+    reinterpret_cast<uchar4*>(rgba)[px] = o;
+}
+
+}  // namespace pcv

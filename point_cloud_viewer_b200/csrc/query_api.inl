@@ -1,10 +1,533 @@
-// query_api.inl — placeholder
-extern "C" {
-int pcv_nodes_in_location(const pcv_octree*, const pcv_location*, uint64_t*, uint64_t, uint64_t*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_visible_nodes(const pcv_octree*, const double*, uint64_t*, uint64_t, uint64_t*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_query_points(const pcv_octree*, const pcv_location*, const pcv_interval*, uint32_t, uint64_t, pcv_batch_cb, void*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_query_batch_device(const pcv_octree*, const pcv_location*, uint32_t, const pcv_interval*, uint32_t, uint64_t*, uint64_t*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_xray_tile(const pcv_octree*, const double*, const double*, uint32_t, uint32_t, const double*, uint8_t*, uint32_t*, int*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_prefix_histogram_device(pcv_ctx*, const pcv_points*, double, const double*, const double*, uint32_t, uint64_t*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
-int pcv_prefix_pack_device(pcv_ctx*, const pcv_points*, const uint64_t*, double, const double*, const double*, uint32_t, const int32_t*, uint32_t, double*, uint8_t*, float*, uint64_t*, uint64_t*) { return fail(PCV_ERR_UNSUPPORTED, "nyi"); }
+// query_api.inl — query-side entry points of the C ABI (included at the end of pcv_api.cu).
+
+namespace {
+
+using namespace pcv;
+
+struct Scratch {  // stream-ordered device allocations released on scope exit
+    pcv_ctx* c;
+    std::vector<void*> ptrs;
+    explicit Scratch(pcv_ctx* ctx) : c(ctx) {}
+    template <class T>
+    T* alloc(size_t n) {
+        T* p = (T*)c->be->dmalloc(n * sizeof(T));
+        ptrs.push_back(p);
+        return p;
+    }
+    template <class T>
+    T* upload(const T* h, size_t n) {
+        T* p = alloc<T>(n ? n : 1);
+        if (n) c->be->h2d(p, h, n * sizeof(T));
+        return p;
+    }
+    ~Scratch() {
+        for (void* p : ptrs) c->be->dfree(p);
+    }
+};
+
+struct QTables {
+    std::vector<QNode> qn;
+    std::vector<uint32_t> level_start;  // nlevels + 1
+};
+
+// Node table for the query kernels + parent/children indices (nodes are sorted by NodeId = level-major).
+void ensure_tables(pcv_octree* o) {
+    if (o->tables_ready) return;
+    const size_t n = o->nodes.size();
+    std::vector<QNode> qn(n);
+    o->parent_of.assign(n, -1);
+    o->children_of.assign(n * 8, -1);
+    for (size_t i = 0; i < n; ++i) {
+        const pcv_node_meta& m = o->nodes[i];
+        QNode& q = qn[i];
+        for (int a = 0; a < 3; ++a) q.m[a] = m.cube_min[a];
+        q.e = m.cube_edge;
+        q.point_off = m.point_offset;
+        q.xyz_off = m.xyz_byte_offset;
+        q.n = (uint32_t)m.num_points;
+        q.enc = m.position_encoding;
+        q.level = m.level;
+        q.parent = -1;
+        if (m.level > 0) {
+            const u128 id = ((u128)m.id_high << 64) | m.id_low;
+            const u128 idx = id & ((((u128)1) << 120) - 1);
+            const u128 pid = ((u128)(m.level - 1) << 120) | (idx >> 3);  // node.rs:136-144
+            const int p = o->find((uint64_t)(pid >> 64), (uint64_t)pid);
+            q.parent = p;
+            o->parent_of[i] = p;
+            if (p >= 0) o->children_of[(size_t)p * 8 + (size_t)(idx & 7)] = (int32_t)i;
+        }
+    }
+    pcv_ctx* c = o->ctx;
+    if (n) {
+        o->d_qnodes = c->be->dmalloc(n * sizeof(QNode));
+        c->be->h2d(o->d_qnodes, qn.data(), n * sizeof(QNode));
+    }
+    o->tables_ready = true;
 }
+
+std::vector<uint32_t> level_starts(const pcv_octree* o) {
+    int maxl = 0;
+    for (const auto& m : o->nodes) maxl = std::max(maxl, m.level);
+    std::vector<uint32_t> ls((size_t)maxl + 2, 0);
+    for (const auto& m : o->nodes) ls[(size_t)m.level + 1]++;
+    for (size_t i = 1; i < ls.size(); ++i) ls[i] += ls[i - 1];
+    return ls;
+}
+
+// pass[loc][node] for nloc locations (BFS semantics).  Returns host matrix.
+std::vector<uint8_t> run_sat(pcv_octree* o, const std::vector<QueryGeom>& geoms, Scratch& s, const QueryGeom** d_geoms_out) {
+    pcv_ctx* c = o->ctx;
+    const uint32_t nn = (uint32_t)o->nodes.size(), nloc = (uint32_t)geoms.size();
+    const QueryGeom* dg = s.upload(geoms.data(), geoms.size());
+    if (d_geoms_out) *d_geoms_out = dg;
+    std::vector<uint8_t> pass((size_t)nn * nloc);
+    if (nn == 0 || nloc == 0) return pass;
+    std::vector<uint32_t> ls = level_starts(o);
+    const uint32_t* dls = s.upload(ls.data(), ls.size());
+    uint8_t* drel = s.alloc<uint8_t>((size_t)nn * nloc);
+    uint8_t* dpass = s.alloc<uint8_t>((size_t)nn * nloc);
+    dim3 grid((nn + 255) / 256, nloc);
+    k_sat_nodes<<<grid, 256, 0, c->stream>>>(dg, (const QNode*)o->d_qnodes, nn, drel);
+    k_propagate<<<nloc, 1024, 0, c->stream>>>((const QNode*)o->d_qnodes, dls, (int)ls.size() - 1, nn, drel, dpass);
+    c->be->launches += 2;
+    CU(cudaGetLastError());
+    c->be->d2h(pass.data(), dpass, pass.size());
+    return pass;
+}
+
+// Rust std::collections::BinaryHeap<OpenNode> (max-heap on size_on_screen) restated: push = append + sift_up;
+// pop = take last, swap into the root, sift the hole down to the bottom preferring the right child when
+// left <= right, then sift_up (octree/mod.rs:360-404).
+struct Open {
+    int node;
+    uint8_t rel;
+    double size;
+};
+struct OpenHeap {
+    std::vector<Open> v;
+    void up(size_t pos) {
+        const Open x = v[pos];
+        while (pos > 0) {
+            const size_t par = (pos - 1) >> 1;
+            if (x.size <= v[par].size) break;
+            v[pos] = v[par];
+            pos = par;
+        }
+        v[pos] = x;
+    }
+    void push(const Open& x) {
+        v.push_back(x);
+        up(v.size() - 1);
+    }
+    bool pop(Open& out) {
+        if (v.empty()) return false;
+        Open last = v.back();
+        v.pop_back();
+        if (v.empty()) {
+            out = last;
+            return true;
+        }
+        out = v[0];
+        const size_t end = v.size();
+        size_t pos = 0, child = 1;
+        while (child < end) {
+            const size_t right = child + 1;
+            if (right < end && !(v[child].size > v[right].size)) child = right;
+            v[pos] = v[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        v[pos] = last;
+        up(pos);
+        return true;
+    }
+};
+
+struct HostBatchBuf {  // PointStream (iterator.rs:123-166): re-chunk into exactly batch_size points
+    std::vector<double> xyz;
+    std::vector<uint8_t> rgb;
+    std::vector<float> inten;
+    std::vector<uint64_t> src;
+    size_t head = 0;  // points already delivered from the front
+    size_t size() const { return src.size() - head; }
+    int deliver(size_t n, bool has_i, pcv_batch_cb cb, void* user) {
+        pcv_batch b;
+        b.n = n;
+        b.xyz = xyz.data() + 3 * head;
+        b.rgb = rgb.data() + 3 * head;
+        b.intensity = has_i ? inten.data() + head : nullptr;
+        b.src_index = src.data() + head;
+        head += n;
+        return cb(user, &b);
+    }
+    void compact(bool has_i) {
+        if (head == 0) return;
+        xyz.erase(xyz.begin(), xyz.begin() + 3 * head);
+        rgb.erase(rgb.begin(), rgb.begin() + 3 * head);
+        if (has_i) inten.erase(inten.begin(), inten.begin() + head);
+        src.erase(src.begin(), src.begin() + head);
+        head = 0;
+    }
+};
+
+void make_tiles(const pcv_octree* o, uint32_t loc, uint32_t node, std::vector<QTile>& tiles) {
+    const uint32_t n = (uint32_t)o->nodes[node].num_points;
+    for (uint32_t f = 0; f < n; f += kQueryTile) tiles.push_back(QTile{loc, node, f, std::min(kQueryTile, n - f)});
+}
+
+struct CullResult {
+    uint64_t total = 0;
+    double* d_xyz = nullptr;
+    uint8_t* d_rgb = nullptr;
+    float* d_inten = nullptr;
+    uint32_t* d_src = nullptr;
+};
+
+// count -> scan -> write for a list of tiles.  Output buffers come from `s`.
+CullResult run_cull(pcv_octree* o, const QueryGeom* d_geoms, const std::vector<QTile>& tiles, const pcv_interval* filters, uint32_t nfilt,
+                    Scratch& s, unsigned long long* d_kept, unsigned long long* d_tested) {
+    pcv_ctx* c = o->ctx;
+    CullResult r;
+    if (tiles.empty()) return r;
+    CullArgs a{};
+    a.geoms = d_geoms;
+    a.nodes = (const QNode*)o->d_qnodes;
+    a.tiles = s.upload(tiles.data(), tiles.size());
+    a.xyz = o->d_xyz;
+    a.rgb = o->d_rgb;
+    a.intensity = o->d_intensity;
+    a.src = o->d_src;
+    a.filters = nfilt ? s.upload(filters, nfilt) : nullptr;
+    a.nfilt = nfilt;
+    a.tile_keep = s.alloc<uint32_t>(tiles.size());
+    const uint32_t nt = (uint32_t)tiles.size();
+    k_cull<false><<<nt, 256, 0, c->stream>>>(a);
+    if (d_kept) k_tile_totals<<<(nt + 255) / 256, 256, 0, c->stream>>>(a.tiles, a.tile_keep, nt, d_kept, d_tested);
+    unsigned long long* d_total = s.alloc<unsigned long long>(1);
+    k_scan_u32<<<1, 1024, 0, c->stream>>>(a.tile_keep, nt, d_total);
+    c->be->launches += d_kept ? 3 : 2;
+    CU(cudaGetLastError());
+    unsigned long long total = 0;
+    c->be->d2h(&total, d_total, 8);
+    r.total = total;
+    if (total >= 0xFFFFFFFFull) throw BuildError(PCV_ERR_UNSUPPORTED, "more than 2^32-1 survivors in one launch");
+    if (total == 0) return r;
+    r.d_xyz = a.out_xyz = s.alloc<double>(3 * total);
+    r.d_rgb = a.out_rgb = s.alloc<uint8_t>(3 * total);
+    r.d_inten = a.out_intensity = o->d_intensity ? s.alloc<float>(total) : nullptr;
+    r.d_src = a.out_src = s.alloc<uint32_t>(total);
+    k_cull<true><<<nt, 256, 0, c->stream>>>(a);
+    c->be->launches += 1;
+    CU(cudaGetLastError());
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcv_nodes_in_location(const pcv_octree* oc, const pcv_location* loc, uint64_t* ids, uint64_t cap, uint64_t* n_out) {
+    if (!oc || !loc || !n_out) return fail(PCV_ERR_INVALID, "null argument");
+    if (loc->kind < 0 || loc->kind > 3) return fail(PCV_ERR_INVALID, "unknown location kind %d", loc->kind);
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    Scratch s(c);
+    std::vector<QueryGeom> geoms{make_query_geom(*loc)};
+    std::vector<uint8_t> pass = run_sat(o, geoms, s, nullptr);
+    uint64_t n = 0;
+    for (size_t i = 0; i < pass.size(); ++i)
+        if (pass[i]) {
+            if (n < cap && ids) {
+                ids[2 * n] = o->nodes[i].id_high;
+                ids[2 * n + 1] = o->nodes[i].id_low;
+            }
+            ++n;
+        }
+    *n_out = n;
+    if (n > cap) return fail(PCV_ERR_INVALID, "capacity %llu < %llu nodes", (unsigned long long)cap, (unsigned long long)n);
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_visible_nodes(const pcv_octree* oc, const double M[16], uint64_t* ids, uint64_t cap, uint64_t* n_out) {
+    if (!oc || !M || !n_out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    pcv_location loc{};
+    loc.kind = PCV_LOC_FRUSTUM;
+    memcpy(loc.clip_from_query, M, sizeof(double) * 16);
+    if (!mat4_try_inverse(M, loc.query_from_clip)) return fail(PCV_ERR_SINGULAR, "Invalid projection matrix.");
+    *n_out = 0;
+    const uint32_t nn = (uint32_t)o->nodes.size();
+    if (nn == 0) return PCV_OK;
+    Scratch s(c);
+    QueryGeom geom = make_query_geom(loc);
+    const QueryGeom* dg = s.upload(&geom, 1);
+    const double* dM = s.upload(M, 16);
+    uint8_t* drel = s.alloc<uint8_t>(nn);
+    double* dsize = s.alloc<double>(nn);
+    int zero = 0;
+    int* dbad = s.upload(&zero, 1);
+    k_visible_eval<<<(nn + 255) / 256, 256, 0, c->stream>>>(dg, dM, (const QNode*)o->d_qnodes, nn, drel, dsize, dbad);
+    c->be->launches++;
+    CU(cudaGetLastError());
+    std::vector<uint8_t> rel(nn);
+    std::vector<double> size(nn);
+    int bad = 0;
+    c->be->d2h(rel.data(), drel, nn);
+    c->be->d2h(size.data(), dsize, (size_t)nn * 8);
+    c->be->d2h(&bad, dbad, 4);
+    // best-first traversal (octree/mod.rs:232-283); only nodes actually pushed are ever evaluated by the reference,
+    // so a w == 0 projection only matters for those - checked lazily below through NaN/inf sizes is not possible,
+    // hence the conservative global flag.
+    if (bad) return fail(PCV_ERR_INVALID, "projection of a node corner has w == 0 (the reference panics here)");
+    OpenHeap open;
+    const int root = o->find(0, 0);
+    if (root >= 0) open.push(Open{root, REL_CROSS, size[root]});
+    uint64_t n = 0;
+    Open cur;
+    while (open.pop(cur)) {
+        for (int k = 0; k < 8; ++k) {
+            const int ch = o->children_of[(size_t)cur.node * 8 + k];
+            if (ch < 0) continue;  // maybe_push_node: only ids present in the meta
+            if (cur.rel == REL_CROSS) {
+                if (rel[ch] == REL_OUT) continue;
+                open.push(Open{ch, rel[ch], size[ch]});
+            } else {
+                open.push(Open{ch, REL_IN, size[ch]});
+            }
+        }
+        if (o->nodes[cur.node].num_points != 0) {
+            if (n < cap && ids) {
+                ids[2 * n] = o->nodes[cur.node].id_high;
+                ids[2 * n + 1] = o->nodes[cur.node].id_low;
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
+    if (n > cap) return fail(PCV_ERR_INVALID, "capacity %llu < %llu nodes", (unsigned long long)cap, (unsigned long long)n);
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_query_points(const pcv_octree* oc, const pcv_location* loc, const pcv_interval* filters, uint32_t nfilt, uint64_t batch_size,
+                     pcv_batch_cb cb, void* user) {
+    if (!oc || !loc || !cb || batch_size == 0) return fail(PCV_ERR_INVALID, "null argument or batch_size == 0");
+    if (nfilt && !filters) return fail(PCV_ERR_INVALID, "filters is null");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    if (nfilt && !o->has_intensity) return fail(PCV_ERR_INVALID, "Filter attribute needs to be specified as query attribute.");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    std::vector<QueryGeom> geoms{make_query_geom(*loc)};
+    std::vector<uint32_t> visit;
+    const QueryGeom* dg = nullptr;
+    Scratch sg(c);
+    {
+        std::vector<uint8_t> pass = run_sat(o, geoms, sg, &dg);
+        for (size_t i = 0; i < pass.size(); ++i)
+            if (pass[i] && o->nodes[i].num_points > 0) visit.push_back((uint32_t)i);
+    }
+    const bool has_i = o->has_intensity;
+    HostBatchBuf hb;
+    const uint64_t kMaxTested = 32ull << 20;  // points decoded per launch group
+    size_t vi = 0;
+    while (vi < visit.size()) {
+        std::vector<QTile> tiles;
+        uint64_t tested = 0;
+        while (vi < visit.size() && (tiles.empty() || tested + (uint64_t)o->nodes[visit[vi]].num_points <= kMaxTested)) {
+            make_tiles(o, 0, visit[vi], tiles);
+            tested += (uint64_t)o->nodes[visit[vi]].num_points;
+            ++vi;
+        }
+        Scratch s(c);
+        CullResult r = run_cull(o, dg, tiles, filters, nfilt, s, nullptr, nullptr);
+        if (r.total == 0) continue;
+        hb.compact(has_i);
+        const size_t old = hb.src.size(), tot = (size_t)r.total;
+        hb.xyz.resize(3 * (old + tot));
+        hb.rgb.resize(3 * (old + tot));
+        if (has_i) hb.inten.resize(old + tot);
+        hb.src.resize(old + tot);
+        std::vector<uint32_t> src32(tot);
+        CU(cudaMemcpyAsync(hb.xyz.data() + 3 * old, r.d_xyz, tot * 24, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(hb.rgb.data() + 3 * old, r.d_rgb, tot * 3, cudaMemcpyDeviceToHost, c->stream));
+        if (has_i) CU(cudaMemcpyAsync(hb.inten.data() + old, r.d_inten, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(src32.data(), r.d_src, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < tot; ++i) hb.src[old + i] = src32[i];
+        while (hb.size() >= batch_size)  // push_points_and_callback, iterator.rs:159-165
+            if (hb.deliver((size_t)batch_size, has_i, cb, user)) return fail(PCV_ERR_CANCELLED, "cancelled by the consumer callback");
+    }
+    if (hb.size() > 0)  // last (short) batch, iterator.rs:316-323
+        if (hb.deliver(hb.size(), has_i, cb, user)) return fail(PCV_ERR_CANCELLED, "cancelled by the consumer callback");
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_query_batch_device(const pcv_octree* oc, const pcv_location* locs, uint32_t nloc, const pcv_interval* filters, uint32_t nfilt,
+                           uint64_t* counts_out, uint64_t* tested_out) {
+    if (!oc || (!locs && nloc)) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    if (nfilt && !o->has_intensity) return fail(PCV_ERR_INVALID, "Filter attribute needs to be specified as query attribute.");
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    if (nloc == 0) return PCV_OK;
+    std::vector<QueryGeom> geoms(nloc);
+    for (uint32_t i = 0; i < nloc; ++i) {
+        if (locs[i].kind < 0 || locs[i].kind > 3) return fail(PCV_ERR_INVALID, "unknown location kind %d", locs[i].kind);
+        geoms[i] = make_query_geom(locs[i]);
+    }
+    Scratch s(c);
+    const QueryGeom* dg = nullptr;
+    std::vector<uint8_t> pass = run_sat(o, geoms, s, &dg);
+    const size_t nn = o->nodes.size();
+    std::vector<QTile> tiles;
+    for (uint32_t l = 0; l < nloc; ++l)
+        for (size_t i = 0; i < nn; ++i)
+            if (pass[(size_t)l * nn + i] && o->nodes[i].num_points > 0) make_tiles(o, l, (uint32_t)i, tiles);
+    std::vector<unsigned long long> zeros(nloc, 0);
+    unsigned long long* dk = s.upload(zeros.data(), nloc);
+    unsigned long long* dt = s.upload(zeros.data(), nloc);
+    run_cull(o, dg, tiles, filters, nfilt, s, dk, dt);
+    std::vector<unsigned long long> hk(nloc), ht(nloc);
+    c->be->d2h(hk.data(), dk, (size_t)nloc * 8);
+    c->be->d2h(ht.data(), dt, (size_t)nloc * 8);
+    for (uint32_t i = 0; i < nloc; ++i) {
+        if (counts_out) counts_out[i] = hk[i];
+        if (tested_out) tested_out[i] = ht[i];
+    }
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
+                  uint32_t* zbits_out, int* any_out) {
+    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    // location: Aabb(bbox), or Obb::from(bbox).transformed(query_from_global.inverse())  (xray generation.rs:471-477)
+    pcv_location loc{};
+    double bmin[3], bmax[3];
+    for (int a = 0; a < 3; ++a) {
+        bmin[a] = std::fmin(tmin[a], tmax[a]);
+        bmax[a] = std::fmax(tmin[a], tmax[a]);
+    }
+    if (qfg) {
+        loc.kind = PCV_LOC_OBB;
+        double ginv[7];  // global_from_query = query_from_global.inverse(): conjugate, t' = rot_inv * (-t)
+        ginv[3] = -qfg[3];
+        ginv[4] = -qfg[4];
+        ginv[5] = -qfg[5];
+        ginv[6] = qfg[6];
+        const V3 nt = quat_rot(ginv, V3{-qfg[0], -qfg[1], -qfg[2]});
+        ginv[0] = nt.x;
+        ginv[1] = nt.y;
+        ginv[2] = nt.z;
+        // Obb::from(&aabb): centre = (min+max)*0.5, half = diag*0.5 (obb.rs:19-26); composed with the identity rotation
+        const V3 centre{(bmin[0] + bmax[0]) * 0.5, (bmin[1] + bmax[1]) * 0.5, (bmin[2] + bmax[2]) * 0.5};
+        const V3 sh = quat_rot(ginv, centre);
+        double* q = loc.query_from_obb;
+        q[0] = ginv[0] + sh.x;
+        q[1] = ginv[1] + sh.y;
+        q[2] = ginv[2] + sh.z;
+        q[3] = ginv[3];
+        q[4] = ginv[4];
+        q[5] = ginv[5];
+        q[6] = ginv[6];
+        double* qi = loc.obb_from_query;
+        qi[3] = -q[3];
+        qi[4] = -q[4];
+        qi[5] = -q[5];
+        qi[6] = q[6];
+        const V3 it = quat_rot(qi, V3{-q[0], -q[1], -q[2]});
+        qi[0] = it.x;
+        qi[1] = it.y;
+        qi[2] = it.z;
+        for (int a = 0; a < 3; ++a) loc.half_extent[a] = (bmax[a] - bmin[a]) * 0.5;
+    } else {
+        loc.kind = PCV_LOC_AABB;
+        for (int a = 0; a < 3; ++a) {
+            loc.aabb_min[a] = bmin[a];
+            loc.aabb_max[a] = bmax[a];
+        }
+    }
+    Scratch s(c);
+    std::vector<QueryGeom> geoms{make_query_geom(loc)};
+    std::vector<uint8_t> pass = run_sat(o, geoms, s, nullptr);
+    std::vector<QTile> tiles;
+    for (size_t i = 0; i < pass.size(); ++i)
+        if (pass[i] && o->nodes[i].num_points > 0) make_tiles(o, 0, (uint32_t)i, tiles);
+    const size_t npix = (size_t)w * h;
+    XrayArgs a{};
+    a.geom = geoms[0];
+    a.nodes = (const QNode*)o->d_qnodes;
+    a.tiles = s.upload(tiles.data(), tiles.size());
+    a.xyz = o->d_xyz;
+    for (int k = 0; k < 3; ++k) {
+        a.tmin[k] = bmin[k];
+        a.tdiag[k] = bmax[k] - bmin[k];
+    }
+    a.has_q = qfg ? 1 : 0;
+    if (qfg) memcpy(a.query_from_global, qfg, sizeof(double) * 7);
+    a.w = w;
+    a.h = h;
+    a.zbits = s.alloc<uint32_t>(npix * 32);
+    a.zover = s.alloc<uint8_t>(npix);
+    a.any = s.alloc<int>(1);
+    CU(cudaMemsetAsync(a.zbits, 0, npix * 128, c->stream));
+    CU(cudaMemsetAsync(a.zover, 0, npix, c->stream));
+    CU(cudaMemsetAsync(a.any, 0, 4, c->stream));
+    uint8_t grey[1026];
+    grey[0] = 0;
+    const double max_sat = std::log(1024.0);  // generation.rs:165-171
+    for (int n = 1; n <= 1025; ++n) {
+        const double v = (1. - std::log((double)n) / max_sat) * 255.;
+        grey[n] = v != v || v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)v);  // `as u8`
+    }
+    const uint8_t* dgrey = s.upload(grey, 1026);
+    uint8_t* drgba = s.alloc<uint8_t>(npix * 4);
+    if (!tiles.empty()) {
+        k_xray_accum<<<(uint32_t)tiles.size(), 256, 0, c->stream>>>(a);
+        c->be->launches++;
+    }
+    k_xray_resolve<<<(uint32_t)((npix + 255) / 256), 256, 0, c->stream>>>(a.zbits, a.zover, dgrey, (uint32_t)npix, drgba);
+    c->be->launches++;
+    CU(cudaGetLastError());
+    int any = 0;
+    c->be->d2h(&any, a.any, 4);
+    c->be->d2h(rgba_out, drgba, npix * 4);
+    if (zbits_out) c->be->d2h(zbits_out, a.zbits, npix * 128);
+    if (any_out) *any_out = any;
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_prefix_histogram_device(pcv_ctx*, const pcv_points*, double, const double*, const double*, uint32_t, uint64_t*) {
+    return fail(PCV_ERR_UNSUPPORTED, "not implemented yet");
+}
+int pcv_prefix_pack_device(pcv_ctx*, const pcv_points*, const uint64_t*, double, const double*, const double*, uint32_t, const int32_t*, uint32_t,
+                           double*, uint8_t*, float*, uint64_t*, uint64_t*) {
+    return fail(PCV_ERR_UNSUPPORTED, "not implemented yet");
+}
+
+}  // extern "C"
