@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — build_octree (+ frustum query) throughput on B200, one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W          the CUDA path (this repo)
+  python bench.py --impl reference --gpus N ...           the reference's CPU algorithm (oracle port) on host cores
+
+A step = one build_octree over one batch of synthetic points (BASELINE.json config 2: Gaussian clusters in a
+1024 m cube, resolution 1024/2^20 -> depth 20).  At N=1 the batch is 1e9 points; at N>1 every rank owns 1e9
+points of the same global index space (weak scaling; config 4), bucketed by octree path prefix with one NCCL
+all-to-all.  `value` = points / device time with the inputs already in HBM; `e2e` = the same build through the
+C-ABI host entry point: pinned host buffers -> H2D -> build -> D2H of the node arrays, all inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 1
+METRIC = "build_octree Mpoints/sec"
+UNIT = "Mpoints/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's own algorithm on the host cores: the oracle (C++ restatement of build_octree, same task
+    structure: serial root split, one task per split node, per-level parallel subsampling; in-memory variant, i.e.
+    without the reference's file round trips).  Each step builds a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    import oracle_api as O
+    import point_cloud_viewer_b200 as pcv
+
+    n = int(args.ref_points)
+    x, y, z, rgb = pcv.synth_points_host(pcv.SYNTH_GAUSS_CLUSTERS, SEED, 0, n)
+    bmin, bmax, res = pcv.synth_bbox(pcv.SYNTH_GAUSS_CLUSTERS)
+    cores = os.cpu_count() or 1
+    rgb3 = rgb.reshape(-1, 3)
+    for _ in range(args.warmup):
+        O.build(x, y, z, rgb3, res, bmin, bmax, num_threads=cores)
+    t = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        o = O.build(x, y, z, rgb3, res, bmin, bmax, num_threads=cores)
+        t.append(time.perf_counter() - t0)
+        del o
+    ms = sum(t) / len(t) * 1e3
+    v = n / (ms * 1e3)
+    sample = "first %d points of the same generator per step (in-memory oracle port, %d threads)" % (n, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "build_octree, Gaussian-cluster points (BASELINE config 2 generator), depth 20, CPU sample", "points_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def make_frusta(pcv, bmin, bmax, count, far, seed=7):
+    """eye uniform in the bbox, orientation = normalised 4-vector of Irwin-Hall variates,
+    Perspective3(aspect 1.0, fovy 1.2, near 0.1, far) as in point_cloud_test/src/queries.rs:38-44."""
+    import numpy as np
+
+    G = pcv.geometry
+    rng = np.random.default_rng(seed)
+    locs = []
+    persp = G.Perspective.new_fov(1.0, 1.2, 0.1, far)
+    for _ in range(count):
+        eye = bmin + rng.random(3) * (bmax - bmin)
+        q = rng.random((4, 12)).sum(1) - 6.0
+        q /= np.linalg.norm(q)
+        locs.append(G.frustum(G.Isometry(eye, q), persp))
+    return locs
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import point_cloud_viewer_b200 as pcv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = int(args.points)
+    kind = pcv.SYNTH_GAUSS_CLUSTERS
+    bmin, bmax, res = pcv.synth_bbox(kind)
+    ctx = pcv.Context(local, levels_per_pass=args.levels_per_pass)
+    x, y, z = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+    rgb = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+    ctx.synth_points_device(kind, SEED, rank * n, n, x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if world > 1:
+        from point_cloud_viewer_b200 import distributed as D
+
+        def step():
+            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
+    else:
+
+        def step():
+            return ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
+
+    for _ in range(args.warmup):
+        t = step()
+        t.free()
+    sampler = ClockSampler(local)
+    launches0 = ctx.kernel_launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    w0 = time.perf_counter()
+    dev_ms = 0.0
+    last = None
+    for _ in range(args.steps):
+        if last is not None:
+            last.free()
+        last = step()
+        dev_ms += ctx.last_build_stats()["ms_total"] if world == 1 else last.ms_total
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launch_count() - launches0
+    # device time of the K steps: CUDA events on the library's stream around every build, max over ranks
+    tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(tm[0]), float(tm[1])
+    ms_per_step = dev_ms / args.steps
+    value = world * n / (ms_per_step * 1e3)
+    stats = ctx.last_build_stats() if world == 1 else last.stats
+    nodes = len(last.nodes)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "build_octree on %d synthetic Gaussian-cluster points per GPU (BASELINE config %d), resolution 1024/2^20 (depth 20), XYZ f64 SoA + RGB" % (n, 2 if world == 1 else 4),
+            "points_per_gpu": n, "levels_per_pass": args.levels_per_pass, "max_points_per_node": 100000,
+            "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (27.0 * n / 1e9),
+            "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix, one NCCL all-to-all" % args.prefix_levels,
+        },
+        "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": int(launches), "octree_nodes": nodes, "deepest_level": int(stats["deepest_level"]),
+        "clocks": clocks,
+    }
+
+    if world == 1:
+        peak, peak_src = _peaks()
+        # ---- roofline of the dominant kernel: one extra build with CUDA events around every launch ----
+        ctx.set_profiling(True)
+        t = step()
+        t.free()
+        ks = ctx.kernel_stats()
+        ctx.set_profiling(False)
+        top = max(ks.items(), key=lambda kv: kv[1]["ms"])
+        tname, tst = top
+        achieved = tst["algorithmic_bytes"] / (tst["ms"] * 1e-3) / 1e9 if tst["ms"] > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(tname)
+        except Exception:
+            pass
+        out["roofline"] = {
+            "bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "launches": tst["launches"], "avg_launch_ms": tst["ms"] / max(1, tst["launches"]),
+            "algorithmic_bytes_per_launch": tst["algorithmic_bytes"] / max(1, tst["launches"]),
+            "note": "the descent inside k_hist/k_scatter is IEEE binary64 divide+FMA per level per axis (reference codec semantics): FP64-issue bound before HBM bound; see DESIGN.md",
+            "whole_build": {"algorithmic_bytes": int(stats["algorithmic_bytes"]), "achieved": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9,
+                            "frac": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9 / peak},
+            "kernels": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for k, v in ks.items()},
+        }
+
+        # ---- secondary metric: frustum-culled point query over the resident octree (BASELINE config 3) ----
+        try:
+            fq = {}
+            for label, far in (("far10", 10.0), ("far0.1E", 102.4)):
+                locs = make_frusta(pcv, bmin, bmax, args.frusta if far < 50 else max(1, args.frusta // 10), far)
+                last.query_batch_device(locs[:8])  # warm-up (tables, pool)
+                l0 = ctx.kernel_launch_count()
+                torch.cuda.synchronize()
+                q0 = time.perf_counter()
+                counts, tested = last.query_batch_device(locs)
+                torch.cuda.synchronize()
+                qms = (time.perf_counter() - q0) * 1e3
+                fq[label] = {"frusta": len(locs), "tested_points": int(tested.sum()), "returned_points": int(counts.sum()), "ms": qms,
+                             "Mpoints_per_s_tested": float(tested.sum()) / (qms * 1e3), "gpu_launches": int(ctx.kernel_launch_count() - l0)}
+            out["frustum_query"] = fq
+        except Exception as e:  # never lose the build line
+            out["frustum_query"] = {"error": str(e)[:200]}
+
+        # ---- e2e: the reference-facing call with HOST buffers (H2D + build + D2H inside the timed region) ----
+        last.free()
+        last = None
+        ne = n
+        try:
+            hx, hy, hz = [torch.empty(ne, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+            hrgb = torch.empty(ne * 3, dtype=torch.uint8, pin_memory=True)
+            hx.copy_(x[:ne])
+            hy.copy_(y[:ne])
+            hz.copy_(z[:ne])
+            hrgb.copy_(rgb[: 3 * ne])
+            del x, y, z, rgb
+            torch.cuda.empty_cache()
+            oxyz = torch.empty(int(ne * 12 + (1 << 24)), dtype=torch.uint8, pin_memory=True)
+            orgb = torch.empty(ne * 3, dtype=torch.uint8, pin_memory=True)
+
+            def e2e_step():
+                t = ctx.build_octree(hx.data_ptr(), hy.data_ptr(), hz.data_ptr(), hrgb.data_ptr(), res, bmin, bmax, n=ne)
+                assert t.xyz_bytes <= oxyz.numel()
+                t.download(xyz=oxyz.data_ptr(), rgb=orgb.data_ptr(), want_src=False)  # what build_octree leaves on disk: .xyz + .rgb + meta
+                b = (t.xyz_bytes + ne * 3 + 80 * len(t.nodes), len(t.nodes))
+                t.free()
+                return b
+
+            e2e_step()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            esteps = max(1, min(args.steps, 3))
+            for _ in range(esteps):
+                d2h, _ = e2e_step()
+            torch.cuda.synchronize()
+            ems = (time.perf_counter() - w0) * 1e3 / esteps
+            out["e2e"] = {"value": ne / (ems * 1e3), "unit": UNIT, "h2d_bytes_per_step": int(27 * ne), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems, "steps": esteps,
+                          "note": "pcv_build_octree(host SoA, pinned) + pcv_octree_download(pinned): node table, .xyz codes and .rgb of every node"}
+        except Exception as e:
+            out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": str(e)[:200]}
+
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_api as O
+
+            nc = int(args.cpu_points)
+            cx, cy, cz, crgb = pcv.synth_points_host(kind, SEED, 0, nc)
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            o = O.build(cx, cy, cz, crgb.reshape(-1, 3), res, bmin, bmax, num_threads=cores)
+            ct = time.perf_counter() - t0
+            del o
+            out["cpu_baseline"] = {"value": nc / ct / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "first %d points of the same generator, one build (in-memory oracle port of build_octree, %d threads, %.1f s)" % (nc, cores, ct)}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + str(e)[:160]}
+    else:
+        out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "e2e is measured at N=1"}
+        if last is not None:
+            last.free()
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=float, default=1e9, help="points per GPU per step")
+    ap.add_argument("--levels-per-pass", type=int, default=2)
+    ap.add_argument("--prefix-levels", type=int, default=2)
+    ap.add_argument("--frusta", type=int, default=1000)
+    ap.add_argument("--cpu-points", type=float, default=2e7)
+    ap.add_argument("--ref-points", type=float, default=5e6)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -183,6 +183,16 @@ typedef struct pcv_build_stats {
     float ms_chain_kernels;                          /* hist + scatter kernels only                */
 } pcv_build_stats;
 int pcv_last_build_stats(pcv_ctx* ctx, pcv_build_stats* out);
+/* Optional per-kernel timing: CUDA events on the context's stream around every launch of the build kernels.
+ * Off by default (the events serialise nothing but cost host time); turn on for a measurement build. */
+typedef struct pcv_kernel_stat {
+    char name[24];
+    uint64_t launches;
+    uint64_t algorithmic_bytes; /* bytes the launches had to move (reads of inputs/records + writes of records/outputs) */
+    double ms;
+} pcv_kernel_stat;
+int pcv_set_profiling(pcv_ctx* ctx, int on); /* also resets the accumulated statistics */
+int pcv_kernel_stats(pcv_ctx* ctx, pcv_kernel_stat* out, uint32_t cap, uint32_t* n_out);
 uint64_t pcv_kernel_launch_count(pcv_ctx* ctx); /* cumulative, all entry points                    */
 
 #ifdef __cplusplus

@@ -99,6 +99,15 @@ class Context:
         N.check(N.lib().pcv_last_build_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in N.BuildStats._fields_}
 
+    def set_profiling(self, on):
+        N.check(N.lib().pcv_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_stats(self):
+        arr = (N.KernelStat * 16)()
+        n = C.c_uint32()
+        N.check(N.lib().pcv_kernel_stats(self.h, arr, 16, C.byref(n)))
+        return {arr[i].name.decode(): dict(launches=arr[i].launches, algorithmic_bytes=arr[i].algorithmic_bytes, ms=arr[i].ms) for i in range(n.value)}
+
     def kernel_launch_count(self):
         return int(N.lib().pcv_kernel_launch_count(self.h))
 
@@ -186,12 +195,13 @@ class Octree:
         N.check(N.lib().pcv_octree_node_data(self.h, m["hi"], m["lo"], _p(xyz), _p(rgb), _p(inten), _p(src)))
         return xyz, rgb, inten, src
 
-    def download(self, xyz=None, rgb=None, intensity=None, src=None):
+    def download(self, xyz=None, rgb=None, intensity=None, src=None, want_src=True):
         xyz = np.zeros(max(self.xyz_bytes, 1), np.uint8) if xyz is None else xyz
         rgb = np.zeros(max(self.num_points * 3, 1), np.uint8) if rgb is None else rgb
         if intensity is None and self.has_intensity:
             intensity = np.zeros(self.num_points, np.float32)
-        src = np.zeros(max(self.num_points, 1), np.uint64) if src is None else src
+        if src is None and want_src:
+            src = np.zeros(max(self.num_points, 1), np.uint64)
         N.check(N.lib().pcv_octree_download(self.h, _p(xyz), _p(rgb), _p(intensity), _p(src)))
         return xyz, rgb, intensity, src
 

@@ -96,6 +96,10 @@ class BuildStats(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("ms", C.c_double)]
+
+
 # every symbol include/pcv.h declares: (name, restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _u64p = C.POINTER(C.c_uint64)
@@ -128,6 +132,8 @@ SYMBOLS = [
     ("pcv_synth_bbox", C.c_int, [C.c_int, _dp, _dp, _dp]),
     ("pcv_last_build_stats", C.c_int, [C.c_void_p, C.POINTER(BuildStats)]),
     ("pcv_kernel_launch_count", C.c_uint64, [C.c_void_p]),
+    ("pcv_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("pcv_kernel_stats", C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_uint32, C.POINTER(C.c_uint32)]),
 ]
 
 _lib = None

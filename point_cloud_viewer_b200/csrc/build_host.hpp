@@ -105,6 +105,7 @@ struct PassArgs {
     void* rec_next;
     void* arena;
     uint32_t ntiles, nactive, nchunks;
+    uint64_t npoints;  // points still being partitioned in this pass
     const TileDesc* d_tiles;
     const ActiveDesc* d_active;
     const ChunkDesc* d_chunks;
@@ -123,6 +124,7 @@ struct PlaceArgs {
     const DNode* d_nodes;
     const LeafTile* d_tiles;
     uint32_t ntiles;
+    uint64_t npoints, xyz_bytes;
     uint8_t* out_xyz;
     uint8_t* out_rgb;
     float* out_intensity;
@@ -321,6 +323,7 @@ class BuildPlan {
                 pa.ntiles = (uint32_t)tiles.size();
                 pa.nactive = (uint32_t)active.size();
                 pa.nchunks = (uint32_t)chunks.size();
+                pa.npoints = active_points;
                 pa.d_tiles = upload(tiles, scratch);
                 pa.d_active = upload(adesc, scratch);
                 pa.d_chunks = upload(chunks, scratch);
@@ -503,6 +506,8 @@ class BuildPlan {
         pl.d_nodes = upload(dn, scratch);
         pl.d_tiles = upload(lt, scratch);
         pl.ntiles = (uint32_t)lt.size();
+        pl.npoints = pts.n;
+        pl.xyz_bytes = algo_xyz;
         pl.out_xyz = R.d_xyz;
         pl.out_rgb = R.d_rgb;
         pl.out_intensity = R.d_intensity;

@@ -439,8 +439,47 @@ struct CudaBackend : Backend {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float ms_chain = 0.f;
-    bool time_chain = false;
+    // optional per-kernel timing (CUDA events on the launching stream around every launch)
+    enum { K_BBOX = 0, K_HIST, K_SCAN, K_SCATTER, K_PLACE, K_COUNT };
+    struct KStat {
+        uint64_t launches = 0, bytes = 0;
+        double ms = 0;
+    };
+    bool profile = false;
+    KStat kstat[K_COUNT];
+    struct Pending {
+        int k;
+        cudaEvent_t e0, e1;
+        uint64_t bytes;
+    };
+    std::vector<Pending> pending;
+    void prof_begin(int k, uint64_t bytes) {
+        if (!profile) return;
+        Pending p{k, nullptr, nullptr, bytes};
+        cudaEventCreate(&p.e0);
+        cudaEventCreate(&p.e1);
+        cudaEventRecord(p.e0, stream);
+        pending.push_back(p);
+    }
+    void prof_end() {
+        if (!profile) return;
+        cudaEventRecord(pending.back().e1, stream);
+    }
+    void prof_collect() {  // call after a stream synchronize
+        for (auto& p : pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p.e0, p.e1);
+            kstat[p.k].launches++;
+            kstat[p.k].ms += ms;
+            kstat[p.k].bytes += p.bytes;
+            cudaEventDestroy(p.e0);
+            cudaEventDestroy(p.e1);
+        }
+        pending.clear();
+    }
+    void prof_reset() {
+        for (auto& k : kstat) k = KStat();
+    }
 
     explicit CudaBackend(cudaStream_t s) : stream(s) {
         for (auto& e : ev) PCV_CUDA_CHECK(cudaEventCreate(&e));
@@ -473,6 +512,8 @@ struct CudaBackend : Backend {
 
     void hist(const PassArgs& a) override {
         const size_t sm = (size_t)a.nbins * 4;
+        const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
+        prof_begin(K_HIST, a.npoints * (a.root ? 24 : rec));
         if (a.root) {
             if (a.wide)
                 k_hist<true, true><<<a.ntiles, 256, sm, stream>>>(a);
@@ -484,19 +525,24 @@ struct CudaBackend : Backend {
             else
                 k_hist<false, false><<<a.ntiles, 256, sm, stream>>>(a);
         }
+        prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
     void scan(const PassArgs& a) override {
         const int th = a.nbins < 32 ? 32 : (a.nbins > 512 ? 512 : a.nbins);
+        prof_begin(K_SCAN, (uint64_t)a.ntiles * a.nbins * 12);
         k_scan_chunk_sums<<<a.nchunks, th, 0, stream>>>(a);
         k_scan_nodes<<<a.nactive, th, 0, stream>>>(a);
         k_scan_tiles<<<a.nchunks, th, 0, stream>>>(a);
+        prof_end();
         launches += 3;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
     void scatter(const PassArgs& a) override {
         const size_t sm = scatter_smem(a.nbins);
+        const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
+        prof_begin(K_SCATTER, a.npoints * ((a.root ? 24 : rec) + rec));
         if (a.root) {
             if (a.wide)
                 k_scatter<true, true><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
@@ -508,15 +554,18 @@ struct CudaBackend : Backend {
             else
                 k_scatter<false, false><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
         }
+        prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
     void place(const PlaceArgs& a) override {
         if (a.ntiles == 0) return;
+        prof_begin(K_PLACE, a.npoints * ((a.wide ? sizeof(RecW) : sizeof(RecN)) + 3 + 3 + 4 + (a.out_intensity ? 8 : 0)) + a.xyz_bytes);
         if (a.wide)
             k_place<true><<<a.ntiles, 256, 0, stream>>>(a);
         else
             k_place<false><<<a.ntiles, 256, 0, stream>>>(a);
+        prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
@@ -531,7 +580,9 @@ struct CudaBackend : Backend {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int blocks = (int)std::min<uint64_t>((uint64_t)sms * 8, (p.n + 255) / 256);
         double* d = (double*)dmalloc((size_t)blocks * 6 * 8);
+        prof_begin(K_BBOX, p.n * 24);
         k_bbox<<<blocks, 256, 0, stream>>>(p, d);
+        prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
         std::vector<double> h((size_t)blocks * 6);

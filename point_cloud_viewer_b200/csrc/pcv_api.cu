@@ -296,6 +296,40 @@ int pcv_last_build_stats(pcv_ctx* c, pcv_build_stats* out) {
 }
 uint64_t pcv_kernel_launch_count(pcv_ctx* c) { return c ? c->be->launches : 0; }
 
+int pcv_set_profiling(pcv_ctx* c, int on) {
+    if (!c) return fail(PCV_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->be->prof_collect();
+    c->be->prof_reset();
+    c->be->profile = on != 0;
+    return PCV_OK;
+}
+
+int pcv_kernel_stats(pcv_ctx* c, pcv_kernel_stat* out, uint32_t cap, uint32_t* n_out) {
+    if (!c || !n_out) return fail(PCV_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->be->prof_collect();
+    static const char* names[CudaBackend::K_COUNT] = {"k_bbox", "k_hist", "k_scan", "k_scatter", "k_place"};
+    uint32_t n = 0;
+    for (int k = 0; k < CudaBackend::K_COUNT; ++k) {
+        if (n < cap && out) {
+            pcv_kernel_stat& s = out[n];
+            memset(&s, 0, sizeof s);
+            snprintf(s.name, sizeof s.name, "%s", names[k]);
+            s.launches = c->be->kstat[k].launches;
+            s.algorithmic_bytes = c->be->kstat[k].bytes;
+            s.ms = c->be->kstat[k].ms;
+        }
+        ++n;
+    }
+    *n_out = n;
+    return PCV_OK;
+}
+
 int pcv_octree_info(const pcv_octree* o, uint64_t* num_nodes, uint64_t* num_points, uint64_t* xyz_bytes, double* resolution,
                     double bbox_min[3], double bbox_max[3], int* has_intensity) {
     if (!o) return fail(PCV_ERR_INVALID, "null octree");
