@@ -179,8 +179,9 @@ typedef struct pcv_build_stats {
     uint32_t deepest_level;
     uint64_t num_nodes;
     uint64_t algorithmic_bytes; /* 27*N + sum_nodes n*(3*bpc+3) (+8*N with intensity)             */
-    float ms_bbox, ms_partition, ms_place, ms_total; /* CUDA-event times on the context's stream   */
-    float ms_chain_kernels;                          /* hist + scatter kernels only                */
+    float ms_host_plan, ms_partition, ms_place, ms_total; /* ms_partition/place/total: CUDA events on the context's stream;
+                                                             ms_host_plan: host time spent planning passes (inside ms_total) */
+    float ms_host_wait;                                   /* host time blocked on the per-pass histogram read-back       */
 } pcv_build_stats;
 int pcv_last_build_stats(pcv_ctx* ctx, pcv_build_stats* out);
 /* Optional per-kernel timing: CUDA events on the context's stream around every launch of the build kernels.

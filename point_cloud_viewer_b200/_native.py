@@ -88,11 +88,11 @@ class BuildStats(C.Structure):
         ("deepest_level", C.c_uint32),
         ("num_nodes", C.c_uint64),
         ("algorithmic_bytes", C.c_uint64),
-        ("ms_bbox", C.c_float),
+        ("ms_host_plan", C.c_float),
         ("ms_partition", C.c_float),
         ("ms_place", C.c_float),
         ("ms_total", C.c_float),
-        ("ms_chain_kernels", C.c_float),
+        ("ms_host_wait", C.c_float),
     ]
 
 

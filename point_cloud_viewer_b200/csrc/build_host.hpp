@@ -21,6 +21,7 @@
 // contains only the CUDA one.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -80,6 +81,7 @@ struct BucketDesc {
 struct DNode {
     double m[3];
     double e;
+    double ry;                // RN(1/e)
     uint64_t off_in_parent;   // sum_{k'<k} ceil(n(P.k')/8)
     uint64_t out_point_off;
     uint64_t out_xyz_off;     // bytes
@@ -104,6 +106,10 @@ struct PassArgs {
     const void* rec_in;
     void* rec_next;
     void* arena;
+    // colour travels with the records (packed r | g<<8 | b<<16) so the final placement does not gather it
+    const uint32_t* col_in;
+    uint32_t* col_next;
+    uint32_t* col_arena;
     uint32_t ntiles, nactive, nchunks;
     uint64_t npoints;  // points still being partitioned in this pass
     const TileDesc* d_tiles;
@@ -121,6 +127,8 @@ struct PlaceArgs {
     bool wide;
     PointsView pts;
     const void* arena;
+    const uint32_t* col_arena;
+    int fast;  // LevelTable::fast
     const DNode* d_nodes;
     const LeafTile* d_tiles;
     uint32_t ntiles;
@@ -181,8 +189,11 @@ inline LevelTable make_level_table(double root_edge, double resolution) {
     double e = root_edge;
     t.last_level = kMaxLevels - 1;
     bool found = false;
+    t.fast = 1;
     for (int L = 0; L < kMaxLevels; ++L) {
         t.edge[L] = e;
+        t.ry[L] = 1.0 / e;  // RN(1/edge), for div_known
+        if (!div_known_ok(e)) t.fast = 0;
         t.enc[L] = (int8_t)position_encoding_for(e, resolution);
         // should_split_node (generation.rs:128-150): a node at level L >= 1 is split only if edge > resolution.
         if (!found && L >= 1 && !(e > resolution)) {
@@ -205,6 +216,7 @@ struct BuildResult {
     uint32_t* d_src = nullptr;
     uint32_t passes = 0;
     uint32_t deepest_level = 0;
+    double host_ms_plan = 0, host_ms_wait = 0;
     uint64_t algorithmic_bytes = 0;
     LevelTable lv;
     double root_min[3];
@@ -274,7 +286,9 @@ class BuildPlan {
         std::vector<Active> active{{0, 0, pts.n}};
         int L = 0;
         void* bufs[2] = {nullptr, nullptr};
+        uint32_t* cols[2] = {nullptr, nullptr};
         void* arena = be.dmalloc((size_t)pts.n * rec_bytes);
+        uint32_t* col_arena = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
         uint64_t arena_used = 0;
         int cur = -1;  // -1: raw input
         std::vector<void*> scratch;
@@ -285,6 +299,7 @@ class BuildPlan {
         be.mark(0);
         try {
             while (!active.empty()) {
+                const auto tp0 = std::chrono::steady_clock::now();
                 const int Gp = std::min(G, lv.last_level - L);
                 if (Gp < 1) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
                 const int nbins = 1 << (3 * Gp);
@@ -317,9 +332,15 @@ class BuildPlan {
                 pa.pts = pts;
                 pa.rec_in = cur < 0 ? nullptr : bufs[cur];
                 int nxt = cur < 0 ? 0 : 1 - cur;
-                if (!bufs[nxt]) bufs[nxt] = be.dmalloc((size_t)pts.n * rec_bytes);
+                if (!bufs[nxt]) {
+                    bufs[nxt] = be.dmalloc((size_t)pts.n * rec_bytes);
+                    cols[nxt] = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
+                }
                 pa.rec_next = bufs[nxt];
                 pa.arena = arena;
+                pa.col_in = cur < 0 ? nullptr : cols[cur];
+                pa.col_next = cols[nxt];
+                pa.col_arena = col_arena;
                 pa.ntiles = (uint32_t)tiles.size();
                 pa.nactive = (uint32_t)active.size();
                 pa.nchunks = (uint32_t)chunks.size();
@@ -338,7 +359,11 @@ class BuildPlan {
                 be.hist(pa);
                 be.scan(pa);
                 std::vector<uint64_t> bins((size_t)pa.nactive * nbins);
+                const auto tw0 = std::chrono::steady_clock::now();
+                R.host_ms_plan += std::chrono::duration<double, std::milli>(tw0 - tp0).count();
                 be.d2h(bins.data(), pa.d_node_bins, bins.size() * 8);
+                const auto tw1 = std::chrono::steady_clock::now();
+                R.host_ms_wait += std::chrono::duration<double, std::milli>(tw1 - tw0).count();
 
                 // ---- decide leaf / split for every descendant within Gp levels ----
                 std::vector<uint16_t> lut((size_t)pa.nactive * nbins, 0xFFFF);
@@ -420,6 +445,7 @@ class BuildPlan {
                 pa.d_buckets = upload(buckets, scratch);
                 be.scatter(pa);
                 free_scratch();
+                R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw1).count();
                 R.passes++;
                 active.swap(next_active);
                 cur = nxt;
@@ -428,11 +454,16 @@ class BuildPlan {
         } catch (...) {
             free_scratch();
             be.dfree(arena);
+            be.dfree(col_arena);
             for (void* b : bufs)
+                if (b) be.dfree(b);
+            for (uint32_t* b : cols)
                 if (b) be.dfree(b);
             throw;
         }
         for (void* b : bufs)
+            if (b) be.dfree(b);
+        for (uint32_t* b : cols)
             if (b) be.dfree(b);
         be.mark(1);
 
@@ -473,6 +504,7 @@ class BuildPlan {
         }
         if (poff != pts.n) {
             be.dfree(arena);
+            be.dfree(col_arena);
             throw BuildError(-2, "internal: subsample plan does not conserve points");
         }
         R.xyz_bytes = boff;
@@ -486,6 +518,7 @@ class BuildPlan {
             DNode& d = dn[i];
             for (int a = 0; a < 3; ++a) d.m[a] = x.m[a];
             d.e = x.e;
+            d.ry = 1.0 / x.e;
             d.off_in_parent = x.off_in_parent;
             d.out_point_off = x.out_point_off;
             d.out_xyz_off = x.out_xyz_off;
@@ -503,6 +536,8 @@ class BuildPlan {
         pl.wide = wide;
         pl.pts = pts;
         pl.arena = arena;
+        pl.col_arena = col_arena;
+        pl.fast = lv.fast;
         pl.d_nodes = upload(dn, scratch);
         pl.d_tiles = upload(lt, scratch);
         pl.ntiles = (uint32_t)lt.size();
@@ -516,6 +551,7 @@ class BuildPlan {
         be.mark(2);
         free_scratch();
         be.dfree(arena);
+        be.dfree(col_arena);
         return R;
     }
 };

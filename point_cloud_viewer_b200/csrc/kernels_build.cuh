@@ -154,9 +154,29 @@ __device__ __forceinline__ void load_position(const PassArgs& a, const TileDesc&
         uint64_t c[3];
         load_rec<WIDE>(a.rec_in, g, c, idx);
         const int enc = a.lv.enc[a.level];
+        if (a.lv.fast) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, enc);
+            for (int k = 0; k < 3; ++k) q[k] = decode1_fast(c[k], act.m[k], act.e, enc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, enc);
+        }
     }
+}
+
+// One descent step through the exact fast paths when the level table admits them (identical results).
+__device__ __forceinline__ Step descend_any(const LevelTable& lv, int child_level, double q[3], double m[3], double e_cur) {
+    if (lv.fast) return descend_fast(q, m, e_cur, lv.edge[child_level], lv.ry[child_level], lv.enc[child_level]);
+    return descend(q, m, e_cur, lv.edge[child_level], lv.enc[child_level]);
+}
+
+template <bool ROOT>
+__device__ __forceinline__ uint32_t load_colour(const PassArgs& a, uint64_t g) {
+    if (ROOT) {
+        const uint8_t* p = a.pts.rgb + 3 * g;
+        return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
+    return __ldg(a.col_in + g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,10 +196,9 @@ __global__ void __launch_bounds__(256) k_hist(const __grid_constant__ PassArgs a
         double e = act.e;
         unsigned bin = 0;
         for (int j = 1; j <= a.G; ++j) {
-            const double eh = a.lv.edge[a.level + j];
-            Step s = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+            Step s = descend_any(a.lv, a.level + j, q, m, e);
             bin = (bin << 3) | s.digit;
-            e = eh;
+            e = a.lv.edge[a.level + j];
         }
         atomicAdd(&sh_hist[bin], 1u);
     }
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
 
         uint64_t code[kScatterItems][3];
         uint32_t idxs[kScatterItems];
+        uint32_t cols[kScatterItems];
         uint32_t lbs[kScatterItems];
         uint32_t rank[kScatterItems];
         // phase 1: descent for this thread's items
@@ -307,16 +327,16 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
             if (i < t.count) {
                 double q[3], m[3] = {act.m[0], act.m[1], act.m[2]};
                 load_position<ROOT, WIDE>(a, t, act, i, q, idxs[s]);
+                cols[s] = load_colour<ROOT>(a, t.start + i);
                 double e = act.e;
                 unsigned bin = 0;
                 uint64_t cj[3][3];
 #pragma unroll
                 for (int j = 1; j <= 3; ++j) {
                     if (j <= a.G) {
-                        const double eh = a.lv.edge[a.level + j];
-                        Step st = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+                        Step st = descend_any(a.lv, a.level + j, q, m, e);
                         bin = (bin << 3) | st.digit;
-                        e = eh;
+                        e = a.lv.edge[a.level + j];
                         cj[j - 1][0] = st.code[0];
                         cj[j - 1][1] = st.code[1];
                         cj[j - 1][2] = st.code[2];
@@ -363,8 +383,9 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
             const uint32_t lb = lbs[s];
             if (lb != 0xFFFFu) {
                 const uint32_t dst = wc[warp * nb + lb] + rank[s];
-                void* buf = (meta[lb] >> 8) ? a.arena : a.rec_next;
-                store_rec<WIDE>(buf, dst, code[s], idxs[s]);
+                const bool leaf = (meta[lb] >> 8) != 0;
+                store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, code[s], idxs[s]);
+                (leaf ? a.col_arena : a.col_next)[dst] = cols[s];
             }
         }
         __syncthreads();
@@ -400,8 +421,13 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
             const DNode P = a.d_nodes[nd.parent];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
-                c[k] = encode1(q, P.m[k], P.e, P.enc);
+                if (a.fast) {
+                    const double q = decode1_fast(c[k], nd.m[k], nd.e, nd.enc);
+                    c[k] = encode1_fast(q, P.m[k], P.e, P.ry, P.enc);
+                } else {
+                    const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
+                    c[k] = encode1(q, P.m[k], P.e, P.enc);
+                }
             }
             j = nd.off_in_parent + (j >> 3);
             nd = P;
@@ -411,8 +437,13 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
             // the points that stay are rewritten once into the same cube (child_writer, generation.rs:234-238)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
-                c[k] = encode1(q, nd.m[k], nd.e, nd.enc);
+                if (a.fast) {
+                    const double q = decode1_fast(c[k], nd.m[k], nd.e, nd.enc);
+                    c[k] = encode1_fast(q, nd.m[k], nd.e, nd.ry, nd.enc);
+                } else {
+                    const double q = decode1(c[k], nd.m[k], nd.e, nd.enc);
+                    c[k] = encode1(q, nd.m[k], nd.e, nd.enc);
+                }
             }
             slot = j - (j >> 3) - 1;
         }
@@ -422,11 +453,11 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
         store_code(px, c[0], nd.enc);
         store_code(px + bpc, c[1], nd.enc);
         store_code(px + 2 * bpc, c[2], nd.enc);
-        const uint8_t* rs = a.pts.rgb + 3ull * idx;
+        const uint32_t col = __ldg(a.col_arena + lt.arena_start + i);
         uint8_t* rd = a.out_rgb + 3ull * dp;
-        rd[0] = __ldg(rs);
-        rd[1] = __ldg(rs + 1);
-        rd[2] = __ldg(rs + 2);
+        rd[0] = (uint8_t)col;
+        rd[1] = (uint8_t)(col >> 8);
+        rd[2] = (uint8_t)(col >> 16);
         a.out_src[dp] = idx;
         if (a.out_intensity) a.out_intensity[dp] = __ldg(a.pts.intensity + idx);
     }
@@ -487,6 +518,8 @@ struct CudaBackend : Backend {
     ~CudaBackend() override {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        if (pin) cudaFreeHost(pin);
+        if (pin_back) cudaFreeHost(pin_back);
     }
     void* dmalloc(size_t bytes) override {
         void* p = nullptr;
@@ -496,15 +529,41 @@ struct CudaBackend : Backend {
     void dfree(void* p) override {
         if (p) cudaFreeAsync(p, stream);
     }
+    // Host -> device staging through a pinned ring so that descriptor uploads are truly asynchronous (a pageable
+    // source would make cudaMemcpyAsync wait for all prior work of the stream).  The ring is recycled after a
+    // stream synchronize (d2h below, once per pass) or when it wraps.
+    uint8_t* pin = nullptr;
+    size_t pin_cap = 0, pin_off = 0;
     void h2d(void* d, const void* h, size_t bytes) override {
-        // staging copies come from pageable std::vector storage: the copy is complete (w.r.t. the host
-        // buffer) when the call returns.
-        PCV_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream));
-        PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (bytes == 0) return;
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (need > pin_cap / 2) {  // too big for the ring: grow it (rare) after draining the stream
+            PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (pin) cudaFreeHost(pin);
+            pin_cap = std::max<size_t>(need * 4, (size_t)64 << 20);
+            PCV_CUDA_CHECK(cudaMallocHost(&pin, pin_cap));
+            pin_off = 0;
+        }
+        if (pin_off + need > pin_cap) {
+            PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+            pin_off = 0;
+        }
+        std::memcpy(pin + pin_off, h, bytes);
+        PCV_CUDA_CHECK(cudaMemcpyAsync(d, pin + pin_off, bytes, cudaMemcpyHostToDevice, stream));
+        pin_off += need;
     }
+    uint8_t* pin_back = nullptr;
+    size_t pin_back_cap = 0;
     void d2h(void* h, const void* d, size_t bytes) override {
-        PCV_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream));
+        if (bytes > pin_back_cap) {
+            if (pin_back) cudaFreeHost(pin_back);
+            pin_back_cap = std::max<size_t>(bytes * 2, (size_t)8 << 20);
+            PCV_CUDA_CHECK(cudaMallocHost(&pin_back, pin_back_cap));
+        }
+        PCV_CUDA_CHECK(cudaMemcpyAsync(pin_back, d, bytes, cudaMemcpyDeviceToHost, stream));
         PCV_CUDA_CHECK(cudaStreamSynchronize(stream));
+        std::memcpy(h, pin_back, bytes);
+        pin_off = 0;  // everything staged before this point has been consumed
     }
     void mark(int what) override { cudaEventRecord(ev[what], stream); }
 

@@ -233,6 +233,8 @@ static int build_impl(pcv_ctx* c, const PointsView& v, double resolution, const 
     s.deepest_level = R.deepest_level;
     s.num_nodes = R.nodes.size();
     s.algorithmic_bytes = R.algorithmic_bytes;
+    s.ms_host_plan = (float)R.host_ms_plan;
+    s.ms_host_wait = (float)R.host_ms_wait;
     cudaEventElapsedTime(&s.ms_total, e0, e1);
     if (v.n) {
         cudaEventElapsedTime(&s.ms_partition, be.ev[0], be.ev[1]);

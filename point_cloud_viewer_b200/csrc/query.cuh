@@ -198,7 +198,7 @@ __device__ __forceinline__ bool eval_point(const CullArgs& a, const QueryGeom& g
     const int bpc = enc_bytes(nd.enc);
     const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)i * 3 * bpc;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) p[k] = decode1(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+    for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);  // == decode1, integer-built unit fraction
     bool keep = loc_contains(g, p[0], p[1], p[2]);
     if (a.nfilt) {
         const double v = (double)a.intensity[nd.point_off + i];  // iterator.rs:82-91: attribute as f64, closed interval
@@ -288,6 +288,30 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* v, uint32_t n, unsi
     if (threadIdx.x == 0) *total_out = carry;
 }
 
+// Work list of the batched query: one QTile per kQueryTile points of every (location, node) pair that passed.
+// The order of the list is irrelevant for the batched form (only per-location totals and the compacted survivors
+// are produced), so tiles are appended with one atomic per pair.
+__global__ void __launch_bounds__(256) k_count_tiles(const uint8_t* __restrict__ pass, const QNode* __restrict__ nodes, uint32_t nnodes,
+                                                     uint64_t npairs, unsigned long long* __restrict__ total) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < npairs && pass[i]) c = (nodes[i % nnodes].n + kQueryTile - 1) / kQueryTile;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+__global__ void __launch_bounds__(256) k_fill_tiles(const uint8_t* __restrict__ pass, const QNode* __restrict__ nodes, uint32_t nnodes,
+                                                    uint64_t npairs, unsigned long long* __restrict__ cursor, QTile* __restrict__ tiles) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs || !pass[i]) return;
+    const uint32_t node = (uint32_t)(i % nnodes), loc = (uint32_t)(i / nnodes);
+    const uint32_t n = nodes[node].n;
+    if (n == 0) return;
+    const uint32_t nt = (n + kQueryTile - 1) / kQueryTile;
+    const unsigned long long base = atomicAdd(cursor, (unsigned long long)nt);
+    for (uint32_t k = 0; k < nt; ++k) tiles[base + k] = QTile{loc, node, k * kQueryTile, min(kQueryTile, n - k * kQueryTile)};
+}
+
 // per-location totals: kept[loc] += keep counts, tested[loc] += tile counts
 __global__ void k_tile_totals(const QTile* tiles, const uint32_t* keep_counts, uint32_t ntiles, unsigned long long* kept,
                               unsigned long long* tested) {
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ Xray
         const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)(t.first + i) * 3 * bpc;
         double p[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) p[k] = decode1(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+        for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);  // == decode1, integer-built unit fraction
         if (!loc_contains(a.geom, p[0], p[1], p[2])) continue;
         seen = true;
         if (a.has_q) {  // generation.rs:493-497

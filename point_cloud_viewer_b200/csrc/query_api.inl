@@ -75,6 +75,25 @@ std::vector<uint32_t> level_starts(const pcv_octree* o) {
     return ls;
 }
 
+// pass[loc][node] for nloc locations (BFS semantics), left on the device.
+uint8_t* run_sat_device(pcv_octree* o, const std::vector<QueryGeom>& geoms, Scratch& s, const QueryGeom** d_geoms_out) {
+    pcv_ctx* c = o->ctx;
+    const uint32_t nn = (uint32_t)o->nodes.size(), nloc = (uint32_t)geoms.size();
+    const QueryGeom* dg = s.upload(geoms.data(), geoms.size());
+    if (d_geoms_out) *d_geoms_out = dg;
+    if (nn == 0 || nloc == 0) return nullptr;
+    std::vector<uint32_t> ls = level_starts(o);
+    const uint32_t* dls = s.upload(ls.data(), ls.size());
+    uint8_t* drel = s.alloc<uint8_t>((size_t)nn * nloc);
+    uint8_t* dpass = s.alloc<uint8_t>((size_t)nn * nloc);
+    dim3 grid((nn + 255) / 256, nloc);
+    k_sat_nodes<<<grid, 256, 0, c->stream>>>(dg, (const QNode*)o->d_qnodes, nn, drel);
+    k_propagate<<<nloc, 1024, 0, c->stream>>>((const QNode*)o->d_qnodes, dls, (int)ls.size() - 1, nn, drel, dpass);
+    c->be->launches += 2;
+    CU(cudaGetLastError());
+    return dpass;
+}
+
 // pass[loc][node] for nloc locations (BFS semantics).  Returns host matrix.
 std::vector<uint8_t> run_sat(pcv_octree* o, const std::vector<QueryGeom>& geoms, Scratch& s, const QueryGeom** d_geoms_out) {
     pcv_ctx* c = o->ctx;
@@ -184,24 +203,24 @@ struct CullResult {
     uint32_t* d_src = nullptr;
 };
 
-// count -> scan -> write for a list of tiles.  Output buffers come from `s`.
+// count -> scan -> write for a list of tiles (host list, or a device list when d_tiles != nullptr).
 CullResult run_cull(pcv_octree* o, const QueryGeom* d_geoms, const std::vector<QTile>& tiles, const pcv_interval* filters, uint32_t nfilt,
-                    Scratch& s, unsigned long long* d_kept, unsigned long long* d_tested) {
+                    Scratch& s, unsigned long long* d_kept, unsigned long long* d_tested, const QTile* d_tiles = nullptr, uint64_t n_dtiles = 0) {
     pcv_ctx* c = o->ctx;
     CullResult r;
-    if (tiles.empty()) return r;
+    if (tiles.empty() && n_dtiles == 0) return r;
     CullArgs a{};
     a.geoms = d_geoms;
     a.nodes = (const QNode*)o->d_qnodes;
-    a.tiles = s.upload(tiles.data(), tiles.size());
+    a.tiles = d_tiles ? d_tiles : s.upload(tiles.data(), tiles.size());
     a.xyz = o->d_xyz;
     a.rgb = o->d_rgb;
     a.intensity = o->d_intensity;
     a.src = o->d_src;
     a.filters = nfilt ? s.upload(filters, nfilt) : nullptr;
     a.nfilt = nfilt;
-    a.tile_keep = s.alloc<uint32_t>(tiles.size());
-    const uint32_t nt = (uint32_t)tiles.size();
+    const uint32_t nt = d_tiles ? (uint32_t)n_dtiles : (uint32_t)tiles.size();
+    a.tile_keep = s.alloc<uint32_t>(nt);
     k_cull<false><<<nt, 256, 0, c->stream>>>(a);
     if (d_kept) k_tile_totals<<<(nt + 255) / 256, 256, 0, c->stream>>>(a.tiles, a.tile_keep, nt, d_kept, d_tested);
     unsigned long long* d_total = s.alloc<unsigned long long>(1);
@@ -395,16 +414,31 @@ int pcv_query_batch_device(const pcv_octree* oc, const pcv_location* locs, uint3
     }
     Scratch s(c);
     const QueryGeom* dg = nullptr;
-    std::vector<uint8_t> pass = run_sat(o, geoms, s, &dg);
-    const size_t nn = o->nodes.size();
-    std::vector<QTile> tiles;
-    for (uint32_t l = 0; l < nloc; ++l)
-        for (size_t i = 0; i < nn; ++i)
-            if (pass[(size_t)l * nn + i] && o->nodes[i].num_points > 0) make_tiles(o, l, (uint32_t)i, tiles);
+    const uint8_t* dpass = run_sat_device(o, geoms, s, &dg);
+    const uint32_t nn = (uint32_t)o->nodes.size();
     std::vector<unsigned long long> zeros(nloc, 0);
     unsigned long long* dk = s.upload(zeros.data(), nloc);
     unsigned long long* dt = s.upload(zeros.data(), nloc);
-    run_cull(o, dg, tiles, filters, nfilt, s, dk, dt);
+    if (dpass) {
+        // work list built on the device: count tiles, allocate, fill (one atomic per (location, node) pair)
+        const uint64_t npairs = (uint64_t)nn * nloc;
+        unsigned long long two[2] = {0, 0};
+        unsigned long long* dcnt = s.upload(two, 2);
+        const uint32_t gb = (uint32_t)((npairs + 255) / 256);
+        k_count_tiles<<<gb, 256, 0, c->stream>>>(dpass, (const QNode*)o->d_qnodes, nn, npairs, dcnt);
+        c->be->launches++;
+        unsigned long long ntl = 0;
+        c->be->d2h(&ntl, dcnt, 8);
+        if (ntl >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "work list too large (%llu tiles); split the batch", ntl);
+        if (ntl) {
+            QTile* dtiles = s.alloc<QTile>(ntl);
+            k_fill_tiles<<<gb, 256, 0, c->stream>>>(dpass, (const QNode*)o->d_qnodes, nn, npairs, dcnt + 1, dtiles);
+            c->be->launches++;
+            CU(cudaGetLastError());
+            std::vector<QTile> none;
+            run_cull(o, dg, none, filters, nfilt, s, dk, dt, dtiles, ntl);
+        }
+    }
     std::vector<unsigned long long> hk(nloc), ht(nloc);
     c->be->d2h(hk.data(), dk, (size_t)nloc * 8);
     c->be->d2h(ht.data(), dt, (size_t)nloc * 8);

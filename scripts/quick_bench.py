@@ -19,7 +19,7 @@ for it in range(3):
     tree = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
     t1 = time.time()
     s = ctx.last_build_stats()
-    print("build n=%d G=%d wall %.1f ms | total %.1f partition %.1f place %.1f ms | passes %d launches %d nodes %d deepest %d | %.1f Mpts/s | algo GB/s %.0f" % (
-        n, G, (t1 - t0) * 1e3, s["ms_total"], s["ms_partition"], s["ms_place"], s["passes"], s["kernel_launches"], s["num_nodes"], s["deepest_level"],
+    print("build n=%d G=%d wall %.1f ms | total %.1f partition %.1f place %.1f ms (host plan %.1f wait %.1f) | passes %d launches %d nodes %d deepest %d | %.1f Mpts/s | algo GB/s %.0f" % (
+        n, G, (t1 - t0) * 1e3, s["ms_total"], s["ms_partition"], s["ms_place"], s["ms_host_plan"], s["ms_host_wait"], s["passes"], s["kernel_launches"], s["num_nodes"], s["deepest_level"],
         n / s["ms_total"] / 1e3, s["algorithmic_bytes"] / s["ms_total"] / 1e6))
     tree.free()

@@ -47,15 +47,20 @@ struct CpuBackend : Backend {
         } else {
             uint64_t c[3];
             load_rec(a.rec_in, g, a.wide, c, idx);
-            for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, a.lv.enc[a.level]);
+            for (int k = 0; k < 3; ++k)
+                q[k] = a.lv.fast ? decode1_fast(c[k], act.m[k], act.e, a.lv.enc[a.level]) : decode1(c[k], act.m[k], act.e, a.lv.enc[a.level]);
         }
+    }
+    static uint32_t load_colour(const PassArgs& a, uint64_t g) {
+        if (a.root) return (uint32_t)a.pts.rgb[3 * g] | ((uint32_t)a.pts.rgb[3 * g + 1] << 8) | ((uint32_t)a.pts.rgb[3 * g + 2] << 16);
+        return a.col_in[g];
     }
     static unsigned run_chain(const PassArgs& a, const ActiveDesc& act, double q[3], uint64_t cj[3][3]) {
         double m[3] = {act.m[0], act.m[1], act.m[2]}, e = act.e;
         unsigned bin = 0;
         for (int j = 1; j <= a.G; ++j) {
             const double eh = a.lv.edge[a.level + j];
-            Step s = descend(q, m, e, eh, a.lv.enc[a.level + j]);
+            Step s = a.lv.fast ? descend_fast(q, m, e, eh, a.lv.ry[a.level + j], a.lv.enc[a.level + j]) : descend(q, m, e, eh, a.lv.enc[a.level + j]);
             bin = (bin << 3) | s.digit;
             e = eh;
             for (int k = 0; k < 3; ++k) cj[j - 1][k] = s.code[k];
@@ -144,8 +149,10 @@ struct CpuBackend : Backend {
                 const unsigned bin = run_chain(a, act, q, cj);
                 const uint32_t lb = a.d_lut[(size_t)t.active * nb + bin];
                 const int keep = meta[lb] & 0xFF;
-                void* buf = (meta[lb] >> 8) ? a.arena : a.rec_next;
-                store_rec(buf, base[lb]++, a.wide, cj[keep - 1], idx);
+                const bool leaf = (meta[lb] >> 8) != 0;
+                const uint32_t dst = base[lb]++;
+                store_rec(leaf ? a.arena : a.rec_next, dst, a.wide, cj[keep - 1], idx);
+                (leaf ? a.col_arena : a.col_next)[dst] = load_colour(a, t.start + i);
             }
         }
     }
@@ -161,20 +168,27 @@ struct CpuBackend : Backend {
                 DNode nd = leaf;
                 while (nd.parent >= 0 && (j & 7) == 0) {
                     const DNode P = a.d_nodes[nd.parent];
-                    for (int k = 0; k < 3; ++k) c[k] = encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), P.m[k], P.e, P.enc);
+                    for (int k = 0; k < 3; ++k)
+                        c[k] = a.fast ? encode1_fast(decode1_fast(c[k], nd.m[k], nd.e, nd.enc), P.m[k], P.e, P.ry, P.enc)
+                                      : encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), P.m[k], P.e, P.enc);
                     j = nd.off_in_parent + (j >> 3);
                     nd = P;
                 }
                 uint64_t slot = j;
                 if (nd.parent >= 0) {
-                    for (int k = 0; k < 3; ++k) c[k] = encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), nd.m[k], nd.e, nd.enc);
+                    for (int k = 0; k < 3; ++k)
+                        c[k] = a.fast ? encode1_fast(decode1_fast(c[k], nd.m[k], nd.e, nd.enc), nd.m[k], nd.e, nd.ry, nd.enc)
+                                      : encode1(decode1(c[k], nd.m[k], nd.e, nd.enc), nd.m[k], nd.e, nd.enc);
                     slot = j - (j >> 3) - 1;
                 }
                 const uint64_t dp = nd.out_point_off + slot;
                 const int bpc = enc_bytes(nd.enc);
                 uint8_t* px = a.out_xyz + nd.out_xyz_off + slot * 3 * (uint64_t)bpc;
                 for (int k = 0; k < 3; ++k) std::memcpy(px + k * bpc, &c[k], (size_t)bpc);  // little-endian host
-                std::memcpy(a.out_rgb + 3 * dp, a.pts.rgb + 3ull * idx, 3);
+                const uint32_t col = a.col_arena[lt.arena_start + i];
+                a.out_rgb[3 * dp] = (uint8_t)col;
+                a.out_rgb[3 * dp + 1] = (uint8_t)(col >> 8);
+                a.out_rgb[3 * dp + 2] = (uint8_t)(col >> 16);
                 a.out_src[dp] = idx;
                 if (a.out_intensity) a.out_intensity[dp] = a.pts.intensity[idx];
             }
@@ -239,5 +253,79 @@ void tb_free(void* h) {
     std::free(t->R.d_intensity);
     std::free(t->R.d_src);
     delete t;
+}
+}
+
+// ---- exactness checks of the fast paths in chain.h (host execution) -----------------------------------------
+extern "C" {
+// exhaustive: unit_frac<8>/<16>(v) == (double)v / 255.0 | 65535.0 for every v; returns the number of mismatches
+uint64_t tb_check_unit_frac() {
+    uint64_t bad = 0;
+    for (uint32_t v = 0; v <= 255; ++v) bad += pcv::f64_to_bits(pcv::unit_frac<8>(v)) != pcv::f64_to_bits((double)v / 255.0);
+    for (uint32_t v = 0; v <= 65535; ++v) bad += pcv::f64_to_bits(pcv::unit_frac<16>(v)) != pcv::f64_to_bits((double)v / 65535.0);
+    return bad;
+}
+// random + adversarial: div_known(a, b, 1/b) == a / b.  Divisors are edge-like (E * 2^-L), numerators are the
+// differences the descent produces (multiples of an ulp near the cube) plus near-tie constructions a = RN((k+0.5ulp) * b).
+uint64_t tb_check_div(uint64_t n, uint64_t seed) {
+    uint64_t bad = 0, s = seed;
+    auto next = [&]() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t x = s;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        return x ^ (x >> 31);
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t r0 = next(), r1 = next(), r2 = next();
+        double b = 1.0 + (double)(r0 >> 11) * 0x1.0p-53;          // significand
+        b = std::ldexp(b, (int)(r1 % 60) - 40);                     // edges from 2^-40 to 2^19
+        if (!pcv::div_known_ok(b)) continue;
+        const double y = 1.0 / b;
+        double a;
+        switch (r2 & 3) {
+            case 0: a = b * ((double)(r1 >> 11) * 0x1.0p-53); break;                       // t uniform in [0,1)
+            case 1: a = b * ((double)(r2 >> 40) / 65535.0); break;                          // near code lattice
+            case 2: {                                                                       // near-tie quotients
+                double q = 1.0 + (double)(r1 >> 12) * 0x1.0p-52;
+                a = q * b;
+                a = std::nextafter(a, (r2 & 4) ? 0.0 : 4.0 * a);
+                break;
+            }
+            default: a = std::ldexp(1.0 + (double)(r2 >> 11) * 0x1.0p-53, (int)(r1 % 200) - 100) * ((r2 & 8) ? -1.0 : 1.0);  // wide range
+        }
+        bad += pcv::f64_to_bits(pcv::div_known(a, b, y)) != pcv::f64_to_bits(a / b);
+    }
+    // guard paths: zero, tiny, huge, inf, nan numerators
+    const double specials[] = {0.0, -0.0, 1e-320, 1e-200, 1e200, INFINITY, -INFINITY, NAN};
+    for (double a : specials) {
+        const double b = 3.7, y = 1.0 / b, r = pcv::div_known(a, b, y), w = a / b;
+        bad += !((r != r && w != w) || pcv::f64_to_bits(r) == pcv::f64_to_bits(w));
+    }
+    return bad;
+}
+// encode/decode fast == plain for random cubes at ECEF-like offsets, all encodings
+uint64_t tb_check_codec(uint64_t n, uint64_t seed) {
+    uint64_t bad = 0, s = seed;
+    auto next = [&]() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t x = s;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        return x ^ (x >> 31);
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t r0 = next(), r1 = next(), r2 = next();
+        const double edge = std::ldexp(1.0 + (double)(r0 >> 11) * 0x1.0p-53, (int)(r1 % 30) - 12);
+        if (!pcv::div_known_ok(edge)) continue;
+        const double mn = ((double)(int64_t)(r1 >> 20) - 8.0e12) * 1e-6;  // up to +-8e6 (ECEF scale)
+        const double v = mn + edge * (((double)(r2 >> 11) * 0x1.0p-53) * 1.002 - 0.001);  // slightly outside too
+        for (int enc = 1; enc <= 4; ++enc) {
+            const uint64_t c0 = pcv::encode1(v, mn, edge, enc), c1 = pcv::encode1_fast(v, mn, edge, 1.0 / edge, enc);
+            bad += c0 != c1;
+            bad += pcv::f64_to_bits(pcv::decode1(c0, mn, edge, enc)) != pcv::f64_to_bits(pcv::decode1_fast(c0, mn, edge, enc));
+        }
+    }
+    return bad;
 }
 }
