@@ -111,7 +111,7 @@ PCV_HD double decode1(uint64_t bits, double mn, double edge, int enc) {
 // significand is read off the repeated pattern; the discarded tail is periodic and non-zero, hence
 // never an exact tie: round up iff the first discarded bit is set.
 template <int K>
-PCV_HD double unit_frac(uint32_t v) {
+PCV_HD double unit_frac_int(uint32_t v) {
     const uint32_t M = (1u << K) - 1u;
     if (v == 0u) return 0.0;
     if (v >= M) return 1.0;
@@ -126,6 +126,22 @@ PCV_HD double unit_frac(uint32_t v) {
     const uint64_t mant = (S >> 11) + ((S >> 10) & 1ull);        // 53 bits incl. the leading one (may carry to 2^53)
     // value = 1.f * 2^-(lz+1): biased exponent 1022 - lz; adding `mant` (bit 52 set) bumps the field by one
     return bits_to_f64(((uint64_t)(1021 - lz) << 52) + mant);
+}
+
+// Same value with three FP64 instructions: q0 = RN(v*y), q = RN(q0 + (v - q0*M)*y) with y = RN(1/M).  For the two
+// divisors that occur (255, 65535) this is verified EXHAUSTIVELY against v / M for every code v (tests/test_chain_exact.py),
+// so no proof obligation remains.  int -> f64 is the exact magic-number conversion (no I2F on the XU pipe).
+template <int K>
+PCV_HD double unit_frac(uint32_t v) {
+    const double M = K == 8 ? 255.0 : 65535.0;
+    const double y = K == 8 ? (1.0 / 255.0) : (1.0 / 65535.0);
+#if defined(__CUDA_ARCH__)
+    const double a = __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#else
+    const double a = (double)v;
+#endif
+    const double q0 = a * y;
+    return fma(fma(-q0, M, a), y, q0);
 }
 
 // a / b, correctly rounded, given y = RN(1/b) computed once per divisor on the host.

@@ -261,8 +261,14 @@ extern "C" {
 // exhaustive: unit_frac<8>/<16>(v) == (double)v / 255.0 | 65535.0 for every v; returns the number of mismatches
 uint64_t tb_check_unit_frac() {
     uint64_t bad = 0;
-    for (uint32_t v = 0; v <= 255; ++v) bad += pcv::f64_to_bits(pcv::unit_frac<8>(v)) != pcv::f64_to_bits((double)v / 255.0);
-    for (uint32_t v = 0; v <= 65535; ++v) bad += pcv::f64_to_bits(pcv::unit_frac<16>(v)) != pcv::f64_to_bits((double)v / 65535.0);
+    for (uint32_t v = 0; v <= 255; ++v) {
+        bad += pcv::f64_to_bits(pcv::unit_frac<8>(v)) != pcv::f64_to_bits((double)v / 255.0);
+        bad += pcv::f64_to_bits(pcv::unit_frac_int<8>(v)) != pcv::f64_to_bits((double)v / 255.0);
+    }
+    for (uint32_t v = 0; v <= 65535; ++v) {
+        bad += pcv::f64_to_bits(pcv::unit_frac<16>(v)) != pcv::f64_to_bits((double)v / 65535.0);
+        bad += pcv::f64_to_bits(pcv::unit_frac_int<16>(v)) != pcv::f64_to_bits((double)v / 65535.0);
+    }
     return bad;
 }
 // random + adversarial: div_known(a, b, 1/b) == a / b.  Divisors are edge-like (E * 2^-L), numerators are the
