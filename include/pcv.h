@@ -159,11 +159,25 @@ int pcv_xray_tile(const pcv_octree* o, const double tile_min[3], const double ti
  * buffers.  The exchange itself is one NCCL all-to-all issued by the host layer. */
 int pcv_prefix_histogram_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
                                 const double bbox_max[3], uint32_t k, uint64_t* counts_out /* 8^k, host */);
-int pcv_prefix_pack_device(pcv_ctx* ctx, const pcv_points* dev_points, const uint64_t* dev_global_index, double resolution,
+int pcv_prefix_pack_device(pcv_ctx* ctx, const pcv_points* dev_points, const uint64_t* dev_global_index /* or NULL */,
+                           uint64_t global_index_base /* used when dev_global_index == NULL: index = base + i */, double resolution,
                            const double bbox_min[3], const double bbox_max[3], uint32_t k,
                            const int32_t* cell_to_rank /* 8^k, host */, uint32_t nranks, double* dev_xyz_out /* n*3 AoS */,
                            uint8_t* dev_rgb_out, float* dev_intensity_out, uint64_t* dev_index_out,
                            uint64_t* rank_counts_out /* nranks, host */);
+/* Local part of a sharded build: like pcv_build_octree_device, but nodes of levels <= k take their split decision from
+ * the GLOBAL counts (`prefix_counts`: levels 1..k concatenated, 8 + 64 + .. entries, host), and the nodes of level k-1
+ * collect the every-8th points of their local children for pcv_assemble_top. */
+int pcv_build_octree_sharded_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
+                                    const double bbox_max[3], uint32_t k, const uint64_t* prefix_counts, pcv_octree** out);
+/* n(X): size of node X at the moment it is subsampled into its parent (needed from every level-k node by the assembly). */
+int pcv_octree_node_nsub(const pcv_octree* o, uint64_t id_high, uint64_t id_low, uint64_t* nsub_out);
+/* Nodes of levels 0..k-1 from the gathered collector content (host buffers; level k-1 nodes in index order, inside a
+ * node child order, positions as node-file bytes in the collector's encoding).  src_index of the result = position in
+ * the gathered arrays. */
+int pcv_assemble_top(pcv_ctx* ctx, double resolution, const double bbox_min[3], const double bbox_max[3], uint32_t k,
+                     const uint64_t* prefix_counts, const uint64_t* unit_nsub /* 8^k */, const void* xyz_codes, const uint8_t* rgb,
+                     const float* intensity, uint64_t npoints, pcv_octree** out);
 
 /* ---- synthetic inputs for benchmarks / parity tests (integer-only, counter based) ----------- */
 enum { PCV_SYNTH_SLAB_ECEF = 1, PCV_SYNTH_GAUSS_CLUSTERS = 2 };

@@ -120,14 +120,31 @@ class Context:
         N.check(N.lib().pcv_prefix_histogram_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(counts)))
         return counts
 
-    def prefix_pack_device(self, x, y, z, rgb, intensity, gidx, n, resolution, bbox_min, bbox_max, k, cell_to_rank, nranks, out_xyz, out_rgb,
-                           out_intensity, out_idx, stride=1):
+    def prefix_pack_device(self, x, y, z, rgb, intensity, gidx, gidx_base, n, resolution, bbox_min, bbox_max, k, cell_to_rank, nranks, out_xyz,
+                           out_rgb, out_intensity, out_idx, stride=1):
         pts = N.Points(_p(x), _p(y), _p(z), stride, _p(rgb), _p(intensity), int(n))
         c2r = np.ascontiguousarray(cell_to_rank, np.int32)
         counts = np.zeros(nranks, np.uint64)
-        N.check(N.lib().pcv_prefix_pack_device(self.h, C.byref(pts), _p(gidx), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(c2r), nranks,
-                                               _p(out_xyz), _p(out_rgb), _p(out_intensity), _p(out_idx), _p(counts)))
+        N.check(N.lib().pcv_prefix_pack_device(self.h, C.byref(pts), _p(gidx), int(gidx_base), float(resolution), _d3(bbox_min), _d3(bbox_max), k,
+                                               _p(c2r), nranks, _p(out_xyz), _p(out_rgb), _p(out_intensity), _p(out_idx), _p(counts)))
         return counts
+
+    def build_octree_sharded_device(self, xyz_ptr, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
+        """Local part of a sharded build: AoS xyz (n*3 f64) device pointer; prefix_counts = global counts of levels 1..k."""
+        pts = N.Points(xyz_ptr, xyz_ptr + 8, xyz_ptr + 16, 3, rgb_ptr, intensity_ptr, int(n))
+        pc = np.ascontiguousarray(prefix_counts, np.uint64)
+        out = C.c_void_p()
+        N.check(N.lib().pcv_build_octree_sharded_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(pc), C.byref(out)))
+        return Octree(self, out)
+
+    def assemble_top(self, resolution, bbox_min, bbox_max, k, prefix_counts, unit_nsub, xyz_codes, rgb, intensity):
+        pc = np.ascontiguousarray(prefix_counts, np.uint64)
+        un = np.ascontiguousarray(unit_nsub, np.uint64)
+        npts = len(rgb) // 3
+        out = C.c_void_p()
+        N.check(N.lib().pcv_assemble_top(self.h, float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(pc), _p(un), _p(xyz_codes), _p(rgb), _p(intensity),
+                                         npts, C.byref(out)))
+        return Octree(self, out)
 
 
 def synth_points_host(kind, seed, first, n):
@@ -194,6 +211,12 @@ class Octree:
         src = np.zeros(n, np.uint64)
         N.check(N.lib().pcv_octree_node_data(self.h, m["hi"], m["lo"], _p(xyz), _p(rgb), _p(inten), _p(src)))
         return xyz, rgb, inten, src
+
+    def node_nsub(self, name):
+        m = self.nodes[name]
+        v = C.c_uint64()
+        N.check(N.lib().pcv_octree_node_nsub(self.h, m["hi"], m["lo"], C.byref(v)))
+        return v.value
 
     def download(self, xyz=None, rgb=None, intensity=None, src=None, want_src=True):
         xyz = np.zeros(max(self.xyz_bytes, 1), np.uint8) if xyz is None else xyz

@@ -228,11 +228,23 @@ struct BuildError : std::runtime_error {
     BuildError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
 };
 
+// Multi-GPU sharding: this context builds only the sub-trees below some level-k cells.  `counts` holds the
+// GLOBAL point counts of every cell of levels 1..k (level j at offset (8^j - 8) / 7), so that nodes above level k take
+// the same split decision on every rank; nodes of level k-1 ("collectors") keep the every-8th points of their local
+// children (encoded in the collector's cube, in child order) for the top-of-tree assembly on one rank.
+struct ShardSpec {
+    int k = 0;
+    const uint64_t* counts = nullptr;
+    static size_t level_offset(int level) { return (((size_t)1 << (3 * level)) - 8) / 7; }
+    uint64_t count_at(int level, uint64_t index) const { return counts[level_offset(level) + index]; }
+};
+
 class BuildPlan {
    public:
     Backend& be;
     uint64_t max_points;
     int G;
+    ShardSpec shard;
     BuildPlan(Backend& b, uint64_t max_points_per_node, int levels_per_pass)
         : be(b), max_points(max_points_per_node ? max_points_per_node : 100000), G(levels_per_pass) {
         if (G < 1 || G > 3) G = 3;
@@ -406,7 +418,8 @@ class BuildPlan {
                             c.m[1] = (k & 2) ? p.m[1] + c.e : p.m[1];
                             c.m[2] = (k & 1) ? p.m[2] + c.e : p.m[2];
                             c.enc = lv.enc[c.level];
-                            bool split = cnt > max_points && c.e > resolution;  // generation.rs:128-150
+                            const uint64_t decision_cnt = (shard.k && c.level <= shard.k) ? shard.count_at(c.level, (uint64_t)c.index) : cnt;
+                            bool split = decision_cnt > max_points && c.e > resolution;  // generation.rs:128-150
                             if (split && c.level >= kMaxLevels - 1)
                                 throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
                             c.leaf = !split;
@@ -481,9 +494,11 @@ class BuildPlan {
                     off += (c.n_sub + 7) / 8;  // every 8th point by current index: ceil(n/8)
                 }
                 x.n_sub = off;
+                if (shard.k && x.level < shard.k - 1) x.n_sub = 0;  // above the collectors: assembled elsewhere
             }
         }
-        for (auto& x : nodes) x.final_count = x.parent < 0 ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
+        auto is_collector = [&](const HNode& x) { return shard.k && x.level == shard.k - 1; };
+        for (auto& x : nodes) x.final_count = (x.parent < 0 || is_collector(x)) ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
 
         // ---- output layout: nodes sorted by NodeId (level << 120 | index) ----
         R.sorted.resize(nodes.size());
@@ -522,7 +537,7 @@ class BuildPlan {
             d.off_in_parent = x.off_in_parent;
             d.out_point_off = x.out_point_off;
             d.out_xyz_off = x.out_xyz_off;
-            d.parent = x.parent;
+            d.parent = is_collector(x) ? -1 : x.parent;  // a collector ends the up-walk like the root does
             d.enc = x.enc;
             if (x.leaf)
                 for (uint64_t o = 0; o < x.count; o += kPlaceTile)
@@ -555,5 +570,170 @@ class BuildPlan {
         return R;
     }
 };
+
+// Top-of-tree assembly for the sharded build: the nodes of levels 0..k-1, whose content is what their children gave up
+// (every 8th point) - children being the level-k unit roots (built on their owner ranks) or other top nodes.
+//   counts      global point counts of the cells of levels 1..k (ShardSpec layout)
+//   unit_nsub   n(X) of every level-k cell when it is subsampled into its parent (0 for empty cells)
+//   xyz/rgb/intensity: the collectors' gathered content (level k-1 nodes in index order, inside a node child order
+//               0..7, inside a child rank order), positions as node-file bytes in the COLLECTOR's encoding.
+// The place kernel then walks those points up exactly as in a single-GPU build.
+inline BuildResult assemble_top(Backend& be, double resolution, const double bmin[3], const double bmax[3], int k, const uint64_t* counts,
+                                const uint64_t* unit_nsub, const uint8_t* xyz, const uint8_t* rgb, const float* intensity, uint64_t npoints) {
+    if (k < 1 || k > 3) throw BuildError(-1, "prefix levels must be 1..3");
+    if (npoints >= 0xFFFFFFFFull) throw BuildError(-6, "too many points in the top assembly");
+    BuildResult R;
+    R.n = npoints;
+    const double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
+    for (int a = 0; a < 3; ++a) R.root_min[a] = bmin[a];
+    R.root_edge = E;
+    R.lv = make_level_table(E, resolution);
+    const LevelTable& lv = R.lv;
+    ShardSpec sp;
+    sp.k = k;
+    sp.counts = counts;
+    uint64_t total = 0;
+    for (uint64_t c = 0; c < 8; ++c) total += sp.count_at(1, c);
+    if (total == 0) return R;
+    bool wide = false;
+    for (int L = 1; L <= lv.last_level; ++L) wide = wide || lv.enc[L] == ENC_F64;
+
+    std::vector<HNode>& nodes = R.nodes;
+    HNode r{};
+    r.parent = -1;
+    for (int q = 0; q < 8; ++q) r.child[q] = -1;
+    for (int a = 0; a < 3; ++a) r.m[a] = bmin[a];
+    r.e = E;
+    r.enc = lv.enc[0];
+    r.count = total;
+    nodes.push_back(r);
+    for (size_t i = 0; i < nodes.size(); ++i) {  // breadth first: levels 0..k-2 get their existing children
+        if (nodes[i].level >= k - 1) continue;
+        for (int c = 0; c < 8; ++c) {
+            const HNode p = nodes[i];
+            const uint64_t cidx = ((uint64_t)p.index << 3) + (uint64_t)c;
+            const uint64_t cnt = sp.count_at(p.level + 1, cidx);
+            if (cnt == 0) continue;
+            HNode x{};
+            x.level = p.level + 1;
+            x.index = cidx;
+            x.parent = (int)i;
+            for (int q = 0; q < 8; ++q) x.child[q] = -1;
+            x.count = cnt;
+            x.e = lv.edge[x.level];
+            x.m[0] = (c & 4) ? p.m[0] + x.e : p.m[0];
+            x.m[1] = (c & 2) ? p.m[1] + x.e : p.m[1];
+            x.m[2] = (c & 1) ? p.m[2] + x.e : p.m[2];
+            x.enc = lv.enc[x.level];
+            nodes[i].child[c] = (int)nodes.size();
+            nodes.push_back(x);
+        }
+    }
+    // n(X) bottom-up; collectors (level k-1) sum over the level-k unit roots
+    std::vector<uint64_t> unit_off(nodes.size() * 8, 0);
+    for (size_t i = nodes.size(); i-- > 0;) {
+        HNode& x = nodes[i];
+        uint64_t off = 0;
+        if (x.level == k - 1) {
+            for (int c = 0; c < 8; ++c) {
+                unit_off[i * 8 + c] = off;
+                off += (unit_nsub[((uint64_t)x.index << 3) + (uint64_t)c] + 7) / 8;
+            }
+        } else {
+            for (int c = 0; c < 8; ++c) {
+                if (x.child[c] < 0) continue;
+                nodes[x.child[c]].off_in_parent = off;
+                off += (nodes[x.child[c]].n_sub + 7) / 8;
+            }
+        }
+        x.n_sub = off;
+    }
+    for (auto& x : nodes) x.final_count = x.parent < 0 ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
+    R.sorted.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) R.sorted[i] = (int)i;
+    std::sort(R.sorted.begin(), R.sorted.end(), [&](int a, int b) {
+        if (nodes[a].level != nodes[b].level) return nodes[a].level < nodes[b].level;
+        return nodes[a].index < nodes[b].index;
+    });
+    uint64_t poff = 0, boff = 0, arena_total = 0;
+    for (int i : R.sorted) {
+        HNode& x = nodes[i];
+        x.out_point_off = poff;
+        boff = (boff + 15) & ~15ull;
+        x.out_xyz_off = boff;
+        poff += x.final_count;
+        boff += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
+        if (x.level == k - 1) {
+            x.arena_off = arena_total;
+            arena_total += x.n_sub;
+        }
+    }
+    if (arena_total != npoints || poff != npoints) throw BuildError(-1, "top assembly: gathered point count does not match the unit sizes");
+    R.xyz_bytes = boff;
+
+    // records from the gathered node-file bytes (collector encoding), in arena order == gathered order
+    const int cenc = lv.enc[k - 1], bpc = enc_bytes(cenc);
+    const size_t rec_bytes = wide ? sizeof(RecW) : sizeof(RecN);
+    std::vector<uint8_t> recs((size_t)npoints * rec_bytes);
+    std::vector<uint32_t> cols(npoints);
+    for (uint64_t i = 0; i < npoints; ++i) {
+        uint64_t c[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) std::memcpy(&c[a], xyz + (i * 3 + a) * bpc, (size_t)bpc);
+        if (wide) {
+            RecW w{{c[0], c[1], c[2]}, (uint32_t)i, 0};
+            std::memcpy(&recs[i * rec_bytes], &w, sizeof w);
+        } else {
+            RecN w{{(uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2]}, (uint32_t)i};
+            std::memcpy(&recs[i * rec_bytes], &w, sizeof w);
+        }
+        cols[i] = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+    }
+    std::vector<void*> scratch;
+    auto up = [&](const void* h, size_t bytes) {
+        void* d = be.dmalloc(bytes ? bytes : 16);
+        scratch.push_back(d);
+        if (bytes) be.h2d(d, h, bytes);
+        return d;
+    };
+    std::vector<DNode> dn(nodes.size());
+    std::vector<LeafTile> lt;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const HNode& x = nodes[i];
+        DNode& d = dn[i];
+        for (int a = 0; a < 3; ++a) d.m[a] = x.m[a];
+        d.e = x.e;
+        d.ry = 1.0 / x.e;
+        d.off_in_parent = x.off_in_parent;
+        d.out_point_off = x.out_point_off;
+        d.out_xyz_off = x.out_xyz_off;
+        d.parent = x.parent;
+        d.enc = x.enc;
+        if (x.level == k - 1)
+            for (uint64_t o = 0; o < x.n_sub; o += kPlaceTile)
+                lt.push_back(LeafTile{x.arena_off + o, o, (uint32_t)i, (uint32_t)std::min<uint64_t>(kPlaceTile, x.n_sub - o)});
+    }
+    PlaceArgs pl{};
+    pl.wide = wide;
+    pl.pts = PointsView{nullptr, nullptr, nullptr, 1, nullptr, intensity ? (const float*)up(intensity, (size_t)npoints * 4) : nullptr, npoints};
+    pl.arena = up(recs.data(), recs.size());
+    pl.col_arena = (const uint32_t*)up(cols.data(), cols.size() * 4);
+    pl.fast = lv.fast;
+    pl.d_nodes = (const DNode*)up(dn.data(), dn.size() * sizeof(DNode));
+    pl.d_tiles = (const LeafTile*)up(lt.data(), lt.size() * sizeof(LeafTile));
+    pl.ntiles = (uint32_t)lt.size();
+    pl.npoints = npoints;
+    pl.xyz_bytes = boff;
+    R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
+    R.d_rgb = (uint8_t*)be.dmalloc(std::max<uint64_t>(npoints * 3, 16));
+    R.d_src = (uint32_t*)be.dmalloc(std::max<uint64_t>(npoints * 4, 16));
+    R.d_intensity = intensity ? (float*)be.dmalloc(std::max<uint64_t>(npoints * 4, 16)) : nullptr;
+    pl.out_xyz = R.d_xyz;
+    pl.out_rgb = R.d_rgb;
+    pl.out_intensity = R.d_intensity;
+    pl.out_src = R.d_src;
+    be.place(pl);
+    for (void* p : scratch) be.dfree(p);
+    return R;
+}
 
 }  // namespace pcv

@@ -28,6 +28,7 @@ struct pcv_octree {
     bool has_intensity = false;
     uint64_t n = 0, xyz_bytes = 0;
     std::vector<pcv_node_meta> nodes;                       // sorted by NodeId
+    std::vector<uint64_t> nsub;                             // n(X) when X is subsampled into its parent
     std::map<std::pair<uint64_t, uint64_t>, uint32_t> idx;  // (hi, lo) -> position in `nodes`
     uint8_t* d_xyz = nullptr;
     uint8_t* d_rgb = nullptr;

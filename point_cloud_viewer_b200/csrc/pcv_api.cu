@@ -11,6 +11,7 @@
 #include "../../include/pcv.h"
 #include "disk_io.hpp"
 #include "octree_obj.hpp"
+#include "kernels_shard.cuh"
 #include "query.cuh"
 #include "synth.cuh"
 
@@ -204,12 +205,13 @@ static pcv_octree* octree_from_result(pcv_ctx* c, BuildResult& R, double resolut
         m.xyz_byte_offset = x.out_xyz_off;
         o->idx[{m.id_high, m.id_low}] = (uint32_t)o->nodes.size();
         o->nodes.push_back(m);
+        o->nsub.push_back(x.n_sub);
     }
     return o;
 }
 
 static int build_impl(pcv_ctx* c, const PointsView& v, double resolution, const double bmin_in[3], const double bmax_in[3],
-                      pcv_octree** out) {
+                      pcv_octree** out, const ShardSpec* shard = nullptr) {
     double bmin[3], bmax[3];
     for (int a = 0; a < 3; ++a) {
         bmin[a] = std::fmin(bmin_in[a], bmax_in[a]);
@@ -223,6 +225,7 @@ static int build_impl(pcv_ctx* c, const PointsView& v, double resolution, const 
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, c->stream));
     BuildPlan plan(be, c->cfg.max_points_per_node, (int)c->cfg.levels_per_pass);
+    if (shard) plan.shard = *shard;
     BuildResult R = plan.run(v, resolution, bmin, bmax);
     CU(cudaEventRecord(e1, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -617,3 +620,4 @@ int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* res
 }  // extern "C"
 
 #include "query_api.inl"
+#include "shard_api.inl"

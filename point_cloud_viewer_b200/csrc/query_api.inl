@@ -556,12 +556,4 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     API_CATCH
 }
 
-int pcv_prefix_histogram_device(pcv_ctx*, const pcv_points*, double, const double*, const double*, uint32_t, uint64_t*) {
-    return fail(PCV_ERR_UNSUPPORTED, "not implemented yet");
-}
-int pcv_prefix_pack_device(pcv_ctx*, const pcv_points*, const uint64_t*, double, const double*, const double*, uint32_t, const int32_t*, uint32_t,
-                           double*, uint8_t*, float*, uint64_t*, uint64_t*) {
-    return fail(PCV_ERR_UNSUPPORTED, "not implemented yet");
-}
-
 }  // extern "C"

@@ -1,0 +1,138 @@
+// shard_api.inl — multi-GPU sharding entry points (included at the end of pcv_api.cu).
+
+namespace {
+
+PrefixArgs make_prefix_args(const pcv_points* dp, double resolution, const double bmin_in[3], const double bmax_in[3], uint32_t k) {
+    if (k < 1 || k > 3) throw BuildError(PCV_ERR_INVALID, "prefix levels k must be 1..3");
+    if (!(resolution > 0.0)) throw BuildError(PCV_ERR_INVALID, "resolution must be > 0");
+    PrefixArgs a{};
+    a.pts = view_of(dp);
+    double bmin[3], bmax[3];
+    for (int i = 0; i < 3; ++i) {
+        bmin[i] = std::fmin(bmin_in[i], bmax_in[i]);
+        bmax[i] = std::fmax(bmin_in[i], bmax_in[i]);
+        a.root_min[i] = bmin[i];
+    }
+    const double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
+    a.lv = make_level_table(E, resolution);
+    a.k = (int)k;
+    a.nbins = 1 << (3 * k);
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
+                                uint64_t* counts_out) {
+    if (!c || !dp || !bmin || !bmax || !counts_out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    PrefixArgs a = make_prefix_args(dp, resolution, bmin, bmax, k);
+    std::vector<unsigned long long> h((size_t)a.nbins, 0);
+    if (a.pts.n) {
+        unsigned long long* d = (unsigned long long*)c->be->dmalloc((size_t)a.nbins * 8);
+        CU(cudaMemsetAsync(d, 0, (size_t)a.nbins * 8, c->stream));
+        const int blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, (a.pts.n + 255) / 256);
+        k_prefix_hist<<<blocks, 256, (size_t)a.nbins * 4, c->stream>>>(a, d);
+        c->be->launches++;
+        CU(cudaGetLastError());
+        c->be->d2h(h.data(), d, (size_t)a.nbins * 8);
+        c->be->dfree(d);
+    }
+    for (int i = 0; i < a.nbins; ++i) counts_out[i] = h[(size_t)i];
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgidx, uint64_t gidx_base, double resolution, const double bmin[3],
+                           const double bmax[3], uint32_t k, const int32_t* cell_to_rank, uint32_t nranks, double* out_xyz, uint8_t* out_rgb,
+                           float* out_intensity, uint64_t* out_idx, uint64_t* rank_counts_out) {
+    if (!c || !dp || !bmin || !bmax || !cell_to_rank || !out_xyz || !out_rgb || !out_idx || !rank_counts_out)
+        return fail(PCV_ERR_INVALID, "null argument");
+    if (nranks == 0 || nranks > (uint32_t)kMaxRanks) return fail(PCV_ERR_INVALID, "nranks must be 1..%d", kMaxRanks);
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    PackArgs a{};
+    a.p = make_prefix_args(dp, resolution, bmin, bmax, k);
+    for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = 0;
+    const uint64_t n = a.p.pts.n;
+    if (n == 0) return PCV_OK;
+    if (n >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-2 points per context");
+    if (!a.p.pts.rgb) return fail(PCV_ERR_INVALID, "color is mandatory");
+    for (int i = 0; i < a.p.nbins; ++i)
+        if (cell_to_rank[i] < 0 || cell_to_rank[i] >= (int32_t)nranks) return fail(PCV_ERR_INVALID, "cell_to_rank[%d] out of range", i);
+    Scratch s(c);
+    a.cell_to_rank = s.upload(cell_to_rank, (size_t)a.p.nbins);
+    a.nranks = nranks;
+    a.ntiles = (uint32_t)((n + kPackTile - 1) / kPackTile);
+    a.dest = s.alloc<uint8_t>(n);
+    a.counts = s.alloc<uint32_t>((size_t)nranks * a.ntiles);
+    a.gidx_in = dgidx;
+    a.gidx_base = gidx_base;
+    a.out_xyz = out_xyz;
+    a.out_rgb = out_rgb;
+    a.out_intensity = a.p.pts.intensity ? out_intensity : nullptr;
+    a.out_idx = out_idx;
+    k_pack_count<<<a.ntiles, 256, 0, c->stream>>>(a);
+    unsigned long long* dtot = s.alloc<unsigned long long>(1);
+    // per-rank totals before the scan overwrites the counts: read back the flat array's rank boundaries afterwards
+    k_scan_u32<<<1, 1024, 0, c->stream>>>(a.counts, nranks * a.ntiles, dtot);
+    k_pack_scatter<<<a.ntiles, 256, 0, c->stream>>>(a);
+    c->be->launches += 3;
+    CU(cudaGetLastError());
+    // rank r's first slot = exclusive prefix at (r, tile 0); counts follow from consecutive starts
+    std::vector<uint32_t> starts(nranks);
+    for (uint32_t r = 0; r < nranks; ++r) c->be->d2h(&starts[r], a.counts + (size_t)r * a.ntiles, 4);
+    for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = (r + 1 < nranks ? starts[r + 1] : (uint32_t)n) - starts[r];
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_build_octree_sharded_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
+                                    const uint64_t* prefix_counts, pcv_octree** out) {
+    if (!c || !dp || !bmin || !bmax || !prefix_counts || !out) return fail(PCV_ERR_INVALID, "null argument");
+    if (k < 1 || k > 3) return fail(PCV_ERR_INVALID, "prefix levels k must be 1..3");
+    *out = nullptr;
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ShardSpec sp;
+    sp.k = (int)k;
+    sp.counts = prefix_counts;
+    return build_impl(c, view_of(dp), resolution, bmin, bmax, out, &sp);
+    API_CATCH
+}
+
+int pcv_octree_node_nsub(const pcv_octree* o, uint64_t hi, uint64_t lo, uint64_t* nsub_out) {
+    if (!o || !nsub_out) return fail(PCV_ERR_INVALID, "null argument");
+    const int i = o->find(hi, lo);
+    if (i < 0 || (size_t)i >= o->nsub.size()) return fail(PCV_ERR_NOT_FOUND, "node %s not found", node_name(hi, lo).c_str());
+    *nsub_out = o->nsub[(size_t)i];
+    return PCV_OK;
+}
+
+int pcv_assemble_top(pcv_ctx* c, double resolution, const double bmin_in[3], const double bmax_in[3], uint32_t k, const uint64_t* prefix_counts,
+                     const uint64_t* unit_nsub, const void* xyz_codes, const uint8_t* rgb, const float* intensity, uint64_t npoints, pcv_octree** out) {
+    if (!c || !bmin_in || !bmax_in || !prefix_counts || !unit_nsub || !out || (npoints && (!xyz_codes || !rgb)))
+        return fail(PCV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    double bmin[3], bmax[3];
+    for (int a = 0; a < 3; ++a) {
+        bmin[a] = std::fmin(bmin_in[a], bmax_in[a]);
+        bmax[a] = std::fmax(bmin_in[a], bmax_in[a]);
+    }
+    BuildResult R = assemble_top(*c->be, resolution, bmin, bmax, (int)k, prefix_counts, unit_nsub, (const uint8_t*)xyz_codes, rgb, intensity, npoints);
+    CU(cudaStreamSynchronize(c->stream));
+    *out = octree_from_result(c, R, resolution, bmin, bmax, intensity != nullptr);
+    return PCV_OK;
+    API_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+"""Multi-GPU build_octree: points shard by octree path prefix, one all-to-all.
+
+Every rank holds a contiguous slice of the global point index space.  The split phase of the reference is independent
+below any octree prefix and the subsample phase only couples a parent with its 8 children, so:
+
+  1. all-reduce the 8^k histogram of level-k prefix cells (first k steps of the re-quantising descent on the raw
+     positions - the cell the single-GPU build would route the point to);
+  2. greedily balance the non-empty cells over the ranks (largest first);
+  3. stable pack by destination rank, ONE all-to-all (xyz, rgb, intensity, global index); receivers concatenate in
+     source-rank order, which is global index order, i.e. the reference's stable stream order;
+  4. every rank builds the sub-trees of its cells independently (global bounding cube; the nodes above level k take
+     their split decision from the global counts);
+  5. the <= 1 + 8 + 64 nodes above level k are assembled on rank 0 from the children's every-8th points (collected,
+     already encoded in the parent's cube, by the level k-1 "collector" nodes of every rank).
+
+The compute steps are CUDA kernels behind the C ABI (`CudaOps`); the collectives are torch.distributed (NCCL on GPUs).
+The orchestration below is backend-neutral so that tests can run it on 2 CPU processes over gloo with the test-only
+sequential stand-ins for the kernels.
+"""
+import numpy as np
+
+from . import ENC_BYTES
+
+
+# ---- pure planning helpers ----------------------------------------------------------------------------------------
+def level_counts(counts_k, k):
+    """Counts of the cells of levels 1..k from the level-k histogram."""
+    c = np.asarray(counts_k, np.uint64)
+    return [c.reshape(8 ** j, -1).sum(1).astype(np.uint64) for j in range(1, k + 1)]
+
+
+def concat_counts(levels):
+    return np.concatenate(levels).astype(np.uint64)
+
+
+def usable_prefix_levels(counts_k, k, root_edge, resolution, max_points):
+    """Largest k' <= k such that every non-empty node of levels 1..k'-1 is split by the reference's rule
+    (count > MAX_POINTS_PER_NODE and edge > resolution, generation.rs:128-150), i.e. no leaf sits above the shard level."""
+    levels = level_counts(counts_k, k)
+    ok = 1
+    edge = root_edge
+    for j in range(1, k):
+        edge = edge / 2.0
+        c = levels[j - 1]
+        nz = c[c > 0]
+        if len(nz) and (nz > max_points).all() and edge > resolution:
+            ok = j + 1
+        else:
+            break
+    return ok
+
+
+def assign_cells(counts, nranks):
+    """Longest-processing-time greedy: cells by decreasing count (ties: lower cell first) to the least loaded rank
+    (ties: lower rank).  Deterministic, identical on every rank.  Empty cells -> rank 0."""
+    counts = np.asarray(counts, np.uint64)
+    order = sorted(range(len(counts)), key=lambda c: (-int(counts[c]), c))
+    load = [0] * nranks
+    out = np.zeros(len(counts), np.int32)
+    for c in order:
+        if counts[c] == 0:
+            continue
+        r = min(range(nranks), key=lambda i: (load[i], i))
+        out[c] = r
+        load[r] += int(counts[c])
+    return out
+
+
+# ---- communication over torch.distributed ---------------------------------------------------------------------------
+class TorchComm:
+    def __init__(self, device):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.device = device
+
+    def all_reduce_sum_u64(self, arr):
+        import torch
+
+        t = torch.from_numpy(np.asarray(arr, np.uint64).astype(np.int64)).to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy().astype(np.uint64)
+
+    def all_reduce_minmax(self, mn, mx):
+        import torch
+
+        a = torch.tensor(list(mn), dtype=torch.float64, device=self.device)
+        b = torch.tensor(list(mx), dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(a, op=self.dist.ReduceOp.MIN)
+        self.dist.all_reduce(b, op=self.dist.ReduceOp.MAX)
+        return a.cpu().numpy(), b.cpu().numpy()
+
+    def exchange_counts(self, send_counts):
+        import torch
+
+        s = torch.from_numpy(np.asarray(send_counts, np.int64)).to(self.device)
+        r = torch.empty_like(s)
+        self.dist.all_to_all_single(r, s)
+        return r.cpu().numpy()
+
+    def all_to_all(self, tensor, send_counts, recv_counts):
+        import torch
+
+        out = torch.empty((int(np.sum(recv_counts)),) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        self.dist.all_to_all_single(out, tensor.contiguous(), output_split_sizes=[int(v) for v in recv_counts], input_split_sizes=[int(v) for v in send_counts])
+        return out
+
+    def all_gather_objects(self, obj):
+        lst = [None] * self.world
+        self.dist.all_gather_object(lst, obj)
+        return lst
+
+
+# ---- CUDA implementation of the compute steps ---------------------------------------------------------------------
+class CudaOps:
+    """x, y, z: torch cuda float64 tensors (SoA); rgb: uint8 (n*3); intensity: float32 or None."""
+
+    def __init__(self, ctx, x, y, z, rgb, intensity, resolution, bmin, bmax):
+        self.ctx, self.x, self.y, self.z, self.rgb, self.intensity = ctx, x, y, z, rgb, intensity
+        self.res, self.bmin, self.bmax = resolution, bmin, bmax
+        self.n = x.numel()
+        self.device = x.device
+
+    def local_bbox(self):
+        return self.ctx.bbox(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), n=self.n, device=True)
+
+    def prefix_histogram(self, k):
+        return self.ctx.prefix_histogram_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.n, self.res, self.bmin, self.bmax, k)
+
+    def pack(self, k, cell_to_rank, nranks, index_base):
+        import torch
+
+        n = self.n
+        xyz = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        rgb = torch.empty((n, 3), dtype=torch.uint8, device=self.device)
+        inten = torch.empty(n, dtype=torch.float32, device=self.device) if self.intensity is not None else None
+        idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        counts = self.ctx.prefix_pack_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.rgb.data_ptr(),
+                                             self.intensity.data_ptr() if self.intensity is not None else None, None, index_base, n, self.res, self.bmin,
+                                             self.bmax, k, cell_to_rank, nranks, xyz.data_ptr(), rgb.data_ptr(), inten.data_ptr() if inten is not None else None,
+                                             idx.data_ptr())
+        return xyz, rgb, inten, idx, counts.astype(np.int64)
+
+    def build_sharded(self, xyz, rgb, inten, k, prefix_counts):
+        n = xyz.shape[0]
+        return self.ctx.build_octree_sharded_device(xyz.data_ptr() if n else 0, rgb.data_ptr() if n else 0, inten.data_ptr() if (inten is not None and n) else None, n,
+                                                    self.res, self.bmin, self.bmax, k, prefix_counts)
+
+    def assemble_top(self, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten):
+        return self.ctx.assemble_top(self.res, self.bmin, self.bmax, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten)
+
+
+class ShardedOctree:
+    """The result on one rank: `local` holds the sub-trees of this rank's cells (levels >= k) plus its collector
+    content; `top` (rank 0 only) holds the nodes of levels < k.  The global octree is the union of every rank's
+    level >= k nodes and rank 0's `top` nodes."""
+
+    def __init__(self, local, top, k, recv_index, top_index, cell_to_rank, rank, stats=None):
+        self.local, self.top, self.k = local, top, k
+        self.recv_index, self.top_index = recv_index, top_index
+        self.cell_to_rank, self.rank = cell_to_rank, rank
+        self.stats = stats or {}
+        self.nodes = {name: m for name, m in local.nodes.items() if m["level"] >= k}
+        if top is not None:
+            self.nodes.update(top.nodes)
+
+    def free(self):
+        self.local.free()
+        if self.top is not None:
+            self.top.free()
+
+    def node_arrays(self, name):
+        """(xyz bytes, rgb, intensity, GLOBAL source index) of one of this rank's final nodes."""
+        if len(name) - 1 >= self.k:
+            xyz, rgb, inten, src = self.local.node_data(name)
+            return xyz, rgb, inten, _take(self.recv_index, src)
+        xyz, rgb, inten, src = self.top.node_data(name)
+        return xyz, rgb, inten, np.asarray(self.top_index, np.uint64)[src.astype(np.int64)]
+
+    def gather_all(self, comm):
+        """Test helper: every final node with its content on rank 0 (small clouds only)."""
+        mine = {}
+        for name, m in self.nodes.items():
+            d = dict(num_points=m["num_points"], enc=m["enc"], cube=tuple(m["cube"]))
+            if m["num_points"]:
+                d["xyz"], d["rgb"], d["intensity"], d["src"] = self.node_arrays(name)
+            mine[name] = d
+        out = {}
+        for part in comm.all_gather_objects(mine):
+            for name, d in part.items():
+                assert name not in out, "node %s owned twice" % name
+                out[name] = d
+        return out
+
+
+def _take(index, src):
+    idx = src.astype(np.int64)
+    if hasattr(index, "cpu"):
+        import torch
+
+        return index[torch.from_numpy(idx).to(index.device)].cpu().numpy().astype(np.uint64)
+    return np.asarray(index)[idx].astype(np.uint64)
+
+
+def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=100000):
+    """Backend-neutral orchestration (see module docstring)."""
+    res, bmin, bmax = ops.res, np.asarray(ops.bmin, np.float64), np.asarray(ops.bmax, np.float64)
+    lo, hi = np.minimum(bmin, bmax), np.maximum(bmin, bmax)
+    root_edge = max(max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])
+    nranks, rank = comm.world, comm.rank
+
+    # (0) the bounding box is an argument of build_octree (generation.rs:292); the all-reduced box of the data is only
+    # checked against it (find_bounding_box would be the producer in build_octree_from_file).
+    lmn, lmx = ops.local_bbox()
+    gmn, gmx = comm.all_reduce_minmax(lmn if ops.n else [np.inf] * 3, lmx if ops.n else [-np.inf] * 3)
+    inside = bool((gmn >= lo).all() and (gmx <= hi).all())
+
+    # (1) global histogram of level-k cells
+    k = int(prefix_levels)
+    counts_k = comm.all_reduce_sum_u64(ops.prefix_histogram(k))
+    k2 = usable_prefix_levels(counts_k, k, root_edge, res, max_points_per_node)
+    if k2 < k:
+        counts_k = counts_k.reshape(8 ** k2, -1).sum(1).astype(np.uint64)
+        k = k2
+    levels = level_counts(counts_k, k)
+    prefix_counts = concat_counts(levels)
+
+    # (2) cells -> ranks, (3) stable pack + one all-to-all
+    c2r = assign_cells(counts_k, nranks)
+    xyz, rgb, inten, idx, send_counts = ops.pack(k, c2r, nranks, index_base)
+    recv_counts = comm.exchange_counts(send_counts)
+    r_xyz = comm.all_to_all(xyz, send_counts, recv_counts)
+    r_rgb = comm.all_to_all(rgb, send_counts, recv_counts)
+    r_idx = comm.all_to_all(idx, send_counts, recv_counts)
+    r_int = comm.all_to_all(inten, send_counts, recv_counts) if inten is not None else None
+    del xyz, rgb, inten, idx
+
+    # (4) independent local build of this rank's sub-trees
+    local = ops.build_sharded(r_xyz, r_rgb, r_int, k, prefix_counts)
+    stats = local.ctx.last_build_stats() if hasattr(local, "ctx") and hasattr(local.ctx, "last_build_stats") else {}
+
+    # (5) top of the tree: unit sizes, collectors' content -> rank 0
+    unit_nsub = np.zeros(8 ** k, np.uint64)
+    for name, m in local.nodes.items():
+        if m["level"] == k:
+            unit_nsub[int(name[1:], 8)] = local.node_nsub(name)
+    unit_nsub = comm.all_reduce_sum_u64(unit_nsub)
+    pieces = {}
+    for name, m in local.nodes.items():
+        if m["level"] != k - 1 or m["num_points"] == 0:
+            continue
+        pidx = int(name[1:], 8) if k > 1 else 0
+        cx, cr, ci, cs = local.node_data(name)
+        gsrc = _take(r_idx, cs)
+        bpc = ENC_BYTES[m["enc"]]
+        off = 0
+        for c in range(8):
+            cell = pidx * 8 + c
+            if c2r[cell] != rank or unit_nsub[cell] == 0:
+                continue
+            cnt = (int(unit_nsub[cell]) + 7) // 8
+            pieces[(pidx, c)] = (cx[off * 3 * bpc:(off + cnt) * 3 * bpc].copy(), cr[off * 3:(off + cnt) * 3].copy(), None if ci is None else ci[off:off + cnt].copy(), gsrc[off:off + cnt].copy())
+            off += cnt
+        assert off == m["num_points"], (name, off, m["num_points"])
+    gathered = comm.all_gather_objects(pieces)
+    top, top_index = None, None
+    if rank == 0:
+        allp = {}
+        for part in gathered:
+            allp.update(part)
+        keys = sorted(allp)
+        cat = lambda i, dt: np.concatenate([np.asarray(allp[kk][i]) for kk in keys]).astype(dt) if keys else np.zeros(0, dt)
+        t_xyz, t_rgb, top_index = cat(0, np.uint8), cat(1, np.uint8), cat(3, np.uint64)
+        t_int = cat(2, np.float32) if (keys and allp[keys[0]][2] is not None) else None
+        top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
+    out = ShardedOctree(local, top, k, r_idx, top_index, c2r, rank, stats)
+    out.bbox_inside = inside
+    out.recv_points = int(np.sum(recv_counts))
+    return out
+
+
+def build_octree_sharded(ctx, x, y, z, rgb, intensity, index_base, resolution, bbox_min, bbox_max, prefix_levels=2, max_points_per_node=100000):
+    """GPU entry point used by bench.py: torch cuda tensors in, ShardedOctree out (torch.distributed must be initialised)."""
+    ops = CudaOps(ctx, x, y, z, rgb, intensity, resolution, bbox_min, bbox_max)
+    comm = TorchComm(x.device)
+    return build_sharded(ops, comm, index_base, prefix_levels, max_points_per_node)

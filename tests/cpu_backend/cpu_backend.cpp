@@ -335,3 +335,76 @@ uint64_t tb_check_codec(uint64_t n, uint64_t seed) {
     return bad;
 }
 }
+
+// ---- sharded build with the sequential stand-ins (host logic of the multi-GPU path) ---------------------------
+extern "C" {
+void tb_prefix_cells(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, double resolution, const double* bmin,
+                     const double* bmax, int k, uint32_t* cells_out) {
+    const double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
+    const LevelTable lv = make_level_table(E, resolution);
+    for (uint64_t i = 0; i < n; ++i) {
+        double q[3] = {x[i * stride], y[i * stride], z[i * stride]}, m[3] = {bmin[0], bmin[1], bmin[2]}, e = lv.edge[0];
+        uint32_t cell = 0;
+        for (int j = 1; j <= k; ++j) {
+            Step s = lv.fast ? descend_fast(q, m, e, lv.edge[j], lv.ry[j], lv.enc[j]) : descend(q, m, e, lv.edge[j], lv.enc[j]);
+            cell = (cell << 3) | s.digit;
+            e = lv.edge[j];
+        }
+        cells_out[i] = cell;
+    }
+}
+
+static void* tb_wrap(BuildResult&& R) {
+    TbTree* t = new TbTree();
+    t->R = std::move(R);
+    for (int i : t->R.sorted) {
+        const HNode& h = t->R.nodes[i];
+        pcv_node_meta m{};
+        u128 id = ((u128)h.level << 120) | h.index;
+        m.id_high = (uint64_t)(id >> 64);
+        m.id_low = (uint64_t)id;
+        m.num_points = (int64_t)h.final_count;
+        m.position_encoding = h.enc;
+        m.level = h.level;
+        for (int a = 0; a < 3; ++a) m.cube_min[a] = h.m[a];
+        m.cube_edge = h.e;
+        m.point_offset = h.out_point_off;
+        m.xyz_byte_offset = h.out_xyz_off;
+        t->nodes.push_back(m);
+    }
+    return t;
+}
+
+void* tb_build_sharded(uint64_t n, const double* xyz_aos, const uint8_t* rgb, const float* intensity, double resolution, const double* bmin,
+                       const double* bmax, uint64_t max_points, int levels_per_pass, int k, const uint64_t* prefix_counts, char* err, int errcap) {
+    CpuBackend be;
+    PointsView v{xyz_aos, xyz_aos + 1, xyz_aos + 2, 3, rgb, intensity, n};
+    try {
+        BuildPlan plan(be, max_points, levels_per_pass);
+        plan.shard.k = k;
+        plan.shard.counts = prefix_counts;
+        return tb_wrap(plan.run(v, resolution, bmin, bmax));
+    } catch (const std::exception& e) {
+        if (err) snprintf(err, (size_t)errcap, "%s", e.what());
+        return nullptr;
+    }
+}
+
+void* tb_assemble_top(double resolution, const double* bmin, const double* bmax, int k, const uint64_t* prefix_counts, const uint64_t* unit_nsub,
+                      const uint8_t* xyz, const uint8_t* rgb, const float* intensity, uint64_t npoints, char* err, int errcap) {
+    CpuBackend be;
+    try {
+        return tb_wrap(assemble_top(be, resolution, bmin, bmax, k, prefix_counts, unit_nsub, xyz, rgb, intensity, npoints));
+    } catch (const std::exception& e) {
+        if (err) snprintf(err, (size_t)errcap, "%s", e.what());
+        return nullptr;
+    }
+}
+
+// n(X) of every node, in the order of tb_nodes
+void tb_nsub(void* h, uint64_t* out) {
+    TbTree* t = (TbTree*)h;
+    size_t k = 0;
+    for (int i : t->R.sorted) out[k++] = t->R.nodes[i].n_sub;
+}
+}
