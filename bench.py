@@ -207,7 +207,7 @@ def run_ours(args):
     ms_per_step = dev_ms / args.steps
     value = world * n / (ms_per_step * 1e3)
     stats = ctx.last_build_stats() if world == 1 else last.stats
-    nodes = len(last.nodes)
+    nodes = int(last.num_nodes)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

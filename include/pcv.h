@@ -172,6 +172,7 @@ int pcv_build_octree_sharded_device(pcv_ctx* ctx, const pcv_points* dev_points, 
                                     const double bbox_max[3], uint32_t k, const uint64_t* prefix_counts, pcv_octree** out);
 /* n(X): size of node X at the moment it is subsampled into its parent (needed from every level-k node by the assembly). */
 int pcv_octree_node_nsub(const pcv_octree* o, uint64_t id_high, uint64_t id_low, uint64_t* nsub_out);
+int pcv_octree_nsub_all(const pcv_octree* o, uint64_t* out, uint64_t cap); /* same order as pcv_octree_nodes */
 /* Nodes of levels 0..k-1 from the gathered collector content (host buffers; level k-1 nodes in index order, inside a
  * node child order, positions as node-file bytes in the collector's encoding).  src_index of the result = position in
  * the gathered arrays. */

@@ -14,6 +14,8 @@ from . import geometry
 from ._native import PcvError, Location  # noqa: F401
 
 ENC_BYTES = {1: 1, 2: 2, 3: 4, 4: 8}
+NODE_DTYPE = np.dtype([("id_high", "<u8"), ("id_low", "<u8"), ("num_points", "<i8"), ("enc", "<i4"), ("level", "<i4"), ("cube", "<f8", (4,)),
+                       ("point_offset", "<u8"), ("xyz_byte_offset", "<u8")])
 SYNTH_SLAB_ECEF, SYNTH_GAUSS_CLUSTERS = 1, 2
 
 
@@ -174,22 +176,50 @@ class Octree:
         arr = (N.NodeMeta * max(nn.value, 1))()
         N.check(N.lib().pcv_octree_nodes(self.h, arr, nn.value))
         self.node_array = arr
-        self.order = []
-        self.nodes = {}
-        for i in range(nn.value):
-            m = arr[i]
-            name = node_name(m.id_high, m.id_low)
-            self.order.append(name)
-            self.nodes[name] = dict(
-                num_points=m.num_points,
-                enc=m.position_encoding,
-                level=m.level,
-                cube=(m.cube_min[0], m.cube_min[1], m.cube_min[2], m.cube_edge),
-                hi=m.id_high,
-                lo=m.id_low,
-                point_offset=m.point_offset,
-                xyz_byte_offset=m.xyz_byte_offset,
-            )
+        self.num_nodes = nn.value
+        # structured numpy view of the node table (no per-node Python objects until someone asks for `nodes`)
+        self.meta = np.frombuffer(arr, dtype=NODE_DTYPE, count=nn.value) if nn.value else np.zeros(0, NODE_DTYPE)
+        self._nodes = None
+        self._order = None
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            self._nodes, self._order = {}, []
+            for m in self.meta:
+                name = node_name(m["id_high"], m["id_low"])
+                self._order.append(name)
+                self._nodes[name] = dict(
+                    num_points=int(m["num_points"]),
+                    enc=int(m["enc"]),
+                    level=int(m["level"]),
+                    cube=(float(m["cube"][0]), float(m["cube"][1]), float(m["cube"][2]), float(m["cube"][3])),
+                    hi=int(m["id_high"]),
+                    lo=int(m["id_low"]),
+                    point_offset=int(m["point_offset"]),
+                    xyz_byte_offset=int(m["xyz_byte_offset"]),
+                )
+        return self._nodes
+
+    @property
+    def order(self):
+        self.nodes
+        return self._order
+
+    def nsub_all(self):
+        out = np.zeros(max(self.num_nodes, 1), np.uint64)
+        N.check(N.lib().pcv_octree_nsub_all(self.h, _p(out), self.num_nodes))
+        return out[: self.num_nodes]
+
+    def node_data_at(self, i):
+        """node_data by position in the node table."""
+        m = self.meta[i]
+        n, bpc = int(m["num_points"]), ENC_BYTES[int(m["enc"])]
+        xyz, rgb = np.zeros(n * 3 * bpc, np.uint8), np.zeros(n * 3, np.uint8)
+        inten = np.zeros(n, np.float32) if self.has_intensity else None
+        src = np.zeros(n, np.uint64)
+        N.check(N.lib().pcv_octree_node_data(self.h, int(m["id_high"]), int(m["id_low"]), _p(xyz), _p(rgb), _p(inten), _p(src)))
+        return xyz, rgb, inten, src
 
     def free(self):
         if self.h:

@@ -129,6 +129,7 @@ SYMBOLS = [
     ("pcv_prefix_pack_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_uint64, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_build_octree_sharded_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_octree_node_nsub", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
+    ("pcv_octree_nsub_all", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     ("pcv_assemble_top", C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("pcv_synth_points_device", C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_synth_points_host", C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

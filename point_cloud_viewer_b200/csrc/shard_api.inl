@@ -115,6 +115,13 @@ int pcv_octree_node_nsub(const pcv_octree* o, uint64_t hi, uint64_t lo, uint64_t
     return PCV_OK;
 }
 
+int pcv_octree_nsub_all(const pcv_octree* o, uint64_t* out, uint64_t cap) {
+    if (!o || (!out && cap)) return fail(PCV_ERR_INVALID, "null argument");
+    if (cap < o->nsub.size()) return fail(PCV_ERR_INVALID, "capacity too small");
+    if (!o->nsub.empty()) memcpy(out, o->nsub.data(), o->nsub.size() * 8);
+    return PCV_OK;
+}
+
 int pcv_assemble_top(pcv_ctx* c, double resolution, const double bmin_in[3], const double bmax_in[3], uint32_t k, const uint64_t* prefix_counts,
                      const uint64_t* unit_nsub, const void* xyz_codes, const uint8_t* rgb, const float* intensity, uint64_t npoints, pcv_octree** out) {
     if (!c || !bmin_in || !bmax_in || !prefix_counts || !unit_nsub || !out || (npoints && (!xyz_codes || !rgb)))

@@ -162,9 +162,17 @@ class ShardedOctree:
         self.recv_index, self.top_index = recv_index, top_index
         self.cell_to_rank, self.rank = cell_to_rank, rank
         self.stats = stats or {}
-        self.nodes = {name: m for name, m in local.nodes.items() if m["level"] >= k}
-        if top is not None:
-            self.nodes.update(top.nodes)
+        self._nodes = None
+        self.num_nodes = (int((local.meta["level"] >= k).sum()) if hasattr(local, "meta") else sum(1 for m in local.nodes.values() if m["level"] >= k)) + (
+            (top.num_nodes if hasattr(top, "num_nodes") else len(top.nodes)) if top is not None else 0)
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            self._nodes = {name: m for name, m in self.local.nodes.items() if m["level"] >= self.k}
+            if self.top is not None:
+                self._nodes.update(self.top.nodes)
+        return self._nodes
 
     def free(self):
         self.local.free()
@@ -243,18 +251,28 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
 
     # (5) top of the tree: unit sizes, collectors' content -> rank 0
     unit_nsub = np.zeros(8 ** k, np.uint64)
-    for name, m in local.nodes.items():
-        if m["level"] == k:
-            unit_nsub[int(name[1:], 8)] = local.node_nsub(name)
+    collectors = []  # (cell index at level k-1, node name or table position)
+    if hasattr(local, "meta"):  # CUDA tree: vectorised over the node table
+        meta, ns = local.meta, local.nsub_all()
+        idx_mask = (1 << 60) - 1
+        sel = np.nonzero(meta["level"] == k)[0]
+        unit_nsub[(meta["id_low"][sel] & idx_mask).astype(np.int64)] = ns[sel]
+        for i in np.nonzero((meta["level"] == k - 1) & (meta["num_points"] > 0))[0]:
+            collectors.append((int(meta["id_low"][i] & idx_mask), int(i), int(meta["num_points"][i]), int(meta["enc"][i])))
+        fetch = local.node_data_at
+    else:
+        for name, m in local.nodes.items():
+            if m["level"] == k:
+                unit_nsub[int(name[1:], 8)] = local.node_nsub(name)
+            elif m["level"] == k - 1 and m["num_points"] > 0:
+                collectors.append((int(name[1:], 8) if k > 1 else 0, name, m["num_points"], m["enc"]))
+        fetch = local.node_data
     unit_nsub = comm.all_reduce_sum_u64(unit_nsub)
     pieces = {}
-    for name, m in local.nodes.items():
-        if m["level"] != k - 1 or m["num_points"] == 0:
-            continue
-        pidx = int(name[1:], 8) if k > 1 else 0
-        cx, cr, ci, cs = local.node_data(name)
+    for pidx, key, npts, enc in collectors:
+        cx, cr, ci, cs = fetch(key)
         gsrc = _take(r_idx, cs)
-        bpc = ENC_BYTES[m["enc"]]
+        bpc = ENC_BYTES[enc]
         off = 0
         for c in range(8):
             cell = pidx * 8 + c
@@ -263,7 +281,7 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
             cnt = (int(unit_nsub[cell]) + 7) // 8
             pieces[(pidx, c)] = (cx[off * 3 * bpc:(off + cnt) * 3 * bpc].copy(), cr[off * 3:(off + cnt) * 3].copy(), None if ci is None else ci[off:off + cnt].copy(), gsrc[off:off + cnt].copy())
             off += cnt
-        assert off == m["num_points"], (name, off, m["num_points"])
+        assert off == npts, (pidx, off, npts)
     gathered = comm.all_gather_objects(pieces)
     top, top_index = None, None
     if rank == 0:
