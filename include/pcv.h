@@ -122,7 +122,8 @@ int pcv_octree_nodes(const pcv_octree* o, pcv_node_meta* out, uint64_t cap); /* 
 /* Octree::get_node_data (octree/mod.rs:285-307): raw .xyz / .rgb bytes (+ intensity, provenance). */
 int pcv_octree_node_data(const pcv_octree* o, uint64_t id_high, uint64_t id_low, void* xyz_out, uint8_t* rgb_out,
                          float* intensity_out, uint64_t* src_index_out);
-/* All nodes at once into caller (ideally pinned) buffers, node-contiguous in pcv_octree_nodes order. */
+/* All nodes at once into caller (ideally pinned) buffers: node n occupies points [point_offset, +num_points) and
+ * bytes [xyz_byte_offset, +num_points*3*bpc) of these arrays (offsets from pcv_octree_nodes; no particular order). */
 int pcv_octree_download(const pcv_octree* o, void* xyz_out, uint8_t* rgb_out, float* intensity_out, uint64_t* src_index_out);
 /* Device views of the same arrays (valid until pcv_octree_free). */
 int pcv_octree_device_arrays(const pcv_octree* o, const void** xyz, const uint8_t** rgb, const float** intensity,

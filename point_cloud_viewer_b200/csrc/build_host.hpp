@@ -24,6 +24,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -63,8 +65,10 @@ struct TileDesc {
 struct ActiveDesc {
     double m[3];
     double e;
+    uint64_t start, count;  // the node's segment in the pass's input (records, or raw points for the root)
     uint32_t chunk_begin, nchunks;
-    uint32_t pad0, pad1;
+    uint32_t tile_begin;    // first tile of the node (tiles never straddle nodes)
+    uint32_t pad0;
 };
 struct ChunkDesc {
     uint32_t tile_begin, ntiles;
@@ -85,6 +89,7 @@ struct DNode {
     uint64_t off_in_parent;   // sum_{k'<k} ceil(n(P.k')/8)
     uint64_t out_point_off;
     uint64_t out_xyz_off;     // bytes
+    uint64_t arena_off, count;  // leaves (and collectors in the top assembly): segment of the leaf arena
     int32_t parent;           // -1 for the root
     int32_t enc;
 };
@@ -112,7 +117,6 @@ struct PassArgs {
     uint32_t* col_arena;
     uint32_t ntiles, nactive, nchunks;
     uint64_t npoints;  // points still being partitioned in this pass
-    const TileDesc* d_tiles;
     const ActiveDesc* d_active;
     const ChunkDesc* d_chunks;
     uint32_t* d_tile_counts;  // [ntiles][nbins]; after scan: exclusive prefix over the node's tiles
@@ -130,7 +134,9 @@ struct PlaceArgs {
     const uint32_t* col_arena;
     int fast;  // LevelTable::fast
     const DNode* d_nodes;
-    const LeafTile* d_tiles;
+    const uint32_t* d_leaf_tile_begin;  // [nleaves + 1] first tile of every leaf
+    const uint32_t* d_leaf_node;        // [nleaves] index into d_nodes
+    uint32_t nleaves;
     uint32_t ntiles;
     uint64_t npoints, xyz_bytes;
     uint8_t* out_xyz;
@@ -138,6 +144,34 @@ struct PlaceArgs {
     float* out_intensity;
     uint32_t* out_src;
 };
+
+// Tile descriptors are not materialised: a block finds its node by binary search over the per-node first-tile index.
+PCV_HD uint32_t upper_index(const uint32_t* begin, size_t stride_words, uint32_t n, uint32_t b) {
+    uint32_t lo = 0, hi = n;  // largest i in [0, n) with begin[i] <= b
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (begin[(size_t)mid * stride_words] <= b)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+PCV_HD TileDesc tile_of(const PassArgs& a, uint32_t b) {
+    const uint32_t i = upper_index(&a.d_active[0].tile_begin, sizeof(ActiveDesc) / 4, a.nactive, b);
+    const ActiveDesc& act = a.d_active[i];
+    const uint64_t o = (uint64_t)(b - act.tile_begin) * kTilePoints;
+    const uint64_t rem = act.count - o;
+    return TileDesc{act.start + o, (uint32_t)(rem < kTilePoints ? rem : kTilePoints), i};
+}
+PCV_HD LeafTile leaf_tile_of(const PlaceArgs& a, uint32_t b) {
+    const uint32_t l = upper_index(a.d_leaf_tile_begin, 1, a.nleaves, b);
+    const uint32_t node = a.d_leaf_node[l];
+    const DNode& nd = a.d_nodes[node];
+    const uint64_t o = (uint64_t)(b - a.d_leaf_tile_begin[l]) * kPlaceTile;
+    const uint64_t rem = nd.count - o;
+    return LeafTile{nd.arena_off + o, o, node, (uint32_t)(rem < kPlaceTile ? rem : kPlaceTile)};
+}
 
 struct Backend {
     virtual ~Backend() {}
@@ -316,7 +350,7 @@ class BuildPlan {
                 if (Gp < 1) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
                 const int nbins = 1 << (3 * Gp);
                 // ---- tiles / chunks ----
-                std::vector<TileDesc> tiles;
+                uint32_t ntiles_total = 0;
                 std::vector<ChunkDesc> chunks;
                 std::vector<ActiveDesc> adesc(active.size());
                 uint64_t active_points = 0;
@@ -326,10 +360,12 @@ class BuildPlan {
                     adesc[a].e = nd.e;
                     uint64_t c = active[a].count, s = active[a].start;
                     active_points += c;
-                    uint32_t t0 = (uint32_t)tiles.size();
-                    for (uint64_t o = 0; o < c; o += kTilePoints)
-                        tiles.push_back(TileDesc{s + o, (uint32_t)std::min<uint64_t>(kTilePoints, c - o), (uint32_t)a});
-                    uint32_t nt = (uint32_t)tiles.size() - t0;
+                    const uint32_t t0 = ntiles_total;
+                    const uint32_t nt = (uint32_t)((c + kTilePoints - 1) / kTilePoints);
+                    ntiles_total += nt;
+                    adesc[a].start = s;
+                    adesc[a].count = c;
+                    adesc[a].tile_begin = t0;
                     adesc[a].chunk_begin = (uint32_t)chunks.size();
                     adesc[a].nchunks = (nt + kChunkTiles - 1) / kChunkTiles;
                     for (uint32_t o = 0; o < nt; o += kChunkTiles)
@@ -353,11 +389,10 @@ class BuildPlan {
                 pa.col_in = cur < 0 ? nullptr : cols[cur];
                 pa.col_next = cols[nxt];
                 pa.col_arena = col_arena;
-                pa.ntiles = (uint32_t)tiles.size();
+                pa.ntiles = ntiles_total;
                 pa.nactive = (uint32_t)active.size();
                 pa.nchunks = (uint32_t)chunks.size();
                 pa.npoints = active_points;
-                pa.d_tiles = upload(tiles, scratch);
                 pa.d_active = upload(adesc, scratch);
                 pa.d_chunks = upload(chunks, scratch);
                 pa.d_tile_counts = (uint32_t*)be.dmalloc((size_t)pa.ntiles * nbins * 4);
@@ -368,6 +403,7 @@ class BuildPlan {
                 scratch.push_back(pa.d_node_bins);
                 pa.lv = lv;
 
+                const auto tq0 = std::chrono::steady_clock::now();
                 be.hist(pa);
                 be.scan(pa);
                 std::vector<uint64_t> bins((size_t)pa.nactive * nbins);
@@ -378,6 +414,7 @@ class BuildPlan {
                 R.host_ms_wait += std::chrono::duration<double, std::milli>(tw1 - tw0).count();
 
                 // ---- decide leaf / split for every descendant within Gp levels ----
+                nodes.reserve(nodes.size() + (size_t)pa.nactive * 16 + 64);
                 std::vector<uint16_t> lut((size_t)pa.nactive * nbins, 0xFFFF);
                 std::vector<BucketDesc> buckets((size_t)pa.nactive * nbins);
                 std::vector<Active> next_active;
@@ -392,14 +429,14 @@ class BuildPlan {
                     struct Fr {
                         int node, j, b0, w;
                     };
-                    std::vector<Fr> st{{active[a].node, 0, 0, nbins}};
-                    // children must be visited in digit order so that destinations are laid out in
-                    // node order; use recursion order via reversed pushes.
-                    while (!st.empty()) {
-                        Fr f = st.back();
-                        st.pop_back();
+                    Fr st[64];  // depth-first over <= 3 sub-levels: at most 8 pending frames per level
+                    int sp = 0;
+                    st[sp++] = Fr{active[a].node, 0, 0, nbins};
+                    while (sp > 0) {
+                        const Fr f = st[--sp];
                         int w = f.w / 8;
-                        std::vector<Fr> pend;
+                        Fr pend[8];
+                        int npend = 0;
                         for (int k = 0; k < 8; ++k) {
                             int b0 = f.b0 + k * w;
                             uint64_t cnt = 0;
@@ -428,7 +465,7 @@ class BuildPlan {
                             nodes[f.node].child[k] = ci;
                             int j = f.j + 1;
                             if (split && j < Gp) {
-                                pend.push_back(Fr{ci, j, b0, w});
+                                pend[npend++] = Fr{ci, j, b0, w};
                                 continue;
                             }
                             BucketDesc bd{};
@@ -451,12 +488,18 @@ class BuildPlan {
                             buckets[a * nbins + nlocal] = bd;
                             ++nlocal;
                         }
-                        for (size_t i = pend.size(); i-- > 0;) st.push_back(pend[i]);
+                        for (int i = npend; i-- > 0;) st[sp++] = pend[i];
                     }
                 }
+                const auto tq1 = std::chrono::steady_clock::now();
                 pa.d_lut = upload(lut, scratch);
                 pa.d_buckets = upload(buckets, scratch);
                 be.scatter(pa);
+                if (std::getenv("PCV_TIMING"))
+                    fprintf(stderr, "[pcv timing] pass L=%d G=%d active=%zu tiles=%u pts=%llu | descs %.2f wait %.2f decide %.2f upload+launch %.2f ms\n", L, Gp, active.size(),
+                            pa.ntiles, (unsigned long long)active_points, std::chrono::duration<double, std::milli>(tq0 - tp0).count(),
+                            std::chrono::duration<double, std::milli>(tw1 - tw0).count(), std::chrono::duration<double, std::milli>(tq1 - tw1).count(),
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq1).count());
                 free_scratch();
                 R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw1).count();
                 R.passes++;
@@ -480,6 +523,10 @@ class BuildPlan {
             if (b) be.dfree(b);
         be.mark(1);
 
+        const bool dbg = std::getenv("PCV_TIMING") != nullptr;
+        auto tnow = []() { return std::chrono::steady_clock::now(); };
+        auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        const auto ts0 = tnow();
         // ---- subsample plan: closed form of generation.rs:195-253,335-387 ----
         for (size_t i = nodes.size(); i-- > 0;) {
             HNode& x = nodes[i];
@@ -500,15 +547,12 @@ class BuildPlan {
         auto is_collector = [&](const HNode& x) { return shard.k && x.level == shard.k - 1; };
         for (auto& x : nodes) x.final_count = (x.parent < 0 || is_collector(x)) ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
 
+        const auto ts1 = tnow();
         // ---- output layout: nodes sorted by NodeId (level << 120 | index) ----
-        R.sorted.resize(nodes.size());
-        for (size_t i = 0; i < nodes.size(); ++i) R.sorted[i] = (int)i;
-        std::sort(R.sorted.begin(), R.sorted.end(), [&](int a, int b) {
-            if (nodes[a].level != nodes[b].level) return nodes[a].level < nodes[b].level;
-            return nodes[a].index < nodes[b].index;
-        });
+        // (the device arrays are laid out in node creation order; the NodeId-sorted table is produced while the place
+        // kernel runs)
         uint64_t poff = 0, boff = 0, algo_xyz = 0;
-        for (int i : R.sorted) {
+        for (size_t i = 0; i < nodes.size(); ++i) {
             HNode& x = nodes[i];
             x.out_point_off = poff;
             boff = (boff + 15) & ~15ull;  // node .xyz blocks are 16-byte aligned inside the device array
@@ -525,9 +569,13 @@ class BuildPlan {
         R.xyz_bytes = boff;
         R.algorithmic_bytes = 27ull * pts.n + algo_xyz + 3ull * pts.n + (pts.intensity ? 8ull * pts.n : 0ull);
 
+        const auto ts2 = tnow();
         // ---- place ----
         std::vector<DNode> dn(nodes.size());
-        std::vector<LeafTile> lt;
+        std::vector<uint32_t> leaf_tile_begin, leaf_node;
+        leaf_tile_begin.reserve(nodes.size() + 1);
+        leaf_node.reserve(nodes.size());
+        uint32_t nplace_tiles = 0;
         for (size_t i = 0; i < nodes.size(); ++i) {
             const HNode& x = nodes[i];
             DNode& d = dn[i];
@@ -537,16 +585,23 @@ class BuildPlan {
             d.off_in_parent = x.off_in_parent;
             d.out_point_off = x.out_point_off;
             d.out_xyz_off = x.out_xyz_off;
+            d.arena_off = x.arena_off;
+            d.count = x.leaf ? x.count : 0;
             d.parent = is_collector(x) ? -1 : x.parent;  // a collector ends the up-walk like the root does
             d.enc = x.enc;
-            if (x.leaf)
-                for (uint64_t o = 0; o < x.count; o += kPlaceTile)
-                    lt.push_back(LeafTile{x.arena_off + o, o, (uint32_t)i, (uint32_t)std::min<uint64_t>(kPlaceTile, x.count - o)});
+            if (x.leaf) {
+                leaf_tile_begin.push_back(nplace_tiles);
+                leaf_node.push_back((uint32_t)i);
+                nplace_tiles += (uint32_t)((x.count + kPlaceTile - 1) / kPlaceTile);
+            }
         }
+        leaf_tile_begin.push_back(nplace_tiles);
+        const auto ts3 = tnow();
         R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
         R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
         R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
         R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
+        const auto ts4 = tnow();
         PlaceArgs pl{};
         pl.wide = wide;
         pl.pts = pts;
@@ -554,19 +609,31 @@ class BuildPlan {
         pl.col_arena = col_arena;
         pl.fast = lv.fast;
         pl.d_nodes = upload(dn, scratch);
-        pl.d_tiles = upload(lt, scratch);
-        pl.ntiles = (uint32_t)lt.size();
+        pl.d_leaf_tile_begin = upload(leaf_tile_begin, scratch);
+        pl.d_leaf_node = upload(leaf_node, scratch);
+        pl.nleaves = (uint32_t)leaf_node.size();
+        pl.ntiles = nplace_tiles;
         pl.npoints = pts.n;
         pl.xyz_bytes = algo_xyz;
         pl.out_xyz = R.d_xyz;
         pl.out_rgb = R.d_rgb;
         pl.out_intensity = R.d_intensity;
         pl.out_src = R.d_src;
+        const auto ts5 = tnow();
         be.place(pl);
         be.mark(2);
+        R.sorted.resize(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) R.sorted[i] = (int)i;
+        std::sort(R.sorted.begin(), R.sorted.end(), [&](int a, int b) {
+            if (nodes[a].level != nodes[b].level) return nodes[a].level < nodes[b].level;
+            return nodes[a].index < nodes[b].index;
+        });
         free_scratch();
         be.dfree(arena);
         be.dfree(col_arena);
+        if (dbg)
+            fprintf(stderr, "[pcv timing] plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", tms(ts0, ts1), tms(ts1, ts2),
+                    tms(ts2, ts3), tms(ts3, ts4), tms(ts4, ts5), nodes.size(), (size_t)nplace_tiles);
         return R;
     }
 };
@@ -696,7 +763,8 @@ inline BuildResult assemble_top(Backend& be, double resolution, const double bmi
         return d;
     };
     std::vector<DNode> dn(nodes.size());
-    std::vector<LeafTile> lt;
+    std::vector<uint32_t> leaf_tile_begin, leaf_node;
+    uint32_t nplace_tiles = 0;
     for (size_t i = 0; i < nodes.size(); ++i) {
         const HNode& x = nodes[i];
         DNode& d = dn[i];
@@ -706,12 +774,17 @@ inline BuildResult assemble_top(Backend& be, double resolution, const double bmi
         d.off_in_parent = x.off_in_parent;
         d.out_point_off = x.out_point_off;
         d.out_xyz_off = x.out_xyz_off;
+        d.arena_off = x.arena_off;
+        d.count = x.level == k - 1 ? x.n_sub : 0;
         d.parent = x.parent;
         d.enc = x.enc;
-        if (x.level == k - 1)
-            for (uint64_t o = 0; o < x.n_sub; o += kPlaceTile)
-                lt.push_back(LeafTile{x.arena_off + o, o, (uint32_t)i, (uint32_t)std::min<uint64_t>(kPlaceTile, x.n_sub - o)});
+        if (x.level == k - 1 && x.n_sub) {
+            leaf_tile_begin.push_back(nplace_tiles);
+            leaf_node.push_back((uint32_t)i);
+            nplace_tiles += (uint32_t)((x.n_sub + kPlaceTile - 1) / kPlaceTile);
+        }
     }
+    leaf_tile_begin.push_back(nplace_tiles);
     PlaceArgs pl{};
     pl.wide = wide;
     pl.pts = PointsView{nullptr, nullptr, nullptr, 1, nullptr, intensity ? (const float*)up(intensity, (size_t)npoints * 4) : nullptr, npoints};
@@ -719,8 +792,10 @@ inline BuildResult assemble_top(Backend& be, double resolution, const double bmi
     pl.col_arena = (const uint32_t*)up(cols.data(), cols.size() * 4);
     pl.fast = lv.fast;
     pl.d_nodes = (const DNode*)up(dn.data(), dn.size() * sizeof(DNode));
-    pl.d_tiles = (const LeafTile*)up(lt.data(), lt.size() * sizeof(LeafTile));
-    pl.ntiles = (uint32_t)lt.size();
+    pl.d_leaf_tile_begin = (const uint32_t*)up(leaf_tile_begin.data(), leaf_tile_begin.size() * 4);
+    pl.d_leaf_node = (const uint32_t*)up(leaf_node.data(), leaf_node.size() * 4);
+    pl.nleaves = (uint32_t)leaf_node.size();
+    pl.ntiles = nplace_tiles;
     pl.npoints = npoints;
     pl.xyz_bytes = boff;
     R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));

@@ -12,7 +12,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "build_host.hpp"
+#include "chain_device.cuh"
 
 namespace pcv {
 
@@ -182,29 +185,90 @@ __device__ __forceinline__ uint32_t load_colour(const PassArgs& a, uint64_t g) {
 // ------------------------------------------------------------------------------------------------
 // hist
 // ------------------------------------------------------------------------------------------------
-template <bool ROOT, bool WIDE>
+// Position of item i as the node's file would hand it to split(): raw for the root, decoded from the node's own
+// encoding (ENC_IN) otherwise.
+template <bool ROOT, bool WIDE, int ENC_IN>
+__device__ __forceinline__ void load_position_t(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i, double q[3], uint32_t& idx) {
+    const uint64_t g = t.start + i;
+    if (ROOT) {
+        q[0] = __ldg(a.pts.x + g * a.pts.stride);
+        q[1] = __ldg(a.pts.y + g * a.pts.stride);
+        q[2] = __ldg(a.pts.z + g * a.pts.stride);
+        idx = (uint32_t)g;
+    } else {
+        uint64_t c[3];
+        load_rec<WIDE>(a.rec_in, g, c, idx);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) q[k] = decode_axis<ENC_IN>(c[k], act.m[k], act.e);
+    }
+}
+
+constexpr int kHistItems = 2;  // points per thread in flight (x 3 independent axis chains each)
+
+// Histogram of the G-level digits of one tile.  The last level needs only the child digit (no encode/decode).
+template <bool ROOT, bool WIDE, int G, bool FAST>
+__device__ __forceinline__ unsigned hist_tile(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t* sh_hist) {
+    unsigned bad = 0;
+    for (uint32_t i0 = threadIdx.x; i0 < t.count; i0 += blockDim.x * kHistItems) {
+        double q[kHistItems][3], m[kHistItems][3];
+        uint32_t idx;
+#pragma unroll
+        for (int u = 0; u < kHistItems; ++u) {
+            const uint32_t i = min(i0 + u * blockDim.x, t.count - 1);  // clamp: out-of-range lanes redo the last item, not counted
+            if (ROOT) {
+                load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[u], idx);
+            } else {
+                PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx);)
+            }
+            m[u][0] = act.m[0];
+            m[u][1] = act.m[1];
+            m[u][2] = act.m[2];
+        }
+        unsigned bin[kHistItems];
+#pragma unroll
+        for (int u = 0; u < kHistItems; ++u) bin[u] = 0;
+        double e = act.e;
+#pragma unroll
+        for (int j = 1; j < G; ++j) {
+            const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
+            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kHistItems; ++u) {
+                uint32_t code[3];
+                uint64_t codew[3];
+                const unsigned d = WIDE ? level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, codew, bad) : level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, code, bad);
+                bin[u] = (bin[u] << 3) | d;
+            })
+            e = eh;
+        }
+#pragma unroll
+        for (int u = 0; u < kHistItems; ++u) {
+            bin[u] = (bin[u] << 3) | level_digit(q[u], m[u], e);
+            if (i0 + u * blockDim.x < t.count) atomicAdd(&sh_hist[bin[u]], 1u);
+        }
+    }
+    return bad;
+}
+
+template <bool ROOT, bool WIDE, int G>
 __global__ void __launch_bounds__(256) k_hist(const __grid_constant__ PassArgs a) {
     extern __shared__ uint32_t sh_hist[];
-    const TileDesc t = a.d_tiles[blockIdx.x];
+    const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
-    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) sh_hist[b] = 0;
+    constexpr int NB = 1 << (3 * G);
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
-        double q[3], m[3] = {act.m[0], act.m[1], act.m[2]};
-        uint32_t idx;
-        load_position<ROOT, WIDE>(a, t, act, i, q, idx);
-        double e = act.e;
-        unsigned bin = 0;
-        for (int j = 1; j <= a.G; ++j) {
-            Step s = descend_any(a.lv, a.level + j, q, m, e);
-            bin = (bin << 3) | s.digit;
-            e = a.lv.edge[a.level + j];
+    if (a.lv.fast) {
+        const unsigned bad = hist_tile<ROOT, WIDE, G, true>(a, t, act, sh_hist);
+        if (__syncthreads_or((int)bad)) {  // a numerator outside the proven range: redo the tile with the IEEE operator
+            for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
+            __syncthreads();
+            hist_tile<ROOT, WIDE, G, false>(a, t, act, sh_hist);
         }
-        atomicAdd(&sh_hist[bin], 1u);
+    } else {
+        hist_tile<ROOT, WIDE, G, false>(a, t, act, sh_hist);
     }
     __syncthreads();
-    uint32_t* out = a.d_tile_counts + (size_t)blockIdx.x * a.nbins;
-    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) out[b] = sh_hist[b];
+    uint32_t* out = a.d_tile_counts + (size_t)blockIdx.x * NB;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) out[b] = sh_hist[b];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -254,17 +318,58 @@ constexpr int kScatterItems = 4;                                   // items per 
 constexpr int kRoundPoints = kScatterThreads * kScatterItems;      // 1024
 static_assert(kTilePoints % kRoundPoints == 0, "tile must be a whole number of rounds");
 
-template <bool ROOT, bool WIDE>
+// Descent of this thread's items of one round: digits of all G levels + the codes of every level (the destination
+// decides afterwards which level's codes it stores).
+template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
+__device__ __forceinline__ unsigned scatter_round_chain(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t r0, int warp, int lane,
+                                                        CodeT (&cj)[kScatterItems][G][3], unsigned (&bin)[kScatterItems], uint32_t (&idxs)[kScatterItems],
+                                                        uint32_t (&cols)[kScatterItems]) {
+    unsigned bad = 0;
+    double q[kScatterItems][3], m[kScatterItems][3];
+#pragma unroll
+    for (int s = 0; s < kScatterItems; ++s) {
+        const uint32_t i = min(r0 + warp * (32 * kScatterItems) + s * 32 + lane, t.count - 1);
+        if (ROOT) {
+            load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[s], idxs[s]);
+        } else {
+            PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[s], idxs[s]);)
+        }
+        cols[s] = load_colour<ROOT>(a, t.start + i);
+        m[s][0] = act.m[0];
+        m[s][1] = act.m[1];
+        m[s][2] = act.m[2];
+        bin[s] = 0;
+    }
+    double e = act.e;
+#pragma unroll
+    for (int j = 1; j <= G; ++j) {
+        const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
+        if (j < G) {
+            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int s = 0; s < kScatterItems; ++s) {
+                bin[s] = (bin[s] << 3) | level_step<ENC, FAST, true>(q[s], m[s], e, eh, ry, cj[s][j - 1], bad);
+            })
+        } else {  // last level: the decoded position is not needed any more
+            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int s = 0; s < kScatterItems; ++s) {
+                bin[s] = (bin[s] << 3) | level_step<ENC, FAST, false>(q[s], m[s], e, eh, ry, cj[s][j - 1], bad);
+            })
+        }
+        e = eh;
+    }
+    return bad;
+}
+
+template <bool ROOT, bool WIDE, int G>
 __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_constant__ PassArgs a) {
+    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
     // shared: base[nbins] u32 | wc[8][nbins] u32 | lut[nbins] u16 | meta[nbins] u16
     extern __shared__ uint32_t sh[];
-    const int nb = a.nbins;
+    constexpr int nb = 1 << (3 * G);
     uint32_t* base = sh;
     uint32_t* wc = sh + nb;
     uint16_t* lut = reinterpret_cast<uint16_t*>(wc + kScatterWarps * nb);
     uint16_t* meta = lut + nb;
 
-    const TileDesc t = a.d_tiles[blockIdx.x];
+    const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -308,45 +413,34 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
     }
     __syncthreads();
 
-    const int enc_in = a.lv.enc[a.level];
-    (void)enc_in;
     for (uint32_t r0 = 0; r0 < t.count; r0 += kRoundPoints) {
         for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) wc[i] = 0;
-        __syncthreads();
 
-        uint64_t code[kScatterItems][3];
-        uint32_t idxs[kScatterItems];
-        uint32_t cols[kScatterItems];
-        uint32_t lbs[kScatterItems];
-        uint32_t rank[kScatterItems];
-        // phase 1: descent for this thread's items
+        CodeT cj[kScatterItems][G][3];
+        unsigned bin[kScatterItems];
+        uint32_t idxs[kScatterItems], cols[kScatterItems], lbs[kScatterItems], rank[kScatterItems];
+        // phase 1: descent (speculatively through the reciprocal division; redone with the IEEE operator if any
+        // numerator of the block was outside the proven range)
+        if (a.lv.fast) {
+            const unsigned bad = scatter_round_chain<ROOT, WIDE, G, true, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
+            if (__syncthreads_or((int)bad)) scatter_round_chain<ROOT, WIDE, G, false, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
+        } else {
+            scatter_round_chain<ROOT, WIDE, G, false, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
+            __syncthreads();
+        }
+        CodeT code[kScatterItems][3];
 #pragma unroll
         for (int s = 0; s < kScatterItems; ++s) {
             const uint32_t i = r0 + warp * (32 * kScatterItems) + s * 32 + lane;
-            lbs[s] = 0xFFFFu;
-            if (i < t.count) {
-                double q[3], m[3] = {act.m[0], act.m[1], act.m[2]};
-                load_position<ROOT, WIDE>(a, t, act, i, q, idxs[s]);
-                cols[s] = load_colour<ROOT>(a, t.start + i);
-                double e = act.e;
-                unsigned bin = 0;
-                uint64_t cj[3][3];
+            const uint32_t lb = lut[bin[s]];
+            lbs[s] = i < t.count ? lb : 0xFFFFu;
+            const int keep = meta[lb] & 0xFF;
 #pragma unroll
-                for (int j = 1; j <= 3; ++j) {
-                    if (j <= a.G) {
-                        Step st = descend_any(a.lv, a.level + j, q, m, e);
-                        bin = (bin << 3) | st.digit;
-                        e = a.lv.edge[a.level + j];
-                        cj[j - 1][0] = st.code[0];
-                        cj[j - 1][1] = st.code[1];
-                        cj[j - 1][2] = st.code[2];
-                    }
-                }
-                const uint32_t lb = lut[bin];
-                lbs[s] = lb;
-                const int keep = meta[lb] & 0xFF;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) code[s][k] = keep == 1 ? cj[0][k] : (keep == 2 ? cj[1][k] : cj[2][k]);
+            for (int k = 0; k < 3; ++k) {
+                CodeT c = cj[s][0][k];
+                if (G >= 2 && keep == 2) c = cj[s][G >= 2 ? 1 : 0][k];
+                if (G >= 3 && keep == 3) c = cj[s][G >= 3 ? 2 : 0][k];
+                code[s][k] = c;
             }
         }
         // phase 2: stable rank inside the warp, sub-round by sub-round
@@ -384,7 +478,8 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
             if (lb != 0xFFFFu) {
                 const uint32_t dst = wc[warp * nb + lb] + rank[s];
                 const bool leaf = (meta[lb] >> 8) != 0;
-                store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, code[s], idxs[s]);
+                uint64_t c64[3] = {(uint64_t)code[s][0], (uint64_t)code[s][1], (uint64_t)code[s][2]};
+                store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idxs[s]);
                 (leaf ? a.col_arena : a.col_next)[dst] = cols[s];
             }
         }
@@ -406,17 +501,54 @@ __device__ __forceinline__ void store_code(uint8_t* p, uint64_t c, int enc) {
         *reinterpret_cast<uint64_t*>(p) = c;
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
-    const LeafTile lt = a.d_tiles[blockIdx.x];
-    const DNode leaf = a.d_nodes[lt.node];
-    for (uint32_t i = threadIdx.x; i < lt.count; i += blockDim.x) {
+__device__ __forceinline__ void place_store(const PlaceArgs& a, const DNode& nd, uint64_t slot, const uint64_t c[3], uint32_t col, uint32_t idx) {
+    const uint64_t dp = nd.out_point_off + slot;
+    const int bpc = enc_bytes(nd.enc);
+    uint8_t* px = a.out_xyz + nd.out_xyz_off + slot * 3 * (uint64_t)bpc;
+    store_code(px, c[0], nd.enc);
+    store_code(px + bpc, c[1], nd.enc);
+    store_code(px + 2 * bpc, c[2], nd.enc);
+    uint8_t* rd = a.out_rgb + 3ull * dp;
+    rd[0] = (uint8_t)col;
+    rd[1] = (uint8_t)(col >> 8);
+    rd[2] = (uint8_t)(col >> 16);
+    a.out_src[dp] = idx;
+    if (a.out_intensity) a.out_intensity[dp] = __ldg(a.pts.intensity + idx);
+}
+
+// The 7 of 8 points of a non-root node that stay: one same-cube rewrite (child_writer, generation.rs:234-238) with the
+// node's encoding hoisted out of the loop; dense lane mapping (stayer s <-> rank j = 8*(s/7) + s%7 + 1).
+template <bool WIDE, int ENC, bool FAST>
+__device__ __forceinline__ unsigned place_stayers(const PlaceArgs& a, const LeafTile& lt, const DNode& nd) {
+    unsigned bad = 0;
+    const uint32_t nst = lt.count - (lt.count + 7) / 8;  // tile starts at a multiple of 8
+    for (uint32_t s = threadIdx.x; s < nst; s += blockDim.x) {
+        const uint32_t i = 8 * (s / 7) + (s % 7) + 1;
         uint64_t c[3];
         uint32_t idx;
         load_rec<WIDE>(a.arena, lt.arena_start + i, c, idx);
+        const uint32_t col = __ldg(a.col_arena + lt.arena_start + i);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c[k] = encode_axis<ENC, FAST>(decode_axis<ENC>(c[k], nd.m[k], nd.e), nd.m[k], nd.e, nd.ry, bad);
+        if (!FAST || !bad) {
+            const uint64_t j = lt.j0 + i;
+            place_store(a, nd, j - (j >> 3) - 1, c, col, idx);
+        }
+    }
+    return bad;
+}
+
+// Points that move (every 8th by current rank, generation.rs:224-238): walk up re-encoding through every cube.
+template <bool WIDE>
+__device__ __forceinline__ void place_movers(const PlaceArgs& a, const LeafTile& lt, const DNode& leaf, bool all_points) {
+    const uint32_t step = all_points ? 1u : 8u;
+    for (uint32_t i = threadIdx.x * step; i < lt.count; i += blockDim.x * step) {
+        uint64_t c[3];
+        uint32_t idx;
+        load_rec<WIDE>(a.arena, lt.arena_start + i, c, idx);
+        const uint32_t col = __ldg(a.col_arena + lt.arena_start + i);
         uint64_t j = lt.j0 + i;
         DNode nd = leaf;
-        // every 8th point (by current rank) moves into the parent: generation.rs:224-238
         while (nd.parent >= 0 && (j & 7) == 0) {
             const DNode P = a.d_nodes[nd.parent];
 #pragma unroll
@@ -434,7 +566,6 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
         }
         uint64_t slot = j;
         if (nd.parent >= 0) {
-            // the points that stay are rewritten once into the same cube (child_writer, generation.rs:234-238)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 if (a.fast) {
@@ -447,20 +578,31 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
             }
             slot = j - (j >> 3) - 1;
         }
-        const uint64_t dp = nd.out_point_off + slot;
-        const int bpc = enc_bytes(nd.enc);
-        uint8_t* px = a.out_xyz + nd.out_xyz_off + slot * 3 * (uint64_t)bpc;
-        store_code(px, c[0], nd.enc);
-        store_code(px + bpc, c[1], nd.enc);
-        store_code(px + 2 * bpc, c[2], nd.enc);
-        const uint32_t col = __ldg(a.col_arena + lt.arena_start + i);
-        uint8_t* rd = a.out_rgb + 3ull * dp;
-        rd[0] = (uint8_t)col;
-        rd[1] = (uint8_t)(col >> 8);
-        rd[2] = (uint8_t)(col >> 16);
-        a.out_src[dp] = idx;
-        if (a.out_intensity) a.out_intensity[dp] = __ldg(a.pts.intensity + idx);
+        place_store(a, nd, slot, c, col, idx);
     }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
+    const LeafTile lt = leaf_tile_of(a, blockIdx.x);
+    const DNode leaf = a.d_nodes[lt.node];
+    // A tile whose start rank is not a multiple of 8 (top assembly: a collector's points start at arbitrary ranks), or
+    // whose node ends the walk (root / collector), goes through the generic per-point path.
+    const bool generic = leaf.parent < 0 || (lt.j0 & 7) != 0;
+    if (generic) {
+        place_movers<WIDE>(a, lt, leaf, true);
+        return;
+    }
+    if (a.fast) {
+        unsigned bad = 0;
+        PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, true>(a, lt, leaf);)
+        if (__syncthreads_or((int)bad)) {  // rare: redo the tile's stayers with the IEEE operator (idempotent stores)
+            PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, false>(a, lt, leaf);)
+        }
+    } else {
+        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, false>(a, lt, leaf);)
+    }
+    place_movers<WIDE>(a, lt, leaf, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,20 +711,29 @@ struct CudaBackend : Backend {
 
     static size_t scatter_smem(int nbins) { return (size_t)nbins * 4 * (1 + kScatterWarps) + (size_t)nbins * 2 * 2; }
 
+    template <bool ROOT, bool WIDE>
+    void launch_hist(const PassArgs& a, size_t sm) {
+        if (a.G == 1)
+            k_hist<ROOT, WIDE, 1><<<a.ntiles, 256, sm, stream>>>(a);
+        else if (a.G == 2)
+            k_hist<ROOT, WIDE, 2><<<a.ntiles, 256, sm, stream>>>(a);
+        else
+            k_hist<ROOT, WIDE, 3><<<a.ntiles, 256, sm, stream>>>(a);
+    }
     void hist(const PassArgs& a) override {
         const size_t sm = (size_t)a.nbins * 4;
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
         prof_begin(K_HIST, a.npoints * (a.root ? 24 : rec));
         if (a.root) {
             if (a.wide)
-                k_hist<true, true><<<a.ntiles, 256, sm, stream>>>(a);
+                launch_hist<true, true>(a, sm);
             else
-                k_hist<true, false><<<a.ntiles, 256, sm, stream>>>(a);
+                launch_hist<true, false>(a, sm);
         } else {
             if (a.wide)
-                k_hist<false, true><<<a.ntiles, 256, sm, stream>>>(a);
+                launch_hist<false, true>(a, sm);
             else
-                k_hist<false, false><<<a.ntiles, 256, sm, stream>>>(a);
+                launch_hist<false, false>(a, sm);
         }
         prof_end();
         ++launches;
@@ -598,20 +749,29 @@ struct CudaBackend : Backend {
         launches += 3;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
+    template <bool ROOT, bool WIDE>
+    void launch_scatter(const PassArgs& a, size_t sm) {
+        if (a.G == 1)
+            k_scatter<ROOT, WIDE, 1><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+        else if (a.G == 2)
+            k_scatter<ROOT, WIDE, 2><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+        else
+            k_scatter<ROOT, WIDE, 3><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+    }
     void scatter(const PassArgs& a) override {
         const size_t sm = scatter_smem(a.nbins);
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
-        prof_begin(K_SCATTER, a.npoints * ((a.root ? 24 : rec) + rec));
+        prof_begin(K_SCATTER, a.npoints * ((a.root ? 27 : rec + 4) + rec + 4));
         if (a.root) {
             if (a.wide)
-                k_scatter<true, true><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+                launch_scatter<true, true>(a, sm);
             else
-                k_scatter<true, false><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+                launch_scatter<true, false>(a, sm);
         } else {
             if (a.wide)
-                k_scatter<false, true><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+                launch_scatter<false, true>(a, sm);
             else
-                k_scatter<false, false><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+                launch_scatter<false, false>(a, sm);
         }
         prof_end();
         ++launches;

@@ -70,7 +70,7 @@ struct CpuBackend : Backend {
 
     void hist(const PassArgs& a) override {
         for (uint32_t b = 0; b < a.ntiles; ++b) {
-            const TileDesc t = a.d_tiles[b];
+            const TileDesc t = tile_of(a, b);
             const ActiveDesc act = a.d_active[t.active];
             uint32_t* out = a.d_tile_counts + (size_t)b * a.nbins;
             for (int k = 0; k < a.nbins; ++k) out[k] = 0;
@@ -123,7 +123,7 @@ struct CpuBackend : Backend {
         std::vector<uint32_t> incl(nb), base(nb);
         std::vector<uint16_t> meta(nb);
         for (uint32_t blk = 0; blk < a.ntiles; ++blk) {
-            const TileDesc t = a.d_tiles[blk];
+            const TileDesc t = tile_of(a, blk);
             const ActiveDesc act = a.d_active[t.active];
             const uint32_t* pfx = a.d_tile_counts + (size_t)blk * nb;
             uint32_t run = 0;
@@ -158,7 +158,7 @@ struct CpuBackend : Backend {
     }
     void place(const PlaceArgs& a) override {
         for (uint32_t b = 0; b < a.ntiles; ++b) {
-            const LeafTile lt = a.d_tiles[b];
+            const LeafTile lt = leaf_tile_of(a, b);
             const DNode leaf = a.d_nodes[lt.node];
             for (uint32_t i = 0; i < lt.count; ++i) {
                 uint64_t c[3];
