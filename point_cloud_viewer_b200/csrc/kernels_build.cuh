@@ -312,62 +312,110 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
 // ------------------------------------------------------------------------------------------------
 // scatter
 // ------------------------------------------------------------------------------------------------
-constexpr int kScatterThreads = 256;
+// One block (16 warps) per 4096-point tile, warp w owns the contiguous items [256 w, 256 w + 256).
+//   sweep A  descent of every item (2 sub-rounds of 32 items in flight per warp); destination bucket, kept codes, source
+//            index and colour are staged in shared memory; per-warp bucket counts with __match_any_sync
+//   scan     exclusive prefix over the warps per bucket, on top of the tile's first slot (from the histogram prefix)
+//   sweep B  every warp walks its items in order, ranks them inside the sub-round with __match_any_sync and writes the
+//            staged record to its slot (next pass segment or leaf arena)
+// Two block barriers per tile; the order inside every bucket is the tile order, i.e. the input order (stable).
+constexpr int kScatterThreads = 512;
 constexpr int kScatterWarps = kScatterThreads / 32;
-constexpr int kScatterItems = 4;                                   // items per thread per round
-constexpr int kRoundPoints = kScatterThreads * kScatterItems;      // 1024
-static_assert(kTilePoints % kRoundPoints == 0, "tile must be a whole number of rounds");
+constexpr int kWarpItems = kTilePoints / kScatterWarps;  // 256
+constexpr int kSubRounds = kWarpItems / 32;              // 8
+constexpr int kScatterU = 2;                             // sub-rounds in flight
+static_assert(kSubRounds % kScatterU == 0, "sub-rounds must be a multiple of the unroll");
 
-// Descent of this thread's items of one round: digits of all G levels + the codes of every level (the destination
-// decides afterwards which level's codes it stores).
-template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
-__device__ __forceinline__ unsigned scatter_round_chain(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t r0, int warp, int lane,
-                                                        CodeT (&cj)[kScatterItems][G][3], unsigned (&bin)[kScatterItems], uint32_t (&idxs)[kScatterItems],
-                                                        uint32_t (&cols)[kScatterItems]) {
-    unsigned bad = 0;
-    double q[kScatterItems][3], m[kScatterItems][3];
-#pragma unroll
-    for (int s = 0; s < kScatterItems; ++s) {
-        const uint32_t i = min(r0 + warp * (32 * kScatterItems) + s * 32 + lane, t.count - 1);
-        if (ROOT) {
-            load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[s], idxs[s]);
-        } else {
-            PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[s], idxs[s]);)
-        }
-        cols[s] = load_colour<ROOT>(a, t.start + i);
-        m[s][0] = act.m[0];
-        m[s][1] = act.m[1];
-        m[s][2] = act.m[2];
-        bin[s] = 0;
+template <bool WIDE>
+struct ScatterSmem {
+    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
+    static constexpr size_t bytes(int nb) {
+        return (size_t)kTilePoints * (3 * sizeof(CodeT) + 4 + 4 + 2) + (size_t)nb * 4 * (1 + kScatterWarps) + (size_t)nb * 2 * 2;
     }
-    double e = act.e;
+};
+
+template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
+__device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, CodeT* sc0, CodeT* sc1,
+                                                    CodeT* sc2, uint32_t* sidx, uint32_t* scol, uint16_t* slb, const uint16_t* lut, const uint16_t* meta,
+                                                    uint32_t* cnt) {
+    constexpr int nb = 1 << (3 * G);
+    unsigned bad = 0;
+    for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
+        double q[kScatterU][3], m[kScatterU][3];
+        uint32_t idx[kScatterU], col[kScatterU];
+        unsigned bin[kScatterU];
+        CodeT cj[kScatterU][G][3];
 #pragma unroll
-    for (int j = 1; j <= G; ++j) {
-        const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
-        if (j < G) {
-            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int s = 0; s < kScatterItems; ++s) {
-                bin[s] = (bin[s] << 3) | level_step<ENC, FAST, true>(q[s], m[s], e, eh, ry, cj[s][j - 1], bad);
-            })
-        } else {  // last level: the decoded position is not needed any more
-            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int s = 0; s < kScatterItems; ++s) {
-                bin[s] = (bin[s] << 3) | level_step<ENC, FAST, false>(q[s], m[s], e, eh, ry, cj[s][j - 1], bad);
-            })
+        for (int u = 0; u < kScatterU; ++u) {
+            const uint32_t i = min((uint32_t)(warp * kWarpItems + (s0 + u) * 32 + lane), t.count - 1);
+            if (ROOT) {
+                load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[u], idx[u]);
+            } else {
+                PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx[u]);)
+            }
+            col[u] = load_colour<ROOT>(a, t.start + i);
+            m[u][0] = act.m[0];
+            m[u][1] = act.m[1];
+            m[u][2] = act.m[2];
+            bin[u] = 0;
         }
-        e = eh;
+        double e = act.e;
+#pragma unroll
+        for (int j = 1; j <= G; ++j) {
+            const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
+            if (j < G) {
+                PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kScatterU; ++u) {
+                    bin[u] = (bin[u] << 3) | level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, cj[u][j - 1], bad);
+                })
+            } else {  // last level: the decoded position is not needed any more
+                PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kScatterU; ++u) {
+                    bin[u] = (bin[u] << 3) | level_step<ENC, FAST, false>(q[u], m[u], e, eh, ry, cj[u][j - 1], bad);
+                })
+            }
+            e = eh;
+        }
+#pragma unroll
+        for (int u = 0; u < kScatterU; ++u) {
+            const uint32_t i = warp * kWarpItems + (s0 + u) * 32 + lane;
+            const uint32_t lb = lut[bin[u]];
+            const uint32_t lbv = i < t.count ? lb : 0xFFFFu;
+            const int keep = meta[lb & (nb - 1)] & 0xFF;
+            CodeT c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                c[k] = cj[u][0][k];
+                if (G >= 2 && keep == 2) c[k] = cj[u][G >= 2 ? 1 : 0][k];
+                if (G >= 3 && keep == 3) c[k] = cj[u][G >= 3 ? 2 : 0][k];
+            }
+            sc0[i] = c[0];
+            sc1[i] = c[1];
+            sc2[i] = c[2];
+            sidx[i] = idx[u];
+            scol[i] = col[u];
+            slb[i] = (uint16_t)lbv;
+            const unsigned mask = __match_any_sync(0xffffffffu, lbv);
+            if (lbv != 0xFFFFu && lane == __ffs(mask) - 1) cnt[warp * nb + lbv] += __popc(mask);
+            __syncwarp();
+        }
     }
     return bad;
 }
 
 template <bool ROOT, bool WIDE, int G>
-__global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const __grid_constant__ PassArgs a) {
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
-    // shared: base[nbins] u32 | wc[8][nbins] u32 | lut[nbins] u16 | meta[nbins] u16
-    extern __shared__ uint32_t sh[];
     constexpr int nb = 1 << (3 * G);
-    uint32_t* base = sh;
-    uint32_t* wc = sh + nb;
-    uint16_t* lut = reinterpret_cast<uint16_t*>(wc + kScatterWarps * nb);
-    uint16_t* meta = lut + nb;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CodeT* sc0 = reinterpret_cast<CodeT*>(smem_raw);
+    CodeT* sc1 = sc0 + kTilePoints;
+    CodeT* sc2 = sc1 + kTilePoints;
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(sc2 + kTilePoints);
+    uint32_t* scol = sidx + kTilePoints;
+    uint32_t* base = scol + kTilePoints;          // [nb]
+    uint32_t* cnt = base + nb;                    // [warps][nb]
+    uint16_t* slb = reinterpret_cast<uint16_t*>(cnt + kScatterWarps * nb);  // [tile]
+    uint16_t* lut = slb + kTilePoints;            // [nb]
+    uint16_t* meta = lut + nb;                    // [nb]
 
     const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
@@ -376,7 +424,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
     // (1) exclusive prefix of this node's earlier tiles, per digit -> inclusive scan over digits
     const uint32_t* pfx = a.d_tile_counts + (size_t)blockIdx.x * nb;
     for (int b = tid; b < nb; b += kScatterThreads) {
-        wc[b] = pfx[b];
+        cnt[b] = pfx[b];
         lut[b] = a.d_lut[(size_t)t.active * nb + b];
     }
     __syncthreads();
@@ -384,7 +432,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
         const int per = (nb + 31) / 32;
         const int b0 = lane * per, b1 = min(nb, b0 + per);
         uint32_t s = 0;
-        for (int b = b0; b < b1; ++b) s += wc[b];
+        for (int b = b0; b < b1; ++b) s += cnt[b];
         uint32_t incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -393,8 +441,8 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
         }
         uint32_t run = incl - s;
         for (int b = b0; b < b1; ++b) {
-            run += wc[b];
-            wc[b] = run;  // inclusive over digits
+            run += cnt[b];
+            cnt[b] = run;  // inclusive over digits
         }
     }
     __syncthreads();
@@ -404,7 +452,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
         uint32_t v = 0;
         uint16_t mt = 0;
         if (bd.b1 != 0) {
-            const uint32_t hi = wc[bd.b1 - 1], lo = bd.b0 ? wc[bd.b0 - 1] : 0u;
+            const uint32_t hi = cnt[bd.b1 - 1], lo = bd.b0 ? cnt[bd.b0 - 1] : 0u;
             v = (uint32_t)bd.dest + (hi - lo);
             mt = (uint16_t)(bd.keep | (bd.kind << 8));
         }
@@ -412,78 +460,54 @@ __global__ void __launch_bounds__(kScatterThreads) k_scatter(const __grid_consta
         meta[lb] = mt;
     }
     __syncthreads();
+    for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
+    __syncthreads();
 
-    for (uint32_t r0 = 0; r0 < t.count; r0 += kRoundPoints) {
-        for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) wc[i] = 0;
-
-        CodeT cj[kScatterItems][G][3];
-        unsigned bin[kScatterItems];
-        uint32_t idxs[kScatterItems], cols[kScatterItems], lbs[kScatterItems], rank[kScatterItems];
-        // phase 1: descent (speculatively through the reciprocal division; redone with the IEEE operator if any
-        // numerator of the block was outside the proven range)
-        if (a.lv.fast) {
-            const unsigned bad = scatter_round_chain<ROOT, WIDE, G, true, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
-            if (__syncthreads_or((int)bad)) scatter_round_chain<ROOT, WIDE, G, false, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
-        } else {
-            scatter_round_chain<ROOT, WIDE, G, false, CodeT>(a, t, act, r0, warp, lane, cj, bin, idxs, cols);
+    // (3) sweep A (speculatively through the reciprocal division; redone with the IEEE operator if any numerator of
+    // the block was outside the proven range)
+    if (a.lv.fast) {
+        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
+        if (__syncthreads_or((int)bad)) {
+            for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
+            __syncthreads();
+            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
             __syncthreads();
         }
-        CodeT code[kScatterItems][3];
-#pragma unroll
-        for (int s = 0; s < kScatterItems; ++s) {
-            const uint32_t i = r0 + warp * (32 * kScatterItems) + s * 32 + lane;
-            const uint32_t lb = lut[bin[s]];
-            lbs[s] = i < t.count ? lb : 0xFFFFu;
-            const int keep = meta[lb] & 0xFF;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                CodeT c = cj[s][0][k];
-                if (G >= 2 && keep == 2) c = cj[s][G >= 2 ? 1 : 0][k];
-                if (G >= 3 && keep == 3) c = cj[s][G >= 3 ? 2 : 0][k];
-                code[s][k] = c;
-            }
-        }
-        // phase 2: stable rank inside the warp, sub-round by sub-round
-#pragma unroll
-        for (int s = 0; s < kScatterItems; ++s) {
-            const uint32_t lb = lbs[s];
-            const unsigned mask = __match_any_sync(0xffffffffu, lb);
-            const int leader = __ffs(mask) - 1;
-            uint32_t old = 0;
-            if (lane == leader && lb != 0xFFFFu) {
-                old = wc[warp * nb + lb];
-                wc[warp * nb + lb] = old + __popc(mask);
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[s] = old + __popc(mask & ((1u << lane) - 1u));
-            __syncwarp();
-        }
+    } else {
+        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
         __syncthreads();
-        // phase 3: exclusive scan over warps, advance the tile cursor
-        for (int lb = tid; lb < nb; lb += kScatterThreads) {
-            uint32_t run = base[lb];
+    }
+    // (4) exclusive scan over the warps per bucket, starting at the tile's first slot
+    for (int lb = tid; lb < nb; lb += kScatterThreads) {
+        uint32_t run = base[lb];
 #pragma unroll
-            for (int w = 0; w < kScatterWarps; ++w) {
-                const uint32_t c = wc[w * nb + lb];
-                wc[w * nb + lb] = run;
-                run += c;
-            }
-            base[lb] = run;
+        for (int w = 0; w < kScatterWarps; ++w) {
+            const uint32_t c = cnt[w * nb + lb];
+            cnt[w * nb + lb] = run;
+            run += c;
         }
-        __syncthreads();
-        // phase 4: write
-#pragma unroll
-        for (int s = 0; s < kScatterItems; ++s) {
-            const uint32_t lb = lbs[s];
-            if (lb != 0xFFFFu) {
-                const uint32_t dst = wc[warp * nb + lb] + rank[s];
-                const bool leaf = (meta[lb] >> 8) != 0;
-                uint64_t c64[3] = {(uint64_t)code[s][0], (uint64_t)code[s][1], (uint64_t)code[s][2]};
-                store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idxs[s]);
-                (leaf ? a.col_arena : a.col_next)[dst] = cols[s];
-            }
+    }
+    __syncthreads();
+    // (5) sweep B: stable rank inside the warp, sub-round by sub-round, and the final store
+    for (int s = 0; s < kSubRounds; ++s) {
+        const uint32_t i = warp * kWarpItems + s * 32 + lane;
+        const uint32_t lbv = slb[i];
+        const unsigned mask = __match_any_sync(0xffffffffu, lbv);
+        const int leader = __ffs(mask) - 1;
+        uint32_t old = 0;
+        if (lane == leader && lbv != 0xFFFFu) {
+            old = cnt[warp * nb + lbv];
+            cnt[warp * nb + lbv] = old + __popc(mask);
         }
-        __syncthreads();
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (lbv != 0xFFFFu) {
+            const uint32_t dst = old + __popc(mask & ((1u << lane) - 1u));
+            const bool leaf = (meta[lbv] >> 8) != 0;
+            const uint64_t c64[3] = {(uint64_t)sc0[i], (uint64_t)sc1[i], (uint64_t)sc2[i]};
+            store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, sidx[i]);
+            (leaf ? a.col_arena : a.col_next)[dst] = scol[i];
+        }
+        __syncwarp();
     }
 }
 
@@ -656,6 +680,7 @@ struct CudaBackend : Backend {
 
     explicit CudaBackend(cudaStream_t s) : stream(s) {
         for (auto& e : ev) PCV_CUDA_CHECK(cudaEventCreate(&e));
+        allow_smem_all();
     }
     ~CudaBackend() override {
         for (auto& e : ev)
@@ -709,7 +734,16 @@ struct CudaBackend : Backend {
     }
     void mark(int what) override { cudaEventRecord(ev[what], stream); }
 
-    static size_t scatter_smem(int nbins) { return (size_t)nbins * 4 * (1 + kScatterWarps) + (size_t)nbins * 2 * 2; }
+    template <bool ROOT, bool WIDE, int G>
+    static void allow_smem() {
+        cudaFuncSetAttribute(k_scatter<ROOT, WIDE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<WIDE>::bytes(1 << (3 * G)));
+    }
+    static void allow_smem_all() {
+        allow_smem<false, false, 1>(), allow_smem<false, false, 2>(), allow_smem<false, false, 3>();
+        allow_smem<true, false, 1>(), allow_smem<true, false, 2>(), allow_smem<true, false, 3>();
+        allow_smem<false, true, 1>(), allow_smem<false, true, 2>(), allow_smem<false, true, 3>();
+        allow_smem<true, true, 1>(), allow_smem<true, true, 2>(), allow_smem<true, true, 3>();
+    }
 
     template <bool ROOT, bool WIDE>
     void launch_hist(const PassArgs& a, size_t sm) {
@@ -759,7 +793,7 @@ struct CudaBackend : Backend {
             k_scatter<ROOT, WIDE, 3><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
     }
     void scatter(const PassArgs& a) override {
-        const size_t sm = scatter_smem(a.nbins);
+        const size_t sm = a.wide ? ScatterSmem<true>::bytes(a.nbins) : ScatterSmem<false>::bytes(a.nbins);
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
         prof_begin(K_SCATTER, a.npoints * ((a.root ? 27 : rec + 4) + rec + 4));
         if (a.root) {
