@@ -326,18 +326,20 @@ constexpr int kSubRounds = kWarpItems / 32;              // 8
 constexpr int kScatterU = 2;                             // sub-rounds in flight
 static_assert(kSubRounds % kScatterU == 0, "sub-rounds must be a multiple of the unroll");
 
+constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;  // root pass: the tile's rgb bytes, staged with 16-byte loads
+
 template <bool WIDE>
 struct ScatterSmem {
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
     static constexpr size_t bytes(int nb) {
-        return (size_t)kTilePoints * (3 * sizeof(CodeT) + 4 + 4 + 2) + (size_t)nb * 4 * (1 + kScatterWarps) + (size_t)nb * 2 * 2;
+        return (size_t)kTilePoints * (3 * sizeof(CodeT) + 4 + 4 + 2) + (size_t)nb * 4 * (1 + kScatterWarps) + (size_t)nb * 2 * 2 + kRgbStage;
     }
 };
 
 template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
 __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, CodeT* sc0, CodeT* sc1,
                                                     CodeT* sc2, uint32_t* sidx, uint32_t* scol, uint16_t* slb, const uint16_t* lut, const uint16_t* meta,
-                                                    uint32_t* cnt) {
+                                                    uint32_t* cnt, const uint8_t* srgb) {
     constexpr int nb = 1 << (3 * G);
     unsigned bad = 0;
     for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
@@ -353,7 +355,12 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
             } else {
                 PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx[u]);)
             }
-            col[u] = load_colour<ROOT>(a, t.start + i);
+            if (ROOT) {
+                const uint8_t* p = srgb + 3 * i;
+                col[u] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+            } else {
+                col[u] = __ldg(a.col_in + t.start + i);
+            }
             m[u][0] = act.m[0];
             m[u][1] = act.m[1];
             m[u][2] = act.m[2];
@@ -416,6 +423,7 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     uint16_t* slb = reinterpret_cast<uint16_t*>(cnt + kScatterWarps * nb);  // [tile]
     uint16_t* lut = slb + kTilePoints;            // [nb]
     uint16_t* meta = lut + nb;                    // [nb]
+    uint8_t* srgb = reinterpret_cast<uint8_t*>(meta + nb);  // root pass only: rgb bytes of the tile (+ alignment slack)
 
     const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
@@ -461,20 +469,37 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     }
     __syncthreads();
     for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
+    if (ROOT) {
+        // stage the tile's rgb bytes with aligned 16-byte loads (3-byte-strided per-thread loads are LSU-hostile)
+        const uint8_t* g0 = a.pts.rgb + 3 * t.start;
+        const uint32_t nbytes = 3 * t.count;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);  // srgb[mis + k] = g0[k]
+        const uint8_t* ga = g0 - mis;
+        const uint32_t nvec = (mis + nbytes + 15) / 16;
+        // the last vector may extend past the tile's bytes but never past the 16-byte granule that contains the
+        // array's last byte only if the allocation is 16-byte padded; read it byte-wise instead
+        for (uint32_t v = tid; v + 1 < nvec; v += kScatterThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldg(reinterpret_cast<const uint4*>(ga) + v);
+        if (tid < 16) {
+            const uint32_t k = (nvec - 1) * 16 + tid;
+            if (k >= mis && k < mis + nbytes) srgb[k] = __ldg(ga + k);
+            else if (nvec == 1 && k < mis) srgb[k] = 0;
+        }
+        srgb += mis;
+    }
     __syncthreads();
 
     // (3) sweep A (speculatively through the reciprocal division; redone with the IEEE operator if any numerator of
     // the block was outside the proven range)
     if (a.lv.fast) {
-        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
+        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
         if (__syncthreads_or((int)bad)) {
             for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
             __syncthreads();
-            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
+            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
             __syncthreads();
         }
     } else {
-        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt);
+        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
         __syncthreads();
     }
     // (4) exclusive scan over the warps per bucket, starting at the tile's first slot
