@@ -234,9 +234,9 @@ def run_ours(args):
         tname, tst = top
         achieved = tst["algorithmic_bytes"] / (tst["ms"] * 1e-3) / 1e9 if tst["ms"] > 0 else 0.0
         traffic = None
-        try:
+        try:  # DRAM bytes per launch from the committed `ncu --set full` capture (ratio to algorithmic bytes at N = 1e8)
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(tname)
+                traffic = json.load(f)[tname]["ratio"] * tst["algorithmic_bytes"] / max(1, tst["launches"])
         except Exception:
             pass
         out["roofline"] = {

@@ -1,0 +1,272 @@
+// pcv.hpp — header-only C++ host layer over the C ABI (pcv.h), mirroring the names, argument meaning and error behaviour
+// of the reference's Rust interface for this path, so that callers (and tests) read like the reference's own:
+//
+//   point_viewer::octree::build_octree                  src/octree/generation.rs:289-295   -> pcv::build_octree
+//   point_viewer::octree::Octree::{from_data_provider, get_visible_nodes, get_node_data, nodes_in_location}
+//                                                       src/octree/mod.rs:156,228,285,329  -> pcv::Octree
+//   point_viewer::iterator::{PointQuery, PointLocation, ParallelIterator::try_for_each_batch}
+//                                                       src/iterator.rs:13-20,66-72,255    -> pcv::PointQuery, pcv::ParallelIterator
+//   point_viewer::{PointsBatch, NodeId}                 src/lib.rs:102-107, src/octree/node.rs:52-111
+//
+// Error behaviour: the reference panics (unwrap) in build_octree / get_visible_nodes and returns Result elsewhere; here
+// every failure is a pcv::Error exception carrying the pcv_status and text (callers that want the panic semantics let it
+// propagate).  A consumer callback returning false cancels the stream (== Err -> ErrorKind::Channel).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pcv.h"
+
+namespace pcv {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+inline void check(int rc) {
+    if (rc != PCV_OK) throw Error(rc, pcv_last_error());
+}
+
+// NodeId: u128 = level << 120 | index (node.rs:52-111), Display "r" + octal path (node.rs:73-86)
+struct NodeId {
+    uint64_t high = 0, low = 0;
+    int level() const { return (int)(high >> 56); }
+    std::string to_string() const {
+        unsigned __int128 v = ((unsigned __int128)high << 64) | low;
+        std::string s(1, 'r');
+        for (int i = level() - 1; i >= 0; --i) s.push_back((char)('0' + (int)((v >> (3 * i)) & 7)));
+        return s;
+    }
+    bool operator==(const NodeId& o) const { return high == o.high && low == o.low; }
+};
+
+struct Aabb {  // Aabb::new takes inf/sup of the two corners (aabb.rs:19-24)
+    std::array<double, 3> min, max;
+    Aabb(std::array<double, 3> a, std::array<double, 3> b) {
+        for (int i = 0; i < 3; ++i) {
+            min[i] = a[i] < b[i] ? a[i] : b[i];
+            max[i] = a[i] < b[i] ? b[i] : a[i];
+        }
+    }
+};
+
+// PointsBatch (lib.rs:102-107): AoS positions + colour (U8Vec3) and optional intensity (F32)
+struct PointsBatch {
+    std::vector<std::array<double, 3>> position;
+    std::vector<std::array<uint8_t, 3>> color;
+    std::vector<float> intensity;         // empty if absent
+    std::vector<uint64_t> source_index;   // provenance (not in the reference)
+};
+
+// PointLocation (iterator.rs:13-20).  Frustum / Obb carry the fields the reference structs hold.
+struct PointLocation {
+    pcv_location raw{};
+    static PointLocation AllPoints() {
+        PointLocation l;
+        l.raw.kind = PCV_LOC_ALL;
+        return l;
+    }
+    static PointLocation from(const Aabb& b) {
+        PointLocation l;
+        l.raw.kind = PCV_LOC_AABB;
+        for (int i = 0; i < 3; ++i) {
+            l.raw.aabb_min[i] = b.min[i];
+            l.raw.aabb_max[i] = b.max[i];
+        }
+        return l;
+    }
+    // Frustum{query_from_clip, clip_from_query}: column-major 4x4 (nalgebra storage)
+    static PointLocation Frustum(const double clip_from_query[16], const double query_from_clip[16]) {
+        PointLocation l;
+        l.raw.kind = PCV_LOC_FRUSTUM;
+        for (int i = 0; i < 16; ++i) {
+            l.raw.clip_from_query[i] = clip_from_query[i];
+            l.raw.query_from_clip[i] = query_from_clip[i];
+        }
+        return l;
+    }
+    // Obb{query_from_obb, obb_from_query, half_extent}: isometries as tx,ty,tz,qi,qj,qk,qw
+    static PointLocation Obb(const double query_from_obb[7], const double obb_from_query[7], const double half_extent[3]) {
+        PointLocation l;
+        l.raw.kind = PCV_LOC_OBB;
+        for (int i = 0; i < 7; ++i) {
+            l.raw.query_from_obb[i] = query_from_obb[i];
+            l.raw.obb_from_query[i] = obb_from_query[i];
+        }
+        for (int i = 0; i < 3; ++i) l.raw.half_extent[i] = half_extent[i];
+        return l;
+    }
+};
+
+struct ClosedInterval {
+    double lower_bound, upper_bound;
+};
+struct PointQuery {  // iterator.rs:66-72 (attributes: colour is always delivered, intensity when the octree has it)
+    PointLocation location = PointLocation::AllPoints();
+    std::vector<ClosedInterval> filter_intervals;  // on "intensity"
+};
+
+class Context {
+   public:
+    explicit Context(int device = 0, uint64_t max_points_per_node = 0) {
+        pcv_config cfg{max_points_per_node, 0, 0};
+        check(pcv_create(device, &cfg, &h_));
+    }
+    ~Context() { pcv_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    pcv_ctx* raw() const { return h_; }
+
+   private:
+    pcv_ctx* h_ = nullptr;
+};
+
+struct NodeData {  // octree/mod.rs:147-152
+    pcv_node_meta meta;
+    std::vector<uint8_t> position, color;
+};
+
+class Octree {
+   public:
+    Octree(pcv_octree* o) : o_(o) { load_table(); }
+    // Octree::from_data_provider(OnDiskDataProvider{directory})
+    static Octree from_directory(Context& ctx, const std::string& dir) {
+        pcv_octree* o = nullptr;
+        check(pcv_octree_load_dir(ctx.raw(), dir.c_str(), &o));
+        return Octree(o);
+    }
+    Octree(Octree&& other) noexcept : o_(other.o_), nodes_(std::move(other.nodes_)) { other.o_ = nullptr; }
+    Octree(const Octree&) = delete;
+    ~Octree() {
+        if (o_) pcv_octree_free(o_);
+    }
+    const std::vector<pcv_node_meta>& nodes() const { return nodes_; }
+    int64_t num_points() const {
+        int64_t n = 0;
+        for (auto& m : nodes_) n += m.num_points;
+        return n;
+    }
+    std::vector<NodeId> get_visible_nodes(const double projection_matrix[16]) const {  // mod.rs:228 (panics if singular)
+        std::vector<uint64_t> ids(2 * nodes_.size() + 2);
+        uint64_t n = 0;
+        check(pcv_visible_nodes(o_, projection_matrix, ids.data(), nodes_.size(), &n));
+        return to_ids(ids, n);
+    }
+    std::vector<NodeId> nodes_in_location(const PointLocation& loc) const {  // mod.rs:329-331
+        std::vector<uint64_t> ids(2 * nodes_.size() + 2);
+        uint64_t n = 0;
+        check(pcv_nodes_in_location(o_, &loc.raw, ids.data(), nodes_.size(), &n));
+        return to_ids(ids, n);
+    }
+    NodeData get_node_data(const NodeId& id) const {  // mod.rs:285-307
+        for (auto& m : nodes_)
+            if (m.id_high == id.high && m.id_low == id.low) {
+                NodeData d;
+                d.meta = m;
+                const size_t bpc = m.position_encoding == 1 ? 1 : m.position_encoding == 2 ? 2 : m.position_encoding == 3 ? 4 : 8;
+                d.position.resize((size_t)m.num_points * 3 * bpc);
+                d.color.resize((size_t)m.num_points * 3);
+                check(pcv_octree_node_data(o_, id.high, id.low, d.position.data(), d.color.data(), nullptr, nullptr));
+                return d;
+            }
+        throw Error(PCV_ERR_NOT_FOUND, "node " + id.to_string() + " not found");
+    }
+    void write_to_directory(const std::string& dir) const { check(pcv_octree_write_dir(o_, dir.c_str())); }
+    pcv_octree* raw() const { return o_; }
+
+   private:
+    void load_table() {
+        uint64_t nn = 0;
+        check(pcv_octree_info(o_, &nn, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        nodes_.resize(nn);
+        check(pcv_octree_nodes(o_, nodes_.data(), nn));
+    }
+    static std::vector<NodeId> to_ids(const std::vector<uint64_t>& v, uint64_t n) {
+        std::vector<NodeId> out(n);
+        for (uint64_t i = 0; i < n; ++i) out[i] = NodeId{v[2 * i], v[2 * i + 1]};
+        return out;
+    }
+    pcv_octree* o_;
+    std::vector<pcv_node_meta> nodes_;
+};
+
+// build_octree(output_directory, resolution, bounding_box, input, attributes) — generation.rs:289-295.  `input` is drained on
+// the calling thread; colour is mandatory; attributes selects whether intensity is carried.  Returns the GPU-resident
+// octree as well (the reference returns ()).
+template <class BatchIterator>
+inline Octree build_octree(Context& ctx, const std::string& output_directory, double resolution, const Aabb& bounding_box, BatchIterator begin,
+                           BatchIterator end, const std::vector<std::string>& attributes = {"color"}) {
+    std::vector<std::array<double, 3>> pos;
+    std::vector<std::array<uint8_t, 3>> col;
+    std::vector<float> inten;
+    bool want_i = false;
+    for (auto& a : attributes) want_i = want_i || a == "intensity";
+    for (BatchIterator it = begin; it != end; ++it) {
+        const PointsBatch& b = *it;
+        if (b.color.size() != b.position.size()) throw Error(PCV_ERR_INVALID, "color is mandatory (on_disk.rs:23-33)");
+        pos.insert(pos.end(), b.position.begin(), b.position.end());
+        col.insert(col.end(), b.color.begin(), b.color.end());
+        if (want_i && !b.intensity.empty()) inten.insert(inten.end(), b.intensity.begin(), b.intensity.end());
+    }
+    pcv_points pts{};
+    const double* base = pos.empty() ? nullptr : pos[0].data();
+    pts.x = base;
+    pts.y = base ? base + 1 : nullptr;
+    pts.z = base ? base + 2 : nullptr;
+    pts.stride = 3;  // AoS Point3<f64>, no transpose
+    pts.rgb = col.empty() ? nullptr : col[0].data();
+    pts.intensity = (want_i && inten.size() == pos.size() && !inten.empty()) ? inten.data() : nullptr;
+    pts.n = pos.size();
+    pcv_octree* o = nullptr;
+    check(pcv_build_octree(ctx.raw(), &pts, resolution, bounding_box.min.data(), bounding_box.max.data(), &o));
+    Octree tree(o);
+    if (!output_directory.empty()) tree.write_to_directory(output_directory);
+    return tree;
+}
+
+// ParallelIterator::new(point_clouds, query, batch_size, num_threads, buffer_size).try_for_each_batch(func) — iterator.rs:238-257.
+// num_threads / buffer_size are accepted for signature parity; the GPU path streams on the caller's thread.
+class ParallelIterator {
+   public:
+    ParallelIterator(const std::vector<const Octree*>& point_clouds, const PointQuery& query, size_t batch_size, size_t /*num_threads*/ = 1,
+                     size_t /*buffer_size*/ = 4)
+        : clouds_(point_clouds), query_(query), batch_size_(batch_size) {}
+    // func returns true to continue, false to stop (== Err).  Returns true if every batch was consumed.
+    bool try_for_each_batch(const std::function<bool(PointsBatch&&)>& func) {
+        struct State {
+            const std::function<bool(PointsBatch&&)>* f;
+        } st{&func};
+        auto tramp = [](void* user, const pcv_batch* b) -> int {
+            State* s = (State*)user;
+            PointsBatch pb;
+            pb.position.resize(b->n);
+            pb.color.resize(b->n);
+            for (uint64_t i = 0; i < b->n; ++i) {
+                pb.position[i] = {b->xyz[3 * i], b->xyz[3 * i + 1], b->xyz[3 * i + 2]};
+                pb.color[i] = {b->rgb[3 * i], b->rgb[3 * i + 1], b->rgb[3 * i + 2]};
+            }
+            if (b->intensity) pb.intensity.assign(b->intensity, b->intensity + b->n);
+            pb.source_index.assign(b->src_index, b->src_index + b->n);
+            return (*s->f)(std::move(pb)) ? 0 : 1;
+        };
+        std::vector<pcv_interval> f;
+        for (auto& iv : query_.filter_intervals) f.push_back(pcv_interval{iv.lower_bound, iv.upper_bound});
+        for (const Octree* o : clouds_) {
+            const int rc = pcv_query_points(o->raw(), &query_.location.raw, f.empty() ? nullptr : f.data(), (uint32_t)f.size(), batch_size_, tramp, &st);
+            if (rc == PCV_ERR_CANCELLED) return false;
+            check(rc);
+        }
+        return true;
+    }
+
+   private:
+    std::vector<const Octree*> clouds_;
+    PointQuery query_;
+    size_t batch_size_;
+};
+
+}  // namespace pcv
