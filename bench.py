@@ -170,7 +170,7 @@ def run_ours(args):
         def step():
             return ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
 
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
         t = step()
         t.free()
     sampler = ClockSampler(local)

@@ -112,6 +112,14 @@ class TorchComm:
         self.dist.all_gather_object(lst, obj)
         return lst
 
+    def release_memory(self):
+        """Give torch's cached blocks back to the driver so that the library's own stream-ordered pool can use them."""
+        if self.device.type == "cuda":
+            import torch
+
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+
 
 # ---- CUDA implementation of the compute steps ---------------------------------------------------------------------
 class CudaOps:
@@ -239,11 +247,16 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     c2r = assign_cells(counts_k, nranks)
     xyz, rgb, inten, idx, send_counts = ops.pack(k, c2r, nranks, index_base)
     recv_counts = comm.exchange_counts(send_counts)
+    # one logical all-to-all, issued per attribute array; every send buffer is released as soon as it has been exchanged so
+    # that the peak footprint stays at (input + largest send + receive) instead of (input + all sends + all receives)
     r_xyz = comm.all_to_all(xyz, send_counts, recv_counts)
+    del xyz
+    comm.release_memory()
     r_rgb = comm.all_to_all(rgb, send_counts, recv_counts)
     r_idx = comm.all_to_all(idx, send_counts, recv_counts)
     r_int = comm.all_to_all(inten, send_counts, recv_counts) if inten is not None else None
-    del xyz, rgb, inten, idx
+    del rgb, inten, idx
+    comm.release_memory()
 
     # (4) independent local build of this rank's sub-trees
     local = ops.build_sharded(r_xyz, r_rgb, r_int, k, prefix_counts)

@@ -116,3 +116,28 @@ def test_synth_host_device_identical(ctx):
         torch.cuda.synchronize()
         assert np.array_equal(dx.cpu().numpy(), hx) and np.array_equal(dy.cpu().numpy(), hy) and np.array_equal(dz.cpu().numpy(), hz)
         assert np.array_equal(drgb.cpu().numpy(), hrgb)
+
+
+def test_degenerate_numerators_take_the_ieee_path(ctx):
+    """Zero, negative-zero, tiny (< 2^-500) and boundary coordinates: the reciprocal-division fast path flags them and the
+    block repeats its tile with the IEEE operator; results stay bit-identical to the oracle."""
+    import point_cloud_viewer_b200 as pcv
+
+    rng = np.random.default_rng(17)
+    n = 60000
+    P = rng.random((n, 3))
+    P[:5000] = 0.0
+    P[5000:6000, 0] = -0.0
+    P[6000:7000, 1] = 1e-200
+    P[7000:8000, 2] = 5e-324
+    P[8000:9000] = 1.0  # on the max corner
+    P[9000:10000] = 0.5  # exactly on the centre planes (strict > decides)
+    x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
+    rgb = rng.integers(0, 255, n * 3, dtype=np.uint8)
+    for maxpts, res in ((300, 1e-4), (2000, 1e-9)):
+        c = pcv.Context(0, max_points_per_node=maxpts)
+        tree = c.build_octree(x, y, z, rgb, res, (0, 0, 0), (1, 1, 1))
+        ref = O.build(x, y, z, rgb.reshape(-1, 3), res, (0, 0, 0), (1, 1, 1), max_points_per_node=maxpts)
+        compare_trees(ref, tree)
+        tree.free()
+        c.close()

@@ -66,3 +66,19 @@ def test_aos_stride():
     t = TbTree(flat[0:], flat[1:], flat[2:], rgb, 0.01, P.min(0), P.max(0), 500, 3, stride=3)
     x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
     compare_trees(O.build(x, y, z, rgb.reshape(-1, 3), 0.01, P.min(0), P.max(0), max_points_per_node=500), t)
+
+
+def test_degenerate_numerators():
+    rng = np.random.default_rng(17)
+    n = 30000
+    P = rng.random((n, 3))
+    P[:3000] = 0.0
+    P[3000:3500, 0] = -0.0
+    P[3500:4000, 1] = 1e-200
+    P[4000:4500, 2] = 5e-324
+    P[4500:5000] = 1.0
+    P[5000:5500] = 0.5
+    x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
+    rgb = rng.integers(0, 255, n * 3, dtype=np.uint8)
+    ref = O.build(x, y, z, rgb.reshape(-1, 3), 1e-6, (0, 0, 0), (1, 1, 1), max_points_per_node=200)
+    compare_trees(ref, TbTree(x, y, z, rgb, 1e-6, (0, 0, 0), (1, 1, 1), 200, 2))
