@@ -188,6 +188,11 @@ int pcv_synth_points_device(pcv_ctx* ctx, int kind, uint64_t seed, uint64_t firs
 int pcv_synth_points_host(int kind, uint64_t seed, uint64_t first_index, uint64_t n, double* x, double* y, double* z, uint8_t* rgb);
 int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* resolution);
 
+/* ---- device memory from the context's stream-ordered pool (so that callers' staging buffers, e.g. the all-to-all
+ * send/receive buffers of the sharded build, share one allocator with the build's working set) --------------------- */
+int pcv_device_alloc(pcv_ctx* ctx, uint64_t bytes, void** out); /* usable on any stream after the call returns */
+int pcv_device_free(pcv_ctx* ctx, void* ptr);                   /* caller guarantees its own streams are done with it */
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 typedef struct pcv_build_stats {
     uint64_t kernel_launches; /* CUDA kernels launched by the last build on this context           */

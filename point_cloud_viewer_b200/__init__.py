@@ -96,6 +96,10 @@ class Context:
         N.check(N.lib().pcv_octree_load_dir(self.h, str(directory).encode(), C.byref(out)))
         return Octree(self, out)
 
+    def device_buffer(self, shape, typestr):
+        """Device memory from the context's pool, viewable by torch through __cuda_array_interface__ (typestr e.g. '<f8')."""
+        return DeviceBuffer(self, shape, typestr)
+
     def last_build_stats(self):
         s = N.BuildStats()
         N.check(N.lib().pcv_last_build_stats(self.h, C.byref(s)))
@@ -147,6 +151,40 @@ class Context:
         N.check(N.lib().pcv_assemble_top(self.h, float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(pc), _p(un), _p(xyz_codes), _p(rgb), _p(intensity),
                                          npts, C.byref(out)))
         return Octree(self, out)
+
+
+class DeviceBuffer:
+    """A block of the context's stream-ordered pool exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ctx, shape, typestr):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in shape)
+        itemsize = int(typestr[2:])
+        nbytes = itemsize
+        for s in self.shape:
+            nbytes *= s
+        p = C.c_void_p()
+        N.check(N.lib().pcv_device_alloc(ctx.h, max(nbytes, 16), C.byref(p)))
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def tensor(self):
+        import torch
+
+        t = torch.as_tensor(self, device="cuda:%d" % self.ctx.device)
+        t._pcv_owner = self  # keep the block alive as long as the view
+        return t
+
+    def free(self):
+        if self.ptr and self.ctx.h:
+            N.lib().pcv_device_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def synth_points_host(kind, seed, first, n):

@@ -134,6 +134,8 @@ SYMBOLS = [
     ("pcv_synth_points_device", C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_synth_points_host", C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_synth_bbox", C.c_int, [C.c_int, _dp, _dp, _dp]),
+    ("pcv_device_alloc", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("pcv_device_free", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcv_last_build_stats", C.c_int, [C.c_void_p, C.POINTER(BuildStats)]),
     ("pcv_kernel_launch_count", C.c_uint64, [C.c_void_p]),
     ("pcv_set_profiling", C.c_int, [C.c_void_p, C.c_int]),

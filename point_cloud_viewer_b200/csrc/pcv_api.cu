@@ -294,6 +294,24 @@ void pcv_octree_free(pcv_octree* o) {
     delete o;
 }
 
+int pcv_device_alloc(pcv_ctx* c, uint64_t bytes, void** out) {
+    if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    *out = c->be->dmalloc(bytes);
+    CU(cudaStreamSynchronize(c->stream));
+    return PCV_OK;
+    API_CATCH
+}
+int pcv_device_free(pcv_ctx* c, void* ptr) {
+    if (!c) return fail(PCV_ERR_INVALID, "null context");
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    c->be->dfree(ptr);
+    return PCV_OK;
+}
+
 int pcv_last_build_stats(pcv_ctx* c, pcv_build_stats* out) {
     if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
     *out = c->stats;

@@ -100,10 +100,11 @@ class TorchComm:
         self.dist.all_to_all_single(r, s)
         return r.cpu().numpy()
 
-    def all_to_all(self, tensor, send_counts, recv_counts):
+    def all_to_all(self, tensor, send_counts, recv_counts, alloc=None):
         import torch
 
-        out = torch.empty((int(np.sum(recv_counts)),) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        n = int(np.sum(recv_counts))
+        out = alloc(tensor, n) if alloc is not None else torch.empty((n,) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
         self.dist.all_to_all_single(out, tensor.contiguous(), output_split_sizes=[int(v) for v in recv_counts], input_split_sizes=[int(v) for v in send_counts])
         return out
 
@@ -112,13 +113,16 @@ class TorchComm:
         self.dist.all_gather_object(lst, obj)
         return lst
 
-    def release_memory(self):
-        """Give torch's cached blocks back to the driver so that the library's own stream-ordered pool can use them."""
+    def done_with(self, *tensors):
+        """The exchange that read these send buffers has completed: pool-backed buffers go back to the library's pool."""
         if self.device.type == "cuda":
             import torch
 
             torch.cuda.synchronize()
-            torch.cuda.empty_cache()
+        for t in tensors:
+            owner = getattr(t, "_pcv_owner", None) if t is not None else None
+            if owner is not None:
+                owner.free()
 
 
 # ---- CUDA implementation of the compute steps ---------------------------------------------------------------------
@@ -141,10 +145,11 @@ class CudaOps:
         import torch
 
         n = self.n
-        xyz = torch.empty((n, 3), dtype=torch.float64, device=self.device)
-        rgb = torch.empty((n, 3), dtype=torch.uint8, device=self.device)
-        inten = torch.empty(n, dtype=torch.float32, device=self.device) if self.intensity is not None else None
-        idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        # send buffers come from the library's pool (one allocator for staging + build working set: no cudaMalloc churn)
+        xyz = self.ctx.device_buffer((n, 3), "<f8").tensor()
+        rgb = self.ctx.device_buffer((n, 3), "|u1").tensor()
+        inten = self.ctx.device_buffer((n,), "<f4").tensor() if self.intensity is not None else None
+        idx = self.ctx.device_buffer((n,), "<i8").tensor()
         counts = self.ctx.prefix_pack_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.rgb.data_ptr(),
                                              self.intensity.data_ptr() if self.intensity is not None else None, None, index_base, n, self.res, self.bmin,
                                              self.bmax, k, cell_to_rank, nranks, xyz.data_ptr(), rgb.data_ptr(), inten.data_ptr() if inten is not None else None,
@@ -158,6 +163,10 @@ class CudaOps:
 
     def assemble_top(self, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten):
         return self.ctx.assemble_top(self.res, self.bmin, self.bmax, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten)
+
+    def recv_buffer(self, like, n):
+        ts = {"torch.float64": "<f8", "torch.uint8": "|u1", "torch.float32": "<f4", "torch.int64": "<i8"}[str(like.dtype)]
+        return self.ctx.device_buffer((n,) + tuple(like.shape[1:]), ts).tensor()
 
 
 class ShardedOctree:
@@ -222,6 +231,19 @@ def _take(index, src):
 
 def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=100000):
     """Backend-neutral orchestration (see module docstring)."""
+    import os
+    import time
+
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):
+        if os.environ.get("PCV_TIMING"):
+            if hasattr(comm, "device") and getattr(comm.device, "type", "cpu") == "cuda":
+                import torch
+
+                torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
     res, bmin, bmax = ops.res, np.asarray(ops.bmin, np.float64), np.asarray(ops.bmax, np.float64)
     lo, hi = np.minimum(bmin, bmax), np.maximum(bmin, bmax)
     root_edge = max(max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])
@@ -233,6 +255,7 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     gmn, gmx = comm.all_reduce_minmax(lmn if ops.n else [np.inf] * 3, lmx if ops.n else [-np.inf] * 3)
     inside = bool((gmn >= lo).all() and (gmx <= hi).all())
 
+    mark("bbox")
     # (1) global histogram of level-k cells
     k = int(prefix_levels)
     counts_k = comm.all_reduce_sum_u64(ops.prefix_histogram(k))
@@ -243,23 +266,29 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     levels = level_counts(counts_k, k)
     prefix_counts = concat_counts(levels)
 
+    mark("histogram")
     # (2) cells -> ranks, (3) stable pack + one all-to-all
     c2r = assign_cells(counts_k, nranks)
     xyz, rgb, inten, idx, send_counts = ops.pack(k, c2r, nranks, index_base)
+    mark("pack")
     recv_counts = comm.exchange_counts(send_counts)
     # one logical all-to-all, issued per attribute array; every send buffer is released as soon as it has been exchanged so
     # that the peak footprint stays at (input + largest send + receive) instead of (input + all sends + all receives)
-    r_xyz = comm.all_to_all(xyz, send_counts, recv_counts)
+    alloc = getattr(ops, "recv_buffer", None)
+    a2a = (lambda t: comm.all_to_all(t, send_counts, recv_counts, alloc)) if alloc is not None else (lambda t: comm.all_to_all(t, send_counts, recv_counts))
+    r_xyz = a2a(xyz)
+    comm.done_with(xyz)
     del xyz
-    comm.release_memory()
-    r_rgb = comm.all_to_all(rgb, send_counts, recv_counts)
-    r_idx = comm.all_to_all(idx, send_counts, recv_counts)
-    r_int = comm.all_to_all(inten, send_counts, recv_counts) if inten is not None else None
+    r_rgb = a2a(rgb)
+    r_idx = a2a(idx)
+    r_int = a2a(inten) if inten is not None else None
+    comm.done_with(rgb, idx, inten)
     del rgb, inten, idx
-    comm.release_memory()
 
+    mark("all_to_all")
     # (4) independent local build of this rank's sub-trees
     local = ops.build_sharded(r_xyz, r_rgb, r_int, k, prefix_counts)
+    mark("local build")
     stats = local.ctx.last_build_stats() if hasattr(local, "ctx") and hasattr(local.ctx, "last_build_stats") else {}
 
     # (5) top of the tree: unit sizes, collectors' content -> rank 0
@@ -306,6 +335,9 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
         t_xyz, t_rgb, top_index = cat(0, np.uint8), cat(1, np.uint8), cat(3, np.uint64)
         t_int = cat(2, np.float32) if (keys and allp[keys[0]][2] is not None) else None
         top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
+    mark("top assembly")
+    if os.environ.get("PCV_TIMING") and rank == 0:
+        print("[pcv sharded] " + "  ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), flush=True)
     out = ShardedOctree(local, top, k, r_idx, top_index, c2r, rank, stats)
     out.bbox_inside = inside
     out.recv_points = int(np.sum(recv_counts))
