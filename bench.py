@@ -150,9 +150,18 @@ def run_ours(args):
     kind = pcv.SYNTH_GAUSS_CLUSTERS
     bmin, bmax, res = pcv.synth_bbox(kind)
     ctx = pcv.Context(local, levels_per_pass=args.levels_per_pass)
-    x, y, z = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
-    rgb = torch.empty(n * 3, dtype=torch.uint8, device=dev)
-    ctx.synth_points_device(kind, SEED, rank * n, n, x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr())
+
+    def make_input():
+        if world > 1:  # pool-backed so that the sharded build can release it right after the pack (memory: DESIGN.md 7)
+            xs = [ctx.device_buffer((n,), "<f8").tensor() for _ in range(3)]
+            c = ctx.device_buffer((n * 3,), "|u1").tensor()
+        else:
+            xs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+            c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+        ctx.synth_points_device(kind, SEED, rank * n, n, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
+        return xs[0], xs[1], xs[2], c
+
+    x, y, z, rgb = make_input()
 
     def barrier():
         torch.cuda.synchronize()
@@ -164,7 +173,7 @@ def run_ours(args):
         from point_cloud_viewer_b200 import distributed as D
 
         def step():
-            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
+            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels, consume_input=True)
     else:
 
         def step():
@@ -173,30 +182,38 @@ def run_ours(args):
     for w in range(args.warmup):
         t = step()
         t.free()
+        if world > 1:
+            del x, y, z, rgb
+            x, y, z, rgb = make_input()
     sampler = ClockSampler(local)
     launches0 = ctx.kernel_launch_count()
     barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    w0 = time.perf_counter()
     dev_ms = 0.0
+    wall_ms = 0.0
     last = None
     for _ in range(args.steps):
         if last is not None:
             last.free()
+            if world > 1:  # the sharded build consumed its input: regenerate it outside the timed region
+                del x, y, z, rgb
+                x, y, z, rgb = make_input()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        w0 = time.perf_counter()
         last = step()
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        wall_ms += (time.perf_counter() - w0) * 1e3
         if world == 1:
             dev_ms += ctx.last_build_stats()["ms_total"]
-    torch.cuda.synchronize()
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3
-    if world > 1:
-        # every phase of a sharded step ends in a host-visible synchronisation (histogram read-back, all-to-all, build),
-        # so the event pair on the current stream brackets exactly the device timeline of the K steps
-        dev_ms = e0.elapsed_time(e1)
+        else:
+            # every phase of a sharded step ends in a host-visible synchronisation (histogram read-back, all-to-all, build),
+            # so the event pair on the current stream brackets exactly the device timeline of the step
+            dev_ms += e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launch_count() - launches0
     # device time of the K steps: CUDA events on the library's stream around every build, max over ranks

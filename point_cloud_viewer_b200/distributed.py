@@ -129,7 +129,8 @@ class TorchComm:
 class CudaOps:
     """x, y, z: torch cuda float64 tensors (SoA); rgb: uint8 (n*3); intensity: float32 or None."""
 
-    def __init__(self, ctx, x, y, z, rgb, intensity, resolution, bmin, bmax):
+    def __init__(self, ctx, x, y, z, rgb, intensity, resolution, bmin, bmax, consume_input=False):
+        self.consume_input = consume_input  # release pool-backed input tensors as soon as they have been packed
         self.ctx, self.x, self.y, self.z, self.rgb, self.intensity = ctx, x, y, z, rgb, intensity
         self.res, self.bmin, self.bmax = resolution, bmin, bmax
         self.n = x.numel()
@@ -154,6 +155,12 @@ class CudaOps:
                                              self.intensity.data_ptr() if self.intensity is not None else None, None, index_base, n, self.res, self.bmin,
                                              self.bmax, k, cell_to_rank, nranks, xyz.data_ptr(), rgb.data_ptr(), inten.data_ptr() if inten is not None else None,
                                              idx.data_ptr())
+        if self.consume_input:
+            for t in (self.x, self.y, self.z, self.rgb, self.intensity):
+                owner = getattr(t, "_pcv_owner", None) if t is not None else None
+                if owner is not None:
+                    owner.free()
+            self.x = self.y = self.z = self.rgb = self.intensity = None
         return xyz, rgb, inten, idx, counts.astype(np.int64)
 
     def build_sharded(self, xyz, rgb, inten, k, prefix_counts):
@@ -344,8 +351,11 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     return out
 
 
-def build_octree_sharded(ctx, x, y, z, rgb, intensity, index_base, resolution, bbox_min, bbox_max, prefix_levels=2, max_points_per_node=100000):
-    """GPU entry point used by bench.py: torch cuda tensors in, ShardedOctree out (torch.distributed must be initialised)."""
-    ops = CudaOps(ctx, x, y, z, rgb, intensity, resolution, bbox_min, bbox_max)
+def build_octree_sharded(ctx, x, y, z, rgb, intensity, index_base, resolution, bbox_min, bbox_max, prefix_levels=2, max_points_per_node=100000,
+                         consume_input=False):
+    """GPU entry point used by bench.py: torch cuda tensors in, ShardedOctree out (torch.distributed must be initialised).
+    consume_input=True releases pool-backed (Context.device_buffer) input tensors right after the pack, which is what lets
+    1e9 points per GPU fit: input 27 GB -> send 35 GB -> receive 35 GB -> build working set ~80 GB, never all at once."""
+    ops = CudaOps(ctx, x, y, z, rgb, intensity, resolution, bbox_min, bbox_max, consume_input=consume_input)
     comm = TorchComm(x.device)
     return build_sharded(ops, comm, index_base, prefix_levels, max_points_per_node)
