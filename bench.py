@@ -147,17 +147,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = int(args.points)
+    if world > 1 and args.points_multi > 0:
+        # The sharded build stages every point twice (send + receive buffers, 35 B/pt each) next to the input (27 B/pt)
+        # and the build's working set (~80 B/pt): 1e9 points per GPU would need ~177 GB of the 180 GB.  N > 1 therefore
+        # runs a fixed 5e8 points per GPU (weak scaling across N = 2, 4, 8); N = 1 keeps BASELINE config 2 (1e9).
+        n = int(args.points_multi)
     kind = pcv.SYNTH_GAUSS_CLUSTERS
     bmin, bmax, res = pcv.synth_bbox(kind)
     ctx = pcv.Context(local, levels_per_pass=args.levels_per_pass)
 
     def make_input():
-        if world > 1:  # pool-backed so that the sharded build can release it right after the pack (memory: DESIGN.md 7)
-            xs = [ctx.device_buffer((n,), "<f8").tensor() for _ in range(3)]
-            c = ctx.device_buffer((n * 3,), "|u1").tensor()
-        else:
-            xs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
-            c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+        xs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+        c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
         ctx.synth_points_device(kind, SEED, rank * n, n, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
         return xs[0], xs[1], xs[2], c
 
@@ -173,7 +174,7 @@ def run_ours(args):
         from point_cloud_viewer_b200 import distributed as D
 
         def step():
-            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels, consume_input=True)
+            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
     else:
 
         def step():
@@ -182,9 +183,6 @@ def run_ours(args):
     for w in range(args.warmup):
         t = step()
         t.free()
-        if world > 1:
-            del x, y, z, rgb
-            x, y, z, rgb = make_input()
     sampler = ClockSampler(local)
     launches0 = ctx.kernel_launch_count()
     barrier()
@@ -196,9 +194,6 @@ def run_ours(args):
     for _ in range(args.steps):
         if last is not None:
             last.free()
-            if world > 1:  # the sharded build consumed its input: regenerate it outside the timed region
-                del x, y, z, rgb
-                x, y, z, rgb = make_input()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -356,6 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=float, default=1e9, help="points per GPU per step")
+    ap.add_argument("--points-multi", type=float, default=5e8, help="points per GPU per step when --gpus > 1 (0: use --points)")
     ap.add_argument("--levels-per-pass", type=int, default=2)
     ap.add_argument("--prefix-levels", type=int, default=2)
     ap.add_argument("--frusta", type=int, default=1000)
