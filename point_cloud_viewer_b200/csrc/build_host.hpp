@@ -334,7 +334,7 @@ class BuildPlan {
         void* bufs[2] = {nullptr, nullptr};
         uint32_t* cols[2] = {nullptr, nullptr};
         void* arena = be.dmalloc((size_t)pts.n * rec_bytes);
-        uint32_t* col_arena = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
+        uint32_t* col_arena = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
         uint64_t arena_used = 0;
         int cur = -1;  // -1: raw input
         std::vector<void*> scratch;
@@ -382,7 +382,7 @@ class BuildPlan {
                 int nxt = cur < 0 ? 0 : 1 - cur;
                 if (!bufs[nxt]) {
                     bufs[nxt] = be.dmalloc((size_t)pts.n * rec_bytes);
-                    cols[nxt] = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
+                    cols[nxt] = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
                 }
                 pa.rec_next = bufs[nxt];
                 pa.arena = arena;
@@ -599,7 +599,7 @@ class BuildPlan {
         const auto ts3 = tnow();
         R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
         R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
-        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4);
+        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
         R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
         const auto ts4 = tnow();
         PlaceArgs pl{};

@@ -313,53 +313,108 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
 // scatter
 // ------------------------------------------------------------------------------------------------
 // One block (16 warps) per 4096-point tile, warp w owns the contiguous items [256 w, 256 w + 256).
-//   sweep A  descent of every item (2 sub-rounds of 32 items in flight per warp); destination bucket, kept codes, source
-//            index and colour are staged in shared memory; per-warp bucket counts with __match_any_sync
+//   stage    the tile's input records and colours are contiguous in HBM: one elected thread issues two TMA bulk copies
+//            (cp.async.bulk global -> shared, completion on an mbarrier) that overlap the bucket-table set-up
+//   sweep A  descent of every item (2 sub-rounds of 32 items in flight per warp) from the staged record; the kept codes
+//            replace the record's codes in shared memory (index and colour pass through); destination bucket staged
+//            next to it; per-warp bucket counts with __match_any_sync
 //   scan     exclusive prefix over the warps per bucket, on top of the tile's first slot (from the histogram prefix)
 //   sweep B  every warp walks its items in order, ranks them inside the sub-round with __match_any_sync and writes the
 //            staged record to its slot (next pass segment or leaf arena)
-// Two block barriers per tile; the order inside every bucket is the tile order, i.e. the input order (stable).
+// Two block barriers per tile after set-up; the order inside every bucket is the tile order, i.e. input order (stable).
 constexpr int kScatterThreads = 512;
 constexpr int kScatterWarps = kScatterThreads / 32;
 constexpr int kWarpItems = kTilePoints / kScatterWarps;  // 256
 constexpr int kSubRounds = kWarpItems / 32;              // 8
 constexpr int kScatterU = 2;                             // sub-rounds in flight
 static_assert(kSubRounds % kScatterU == 0, "sub-rounds must be a multiple of the unroll");
-
 constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;  // root pass: the tile's rgb bytes, staged with 16-byte loads
 
 template <bool WIDE>
 struct ScatterSmem {
-    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
-    static constexpr size_t bytes(int nb) {
-        return (size_t)kTilePoints * (3 * sizeof(CodeT) + 4 + 4 + 2) + (size_t)nb * 4 * (1 + kScatterWarps) + (size_t)nb * 2 * 2 + kRgbStage;
+    static constexpr size_t rec_bytes = WIDE ? 32 : 16;
+    __host__ __device__ static constexpr size_t bytes(int nb) {
+        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 2 + (size_t)nb * 4 * (1 + kScatterWarps) +
+               (size_t)nb * 2 * 2 + kRgbStage + 16;
     }
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    uint64_t state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;" : "=l"(state) : "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    (void)state;
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void smem_load_rec(const unsigned char* srec, uint32_t i, uint64_t c[3], uint32_t& idx) {
+    if (WIDE) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(srec) + 2 * (size_t)i;
+        const ulonglong2 v0 = p[0], v1 = p[1];
+        c[0] = v0.x, c[1] = v0.y, c[2] = v1.x, idx = (uint32_t)v1.y;
+    } else {
+        const uint4 v = reinterpret_cast<const uint4*>(srec)[i];
+        c[0] = v.x, c[1] = v.y, c[2] = v.z, idx = v.w;
+    }
+}
+template <bool WIDE>
+__device__ __forceinline__ void smem_store_rec(unsigned char* srec, uint32_t i, const uint64_t c[3], uint32_t idx) {
+    if (WIDE) {
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(srec) + 2 * (size_t)i;
+        p[0] = make_ulonglong2(c[0], c[1]);
+        p[1] = make_ulonglong2(c[2], (unsigned long long)idx);
+    } else {
+        reinterpret_cast<uint4*>(srec)[i] = make_uint4((uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2], idx);
+    }
+}
+
 template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
-__device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, CodeT* sc0, CodeT* sc1,
-                                                    CodeT* sc2, uint32_t* sidx, uint32_t* scol, uint16_t* slb, const uint16_t* lut, const uint16_t* meta,
-                                                    uint32_t* cnt, const uint8_t* srgb) {
+__device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, unsigned char* srec,
+                                                    uint32_t* scol, uint16_t* slb, const uint16_t* lut, const uint16_t* meta, uint32_t* cnt, const uint8_t* srgb) {
     constexpr int nb = 1 << (3 * G);
     unsigned bad = 0;
     for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
         double q[kScatterU][3], m[kScatterU][3];
-        uint32_t idx[kScatterU], col[kScatterU];
+        uint32_t idx[kScatterU];
         unsigned bin[kScatterU];
         CodeT cj[kScatterU][G][3];
 #pragma unroll
         for (int u = 0; u < kScatterU; ++u) {
-            const uint32_t i = min((uint32_t)(warp * kWarpItems + (s0 + u) * 32 + lane), t.count - 1);
+            const uint32_t i = warp * kWarpItems + (s0 + u) * 32 + lane;
+            const bool valid = i < t.count;
             if (ROOT) {
-                load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[u], idx[u]);
+                const uint32_t ic = min(i, t.count - 1);
+                load_position_t<true, WIDE, ENC_F64>(a, t, act, ic, q[u], idx[u]);
+                if (valid) {
+                    const uint8_t* p = srgb + 3 * i;
+                    scol[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+                }
             } else {
-                PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx[u]);)
-            }
-            if (ROOT) {
-                const uint8_t* p = srgb + 3 * i;
-                col[u] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-            } else {
-                col[u] = __ldg(a.col_in + t.start + i);
+                uint64_t c[3] = {0, 0, 0};  // lanes past the end of the tile descend from the cube's min corner (harmless)
+                idx[u] = 0;
+                if (valid) smem_load_rec<WIDE>(srec, i, c, idx[u]);
+                PCV_ENC_SWITCH(a.lv.enc[a.level], _Pragma("unroll") for (int k = 0; k < 3; ++k) q[u][k] = decode_axis<ENC>(c[k], act.m[k], act.e);)
             }
             m[u][0] = act.m[0];
             m[u][1] = act.m[1];
@@ -387,18 +442,15 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
             const uint32_t lb = lut[bin[u]];
             const uint32_t lbv = i < t.count ? lb : 0xFFFFu;
             const int keep = meta[lb & (nb - 1)] & 0xFF;
-            CodeT c[3];
+            uint64_t c[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                c[k] = cj[u][0][k];
-                if (G >= 2 && keep == 2) c[k] = cj[u][G >= 2 ? 1 : 0][k];
-                if (G >= 3 && keep == 3) c[k] = cj[u][G >= 3 ? 2 : 0][k];
+                CodeT v = cj[u][0][k];
+                if (G >= 2 && keep == 2) v = cj[u][G >= 2 ? 1 : 0][k];
+                if (G >= 3 && keep == 3) v = cj[u][G >= 3 ? 2 : 0][k];
+                c[k] = (uint64_t)v;
             }
-            sc0[i] = c[0];
-            sc1[i] = c[1];
-            sc2[i] = c[2];
-            sidx[i] = idx[u];
-            scol[i] = col[u];
+            if (lbv != 0xFFFFu) smem_store_rec<WIDE>(srec, i, c, idx[u]);
             slb[i] = (uint16_t)lbv;
             const unsigned mask = __match_any_sync(0xffffffffu, lbv);
             if (lbv != 0xFFFFu && lane == __ffs(mask) - 1) cnt[warp * nb + lbv] += __popc(mask);
@@ -412,22 +464,37 @@ template <bool ROOT, bool WIDE, int G>
 __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const __grid_constant__ PassArgs a) {
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
     constexpr int nb = 1 << (3 * G);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CodeT* sc0 = reinterpret_cast<CodeT*>(smem_raw);
-    CodeT* sc1 = sc0 + kTilePoints;
-    CodeT* sc2 = sc1 + kTilePoints;
-    uint32_t* sidx = reinterpret_cast<uint32_t*>(sc2 + kTilePoints);
-    uint32_t* scol = sidx + kTilePoints;
-    uint32_t* base = scol + kTilePoints;          // [nb]
-    uint32_t* cnt = base + nb;                    // [warps][nb]
-    uint16_t* slb = reinterpret_cast<uint16_t*>(cnt + kScatterWarps * nb);  // [tile]
-    uint16_t* lut = slb + kTilePoints;            // [nb]
-    uint16_t* meta = lut + nb;                    // [nb]
-    uint8_t* srgb = reinterpret_cast<uint8_t*>(meta + nb);  // root pass only: rgb bytes of the tile (+ alignment slack)
+    constexpr size_t recsz = ScatterSmem<WIDE>::rec_bytes;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* srec = smem_raw;                                                      // [tile] records (AoS, as in HBM)
+    uint32_t* scol_base = reinterpret_cast<uint32_t*>(srec + (size_t)kTilePoints * recsz);  // [tile + 4] colours
+    uint32_t* base = scol_base + kTilePoints + 4;                                        // [nb]
+    uint32_t* cnt = base + nb;                                                           // [warps][nb]
+    uint16_t* slb = reinterpret_cast<uint16_t*>(cnt + kScatterWarps * nb);               // [tile]
+    uint16_t* lut = slb + kTilePoints;                                                   // [nb]
+    uint16_t* meta = lut + nb;                                                           // [nb]
+    uint8_t* srgb = reinterpret_cast<uint8_t*>(meta + nb);                               // root pass only: rgb bytes of the tile
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + ((ScatterSmem<WIDE>::bytes(nb) - 8) & ~(size_t)7));
 
     const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // (0) TMA: bulk-copy the tile's records and colours into shared memory while the tables below are set up
+    uint32_t* scol = scol_base;
+    if (!ROOT) {
+        const uint32_t coff = (uint32_t)(t.start & 3);  // the colour source must be 16-byte aligned: start 0..3 entries early
+        scol = scol_base + coff;
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t rec_bytes = t.count * (uint32_t)recsz;
+            const uint32_t col_bytes = ((coff + t.count) * 4u + 15u) & ~15u;
+            mbar_expect_tx(mbar, rec_bytes + col_bytes);
+            tma_bulk_load(srec, reinterpret_cast<const unsigned char*>(a.rec_in) + t.start * recsz, rec_bytes, mbar);
+            tma_bulk_load(scol_base, a.col_in + (t.start - coff), col_bytes, mbar);
+        }
+    }
 
     // (1) exclusive prefix of this node's earlier tiles, per digit -> inclusive scan over digits
     const uint32_t* pfx = a.d_tile_counts + (size_t)blockIdx.x * nb;
@@ -476,30 +543,38 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
         const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);  // srgb[mis + k] = g0[k]
         const uint8_t* ga = g0 - mis;
         const uint32_t nvec = (mis + nbytes + 15) / 16;
-        // the last vector may extend past the tile's bytes but never past the 16-byte granule that contains the
-        // array's last byte only if the allocation is 16-byte padded; read it byte-wise instead
         for (uint32_t v = tid; v + 1 < nvec; v += kScatterThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldg(reinterpret_cast<const uint4*>(ga) + v);
-        if (tid < 16) {
+        if (tid < 16) {  // the last vector byte-wise: never read past the array's last byte
             const uint32_t k = (nvec - 1) * 16 + tid;
             if (k >= mis && k < mis + nbytes) srgb[k] = __ldg(ga + k);
-            else if (nvec == 1 && k < mis) srgb[k] = 0;
         }
         srgb += mis;
+    } else {
+        mbar_wait(mbar, 0);  // the staged records / colours have landed
     }
     __syncthreads();
 
     // (3) sweep A (speculatively through the reciprocal division; redone with the IEEE operator if any numerator of
-    // the block was outside the proven range)
+    // the block was outside the proven range - the codes in shared memory are only replaced by valid lanes, so the
+    // second run must start from the original records: reload them)
     if (a.lv.fast) {
-        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
+        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
         if (__syncthreads_or((int)bad)) {
             for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
+            if (!ROOT) {  // restore the input records (sweep A overwrote their codes)
+                for (uint32_t i = tid; i < t.count; i += kScatterThreads) {
+                    uint64_t c[3];
+                    uint32_t idx;
+                    load_rec<WIDE>(a.rec_in, t.start + i, c, idx);
+                    smem_store_rec<WIDE>(srec, i, c, idx);
+                }
+            }
             __syncthreads();
-            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
+            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
             __syncthreads();
         }
     } else {
-        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, sc0, sc1, sc2, sidx, scol, slb, lut, meta, cnt, srgb);
+        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
         __syncthreads();
     }
     // (4) exclusive scan over the warps per bucket, starting at the tile's first slot
@@ -528,8 +603,10 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
         if (lbv != 0xFFFFu) {
             const uint32_t dst = old + __popc(mask & ((1u << lane) - 1u));
             const bool leaf = (meta[lbv] >> 8) != 0;
-            const uint64_t c64[3] = {(uint64_t)sc0[i], (uint64_t)sc1[i], (uint64_t)sc2[i]};
-            store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, sidx[i]);
+            uint64_t c64[3];
+            uint32_t idx;
+            smem_load_rec<WIDE>(srec, i, c64, idx);
+            store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idx);
             (leaf ? a.col_arena : a.col_next)[dst] = scol[i];
         }
         __syncwarp();
