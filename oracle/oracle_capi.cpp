@@ -5,6 +5,7 @@
 
 #include "oracle_build.hpp"
 #include "oracle_disk.hpp"
+#include "oracle_ply.hpp"
 #include "oracle_query.hpp"
 
 using namespace orc;
@@ -308,6 +309,46 @@ void orc_octree_meta(void* hp, double* resolution, double* bbox6, int* with_inte
     bbox6[4] = h->oct.bbox.maxs.y;
     bbox6[5] = h->oct.bbox.maxs.z;
     *with_intensity = h->oct.with_intensity ? 1 : 0;
+}
+
+// ---- PLY input (oracle_ply.hpp) ----
+struct orc_ply_info {
+    uint64_t num_points, header_bytes;
+    uint32_t record_bytes;
+    int32_t has_color, has_intensity, num_fields;
+    double offset[3];
+};
+static thread_local std::string g_ply_err;
+const char* orc_ply_error() { return g_ply_err.c_str(); }
+int orc_ply_open(const char* path, orc_ply_info* out) {
+    PlyLayout L;
+    if (!ply_open(path, L, g_ply_err)) return -1;
+    out->num_points = (uint64_t)L.num_points;
+    out->header_bytes = L.header.header_len;
+    out->record_bytes = L.record_bytes;
+    out->has_color = L.has_color;
+    out->has_intensity = L.has_intensity;
+    out->num_fields = (int32_t)L.fields.size();
+    for (int a = 0; a < 3; ++a) out->offset[a] = L.header.offset[a];
+    return 0;
+}
+// field i of the vertex record: role (PlyRole), type (PlyType), byte offset, bytes consumed
+int orc_ply_field(const char* path, int i, int32_t* role, int32_t* type, uint32_t* offset, uint32_t* bytes) {
+    PlyLayout L;
+    if (!ply_open(path, L, g_ply_err) || i < 0 || i >= (int)L.fields.size()) return -1;
+    *role = L.fields[i].role;
+    *type = L.fields[i].type;
+    *offset = L.fields[i].offset;
+    *bytes = L.fields[i].bytes;
+    return 0;
+}
+int orc_ply_read(const char* path, uint64_t first, uint64_t count, double* x, double* y, double* z, uint8_t* rgb, float* intensity) {
+    PlyLayout L;
+    if (!ply_open(path, L, g_ply_err)) return -1;
+    return ply_read_range(path, L, first, count, x, y, z, L.has_color ? rgb : nullptr, L.has_intensity ? intensity : nullptr, g_ply_err) ? 0 : -1;
+}
+int orc_ply_find_bounding_box(const char* path, double* out6) {
+    return ply_find_bounding_box(path, out6, out6 + 3, g_ply_err) ? 0 : -1;
 }
 
 }  // extern "C"

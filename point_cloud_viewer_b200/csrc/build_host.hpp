@@ -139,6 +139,7 @@ struct PlaceArgs {
     uint32_t nleaves;
     uint32_t ntiles;
     uint64_t npoints, xyz_bytes;
+    uint32_t prefetch_tiles = 0;  // device backends: L2-prefetch the leaf tile this many blocks ahead (0 = off)
     uint8_t* out_xyz;
     uint8_t* out_rgb;
     float* out_intensity;

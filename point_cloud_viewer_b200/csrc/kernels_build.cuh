@@ -91,6 +91,19 @@ __global__ void __launch_bounds__(256) k_bbox(PointsView p, double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// L2 prefetch of the tile the SM will work on one wave later
+// ------------------------------------------------------------------------------------------------
+// k_place streams leaf tiles whose addresses are known long before they are needed.  One thread asks the TMA unit to
+// pull the tile that is about one wave of resident blocks away into L2 (cp.async.bulk.prefetch.L2: no registers, no L1
+// lines, no completion to wait for), so that when that block runs its loads hit L2 instead of HBM (measured at N = 1e9:
+// k_place 13.4 -> 11.2 ms; the same prefetch did not help k_hist / k_scatter, whose time is not load latency).  The byte
+// range is shrunk to 16-byte alignment inside [p, p + bytes): nothing outside the caller's range is ever touched.
+__device__ __forceinline__ void l2_prefetch(const void* p, uint64_t bytes) {
+    const uintptr_t b = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
+    const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(uintptr_t)15;
+    if (e > b) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b), "r"((uint32_t)(e - b)) : "memory");
+}
+// ------------------------------------------------------------------------------------------------
 // record load / store helpers
 // ------------------------------------------------------------------------------------------------
 template <bool WIDE>
@@ -191,9 +204,11 @@ template <bool ROOT, bool WIDE, int ENC_IN>
 __device__ __forceinline__ void load_position_t(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i, double q[3], uint32_t& idx) {
     const uint64_t g = t.start + i;
     if (ROOT) {
-        q[0] = __ldg(a.pts.x + g * a.pts.stride);
-        q[1] = __ldg(a.pts.y + g * a.pts.stride);
-        q[2] = __ldg(a.pts.z + g * a.pts.stride);
+        // streamed once: bypass L1 (ld.global.cg).  The scatter kernel leaves only ~29 KB of L1 next to its shared
+        // memory, too few lines for the loads in flight if they allocated there.
+        q[0] = __ldcg(a.pts.x + g * a.pts.stride);
+        q[1] = __ldcg(a.pts.y + g * a.pts.stride);
+        q[2] = __ldcg(a.pts.z + g * a.pts.stride);
         idx = (uint32_t)g;
     } else {
         uint64_t c[3];
@@ -318,10 +333,12 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
 //   sweep A  descent of every item (2 sub-rounds of 32 items in flight per warp) from the staged record; the kept codes
 //            replace the record's codes in shared memory (index and colour pass through); destination bucket staged
 //            next to it; per-warp bucket counts with __match_any_sync
-//   scan     exclusive prefix over the warps per bucket, on top of the tile's first slot (from the histogram prefix)
-//   sweep B  every warp walks its items in order, ranks them inside the sub-round with __match_any_sync and writes the
-//            staged record to its slot (next pass segment or leaf arena)
-// Two block barriers per tile after set-up; the order inside every bucket is the tile order, i.e. input order (stable).
+//   scan     per-bucket totals, exclusive prefix over the buckets (sorted start inside the tile) and over the warps
+//   sweep B1 every warp walks its items in order and writes (item, bucket) at the item's stable sorted position: the tile
+//            is sorted by bucket as a permutation in shared memory
+//   sweep B2 consecutive threads store consecutive records of a bucket's run to the next pass segment or the leaf arena:
+//            a warp's store covers a few contiguous runs instead of up to 32 scattered 16-byte slots (and pages)
+// The order inside every bucket is the tile order, i.e. input order (stable).
 constexpr int kScatterThreads = 512;
 constexpr int kScatterWarps = kScatterThreads / 32;
 constexpr int kWarpItems = kTilePoints / kScatterWarps;  // 256
@@ -334,8 +351,8 @@ template <bool WIDE>
 struct ScatterSmem {
     static constexpr size_t rec_bytes = WIDE ? 32 : 16;
     __host__ __device__ static constexpr size_t bytes(int nb) {
-        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 2 + (size_t)nb * 4 * (1 + kScatterWarps) +
-               (size_t)nb * 2 * 2 + kRgbStage + 16;
+        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 4 + (size_t)nb * 4 * (2 + kScatterWarps) +
+               (size_t)nb * 4 + kRgbStage + 16;
     }
 };
 
@@ -391,7 +408,7 @@ __device__ __forceinline__ void smem_store_rec(unsigned char* srec, uint32_t i, 
 
 template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
 __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, unsigned char* srec,
-                                                    uint32_t* scol, uint16_t* slb, const uint16_t* lut, const uint16_t* meta, uint32_t* cnt, const uint8_t* srgb) {
+                                                    uint32_t* sinfo, const uint32_t* lutm, uint32_t* cnt) {
     constexpr int nb = 1 << (3 * G);
     unsigned bad = 0;
     for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
@@ -406,10 +423,6 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
             if (ROOT) {
                 const uint32_t ic = min(i, t.count - 1);
                 load_position_t<true, WIDE, ENC_F64>(a, t, act, ic, q[u], idx[u]);
-                if (valid) {
-                    const uint8_t* p = srgb + 3 * i;
-                    scol[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-                }
             } else {
                 uint64_t c[3] = {0, 0, 0};  // lanes past the end of the tile descend from the cube's min corner (harmless)
                 idx[u] = 0;
@@ -439,9 +452,9 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
 #pragma unroll
         for (int u = 0; u < kScatterU; ++u) {
             const uint32_t i = warp * kWarpItems + (s0 + u) * 32 + lane;
-            const uint32_t lb = lut[bin[u]];
-            const uint32_t lbv = i < t.count ? lb : 0xFFFFu;
-            const int keep = meta[lb & (nb - 1)] & 0xFF;
+            const uint32_t lm = lutm[bin[u]];  // local bucket | keep << 16
+            const uint32_t lbv = i < t.count ? (lm & 0xFFFFu) : 0xFFFFu;
+            const int keep = (lm >> 16) & 0xFF;
             uint64_t c[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -451,10 +464,11 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
                 c[k] = (uint64_t)v;
             }
             if (lbv != 0xFFFFu) smem_store_rec<WIDE>(srec, i, c, idx[u]);
-            slb[i] = (uint16_t)lbv;
+            // group the sub-round's lanes by bucket once; sweep B reuses rank / leader / group size
             const unsigned mask = __match_any_sync(0xffffffffu, lbv);
-            if (lbv != 0xFFFFu && lane == __ffs(mask) - 1) cnt[warp * nb + lbv] += __popc(mask);
-            __syncwarp();
+            const uint32_t leader = (uint32_t)__ffs(mask) - 1u, gsize = (uint32_t)__popc(mask), rank = (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            sinfo[i] = lbv | (rank << 16) | (leader << 21) | ((gsize - 1u) << 26);
+            if (lbv != 0xFFFFu && lane == (int)leader) atomicAdd(&cnt[warp * nb + lbv], gsize);
         }
     }
     return bad;
@@ -468,12 +482,11 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* srec = smem_raw;                                                      // [tile] records (AoS, as in HBM)
     uint32_t* scol_base = reinterpret_cast<uint32_t*>(srec + (size_t)kTilePoints * recsz);  // [tile + 4] colours
-    uint32_t* base = scol_base + kTilePoints + 4;                                        // [nb]
-    uint32_t* cnt = base + nb;                                                           // [warps][nb]
-    uint16_t* slb = reinterpret_cast<uint16_t*>(cnt + kScatterWarps * nb);               // [tile]
-    uint16_t* lut = slb + kTilePoints;                                                   // [nb]
-    uint16_t* meta = lut + nb;                                                           // [nb]
-    uint8_t* srgb = reinterpret_cast<uint8_t*>(meta + nb);                               // root pass only: rgb bytes of the tile
+    uint2* bdst = reinterpret_cast<uint2*>(scol_base + kTilePoints + 4);                 // [nb] {first slot of this tile, sorted start | leaf << 31}
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(bdst + nb);                              // [warps][nb]
+    uint32_t* sinfo = cnt + kScatterWarps * nb;                                          // [tile] bucket | rank | leader | group size | leaf
+    uint32_t* lutm = sinfo + kTilePoints;                                                // [nb] digit -> bucket | keep << 16 | leaf << 24
+    uint8_t* srgb = reinterpret_cast<uint8_t*>(lutm + nb);                               // root pass only: rgb bytes of the tile
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + ((ScatterSmem<WIDE>::bytes(nb) - 8) & ~(size_t)7));
 
     const TileDesc t = tile_of(a, blockIdx.x);
@@ -500,7 +513,7 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     const uint32_t* pfx = a.d_tile_counts + (size_t)blockIdx.x * nb;
     for (int b = tid; b < nb; b += kScatterThreads) {
         cnt[b] = pfx[b];
-        lut[b] = a.d_lut[(size_t)t.active * nb + b];
+        lutm[b] = 0xFFFFu;  // digits without points keep an invalid bucket
     }
     __syncthreads();
     if (warp == 0) {
@@ -525,14 +538,13 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     for (int lb = tid; lb < nb; lb += kScatterThreads) {
         const BucketDesc bd = a.d_buckets[(size_t)t.active * nb + lb];
         uint32_t v = 0;
-        uint16_t mt = 0;
         if (bd.b1 != 0) {
             const uint32_t hi = cnt[bd.b1 - 1], lo = bd.b0 ? cnt[bd.b0 - 1] : 0u;
             v = (uint32_t)bd.dest + (hi - lo);
-            mt = (uint16_t)(bd.keep | (bd.kind << 8));
+            // every digit of the bucket's range learns (bucket, keep, leaf) in one table entry
+            for (uint32_t d = bd.b0; d < bd.b1; ++d) lutm[d] = (uint32_t)lb | ((uint32_t)bd.keep << 16);
         }
-        base[lb] = v;
-        meta[lb] = mt;
+        bdst[lb] = make_uint2(v, bd.b1 != 0 && bd.kind ? 0x80000000u : 0u);
     }
     __syncthreads();
     for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
@@ -543,12 +555,26 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
         const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);  // srgb[mis + k] = g0[k]
         const uint8_t* ga = g0 - mis;
         const uint32_t nvec = (mis + nbytes + 15) / 16;
-        for (uint32_t v = tid; v + 1 < nvec; v += kScatterThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldg(reinterpret_cast<const uint4*>(ga) + v);
+        for (uint32_t v = tid; v + 1 < nvec; v += kScatterThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldcg(reinterpret_cast<const uint4*>(ga) + v);
         if (tid < 16) {  // the last vector byte-wise: never read past the array's last byte
             const uint32_t k = (nvec - 1) * 16 + tid;
             if (k >= mis && k < mis + nbytes) srgb[k] = __ldg(ga + k);
         }
-        srgb += mis;
+        __syncthreads();
+        // colours of 4 consecutive points are 12 staged bytes: 4 aligned words, funnel-shifted by the misalignment, give
+        // the 4 packed colours with one 16-byte store (instead of 3 byte loads and a store per point inside sweep A)
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(srgb);
+        for (uint32_t k = tid; 4 * k < t.count; k += kScatterThreads) {
+            const uint32_t byte0 = mis + 12 * k, wi = byte0 >> 2, sh = (byte0 & 3) * 8;
+            const uint32_t w0 = w[wi], w1 = w[wi + 1], w2 = w[wi + 2], w3 = w[wi + 3];
+            const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+            uint4 c;  // a0 = r0 g0 b0 r1 | a1 = g1 b1 r2 g2 | a2 = b2 r3 g3 b3 (little endian)
+            c.x = a0 & 0xFFFFFFu;
+            c.y = (a0 >> 24) | ((a1 & 0xFFFFu) << 8);
+            c.z = (a1 >> 16) | ((a2 & 0xFFu) << 16);
+            c.w = a2 >> 8;
+            reinterpret_cast<uint4*>(scol)[k] = c;
+        }
     } else {
         mbar_wait(mbar, 0);  // the staged records / colours have landed
     }
@@ -558,7 +584,7 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     // the block was outside the proven range - the codes in shared memory are only replaced by valid lanes, so the
     // second run must start from the original records: reload them)
     if (a.lv.fast) {
-        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
+        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
         if (__syncthreads_or((int)bad)) {
             for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
             if (!ROOT) {  // restore the input records (sweep A overwrote their codes)
@@ -570,16 +596,44 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
                 }
             }
             __syncthreads();
-            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
+            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
             __syncthreads();
         }
     } else {
-        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, scol, slb, lut, meta, cnt, srgb);
+        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
         __syncthreads();
     }
-    // (4) exclusive scan over the warps per bucket, starting at the tile's first slot
+    // (4) sort the tile by bucket inside shared memory (as a permutation) so that the global stores are coalesced runs:
+    //     per-bucket totals -> exclusive scan over the buckets (sorted start of every bucket) -> per-warp offsets
     for (int lb = tid; lb < nb; lb += kScatterThreads) {
-        uint32_t run = base[lb];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < kScatterWarps; ++w) tot += cnt[w * nb + lb];
+        lutm[lb] = tot;  // the digit table is dead after sweep A
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int per = (nb + 31) / 32;
+        const int b0 = lane * per, b1 = min(nb, b0 + per);
+        uint32_t sum = 0;
+        for (int b = b0; b < b1; ++b) sum += lutm[b];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        uint32_t run = incl - sum;
+        for (int b = b0; b < b1; ++b) {
+            const uint32_t c = lutm[b];
+            lutm[b] = run;  // exclusive: sorted position of the bucket's first record
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int lb = tid; lb < nb; lb += kScatterThreads) {
+        uint32_t run = lutm[lb];
+        bdst[lb].y |= run;
 #pragma unroll
         for (int w = 0; w < kScatterWarps; ++w) {
             const uint32_t c = cnt[w * nb + lb];
@@ -587,29 +641,39 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
             run += c;
         }
     }
+    // every thread takes the sweep-A notes of its items into registers: the permutation is built in the same array
+    uint32_t info[kSubRounds];
+#pragma unroll
+    for (int s = 0; s < kSubRounds; ++s) info[s] = sinfo[warp * kWarpItems + s * 32 + lane];
     __syncthreads();
-    // (5) sweep B: stable rank inside the warp, sub-round by sub-round, and the final store
+    // (5) sweep B1: stable sorted position of every item (warp by warp, sub-round by sub-round, rank inside the group)
+    uint32_t* perm = sinfo;  // [tile] item index | bucket << 12, in sorted order
+#pragma unroll
     for (int s = 0; s < kSubRounds; ++s) {
         const uint32_t i = warp * kWarpItems + s * 32 + lane;
-        const uint32_t lbv = slb[i];
-        const unsigned mask = __match_any_sync(0xffffffffu, lbv);
-        const int leader = __ffs(mask) - 1;
+        const uint32_t lbv = info[s] & 0xFFFFu, rank = (info[s] >> 16) & 31u, gsize = ((info[s] >> 26) & 31u) + 1u;
+        const int leader = (int)((info[s] >> 21) & 31u);
         uint32_t old = 0;
         if (lane == leader && lbv != 0xFFFFu) {
             old = cnt[warp * nb + lbv];
-            cnt[warp * nb + lbv] = old + __popc(mask);
+            cnt[warp * nb + lbv] = old + gsize;
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        if (lbv != 0xFFFFu) {
-            const uint32_t dst = old + __popc(mask & ((1u << lane) - 1u));
-            const bool leaf = (meta[lbv] >> 8) != 0;
-            uint64_t c64[3];
-            uint32_t idx;
-            smem_load_rec<WIDE>(srec, i, c64, idx);
-            store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idx);
-            (leaf ? a.col_arena : a.col_next)[dst] = scol[i];
-        }
+        if (lbv != 0xFFFFu) perm[old + rank] = i | (lbv << 12);
         __syncwarp();
+    }
+    __syncthreads();
+    // (6) sweep B2: consecutive threads store consecutive records of a bucket's run (next pass segment or leaf arena)
+    for (uint32_t p = tid; p < t.count; p += kScatterThreads) {
+        const uint32_t e = perm[p], i = e & (kTilePoints - 1), lb = e >> 12;
+        const uint2 bd = bdst[lb];
+        const bool leaf = (bd.y >> 31) != 0;
+        const uint32_t dst = bd.x + (p - (bd.y & 0x7FFFFFFFu));
+        uint64_t c64[3];
+        uint32_t idx;
+        smem_load_rec<WIDE>(srec, i, c64, idx);
+        store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idx);
+        (leaf ? a.col_arena : a.col_next)[dst] = scol[i];
     }
 }
 
@@ -712,6 +776,14 @@ template <bool WIDE>
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
     const LeafTile lt = leaf_tile_of(a, blockIdx.x);
     const DNode leaf = a.d_nodes[lt.node];
+    if (threadIdx.x == 32 && a.prefetch_tiles) {  // leaf tiles are consecutive in the arena
+        const uint64_t first = lt.arena_start + (uint64_t)a.prefetch_tiles * kPlaceTile;
+        if (first < a.npoints) {
+            const uint64_t cnt = min((uint64_t)kPlaceTile, a.npoints - first), rb = WIDE ? 32 : 16;
+            l2_prefetch(reinterpret_cast<const unsigned char*>(a.arena) + first * rb, cnt * rb);
+            l2_prefetch(a.col_arena + first, cnt * 4);
+        }
+    }
     // A tile whose start rank is not a multiple of 8 (top assembly: a collector's points start at arbitrary ranks), or
     // whose node ends the walk (root / collector), goes through the generic per-point path.
     const bool generic = leaf.parent < 0 || (lt.j0 & 7) != 0;
@@ -856,6 +928,18 @@ struct CudaBackend : Backend {
         else
             k_hist<ROOT, WIDE, 3><<<a.ntiles, 256, sm, stream>>>(a);
     }
+    // prefetch distance = blocks resident at once (SMs x blocks per SM); 0 disables (PCV_NO_PREFETCH=1 for experiments)
+    int sms = 0;
+    bool no_prefetch = false;
+    uint32_t resident(int blocks_per_sm) {
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            no_prefetch = std::getenv("PCV_NO_PREFETCH") != nullptr;
+        }
+        return no_prefetch ? 0u : (uint32_t)(sms * blocks_per_sm);
+    }
     void hist(const PassArgs& a) override {
         const size_t sm = (size_t)a.nbins * 4;
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
@@ -913,8 +997,10 @@ struct CudaBackend : Backend {
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
-    void place(const PlaceArgs& a) override {
-        if (a.ntiles == 0) return;
+    void place(const PlaceArgs& a_in) override {
+        if (a_in.ntiles == 0) return;
+        PlaceArgs a = a_in;
+        a.prefetch_tiles = resident(4);
         prof_begin(K_PLACE, a.npoints * ((a.wide ? sizeof(RecW) : sizeof(RecN)) + 3 + 3 + 4 + (a.out_intensity ? 8 : 0)) + a.xyz_bytes);
         if (a.wide)
             k_place<true><<<a.ntiles, 256, 0, stream>>>(a);

@@ -14,7 +14,8 @@ ctx.synth_points_device(kind, 1, 0, n, x.data_ptr(), y.data_ptr(), z.data_ptr(),
 bmin, bmax, res = pcv.synth_bbox(kind)
 t0 = time.time(); mn, mx = ctx.bbox(x.data_ptr(), y.data_ptr(), z.data_ptr(), n=n, device=True); t1 = time.time()
 print("bbox", mn, mx, "%.2f ms" % ((t1 - t0) * 1e3))
-for it in range(3):
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+for it in range(iters):
     t0 = time.time()
     tree = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
     t1 = time.time()
@@ -23,3 +24,9 @@ for it in range(3):
         n, G, (t1 - t0) * 1e3, s["ms_total"], s["ms_partition"], s["ms_place"], s["ms_host_plan"], s["ms_host_wait"], s["passes"], s["kernel_launches"], s["num_nodes"], s["deepest_level"],
         n / s["ms_total"] / 1e3, s["algorithmic_bytes"] / s["ms_total"] / 1e6))
     tree.free()
+
+ctx.set_profiling(True)
+tree = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
+for k, v in sorted(ctx.kernel_stats().items(), key=lambda kv: -kv[1]["ms"]):
+    print("  %-22s launches %3d  %8.3f ms  %7.1f algo GB/s" % (k, v["launches"], v["ms"], v["algorithmic_bytes"] / max(v["ms"], 1e-9) / 1e6))
+tree.free()

@@ -36,6 +36,11 @@ class Location(C.Structure):
     ]
 
 
+class PlyInfo(C.Structure):
+    _fields_ = [("num_points", C.c_uint64), ("header_bytes", C.c_uint64), ("record_bytes", C.c_uint32), ("has_color", C.c_int32),
+                ("has_intensity", C.c_int32), ("num_fields", C.c_int32), ("offset", C.c_double * 3)]
+
+
 _lib = None
 
 
@@ -88,6 +93,11 @@ def lib():
         L.orc_load_dir.restype = C.c_void_p
         L.orc_load_dir.argtypes = [C.c_char_p]
         L.orc_octree_meta.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_int)]
+        L.orc_ply_error.restype = C.c_char_p
+        L.orc_ply_open.argtypes = [C.c_char_p, C.POINTER(PlyInfo)]
+        L.orc_ply_field.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_ply_read.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ply_find_bounding_box.argtypes = [C.c_char_p, dp]
         _lib = L
     return _lib
 
@@ -214,3 +224,53 @@ def bbox(x, y, z, stride=1):
     n = len(x) if stride == 1 else len(x) // 1
     lib().orc_bbox(n, _ptr(x), _ptr(y), _ptr(z), stride, out)
     return tuple(out)
+
+
+# ---- PLY input (oracle/oracle_ply.hpp) ----
+class PlyError(Exception):
+    pass
+
+
+def ply_open(path):
+    info = PlyInfo()
+    if lib().orc_ply_open(os.fsencode(path), C.byref(info)) != 0:
+        raise PlyError(lib().orc_ply_error().decode())
+    return dict(num_points=info.num_points, header_bytes=info.header_bytes, record_bytes=info.record_bytes, has_color=bool(info.has_color),
+                has_intensity=bool(info.has_intensity), num_fields=info.num_fields, offset=tuple(info.offset))
+
+
+def ply_fields(path):
+    out = []
+    for i in range(ply_open(path)["num_fields"]):
+        role, typ, off, nb = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint32()
+        assert lib().orc_ply_field(os.fsencode(path), i, C.byref(role), C.byref(typ), C.byref(off), C.byref(nb)) == 0
+        out.append((role.value, typ.value, off.value, nb.value))
+    return out
+
+
+def ply_read(path, first=0, count=None):
+    """Points [first, first + count) as the PointsBatch stream delivers them: x, y, z (offset added), rgb (n, 3) or None, intensity or None."""
+    info = ply_open(path)
+    if count is None:
+        count = info["num_points"] - first
+    x, y, z = np.empty(count), np.empty(count), np.empty(count)
+    rgb = np.zeros((count, 3), np.uint8) if info["has_color"] else None
+    inten = np.zeros(count, np.float32) if info["has_intensity"] else None
+    rc = lib().orc_ply_read(os.fsencode(path), first, count, _ptr(x), _ptr(y), _ptr(z), _ptr(rgb) if rgb is not None else None,
+                            _ptr(inten) if inten is not None else None)
+    if rc != 0:
+        raise PlyError(lib().orc_ply_error().decode())
+    return x, y, z, rgb, inten
+
+
+def ply_batches(path, batch_size):
+    """PlyIterator::next (ply.rs:522-556): ceil(n / batch_size) batches, the last one short."""
+    n = ply_open(path)["num_points"]
+    return [ply_read(path, first, min(batch_size, n - first)) for first in range(0, n, batch_size)]
+
+
+def ply_find_bounding_box(path):
+    out = (C.c_double * 6)()
+    if lib().orc_ply_find_bounding_box(os.fsencode(path), out) != 0:
+        raise PlyError(lib().orc_ply_error().decode())
+    return tuple(out[:3]), tuple(out[3:])
