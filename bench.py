@@ -132,6 +132,60 @@ def make_frusta(pcv, bmin, bmax, count, far, seed=7):
     return locs
 
 
+def bench_ply(ctx, pcv, n, peak):
+    """build_octree_from_file's input side on a synthetic xyz-f32 + rgb-u8 PLY (15-byte records, page-cache resident)."""
+    import numpy as np
+
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    path = os.path.join(d, "pcv_bench_%d_%d.ply" % (os.getpid(), n))
+    rec = np.zeros(n, dtype=np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")]))
+    rng = np.random.default_rng(0)
+    for k, scale in (("x", 200.0), ("y", 200.0), ("z", 20.0)):
+        rec[k] = rng.random(n, dtype=np.float32) * scale
+    rec["red"] = np.arange(n, dtype=np.uint32) & 255
+    try:
+        with open(path, "wb") as f:
+            f.write(("ply\nformat binary_little_endian 1.0\ncomment offset: 4100000 660000 4700000\nelement vertex %d\nproperty float x\nproperty float y\n"
+                     "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n" % n).encode())
+            rec.tofile(f)
+        del rec
+        fbytes = os.path.getsize(path)
+        ctx.load_ply(path).free()  # warm-up: pinned ring, pool
+        ctx.set_profiling(True)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            pp = ctx.load_ply(path)
+            times.append((time.perf_counter() - t0) * 1e3)
+            pp.free()
+        ks = ctx.kernel_stats()["k_ply_unpack"]
+        ctx.set_profiling(False)
+        ms = sorted(times)[1]
+        t0 = time.perf_counter()
+        tree = ctx.build_octree_from_file(path, 0.001)
+        bms = (time.perf_counter() - t0) * 1e3
+        nodes = int(tree.num_nodes)
+        tree.free()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+
+        m = min(n, 5_000_000)
+        t0 = time.perf_counter()
+        O.ply_read(path, 0, m)
+        cms = (time.perf_counter() - t0) * 1e3
+        kg = ks["algorithmic_bytes"] / (ks["ms"] * 1e-3) / 1e9 if ks["ms"] > 0 else 0.0
+        return {"workload": "%d-point binary PLY (x,y,z float + r,g,b uchar, %d-byte records), page-cache resident" % (n, fbytes // max(1, n)),
+                "load_ms": ms, "Mpoints_per_s": n / (ms * 1e3), "file_GB_per_s": fbytes / (ms * 1e-3) / 1e9, "h2d_bytes": fbytes,
+                "kernel": {"name": "k_ply_unpack", "launches": ks["launches"], "ms": ks["ms"], "achieved_GBps": kg, "frac_of_hbm_peak": kg / peak,
+                           "algorithmic_bytes": ks["algorithmic_bytes"]},
+                "build_octree_from_file_ms": bms, "build_octree_from_file_Mpoints_per_s": n / (bms * 1e3), "octree_nodes": nodes,
+                "cpu_baseline": {"value": m / (cms * 1e3), "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                                 "sample": "first %d points through the oracle restatement of PlyIterator (single thread, as the reference)" % m}}
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -333,6 +387,12 @@ def run_ours(args):
                                    "sample": "first %d points of the same generator, one build (in-memory oracle port of build_octree, %d threads, %.1f s)" % (nc, cores, ct)}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + str(e)[:160]}
+
+        # ---- PLY input path: file -> pinned ring -> H2D -> k_ply_unpack (+ fused bounding box) ----
+        try:
+            out["ply_ingest"] = bench_ply(ctx, pcv, int(args.ply_points), peak)
+        except Exception as e:
+            out["ply_ingest"] = {"error": str(e)[:200]}
     else:
         out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "e2e is measured at N=1"}
         if last is not None:
@@ -356,6 +416,7 @@ def main():
     ap.add_argument("--prefix-levels", type=int, default=2)
     ap.add_argument("--frusta", type=int, default=1000)
     ap.add_argument("--cpu-points", type=float, default=2e7)
+    ap.add_argument("--ply-points", type=float, default=1e8, help="points of the synthetic PLY file for the ingest measurement")
     ap.add_argument("--ref-points", type=float, default=5e6)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

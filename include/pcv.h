@@ -181,6 +181,43 @@ int pcv_assemble_top(pcv_ctx* ctx, double resolution, const double bbox_min[3], 
                      const uint64_t* prefix_counts, const uint64_t* unit_nsub /* 8^k */, const void* xyz_codes, const uint8_t* rgb,
                      const float* intensity, uint64_t npoints, pcv_octree** out);
 
+/* ---- PLY input: src/read_write/ply.rs:126-229 (parse_header), :327-450
+ * (PlyIterator::from_file), :453-556 (batches), src/octree/generation.rs:256-287 (find_bounding_box,
+ * build_octree_from_file).  The file body goes to the GPU as raw vertex records through a pinned,
+ * double-buffered staging ring; one kernel turns the records into the SoA arrays pcv_build_octree_device
+ * takes (position = (x, y, z) as f64 + header offset, colour r,g,b, intensity) and reduces the bounding box
+ * in the same pass (the reference reads the whole file twice). ------------------------------------- */
+enum {  /* property types, ply.rs:43-73 */
+    PCV_PLY_I8 = 0, PCV_PLY_U8, PCV_PLY_I16, PCV_PLY_U16, PCV_PLY_I32, PCV_PLY_U32, PCV_PLY_I64, PCV_PLY_U64, PCV_PLY_F32, PCV_PLY_F64
+};
+typedef struct pcv_ply_info {
+    uint64_t num_points;   /* `element vertex N`                                                   */
+    uint64_t header_bytes; /* the body starts here (the vertex element must come first)            */
+    uint32_t record_bytes; /* bytes per vertex, skipped properties included                        */
+    int32_t has_color;     /* uchar red/green/blue (or r/g/b) present                              */
+    int32_t has_intensity; /* float `intensity` present                                            */
+    int32_t type_xyz[3];   /* PCV_PLY_* of x, y, z (cast to f64 like `as f64`; int8 reads unsigned) */
+    uint32_t off_xyz[3];   /* byte offsets inside the record                                       */
+    uint32_t off_rgb[3];
+    uint32_t off_intensity;
+    double offset[3];      /* `comment offset: x y z`, added to every position                     */
+} pcv_ply_info;
+/* Parses the header with the reference's rules and error conditions (where the reference panics — no vertex element,
+ * not binary_little_endian, missing x/y/z — this returns PCV_ERR_INVALID; unreadable file: PCV_ERR_IO). */
+int pcv_ply_read_header(const char* path, pcv_ply_info* out);
+/* Kernel-level entry: `n` raw records already in device memory (16-byte aligned) -> SoA arrays (device).  rgb /
+ * intensity may be NULL.  bbox_min/max (host, may be NULL) receive the component-wise min/max of the positions
+ * (Aabb::grow, aabb.rs:41-44); for n == 0 they are Aabb::zero (generation.rs:269). */
+int pcv_ply_unpack_device(pcv_ctx* ctx, const pcv_ply_info* info, const void* dev_records, uint64_t n, double* dev_x,
+                          double* dev_y, double* dev_z, uint8_t* dev_rgb, float* dev_intensity, double bbox_min[3],
+                          double bbox_max[3]);
+/* File -> device SoA arrays (capacity info->num_points each) + bounding box; a truncated body is PCV_ERR_IO. */
+int pcv_ply_load_device(pcv_ctx* ctx, const char* path, const pcv_ply_info* info, double* dev_x, double* dev_y,
+                        double* dev_z, uint8_t* dev_rgb, float* dev_intensity, double bbox_min[3], double bbox_max[3]);
+/* build_octree_from_file (generation.rs:272-287): bounding box of the file's points, then build_octree.  Colour is
+ * mandatory; `with_intensity` mirrors "intensity" in the reference's `attributes` argument. */
+int pcv_build_octree_from_file(pcv_ctx* ctx, const char* path, double resolution, int with_intensity, pcv_octree** out);
+
 /* ---- synthetic inputs for benchmarks / parity tests (integer-only, counter based) ----------- */
 enum { PCV_SYNTH_SLAB_ECEF = 1, PCV_SYNTH_GAUSS_CLUSTERS = 2 };
 int pcv_synth_points_device(pcv_ctx* ctx, int kind, uint64_t seed, uint64_t first_index, uint64_t n, double* dev_x,

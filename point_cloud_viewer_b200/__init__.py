@@ -6,6 +6,7 @@ layer used by tests and bench.py: it mirrors the names of the reference's interf
 and never computes on the CPU — every call goes through the C ABI and fails loudly without a GPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -89,6 +90,23 @@ class Context:
         fn = N.lib().pcv_build_octree_device if device else N.lib().pcv_build_octree
         N.check(fn(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), C.byref(out)))
         del keep
+        return Octree(self, out)
+
+    # -- PLY input (src/read_write/ply.rs, generation.rs:256-287)
+    def load_ply(self, path):
+        """PlyIterator + find_bounding_box in one pass: the file's points as device SoA arrays.  Returns a PlyPoints."""
+        info = ply_read_header(path)
+        return PlyPoints(self, path, info)
+
+    def ply_unpack_device(self, info, records_ptr, n, x_ptr, y_ptr, z_ptr, rgb_ptr=None, intensity_ptr=None):
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        N.check(N.lib().pcv_ply_unpack_device(self.h, C.byref(info), records_ptr, int(n), x_ptr, y_ptr, z_ptr, rgb_ptr, intensity_ptr, mn, mx))
+        return np.array(mn), np.array(mx)
+
+    def build_octree_from_file(self, path, resolution, attributes=("color",)):
+        """build_octree_from_file (generation.rs:272-287) without the directory: the octree stays resident in HBM."""
+        out = C.c_void_p()
+        N.check(N.lib().pcv_build_octree_from_file(self.h, os.fsencode(str(path)), float(resolution), 1 if "intensity" in attributes else 0, C.byref(out)))
         return Octree(self, out)
 
     def load_dir(self, directory):
@@ -361,6 +379,65 @@ class Octree:
         q = (C.c_double * 7)(*[float(v) for v in query_from_global]) if query_from_global is not None else None
         N.check(N.lib().pcv_xray_tile(self.h, _d3(tile_min), _d3(tile_max), w, h, q, _p(rgba), _p(zb), C.byref(anyp)))
         return bool(anyp.value), rgba, zb
+
+
+def ply_read_header(path):
+    """parse_header + the property checks of PlyIterator::from_file (ply.rs:126-229, 327-450) -> pcv_ply_info."""
+    info = N.PlyInfo()
+    N.check(N.lib().pcv_ply_read_header(os.fsencode(str(path)), C.byref(info)))
+    return info
+
+
+class PlyPoints:
+    """The points of a PLY file on the device: x, y, z (f64, header offset added), rgb (n*3 u8), intensity (f32) as
+    DeviceBuffers, plus the bounding box the reference's find_bounding_box pass would return."""
+
+    def __init__(self, ctx, path, info):
+        self.ctx, self.info, self.n = ctx, info, int(info.num_points)
+        n = self.n
+        self.x, self.y, self.z = (ctx.device_buffer((max(n, 1),), "<f8") for _ in range(3))
+        self.rgb = ctx.device_buffer((max(3 * n, 1),), "|u1") if info.has_color else None
+        self.intensity = ctx.device_buffer((max(n, 1),), "<f4") if info.has_intensity else None
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        N.check(N.lib().pcv_ply_load_device(ctx.h, os.fsencode(str(path)), C.byref(info), self.x.ptr, self.y.ptr, self.z.ptr,
+                                            self.rgb.ptr if self.rgb else None, self.intensity.ptr if self.intensity else None, mn, mx))
+        self.bbox_min, self.bbox_max = np.array(mn), np.array(mx)
+
+    def batches(self, batch_size):
+        """The PointsBatch stream of PlyIterator (ply.rs:522-556): ceil(n / batch_size) host batches, the last one short."""
+        x, y, z = (b.tensor()[: self.n].cpu().numpy() for b in (self.x, self.y, self.z))
+        rgb = self.rgb.tensor()[: 3 * self.n].cpu().numpy().reshape(-1, 3) if self.rgb else None
+        inten = self.intensity.tensor()[: self.n].cpu().numpy() if self.intensity else None
+        for first in range(0, self.n, batch_size):
+            sl = slice(first, min(first + batch_size, self.n))
+            b = {"position": np.stack([x[sl], y[sl], z[sl]], 1)}
+            if rgb is not None:
+                b["color"] = rgb[sl]
+            if inten is not None:
+                b["intensity"] = inten[sl]
+            yield b
+
+    def build_octree(self, resolution, with_intensity=False):
+        return self.ctx.build_octree(self.x.ptr, self.y.ptr, self.z.ptr, self.rgb.ptr if self.rgb else None, resolution, self.bbox_min, self.bbox_max,
+                                     intensity=self.intensity.ptr if (with_intensity and self.intensity) else None, n=self.n, device=True)
+
+    def free(self):
+        for b in (self.x, self.y, self.z, self.rgb, self.intensity):
+            if b is not None:
+                b.free()
+
+
+def build_octree_from_file(output_directory, resolution, filename, attributes=("color",), device=0, ctx=None):
+    """Drop-in shape of point_viewer::octree::build_octree_from_file (src/octree/generation.rs:272-287)."""
+    own = ctx is None
+    ctx = ctx or Context(device)
+    tree = ctx.build_octree_from_file(filename, resolution, attributes)
+    tree.write_dir(output_directory)
+    if own:
+        tree.free()
+        ctx.close()
+        return None
+    return tree
 
 
 def build_octree(output_directory, resolution, bounding_box, batches, attributes=("color",), device=0, ctx=None):

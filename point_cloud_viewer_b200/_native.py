@@ -100,6 +100,14 @@ class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("ms", C.c_double)]
 
 
+class PlyInfo(C.Structure):
+    """pcv_ply_info (include/pcv.h)."""
+
+    _fields_ = [("num_points", C.c_uint64), ("header_bytes", C.c_uint64), ("record_bytes", C.c_uint32), ("has_color", C.c_int32),
+                ("has_intensity", C.c_int32), ("type_xyz", C.c_int32 * 3), ("off_xyz", C.c_uint32 * 3), ("off_rgb", C.c_uint32 * 3),
+                ("off_intensity", C.c_uint32), ("offset", C.c_double * 3)]
+
+
 # every symbol include/pcv.h declares: (name, restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _u64p = C.POINTER(C.c_uint64)
@@ -131,6 +139,10 @@ SYMBOLS = [
     ("pcv_octree_node_nsub", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
     ("pcv_octree_nsub_all", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     ("pcv_assemble_top", C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("pcv_ply_read_header", C.c_int, [C.c_char_p, C.POINTER(PlyInfo)]),
+    ("pcv_ply_unpack_device", C.c_int, [C.c_void_p, C.POINTER(PlyInfo), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp]),
+    ("pcv_ply_load_device", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(PlyInfo), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp]),
+    ("pcv_build_octree_from_file", C.c_int, [C.c_void_p, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     ("pcv_synth_points_device", C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_synth_points_host", C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_synth_bbox", C.c_int, [C.c_int, _dp, _dp, _dp]),

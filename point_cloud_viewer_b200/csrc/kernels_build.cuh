@@ -811,7 +811,7 @@ struct CudaBackend : Backend {
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing (CUDA events on the launching stream around every launch)
-    enum { K_BBOX = 0, K_HIST, K_SCAN, K_SCATTER, K_PLACE, K_COUNT };
+    enum { K_BBOX = 0, K_HIST, K_SCAN, K_SCATTER, K_PLACE, K_PLY, K_COUNT };
     struct KStat {
         uint64_t launches = 0, bytes = 0;
         double ms = 0;

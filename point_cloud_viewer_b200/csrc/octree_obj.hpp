@@ -19,6 +19,8 @@ struct pcv_ctx {
     pcv_build_stats stats{};
     int sm_count = 148;
     std::mutex mu;  // build / query entry points serialise on the context's stream
+    uint8_t* ply_pin[3] = {nullptr, nullptr, nullptr};  // pinned staging ring of the PLY loader (ply_api.inl)
+    size_t ply_pin_bytes = 0;
 };
 
 struct pcv_octree {

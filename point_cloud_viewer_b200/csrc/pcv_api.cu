@@ -5,12 +5,18 @@
 #include <sys/stat.h>
 
 #include <cstdarg>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <string>
+#include <thread>
 
 #include "../../include/pcv.h"
 #include "disk_io.hpp"
 #include "octree_obj.hpp"
+#include "ply.cuh"
+#include "ply_host.hpp"
 #include "kernels_shard.cuh"
 #include "query.cuh"
 #include "synth.cuh"
@@ -87,6 +93,8 @@ void pcv_destroy(pcv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     delete c->be;
+    for (auto& p : c->ply_pin)
+        if (p) cudaFreeHost(p);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -336,7 +344,7 @@ int pcv_kernel_stats(pcv_ctx* c, pcv_kernel_stat* out, uint32_t cap, uint32_t* n
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->be->prof_collect();
-    static const char* names[CudaBackend::K_COUNT] = {"k_bbox", "k_hist", "k_scan", "k_scatter", "k_place"};
+    static const char* names[CudaBackend::K_COUNT] = {"k_bbox", "k_hist", "k_scan", "k_scatter", "k_place", "k_ply_unpack"};
     uint32_t n = 0;
     for (int k = 0; k < CudaBackend::K_COUNT; ++k) {
         if (n < cap && out) {
@@ -638,4 +646,5 @@ int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* res
 }  // extern "C"
 
 #include "query_api.inl"
+#include "ply_api.inl"
 #include "shard_api.inl"

@@ -25,6 +25,7 @@ def test_struct_layouts_match_header():
 
     assert C.sizeof(N.NodeMeta) == 80 and C.sizeof(N.Points) == 56 and C.sizeof(N.Location) == 8 + 8 * (6 + 32 + 14 + 3)
     assert C.sizeof(N.Config) == 16 and C.sizeof(N.Interval) == 16 and C.sizeof(N.Batch) == 40
+    assert C.sizeof(N.PlyInfo) == 96 and N.PlyInfo.offset.offset == 72 and N.PlyInfo.off_intensity.offset == 64
 
 
 def test_no_cpu_fallback():
