@@ -122,6 +122,11 @@ int pcv_octree_nodes(const pcv_octree* o, pcv_node_meta* out, uint64_t cap); /* 
 /* Octree::get_node_data (octree/mod.rs:285-307): raw .xyz / .rgb bytes (+ intensity, provenance). */
 int pcv_octree_node_data(const pcv_octree* o, uint64_t id_high, uint64_t id_low, void* xyz_out, uint8_t* rgb_out,
                          float* intensity_out, uint64_t* src_index_out);
+/* The web viewer's `/nodes_data` reply (octree_web_viewer/src/backend.rs:66-75, 92-165): for every requested node, in
+ * request order: cube min (3 f64 LE), edge (f64), num_points (u32), bytes per coordinate (u8), zero padding to 8 bytes,
+ * position bytes, padding, colour bytes, padding.  ids_hi_lo = num_nodes x (high, low).  out == NULL: size query.
+ * An unknown id or a node without points is PCV_ERR_NOT_FOUND (get_node_data -> NodeNotFound: no files). */
+int pcv_nodes_data_blob(const pcv_octree* o, const uint64_t* ids_hi_lo, uint32_t num_nodes, void* out, uint64_t cap, uint64_t* size_out);
 /* All nodes at once into caller (ideally pinned) buffers: node n occupies points [point_offset, +num_points) and
  * bytes [xyz_byte_offset, +num_points*3*bpc) of these arrays (offsets from pcv_octree_nodes; no particular order). */
 int pcv_octree_download(const pcv_octree* o, void* xyz_out, uint8_t* rgb_out, float* intensity_out, uint64_t* src_index_out);

@@ -311,6 +311,37 @@ void orc_octree_meta(void* hp, double* resolution, double* bbox6, int* with_inte
     *with_intensity = h->oct.with_intensity ? 1 : 0;
 }
 
+// ---- /nodes_data reply (octree_web_viewer/src/backend.rs:66-75 pad, :92-165 get_nodes_data) ----
+// Literal restatement: for each requested id, get_node_data (octree/mod.rs:285-307: NodeNotFound when the node has no
+// files, i.e. unknown id or zero points), then min xyz, edge (f64 LE), num_points as u32, bytes_per_coordinate as u8, pad
+// to 8, position bytes, pad, colour bytes, pad.  Returns the blob size, or -1 - k if request k cannot be served.
+int64_t orc_nodes_data_blob(void* hp, const uint64_t* ids_hi_lo, uint32_t num_nodes, uint8_t* out, uint64_t cap) {
+    Handle* h = (Handle*)hp;
+    std::vector<uint8_t> blob;
+    auto pad = [&]() {
+        while (blob.size() % 8) blob.push_back(0);
+    };
+    auto put = [&](const void* p, size_t n) { blob.insert(blob.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    for (uint32_t k = 0; k < num_nodes; ++k) {
+        NodeId id = NodeId::from_high_low(ids_hi_lo[2 * k], ids_hi_lo[2 * k + 1]);
+        auto f = h->oct.files.find(id);
+        if (!h->oct.nodes.count(id) || f == h->oct.files.end()) return -1 - (int64_t)k;
+        const NodeMeta& m = h->oct.nodes[id];
+        put(&m.cube.min.x, 8), put(&m.cube.min.y, 8), put(&m.cube.min.z, 8), put(&m.cube.edge, 8);
+        const uint32_t n32 = (uint32_t)m.num_points;
+        put(&n32, 4);
+        const uint8_t bpc = (uint8_t)bytes_per_coordinate(m.enc);
+        put(&bpc, 1);
+        pad();
+        put(f->second.xyz.data(), f->second.xyz.size());
+        pad();
+        put(f->second.rgb.data(), f->second.rgb.size());
+        pad();
+    }
+    if (out && cap >= blob.size()) std::memcpy(out, blob.data(), blob.size());
+    return (int64_t)blob.size();
+}
+
 // ---- PLY input (oracle_ply.hpp) ----
 struct orc_ply_info {
     uint64_t num_points, header_bytes;

@@ -298,6 +298,19 @@ class Octree:
         N.check(N.lib().pcv_octree_node_data(self.h, m["hi"], m["lo"], _p(xyz), _p(rgb), _p(inten), _p(src)))
         return xyz, rgb, inten, src
 
+    def nodes_data_blob(self, names, out=None):
+        """`/nodes_data` of the web viewer (octree_web_viewer/src/backend.rs:92-165): one binary reply for a list of node names,
+        gathered on the GPU from the resident octree.  `out`: optional (pinned) uint8 array to receive the blob."""
+        ids = np.zeros(2 * len(names), np.uint64)
+        for k, nm in enumerate(names):
+            ids[2 * k], ids[2 * k + 1] = node_id_from_name(nm)
+        size = C.c_uint64()
+        N.check(N.lib().pcv_nodes_data_blob(self.h, _p(ids), len(names), None, 0, C.byref(size)))
+        if out is None:
+            out = np.zeros(max(size.value, 1), np.uint8)
+        N.check(N.lib().pcv_nodes_data_blob(self.h, _p(ids), len(names), _p(out), out.nbytes if hasattr(out, "nbytes") else len(out), C.byref(size)))
+        return out[: size.value]
+
     def node_nsub(self, name):
         m = self.nodes[name]
         v = C.c_uint64()

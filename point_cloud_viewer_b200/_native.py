@@ -124,6 +124,7 @@ SYMBOLS = [
     ("pcv_octree_info", C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, _dp, _dp, _dp, C.POINTER(C.c_int)]),
     ("pcv_octree_nodes", C.c_int, [C.c_void_p, C.POINTER(NodeMeta), C.c_uint64]),
     ("pcv_octree_node_data", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_nodes_data_blob", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, _u64p]),
     ("pcv_octree_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_octree_device_arrays", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("pcv_octree_write_dir", C.c_int, [C.c_void_p, C.c_char_p]),

@@ -389,4 +389,36 @@ __global__ void __launch_bounds__(256) k_xray_resolve(const uint32_t* __restrict
     reinterpret_cast<uchar4*>(rgba)[px] = o;
 }
 
+// ------------------------------------------------------------------------------------------------
+// /nodes_data blob (octree_web_viewer/src/backend.rs:92-165): gather the position and colour bytes of the requested
+// nodes from their places in the octree arrays into one contiguous, 8-byte-padded reply buffer.
+// ------------------------------------------------------------------------------------------------
+// One work item = up to kBlobSeg destination bytes of one node part.  Destination offsets are multiples of 8 (the
+// blob's padding rule); sources start at arbitrary byte offsets (a Uint8 node has 3 n bytes), so every destination word
+// is assembled from two aligned source words with a funnel shift.  HBM-bound byte copy: 2 bytes moved per byte of reply.
+struct BlobItem {
+    uint64_t src;   // byte offset into the source array
+    uint64_t dst;   // byte offset into the blob (multiple of 8)
+    uint32_t bytes;
+    uint32_t from_rgb;  // 0: position bytes, 1: colour bytes
+};
+constexpr uint32_t kBlobSeg = 32768;
+
+__global__ void __launch_bounds__(256) k_blob_gather(const BlobItem* __restrict__ items, const uint8_t* __restrict__ xyz, const uint8_t* __restrict__ rgb,
+                                                     uint8_t* __restrict__ blob) {
+    const BlobItem it = items[blockIdx.x];
+    const uint8_t* src = (it.from_rgb ? rgb : xyz) + it.src;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(blob + it.dst);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3), sh = mis * 8;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src - mis);
+    const uint32_t nwords = it.bytes / 4;
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const uint32_t lo = __ldg(w + i);
+        const uint32_t hi = mis ? __ldg(w + i + 1) : 0u;  // never read a word the source range does not touch
+        dst[i] = __funnelshift_r(lo, hi, sh);
+    }
+    // the last 0..3 bytes; the blob's zero padding is written by the host-side memset of the reply buffer
+    if (threadIdx.x < (it.bytes & 3u)) blob[it.dst + 4ull * nwords + threadIdx.x] = src[4ull * nwords + threadIdx.x];
+}
+
 }  // namespace pcv

@@ -557,3 +557,72 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
 }
 
 }  // extern "C"
+
+// ---- /nodes_data reply blob (octree_web_viewer/src/backend.rs:66-75 pad, :92-165 get_nodes_data) ----------------
+// Per requested node, in request order: cube min x, y, z (f64 LE), edge length (f64), num_points (u32), bytes per
+// coordinate (u8), zeros up to a multiple of 8, the node's position bytes, padding, the node's colour bytes, padding.
+// Octree::get_node_data fails with NodeNotFound for ids without files - unknown ids and nodes with zero points, whose
+// files were deleted (data_provider/on_disk.rs:51-68, node_writer.rs:78-89): PCV_ERR_NOT_FOUND here.
+// One gather kernel + one device-to-host copy serve the whole request from HBM.
+int pcv_nodes_data_blob(const pcv_octree* o, const uint64_t* ids_hi_lo, uint32_t num_nodes, void* out, uint64_t cap, uint64_t* size_out) {
+    if (!o || (num_nodes && !ids_hi_lo) || !size_out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    auto pad8 = [](uint64_t v) { return (v + 7) & ~(uint64_t)7; };
+    std::vector<BlobItem> items;
+    std::vector<uint64_t> header_at(num_nodes);
+    std::vector<int> which(num_nodes);
+    uint64_t size = 0;
+    for (uint32_t k = 0; k < num_nodes; ++k) {
+        const int i = o->find(ids_hi_lo[2 * k], ids_hi_lo[2 * k + 1]);
+        if (i < 0 || o->nodes[i].num_points == 0)
+            return fail(PCV_ERR_NOT_FOUND, "Could not get node %s.", node_name(ids_hi_lo[2 * k], ids_hi_lo[2 * k + 1]).c_str());
+        const pcv_node_meta& m = o->nodes[i];
+        which[k] = i;
+        header_at[k] = size;
+        size += pad8(8 * 4 + 4 + 1);
+        const uint64_t n = (uint64_t)m.num_points, pb = n * 3 * (uint64_t)enc_bytes(m.position_encoding), cb = n * 3;
+        for (uint64_t o2 = 0; o2 < pb; o2 += kBlobSeg) items.push_back(BlobItem{m.xyz_byte_offset + o2, size + o2, (uint32_t)std::min<uint64_t>(kBlobSeg, pb - o2), 0});
+        size += pad8(pb);
+        for (uint64_t o2 = 0; o2 < cb; o2 += kBlobSeg) items.push_back(BlobItem{3 * m.point_offset + o2, size + o2, (uint32_t)std::min<uint64_t>(kBlobSeg, cb - o2), 1});
+        size += pad8(cb);
+    }
+    *size_out = size;
+    if (!out) return PCV_OK;  // size query
+    if (cap < size) return fail(PCV_ERR_INVALID, "reply buffer too small: %llu < %llu", (unsigned long long)cap, (unsigned long long)size);
+    if (size == 0) return PCV_OK;
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CudaBackend& be = *c->be;
+    uint8_t* d_blob = (uint8_t*)be.dmalloc(size);
+    BlobItem* d_items = (BlobItem*)be.dmalloc(items.size() * sizeof(BlobItem));
+    try {
+        CU(cudaMemsetAsync(d_blob, 0, size, c->stream));  // padding bytes are zeros
+        be.h2d(d_items, items.data(), items.size() * sizeof(BlobItem));
+        k_blob_gather<<<(uint32_t)items.size(), 256, 0, c->stream>>>(d_items, o->d_xyz, o->d_rgb, d_blob);
+        ++be.launches;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, d_blob, size, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        be.dfree(d_blob);
+        be.dfree(d_items);
+        throw;
+    }
+    be.dfree(d_blob);
+    be.dfree(d_items);
+    // the 40-byte headers are host data (node table): written after the copy
+    uint8_t* ob = (uint8_t*)out;
+    for (uint32_t k = 0; k < num_nodes; ++k) {
+        const pcv_node_meta& m = o->nodes[which[k]];
+        uint8_t* h = ob + header_at[k];
+        std::memcpy(h, m.cube_min, 24);
+        std::memcpy(h + 24, &m.cube_edge, 8);
+        const uint32_t n32 = (uint32_t)m.num_points;  // `as u32`
+        std::memcpy(h + 32, &n32, 4);
+        h[36] = (uint8_t)enc_bytes(m.position_encoding);
+        h[37] = h[38] = h[39] = 0;
+    }
+    return PCV_OK;
+    API_CATCH
+}

@@ -93,6 +93,8 @@ def lib():
         L.orc_load_dir.restype = C.c_void_p
         L.orc_load_dir.argtypes = [C.c_char_p]
         L.orc_octree_meta.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_int)]
+        L.orc_nodes_data_blob.restype = C.c_int64
+        L.orc_nodes_data_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
         L.orc_ply_error.restype = C.c_char_p
         L.orc_ply_open.argtypes = [C.c_char_p, C.POINTER(PlyInfo)]
         L.orc_ply_field.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -198,6 +200,16 @@ class OracleOctree:
 
     def write_dir(self, d):
         assert lib().orc_write_dir(self.h, d.encode()) == 0
+
+    def nodes_data_blob(self, names):
+        """The web viewer's /nodes_data reply for the named nodes (backend.rs:92-165); KeyError(name) if one has no files."""
+        ids = np.array([v for nm in names for v in id_from_str(nm)], np.uint64)
+        size = lib().orc_nodes_data_blob(self.h, _ptr(ids), len(names), None, 0)
+        if size < 0:
+            raise KeyError(names[-1 - size])
+        out = np.zeros(max(size, 1), np.uint8)
+        assert lib().orc_nodes_data_blob(self.h, _ptr(ids), len(names), _ptr(out), size) == size
+        return out[:size].tobytes()
 
     def meta(self):
         res, bb, wi = C.c_double(), (C.c_double * 6)(), C.c_int()
