@@ -219,7 +219,11 @@ inline int position_encoding_for(double edge, double resolution) {
     return ENC_F64;
 }
 
-inline LevelTable make_level_table(double root_edge, double resolution) {
+// `root_min`: min corner of the root cube.  When every coordinate inside the root cube has a magnitude in
+// [2^-300, 2^300) on every axis, the numerators q - m of the whole tree are exactly 0 or in [2^-353, 2^500) (q and m are
+// doubles of at least that magnitude, so a non-zero difference is at least half an ulp of 2^-300), i.e. inside
+// div_known's proven range without looking at them: fast = 2 (the kernels then only check the raw inputs once).
+inline LevelTable make_level_table(double root_edge, double resolution, const double* root_min = nullptr) {
     LevelTable t;
     double e = root_edge;
     t.last_level = kMaxLevels - 1;
@@ -236,6 +240,15 @@ inline LevelTable make_level_table(double root_edge, double resolution) {
             found = true;
         }
         e /= 2.;  // node.rs:161
+    }
+    if (t.fast && root_min && !std::getenv("PCV_CHECKED_FAST")) {  // PCV_CHECKED_FAST=1: diagnostic, keep the per-numerator checks
+        const double lo = std::ldexp(1.0, -300), hi = std::ldexp(1.0, 300);
+        bool ok = root_edge > 0.0 && root_edge < hi;
+        for (int k = 0; k < 3 && ok; ++k) {
+            const double a = root_min[k], b = root_min[k] + root_edge;
+            ok = std::isfinite(a) && std::fabs(a) < hi && std::fabs(b) < hi && (a >= lo || b <= -lo);
+        }
+        if (ok) t.fast = 2;
     }
     return t;
 }
@@ -303,7 +316,7 @@ class BuildPlan {
         double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
         for (int a = 0; a < 3; ++a) R.root_min[a] = bmin[a];
         R.root_edge = E;
-        R.lv = make_level_table(E, resolution);
+        R.lv = make_level_table(E, resolution, bmin);
         const LevelTable& lv = R.lv;
         if (pts.n == 0) return R;  // no leaves -> no nodes at all (generation.rs:325-397)
 
@@ -655,7 +668,7 @@ inline BuildResult assemble_top(Backend& be, double resolution, const double bmi
     const double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
     for (int a = 0; a < 3; ++a) R.root_min[a] = bmin[a];
     R.root_edge = E;
-    R.lv = make_level_table(E, resolution);
+    R.lv = make_level_table(E, resolution, bmin);
     const LevelTable& lv = R.lv;
     ShardSpec sp;
     sp.k = k;

@@ -70,10 +70,14 @@ PCV_HD double clamp01(double x) {
     return x;
 }
 
-// Rust `f64 as u32` for s in [0, 65535] or NaN: truncate toward zero, NaN -> 0.
+// Rust `f64 as u16/u8` as the callers need it (they cap the result at 255 / 65535): truncate toward zero, NaN -> 0,
+// negative -> 0, huge -> saturated.  On the GPU this goes through the SIGNED conversion: measured on sm_100,
+// cvt.rzi.u32.f64 returns 0x80000000 for NaN (not 0), while cvt.rzi.s32.f64 gives INT_MIN for NaN / -inf and INT_MAX
+// for +inf / huge, so max(v, 0) has exactly the semantics of the Rust cast below 2^31.
 PCV_HD uint32_t trunc_u32(double s) {
 #if defined(__CUDA_ARCH__)
-    return __double2uint_rz(s);  // cvt.rzi.u32.f64: saturating, NaN -> 0 (same as Rust `as`)
+    const int v = __double2int_rz(s);
+    return (uint32_t)(v < 0 ? 0 : v);
 #else
     if (!(s == s)) return 0u;
     if (s <= 0.0) return 0u;

@@ -23,8 +23,15 @@ __device__ __forceinline__ unsigned div_bad(double a) {
     return (inrange || (hi | lo) == 0u) ? 0u : 1u;
 }
 
+// Raw input coordinate admissible for the unchecked fast sequence (FAST == 2)?  |x| < 2^400, which also rejects inf / NaN.
+__device__ __forceinline__ unsigned input_bad(double x) { return fabs(x) < 2.582249878086908589655919172003011874329705792829223512830659e120 ? 0u : 1u; }
+
+// FAST: 0 = IEEE division; 1 = reciprocal sequence, every numerator range-checked (flag -> the caller redoes with 0);
+// 2 = reciprocal sequence without per-numerator checks: the host proved that every cube of the tree keeps all
+// coordinates at magnitudes in [2^-300, 2^301) (LevelTable::fast == 2), so q - m is exactly 0 or in [2^-353, 2^500)
+// once the raw inputs passed input_bad() in the root pass.
 // One axis, one level.  Returns the code; updates q (if DECODE), m, digit bit, bad flag.
-template <int ENC, bool FAST, bool DECODE>
+template <int ENC, int FAST, bool DECODE>
 __device__ __forceinline__ uint64_t axis_step(double& q, double& m, double e_cur, double e_half, double ry, unsigned& bit, unsigned& bad) {
     const double c = (m + (m + e_cur)) * 0.5;  // Cube::center: (min + max) / 2 (halving is exact either way)
     bit = q > c ? 1u : 0u;
@@ -32,7 +39,7 @@ __device__ __forceinline__ uint64_t axis_step(double& q, double& m, double e_cur
     const double a = q - m;
     double t;
     if (FAST) {
-        bad |= div_bad(a);
+        if (FAST == 1) bad |= div_bad(a);
         const double q0 = a * ry;
         const double q1 = fma(fma(-q0, e_half, a), ry, q0);
         t = fma(fma(-q1, e_half, a), ry, q1);
@@ -40,13 +47,13 @@ __device__ __forceinline__ uint64_t axis_step(double& q, double& m, double e_cur
         t = a / e_half;
     }
     if (ENC == ENC_U8) {
-        uint32_t v = __double2uint_rz(255.0 * t);  // saturating, NaN -> 0: equals the clamped form (chain.h encode1_fast)
+        uint32_t v = trunc_u32(255.0 * t);  // saturating, NaN -> 0: equals the clamped form (chain.h encode1_fast)
         v = v > 255u ? 255u : v;
         if (DECODE) q = fma(unit_frac<8>(v), e_half, m);
         return v;
     }
     if (ENC == ENC_U16) {
-        uint32_t v = __double2uint_rz(65535.0 * t);
+        uint32_t v = trunc_u32(65535.0 * t);
         v = v > 65535u ? 65535u : v;
         if (DECODE) q = fma(unit_frac<16>(v), e_half, m);
         return v;
@@ -62,7 +69,7 @@ __device__ __forceinline__ uint64_t axis_step(double& q, double& m, double e_cur
 }
 
 // One level for one point: digit = (x > cx) << 2 | (y > cy) << 1 | (z > cz)  (node.rs:34-42)
-template <int ENC, bool FAST, bool DECODE, typename CodeT>
+template <int ENC, int FAST, bool DECODE, typename CodeT>
 __device__ __forceinline__ unsigned level_step(double q[3], double m[3], double e_cur, double e_half, double ry, CodeT code[3], unsigned& bad) {
     unsigned bx, by, bz;
     code[0] = (CodeT)axis_step<ENC, FAST, DECODE>(q[0], m[0], e_cur, e_half, ry, bx, bad);
@@ -92,12 +99,12 @@ __device__ __forceinline__ double decode_axis(uint64_t bits, double mn, double e
 }
 
 // encode into a known cube (ry = RN(1/edge)), encoding as template parameter; same value as chain.h encode1()
-template <int ENC, bool FAST>
+template <int ENC, int FAST>
 __device__ __forceinline__ uint64_t encode_axis(double value, double mn, double edge, double ry, unsigned& bad) {
     const double a = value - mn;
     double t;
     if (FAST) {
-        bad |= div_bad(a);
+        if (FAST == 1) bad |= div_bad(a);
         const double q0 = a * ry;
         const double q1 = fma(fma(-q0, edge, a), ry, q0);
         t = fma(fma(-q1, edge, a), ry, q1);
@@ -105,11 +112,11 @@ __device__ __forceinline__ uint64_t encode_axis(double value, double mn, double 
         t = a / edge;
     }
     if (ENC == ENC_U8) {
-        const uint32_t v = __double2uint_rz(255.0 * t);
+        const uint32_t v = trunc_u32(255.0 * t);
         return v > 255u ? 255u : v;
     }
     if (ENC == ENC_U16) {
-        const uint32_t v = __double2uint_rz(65535.0 * t);
+        const uint32_t v = trunc_u32(65535.0 * t);
         return v > 65535u ? 65535u : v;
     }
     const double cl = clamp01(t);

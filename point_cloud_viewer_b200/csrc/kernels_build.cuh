@@ -221,7 +221,7 @@ __device__ __forceinline__ void load_position_t(const PassArgs& a, const TileDes
 constexpr int kHistItems = 2;  // points per thread in flight (x 3 independent axis chains each)
 
 // Histogram of the G-level digits of one tile.  The last level needs only the child digit (no encode/decode).
-template <bool ROOT, bool WIDE, int G, bool FAST>
+template <bool ROOT, bool WIDE, int G, int FAST>
 __device__ __forceinline__ unsigned hist_tile(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t* sh_hist) {
     unsigned bad = 0;
     for (uint32_t i0 = threadIdx.x; i0 < t.count; i0 += blockDim.x * kHistItems) {
@@ -232,6 +232,7 @@ __device__ __forceinline__ unsigned hist_tile(const PassArgs& a, const TileDesc&
             const uint32_t i = min(i0 + u * blockDim.x, t.count - 1);  // clamp: out-of-range lanes redo the last item, not counted
             if (ROOT) {
                 load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[u], idx);
+                if (FAST == 2) bad |= input_bad(q[u][0]) | input_bad(q[u][1]) | input_bad(q[u][2]);
             } else {
                 PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx);)
             }
@@ -272,14 +273,14 @@ __global__ void __launch_bounds__(256) k_hist(const __grid_constant__ PassArgs a
     for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
     __syncthreads();
     if (a.lv.fast) {
-        const unsigned bad = hist_tile<ROOT, WIDE, G, true>(a, t, act, sh_hist);
+        const unsigned bad = a.lv.fast == 2 ? hist_tile<ROOT, WIDE, G, 2>(a, t, act, sh_hist) : hist_tile<ROOT, WIDE, G, 1>(a, t, act, sh_hist);
         if (__syncthreads_or((int)bad)) {  // a numerator outside the proven range: redo the tile with the IEEE operator
             for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
             __syncthreads();
-            hist_tile<ROOT, WIDE, G, false>(a, t, act, sh_hist);
+            hist_tile<ROOT, WIDE, G, 0>(a, t, act, sh_hist);
         }
     } else {
-        hist_tile<ROOT, WIDE, G, false>(a, t, act, sh_hist);
+        hist_tile<ROOT, WIDE, G, 0>(a, t, act, sh_hist);
     }
     __syncthreads();
     uint32_t* out = a.d_tile_counts + (size_t)blockIdx.x * NB;
@@ -406,7 +407,7 @@ __device__ __forceinline__ void smem_store_rec(unsigned char* srec, uint32_t i, 
     }
 }
 
-template <bool ROOT, bool WIDE, int G, bool FAST, typename CodeT>
+template <bool ROOT, bool WIDE, int G, int FAST, typename CodeT>
 __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, unsigned char* srec,
                                                     uint32_t* sinfo, const uint32_t* lutm, uint32_t* cnt) {
     constexpr int nb = 1 << (3 * G);
@@ -423,6 +424,7 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
             if (ROOT) {
                 const uint32_t ic = min(i, t.count - 1);
                 load_position_t<true, WIDE, ENC_F64>(a, t, act, ic, q[u], idx[u]);
+                if (FAST == 2) bad |= input_bad(q[u][0]) | input_bad(q[u][1]) | input_bad(q[u][2]);
             } else {
                 uint64_t c[3] = {0, 0, 0};  // lanes past the end of the tile descend from the cube's min corner (harmless)
                 idx[u] = 0;
@@ -584,7 +586,8 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     // the block was outside the proven range - the codes in shared memory are only replaced by valid lanes, so the
     // second run must start from the original records: reload them)
     if (a.lv.fast) {
-        const unsigned bad = scatter_sweep_a<ROOT, WIDE, G, true, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
+        const unsigned bad = a.lv.fast == 2 ? scatter_sweep_a<ROOT, WIDE, G, 2, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt)
+                                            : scatter_sweep_a<ROOT, WIDE, G, 1, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
         if (__syncthreads_or((int)bad)) {
             for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
             if (!ROOT) {  // restore the input records (sweep A overwrote their codes)
@@ -596,11 +599,11 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
                 }
             }
             __syncthreads();
-            scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
+            scatter_sweep_a<ROOT, WIDE, G, 0, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
             __syncthreads();
         }
     } else {
-        scatter_sweep_a<ROOT, WIDE, G, false, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
+        scatter_sweep_a<ROOT, WIDE, G, 0, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
         __syncthreads();
     }
     // (4) sort the tile by bucket inside shared memory (as a permutation) so that the global stores are coalesced runs:
@@ -708,7 +711,7 @@ __device__ __forceinline__ void place_store(const PlaceArgs& a, const DNode& nd,
 
 // The 7 of 8 points of a non-root node that stay: one same-cube rewrite (child_writer, generation.rs:234-238) with the
 // node's encoding hoisted out of the loop; dense lane mapping (stayer s <-> rank j = 8*(s/7) + s%7 + 1).
-template <bool WIDE, int ENC, bool FAST>
+template <bool WIDE, int ENC, int FAST>
 __device__ __forceinline__ unsigned place_stayers(const PlaceArgs& a, const LeafTile& lt, const DNode& nd) {
     unsigned bad = 0;
     const uint32_t nst = lt.count - (lt.count + 7) / 8;  // tile starts at a multiple of 8
@@ -793,12 +796,16 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     }
     if (a.fast) {
         unsigned bad = 0;
-        PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, true>(a, lt, leaf);)
+        if (a.fast == 2) {
+            PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, 2>(a, lt, leaf);)
+        } else {
+            PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, 1>(a, lt, leaf);)
+        }
         if (__syncthreads_or((int)bad)) {  // rare: redo the tile's stayers with the IEEE operator (idempotent stores)
-            PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, false>(a, lt, leaf);)
+            PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 0>(a, lt, leaf);)
         }
     } else {
-        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, false>(a, lt, leaf);)
+        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 0>(a, lt, leaf);)
     }
     place_movers<WIDE>(a, lt, leaf, false);
 }

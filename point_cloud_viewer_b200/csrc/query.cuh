@@ -336,6 +336,12 @@ struct XrayArgs {
     int* any;
 };
 
+// Rust `f64 as u32`: truncating, saturating, NaN -> 0.  cvt.rzi.u32.f64 saturates but returns 0x80000000 for NaN (measured).
+__device__ __forceinline__ uint32_t rust_as_u32_dev(double v) {
+    const uint32_t u = __double2uint_rz(v);
+    return v != v ? 0u : u;
+}
+
 __global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ XrayArgs a) {
     const QTile t = a.tiles[blockIdx.x];
     const QNode nd = a.nodes[t.node];
@@ -355,9 +361,9 @@ __global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ Xray
             p[2] = q.z;
         }
         // process_point_data, generation.rs:108-127 (`as u32` saturates, NaN -> 0)
-        const uint32_t x = __double2uint_rz(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
-        const uint32_t y = __double2uint_rz((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
-        const uint32_t z = __double2uint_rz(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
+        const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
+        const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
+        const uint32_t z = rust_as_u32_dev(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
         if (x < a.w && y < a.h) {
             const size_t px = (size_t)y * a.w + x;
             if (z < 1024)

@@ -141,3 +141,31 @@ def test_degenerate_numerators_take_the_ieee_path(ctx):
         compare_trees(ref, tree)
         tree.free()
         c.close()
+
+
+def test_wild_inputs_with_unchecked_fast_path(ctx):
+    """Root cube far from zero -> the kernels skip the per-numerator range checks (LevelTable::fast == 2) and only look at
+    the raw inputs once: huge, infinite and NaN coordinates (outside the bounding box) must send their tiles through the
+    IEEE operator and still match the oracle bit for bit."""
+    import point_cloud_viewer_b200 as pcv
+
+    rng = np.random.default_rng(23)
+    n = 80000
+    P = rng.random((n, 3)) * 100.0 + [4.1e6, 6.6e5, 4.7e6]
+    bmin, bmax = P.min(0).copy(), P.max(0).copy()
+    P[100] = [1e200, 6.6e5, 4.7e6]
+    P[5000, 1] = -1e300
+    P[9000, 2] = np.inf
+    P[12000, 0] = -np.inf
+    P[20000] = [np.nan, 6.6e5 + 1, 4.7e6 + 1]
+    P[20001, 2] = 2.0 ** 399  # just inside the admissible input range
+    P[30000] = 0.0  # far outside the box, towards zero
+    x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
+    rgb = rng.integers(0, 255, n * 3, dtype=np.uint8)
+    for maxpts, res, G in ((400, 1e-4, 2), (3000, 1e-9, 3), (400, 1e-3, 1)):
+        c = pcv.Context(0, max_points_per_node=maxpts, levels_per_pass=G)
+        tree = c.build_octree(x, y, z, rgb, res, bmin, bmax)
+        ref = O.build(x, y, z, rgb.reshape(-1, 3), res, bmin, bmax, max_points_per_node=maxpts)
+        compare_trees(ref, tree)
+        tree.free()
+        c.close()
