@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcv_b200.so")
+LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so")  # env override: kernel-variant experiments only
 
 PCV_OK = 0
 ERR_NAMES = {

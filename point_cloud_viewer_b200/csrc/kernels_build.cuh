@@ -218,7 +218,10 @@ __device__ __forceinline__ void load_position_t(const PassArgs& a, const TileDes
     }
 }
 
-constexpr int kHistItems = 2;  // points per thread in flight (x 3 independent axis chains each)
+// Points per thread in flight (x 3 independent axis chains each).  Measured at N = 1e9: one point per thread at 32
+// registers (8 blocks per SM, 100 % occupancy) 17.2 ms; two points at 64 registers (4 blocks) 20.8 ms; two at 40 / 48
+// registers (6 / 5 blocks, spilling) 18.3 / 19.1 ms - thread-level parallelism hides the load latency better than ILP.
+constexpr int kHistItems = 1;
 
 // Histogram of the G-level digits of one tile.  The last level needs only the child digit (no encode/decode).
 template <bool ROOT, bool WIDE, int G, int FAST>
@@ -265,7 +268,7 @@ __device__ __forceinline__ unsigned hist_tile(const PassArgs& a, const TileDesc&
 }
 
 template <bool ROOT, bool WIDE, int G>
-__global__ void __launch_bounds__(256) k_hist(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(256, 8) k_hist(const __grid_constant__ PassArgs a) {
     extern __shared__ uint32_t sh_hist[];
     const TileDesc t = tile_of(a, blockIdx.x);
     const ActiveDesc act = a.d_active[t.active];
@@ -340,22 +343,31 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
 //   sweep B2 consecutive threads store consecutive records of a bucket's run to the next pass segment or the leaf arena:
 //            a warp's store covers a few contiguous runs instead of up to 32 scattered 16-byte slots (and pages)
 // The order inside every bucket is the tile order, i.e. input order (stable).
-constexpr int kScatterThreads = 512;
-constexpr int kScatterWarps = kScatterThreads / 32;
-constexpr int kWarpItems = kTilePoints / kScatterWarps;  // 256
-constexpr int kSubRounds = kWarpItems / 32;              // 8
-constexpr int kScatterU = 2;                             // sub-rounds in flight
-static_assert(kSubRounds % kScatterU == 0, "sub-rounds must be a multiple of the unroll");
-constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;  // root pass: the tile's rgb bytes, staged with 16-byte loads
+// 16 warps per tile with two sub-rounds in flight per warp (64 registers, two blocks per SM for narrow records).  Measured
+// at N = 1e9: 32 warps with one sub-round in flight (32 registers, 2048 threads per SM) 51.9 ms against 50.4 ms - unlike
+// k_hist, the scatter gains nothing from occupancy (its sweeps are bound by shared-memory traffic and barriers).
+template <bool WIDE>
+struct ScatterCfg {
+    static constexpr int threads = 512;
+    static constexpr int warps = threads / 32;
+    static constexpr int warp_items = kTilePoints / warps;  // 256
+    static constexpr int sub_rounds = warp_items / 32;      // 8
+    static constexpr int U = 2;                             // sub-rounds in flight per warp
+    static_assert(sub_rounds % U == 0, "sub-rounds must be a multiple of the unroll");
+};
+constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;  // root pass: the tile's rgb bytes, staged with 16-byte loads in the (not yet used) sinfo area
+static_assert(kRgbStage <= (size_t)kTilePoints * 4, "the rgb staging area aliases sinfo");
 
 template <bool WIDE>
 struct ScatterSmem {
     static constexpr size_t rec_bytes = WIDE ? 32 : 16;
     __host__ __device__ static constexpr size_t bytes(int nb) {
-        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 4 + (size_t)nb * 4 * (2 + kScatterWarps) +
-               (size_t)nb * 4 + kRgbStage + 16;
+        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 4 + (size_t)nb * 4 * (2 + ScatterCfg<WIDE>::warps) +
+               (size_t)nb * 4 + 16;
     }
 };
+
+static_assert(ScatterSmem<false>::bytes(512) <= 232448 && ScatterSmem<true>::bytes(512) <= 232448, "scatter tile exceeds the 227 KB opt-in shared memory of sm_100");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -411,6 +423,7 @@ template <bool ROOT, bool WIDE, int G, int FAST, typename CodeT>
 __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, unsigned char* srec,
                                                     uint32_t* sinfo, const uint32_t* lutm, uint32_t* cnt) {
     constexpr int nb = 1 << (3 * G);
+    constexpr int kWarpItems = ScatterCfg<WIDE>::warp_items, kSubRounds = ScatterCfg<WIDE>::sub_rounds, kScatterU = ScatterCfg<WIDE>::U;
     unsigned bad = 0;
     for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
         double q[kScatterU][3], m[kScatterU][3];
@@ -477,9 +490,11 @@ __device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const Til
 }
 
 template <bool ROOT, bool WIDE, int G>
-__global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(ScatterCfg<WIDE>::threads, WIDE ? 1 : 2) k_scatter(const __grid_constant__ PassArgs a) {
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
     constexpr int nb = 1 << (3 * G);
+    constexpr int kScatterThreads = ScatterCfg<WIDE>::threads, kScatterWarps = ScatterCfg<WIDE>::warps, kWarpItems = ScatterCfg<WIDE>::warp_items,
+                  kSubRounds = ScatterCfg<WIDE>::sub_rounds;
     constexpr size_t recsz = ScatterSmem<WIDE>::rec_bytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* srec = smem_raw;                                                      // [tile] records (AoS, as in HBM)
@@ -488,7 +503,7 @@ __global__ void __launch_bounds__(kScatterThreads, WIDE ? 1 : 2) k_scatter(const
     uint32_t* cnt = reinterpret_cast<uint32_t*>(bdst + nb);                              // [warps][nb]
     uint32_t* sinfo = cnt + kScatterWarps * nb;                                          // [tile] bucket | rank | leader | group size | leaf
     uint32_t* lutm = sinfo + kTilePoints;                                                // [nb] digit -> bucket | keep << 16 | leaf << 24
-    uint8_t* srgb = reinterpret_cast<uint8_t*>(lutm + nb);                               // root pass only: rgb bytes of the tile
+    uint8_t* srgb = reinterpret_cast<uint8_t*>(sinfo);                                   // root pass only: rgb bytes of the tile, consumed before sweep A writes sinfo
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + ((ScatterSmem<WIDE>::bytes(nb) - 8) & ~(size_t)7));
 
     const TileDesc t = tile_of(a, blockIdx.x);
@@ -979,11 +994,11 @@ struct CudaBackend : Backend {
     template <bool ROOT, bool WIDE>
     void launch_scatter(const PassArgs& a, size_t sm) {
         if (a.G == 1)
-            k_scatter<ROOT, WIDE, 1><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+            k_scatter<ROOT, WIDE, 1><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
         else if (a.G == 2)
-            k_scatter<ROOT, WIDE, 2><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+            k_scatter<ROOT, WIDE, 2><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
         else
-            k_scatter<ROOT, WIDE, 3><<<a.ntiles, kScatterThreads, sm, stream>>>(a);
+            k_scatter<ROOT, WIDE, 3><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
     }
     void scatter(const PassArgs& a) override {
         const size_t sm = a.wide ? ScatterSmem<true>::bytes(a.nbins) : ScatterSmem<false>::bytes(a.nbins);

@@ -82,3 +82,24 @@ def test_degenerate_numerators():
     rgb = rng.integers(0, 255, n * 3, dtype=np.uint8)
     ref = O.build(x, y, z, rgb.reshape(-1, 3), 1e-6, (0, 0, 0), (1, 1, 1), max_points_per_node=200)
     compare_trees(ref, TbTree(x, y, z, rgb, 1e-6, (0, 0, 0), (1, 1, 1), 200, 2))
+
+
+def test_nan_inf_and_huge_coordinates():
+    """Rust `as u8/u16` maps NaN to 0 and saturates; NaN survives Float32/Float64 codes (num::clamp passes it through).
+    Host arithmetic (csrc/chain.h) against the oracle; the GPU twin is tests/test_build_gpu.py::test_wild_inputs_*."""
+    rng = np.random.default_rng(23)
+    n = 30000
+    P = rng.random((n, 3)) * 100.0 + [4.1e6, 6.6e5, 4.7e6]
+    bmin, bmax = P.min(0).copy(), P.max(0).copy()
+    P[100] = [1e200, 6.6e5, 4.7e6]
+    P[5000, 1] = -1e300
+    P[9000, 2] = np.inf
+    P[12000, 0] = -np.inf
+    P[20000] = [np.nan, 6.6e5 + 1, 4.7e6 + 1]
+    P[20001, 2] = 2.0 ** 399
+    P[25000] = 0.0
+    x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
+    rgb = rng.integers(0, 255, n * 3, dtype=np.uint8)
+    for maxpts, res, G in ((300, 1e-4, 2), (2000, 1e-9, 3), (300, 1e-3, 1)):
+        ref = O.build(x, y, z, rgb.reshape(-1, 3), res, bmin, bmax, max_points_per_node=maxpts)
+        compare_trees(ref, TbTree(x, y, z, rgb, res, bmin, bmax, maxpts, G))
