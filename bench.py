@@ -350,11 +350,17 @@ def run_ours(args):
             orgb = torch.empty(ne * 3, dtype=torch.uint8, pin_memory=True)
 
             def e2e_step():
+                q0 = time.perf_counter()
                 t = ctx.build_octree(hx.data_ptr(), hy.data_ptr(), hz.data_ptr(), hrgb.data_ptr(), res, bmin, bmax, n=ne)
+                q1 = time.perf_counter()
                 assert t.xyz_bytes <= oxyz.numel()
                 t.download(xyz=oxyz.data_ptr(), rgb=orgb.data_ptr(), want_src=False)  # what build_octree leaves on disk: .xyz + .rgb + meta
-                b = (t.xyz_bytes + ne * 3 + 80 * len(t.nodes), len(t.nodes))
+                q2 = time.perf_counter()
+                b = (t.xyz_bytes + ne * 3 + 80 * t.num_nodes, t.num_nodes)
                 t.free()
+                if os.environ.get("PCV_TIMING"):
+                    print("[e2e] build call %.1f ms, download %.1f ms (%.2f GB), free %.1f ms" % ((q1 - q0) * 1e3, (q2 - q1) * 1e3, b[0] / 1e9, (time.perf_counter() - q2) * 1e3),
+                          file=sys.stderr)
                 return b
 
             e2e_step()  # two warm-up calls: the stream-ordered pool grows to hold the 27 GB staging copy

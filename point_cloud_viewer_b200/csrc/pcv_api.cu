@@ -127,14 +127,20 @@ static PointsView stage_points(pcv_ctx* c, const pcv_points* hp, std::vector<voi
         v.z = d + 2;
         v.stride = 3;
     } else if (stride == 1) {
-        double* d = (double*)c->be->dmalloc(n * 24);
-        owned.push_back(d);
-        CU(cudaMemcpyAsync(d, hp->x, n * 8, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(d + n, hp->y, n * 8, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(d + 2 * n, hp->z, n * 8, cudaMemcpyHostToDevice, c->stream));
-        v.x = d;
-        v.y = d + n;
-        v.z = d + 2 * n;
+        // three separate blocks: after earlier builds the stream-ordered pool holds free blocks of the working-set sizes
+        // (N x 16 / 4 bytes), which an N x 8 request can reuse; one N x 24 block would make the pool map fresh memory on
+        // every call (measured: +0.5 s per 1e9-point call)
+        const double* src[3] = {hp->x, hp->y, hp->z};
+        const double* dst[3];
+        for (int k = 0; k < 3; ++k) {
+            double* d = (double*)c->be->dmalloc(n * 8);
+            owned.push_back(d);
+            CU(cudaMemcpyAsync(d, src[k], n * 8, cudaMemcpyHostToDevice, c->stream));
+            dst[k] = d;
+        }
+        v.x = dst[0];
+        v.y = dst[1];
+        v.z = dst[2];
         v.stride = 1;
     } else {
         throw BuildError(PCV_ERR_INVALID, "positions must be SoA (stride 1) or interleaved xyz (stride 3, y=x+1, z=x+2)");
@@ -276,7 +282,14 @@ int pcv_build_octree(pcv_ctx* c, const pcv_points* hp, double resolution, const 
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     std::vector<void*> owned;
+    const bool timing = std::getenv("PCV_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     PointsView v = stage_points(c, hp, owned);
+    if (timing) {  // diagnostic only: the extra synchronisation separates the copies from the build
+        CU(cudaStreamSynchronize(c->stream));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[pcv_build_octree] staged %.2f GB host->device in %.1f ms (%.1f GB/s)\n", hp->n * 27e-9, ms, hp->n * 27e-6 / ms);
+    }
     int rc;
     try {
         rc = build_impl(c, v, resolution, bbox_min, bbox_max, out);
