@@ -282,7 +282,7 @@ def run_ours(args):
             "workload": "build_octree on %d synthetic Gaussian-cluster points per GPU (BASELINE config %d), resolution 1024/2^20 (depth 20), XYZ f64 SoA + RGB" % (n, 2 if world == 1 else 4),
             "points_per_gpu": n, "levels_per_pass": args.levels_per_pass, "max_points_per_node": 100000,
             "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (27.0 * n / 1e9),
-            "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix, one NCCL all-to-all" % args.prefix_levels,
+            "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix; one fused pack+exchange kernel stores every point into its owner's memory over NVLink (CUDA IPC peer mapping), NCCL only for the small all-reduces" % args.prefix_levels,
         },
         "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": int(launches), "octree_nodes": nodes, "deepest_level": int(stats["deepest_level"]),
         "clocks": clocks,

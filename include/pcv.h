@@ -171,6 +171,24 @@ int pcv_prefix_pack_device(pcv_ctx* ctx, const pcv_points* dev_points, const uin
                            const int32_t* cell_to_rank /* 8^k, host */, uint32_t nranks, double* dev_xyz_out /* n*3 AoS */,
                            uint8_t* dev_rgb_out, float* dev_intensity_out, uint64_t* dev_index_out,
                            uint64_t* rank_counts_out /* nranks, host */);
+/* Fused pack + exchange: the same stable pack, but every record is stored straight into the destination rank's receive
+ * arrays (SoA: x, y, z f64; global index u64; intensity f32; colour packed r | g << 8 | b << 16 as u32) - local memory
+ * for the own rank, peer memory mapped through CUDA IPC (below) for the others, so the transfer over NVLink / NVSwitch
+ * overlaps the ranking; there is no send buffer and no collective call.  dst_*[r]: base pointers of rank r's arrays as
+ * mapped in THIS process; dst_first[r]: first slot of this rank's block inside them (sum of the counts of lower ranks).
+ * The call returns after the kernel has completed; the caller then runs one inter-process barrier. */
+int pcv_prefix_pack_exchange_device(pcv_ctx* ctx, const pcv_points* dev_points, const uint64_t* dev_global_index /* or NULL */,
+                                    uint64_t global_index_base, double resolution, const double bbox_min[3], const double bbox_max[3],
+                                    uint32_t k, const int32_t* cell_to_rank /* 8^k, host */, uint32_t nranks,
+                                    const uint64_t* dst_first /* nranks, host */, void* const* dst_x, void* const* dst_y, void* const* dst_z,
+                                    void* const* dst_index, void* const* dst_intensity /* or NULL */, void* const* dst_colour,
+                                    uint64_t* rank_counts_out /* nranks, host */);
+int pcv_unpack_colours_device(pcv_ctx* ctx, const uint32_t* dev_colour, uint64_t n, uint8_t* dev_rgb /* n * 3 */);
+/* Exportable device memory (plain cudaMalloc + cudaIpcGetMemHandle) and its mapping in a peer process. */
+int pcv_ipc_alloc(pcv_ctx* ctx, uint64_t bytes, void** dev_ptr, uint8_t handle_out[64]);
+int pcv_ipc_free(pcv_ctx* ctx, void* dev_ptr);
+int pcv_ipc_open(pcv_ctx* ctx, const uint8_t handle[64], void** dev_ptr);
+int pcv_ipc_close(pcv_ctx* ctx, void* dev_ptr);
 /* Local part of a sharded build: like pcv_build_octree_device, but nodes of levels <= k take their split decision from
  * the GLOBAL counts (`prefix_counts`: levels 1..k concatenated, 8 + 64 + .. entries, host), and the nodes of level k-1
  * collect the every-8th points of their local children for pcv_assemble_top. */

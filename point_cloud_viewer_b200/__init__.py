@@ -153,6 +153,48 @@ class Context:
                                                _p(c2r), nranks, _p(out_xyz), _p(out_rgb), _p(out_intensity), _p(out_idx), _p(counts)))
         return counts
 
+    def prefix_pack_exchange_device(self, x, y, z, rgb, intensity, gidx_base, n, resolution, bbox_min, bbox_max, k, cell_to_rank, nranks, dst_first,
+                                    dst_x, dst_y, dst_z, dst_index, dst_intensity, dst_colour):
+        """Fused pack + exchange (pcv.h): dst_* are lists of device pointers (one per rank, as mapped in this process)."""
+        pts = N.Points(_p(x), _p(y), _p(z), 1, _p(rgb), _p(intensity), int(n))
+        c2r = np.ascontiguousarray(cell_to_rank, np.int32)
+        first = np.ascontiguousarray(dst_first, np.uint64)
+        arr = lambda lst: (C.c_void_p * nranks)(*[int(v) if v else None for v in lst])
+        ax, ay, az, ai, ac = arr(dst_x), arr(dst_y), arr(dst_z), arr(dst_index), arr(dst_colour)
+        an = arr(dst_intensity) if dst_intensity is not None else None
+        counts = np.zeros(nranks, np.uint64)
+        N.check(N.lib().pcv_prefix_pack_exchange_device(self.h, C.byref(pts), None, int(gidx_base), float(resolution), _d3(bbox_min), _d3(bbox_max), k,
+                                                        _p(c2r), nranks, _p(first), ax, ay, az, ai, an, ac, _p(counts)))
+        return counts
+
+    def unpack_colours_device(self, colour_ptr, n, rgb_ptr):
+        N.check(N.lib().pcv_unpack_colours_device(self.h, colour_ptr, int(n), rgb_ptr))
+
+    def ipc_alloc(self, nbytes):
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        N.check(N.lib().pcv_ipc_alloc(self.h, int(nbytes), C.byref(p), h))
+        return p.value, bytes(h)
+
+    def ipc_free(self, ptr):
+        N.check(N.lib().pcv_ipc_free(self.h, ptr))
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        hb = (C.c_uint8 * 64).from_buffer_copy(handle)
+        N.check(N.lib().pcv_ipc_open(self.h, hb, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        N.check(N.lib().pcv_ipc_close(self.h, ptr))
+
+    def build_octree_sharded_device_soa(self, x_ptr, y_ptr, z_ptr, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
+        """Local part of a sharded build from SoA device arrays (the layout the fused exchange delivers)."""
+        pts = N.Points(x_ptr, y_ptr, z_ptr, 1, rgb_ptr, intensity_ptr, int(n))
+        pc = np.ascontiguousarray(prefix_counts, np.uint64)
+        out = C.c_void_p()
+        N.check(N.lib().pcv_build_octree_sharded_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(pc), C.byref(out)))
+        return Octree(self, out)
+
     def build_octree_sharded_device(self, xyz_ptr, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
         """Local part of a sharded build: AoS xyz (n*3 f64) device pointer; prefix_counts = global counts of levels 1..k."""
         pts = N.Points(xyz_ptr, xyz_ptr + 8, xyz_ptr + 16, 3, rgb_ptr, intensity_ptr, int(n))

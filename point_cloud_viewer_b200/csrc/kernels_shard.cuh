@@ -113,4 +113,73 @@ __global__ void __launch_bounds__(256) k_pack_scatter(const __grid_constant__ Pa
     }
 }
 
+// ---- fused pack + exchange ------------------------------------------------------------------------------------------
+// The same stable ranking as k_pack_scatter, but every record is stored straight into its destination rank's receive
+// arrays - local memory for the own rank, peer memory mapped through CUDA IPC for the others, i.e. the stores travel over
+// NVLink / NVSwitch while the kernel is still ranking the next points.  No send buffers, no separate collective: the
+// exchange is finished when the kernel is (followed by one inter-process barrier).  Receive arrays are SoA (x, y, z,
+// index, intensity, packed colour) so that the lanes of a warp that share a destination write contiguous runs.
+struct PeerTable {
+    double* x[kMaxRanks];
+    double* y[kMaxRanks];
+    double* z[kMaxRanks];
+    uint64_t* idx[kMaxRanks];
+    float* intensity[kMaxRanks];
+    uint32_t* col[kMaxRanks];    // r | g << 8 | b << 16
+    uint64_t first[kMaxRanks];   // first slot of this rank's block inside destination d's arrays
+};
+
+__global__ void __launch_bounds__(256) k_pack_exchange(const __grid_constant__ PackArgs a, const PeerTable* __restrict__ pt) {
+    __shared__ uint64_t base[kMaxRanks];
+    __shared__ uint32_t wc[8][kMaxRanks];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < a.nranks) {
+        const uint32_t* row = a.counts + (size_t)threadIdx.x * a.ntiles;  // exclusive prefix over (rank, tile), rank-major
+        base[threadIdx.x] = pt->first[threadIdx.x] + (row[blockIdx.x] - row[0]);
+    }
+    const uint64_t t0 = (uint64_t)blockIdx.x * kPackTile;
+    const uint32_t n = (uint32_t)min((uint64_t)kPackTile, a.p.pts.n - t0);
+    for (uint32_t r0 = 0; r0 < n; r0 += 256) {
+        for (int i = threadIdx.x; i < 8 * kMaxRanks; i += 256) (&wc[0][0])[i] = 0;
+        __syncthreads();
+        const uint32_t i = r0 + threadIdx.x;
+        const uint32_t d = i < n ? a.dest[t0 + i] : 0xFFu;
+        const unsigned mask = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+        if (d != 0xFFu && lane == __ffs(mask) - 1) wc[warp][d] = __popc(mask);
+        __syncthreads();
+        if (d != 0xFFu) {
+            uint32_t before = 0;
+            for (int w = 0; w < warp; ++w) before += wc[w][d];
+            const uint64_t dst = base[d] + before + rank;
+            const uint64_t g = t0 + i;
+            pt->x[d][dst] = __ldg(a.p.pts.x + g * a.p.pts.stride);
+            pt->y[d][dst] = __ldg(a.p.pts.y + g * a.p.pts.stride);
+            pt->z[d][dst] = __ldg(a.p.pts.z + g * a.p.pts.stride);
+            const uint8_t* c = a.p.pts.rgb + 3 * g;
+            pt->col[d][dst] = (uint32_t)__ldg(c) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c + 2) << 16);
+            if (a.p.pts.intensity) pt->intensity[d][dst] = __ldg(a.p.pts.intensity + g);
+            pt->idx[d][dst] = a.gidx_in ? __ldg(a.gidx_in + g) : a.gidx_base + g;
+        }
+        __syncthreads();
+        if (threadIdx.x < a.nranks) {
+            uint32_t s = 0;
+            for (int w = 0; w < 8; ++w) s += wc[w][threadIdx.x];
+            base[threadIdx.x] += s;
+        }
+        __syncthreads();
+    }
+}
+
+// packed colours (as exchanged) -> the r, g, b byte array the build takes
+__global__ void __launch_bounds__(256) k_unpack_colours(const uint32_t* __restrict__ col, uint64_t n, uint8_t* __restrict__ rgb) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const uint32_t c = __ldg(col + i);
+        rgb[3 * i] = (uint8_t)c;
+        rgb[3 * i + 1] = (uint8_t)(c >> 8);
+        rgb[3 * i + 2] = (uint8_t)(c >> 16);
+    }
+}
+
 }  // namespace pcv

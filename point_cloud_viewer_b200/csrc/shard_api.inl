@@ -92,6 +92,125 @@ int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgi
     API_CATCH
 }
 
+// ---- peer memory for the fused pack + exchange (CUDA IPC; one process per GPU) ----------------------------------------
+int pcv_ipc_alloc(pcv_ctx* c, uint64_t bytes, void** dev_ptr, uint8_t handle_out[64]) {
+    if (!c || !dev_ptr || !handle_out) return fail(PCV_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes ? bytes : 256));  // plain cudaMalloc: stream-ordered pool memory cannot be exported
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        throw BuildError(PCV_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, 64);
+    *dev_ptr = p;
+    return PCV_OK;
+    API_CATCH
+}
+int pcv_ipc_free(pcv_ctx* c, void* dev_ptr) {
+    if (!c) return fail(PCV_ERR_INVALID, "null context");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (dev_ptr) CU(cudaFree(dev_ptr));
+    return PCV_OK;
+    API_CATCH
+}
+int pcv_ipc_open(pcv_ctx* c, const uint8_t handle[64], void** dev_ptr) {
+    if (!c || !handle || !dev_ptr) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PCV_OK;
+    API_CATCH
+}
+int pcv_ipc_close(pcv_ctx* c, void* dev_ptr) {
+    if (!c) return fail(PCV_ERR_INVALID, "null context");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (dev_ptr) CU(cudaIpcCloseMemHandle(dev_ptr));
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_prefix_pack_exchange_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgidx, uint64_t gidx_base, double resolution,
+                                    const double bmin[3], const double bmax[3], uint32_t k, const int32_t* cell_to_rank, uint32_t nranks,
+                                    const uint64_t* dst_first, void* const* dst_x, void* const* dst_y, void* const* dst_z, void* const* dst_index,
+                                    void* const* dst_intensity, void* const* dst_colour, uint64_t* rank_counts_out) {
+    if (!c || !dp || !bmin || !bmax || !cell_to_rank || !dst_first || !dst_x || !dst_y || !dst_z || !dst_index || !dst_colour || !rank_counts_out)
+        return fail(PCV_ERR_INVALID, "null argument");
+    if (nranks == 0 || nranks > (uint32_t)kMaxRanks) return fail(PCV_ERR_INVALID, "nranks must be 1..%d", kMaxRanks);
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    PackArgs a{};
+    a.p = make_prefix_args(dp, resolution, bmin, bmax, k);
+    for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = 0;
+    const uint64_t n = a.p.pts.n;
+    if (n == 0) return PCV_OK;
+    if (n >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-2 points per context");
+    if (!a.p.pts.rgb) return fail(PCV_ERR_INVALID, "color is mandatory");
+    if (a.p.pts.intensity && !dst_intensity) return fail(PCV_ERR_INVALID, "intensity destinations missing");
+    for (int i = 0; i < a.p.nbins; ++i)
+        if (cell_to_rank[i] < 0 || cell_to_rank[i] >= (int32_t)nranks) return fail(PCV_ERR_INVALID, "cell_to_rank[%d] out of range", i);
+    Scratch s(c);
+    a.cell_to_rank = s.upload(cell_to_rank, (size_t)a.p.nbins);
+    a.nranks = nranks;
+    a.ntiles = (uint32_t)((n + kPackTile - 1) / kPackTile);
+    a.dest = s.alloc<uint8_t>(n);
+    a.counts = s.alloc<uint32_t>((size_t)nranks * a.ntiles);
+    a.gidx_in = dgidx;
+    a.gidx_base = gidx_base;
+    PeerTable pt{};
+    for (uint32_t r = 0; r < nranks; ++r) {
+        pt.x[r] = (double*)dst_x[r];
+        pt.y[r] = (double*)dst_y[r];
+        pt.z[r] = (double*)dst_z[r];
+        pt.idx[r] = (uint64_t*)dst_index[r];
+        pt.intensity[r] = dst_intensity ? (float*)dst_intensity[r] : nullptr;
+        pt.col[r] = (uint32_t*)dst_colour[r];
+        pt.first[r] = dst_first[r];
+    }
+    const PeerTable* d_pt = s.upload(&pt, 1);
+    k_pack_count<<<a.ntiles, 256, 0, c->stream>>>(a);
+    unsigned long long* dtot = s.alloc<unsigned long long>(1);
+    k_scan_u32<<<1, 1024, 0, c->stream>>>(a.counts, nranks * a.ntiles, dtot);
+    k_pack_exchange<<<a.ntiles, 256, 0, c->stream>>>(a, d_pt);
+    c->be->launches += 3;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> starts(nranks);
+    for (uint32_t r = 0; r < nranks; ++r) c->be->d2h(&starts[r], a.counts + (size_t)r * a.ntiles, 4);  // synchronises: the stores are out
+    for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = (r + 1 < nranks ? starts[r + 1] : (uint32_t)n) - starts[r];
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_unpack_colours_device(pcv_ctx* c, const uint32_t* dev_colour, uint64_t n, uint8_t* dev_rgb) {
+    if (!c || (n && (!dev_colour || !dev_rgb))) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return PCV_OK;
+    const int blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 16, (n + 255) / 256);
+    k_unpack_colours<<<blocks, 256, 0, c->stream>>>(dev_colour, n, dev_rgb);
+    c->be->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return PCV_OK;
+    API_CATCH
+}
+
 int pcv_build_octree_sharded_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
                                     const uint64_t* prefix_counts, pcv_octree** out) {
     if (!c || !dp || !bmin || !bmax || !prefix_counts || !out) return fail(PCV_ERR_INVALID, "null argument");

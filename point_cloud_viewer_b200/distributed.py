@@ -113,6 +113,22 @@ class TorchComm:
         self.dist.all_gather_object(lst, obj)
         return lst
 
+    def all_gather_counts(self, counts):
+        """(world, len(counts)) int64 matrix: row s = the counts of rank s."""
+        import torch
+
+        s = torch.from_numpy(np.asarray(counts, np.int64)).to(self.device)
+        out = torch.empty((self.world, s.numel()), dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, s)
+        return out.cpu().numpy()
+
+    def barrier(self):
+        if self.device.type == "cuda":
+            import torch
+
+            torch.cuda.synchronize()
+        self.dist.barrier()
+
     def done_with(self, *tensors):
         """The exchange that read these send buffers has completed: pool-backed buffers go back to the library's pool."""
         if self.device.type == "cuda":
@@ -164,6 +180,42 @@ class CudaOps:
             self.x = self.y = self.z = self.rgb = self.intensity = None
         return xyz, rgb, inten, idx, counts.astype(np.int64)
 
+    # ---- fused pack + exchange over peer memory (NVLink / NVSwitch), see kernels_shard.cuh::k_pack_exchange ----
+    def pack_exchange(self, k, cell_to_rank, nranks, index_base, comm, send_counts):
+        """Returns a PeerReceive: this rank's received points (SoA device arrays inside its exportable slab)."""
+        import torch
+
+        M = comm.all_gather_counts(send_counts)  # M[s][d]: points rank s sends to rank d; identical on every rank
+        need = M.sum(0)  # per destination
+        slab = PeerSlab.get(self.ctx, comm, int(need.max()), self.intensity is not None)
+        rank = comm.rank
+        first = [int(M[:rank, d].sum()) for d in range(nranks)]
+        A = [slab.arrays(d) for d in range(nranks)]
+        counts = self.ctx.prefix_pack_exchange_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.rgb.data_ptr(),
+                                                      self.intensity.data_ptr() if self.intensity is not None else None, index_base, self.n, self.res,
+                                                      self.bmin, self.bmax, k, cell_to_rank, nranks, first, [a["x"] for a in A], [a["y"] for a in A],
+                                                      [a["z"] for a in A], [a["idx"] for a in A],
+                                                      [a["intensity"] for a in A] if self.intensity is not None else None, [a["col"] for a in A])
+        assert [int(c) for c in counts] == [int(v) for v in M[rank]], "local histogram and pack disagree"
+        if self.consume_input:
+            for t in (self.x, self.y, self.z, self.rgb, self.intensity):
+                owner = getattr(t, "_pcv_owner", None) if t is not None else None
+                if owner is not None:
+                    owner.free()
+            self.x = self.y = self.z = self.rgb = self.intensity = None
+        comm.barrier()  # every rank's stores have landed (each kernel completed before its rank entered the barrier)
+        n = int(need[rank])
+        mine = slab.arrays(rank)
+        rgb = torch.empty(max(3 * n, 1), dtype=torch.uint8, device=self.device)
+        self.ctx.unpack_colours_device(mine["col"], n, rgb.data_ptr())
+        idx = torch.as_tensor(_RawCuda(mine["idx"], (max(n, 1),), "<i8"), device=self.device)[:n].clone()  # the slab is reused by the next step
+        return PeerReceive(n, mine["x"], mine["y"], mine["z"], rgb, mine["intensity"] if self.intensity is not None else None, idx)
+
+    def build_sharded_soa(self, recv, k, prefix_counts):
+        n = recv.n
+        return self.ctx.build_octree_sharded_device_soa(recv.x if n else 0, recv.y if n else 0, recv.z if n else 0, recv.rgb.data_ptr() if n else 0,
+                                                        recv.intensity if (recv.intensity and n) else None, n, self.res, self.bmin, self.bmax, k, prefix_counts)
+
     def build_sharded(self, xyz, rgb, inten, k, prefix_counts):
         n = xyz.shape[0]
         return self.ctx.build_octree_sharded_device(xyz.data_ptr() if n else 0, rgb.data_ptr() if n else 0, inten.data_ptr() if (inten is not None and n) else None, n,
@@ -172,6 +224,58 @@ class CudaOps:
     def assemble_top(self, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten):
         return self.ctx.assemble_top(self.res, self.bmin, self.bmax, k, prefix_counts, unit_nsub, xyz_codes, rgb, inten)
 
+
+
+class _RawCuda:
+    """A device pointer as __cuda_array_interface__ (zero-copy torch view of slab memory)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class PeerReceive:
+    def __init__(self, n, x, y, z, rgb, intensity, idx):
+        self.n, self.x, self.y, self.z, self.rgb, self.intensity, self.idx = n, x, y, z, rgb, intensity, idx
+
+
+class PeerSlab:
+    """Per-rank receive slab in exportable device memory, mapped into every peer process through CUDA IPC.  All ranks use
+    the same capacity (so that the sub-array offsets of a peer's slab are known): x | y | z | index (8 B each) | intensity |
+    packed colour (4 B each).  Re-created collectively, and rarely, when a step needs more room (decided from the
+    all-gathered count matrix, i.e. identically on every rank, without an extra collective)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, ctx, comm, need_points, with_intensity):
+        cur = cls._cache.get(id(ctx))
+        if cur is not None and cur.cap >= need_points and cur.world == comm.world:
+            return cur
+        if cur is not None:
+            cur.close(comm)
+        cap = ((int(need_points * 1.05) + 4096 + 4095) // 4096) * 4096
+        cls._cache[id(ctx)] = slab = cls(ctx, comm, cap)
+        return slab
+
+    def __init__(self, ctx, comm, cap):
+        self.ctx, self.cap, self.world, self.rank = ctx, cap, comm.world, comm.rank
+        self.ptr, handle = ctx.ipc_alloc(40 * cap)
+        handles = comm.all_gather_objects(handle)
+        self.peer = [self.ptr if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        comm.barrier()
+
+    def arrays(self, r):
+        b, c = self.peer[r], self.cap
+        return {"x": b, "y": b + 8 * c, "z": b + 16 * c, "idx": b + 24 * c, "intensity": b + 32 * c, "col": b + 36 * c}
+
+    def close(self, comm):
+        comm.barrier()  # nobody is still writing into a slab that is about to disappear
+        for r, p in enumerate(self.peer):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        comm.barrier()
+        self.ctx.ipc_free(self.ptr)
+        PeerSlab._cache.pop(id(self.ctx), None)
 
 
 class ShardedOctree:
@@ -263,10 +367,12 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     mark("bbox")
     # (1) global histogram of level-k cells
     k = int(prefix_levels)
-    counts_k = comm.all_reduce_sum_u64(ops.prefix_histogram(k))
+    local_hist = np.asarray(ops.prefix_histogram(k), np.uint64)
+    counts_k = comm.all_reduce_sum_u64(local_hist)
     k2 = usable_prefix_levels(counts_k, k, root_edge, res, max_points_per_node)
     if k2 < k:
         counts_k = counts_k.reshape(8 ** k2, -1).sum(1).astype(np.uint64)
+        local_hist = local_hist.reshape(8 ** k2, -1).sum(1).astype(np.uint64)
         k = k2
     levels = level_counts(counts_k, k)
     prefix_counts = concat_counts(levels)
@@ -274,6 +380,24 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     mark("histogram")
     # (2) cells -> ranks, (3) stable pack + one all-to-all
     c2r = assign_cells(counts_k, nranks)
+    fused = hasattr(ops, "pack_exchange") and not os.environ.get("PCV_NO_FUSED_EXCHANGE")
+    if fused:
+        # one kernel ranks the points and stores them straight into the destination ranks' receive arrays over NVLink
+        send_counts = np.array([int(local_hist[c2r == d].sum()) for d in range(nranks)], np.int64)
+        recv = ops.pack_exchange(k, c2r, nranks, index_base, comm, send_counts)
+        mark("pack+exchange")
+        local = ops.build_sharded_soa(recv, k, prefix_counts)
+        r_idx = recv.idx
+        mark("local build")
+    else:
+        local, r_idx = _staged_exchange_and_build(ops, comm, k, c2r, nranks, index_base, prefix_counts, mark)
+    stats = local.ctx.last_build_stats() if hasattr(local, "ctx") and hasattr(local.ctx, "last_build_stats") else {}
+    return _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts, stats, inside, marks, mark)
+
+
+def _staged_exchange_and_build(ops, comm, k, c2r, nranks, index_base, prefix_counts, mark):
+    """Stable pack into send buffers + one NCCL / gloo all-to-all per attribute array (the path of the CPU tests, and of
+    PCV_NO_FUSED_EXCHANGE=1)."""
     xyz, rgb, inten, idx, send_counts = ops.pack(k, c2r, nranks, index_base)
     mark("pack")
     recv_counts = comm.exchange_counts(send_counts)
@@ -294,7 +418,14 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     # (4) independent local build of this rank's sub-trees
     local = ops.build_sharded(r_xyz, r_rgb, r_int, k, prefix_counts)
     mark("local build")
-    stats = local.ctx.last_build_stats() if hasattr(local, "ctx") and hasattr(local.ctx, "last_build_stats") else {}
+    return local, r_idx
+
+
+def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts, stats, inside, marks, mark):
+    import os
+    import time
+
+    res = ops.res
 
     # (5) top of the tree: unit sizes, collectors' content -> rank 0
     unit_nsub = np.zeros(8 ** k, np.uint64)
@@ -345,7 +476,7 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
         print("[pcv sharded] " + "  ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), flush=True)
     out = ShardedOctree(local, top, k, r_idx, top_index, c2r, rank, stats)
     out.bbox_inside = inside
-    out.recv_points = int(np.sum(recv_counts))
+    out.recv_points = int(r_idx.numel()) if hasattr(r_idx, "numel") else len(r_idx)
     return out
 
 
