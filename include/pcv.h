@@ -158,6 +158,14 @@ int pcv_query_batch_device(const pcv_octree* o, const pcv_location* locs, uint32
  * (the reference returns None). zbits_out (optional): w*h*32 u32 z-bucket bitsets. */
 int pcv_xray_tile(const pcv_octree* o, const double tile_min[3], const double tile_max[3], uint32_t w, uint32_t h,
                   const double* query_from_global, uint8_t* rgba_out, uint32_t* zbits_out, int* any_points_out);
+/* The other ColoringStrategyKinds (xray/src/generation.rs:76-97): point colour mean (:294-363), intensity mean brightened
+ * by ln(mean - min) / ln(max - min) (:210-290; p0 = min, p1 = max), height standard deviation through the Jet (0) or
+ * Purplish (1) colormap (:365-405, xray/src/colormap.rs; p0 = max_stddev).  Binning = None.  The reference accumulates in
+ * arrival order from several threads, so results are defined up to rounding: expect +-1 per channel. */
+enum { PCV_XRAY_COLORED = 1, PCV_XRAY_INTENSITY = 2, PCV_XRAY_HEIGHT_STDDEV = 3 };
+int pcv_xray_tile_attr(const pcv_octree* o, const double tile_min[3], const double tile_max[3], uint32_t w, uint32_t h,
+                       const double* query_from_global /* 7 or NULL */, int strategy, float p0, float p1, int colormap, uint8_t* rgba_out,
+                       int* any_out);
 
 /* ---- multi-GPU helpers (points shard by level-k path prefix) ------------------ */
 /* Per-point level-k cell (first k steps of the re-quantising descent on the raw positions) ->

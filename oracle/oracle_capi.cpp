@@ -288,6 +288,18 @@ int orc_xray_tile(void* hp, const double* bbox_min, const double* bbox_max, uint
     return any ? 1 : 0;
 }
 
+int orc_xray_tile_attr(void* hp, const double* bbox_min, const double* bbox_max, uint32_t w, uint32_t hgt, const double* query_from_global7, int mode,
+                       float p0, float p1, int colormap, uint8_t* rgba_out) {
+    Handle* h = (Handle*)hp;
+    Aabb bb = Aabb::make({bbox_min[0], bbox_min[1], bbox_min[2]}, {bbox_max[0], bbox_max[1], bbox_max[2]});
+    Iso3 q{};
+    if (query_from_global7) q = iso_from7(query_from_global7);
+    std::vector<uint8_t> rgba;
+    bool any = xray_tile_attr(h->oct, bb, w, hgt, query_from_global7 != nullptr, q, mode, p0, p1, colormap, rgba);
+    std::memcpy(rgba_out, rgba.data(), rgba.size());
+    return any ? 1 : 0;
+}
+
 // ---- disk ----
 int orc_write_dir(void* hp, const char* dir) { return write_dir(((Handle*)hp)->oct, dir) ? 0 : -1; }
 void* orc_load_dir(const char* dir) {

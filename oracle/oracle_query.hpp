@@ -522,4 +522,135 @@ inline bool xray_tile(const Octree& oct, const Aabb& bbox, uint32_t w, uint32_t 
     return true;
 }
 
+// ---- the other colouring strategies of the X-ray tiles (xray/src/generation.rs:200-405), binning = None ------------------
+// Points arrive in the canonical order (nodes in BFS order, points in node order).  The reference receives its batches
+// from several worker threads in unspecified order and accumulates in f32 / f64 without compensation, so its own output
+// is reproducible only up to rounding; tests compare with a tolerance of one grey level.  With `Binning = None` every
+// column has the single bin 0, so the outer mean over bins is `(0 + mean) / 1`.
+//   mode 1  PointColorColoringStrategy  (:294-363): per column sum of Color<f32> (u8 / 255), mean, to_u8 (`as u8`)
+//   mode 2  IntensityColoringStrategy   (:210-290): per column mean intensity, clamped to [min, max],
+//                                                   brighten = ln(mean - min) / ln(max - min)  (f32), grey = to_u8.
+//           The reference `return`s from the whole batch at the first negative intensity (:245-247), which makes the
+//           result depend on batch boundaries; restated as "points with negative intensity are skipped".
+//   mode 3  HeightStddevColoringStrategy (:365-405): stats::OnlineStats per column over the (transformed) z, colour =
+//           colormap(clamp(stddev as f32, 0, max_stddev) / max_stddev); colormap 0 = Jet, 1 = Monochrome(PURPLISH)
+//           (xray/src/colormap.rs).  OnlineStats (crate `stats`, un-vendored) restated from memory as the Welford update
+//           with population variance: parity unpinned.
+inline uint8_t f32_to_u8(float v) {  // Color<f32>::to_u8: (v * 255.) as u8
+    const float s = v * 255.f;
+    if (!(s == s) || s <= 0.f) return 0;
+    if (s >= 255.f) return 255;
+    return (uint8_t)s;
+}
+inline float jet_base(float val) {
+    auto interp = [](float v, float y0, float x0, float y1, float x1) { return (v - x0) * (y1 - y0) / (x1 - x0) + y0; };
+    if (val <= -0.75f) return 0.f;
+    if (val <= -0.25f) return interp(val, 0.0f, -0.75f, 1.0f, -0.25f);
+    if (val <= 0.25f) return 1.0f;
+    if (val <= 0.75f) return interp(val, 1.0f, 0.25f, 0.0f, 0.75f);
+    return 0.0f;
+}
+inline void colormap_u8(int colormap, float val, uint8_t out[4]) {
+    if (colormap == 0) {  // Jet
+        out[0] = f32_to_u8(jet_base(val - 0.5f));
+        out[1] = f32_to_u8(jet_base(val));
+        out[2] = f32_to_u8(jet_base(val + 0.5f));
+    } else {  // Monochrome(PURPLISH = 0.8, 0.8, 1.0)
+        out[0] = f32_to_u8((1.0f - val) * 0.8f);
+        out[1] = f32_to_u8((1.0f - val) * 0.8f);
+        out[2] = f32_to_u8((1.0f - val) * 1.0f);
+    }
+    out[3] = f32_to_u8(1.0f);
+}
+
+inline Location xray_location(const Aabb& bbox, bool has_q, const Iso3& query_from_global) {
+    Location loc;
+    if (has_q) {  // as in xray_tile above
+        Iso3 global_from_query = iso_inverse(query_from_global);
+        Vec3 c{(bbox.mins.x + bbox.maxs.x) * 0.5, (bbox.mins.y + bbox.maxs.y) * 0.5, (bbox.mins.z + bbox.maxs.z) * 0.5};
+        Vec3 d = bbox.diag();
+        Obb o;
+        o.half_extent = {d.x * 0.5, d.y * 0.5, d.z * 0.5};
+        Iso3 qfo;
+        Vec3 sh = quat_rotate(global_from_query.q, c);
+        qfo.t = {global_from_query.t.x + sh.x, global_from_query.t.y + sh.y, global_from_query.t.z + sh.z};
+        const double* g = global_from_query.q;
+        qfo.q[3] = g[3] * 1.0 - g[0] * 0.0 - g[1] * 0.0 - g[2] * 0.0;
+        qfo.q[0] = g[3] * 0.0 + g[0] * 1.0 + g[1] * 0.0 - g[2] * 0.0;
+        qfo.q[1] = g[3] * 0.0 - g[0] * 0.0 + g[1] * 1.0 + g[2] * 0.0;
+        qfo.q[2] = g[3] * 0.0 + g[0] * 0.0 - g[1] * 0.0 + g[2] * 1.0;
+        o.query_from_obb = qfo;
+        o.obb_from_query = iso_inverse(qfo);
+        loc.kind = LOC_OBB;
+        loc.obb = o;
+    } else {
+        loc.kind = LOC_AABB;
+        loc.aabb = bbox;
+    }
+    return loc;
+}
+
+inline bool xray_tile_attr(const Octree& oct, const Aabb& bbox, uint32_t w, uint32_t h, bool has_q, const Iso3& query_from_global, int mode,
+                           float p0, float p1, int colormap, std::vector<uint8_t>& rgba) {
+    const Location loc = xray_location(bbox, has_q, query_from_global);
+    const size_t npix = (size_t)w * h;
+    std::vector<float> sum(npix * 4, 0.f);
+    std::vector<uint64_t> count(npix, 0);
+    std::vector<double> mean(npix, 0.0), variance(npix, 0.0);  // OnlineStats
+    bool seen_any = false;
+    std::vector<Interval> nofilter;
+    Vec3 mn = bbox.mins, dg = bbox.diag();
+    for (NodeId id : nodes_in_location(oct, loc)) {
+        QueryOut q;
+        query_node(oct, id, loc, nofilter, q);
+        const size_t n = q.src.size();
+        for (size_t i = 0; i < n; ++i) {
+            seen_any = true;
+            Vec3 p{q.xyz[3 * i], q.xyz[3 * i + 1], q.xyz[3 * i + 2]};
+            if (has_q) p = iso_transform_point(query_from_global, p);
+            const uint32_t x = rust_f64_as_u32(((p.x - mn.x) / dg.x) * (double)w);
+            const uint32_t y = rust_f64_as_u32((1. - ((p.y - mn.y) / dg.y)) * (double)h);
+            if (!(x < w && y < h)) continue;
+            const size_t px = (size_t)y * w + x;
+            if (mode == 1) {
+                sum[px * 4 + 0] += (float)q.rgb[3 * i] / 255.f;
+                sum[px * 4 + 1] += (float)q.rgb[3 * i + 1] / 255.f;
+                sum[px * 4 + 2] += (float)q.rgb[3 * i + 2] / 255.f;
+                sum[px * 4 + 3] += 255.f / 255.f;
+                count[px]++;
+            } else if (mode == 2) {
+                const float v = q.intensity.empty() ? 0.f : q.intensity[i];
+                if (v < 0.f) continue;
+                sum[px * 4] += v;
+                count[px]++;
+            } else {
+                const double sample = p.z, oldmean = mean[px], prevq = variance[px] * (double)count[px];
+                count[px]++;
+                mean[px] += (sample - oldmean) / (double)count[px];
+                variance[px] = (prevq + (sample - oldmean) * (sample - mean[px])) / (double)count[px];
+            }
+        }
+    }
+    rgba.assign(npix * 4, 0);
+    if (!seen_any) return false;
+    for (size_t px = 0; px < npix; ++px) {
+        if (count[px] == 0) continue;
+        uint8_t* o = &rgba[px * 4];
+        if (mode == 1) {
+            for (int k = 0; k < 4; ++k) o[k] = f32_to_u8((0.f + sum[px * 4 + k] / (float)count[px]) / 1.f);
+        } else if (mode == 2) {
+            float m = (0.f + sum[px * 4] / (float)count[px]) / 1.f;
+            m = std::fmin(std::fmax(m, p0), p1);  // f32::max / f32::min
+            const float brighten = std::log(m - p0) / std::log(p1 - p0);
+            o[0] = o[1] = o[2] = f32_to_u8(brighten);
+            o[3] = f32_to_u8(1.f);
+        } else {
+            float sd = (float)std::sqrt(variance[px]);
+            sd = sd < 0.f ? 0.f : (sd > p0 ? p0 : sd);  // num::clamp
+            colormap_u8(colormap, sd / p0, o);
+        }
+    }
+    return true;
+}
+
 }  // namespace orc

@@ -50,6 +50,9 @@ def device_count():
     return N.lib().pcv_device_count()
 
 
+XRAY_COLORED, XRAY_INTENSITY, XRAY_HEIGHT_STDDEV = 1, 2, 3
+
+
 class Context:
     """One per GPU (pcv_ctx)."""
 
@@ -434,6 +437,15 @@ class Octree:
         q = (C.c_double * 7)(*[float(v) for v in query_from_global]) if query_from_global is not None else None
         N.check(N.lib().pcv_xray_tile(self.h, _d3(tile_min), _d3(tile_max), w, h, q, _p(rgba), _p(zb), C.byref(anyp)))
         return bool(anyp.value), rgba, zb
+
+    def xray_tile_attr(self, tile_min, tile_max, w, h, strategy, p0=0.0, p1=0.0, colormap=0, query_from_global=None):
+        """strategy: XRAY_COLORED / XRAY_INTENSITY (p0 = min, p1 = max) / XRAY_HEIGHT_STDDEV (p0 = max_stddev, colormap 0 Jet, 1 Purplish)."""
+        rgba = np.zeros((h, w, 4), np.uint8)
+        anyp = C.c_int()
+        q = (C.c_double * 7)(*[float(v) for v in query_from_global]) if query_from_global is not None else None
+        N.check(N.lib().pcv_xray_tile_attr(self.h, _d3(tile_min), _d3(tile_max), w, h, q, int(strategy), float(p0), float(p1), int(colormap), _p(rgba),
+                                           C.byref(anyp)))
+        return bool(anyp.value), rgba
 
 
 def ply_read_header(path):

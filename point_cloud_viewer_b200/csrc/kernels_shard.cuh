@@ -29,12 +29,17 @@ __device__ __forceinline__ unsigned prefix_cell(const PrefixArgs& a, uint64_t i)
     return cell;
 }
 
-__global__ void __launch_bounds__(256) k_prefix_hist(const __grid_constant__ PrefixArgs a, unsigned long long* __restrict__ counts) {
+// `cells` (optional): the cell of every point, kept for the pack that follows so that it does not repeat the descent.
+__global__ void __launch_bounds__(256) k_prefix_hist(const __grid_constant__ PrefixArgs a, unsigned long long* __restrict__ counts, uint16_t* __restrict__ cells) {
     extern __shared__ uint32_t sh_cnt[];
     for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) sh_cnt[b] = 0;
     __syncthreads();
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pts.n; i += step) atomicAdd(&sh_cnt[prefix_cell(a, i)], 1u);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pts.n; i += step) {
+        const unsigned cell = prefix_cell(a, i);
+        if (cells) cells[i] = (uint16_t)cell;
+        atomicAdd(&sh_cnt[cell], 1u);
+    }
     __syncthreads();
     for (int b = threadIdx.x; b < a.nbins; b += blockDim.x)
         if (sh_cnt[b]) atomicAdd(&counts[b], (unsigned long long)sh_cnt[b]);
@@ -48,6 +53,8 @@ struct PackArgs {
     PrefixArgs p;
     const int32_t* cell_to_rank;  // device, nbins
     uint32_t nranks, ntiles;
+    const uint16_t* cells;  // optional: level-(k + cell_shift / 3) cells from the histogram call over the same points
+    uint32_t cell_shift;
     uint8_t* dest;        // per point destination rank (written by the count pass)
     uint32_t* counts;     // [nranks][ntiles]; after the scan: first output slot of (rank, tile)
     const uint64_t* gidx_in;  // optional global indices of the local points
@@ -65,7 +72,8 @@ __global__ void __launch_bounds__(256) k_pack_count(const __grid_constant__ Pack
     const uint64_t t0 = (uint64_t)blockIdx.x * kPackTile;
     const uint32_t n = (uint32_t)min((uint64_t)kPackTile, a.p.pts.n - t0);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = a.cell_to_rank[prefix_cell(a.p, t0 + i)];
+        const unsigned cell = a.cells ? (unsigned)a.cells[t0 + i] >> a.cell_shift : prefix_cell(a.p, t0 + i);
+        const int r = a.cell_to_rank[cell];
         a.dest[t0 + i] = (uint8_t)r;
         atomicAdd(&cnt[r], 1u);
     }

@@ -19,6 +19,12 @@ struct pcv_ctx {
     pcv_build_stats stats{};
     int sm_count = 148;
     std::mutex mu;  // build / query entry points serialise on the context's stream
+    // cells of the last pcv_prefix_histogram_device call, reused by the pack over the same points (shard_api.inl)
+    uint16_t* shard_cells = nullptr;
+    const double* shard_cells_x = nullptr;
+    uint64_t shard_cells_n = 0;
+    uint32_t shard_cells_k = 0;
+    double shard_cells_geom[7] = {0, 0, 0, 0, 0, 0, 0};  // resolution, bbox
     uint8_t* ply_pin[3] = {nullptr, nullptr, nullptr};  // pinned staging ring of the PLY loader (ply_api.inl)
     size_t ply_pin_bytes = 0;
 };

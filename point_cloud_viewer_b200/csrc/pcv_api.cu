@@ -92,6 +92,8 @@ void pcv_destroy(pcv_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->be->dfree(c->shard_cells);
+    cudaStreamSynchronize(c->stream);
     delete c->be;
     for (auto& p : c->ply_pin)
         if (p) cudaFreeHost(p);

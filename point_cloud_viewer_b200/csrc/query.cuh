@@ -396,6 +396,111 @@ __global__ void __launch_bounds__(256) k_xray_resolve(const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// The other colouring strategies of the X-ray tiles (xray/src/generation.rs:200-405), Binning = None:
+//   1 point colour mean, 2 intensity mean (log-brightened), 3 height standard deviation through a colormap.
+// The reference accumulates per column in arrival order (f32 sums, Welford in f64) and its batches arrive from several
+// threads in unspecified order; here the columns are accumulated with atomics (f32 sums like the reference; for the
+// variance, f64 sums of (z - z0) and (z - z0)^2 around the tile's mid height), so results agree up to rounding.
+// ------------------------------------------------------------------------------------------------
+struct XrayAttrArgs {
+    XrayArgs x;
+    const uint8_t* rgb;      // node-contiguous colours
+    const float* intensity;  // node-contiguous intensities (mode 2)
+    float* sum;              // mode 1: npix * 4; mode 2: npix
+    double* dsum;            // mode 3: npix * 2
+    uint32_t* count;
+    double z0;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_xray_accum_attr(const __grid_constant__ XrayAttrArgs b) {
+    const XrayArgs& a = b.x;
+    const QTile t = a.tiles[blockIdx.x];
+    const QNode nd = a.nodes[t.node];
+    const int bpc = enc_bytes(nd.enc);
+    bool seen = false;
+    for (uint32_t i = threadIdx.x; i < t.count; i += blockDim.x) {
+        const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)(t.first + i) * 3 * bpc;
+        double p[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+        if (!loc_contains(a.geom, p[0], p[1], p[2])) continue;
+        seen = true;
+        if (a.has_q) {
+            const V3 q = iso_apply(a.query_from_global, V3{p[0], p[1], p[2]});
+            p[0] = q.x, p[1] = q.y, p[2] = q.z;
+        }
+        const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
+        const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
+        if (!(x < a.w && y < a.h)) continue;
+        const size_t px = (size_t)y * a.w + x;
+        const uint64_t slot = nd.point_off + t.first + i;
+        if (MODE == 1) {  // Color<u8>::to_f32: f32::from(c) / 255.
+            const uint8_t* c = b.rgb + 3 * slot;
+            atomicAdd(&b.sum[px * 4 + 0], (float)c[0] / 255.f);
+            atomicAdd(&b.sum[px * 4 + 1], (float)c[1] / 255.f);
+            atomicAdd(&b.sum[px * 4 + 2], (float)c[2] / 255.f);
+            atomicAdd(&b.count[px], 1u);
+        } else if (MODE == 2) {
+            const float v = b.intensity[slot];
+            if (v < 0.f) continue;
+            atomicAdd(&b.sum[px], v);
+            atomicAdd(&b.count[px], 1u);
+        } else {
+            const double d = p[2] - b.z0;
+            atomicAdd(&b.dsum[px * 2], d);
+            atomicAdd(&b.dsum[px * 2 + 1], d * d);
+            atomicAdd(&b.count[px], 1u);
+        }
+    }
+    if (__syncthreads_or(seen) && threadIdx.x == 0) atomicExch(a.any, 1);
+}
+
+__device__ __forceinline__ uint8_t f32_to_u8_dev(float v) {  // Color<f32>::to_u8: (v * 255.) as u8 (saturating, NaN -> 0)
+    const float s = v * 255.f;
+    if (!(s == s) || s <= 0.f) return 0;
+    return s >= 255.f ? (uint8_t)255 : (uint8_t)s;
+}
+__device__ __forceinline__ float jet_base_dev(float val) {  // xray/src/colormap.rs:30-46
+    if (val <= -0.75f) return 0.f;
+    if (val <= -0.25f) return (val - -0.75f) * (1.0f - 0.0f) / (-0.25f - -0.75f) + 0.0f;
+    if (val <= 0.25f) return 1.0f;
+    if (val <= 0.75f) return (val - 0.25f) * (0.0f - 1.0f) / (0.75f - 0.25f) + 1.0f;
+    return 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_xray_resolve_attr(int mode, float p0, float p1, int colormap, const float* __restrict__ sum,
+                                                           const double* __restrict__ dsum, const uint32_t* __restrict__ count, uint32_t npix,
+                                                           uint8_t* __restrict__ rgba) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npix) return;
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    const uint32_t n = count[px];
+    if (n) {
+        if (mode == 1) {
+            o = make_uchar4(f32_to_u8_dev(sum[px * 4] / (float)n), f32_to_u8_dev(sum[px * 4 + 1] / (float)n), f32_to_u8_dev(sum[px * 4 + 2] / (float)n), 255);
+        } else if (mode == 2) {
+            float m = sum[px] / (float)n;
+            m = fminf(fmaxf(m, p0), p1);
+            const uint8_t g = f32_to_u8_dev(logf(m - p0) / logf(p1 - p0));
+            o = make_uchar4(g, g, g, 255);
+        } else {
+            const double mean = dsum[px * 2] / (double)n;
+            double var = dsum[px * 2 + 1] / (double)n - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            float sd = (float)sqrt(var);
+            sd = sd < 0.f ? 0.f : (sd > p0 ? p0 : sd);
+            const float val = sd / p0;
+            if (colormap == 0)
+                o = make_uchar4(f32_to_u8_dev(jet_base_dev(val - 0.5f)), f32_to_u8_dev(jet_base_dev(val)), f32_to_u8_dev(jet_base_dev(val + 0.5f)), 255);
+            else
+                o = make_uchar4(f32_to_u8_dev((1.0f - val) * 0.8f), f32_to_u8_dev((1.0f - val) * 0.8f), f32_to_u8_dev((1.0f - val) * 1.0f), 255);
+        }
+    }
+    reinterpret_cast<uchar4*>(rgba)[px] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // /nodes_data blob (octree_web_viewer/src/backend.rs:92-165): gather the position and colour bytes of the requested
 // nodes from their places in the octree arrays into one contiguous, 8-byte-padded reply buffer.
 // ------------------------------------------------------------------------------------------------

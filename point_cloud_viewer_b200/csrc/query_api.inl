@@ -450,15 +450,10 @@ int pcv_query_batch_device(const pcv_octree* oc, const pcv_location* locs, uint3
     API_CATCH
 }
 
-int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
-                  uint32_t* zbits_out, int* any_out) {
-    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
-    API_TRY
-    pcv_octree* o = const_cast<pcv_octree*>(oc);
-    pcv_ctx* c = o->ctx;
-    std::lock_guard<std::mutex> g(c->mu);
-    CU(cudaSetDevice(c->device));
-    ensure_tables(o);
+// Shared by the X-ray entry points: the tile's location (Aabb, or Obb when a query_from_global transform is given), the nodes
+// it intersects, their point tiles, and the kernel arguments that do not depend on the colouring strategy.
+static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, Scratch& s,
+                         XrayArgs& a, size_t& ntiles) {
     // location: Aabb(bbox), or Obb::from(bbox).transformed(query_from_global.inverse())  (xray generation.rs:471-477)
     pcv_location loc{};
     double bmin[3], bmax[3];
@@ -505,14 +500,12 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
             loc.aabb_max[a] = bmax[a];
         }
     }
-    Scratch s(c);
     std::vector<QueryGeom> geoms{make_query_geom(loc)};
     std::vector<uint8_t> pass = run_sat(o, geoms, s, nullptr);
     std::vector<QTile> tiles;
     for (size_t i = 0; i < pass.size(); ++i)
         if (pass[i] && o->nodes[i].num_points > 0) make_tiles(o, 0, (uint32_t)i, tiles);
-    const size_t npix = (size_t)w * h;
-    XrayArgs a{};
+    a = XrayArgs{};
     a.geom = geoms[0];
     a.nodes = (const QNode*)o->d_qnodes;
     a.tiles = s.upload(tiles.data(), tiles.size());
@@ -525,6 +518,24 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     if (qfg) memcpy(a.query_from_global, qfg, sizeof(double) * 7);
     a.w = w;
     a.h = h;
+    ntiles = tiles.size();
+    (void)c;
+}
+
+int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
+                  uint32_t* zbits_out, int* any_out) {
+    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    Scratch s(c);
+    XrayArgs a{};
+    size_t ntiles = 0;
+    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, a, ntiles);
+    const size_t npix = (size_t)w * h;
     a.zbits = s.alloc<uint32_t>(npix * 32);
     a.zover = s.alloc<uint8_t>(npix);
     a.any = s.alloc<int>(1);
@@ -540,8 +551,8 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     }
     const uint8_t* dgrey = s.upload(grey, 1026);
     uint8_t* drgba = s.alloc<uint8_t>(npix * 4);
-    if (!tiles.empty()) {
-        k_xray_accum<<<(uint32_t)tiles.size(), 256, 0, c->stream>>>(a);
+    if (ntiles) {
+        k_xray_accum<<<(uint32_t)ntiles, 256, 0, c->stream>>>(a);
         c->be->launches++;
     }
     k_xray_resolve<<<(uint32_t)((npix + 255) / 256), 256, 0, c->stream>>>(a.zbits, a.zover, dgrey, (uint32_t)npix, drgba);
@@ -557,6 +568,60 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
 }
 
 }  // extern "C"
+
+// The other ColoringStrategyKinds of xray_from_points (xray/src/generation.rs:76-97, 200-405) with Binning = None.
+int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, int mode, float p0,
+                       float p1, int colormap, uint8_t* rgba_out, int* any_out) {
+    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
+    if (mode < PCV_XRAY_COLORED || mode > PCV_XRAY_HEIGHT_STDDEV) return fail(PCV_ERR_INVALID, "unknown colouring strategy %d", mode);
+    if (mode == PCV_XRAY_INTENSITY && !oc->d_intensity)
+        return fail(PCV_ERR_INVALID, "Coloring by intensity was requested, but point data without intensity found.");
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    Scratch s(c);
+    XrayAttrArgs b{};
+    size_t ntiles = 0;
+    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, b.x, ntiles);
+    const size_t npix = (size_t)w * h;
+    b.x.any = s.alloc<int>(1);
+    b.rgb = o->d_rgb;
+    b.intensity = o->d_intensity;
+    b.count = s.alloc<uint32_t>(npix);
+    b.z0 = (std::fmin(tmin[2], tmax[2]) + std::fmax(tmin[2], tmax[2])) * 0.5;
+    CU(cudaMemsetAsync(b.x.any, 0, 4, c->stream));
+    CU(cudaMemsetAsync(b.count, 0, npix * 4, c->stream));
+    if (mode == PCV_XRAY_HEIGHT_STDDEV) {
+        b.dsum = s.alloc<double>(npix * 2);
+        CU(cudaMemsetAsync(b.dsum, 0, npix * 16, c->stream));
+    } else {
+        const size_t per = mode == PCV_XRAY_COLORED ? 4 : 1;
+        b.sum = s.alloc<float>(npix * per);
+        CU(cudaMemsetAsync(b.sum, 0, npix * per * 4, c->stream));
+    }
+    uint8_t* drgba = s.alloc<uint8_t>(npix * 4);
+    if (ntiles) {
+        if (mode == PCV_XRAY_COLORED)
+            k_xray_accum_attr<1><<<(uint32_t)ntiles, 256, 0, c->stream>>>(b);
+        else if (mode == PCV_XRAY_INTENSITY)
+            k_xray_accum_attr<2><<<(uint32_t)ntiles, 256, 0, c->stream>>>(b);
+        else
+            k_xray_accum_attr<3><<<(uint32_t)ntiles, 256, 0, c->stream>>>(b);
+        c->be->launches++;
+    }
+    k_xray_resolve_attr<<<(uint32_t)((npix + 255) / 256), 256, 0, c->stream>>>(mode, p0, p1, colormap, b.sum, b.dsum, b.count, (uint32_t)npix, drgba);
+    c->be->launches++;
+    CU(cudaGetLastError());
+    int any = 0;
+    c->be->d2h(&any, b.x.any, 4);
+    c->be->d2h(rgba_out, drgba, npix * 4);
+    if (any_out) *any_out = any;
+    return PCV_OK;
+    API_CATCH
+}
 
 // ---- /nodes_data reply blob (octree_web_viewer/src/backend.rs:66-75 pad, :92-165 get_nodes_data) ----------------
 // Per requested node, in request order: cube min x, y, z (f64 LE), edge length (f64), num_points (u32), bytes per

@@ -36,7 +36,15 @@ int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolut
         unsigned long long* d = (unsigned long long*)c->be->dmalloc((size_t)a.nbins * 8);
         CU(cudaMemsetAsync(d, 0, (size_t)a.nbins * 8, c->stream));
         const int blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, (a.pts.n + 255) / 256);
-        k_prefix_hist<<<blocks, 256, (size_t)a.nbins * 4, c->stream>>>(a, d);
+        // keep the per-point cells for the pack that follows (freed by the next histogram call or with the context)
+        c->be->dfree(c->shard_cells);
+        c->shard_cells = (uint16_t*)c->be->dmalloc(a.pts.n * 2);
+        c->shard_cells_x = a.pts.x;
+        c->shard_cells_n = a.pts.n;
+        c->shard_cells_k = k;
+        c->shard_cells_geom[0] = resolution;
+        for (int i = 0; i < 3; ++i) c->shard_cells_geom[1 + i] = bmin[i], c->shard_cells_geom[4 + i] = bmax[i];
+        k_prefix_hist<<<blocks, 256, (size_t)a.nbins * 4, c->stream>>>(a, d, c->shard_cells);
         c->be->launches++;
         CU(cudaGetLastError());
         c->be->d2h(h.data(), d, (size_t)a.nbins * 8);
@@ -45,6 +53,17 @@ int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolut
     for (int i = 0; i < a.nbins; ++i) counts_out[i] = h[(size_t)i];
     return PCV_OK;
     API_CATCH
+}
+
+static void attach_cells(pcv_ctx* c, PackArgs& a, double resolution, const double bmin[3], const double bmax[3], uint32_t k) {
+    a.cells = nullptr;
+    a.cell_shift = 0;
+    if (!c->shard_cells || c->shard_cells_x != a.p.pts.x || c->shard_cells_n != a.p.pts.n || c->shard_cells_k < k) return;
+    if (c->shard_cells_geom[0] != resolution) return;
+    for (int i = 0; i < 3; ++i)
+        if (c->shard_cells_geom[1 + i] != bmin[i] || c->shard_cells_geom[4 + i] != bmax[i]) return;
+    a.cells = c->shard_cells;
+    a.cell_shift = 3 * (c->shard_cells_k - k);
 }
 
 int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgidx, uint64_t gidx_base, double resolution, const double bmin[3],
@@ -77,6 +96,7 @@ int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgi
     a.out_rgb = out_rgb;
     a.out_intensity = a.p.pts.intensity ? out_intensity : nullptr;
     a.out_idx = out_idx;
+    attach_cells(c, a, resolution, bmin, bmax, k);
     k_pack_count<<<a.ntiles, 256, 0, c->stream>>>(a);
     unsigned long long* dtot = s.alloc<unsigned long long>(1);
     // per-rank totals before the scan overwrites the counts: read back the flat array's rank boundaries afterwards
@@ -183,6 +203,7 @@ int pcv_prefix_pack_exchange_device(pcv_ctx* c, const pcv_points* dp, const uint
         pt.first[r] = dst_first[r];
     }
     const PeerTable* d_pt = s.upload(&pt, 1);
+    attach_cells(c, a, resolution, bmin, bmax, k);
     k_pack_count<<<a.ntiles, 256, 0, c->stream>>>(a);
     unsigned long long* dtot = s.alloc<unsigned long long>(1);
     k_scan_u32<<<1, 1024, 0, c->stream>>>(a.counts, nranks * a.ntiles, dtot);

@@ -88,6 +88,7 @@ def lib():
         L.orc_visible_nodes.argtypes = [C.c_void_p, dp, C.c_void_p, C.c_int64]
         L.orc_query.restype = C.c_int64
         L.orc_query.argtypes = [C.c_void_p, LP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_xray_tile_attr.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
         L.orc_xray_tile.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_write_dir.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_load_dir.restype = C.c_void_p
@@ -189,6 +190,12 @@ class OracleOctree:
         src = np.zeros(n, np.uint64)
         lib().orc_query(self.h, C.byref(loc), _ptr(f) if nf else None, nf, _ptr(xyz), _ptr(rgb), _ptr(inten), _ptr(src), n, C.byref(tested))
         return dict(xyz=xyz, rgb=rgb, intensity=inten, src=src, tested=tested.value)
+
+    def xray_tile_attr(self, bmin, bmax, w, h, mode, p0=0.0, p1=0.0, colormap=0, query_from_global=None):
+        rgba = np.zeros((h, w, 4), np.uint8)
+        q = _d(query_from_global) if query_from_global is not None else None
+        any_ = lib().orc_xray_tile_attr(self.h, _d(bmin), _d(bmax), w, h, q, mode, p0, p1, colormap, _ptr(rgba))
+        return bool(any_), rgba
 
     def xray_tile(self, bmin, bmax, w, h, query_from_global=None):
         rgba = np.zeros((h, w, 4), np.uint8)

@@ -186,6 +186,37 @@ def test_xray_tiles(scene):
     assert not any_g and not rgba.any()
 
 
+def test_xray_other_colouring_strategies(scene):
+    """xray/src/generation.rs:200-405 with Binning = None: point colour mean, intensity mean, height stddev through Jet /
+    Purplish.  The reference accumulates in (unspecified) arrival order in f32 / Welford-f64, so agreement is defined up to
+    rounding: the set of covered pixels must be identical and every channel within one grey level of the oracle."""
+    pcv = scene["pcv"]
+    tree, ref = scene["tree"], scene["ref"]
+    bmin, bmax = scene["bmin"], scene["bmax"]
+    d = bmax - bmin
+    tmin, tmax = bmin + [0.2, 0.2, 0.0] * d, bmin + [0.7, 0.7, 1.0] * d
+    G = pcv.geometry
+    q = G.quat_mul(G.quat_from_axis_angle([0, 0, 1], 0.7), G.quat_from_axis_angle([0, 1, 0], -0.9))
+    qfg = G.Isometry((4157222.543, 664789.307, 4774952.099), q).inverse().as7()
+    qmin, qmax = np.array([-40.0, -30.0, -10.0]), np.array([24.0, 34.0, 10.0])
+    cases = [(pcv.XRAY_COLORED, 0.0, 0.0, 0), (pcv.XRAY_HEIGHT_STDDEV, 0.8, 0.0, 0), (pcv.XRAY_HEIGHT_STDDEV, 2.5, 0.0, 1)]
+    if tree.has_intensity:
+        cases.append((pcv.XRAY_INTENSITY, 0.0, 1000.0, 0))
+        cases.append((pcv.XRAY_INTENSITY, 100.0, 800.0, 0))
+    for mode, p0, p1, cm in cases:
+        for (lo, hi, w, h, frame) in ((tmin, tmax, 96, 64, None), (qmin, qmax, 128, 128, qfg)):
+            any_g, got = tree.xray_tile_attr(lo, hi, w, h, mode, p0, p1, cm, query_from_global=frame)
+            any_o, want = ref.xray_tile_attr(lo, hi, w, h, mode, p0, p1, cm, query_from_global=frame)
+            assert any_g and any_o
+            assert np.array_equal(got[..., 3], want[..., 3]), (mode, "covered pixels")
+            diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            assert diff.max() <= 1, (mode, p0, p1, cm, int(diff.max()), int((diff > 0).sum()))
+            assert (diff > 0).mean() < 0.02
+            assert (got[..., 3] == 255).sum() > 200 and got[..., :3].std() > 0
+    any_g, rgba = tree.xray_tile_attr(bmax + 10, bmax + 20, 8, 8, pcv.XRAY_COLORED)
+    assert not any_g and not rgba.any()
+
+
 def test_on_disk_round_trip(scene, tmp_path):
     """a8-a10: <dir>/<id>.xyz|.rgb|.intensity + meta.pb; the oracle's reader loads what the product wrote and vice versa."""
     tree, ref = scene["tree"], scene["ref"]
