@@ -147,6 +147,14 @@ class Context:
         N.check(N.lib().pcv_prefix_histogram_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(counts)))
         return counts
 
+    def prefix_histogram_bbox_device(self, x, y, z, n, resolution, bbox_min, bbox_max, k, stride=1):
+        """Level-k cell histogram of the local points + their bounding box, one pass over the positions."""
+        pts = N.Points(_p(x), _p(y), _p(z), stride, None, None, int(n))
+        counts = np.zeros(8 ** k, np.uint64)
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        N.check(N.lib().pcv_prefix_histogram_bbox_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(counts), mn, mx))
+        return counts, np.array(mn), np.array(mx)
+
     def prefix_pack_device(self, x, y, z, rgb, intensity, gidx, gidx_base, n, resolution, bbox_min, bbox_max, k, cell_to_rank, nranks, out_xyz,
                            out_rgb, out_intensity, out_idx, stride=1):
         pts = N.Points(_p(x), _p(y), _p(z), stride, _p(rgb), _p(intensity), int(n))

@@ -16,33 +16,72 @@ struct PrefixArgs {
     int nbins;  // 8^k
 };
 
-__device__ __forceinline__ unsigned prefix_cell(const PrefixArgs& a, uint64_t i) {
-    double q[3] = {__ldg(a.pts.x + i * a.pts.stride), __ldg(a.pts.y + i * a.pts.stride), __ldg(a.pts.z + i * a.pts.stride)};
+__device__ __forceinline__ unsigned prefix_cell_of(const PrefixArgs& a, const double p[3]) {
+    double q[3] = {p[0], p[1], p[2]};
     double m[3] = {a.root_min[0], a.root_min[1], a.root_min[2]};
+    if (a.lv.fast) {  // the kernels' straight-line descent (chain_device.cuh); a flagged numerator falls through to the generic path
+        double e = a.lv.edge[0];
+        unsigned cell = 0, bad = 0;
+        for (int j = 1; j <= a.k; ++j) {
+            const double eh = a.lv.edge[j], ry = a.lv.ry[j];
+            uint64_t code[3];
+            PCV_ENC_SWITCH(a.lv.enc[j], cell = (cell << 3) | level_step<ENC, 1, true>(q, m, e, eh, ry, code, bad);)
+            e = eh;
+        }
+        if (!bad) return cell;
+        q[0] = p[0], q[1] = p[1], q[2] = p[2];
+        m[0] = a.root_min[0], m[1] = a.root_min[1], m[2] = a.root_min[2];
+    }
     double e = a.lv.edge[0];
     unsigned cell = 0;
     for (int j = 1; j <= a.k; ++j) {
-        Step s = descend_any(a.lv, j, q, m, e);
+        Step s = descend(q, m, e, a.lv.edge[j], a.lv.enc[j]);
         cell = (cell << 3) | s.digit;
         e = a.lv.edge[j];
     }
     return cell;
 }
 
+__device__ __forceinline__ unsigned prefix_cell(const PrefixArgs& a, uint64_t i) {
+    double q[3] = {__ldg(a.pts.x + i * a.pts.stride), __ldg(a.pts.y + i * a.pts.stride), __ldg(a.pts.z + i * a.pts.stride)};
+    return prefix_cell_of(a, q);
+}
+
 // `cells` (optional): the cell of every point, kept for the pack that follows so that it does not repeat the descent.
-__global__ void __launch_bounds__(256) k_prefix_hist(const __grid_constant__ PrefixArgs a, unsigned long long* __restrict__ counts, uint16_t* __restrict__ cells) {
+// `bbox_partial` (optional, [gridDim.x][6]): min / max of the block's points - find_bounding_box folded into the same read.
+__global__ void __launch_bounds__(256) k_prefix_hist(const __grid_constant__ PrefixArgs a, unsigned long long* __restrict__ counts, uint16_t* __restrict__ cells,
+                                                     double* __restrict__ bbox_partial) {
     extern __shared__ uint32_t sh_cnt[];
     for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) sh_cnt[b] = 0;
     __syncthreads();
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.pts.n; i += step) {
-        const unsigned cell = prefix_cell(a, i);
+        const double p[3] = {__ldg(a.pts.x + i * a.pts.stride), __ldg(a.pts.y + i * a.pts.stride), __ldg(a.pts.z + i * a.pts.stride)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mn[k] = fmin(mn[k], p[k]), mx[k] = fmax(mx[k], p[k]);
+        const unsigned cell = prefix_cell_of(a, p);
         if (cells) cells[i] = (uint16_t)cell;
         atomicAdd(&sh_cnt[cell], 1u);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < a.nbins; b += blockDim.x)
         if (sh_cnt[b]) atomicAdd(&counts[b], (unsigned long long)sh_cnt[b]);
+    if (bbox_partial) {
+        __shared__ double sh[8][6];
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double lo = warp_min(mn[k]), hi = warp_max(mx[k]);
+            if (l == 0) sh[w][k] = lo, sh[w][3 + k] = hi;
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            double v = sh[0][threadIdx.x];
+            for (int k = 1; k < 8; ++k) v = threadIdx.x < 3 ? fmin(v, sh[k][threadIdx.x]) : fmax(v, sh[k][threadIdx.x]);
+            bbox_partial[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+        }
+    }
 }
 
 // ---- pack -------------------------------------------------------------------------------------------------------

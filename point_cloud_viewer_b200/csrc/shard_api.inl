@@ -24,18 +24,19 @@ PrefixArgs make_prefix_args(const pcv_points* dp, double resolution, const doubl
 
 extern "C" {
 
-int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
-                                uint64_t* counts_out) {
-    if (!c || !dp || !bmin || !bmax || !counts_out) return fail(PCV_ERR_INVALID, "null argument");
-    API_TRY
+static int prefix_histogram_impl(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
+                                 uint64_t* counts_out, double* data_min, double* data_max) {
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     PrefixArgs a = make_prefix_args(dp, resolution, bmin, bmax, k);
     std::vector<unsigned long long> h((size_t)a.nbins, 0);
+    if (data_min)
+        for (int i = 0; i < 3; ++i) data_min[i] = data_max[i] = 0.0;  // Aabb::zero for no points (generation.rs:269)
     if (a.pts.n) {
         unsigned long long* d = (unsigned long long*)c->be->dmalloc((size_t)a.nbins * 8);
         CU(cudaMemsetAsync(d, 0, (size_t)a.nbins * 8, c->stream));
         const int blocks = (int)std::min<uint64_t>((uint64_t)c->sm_count * 8, (a.pts.n + 255) / 256);
+        double* d_part = data_min ? (double*)c->be->dmalloc((size_t)blocks * 6 * 8) : nullptr;
         // keep the per-point cells for the pack that follows (freed by the next histogram call or with the context)
         c->be->dfree(c->shard_cells);
         c->shard_cells = (uint16_t*)c->be->dmalloc(a.pts.n * 2);
@@ -44,14 +45,40 @@ int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolut
         c->shard_cells_k = k;
         c->shard_cells_geom[0] = resolution;
         for (int i = 0; i < 3; ++i) c->shard_cells_geom[1 + i] = bmin[i], c->shard_cells_geom[4 + i] = bmax[i];
-        k_prefix_hist<<<blocks, 256, (size_t)a.nbins * 4, c->stream>>>(a, d, c->shard_cells);
+        k_prefix_hist<<<blocks, 256, (size_t)a.nbins * 4, c->stream>>>(a, d, c->shard_cells, d_part);
         c->be->launches++;
         CU(cudaGetLastError());
         c->be->d2h(h.data(), d, (size_t)a.nbins * 8);
         c->be->dfree(d);
+        if (d_part) {
+            std::vector<double> part((size_t)blocks * 6);
+            c->be->d2h(part.data(), d_part, part.size() * 8);
+            c->be->dfree(d_part);
+            for (int i = 0; i < 3; ++i) data_min[i] = part[i], data_max[i] = part[3 + i];
+            for (int b = 1; b < blocks; ++b)
+                for (int i = 0; i < 3; ++i) {
+                    data_min[i] = std::fmin(data_min[i], part[(size_t)b * 6 + i]);
+                    data_max[i] = std::fmax(data_max[i], part[(size_t)b * 6 + 3 + i]);
+                }
+        }
     }
     for (int i = 0; i < a.nbins; ++i) counts_out[i] = h[(size_t)i];
     return PCV_OK;
+}
+
+int pcv_prefix_histogram_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
+                                uint64_t* counts_out) {
+    if (!c || !dp || !bmin || !bmax || !counts_out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    return prefix_histogram_impl(c, dp, resolution, bmin, bmax, k, counts_out, nullptr, nullptr);
+    API_CATCH
+}
+
+int pcv_prefix_histogram_bbox_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin[3], const double bmax[3], uint32_t k,
+                                     uint64_t* counts_out, double data_min[3], double data_max[3]) {
+    if (!c || !dp || !bmin || !bmax || !counts_out || !data_min || !data_max) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    return prefix_histogram_impl(c, dp, resolution, bmin, bmax, k, counts_out, data_min, data_max);
     API_CATCH
 }
 

@@ -158,6 +158,10 @@ class CudaOps:
     def prefix_histogram(self, k):
         return self.ctx.prefix_histogram_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.n, self.res, self.bmin, self.bmax, k)
 
+    def prefix_histogram_bbox(self, k):
+        """(histogram, data min, data max): the bounding box rides on the histogram's read of the positions."""
+        return self.ctx.prefix_histogram_bbox_device(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.n, self.res, self.bmin, self.bmax, k)
+
     def pack(self, k, cell_to_rank, nranks, index_base):
         import torch
 
@@ -360,14 +364,18 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
 
     # (0) the bounding box is an argument of build_octree (generation.rs:292); the all-reduced box of the data is only
     # checked against it (find_bounding_box would be the producer in build_octree_from_file).
-    lmn, lmx = ops.local_bbox()
+    k = int(prefix_levels)
+    if hasattr(ops, "prefix_histogram_bbox"):  # one pass over the positions for both
+        local_hist, lmn, lmx = ops.prefix_histogram_bbox(k)
+    else:
+        lmn, lmx = ops.local_bbox()
+        local_hist = ops.prefix_histogram(k)
+    local_hist = np.asarray(local_hist, np.uint64)
     gmn, gmx = comm.all_reduce_minmax(lmn if ops.n else [np.inf] * 3, lmx if ops.n else [-np.inf] * 3)
     inside = bool((gmn >= lo).all() and (gmx <= hi).all())
 
-    mark("bbox")
+    mark("bbox + local histogram")
     # (1) global histogram of level-k cells
-    k = int(prefix_levels)
-    local_hist = np.asarray(ops.prefix_histogram(k), np.uint64)
     counts_k = comm.all_reduce_sum_u64(local_hist)
     k2 = usable_prefix_levels(counts_k, k, root_edge, res, max_points_per_node)
     if k2 < k:
