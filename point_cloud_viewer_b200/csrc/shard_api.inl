@@ -234,7 +234,11 @@ int pcv_prefix_pack_exchange_device(pcv_ctx* c, const pcv_points* dp, const uint
     k_pack_count<<<a.ntiles, 256, 0, c->stream>>>(a);
     unsigned long long* dtot = s.alloc<unsigned long long>(1);
     k_scan_u32<<<1, 1024, 0, c->stream>>>(a.counts, nranks * a.ntiles, dtot);
-    k_pack_exchange<<<a.ntiles, 256, 0, c->stream>>>(a, d_pt);
+    static const bool v1 = std::getenv("PCV_EXCHANGE_V1") != nullptr;  // diagnostic: the unsorted variant
+    if (v1)
+        k_pack_exchange<<<a.ntiles, 256, 0, c->stream>>>(a, d_pt);
+    else
+        k_pack_exchange_sorted<<<a.ntiles, 256, 0, c->stream>>>(a, d_pt);
     c->be->launches += 3;
     CU(cudaGetLastError());
     std::vector<uint32_t> starts(nranks);
