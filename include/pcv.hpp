@@ -175,6 +175,25 @@ class Octree {
             }
         throw Error(PCV_ERR_NOT_FOUND, "node " + id.to_string() + " not found");
     }
+    // The web viewer's /nodes_data reply for a list of nodes (octree_web_viewer/src/backend.rs:92-165), gathered on the GPU.
+    std::vector<uint8_t> nodes_data_blob(const std::vector<NodeId>& ids) const {
+        std::vector<uint64_t> hl;
+        for (auto& id : ids) hl.push_back(id.high), hl.push_back(id.low);
+        uint64_t size = 0;
+        check(pcv_nodes_data_blob(o_, hl.data(), (uint32_t)ids.size(), nullptr, 0, &size));
+        std::vector<uint8_t> blob(size);
+        if (size) check(pcv_nodes_data_blob(o_, hl.data(), (uint32_t)ids.size(), blob.data(), size, &size));
+        return blob;
+    }
+    // xray_from_points for one tile with ColoringStrategyKind::{Colored, ColoredWithIntensity, ColoredWithHeightStddev}
+    // (xray/src/generation.rs:76-97); returns false for a tile without points (None in the reference).
+    bool xray_tile_attr(const Aabb& tile, uint32_t w, uint32_t h, int strategy, float p0, float p1, int colormap, std::vector<uint8_t>& rgba,
+                        const double* query_from_global7 = nullptr) const {
+        rgba.assign((size_t)w * h * 4, 0);
+        int any = 0;
+        check(pcv_xray_tile_attr(o_, tile.min.data(), tile.max.data(), w, h, query_from_global7, strategy, p0, p1, colormap, rgba.data(), &any));
+        return any != 0;
+    }
     void write_to_directory(const std::string& dir) const { check(pcv_octree_write_dir(o_, dir.c_str())); }
     pcv_octree* raw() const { return o_; }
 
@@ -223,6 +242,19 @@ inline Octree build_octree(Context& ctx, const std::string& output_directory, do
     pts.n = pos.size();
     pcv_octree* o = nullptr;
     check(pcv_build_octree(ctx.raw(), &pts, resolution, bounding_box.min.data(), bounding_box.max.data(), &o));
+    Octree tree(o);
+    if (!output_directory.empty()) tree.write_to_directory(output_directory);
+    return tree;
+}
+
+// build_octree_from_file(output_directory, resolution, filename, attributes) — generation.rs:272-287: the PLY body goes to the
+// GPU as raw records, the bounding-box pass is fused into the unpack kernel.
+inline Octree build_octree_from_file(Context& ctx, const std::string& output_directory, double resolution, const std::string& filename,
+                                     const std::vector<std::string>& attributes = {"color"}) {
+    bool want_i = false;
+    for (auto& a : attributes) want_i = want_i || a == "intensity";
+    pcv_octree* o = nullptr;
+    check(pcv_build_octree_from_file(ctx.raw(), filename.c_str(), resolution, want_i ? 1 : 0, &o));
     Octree tree(o);
     if (!output_directory.empty()) tree.write_to_directory(output_directory);
     return tree;

@@ -2,6 +2,7 @@
 // include/pcv.hpp so that it reads like the original: build the 100 001-point octree, stream it through the
 // ParallelIterator with an erroring consumer and with a large batch.
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <string>
 
@@ -79,6 +80,49 @@ int main(int argc, char** argv) {
         pcv::NodeData d = octree.get_node_data(pcv::NodeId{0, 0});
         ASSERT_EQ(d.position.size(), 12501u * 3u);  // Uint8 encoding
         ASSERT_EQ(d.color.size(), 12501u * 3u);
+    }
+    {  // PLY input + /nodes_data blob + colour tile through the C++ mirror
+        const std::string ply = dir + "_in.ply";
+        const uint32_t n = 20000;
+        {
+            FILE* f = fopen(ply.c_str(), "wb");
+            if (!f) return 3;
+            fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment offset: 10 20 30\nelement vertex %u\nproperty float x\nproperty float y\n"
+                       "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", n);
+            for (uint32_t i = 0; i < n; ++i) {
+                const float xyz[3] = {(float)(i % 200) * 0.5f, (float)((i / 200) % 100) * 0.5f, (float)(i % 7)};
+                const uint8_t rgb[3] = {(uint8_t)(i % 251), 17, (uint8_t)(i % 3)};
+                fwrite(xyz, 4, 3, f);
+                fwrite(rgb, 1, 3, f);
+            }
+            fclose(f);
+        }
+        pcv::Octree t = pcv::build_octree_from_file(ctx, "", 0.01, ply);
+        ASSERT_EQ(t.num_points(), (int64_t)n);
+        std::vector<pcv::NodeId> ids;
+        size_t expect = 0;
+        for (auto& m : t.nodes())
+            if (m.num_points > 0) {
+                ids.push_back(pcv::NodeId{m.id_high, m.id_low});
+                const size_t bpc = m.position_encoding == 1 ? 1 : m.position_encoding == 2 ? 2 : m.position_encoding == 3 ? 4 : 8;
+                expect += 40 + (((size_t)m.num_points * 3 * bpc + 7) / 8) * 8 + (((size_t)m.num_points * 3 + 7) / 8) * 8;
+            }
+        const std::vector<uint8_t> blob = t.nodes_data_blob(ids);
+        ASSERT_EQ(blob.size(), expect);
+        uint32_t n0 = 0;
+        memcpy(&n0, blob.data() + 32, 4);
+        for (auto& m : t.nodes())
+            if (m.num_points > 0) {  // the blob starts with the header of the first requested node
+                ASSERT_EQ((int64_t)n0, m.num_points);
+                break;
+            }
+        std::vector<uint8_t> rgba;
+        const bool any = t.xray_tile_attr(pcv::Aabb({10, 20, 30}, {110, 70, 37}), 64, 32, PCV_XRAY_COLORED, 0.f, 0.f, 0, rgba);
+        ASSERT_EQ(any, true);
+        size_t covered = 0;
+        for (size_t px = 0; px < rgba.size() / 4; ++px) covered += rgba[px * 4 + 3] == 255;
+        if (covered < 100) return 4;
+        remove(ply.c_str());
     }
     printf("cpp octree tests OK\n");
     return 0;
