@@ -77,6 +77,16 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(n, world, args):
+    """The `config` object of the JSON line - shared by both arms so that the reference arm names the same workload."""
+    return {
+        "workload": "build_octree on %d synthetic Gaussian-cluster points per GPU (BASELINE config %d), resolution 1024/2^20 (depth 20), XYZ f64 SoA + RGB" % (n, 2 if world == 1 else 4),
+        "points_per_gpu": n, "levels_per_pass": args.levels_per_pass, "max_points_per_node": 100000,
+        "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (27.0 * n / 1e9),
+        "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix; one fused pack+exchange kernel stores every point into its owner's memory over NVLink (CUDA IPC peer mapping), NCCL only for the small all-reduces" % args.prefix_levels,
+    }
+
+
 def run_reference(args):
     """The reference's own algorithm on the host cores: the oracle (C++ restatement of build_octree, same task
     structure: serial root split, one task per split node, per-level parallel subsampling; in-memory variant, i.e.
@@ -109,7 +119,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "build_octree, Gaussian-cluster points (BASELINE config 2 generator), depth 20, CPU sample", "points_per_step": n},
+        "config": dict(workload_config(int(args.points) if args.gpus == 1 or args.points_multi <= 0 else int(args.points_multi), args.gpus, args),
+                       sample_points_per_step=n, note="the reference's CPU algorithm (oracle port) timed on a bounded sample of this workload"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -278,12 +289,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": "build_octree on %d synthetic Gaussian-cluster points per GPU (BASELINE config %d), resolution 1024/2^20 (depth 20), XYZ f64 SoA + RGB" % (n, 2 if world == 1 else 4),
-            "points_per_gpu": n, "levels_per_pass": args.levels_per_pass, "max_points_per_node": 100000,
-            "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (27.0 * n / 1e9),
-            "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix; one fused pack+exchange kernel stores every point into its owner's memory over NVLink (CUDA IPC peer mapping), NCCL only for the small all-reduces" % args.prefix_levels,
-        },
+        "config": workload_config(n, world, args),
         "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": int(launches), "octree_nodes": nodes, "deepest_level": int(stats["deepest_level"]),
         "clocks": clocks,
     }
@@ -423,7 +429,7 @@ def main():
     ap.add_argument("--frusta", type=int, default=1000)
     ap.add_argument("--cpu-points", type=float, default=2e7)
     ap.add_argument("--ply-points", type=float, default=1e8, help="points of the synthetic PLY file for the ingest measurement")
-    ap.add_argument("--ref-points", type=float, default=5e6)
+    ap.add_argument("--ref-points", type=float, default=2e7, help="points of the bounded sample each --impl reference step builds")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
