@@ -67,3 +67,19 @@ def test_synth_generators_host():
     P = np.stack([x, y, z], 1)
     assert res == 1024.0 / 2 ** 20 and (P >= mn).all() and (P <= mx).all()
     assert (P[10:150010] == P[10]).all() and not (P[:10] == P[10]).all()  # one block of 150 000 identical points
+
+
+def test_cpp_mirror_compiles_against_the_library():
+    """include/pcv.hpp (header-only C++ mirror of the crate's names) and its test program build and link against the
+    library; running them needs a GPU (tests/test_cpp_host_gpu.py)."""
+    import subprocess
+    import tempfile
+
+    from point_cloud_viewer_b200 import _native
+
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "test_octree")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "test_octree.cpp"), "-o", exe, "-L" + lib_dir,
+                               "-l:libpcv_b200.so", "-Wl,-rpath," + lib_dir])
+        assert os.path.exists(exe)
