@@ -40,7 +40,7 @@ def clouds(draw):
     return P, rgb, inten, res, maxpts, G, pad
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(clouds())
 def test_random_clouds_match_oracle(c):
     P, rgb, inten, res, maxpts, G, pad = c
