@@ -189,7 +189,9 @@ inline pcv_ply_info ply_parse(const char* path) {
 }
 
 inline void ply_validate(const pcv_ply_info& i) {
-    if (i.record_bytes == 0 || i.record_bytes > 4096) throw BuildError(PCV_ERR_INVALID, "PLY record size out of range");
+    // one 256-record tile must fit the unpack kernel's shared memory (256 * record_bytes + colour staging <= 200 KB)
+    if (i.record_bytes == 0) throw BuildError(PCV_ERR_INVALID, "PLY record size is zero");
+    if (i.record_bytes > 768) throw BuildError(PCV_ERR_UNSUPPORTED, "PLY vertex records larger than 768 bytes are not supported");
     for (int a = 0; a < 3; ++a) {
         const int t = i.type_xyz[a];
         if (t < 0 || t > PCV_PLY_F64 || t == PCV_PLY_I64 || t == PCV_PLY_U64) throw BuildError(PCV_ERR_INVALID, "bad coordinate type");
