@@ -1,4 +1,4 @@
-"""Multi-GPU build_octree: points shard by octree path prefix, one all-to-all.
+"""Multi-GPU build_octree: points shard by octree path prefix and move once to their owners.
 
 Every rank holds a contiguous slice of the global point index space.  The split phase of the reference is independent
 below any octree prefix and the subsample phase only couples a parent with its 8 children, so:
@@ -6,8 +6,10 @@ below any octree prefix and the subsample phase only couples a parent with its 8
   1. all-reduce the 8^k histogram of level-k prefix cells (first k steps of the re-quantising descent on the raw
      positions - the cell the single-GPU build would route the point to);
   2. greedily balance the non-empty cells over the ranks (largest first);
-  3. stable pack by destination rank, ONE all-to-all (xyz, rgb, intensity, global index); receivers concatenate in
-     source-rank order, which is global index order, i.e. the reference's stable stream order;
+  3. stable pack by destination rank and ONE exchange (xyz, rgb, intensity, global index); every receiver holds the
+     source ranks' blocks in rank order, which is global index order, i.e. the reference's stable stream order.  On
+     GPUs pack and exchange are one kernel that stores straight into the owners' memory over NVLink (CUDA-IPC peer
+     mapping, `CudaOps.pack_exchange`); the staged variant (send buffers + all_to_all_single) serves the CPU tests;
   4. every rank builds the sub-trees of its cells independently (global bounding cube; the nodes above level k take
      their split decision from the global counts);
   5. the <= 1 + 8 + 64 nodes above level k are assembled on rank 0 from the children's every-8th points (collected,
