@@ -83,6 +83,8 @@ int pcv_create(int device, const pcv_config* cfg, pcv_ctx** out) {
     uint64_t thr = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c->be = new CudaBackend(c->stream);
+    // per-device attribute (a second context on another GPU of the same process needs its own opt-in)
+    CU(cudaFuncSetAttribute(k_ply_unpack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = c;
     return PCV_OK;
     API_CATCH

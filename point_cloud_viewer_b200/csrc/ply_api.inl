@@ -26,11 +26,7 @@ static void ply_launch(pcv_ctx* c, PlyUnpackArgs a, const uint8_t* raw, uint64_t
     a.out_first = out_first;
     a.partial = partial;
     const size_t sm = ply_smem_bytes(a.record_bytes, a.tile_points);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(k_ply_unpack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // the dynamic shared memory opt-in of k_ply_unpack is per device: done in pcv_create for the context's GPU
     const uint32_t blocks = (uint32_t)((n + a.tile_points - 1) / a.tile_points);
     c->be->prof_begin(CudaBackend::K_PLY, n * ((uint64_t)a.record_bytes + 24 + (a.has_color && a.rgb ? 3 : 0) + (a.has_intensity && a.intensity ? 4 : 0)));
     k_ply_unpack<<<blocks, kPlyThreads, sm, c->stream>>>(a);

@@ -66,7 +66,11 @@ inline void ply_header_text(int fd, std::string& text) {
         // stop once a complete end_header line is inside the text
         size_t at = 0;
         while ((at = text.find("end_header", at)) != std::string::npos) {
-            const bool line_start = at == 0 || text[at - 1] == '\n' || text[at - 1] == ' ' || text[at - 1] == '\t' || text[at - 1] == '\r';
+            // only the first token of a line terminates the header (ply.rs:139-146 splits lines into tokens): a
+            // "comment ... end_header" line does not
+            size_t b = at;
+            while (b > 0 && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) --b;
+            const bool line_start = b == 0 || text[b - 1] == '\n';
             const size_t nl = text.find('\n', at);
             if (line_start && nl != std::string::npos) return;
             at += 10;

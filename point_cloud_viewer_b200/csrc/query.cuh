@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(1024) k_propagate(const QNode* __restrict__ no
 __device__ __forceinline__ double num_clamp_d(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __global__ void __launch_bounds__(256) k_visible_eval(const QueryGeom* __restrict__ geom, const double* __restrict__ M,
                                                       const QNode* __restrict__ nodes, uint32_t nnodes, uint8_t* __restrict__ rel,
-                                                      double* __restrict__ size, int* __restrict__ bad) {
+                                                      double* __restrict__ size) {
     __shared__ double aproj[26][2];
     const QueryGeom& g = geom[0];
     project_location(g, aproj);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) k_visible_eval(const QueryGeom* __restric
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
     const QNode nd = nodes[i];
-    rel[i] = sat_cube(g, aproj, nd.m, nd.e);
+    uint8_t relv = sat_cube(g, aproj, nd.m, nd.e);
     const double mn[3] = {nd.m[0], nd.m[1], nd.m[2]}, mx[3] = {nd.m[0] + nd.e, nd.m[1] + nd.e, nd.m[2] + nd.e};
     double lo[2] = {0, 0}, hi[2] = {0, 0};
     // corner order of mod.rs:122-137: min, max, then 6 mixed corners (order is irrelevant for min/max)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_visible_eval(const QueryGeom* __restric
             a = M[12 + r] * 1.0 + a;
             q[r] = a;
         }
-        if (q[3] == 0.0) atomicExch(bad, 1);
+        if (q[3] == 0.0) relv |= 0x80;  // Point3::from_homogeneous(..).unwrap() panics for this node (mod.rs:103-106) - if it is ever pushed
         const double x = num_clamp_d(q[0] / q[3], -1., 1.), y = num_clamp_d(q[1] / q[3], -1., 1.);
         if (c == 0) {
             lo[0] = hi[0] = x;
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) k_visible_eval(const QueryGeom* __restric
         }
     }
     size[i] = (hi[0] - lo[0]) * (hi[1] - lo[1]);
+    rel[i] = relv;
 }
 
 // ---- per-point culling -----------------------------------------------------------------------------

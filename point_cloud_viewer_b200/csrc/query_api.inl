@@ -294,34 +294,38 @@ int pcv_visible_nodes(const pcv_octree* oc, const double M[16], uint64_t* ids, u
     const double* dM = s.upload(M, 16);
     uint8_t* drel = s.alloc<uint8_t>(nn);
     double* dsize = s.alloc<double>(nn);
-    int zero = 0;
-    int* dbad = s.upload(&zero, 1);
-    k_visible_eval<<<(nn + 255) / 256, 256, 0, c->stream>>>(dg, dM, (const QNode*)o->d_qnodes, nn, drel, dsize, dbad);
+    k_visible_eval<<<(nn + 255) / 256, 256, 0, c->stream>>>(dg, dM, (const QNode*)o->d_qnodes, nn, drel, dsize);
     c->be->launches++;
     CU(cudaGetLastError());
     std::vector<uint8_t> rel(nn);
     std::vector<double> size(nn);
-    int bad = 0;
     c->be->d2h(rel.data(), drel, nn);
     c->be->d2h(size.data(), dsize, (size_t)nn * 8);
-    c->be->d2h(&bad, dbad, 4);
-    // best-first traversal (octree/mod.rs:232-283); only nodes actually pushed are ever evaluated by the reference,
-    // so a w == 0 projection only matters for those - checked lazily below through NaN/inf sizes is not possible,
-    // hence the conservative global flag.
-    if (bad) return fail(PCV_ERR_INVALID, "projection of a node corner has w == 0 (the reference panics here)");
+    // best-first traversal (octree/mod.rs:232-283).  The reference projects a node's corners when it pushes the node
+    // (maybe_push_node -> relative_size_on_screen), so a corner with w == 0 (bit 7 of rel) is an error only for nodes that
+    // are actually pushed - children of Out nodes are never looked at.
+    const uint8_t kBadW = 0x80;
+    auto bad_w = [&](int node) { return fail(PCV_ERR_INVALID, "projection of a corner of node %s has w == 0 (the reference panics here)",
+                                             node_name(o->nodes[node].id_high, o->nodes[node].id_low).c_str()); };
     OpenHeap open;
     const int root = o->find(0, 0);
-    if (root >= 0) open.push(Open{root, REL_CROSS, size[root]});
+    if (root >= 0) {
+        if (rel[root] & kBadW) return bad_w(root);
+        open.push(Open{root, REL_CROSS, size[root]});
+    }
     uint64_t n = 0;
     Open cur;
     while (open.pop(cur)) {
         for (int k = 0; k < 8; ++k) {
             const int ch = o->children_of[(size_t)cur.node * 8 + k];
             if (ch < 0) continue;  // maybe_push_node: only ids present in the meta
+            const uint8_t r = rel[ch] & 0x7f;
             if (cur.rel == REL_CROSS) {
-                if (rel[ch] == REL_OUT) continue;
-                open.push(Open{ch, rel[ch], size[ch]});
+                if (r == REL_OUT) continue;
+                if (rel[ch] & kBadW) return bad_w(ch);
+                open.push(Open{ch, r, size[ch]});
             } else {
+                if (rel[ch] & kBadW) return bad_w(ch);
                 open.push(Open{ch, REL_IN, size[ch]});
             }
         }

@@ -8,6 +8,7 @@
 
 #include "../../include/pcv.h"
 #include "../../point_cloud_viewer_b200/csrc/build_host.hpp"
+#include "../../point_cloud_viewer_b200/csrc/disk_io.hpp"
 
 using namespace pcv;
 
@@ -406,5 +407,42 @@ void tb_nsub(void* h, uint64_t* out) {
     TbTree* t = (TbTree*)h;
     size_t k = 0;
     for (int i : t->R.sorted) out[k++] = t->R.nodes[i].n_sub;
+}
+}
+
+// ---- the product's meta.pb writer / reader (csrc/disk_io.hpp), host code: pinned against python-protobuf on the CPU ----
+extern "C" {
+// nodes: n x (high, low, num_points, enc).  Returns the byte count (or -needed if cap is too small).
+int64_t tb_encode_meta(double resolution, const double* bmin, const double* bmax, const uint64_t* nodes4, uint64_t n, uint8_t* out, uint64_t cap) {
+    MetaHeader h;
+    h.resolution = resolution;
+    for (int a = 0; a < 3; ++a) h.bbox_min[a] = bmin[a], h.bbox_max[a] = bmax[a];
+    std::vector<pcv_node_meta> v(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        v[i] = pcv_node_meta{};
+        v[i].id_high = nodes4[4 * i];
+        v[i].id_low = nodes4[4 * i + 1];
+        v[i].num_points = (int64_t)nodes4[4 * i + 2];
+        v[i].position_encoding = (int32_t)nodes4[4 * i + 3];
+    }
+    const std::string s = encode_meta(h, v);
+    if (s.size() > cap) return -(int64_t)s.size();
+    std::memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+}
+// Returns the node count (or -1 if rejected); nodes4 receives up to cap entries.
+int64_t tb_decode_meta(const uint8_t* buf, uint64_t len, double* resolution, double* bmin, double* bmax, int* version, uint64_t* nodes4, uint64_t cap) {
+    MetaHeader h;
+    std::vector<ParsedNode> pn;
+    int ver = 0;
+    const bool ok = decode_meta(std::string((const char*)buf, len), h, pn, ver);
+    *version = ver;
+    if (!ok) return -1;
+    *resolution = h.resolution;
+    for (int a = 0; a < 3; ++a) bmin[a] = h.bbox_min[a], bmax[a] = h.bbox_max[a];
+    for (uint64_t i = 0; i < pn.size() && i < cap; ++i) {
+        nodes4[4 * i] = pn[i].hi, nodes4[4 * i + 1] = pn[i].lo, nodes4[4 * i + 2] = (uint64_t)pn[i].num_points, nodes4[4 * i + 3] = (uint64_t)pn[i].enc;
+    }
+    return (int64_t)pn.size();
 }
 }
