@@ -294,7 +294,7 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    if world == 1:
+    if world == 1 and not args.no_extras:
         peak, peak_src = _peaks()
         # ---- roofline of the dominant kernel: one extra build with CUDA events around every launch ----
         ctx.set_profiling(True)
@@ -406,7 +406,7 @@ def run_ours(args):
         except Exception as e:
             out["ply_ingest"] = {"error": str(e)[:200]}
     else:
-        out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "e2e is measured at N=1"}
+        out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "e2e is measured at N=1 (without --no-extras)"}
         if last is not None:
             last.free()
 
@@ -430,6 +430,7 @@ def main():
     ap.add_argument("--cpu-points", type=float, default=2e7)
     ap.add_argument("--ply-points", type=float, default=1e8, help="points of the synthetic PLY file for the ingest measurement")
     ap.add_argument("--ref-points", type=float, default=2e7, help="points of the bounded sample each --impl reference step builds")
+    ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the timed build steps (no roofline / query / e2e / CPU legs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

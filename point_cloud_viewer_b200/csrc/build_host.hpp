@@ -4,12 +4,14 @@
 // same tree, the same per-node point order and the same stored position codes:
 //
 //   split phase    the reference's recursive 8-way file split (generation.rs:58-193) becomes a
-//                  top-down, level-synchronous stable multi-way partition: each pass resolves G octree
+//                  top-down, level-synchronous stable multi-way partition: each pass resolves two octree
 //                  levels for every point that still sits in a node with > MAX_POINTS_PER_NODE points
-//                  (`hist` -> per-tile digit histograms, `scan` -> per-digit prefix over tiles, host
-//                  decides leaf/split for the 8^1..8^G descendants, `scatter` -> stable partition
-//                  into the next pass's segments or into the leaf arena).  The per-point digits come
-//                  from the re-quantising descent in chain.h, so node membership is bit-identical.
+//                  (digit histogram per tile -> per-digit prefix over tiles -> a planner kernel decides
+//                  leaf/split for the 8 + 64 descendants -> stable partition into the next pass's
+//                  segments or into the leaf arena, all enqueued without a host round trip).  The
+//                  per-point digits come from the re-quantising descent in chain.h, computed one pass
+//                  ahead and carried with the record, so node membership is bit-identical and every
+//                  level of the chain is encoded exactly once.
 //   subsample      the level-by-level rewrite (generation.rs:195-253,335-387) is replaced by its closed
 //                  form: a point at rank j of a node X with parent P moves up iff j % 8 == 0, to rank
 //                  off(X in P) + j/8; otherwise it stays at slot j - j/8 - 1.  `place` walks each leaf
@@ -58,17 +60,17 @@ struct RecW {  // wide record: used for the whole build when any level >= 1 is F
     uint32_t pad;
 };
 struct TileDesc {
-    uint64_t start;   // first record (or raw point) of the tile
+    uint64_t start;   // first record of the tile
     uint32_t count;   // <= kTilePoints
     uint32_t active;  // index into the pass's active-node array
 };
 struct ActiveDesc {
     double m[3];
     double e;
-    uint64_t start, count;  // the node's segment in the pass's input (records, or raw points for the root)
+    uint64_t start, count;  // the node's segment in the pass's input records
     uint32_t chunk_begin, nchunks;
     uint32_t tile_begin;    // first tile of the node (tiles never straddle nodes)
-    uint32_t pad0;
+    uint32_t node;          // index into the node table
 };
 struct ChunkDesc {
     uint32_t tile_begin, ntiles;
@@ -77,10 +79,19 @@ struct ChunkDesc {
 };
 struct BucketDesc {
     uint64_t dest;    // first record of the bucket in its destination buffer
-    uint16_t b0, b1;  // digit range [b0,b1) it collects (contiguous: a whole sub-tree)
+    uint16_t b0, b1;  // digit range [b0,b1) it collects (contiguous: a whole sub-tree); b1 == 0: unused entry
     uint8_t keep;     // 1..G: which level's codes the destination stores
     uint8_t kind;     // 0 = next pass segment, 1 = leaf arena
     uint16_t pad;
+};
+// Node table entry, appended on the device by the planner (parents before children).
+struct DevNode {
+    uint64_t index_hi, index_lo;  // octal path index (u128, node.rs:120-125)
+    double m[3];
+    uint64_t count;      // points routed into the node by the split phase
+    uint64_t arena_off;  // leaves: first record in the leaf arena
+    int32_t level, parent;
+    int32_t leaf, pad;
 };
 struct DNode {
     double m[3];
@@ -100,14 +111,62 @@ struct LeafTile {
     uint32_t count;
 };
 
-constexpr uint32_t kTilePoints = 4096;   // partition tile (hist / scatter)
+constexpr uint32_t kTilePoints = 2048;   // partition tile
 constexpr uint32_t kChunkTiles = 256;    // tiles per scan chunk
 constexpr uint32_t kPlaceTile = 2048;    // place tile
+constexpr int kMaxPasses = kMaxLevels;   // a pass resolves at least one level
+
+// Device-resident bookkeeping of one build: written by the planner kernel, read by every kernel of the following pass
+// (grid sizes are upper bounds; blocks beyond the live counts exit), read back by the host once after the last pass.
+struct PassState {
+    uint32_t nactive, ntiles, nchunks, pad;
+    uint64_t npoints;      // points partitioned by this pass
+};
+struct BuildState {
+    uint32_t nnodes;
+    int32_t error;         // 0, or a BuildError code raised on the device (kErr*)
+    uint64_t arena_used;
+    uint32_t deepest_level, pad;
+    PassState pass[kMaxPasses + 1];
+};
+enum : int32_t { kErrHistMismatch = 1, kErrTooDeep = 2, kErrCapacity = 3 };
+
+// Multi-GPU sharding (SURVEY 8e): this context builds only the sub-trees below some level-k cells.  `counts` holds the
+// GLOBAL point counts of every cell of levels 1..k (level j at offset (8^j - 8) / 7), so that nodes above level k take
+// the same split decision on every rank; nodes of level k-1 ("collectors") keep the every-8th points of their local
+// children (encoded in the collector's cube, in child order) for the top-of-tree assembly on one rank.
+struct ShardSpec {
+    int k = 0;
+    const uint64_t* counts = nullptr;
+    static size_t level_offset(int level) { return (((size_t)1 << (3 * level)) - 8) / 7; }
+    uint64_t count_at(int level, uint64_t index) const { return counts[level_offset(level) + index]; }
+};
+
+// The split phase runs "one pass ahead" (DESIGN 3): a record entering the pass of a node A at level L already holds the
+// point's codes at level L+1 (inside the child cube it falls into) plus the digits of levels L+1..L+G, computed while the
+// previous pass (or the ingest kernel) still had the decoded position in registers.  The pass therefore ranks by digit
+// without any arithmetic, and only then - in destination order - finishes the codes each destination stores and, for
+// points that continue, runs the next pass's descent.  Every level of the re-quantising chain is encoded exactly once.
+struct IngestArgs {
+    PointsView pts;
+    void* rec_out;       // codes at level 1 (RecN / RecW), idx = input position
+    uint32_t* col_out;   // r | g << 8 | b << 16
+    uint8_t* dig_out;    // digit of level 1 (G0 == 1) or levels 1,2 (d1 << 3 | d2)
+    int G0;              // levels the first pass resolves
+    bool wide;
+    uint32_t ntiles;
+    LevelTable lv;
+    double root_min[3];
+};
 
 struct PassArgs {
-    int level, G, nbins;
-    bool root, wide;
-    PointsView pts;
+    int pass, level, G, nbins;  // level L of the pass's active nodes; G = levels it resolves (1 or 2); nbins = 8^G
+    int Gn;                     // levels the following pass resolves (0: there is none - every destination is a leaf)
+    bool wide;
+    // per-pass level constants as plain scalars (a dynamically indexed read of `lv` in a kernel is an indexed constant load
+    // per use): levels L+1, L+2 and, for records that continue, the node level Lb = L+G and its child level
+    double e1, e2, ry2, eb, eh, ryh;
+    int enc1, enc2, ench, fast;
     const void* rec_in;
     void* rec_next;
     void* arena;
@@ -115,15 +174,25 @@ struct PassArgs {
     const uint32_t* col_in;
     uint32_t* col_next;
     uint32_t* col_arena;
-    uint32_t ntiles, nactive, nchunks;
-    uint64_t npoints;  // points still being partitioned in this pass
-    const ActiveDesc* d_active;
-    const ChunkDesc* d_chunks;
-    uint32_t* d_tile_counts;  // [ntiles][nbins]; after scan: exclusive prefix over the node's tiles
-    uint32_t* d_chunk_sums;   // [nchunks][nbins]
-    uint64_t* d_node_bins;    // [nactive][nbins]
-    const uint16_t* d_lut;    // [nactive][nbins] -> local bucket, 0xFFFF for empty digits
-    const BucketDesc* d_buckets;  // [nactive][nbins]
+    const uint8_t* dig_in;
+    uint8_t* dig_next;
+    BuildState* st;
+    const ActiveDesc* active;
+    ActiveDesc* active_next;
+    const ChunkDesc* chunks;
+    ChunkDesc* chunks_next;
+    uint32_t* tile_active;  // [tiles] active node of every tile (from the scan chunks)
+    uint32_t* tile_counts;  // [tiles][nbins]; after scan: exclusive prefix over the node's tiles
+    uint32_t* chunk_sums;   // [chunks][nbins]
+    uint64_t* node_bins;    // [active][nbins]
+    BucketDesc* buckets;    // [active][nbins]
+    DevNode* nodes;
+    uint32_t cap_active, cap_nodes, cap_tiles, cap_chunks;
+    // split rule (generation.rs:128-150) + sharding
+    uint64_t max_points;
+    double resolution;
+    int shard_k;
+    const uint64_t* shard_counts;  // device copy of ShardSpec::counts
     LevelTable lv;
 };
 
@@ -158,9 +227,9 @@ PCV_HD uint32_t upper_index(const uint32_t* begin, size_t stride_words, uint32_t
     }
     return lo;
 }
-PCV_HD TileDesc tile_of(const PassArgs& a, uint32_t b) {
-    const uint32_t i = upper_index(&a.d_active[0].tile_begin, sizeof(ActiveDesc) / 4, a.nactive, b);
-    const ActiveDesc& act = a.d_active[i];
+PCV_HD TileDesc tile_of(const ActiveDesc* active, uint32_t nactive, uint32_t b) {
+    const uint32_t i = upper_index(&active[0].tile_begin, sizeof(ActiveDesc) / 4, nactive, b);
+    const ActiveDesc& act = active[i];
     const uint64_t o = (uint64_t)(b - act.tile_begin) * kTilePoints;
     const uint64_t rem = act.count - o;
     return TileDesc{act.start + o, (uint32_t)(rem < kTilePoints ? rem : kTilePoints), i};
@@ -174,17 +243,136 @@ PCV_HD LeafTile leaf_tile_of(const PlaceArgs& a, uint32_t b) {
     return LeafTile{nd.arena_off + o, o, node, (uint32_t)(rem < kPlaceTile ? rem : kPlaceTile)};
 }
 
+// ---- pass planning, on the device (one thread per active node; the CPU test backend calls the same function) -------------
+// What `split` decides per batch (generation.rs:110-124) and `should_split_node` (:128-150), for the children and - in a
+// two-level pass - the grandchildren of one active node: which digits form a bucket, whether the bucket is a leaf (arena)
+// or a node of the next pass, where it starts, plus the node table entries, the next pass's active list and scan chunks.
+// Running totals of one pass: in counting mode they start at zero and return the node's demand; in emit mode they start at
+// the node's exclusive prefix (and the global bases) and every structure is written.
+struct PlanRun {
+    uint32_t nodes, actives, tiles, chunks;
+    uint64_t next_pts, arena_pts;
+};
+
+template <bool EMIT>
+PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& err, uint32_t& deepest) {
+    const ActiveDesc act = a.active[ai];
+    const DevNode pn = a.nodes[act.node];
+    const uint64_t* nb = a.node_bins + (size_t)ai * a.nbins;
+    BucketDesc* bk = a.buckets + (size_t)ai * a.nbins;
+    const int w = a.nbins / 8;
+    uint32_t nlocal = 0;
+    if (!EMIT) {
+        uint64_t total = 0;
+        for (int b = 0; b < a.nbins; ++b) total += nb[b];
+        if (total != act.count) err = kErrHistMismatch;
+    }
+    // destination of a bucket: leaf -> arena, split -> a node of the next pass
+    auto route = [&](uint32_t node_index, int level, const double m[3], uint64_t cnt, bool split, int b0, int b1, int keep) {
+        BucketDesc bd{};
+        bd.b0 = (uint16_t)b0;
+        bd.b1 = (uint16_t)b1;
+        bd.keep = (uint8_t)keep;
+        if (split) {
+            bd.kind = 0;
+            bd.dest = run.next_pts;
+            const uint32_t nt = (uint32_t)((cnt + kTilePoints - 1) / kTilePoints);
+            const uint32_t nc = (nt + kChunkTiles - 1) / kChunkTiles;
+            if (EMIT && run.actives < a.cap_active && run.chunks + nc <= a.cap_chunks) {
+                ActiveDesc& na = a.active_next[run.actives];
+                na.m[0] = m[0], na.m[1] = m[1], na.m[2] = m[2];
+                na.e = a.lv.edge[level];
+                na.start = run.next_pts;
+                na.count = cnt;
+                na.chunk_begin = run.chunks;
+                na.nchunks = nc;
+                na.tile_begin = run.tiles;
+                na.node = node_index;
+                for (uint32_t o = 0, c = 0; o < nt; o += kChunkTiles, ++c)
+                    a.chunks_next[run.chunks + c] = ChunkDesc{run.tiles + o, (nt - o < kChunkTiles ? nt - o : kChunkTiles), run.actives, o == 0 ? 1u : 0u};
+            }
+            run.actives += 1;
+            run.tiles += nt;
+            run.chunks += nc;
+            run.next_pts += cnt;
+        } else {
+            bd.kind = 1;
+            bd.dest = run.arena_pts;
+            if (EMIT && node_index < a.cap_nodes) a.nodes[node_index].arena_off = run.arena_pts;
+            run.arena_pts += cnt;
+            if ((uint32_t)level > deepest) deepest = (uint32_t)level;
+        }
+        if (EMIT) bk[nlocal] = bd;
+        ++nlocal;
+    };
+    auto emit_node = [&](uint32_t ni, uint64_t ihi, uint64_t ilo, int level, const double m[3], uint64_t cnt, bool leaf) {
+        if (!EMIT || ni >= a.cap_nodes) return;
+        DevNode& d = a.nodes[ni];
+        d.index_hi = ihi;
+        d.index_lo = ilo;
+        d.m[0] = m[0], d.m[1] = m[1], d.m[2] = m[2];
+        d.count = cnt;
+        d.arena_off = 0;
+        d.level = level;
+        d.parent = (int32_t)act.node;
+        d.leaf = leaf ? 1 : 0;
+        d.pad = 0;
+    };
+    // should_split_node (generation.rs:128-150); nodes of levels <= k of a sharded build decide on the global counts
+    auto should_split = [&](int level, uint64_t ihi, uint64_t ilo, uint64_t cnt) {
+        uint64_t decision = cnt;
+        if (a.shard_k && level <= a.shard_k) decision = a.shard_counts[ShardSpec::level_offset(level) + ilo];
+        (void)ihi;
+        const bool split = decision > a.max_points && a.lv.edge[level] > a.resolution;
+        if (split && level >= kMaxLevels - 1) err = kErrTooDeep;  // deeper than 40 levels is not representable in NodeId
+        return split;
+    };
+    for (int k = 0; k < 8; ++k) {
+        uint64_t cnt1 = 0;
+        for (int b = k * w; b < (k + 1) * w; ++b) cnt1 += nb[b];
+        if (cnt1 == 0) continue;
+        const int l1 = a.level + 1;
+        const uint64_t i1hi = (pn.index_hi << 3) | (pn.index_lo >> 61), i1lo = (pn.index_lo << 3) + (uint64_t)k;  // node.rs:120-125
+        const double e1 = a.lv.edge[l1];
+        // node.rs:165-170: x = bit2, y = bit1, z = bit0
+        const double m1[3] = {(k & 4) ? pn.m[0] + e1 : pn.m[0], (k & 2) ? pn.m[1] + e1 : pn.m[1], (k & 1) ? pn.m[2] + e1 : pn.m[2]};
+        const bool split1 = should_split(l1, i1hi, i1lo, cnt1);
+        const uint32_t c1 = run.nodes++;
+        emit_node(c1, i1hi, i1lo, l1, m1, cnt1, !split1);
+        if (split1 && a.G == 2) {
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const uint64_t cnt2 = nb[k * 8 + k2];
+                if (cnt2 == 0) continue;
+                const int l2 = l1 + 1;
+                const uint64_t i2hi = (i1hi << 3) | (i1lo >> 61), i2lo = (i1lo << 3) + (uint64_t)k2;
+                const double e2 = a.lv.edge[l2];
+                const double m2[3] = {(k2 & 4) ? m1[0] + e2 : m1[0], (k2 & 2) ? m1[1] + e2 : m1[1], (k2 & 1) ? m1[2] + e2 : m1[2]};
+                const bool split2 = should_split(l2, i2hi, i2lo, cnt2);
+                const uint32_t c2 = run.nodes++;
+                emit_node(c2, i2hi, i2lo, l2, m2, cnt2, !split2);
+                if (EMIT && c2 < a.cap_nodes) a.nodes[c2].parent = (int32_t)c1;
+                route(c2, l2, m2, cnt2, split2, k * 8 + k2, k * 8 + k2 + 1, 2);
+            }
+        } else {
+            route(c1, l1, m1, cnt1, split1, k * w, (k + 1) * w, 1);
+        }
+    }
+    if (EMIT)
+        for (int lb = (int)nlocal; lb < a.nbins; ++lb) bk[lb] = BucketDesc{};
+}
+
 struct Backend {
     virtual ~Backend() {}
     virtual void* dmalloc(size_t bytes) = 0;
     virtual void dfree(void* p) = 0;
     virtual void h2d(void* d, const void* h, size_t bytes) = 0;
-    virtual void d2h(void* h, const void* d, size_t bytes) = 0;
-    virtual void hist(const PassArgs& a) = 0;
-    virtual void scan(const PassArgs& a) = 0;
-    virtual void scatter(const PassArgs& a) = 0;
+    virtual void d2h(void* h, const void* d, size_t bytes) = 0;  // synchronises
+    virtual void zero(void* d, size_t bytes) = 0;
+    virtual void ingest(const IngestArgs& a) = 0;   // raw points -> level-1 records + first digits
+    virtual void pass(const PassArgs& a) = 0;       // digit histogram + scan + plan + partition of one pass (asynchronous)
     virtual void place(const PlaceArgs& a) = 0;
     virtual void mark(int what) {}  // timing hooks: 0 partition start, 1 partition end / place start, 2 place end
+    virtual void pass_points(int pass, uint64_t npoints, uint64_t leaf_points) {}  // profiling: live point counts, known after the read-back
 };
 
 // ---- host-side node algebra (node.rs) -------------------------------------------------------------
@@ -276,27 +464,13 @@ struct BuildError : std::runtime_error {
     BuildError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
 };
 
-// Multi-GPU sharding (SURVEY 8e): this context builds only the sub-trees below some level-k cells.  `counts` holds the
-// GLOBAL point counts of every cell of levels 1..k (level j at offset (8^j - 8) / 7), so that nodes above level k take
-// the same split decision on every rank; nodes of level k-1 ("collectors") keep the every-8th points of their local
-// children (encoded in the collector's cube, in child order) for the top-of-tree assembly on one rank.
-struct ShardSpec {
-    int k = 0;
-    const uint64_t* counts = nullptr;
-    static size_t level_offset(int level) { return (((size_t)1 << (3 * level)) - 8) / 7; }
-    uint64_t count_at(int level, uint64_t index) const { return counts[level_offset(level) + index]; }
-};
-
 class BuildPlan {
    public:
     Backend& be;
     uint64_t max_points;
-    int G;
     ShardSpec shard;
-    BuildPlan(Backend& b, uint64_t max_points_per_node, int levels_per_pass)
-        : be(b), max_points(max_points_per_node ? max_points_per_node : 100000), G(levels_per_pass) {
-        if (G < 1 || G > 3) G = 3;
-    }
+    BuildPlan(Backend& b, uint64_t max_points_per_node, int /*levels_per_pass: the split phase resolves two levels per pass*/)
+        : be(b), max_points(max_points_per_node ? max_points_per_node : 100000) {}
 
     template <class T>
     T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
@@ -323,224 +497,220 @@ class BuildPlan {
         bool wide = false;
         for (int L = 1; L <= lv.last_level; ++L) wide = wide || lv.enc[L] == ENC_F64;
         const size_t rec_bytes = wide ? sizeof(RecW) : sizeof(RecN);
+        const uint64_t N = pts.n;
 
-        std::vector<HNode>& nodes = R.nodes;
-        {
-            HNode r{};
-            r.index = 0;
-            r.level = 0;
-            r.parent = -1;
-            for (int k = 0; k < 8; ++k) r.child[k] = -1;
-            r.count = pts.n;
-            r.leaf = false;
-            for (int a = 0; a < 3; ++a) r.m[a] = bmin[a];
-            r.e = E;
-            r.enc = lv.enc[0];
-            nodes.push_back(r);
+        // pass schedule: level-synchronous, two levels per pass (one when a single level is left)
+        struct Sched {
+            int level, G;
+        };
+        std::vector<Sched> sched;
+        for (int L = 0; L < lv.last_level;) {
+            const int G = std::min(2, lv.last_level - L);
+            sched.push_back(Sched{L, G});
+            L += G;
         }
+        if (sched.empty()) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
 
-        struct Active {
-            int node;
-            uint64_t start, count;
+        // capacities (upper bounds; the planner raises kErrCapacity instead of overrunning them).  A node that is split has more
+        // than max_points points - or, in a sharded build, sits at a level <= k - so a pass has at most N / (max_points + 1) (+
+        // the shard's top cells) active nodes; every node but the root is a child of a split node.
+        uint64_t shard_cells = 0;
+        for (int j = 1; j <= shard.k; ++j) shard_cells += (uint64_t)1 << (3 * j);
+        const uint64_t cap_active64 = N / (max_points + 1) + shard_cells + 2;
+        const uint64_t cap_tiles64 = N / kTilePoints + cap_active64 + 1;
+        const uint64_t cap_chunks64 = cap_tiles64 / kChunkTiles + cap_active64 + 1;
+        const uint64_t cap_nodes64 = 2 + 8 * (uint64_t)lv.last_level * cap_active64;
+        if (cap_nodes64 >= 0x7FFFFFFFull || cap_tiles64 >= 0xFFFFFFFFull) throw BuildError(-6, "node / tile tables exceed 2^31 entries");
+        const uint32_t cap_active = (uint32_t)cap_active64, cap_tiles = (uint32_t)cap_tiles64, cap_chunks = (uint32_t)cap_chunks64,
+                       cap_nodes = (uint32_t)cap_nodes64;
+
+        std::vector<void*> owned;
+        auto dalloc = [&](size_t bytes) {
+            void* p = be.dmalloc(bytes);
+            owned.push_back(p);
+            return p;
         };
-        std::vector<Active> active{{0, 0, pts.n}};
-        int L = 0;
-        void* bufs[2] = {nullptr, nullptr};
-        uint32_t* cols[2] = {nullptr, nullptr};
-        void* arena = be.dmalloc((size_t)pts.n * rec_bytes);
-        uint32_t* col_arena = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
-        uint64_t arena_used = 0;
-        int cur = -1;  // -1: raw input
-        std::vector<void*> scratch;
-        auto free_scratch = [&]() {
-            for (void* p : scratch) be.dfree(p);
-            scratch.clear();
-        };
-        be.mark(0);
+        void* arena = nullptr;
+        uint32_t* col_arena = nullptr;
+        std::vector<HNode>& nodes = R.nodes;
+        BuildState hs{};
         try {
-            while (!active.empty()) {
-                const auto tp0 = std::chrono::steady_clock::now();
-                const int Gp = std::min(G, lv.last_level - L);
-                if (Gp < 1) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
-                const int nbins = 1 << (3 * Gp);
-                // ---- tiles / chunks ----
-                uint32_t ntiles_total = 0;
-                std::vector<ChunkDesc> chunks;
-                std::vector<ActiveDesc> adesc(active.size());
-                uint64_t active_points = 0;
-                for (size_t a = 0; a < active.size(); ++a) {
-                    const HNode& nd = nodes[active[a].node];
-                    for (int k = 0; k < 3; ++k) adesc[a].m[k] = nd.m[k];
-                    adesc[a].e = nd.e;
-                    uint64_t c = active[a].count, s = active[a].start;
-                    active_points += c;
-                    const uint32_t t0 = ntiles_total;
-                    const uint32_t nt = (uint32_t)((c + kTilePoints - 1) / kTilePoints);
-                    ntiles_total += nt;
-                    adesc[a].start = s;
-                    adesc[a].count = c;
-                    adesc[a].tile_begin = t0;
-                    adesc[a].chunk_begin = (uint32_t)chunks.size();
-                    adesc[a].nchunks = (nt + kChunkTiles - 1) / kChunkTiles;
-                    for (uint32_t o = 0; o < nt; o += kChunkTiles)
-                        chunks.push_back(ChunkDesc{t0 + o, std::min(kChunkTiles, nt - o), (uint32_t)a, o == 0 ? 1u : 0u});
-                }
+            void* bufs[2] = {dalloc((size_t)N * rec_bytes + 64), dalloc((size_t)N * rec_bytes + 64)};
+            uint32_t* cols[2] = {(uint32_t*)dalloc((size_t)N * 4 + 64), (uint32_t*)dalloc((size_t)N * 4 + 64)};  // + slack: bulk copies read whole 16-byte granules
+            uint8_t* digs[2] = {(uint8_t*)dalloc((size_t)N + 64), (uint8_t*)dalloc((size_t)N + 64)};
+            arena = dalloc((size_t)N * rec_bytes);
+            col_arena = (uint32_t*)dalloc((size_t)N * 4 + 64);
+            BuildState* d_st = (BuildState*)dalloc(sizeof(BuildState));
+            ActiveDesc* act[2] = {(ActiveDesc*)dalloc((size_t)cap_active * sizeof(ActiveDesc)), (ActiveDesc*)dalloc((size_t)cap_active * sizeof(ActiveDesc))};
+            ChunkDesc* chk[2] = {(ChunkDesc*)dalloc((size_t)cap_chunks * sizeof(ChunkDesc)), (ChunkDesc*)dalloc((size_t)cap_chunks * sizeof(ChunkDesc))};
+            uint32_t* tile_counts = (uint32_t*)dalloc((size_t)cap_tiles * 64 * 4);
+            uint32_t* tile_active = (uint32_t*)dalloc((size_t)cap_tiles * 4);
+            uint32_t* chunk_sums = (uint32_t*)dalloc((size_t)cap_chunks * 64 * 4);
+            uint64_t* node_bins = (uint64_t*)dalloc((size_t)cap_active * 64 * 8);
+            BucketDesc* buckets = (BucketDesc*)dalloc((size_t)cap_active * 64 * sizeof(BucketDesc));
+            DevNode* d_nodes = (DevNode*)dalloc((size_t)cap_nodes * sizeof(DevNode));
+            uint64_t* d_shard = nullptr;
+            if (shard.k) {
+                const size_t ncount = ShardSpec::level_offset(shard.k + 1);
+                d_shard = (uint64_t*)dalloc(ncount * 8);
+                be.h2d(d_shard, shard.counts, ncount * 8);
+            }
+
+            // initial state: the root node (always split, generation.rs:312-323), one active node covering the input
+            const uint32_t nt0 = (uint32_t)((N + kTilePoints - 1) / kTilePoints);
+            hs.nnodes = 1;
+            hs.pass[0].nactive = 1;
+            hs.pass[0].ntiles = nt0;
+            hs.pass[0].nchunks = (nt0 + kChunkTiles - 1) / kChunkTiles;
+            hs.pass[0].npoints = N;
+            be.h2d(d_st, &hs, sizeof hs);
+            DevNode root{};
+            for (int a = 0; a < 3; ++a) root.m[a] = bmin[a];
+            root.count = N;
+            root.level = 0;
+            root.parent = -1;
+            be.h2d(d_nodes, &root, sizeof root);
+            ActiveDesc a0{};
+            for (int a = 0; a < 3; ++a) a0.m[a] = bmin[a];
+            a0.e = E;
+            a0.start = 0;
+            a0.count = N;
+            a0.chunk_begin = 0;
+            a0.nchunks = hs.pass[0].nchunks;
+            a0.tile_begin = 0;
+            a0.node = 0;
+            be.h2d(act[0], &a0, sizeof a0);
+            std::vector<ChunkDesc> c0;
+            for (uint32_t o = 0; o < nt0; o += kChunkTiles) c0.push_back(ChunkDesc{o, std::min(kChunkTiles, nt0 - o), 0u, o == 0 ? 1u : 0u});
+            be.h2d(chk[0], c0.data(), c0.size() * sizeof(ChunkDesc));
+
+            be.mark(0);
+            IngestArgs ia{};
+            ia.pts = pts;
+            ia.rec_out = bufs[0];
+            ia.col_out = cols[0];
+            ia.dig_out = digs[0];
+            ia.G0 = sched[0].G;
+            ia.wide = wide;
+            ia.ntiles = nt0;
+            ia.lv = lv;
+            for (int a = 0; a < 3; ++a) ia.root_min[a] = bmin[a];
+            be.ingest(ia);
+
+            // Small inputs: read the state back after every pass and stop at the first pass without active nodes (a few empty
+            // launches cost more than the build of a 1e5-point cloud).  Large inputs: enqueue everything, one read-back at the end.
+            const bool poll = N < (4u << 20);
+            size_t launched = 0;
+            for (size_t p = 0; p < sched.size(); ++p) {
                 PassArgs pa{};
-                pa.level = L;
-                pa.G = Gp;
-                pa.nbins = nbins;
-                pa.root = cur < 0;
+                pa.pass = (int)p;
+                pa.level = sched[p].level;
+                pa.G = sched[p].G;
+                pa.nbins = 1 << (3 * pa.G);
+                pa.Gn = p + 1 < sched.size() ? sched[p + 1].G : 0;
                 pa.wide = wide;
-                pa.pts = pts;
-                pa.rec_in = cur < 0 ? nullptr : bufs[cur];
-                int nxt = cur < 0 ? 0 : 1 - cur;
-                if (!bufs[nxt]) {
-                    bufs[nxt] = be.dmalloc((size_t)pts.n * rec_bytes);
-                    cols[nxt] = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
-                }
-                pa.rec_next = bufs[nxt];
+                pa.rec_in = bufs[p & 1];
+                pa.rec_next = bufs[(p + 1) & 1];
                 pa.arena = arena;
-                pa.col_in = cur < 0 ? nullptr : cols[cur];
-                pa.col_next = cols[nxt];
+                pa.col_in = cols[p & 1];
+                pa.col_next = cols[(p + 1) & 1];
                 pa.col_arena = col_arena;
-                pa.ntiles = ntiles_total;
-                pa.nactive = (uint32_t)active.size();
-                pa.nchunks = (uint32_t)chunks.size();
-                pa.npoints = active_points;
-                pa.d_active = upload(adesc, scratch);
-                pa.d_chunks = upload(chunks, scratch);
-                pa.d_tile_counts = (uint32_t*)be.dmalloc((size_t)pa.ntiles * nbins * 4);
-                scratch.push_back(pa.d_tile_counts);
-                pa.d_chunk_sums = (uint32_t*)be.dmalloc((size_t)pa.nchunks * nbins * 4);
-                scratch.push_back(pa.d_chunk_sums);
-                pa.d_node_bins = (uint64_t*)be.dmalloc((size_t)pa.nactive * nbins * 8);
-                scratch.push_back(pa.d_node_bins);
+                pa.dig_in = digs[p & 1];
+                pa.dig_next = digs[(p + 1) & 1];
+                pa.st = d_st;
+                pa.active = act[p & 1];
+                pa.active_next = act[(p + 1) & 1];
+                pa.chunks = chk[p & 1];
+                pa.chunks_next = chk[(p + 1) & 1];
+                pa.tile_counts = tile_counts;
+                pa.tile_active = tile_active;
+                pa.chunk_sums = chunk_sums;
+                pa.node_bins = node_bins;
+                pa.buckets = buckets;
+                pa.nodes = d_nodes;
+                pa.cap_active = cap_active;
+                pa.cap_nodes = cap_nodes;
+                pa.cap_tiles = cap_tiles;
+                pa.cap_chunks = cap_chunks;
+                pa.max_points = max_points;
+                pa.resolution = resolution;
+                pa.shard_k = shard.k;
+                pa.shard_counts = d_shard;
                 pa.lv = lv;
-
-                const auto tq0 = std::chrono::steady_clock::now();
-                be.hist(pa);
-                be.scan(pa);
-                std::vector<uint64_t> bins((size_t)pa.nactive * nbins);
-                const auto tw0 = std::chrono::steady_clock::now();
-                R.host_ms_plan += std::chrono::duration<double, std::milli>(tw0 - tp0).count();
-                be.d2h(bins.data(), pa.d_node_bins, bins.size() * 8);
-                const auto tw1 = std::chrono::steady_clock::now();
-                R.host_ms_wait += std::chrono::duration<double, std::milli>(tw1 - tw0).count();
-
-                // ---- decide leaf / split for every descendant within Gp levels ----
-                nodes.reserve(nodes.size() + (size_t)pa.nactive * 16 + 64);
-                std::vector<uint16_t> lut((size_t)pa.nactive * nbins, 0xFFFF);
-                std::vector<BucketDesc> buckets((size_t)pa.nactive * nbins);
-                std::vector<Active> next_active;
-                uint64_t next_used = 0;
-                for (size_t a = 0; a < active.size(); ++a) {
-                    const uint64_t* nb = &bins[a * nbins];
-                    uint16_t nlocal = 0;
-                    uint64_t total = 0;
-                    for (int b = 0; b < nbins; ++b) total += nb[b];
-                    if (total != active[a].count) throw BuildError(-2, "internal: histogram total mismatch");
-                    // iterative expansion with an explicit stack: (node, sublevel j, b0, width)
-                    struct Fr {
-                        int node, j, b0, w;
-                    };
-                    Fr st[64];  // depth-first over <= 3 sub-levels: at most 8 pending frames per level
-                    int sp = 0;
-                    st[sp++] = Fr{active[a].node, 0, 0, nbins};
-                    while (sp > 0) {
-                        const Fr f = st[--sp];
-                        int w = f.w / 8;
-                        Fr pend[8];
-                        int npend = 0;
-                        for (int k = 0; k < 8; ++k) {
-                            int b0 = f.b0 + k * w;
-                            uint64_t cnt = 0;
-                            for (int b = b0; b < b0 + w; ++b) cnt += nb[b];
-                            if (cnt == 0) continue;
-                            HNode c{};
-                            const HNode& p = nodes[f.node];
-                            c.level = p.level + 1;
-                            c.index = (p.index << 3) + (u128)k;  // node.rs:120-125
-                            c.parent = f.node;
-                            for (int q = 0; q < 8; ++q) c.child[q] = -1;
-                            c.count = cnt;
-                            c.e = lv.edge[c.level];
-                            // node.rs:165-170: x = bit2, y = bit1, z = bit0
-                            c.m[0] = (k & 4) ? p.m[0] + c.e : p.m[0];
-                            c.m[1] = (k & 2) ? p.m[1] + c.e : p.m[1];
-                            c.m[2] = (k & 1) ? p.m[2] + c.e : p.m[2];
-                            c.enc = lv.enc[c.level];
-                            const uint64_t decision_cnt = (shard.k && c.level <= shard.k) ? shard.count_at(c.level, (uint64_t)c.index) : cnt;
-                            bool split = decision_cnt > max_points && c.e > resolution;  // generation.rs:128-150
-                            if (split && c.level >= kMaxLevels - 1)
-                                throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
-                            c.leaf = !split;
-                            int ci = (int)nodes.size();
-                            nodes.push_back(c);
-                            nodes[f.node].child[k] = ci;
-                            int j = f.j + 1;
-                            if (split && j < Gp) {
-                                pend[npend++] = Fr{ci, j, b0, w};
-                                continue;
-                            }
-                            BucketDesc bd{};
-                            bd.b0 = (uint16_t)b0;
-                            bd.b1 = (uint16_t)(b0 + w);
-                            bd.keep = (uint8_t)j;
-                            if (split) {
-                                bd.kind = 0;
-                                bd.dest = next_used;
-                                next_active.push_back(Active{ci, next_used, cnt});
-                                next_used += cnt;
-                            } else {
-                                bd.kind = 1;
-                                bd.dest = arena_used;
-                                nodes[ci].arena_off = arena_used;
-                                arena_used += cnt;
-                                R.deepest_level = std::max<uint32_t>(R.deepest_level, (uint32_t)c.level);
-                            }
-                            for (int b = b0; b < b0 + w; ++b) lut[a * nbins + b] = nlocal;
-                            buckets[a * nbins + nlocal] = bd;
-                            ++nlocal;
-                        }
-                        for (int i = npend; i-- > 0;) st[sp++] = pend[i];
-                    }
+                {
+                    const int L1 = pa.level + 1, L2 = std::min(pa.level + 2, kMaxLevels - 1), Lb = pa.level + pa.G, Lh = std::min(Lb + 1, kMaxLevels - 1);
+                    pa.e1 = lv.edge[L1], pa.e2 = lv.edge[L2], pa.ry2 = lv.ry[L2];
+                    pa.eb = lv.edge[Lb], pa.eh = lv.edge[Lh], pa.ryh = lv.ry[Lh];
+                    pa.enc1 = lv.enc[L1], pa.enc2 = lv.enc[L2], pa.ench = lv.enc[Lh];
+                    pa.fast = lv.fast;
                 }
-                const auto tq1 = std::chrono::steady_clock::now();
-                pa.d_lut = upload(lut, scratch);
-                pa.d_buckets = upload(buckets, scratch);
-                be.scatter(pa);
-                if (std::getenv("PCV_TIMING"))
-                    fprintf(stderr, "[pcv timing] pass L=%d G=%d active=%zu tiles=%u pts=%llu | descs %.2f wait %.2f decide %.2f upload+launch %.2f ms\n", L, Gp, active.size(),
-                            pa.ntiles, (unsigned long long)active_points, std::chrono::duration<double, std::milli>(tq0 - tp0).count(),
-                            std::chrono::duration<double, std::milli>(tw1 - tw0).count(), std::chrono::duration<double, std::milli>(tq1 - tw1).count(),
-                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq1).count());
-                free_scratch();
-                R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw1).count();
-                R.passes++;
-                active.swap(next_active);
-                cur = nxt;
-                L += Gp;
+                be.pass(pa);
+                ++launched;
+                if (poll) {
+                    const auto tw0 = std::chrono::steady_clock::now();
+                    be.d2h(&hs, d_st, sizeof hs);
+                    R.host_ms_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+                    if (hs.error || hs.pass[p + 1].nactive == 0) break;
+                }
+            }
+            be.mark(1);
+            const auto tw0 = std::chrono::steady_clock::now();
+            be.d2h(&hs, d_st, sizeof hs);
+            R.host_ms_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+            if (hs.error == kErrTooDeep) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
+            if (hs.error == kErrHistMismatch) throw BuildError(-2, "internal: histogram total mismatch");
+            if (hs.error) throw BuildError(-2, "internal: planner capacity exceeded");
+            if (hs.arena_used != N) throw BuildError(-2, "internal: the split phase lost points");
+            for (size_t p = 0; p < launched; ++p) {
+                if (hs.pass[p].nactive) R.passes++;
+                be.pass_points((int)p, hs.pass[p].npoints, hs.pass[p].npoints - hs.pass[p + 1].npoints);
+            }
+            R.deepest_level = hs.deepest_level;
+
+            const auto tp0 = std::chrono::steady_clock::now();
+            std::vector<DevNode> dv(hs.nnodes);
+            be.d2h(dv.data(), d_nodes, (size_t)hs.nnodes * sizeof(DevNode));
+            nodes.resize(hs.nnodes);
+            for (uint32_t i = 0; i < hs.nnodes; ++i) {
+                const DevNode& d = dv[i];
+                HNode& x = nodes[i];
+                x = HNode{};
+                x.index = ((u128)d.index_hi << 64) | d.index_lo;
+                x.level = d.level;
+                x.parent = d.parent;
+                for (int k = 0; k < 8; ++k) x.child[k] = -1;
+                x.count = d.count;
+                x.leaf = d.leaf != 0;
+                x.arena_off = d.arena_off;
+                for (int a = 0; a < 3; ++a) x.m[a] = d.m[a];
+                x.e = lv.edge[d.level];
+                x.enc = lv.enc[d.level];
+                if (d.parent >= 0) nodes[d.parent].child[(int)(d.index_lo & 7)] = (int)i;
+            }
+            R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+            // the ping-pong buffers and the planner's tables are dead now; the arena lives until the placement is done
+            for (auto& p : owned) {
+                if (p && p != arena && p != (void*)col_arena) {
+                    be.dfree(p);
+                    p = nullptr;
+                }
             }
         } catch (...) {
-            free_scratch();
-            be.dfree(arena);
-            be.dfree(col_arena);
-            for (void* b : bufs)
-                if (b) be.dfree(b);
-            for (uint32_t* b : cols)
-                if (b) be.dfree(b);
+            for (void* p : owned)
+                if (p) be.dfree(p);
             throw;
         }
-        for (void* b : bufs)
-            if (b) be.dfree(b);
-        for (uint32_t* b : cols)
-            if (b) be.dfree(b);
-        be.mark(1);
+        owned.clear();
 
         const bool dbg = std::getenv("PCV_TIMING") != nullptr;
         auto tnow = []() { return std::chrono::steady_clock::now(); };
         auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         const auto ts0 = tnow();
+        std::vector<void*> scratch;
+        auto free_scratch = [&]() {
+            for (void* p : scratch) be.dfree(p);
+            scratch.clear();
+        };
         // ---- subsample plan: closed form of generation.rs:195-253,335-387 ----
         for (size_t i = nodes.size(); i-- > 0;) {
             HNode& x = nodes[i];
@@ -613,7 +783,7 @@ class BuildPlan {
         const auto ts3 = tnow();
         R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
         R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
-        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);  // + slack: the scatter's bulk copy reads whole 16-byte granules
+        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);
         R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
         const auto ts4 = tnow();
         PlaceArgs pl{};
@@ -645,9 +815,10 @@ class BuildPlan {
         free_scratch();
         be.dfree(arena);
         be.dfree(col_arena);
+        R.host_ms_plan += tms(ts0, ts5);
         if (dbg)
-            fprintf(stderr, "[pcv timing] plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", tms(ts0, ts1), tms(ts1, ts2),
-                    tms(ts2, ts3), tms(ts3, ts4), tms(ts4, ts5), nodes.size(), (size_t)nplace_tiles);
+            fprintf(stderr, "[pcv timing] passes %u  wait %.2f | plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", R.passes,
+                    R.host_ms_wait, tms(ts0, ts1), tms(ts1, ts2), tms(ts2, ts3), tms(ts3, ts4), tms(ts4, ts5), nodes.size(), (size_t)nplace_tiles);
         return R;
     }
 };

@@ -1,9 +1,12 @@
 // kernels_build.cuh — sm_100a kernels of the octree build and the CUDA Backend that drives them.
 //
 //   k_bbox      a1  find_bounding_box (generation.rs:256-270): streaming min/max, warp-shuffle reduce
-//   k_hist      a3-a6  per tile: decode -> G descent steps (chain.h) -> digit histogram in shared memory
+//   k_ingest    a3-a6  raw position -> first step of the chain (chain.h): level-1 codes + the first pass's digits
+//   k_dighist   digit histogram of every tile of a pass (1 byte per point)
 //   k_scan_*    per-digit exclusive prefix over the tiles of each active node (+ node totals)
-//   k_scatter   a4  stable multi-way partition of a tile (warp match ranking), re-running the descent
+//   k_plan      a4  should_split_node for all descendants of the pass, bucket tables, node table, next active list
+//   k_pass      a3-a6  stable multi-way partition of a tile by the carried digits (warp match ranking), then - in
+//                   destination order - the codes each destination stores and the next pass's descent
 //   k_place     a7  closed-form LOD subsampling + up-chain re-encode + final node-contiguous store
 //
 // All of them stream SoA/record arrays once with coalesced accesses; none has a dense contraction,
@@ -155,229 +158,16 @@ __device__ __forceinline__ void store_rec(void* base, uint64_t i, const uint64_t
     }
 }
 
-// Position of item `i` of a tile as the node's file would hand it to split(): raw for the root,
-// decoded from the node's own encoding otherwise (raw.rs:127-216).
-template <bool ROOT, bool WIDE>
-__device__ __forceinline__ void load_position(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i,
-                                              double q[3], uint32_t& idx) {
-    const uint64_t g = t.start + i;
-    if (ROOT) {
-        q[0] = __ldg(a.pts.x + g * a.pts.stride);
-        q[1] = __ldg(a.pts.y + g * a.pts.stride);
-        q[2] = __ldg(a.pts.z + g * a.pts.stride);
-        idx = (uint32_t)g;
-    } else {
-        uint64_t c[3];
-        load_rec<WIDE>(a.rec_in, g, c, idx);
-        const int enc = a.lv.enc[a.level];
-        if (a.lv.fast) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) q[k] = decode1_fast(c[k], act.m[k], act.e, enc);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) q[k] = decode1(c[k], act.m[k], act.e, enc);
-        }
-    }
-}
-
-// One descent step through the exact fast paths when the level table admits them (identical results).
-__device__ __forceinline__ Step descend_any(const LevelTable& lv, int child_level, double q[3], double m[3], double e_cur) {
-    if (lv.fast) return descend_fast(q, m, e_cur, lv.edge[child_level], lv.ry[child_level], lv.enc[child_level]);
-    return descend(q, m, e_cur, lv.edge[child_level], lv.enc[child_level]);
-}
-
-template <bool ROOT>
-__device__ __forceinline__ uint32_t load_colour(const PassArgs& a, uint64_t g) {
-    if (ROOT) {
-        const uint8_t* p = a.pts.rgb + 3 * g;
-        return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
-    }
-    return __ldg(a.col_in + g);
-}
-
 // ------------------------------------------------------------------------------------------------
-// hist
+// shared-memory / TMA helpers
 // ------------------------------------------------------------------------------------------------
-// Position of item i as the node's file would hand it to split(): raw for the root, decoded from the node's own
-// encoding (ENC_IN) otherwise.
-template <bool ROOT, bool WIDE, int ENC_IN>
-__device__ __forceinline__ void load_position_t(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i, double q[3], uint32_t& idx) {
-    const uint64_t g = t.start + i;
-    if (ROOT) {
-        // streamed once: bypass L1 (ld.global.cg).  The scatter kernel leaves only ~29 KB of L1 next to its shared
-        // memory, too few lines for the loads in flight if they allocated there.
-        q[0] = __ldcg(a.pts.x + g * a.pts.stride);
-        q[1] = __ldcg(a.pts.y + g * a.pts.stride);
-        q[2] = __ldcg(a.pts.z + g * a.pts.stride);
-        idx = (uint32_t)g;
-    } else {
-        uint64_t c[3];
-        load_rec<WIDE>(a.rec_in, g, c, idx);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) q[k] = decode_axis<ENC_IN>(c[k], act.m[k], act.e);
-    }
-}
-
-// Points per thread in flight (x 3 independent axis chains each).  Measured at N = 1e9: one point per thread at 32
-// registers (8 blocks per SM, 100 % occupancy) 17.2 ms; two points at 64 registers (4 blocks) 20.8 ms; two at 40 / 48
-// registers (6 / 5 blocks, spilling) 18.3 / 19.1 ms - thread-level parallelism hides the load latency better than ILP.
-constexpr int kHistItems = 1;
-
-// Histogram of the G-level digits of one tile.  The last level needs only the child digit (no encode/decode).
-template <bool ROOT, bool WIDE, int G, int FAST>
-__device__ __forceinline__ unsigned hist_tile(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t* sh_hist) {
-    unsigned bad = 0;
-    for (uint32_t i0 = threadIdx.x; i0 < t.count; i0 += blockDim.x * kHistItems) {
-        double q[kHistItems][3], m[kHistItems][3];
-        uint32_t idx;
-#pragma unroll
-        for (int u = 0; u < kHistItems; ++u) {
-            const uint32_t i = min(i0 + u * blockDim.x, t.count - 1);  // clamp: out-of-range lanes redo the last item, not counted
-            if (ROOT) {
-                load_position_t<true, WIDE, ENC_F64>(a, t, act, i, q[u], idx);
-                if (FAST == 2) bad |= input_bad(q[u][0]) | input_bad(q[u][1]) | input_bad(q[u][2]);
-            } else {
-                PCV_ENC_SWITCH(a.lv.enc[a.level], load_position_t<false, WIDE, ENC>(a, t, act, i, q[u], idx);)
-            }
-            m[u][0] = act.m[0];
-            m[u][1] = act.m[1];
-            m[u][2] = act.m[2];
-        }
-        unsigned bin[kHistItems];
-#pragma unroll
-        for (int u = 0; u < kHistItems; ++u) bin[u] = 0;
-        double e = act.e;
-#pragma unroll
-        for (int j = 1; j < G; ++j) {
-            const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
-            PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kHistItems; ++u) {
-                uint32_t code[3];
-                uint64_t codew[3];
-                const unsigned d = WIDE ? level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, codew, bad) : level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, code, bad);
-                bin[u] = (bin[u] << 3) | d;
-            })
-            e = eh;
-        }
-#pragma unroll
-        for (int u = 0; u < kHistItems; ++u) {
-            bin[u] = (bin[u] << 3) | level_digit(q[u], m[u], e);
-            if (i0 + u * blockDim.x < t.count) atomicAdd(&sh_hist[bin[u]], 1u);
-        }
-    }
-    return bad;
-}
-
-template <bool ROOT, bool WIDE, int G>
-__global__ void __launch_bounds__(256, 8) k_hist(const __grid_constant__ PassArgs a) {
-    extern __shared__ uint32_t sh_hist[];
-    const TileDesc t = tile_of(a, blockIdx.x);
-    const ActiveDesc act = a.d_active[t.active];
-    constexpr int NB = 1 << (3 * G);
-    for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
-    __syncthreads();
-    if (a.lv.fast) {
-        const unsigned bad = a.lv.fast == 2 ? hist_tile<ROOT, WIDE, G, 2>(a, t, act, sh_hist) : hist_tile<ROOT, WIDE, G, 1>(a, t, act, sh_hist);
-        if (__syncthreads_or((int)bad)) {  // a numerator outside the proven range: redo the tile with the IEEE operator
-            for (int b = threadIdx.x; b < NB; b += blockDim.x) sh_hist[b] = 0;
-            __syncthreads();
-            hist_tile<ROOT, WIDE, G, 0>(a, t, act, sh_hist);
-        }
-    } else {
-        hist_tile<ROOT, WIDE, G, 0>(a, t, act, sh_hist);
-    }
-    __syncthreads();
-    uint32_t* out = a.d_tile_counts + (size_t)blockIdx.x * NB;
-    for (int b = threadIdx.x; b < NB; b += blockDim.x) out[b] = sh_hist[b];
-}
-
-// ------------------------------------------------------------------------------------------------
-// scan: per digit, exclusive prefix over the tiles of each active node
-// ------------------------------------------------------------------------------------------------
-__global__ void k_scan_chunk_sums(const __grid_constant__ PassArgs a) {
-    const ChunkDesc c = a.d_chunks[blockIdx.x];
-    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
-        uint32_t s = 0;
-        const uint32_t* p = a.d_tile_counts + (size_t)c.tile_begin * a.nbins + b;
-        for (uint32_t t = 0; t < c.ntiles; ++t) s += p[(size_t)t * a.nbins];
-        a.d_chunk_sums[(size_t)blockIdx.x * a.nbins + b] = s;
-    }
-}
-__global__ void k_scan_nodes(const __grid_constant__ PassArgs a) {
-    const ActiveDesc act = a.d_active[blockIdx.x];
-    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
-        uint64_t run = 0;
-        uint32_t* p = a.d_chunk_sums + (size_t)act.chunk_begin * a.nbins + b;
-        for (uint32_t c = 0; c < act.nchunks; ++c) {
-            uint32_t v = p[(size_t)c * a.nbins];
-            p[(size_t)c * a.nbins] = (uint32_t)run;
-            run += v;
-        }
-        a.d_node_bins[(size_t)blockIdx.x * a.nbins + b] = run;
-    }
-}
-__global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
-    const ChunkDesc c = a.d_chunks[blockIdx.x];
-    for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
-        uint32_t run = a.d_chunk_sums[(size_t)blockIdx.x * a.nbins + b];
-        uint32_t* p = a.d_tile_counts + (size_t)c.tile_begin * a.nbins + b;
-        for (uint32_t t = 0; t < c.ntiles; ++t) {
-            uint32_t v = p[(size_t)t * a.nbins];
-            p[(size_t)t * a.nbins] = run;
-            run += v;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// scatter
-// ------------------------------------------------------------------------------------------------
-// One block (16 warps) per 4096-point tile, warp w owns the contiguous items [256 w, 256 w + 256).
-//   stage    the tile's input records and colours are contiguous in HBM: one elected thread issues two TMA bulk copies
-//            (cp.async.bulk global -> shared, completion on an mbarrier) that overlap the bucket-table set-up
-//   sweep A  descent of every item (2 sub-rounds of 32 items in flight per warp) from the staged record; the kept codes
-//            replace the record's codes in shared memory (index and colour pass through); destination bucket staged
-//            next to it; per-warp bucket counts with __match_any_sync
-//   scan     per-bucket totals, exclusive prefix over the buckets (sorted start inside the tile) and over the warps
-//   sweep B1 every warp walks its items in order and writes (item, bucket) at the item's stable sorted position: the tile
-//            is sorted by bucket as a permutation in shared memory
-//   sweep B2 consecutive threads store consecutive records of a bucket's run to the next pass segment or the leaf arena:
-//            a warp's store covers a few contiguous runs instead of up to 32 scattered 16-byte slots (and pages)
-// The order inside every bucket is the tile order, i.e. input order (stable).
-// 16 warps per tile with two sub-rounds in flight per warp (64 registers, two blocks per SM for narrow records).  Measured
-// at N = 1e9: 32 warps with one sub-round in flight (32 registers, 2048 threads per SM) 51.9 ms against 50.4 ms - unlike
-// k_hist, the scatter gains nothing from occupancy (its sweeps are bound by shared-memory traffic and barriers).
-template <bool WIDE>
-struct ScatterCfg {
-    static constexpr int threads = 512;
-    static constexpr int warps = threads / 32;
-    static constexpr int warp_items = kTilePoints / warps;  // 256
-    static constexpr int sub_rounds = warp_items / 32;      // 8
-    static constexpr int U = 2;                             // sub-rounds in flight per warp
-    static_assert(sub_rounds % U == 0, "sub-rounds must be a multiple of the unroll");
-};
-constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;  // root pass: the tile's rgb bytes, staged with 16-byte loads in the (not yet used) sinfo area
-static_assert(kRgbStage <= (size_t)kTilePoints * 4, "the rgb staging area aliases sinfo");
-
-template <bool WIDE>
-struct ScatterSmem {
-    static constexpr size_t rec_bytes = WIDE ? 32 : 16;
-    __host__ __device__ static constexpr size_t bytes(int nb) {
-        return (size_t)kTilePoints * rec_bytes + ((size_t)kTilePoints + 4) * 4 + (size_t)kTilePoints * 4 + (size_t)nb * 4 * (2 + ScatterCfg<WIDE>::warps) +
-               (size_t)nb * 4 + 16;
-    }
-};
-
-static_assert(ScatterSmem<false>::bytes(512) <= 232448 && ScatterSmem<true>::bytes(512) <= 232448, "scatter tile exceeds the 227 KB opt-in shared memory of sm_100");
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    uint64_t state;
-    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;" : "=l"(state) : "r"(smem_u32(bar)), "r"(bytes) : "memory");
-    (void)state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
@@ -408,290 +198,629 @@ __device__ __forceinline__ void smem_load_rec(const unsigned char* srec, uint32_
         c[0] = v.x, c[1] = v.y, c[2] = v.z, idx = v.w;
     }
 }
-template <bool WIDE>
-__device__ __forceinline__ void smem_store_rec(unsigned char* srec, uint32_t i, const uint64_t c[3], uint32_t idx) {
-    if (WIDE) {
-        ulonglong2* p = reinterpret_cast<ulonglong2*>(srec) + 2 * (size_t)i;
-        p[0] = make_ulonglong2(c[0], c[1]);
-        p[1] = make_ulonglong2(c[2], (unsigned long long)idx);
-    } else {
-        reinterpret_cast<uint4*>(srec)[i] = make_uint4((uint32_t)c[0], (uint32_t)c[1], (uint32_t)c[2], idx);
-    }
-}
 
-template <bool ROOT, bool WIDE, int G, int FAST, typename CodeT>
-__device__ __forceinline__ unsigned scatter_sweep_a(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, int warp, int lane, unsigned char* srec,
-                                                    uint32_t* sinfo, const uint32_t* lutm, uint32_t* cnt) {
-    constexpr int nb = 1 << (3 * G);
-    constexpr int kWarpItems = ScatterCfg<WIDE>::warp_items, kSubRounds = ScatterCfg<WIDE>::sub_rounds, kScatterU = ScatterCfg<WIDE>::U;
+// ------------------------------------------------------------------------------------------------
+// ingest: raw points -> level-1 records + the first pass's digits
+// ------------------------------------------------------------------------------------------------
+// One block per 4096-point tile of the input (grid-stride).  Per point: the first step of the chain from the raw position
+// (child digit of the root cube, codes in the level-1 cube) and, when the first pass resolves two levels, the level-2
+// digit of the re-decoded position.  The tile's rgb bytes are staged with aligned 16-byte loads and repacked four points
+// at a time (3-byte-strided per-thread loads are LSU-hostile); everything is written in input order, fully coalesced.
+constexpr int kIngestThreads = 256;
+constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;
+
+template <bool WIDE, int FAST>
+__device__ __forceinline__ unsigned ingest_tile(const IngestArgs& a, uint64_t start, uint32_t count, const uint32_t* scol) {
     unsigned bad = 0;
-    for (int s0 = 0; s0 < kSubRounds; s0 += kScatterU) {
-        double q[kScatterU][3], m[kScatterU][3];
-        uint32_t idx[kScatterU];
-        unsigned bin[kScatterU];
-        CodeT cj[kScatterU][G][3];
-#pragma unroll
-        for (int u = 0; u < kScatterU; ++u) {
-            const uint32_t i = warp * kWarpItems + (s0 + u) * 32 + lane;
-            const bool valid = i < t.count;
-            if (ROOT) {
-                const uint32_t ic = min(i, t.count - 1);
-                load_position_t<true, WIDE, ENC_F64>(a, t, act, ic, q[u], idx[u]);
-                if (FAST == 2) bad |= input_bad(q[u][0]) | input_bad(q[u][1]) | input_bad(q[u][2]);
-            } else {
-                uint64_t c[3] = {0, 0, 0};  // lanes past the end of the tile descend from the cube's min corner (harmless)
-                idx[u] = 0;
-                if (valid) smem_load_rec<WIDE>(srec, i, c, idx[u]);
-                PCV_ENC_SWITCH(a.lv.enc[a.level], _Pragma("unroll") for (int k = 0; k < 3; ++k) q[u][k] = decode_axis<ENC>(c[k], act.m[k], act.e);)
-            }
-            m[u][0] = act.m[0];
-            m[u][1] = act.m[1];
-            m[u][2] = act.m[2];
-            bin[u] = 0;
+    const double e0 = a.lv.edge[0], e1 = a.lv.edge[1], ry1 = a.lv.ry[1];
+    for (uint32_t i = threadIdx.x; i < count; i += kIngestThreads) {
+        const uint64_t g = start + i;
+        double q[3], m[3] = {a.root_min[0], a.root_min[1], a.root_min[2]};
+        // streamed once: bypass L1 (ld.global.cg)
+        q[0] = __ldcg(a.pts.x + g * a.pts.stride);
+        q[1] = __ldcg(a.pts.y + g * a.pts.stride);
+        q[2] = __ldcg(a.pts.z + g * a.pts.stride);
+        if (FAST == 2) bad |= input_bad(q[0]) | input_bad(q[1]) | input_bad(q[2]);
+        typename std::conditional<WIDE, uint64_t, uint32_t>::type code[3];
+        unsigned dig = 0;
+        if (a.G0 == 2) {
+            PCV_ENC_SWITCH(a.lv.enc[1], dig = level_step<ENC, FAST, true>(q, m, e0, e1, ry1, code, bad);)
+            dig = (dig << 3) | level_digit(q, m, e1);
+        } else {
+            PCV_ENC_SWITCH(a.lv.enc[1], dig = level_step<ENC, FAST, false>(q, m, e0, e1, ry1, code, bad);)
         }
-        double e = act.e;
-#pragma unroll
-        for (int j = 1; j <= G; ++j) {
-            const double eh = a.lv.edge[a.level + j], ry = a.lv.ry[a.level + j];
-            if (j < G) {
-                PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kScatterU; ++u) {
-                    bin[u] = (bin[u] << 3) | level_step<ENC, FAST, true>(q[u], m[u], e, eh, ry, cj[u][j - 1], bad);
-                })
-            } else {  // last level: the decoded position is not needed any more
-                PCV_ENC_SWITCH(a.lv.enc[a.level + j], _Pragma("unroll") for (int u = 0; u < kScatterU; ++u) {
-                    bin[u] = (bin[u] << 3) | level_step<ENC, FAST, false>(q[u], m[u], e, eh, ry, cj[u][j - 1], bad);
-                })
-            }
-            e = eh;
-        }
-#pragma unroll
-        for (int u = 0; u < kScatterU; ++u) {
-            const uint32_t i = warp * kWarpItems + (s0 + u) * 32 + lane;
-            const uint32_t lm = lutm[bin[u]];  // local bucket | keep << 16
-            const uint32_t lbv = i < t.count ? (lm & 0xFFFFu) : 0xFFFFu;
-            const int keep = (lm >> 16) & 0xFF;
-            uint64_t c[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                CodeT v = cj[u][0][k];
-                if (G >= 2 && keep == 2) v = cj[u][G >= 2 ? 1 : 0][k];
-                if (G >= 3 && keep == 3) v = cj[u][G >= 3 ? 2 : 0][k];
-                c[k] = (uint64_t)v;
-            }
-            if (lbv != 0xFFFFu) smem_store_rec<WIDE>(srec, i, c, idx[u]);
-            // group the sub-round's lanes by bucket once; sweep B reuses rank / leader / group size
-            const unsigned mask = __match_any_sync(0xffffffffu, lbv);
-            const uint32_t leader = (uint32_t)__ffs(mask) - 1u, gsize = (uint32_t)__popc(mask), rank = (uint32_t)__popc(mask & ((1u << lane) - 1u));
-            sinfo[i] = lbv | (rank << 16) | (leader << 21) | ((gsize - 1u) << 26);
-            if (lbv != 0xFFFFu && lane == (int)leader) atomicAdd(&cnt[warp * nb + lbv], gsize);
-        }
+        const uint64_t c64[3] = {(uint64_t)code[0], (uint64_t)code[1], (uint64_t)code[2]};
+        store_rec<WIDE>(a.rec_out, g, c64, (uint32_t)g);
+        a.col_out[g] = scol[i];
+        a.dig_out[g] = (uint8_t)dig;
     }
     return bad;
 }
 
-template <bool ROOT, bool WIDE, int G>
-__global__ void __launch_bounds__(ScatterCfg<WIDE>::threads, WIDE ? 1 : 2) k_scatter(const __grid_constant__ PassArgs a) {
-    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
-    constexpr int nb = 1 << (3 * G);
-    constexpr int kScatterThreads = ScatterCfg<WIDE>::threads, kScatterWarps = ScatterCfg<WIDE>::warps, kWarpItems = ScatterCfg<WIDE>::warp_items,
-                  kSubRounds = ScatterCfg<WIDE>::sub_rounds;
-    constexpr size_t recsz = ScatterSmem<WIDE>::rec_bytes;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* srec = smem_raw;                                                      // [tile] records (AoS, as in HBM)
-    uint32_t* scol_base = reinterpret_cast<uint32_t*>(srec + (size_t)kTilePoints * recsz);  // [tile + 4] colours
-    uint2* bdst = reinterpret_cast<uint2*>(scol_base + kTilePoints + 4);                 // [nb] {first slot of this tile, sorted start | leaf << 31}
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(bdst + nb);                              // [warps][nb]
-    uint32_t* sinfo = cnt + kScatterWarps * nb;                                          // [tile] bucket | rank | leader | group size | leaf
-    uint32_t* lutm = sinfo + kTilePoints;                                                // [nb] digit -> bucket | keep << 16 | leaf << 24
-    uint8_t* srgb = reinterpret_cast<uint8_t*>(sinfo);                                   // root pass only: rgb bytes of the tile, consumed before sweep A writes sinfo
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + ((ScatterSmem<WIDE>::bytes(nb) - 8) & ~(size_t)7));
-
-    const TileDesc t = tile_of(a, blockIdx.x);
-    const ActiveDesc act = a.d_active[t.active];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // (0) TMA: bulk-copy the tile's records and colours into shared memory while the tables below are set up
-    uint32_t* scol = scol_base;
-    if (!ROOT) {
-        const uint32_t coff = (uint32_t)(t.start & 3);  // the colour source must be 16-byte aligned: start 0..3 entries early
-        scol = scol_base + coff;
-        if (tid == 0) mbar_init(mbar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t rec_bytes = t.count * (uint32_t)recsz;
-            const uint32_t col_bytes = ((coff + t.count) * 4u + 15u) & ~15u;
-            mbar_expect_tx(mbar, rec_bytes + col_bytes);
-            tma_bulk_load(srec, reinterpret_cast<const unsigned char*>(a.rec_in) + t.start * recsz, rec_bytes, mbar);
-            tma_bulk_load(scol_base, a.col_in + (t.start - coff), col_bytes, mbar);
-        }
-    }
-
-    // (1) exclusive prefix of this node's earlier tiles, per digit -> inclusive scan over digits
-    const uint32_t* pfx = a.d_tile_counts + (size_t)blockIdx.x * nb;
-    for (int b = tid; b < nb; b += kScatterThreads) {
-        cnt[b] = pfx[b];
-        lutm[b] = 0xFFFFu;  // digits without points keep an invalid bucket
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const int per = (nb + 31) / 32;
-        const int b0 = lane * per, b1 = min(nb, b0 + per);
-        uint32_t s = 0;
-        for (int b = b0; b < b1; ++b) s += cnt[b];
-        uint32_t incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        uint32_t run = incl - s;
-        for (int b = b0; b < b1; ++b) {
-            run += cnt[b];
-            cnt[b] = run;  // inclusive over digits
-        }
-    }
-    __syncthreads();
-    // (2) per local bucket: destination of this tile's first record
-    for (int lb = tid; lb < nb; lb += kScatterThreads) {
-        const BucketDesc bd = a.d_buckets[(size_t)t.active * nb + lb];
-        uint32_t v = 0;
-        if (bd.b1 != 0) {
-            const uint32_t hi = cnt[bd.b1 - 1], lo = bd.b0 ? cnt[bd.b0 - 1] : 0u;
-            v = (uint32_t)bd.dest + (hi - lo);
-            // every digit of the bucket's range learns (bucket, keep, leaf) in one table entry
-            for (uint32_t d = bd.b0; d < bd.b1; ++d) lutm[d] = (uint32_t)lb | ((uint32_t)bd.keep << 16);
-        }
-        bdst[lb] = make_uint2(v, bd.b1 != 0 && bd.kind ? 0x80000000u : 0u);
-    }
-    __syncthreads();
-    for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
-    if (ROOT) {
-        // stage the tile's rgb bytes with aligned 16-byte loads (3-byte-strided per-thread loads are LSU-hostile)
-        const uint8_t* g0 = a.pts.rgb + 3 * t.start;
-        const uint32_t nbytes = 3 * t.count;
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);  // srgb[mis + k] = g0[k]
-        const uint8_t* ga = g0 - mis;
-        const uint32_t nvec = (mis + nbytes + 15) / 16;
-        for (uint32_t v = tid; v + 1 < nvec; v += kScatterThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldcg(reinterpret_cast<const uint4*>(ga) + v);
-        if (tid < 16) {  // the last vector byte-wise: never read past the array's last byte
-            const uint32_t k = (nvec - 1) * 16 + tid;
-            if (k >= mis && k < mis + nbytes) srgb[k] = __ldg(ga + k);
-        }
-        __syncthreads();
-        // colours of 4 consecutive points are 12 staged bytes: 4 aligned words, funnel-shifted by the misalignment, give
-        // the 4 packed colours with one 16-byte store (instead of 3 byte loads and a store per point inside sweep A)
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(srgb);
-        for (uint32_t k = tid; 4 * k < t.count; k += kScatterThreads) {
-            const uint32_t byte0 = mis + 12 * k, wi = byte0 >> 2, sh = (byte0 & 3) * 8;
-            const uint32_t w0 = w[wi], w1 = w[wi + 1], w2 = w[wi + 2], w3 = w[wi + 3];
-            const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
-            uint4 c;  // a0 = r0 g0 b0 r1 | a1 = g1 b1 r2 g2 | a2 = b2 r3 g3 b3 (little endian)
-            c.x = a0 & 0xFFFFFFu;
-            c.y = (a0 >> 24) | ((a1 & 0xFFFFu) << 8);
-            c.z = (a1 >> 16) | ((a2 & 0xFFu) << 16);
-            c.w = a2 >> 8;
-            reinterpret_cast<uint4*>(scol)[k] = c;
-        }
-    } else {
-        mbar_wait(mbar, 0);  // the staged records / colours have landed
-    }
-    __syncthreads();
-
-    // (3) sweep A (speculatively through the reciprocal division; redone with the IEEE operator if any numerator of
-    // the block was outside the proven range - the codes in shared memory are only replaced by valid lanes, so the
-    // second run must start from the original records: reload them)
-    if (a.lv.fast) {
-        const unsigned bad = a.lv.fast == 2 ? scatter_sweep_a<ROOT, WIDE, G, 2, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt)
-                                            : scatter_sweep_a<ROOT, WIDE, G, 1, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
-        if (__syncthreads_or((int)bad)) {
-            for (int i = tid; i < kScatterWarps * nb; i += kScatterThreads) cnt[i] = 0;
-            if (!ROOT) {  // restore the input records (sweep A overwrote their codes)
-                for (uint32_t i = tid; i < t.count; i += kScatterThreads) {
-                    uint64_t c[3];
-                    uint32_t idx;
-                    load_rec<WIDE>(a.rec_in, t.start + i, c, idx);
-                    smem_store_rec<WIDE>(srec, i, c, idx);
-                }
+template <bool WIDE>
+__global__ void __launch_bounds__(kIngestThreads) k_ingest(const __grid_constant__ IngestArgs a) {
+    __shared__ __align__(16) uint8_t srgb[kRgbStage];
+    __shared__ __align__(16) uint32_t scol[kTilePoints];
+    const int tid = threadIdx.x;
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t start = (uint64_t)tile * kTilePoints;
+        const uint64_t rem = a.pts.n - start;
+        const uint32_t count = (uint32_t)(rem < kTilePoints ? rem : kTilePoints);
+        {
+            const uint8_t* g0 = a.pts.rgb + 3 * start;
+            const uint32_t nbytes = 3 * count;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);  // srgb[mis + k] = g0[k]
+            const uint8_t* ga = g0 - mis;
+            const uint32_t nvec = (mis + nbytes + 15) / 16;
+            for (uint32_t v = tid; v + 1 < nvec; v += kIngestThreads) reinterpret_cast<uint4*>(srgb)[v] = __ldcg(reinterpret_cast<const uint4*>(ga) + v);
+            if (tid < 16) {  // the last vector byte-wise: never read past the array's last byte
+                const uint32_t k = (nvec - 1) * 16 + tid;
+                if (k >= mis && k < mis + nbytes) srgb[k] = __ldg(ga + k);
             }
             __syncthreads();
-            scatter_sweep_a<ROOT, WIDE, G, 0, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
+            // colours of 4 consecutive points are 12 staged bytes: 4 aligned words, funnel-shifted by the misalignment, give
+            // the 4 packed colours with one 16-byte store
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(srgb);
+            for (uint32_t k = tid; 4 * k < count; k += kIngestThreads) {
+                const uint32_t byte0 = mis + 12 * k, wi = byte0 >> 2, sh = (byte0 & 3) * 8;
+                const uint32_t w0 = w[wi], w1 = w[wi + 1], w2 = w[wi + 2], w3 = w[wi + 3];
+                const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+                uint4 c;  // a0 = r0 g0 b0 r1 | a1 = g1 b1 r2 g2 | a2 = b2 r3 g3 b3 (little endian)
+                c.x = a0 & 0xFFFFFFu;
+                c.y = (a0 >> 24) | ((a1 & 0xFFFFu) << 8);
+                c.z = (a1 >> 16) | ((a2 & 0xFFu) << 16);
+                c.w = a2 >> 8;
+                reinterpret_cast<uint4*>(scol)[k] = c;
+            }
             __syncthreads();
         }
-    } else {
-        scatter_sweep_a<ROOT, WIDE, G, 0, CodeT>(a, t, act, warp, lane, srec, sinfo, lutm, cnt);
+        if (a.lv.fast) {
+            const unsigned bad = a.lv.fast == 2 ? ingest_tile<WIDE, 2>(a, start, count, scol) : ingest_tile<WIDE, 1>(a, start, count, scol);
+            if (__syncthreads_or((int)bad)) ingest_tile<WIDE, 0>(a, start, count, scol);  // a numerator outside the proven range: IEEE operator (same stores)
+        } else {
+            ingest_tile<WIDE, 0>(a, start, count, scol);
+        }
         __syncthreads();
     }
-    // (4) sort the tile by bucket inside shared memory (as a permutation) so that the global stores are coalesced runs:
-    //     per-bucket totals -> exclusive scan over the buckets (sorted start of every bucket) -> per-warp offsets
-    for (int lb = tid; lb < nb; lb += kScatterThreads) {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w = 0; w < kScatterWarps; ++w) tot += cnt[w * nb + lb];
-        lutm[lb] = tot;  // the digit table is dead after sweep A
+}
+
+// ------------------------------------------------------------------------------------------------
+// digit histogram of a pass's tiles (1 byte per point) + per-digit prefix over the tiles of every active node
+// ------------------------------------------------------------------------------------------------
+// tile -> active node (written once per pass from the scan chunks): a block learns its tile with two loads instead of a
+// binary search of dependent loads over the active list
+__global__ void k_tile_index(const __grid_constant__ PassArgs a) {
+    const uint32_t nchunks = a.st->pass[a.pass].nchunks;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const ChunkDesc c = a.chunks[ch];
+        for (uint32_t t = threadIdx.x; t < c.ntiles; t += blockDim.x) a.tile_active[c.tile_begin + t] = c.active;
     }
+}
+__device__ __forceinline__ TileDesc tile_lookup(const PassArgs& a, uint32_t tile) {
+    const uint32_t i = a.tile_active[tile];
+    const ActiveDesc& act = a.active[i];
+    const uint64_t o = (uint64_t)(tile - act.tile_begin) * kTilePoints;
+    const uint64_t rem = act.count - o;
+    return TileDesc{act.start + o, (uint32_t)(rem < kTilePoints ? rem : kTilePoints), i};
+}
+
+constexpr int kDigThreads = 128;
+__global__ void __launch_bounds__(kDigThreads) k_dighist(const __grid_constant__ PassArgs a) {
+    __shared__ uint32_t h[kDigThreads / 32][64];
+    const PassState ps = a.st->pass[a.pass];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < ps.ntiles; tile += gridDim.x) {
+        const TileDesc t = tile_lookup(a, tile);
+        for (int b = tid; b < (kDigThreads / 32) * 64; b += kDigThreads) (&h[0][0])[b] = 0;
+        __syncthreads();
+        // aligned 16-byte loads over the covering range, bytes outside [start, start + count) masked
+        const uint64_t lo = t.start, hi = t.start + t.count, base = lo & ~(uint64_t)15;
+        const uint32_t nvec = (uint32_t)((hi - base + 15) >> 4);
+        for (uint32_t v = tid; v < nvec; v += kDigThreads) {
+            const uint64_t p0 = base + 16ull * v;
+            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(a.dig_in + p0));
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint64_t p = p0 + j;
+                if (p >= lo && p < hi) atomicAdd(&h[warp][(ws[j >> 2] >> (8 * (j & 3))) & 63u], 1u);
+            }
+        }
+        __syncthreads();
+        uint32_t* out = a.tile_counts + (size_t)tile * a.nbins;
+        for (int b = tid; b < a.nbins; b += kDigThreads) {
+            uint32_t sacc = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < kDigThreads / 32; ++w8) sacc += h[w8][b];
+            out[b] = sacc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_chunk_sums(const __grid_constant__ PassArgs a) {
+    const uint32_t nchunks = a.st->pass[a.pass].nchunks;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const ChunkDesc c = a.chunks[ch];
+        for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+            uint32_t s = 0;
+            const uint32_t* p = a.tile_counts + (size_t)c.tile_begin * a.nbins + b;
+#pragma unroll 8
+            for (uint32_t t = 0; t < c.ntiles; ++t) s += p[(size_t)t * a.nbins];
+            a.chunk_sums[(size_t)ch * a.nbins + b] = s;
+        }
+    }
+}
+__global__ void k_scan_nodes(const __grid_constant__ PassArgs a) {
+    const uint32_t nactive = a.st->pass[a.pass].nactive;
+    for (uint32_t n = blockIdx.x; n < nactive; n += gridDim.x) {
+        const ActiveDesc act = a.active[n];
+        for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+            uint64_t run = 0;
+            uint32_t* p = a.chunk_sums + (size_t)act.chunk_begin * a.nbins + b;
+            for (uint32_t c = 0; c < act.nchunks; ++c) {
+                uint32_t v = p[(size_t)c * a.nbins];
+                p[(size_t)c * a.nbins] = (uint32_t)run;
+                run += v;
+            }
+            a.node_bins[(size_t)n * a.nbins + b] = run;
+        }
+    }
+}
+__global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
+    const uint32_t nchunks = a.st->pass[a.pass].nchunks;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const ChunkDesc c = a.chunks[ch];
+        for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
+            uint32_t run = a.chunk_sums[(size_t)ch * a.nbins + b];
+            uint32_t* p = a.tile_counts + (size_t)c.tile_begin * a.nbins + b;
+            for (uint32_t t = 0; t < c.ntiles; ++t) {
+                uint32_t v = p[(size_t)t * a.nbins];
+                p[(size_t)t * a.nbins] = run;
+                run += v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan: leaf / split decisions, bucket tables, node table, next pass's active list - one block, no host round trip
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* sh /* [33] */, uint64_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    __syncthreads();  // sh may still be read from the previous call
+    if (lane == 31) sh[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const int per = (nb + 31) / 32;
-        const int b0 = lane * per, b1 = min(nb, b0 + per);
-        uint32_t sum = 0;
-        for (int b = b0; b < b1; ++b) sum += lutm[b];
-        uint32_t incl = sum;
+        uint64_t w = sh[lane], wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            const uint64_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
         }
-        uint32_t run = incl - sum;
-        for (int b = b0; b < b1; ++b) {
-            const uint32_t c = lutm[b];
-            lutm[b] = run;  // exclusive: sorted position of the bucket's first record
-            run += c;
-        }
+        sh[lane] = wi - w;
+        if (lane == 31) sh[32] = wi;
     }
     __syncthreads();
-    for (int lb = tid; lb < nb; lb += kScatterThreads) {
-        uint32_t run = lutm[lb];
-        bdst[lb].y |= run;
-#pragma unroll
-        for (int w = 0; w < kScatterWarps; ++w) {
-            const uint32_t c = cnt[w * nb + lb];
-            cnt[w * nb + lb] = run;
-            run += c;
+    total = sh[32];
+    return incl - v + sh[warp];
+}
+
+__global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ PassArgs a) {
+    __shared__ uint64_t sh[33];
+    __shared__ int32_t s_err;
+    __shared__ uint32_t s_deep;
+    BuildState* st = a.st;
+    const PassState ps = st->pass[a.pass];
+    if (threadIdx.x == 0) {
+        s_err = 0;
+        s_deep = 0;
+    }
+    PlanRun carry;  // global bases of this pass
+    carry.nodes = st->nnodes;
+    carry.actives = 0, carry.tiles = 0, carry.chunks = 0;
+    carry.next_pts = 0;
+    carry.arena_pts = st->arena_used;
+    __syncthreads();
+    int32_t err = 0;
+    uint32_t deepest = 0;
+    for (uint32_t base = 0; base < ps.nactive; base += kPlanThreads) {
+        const uint32_t ai = base + threadIdx.x;
+        PlanRun t{};
+        if (ai < ps.nactive) plan_active<false>(a, ai, t, err, deepest);
+        uint64_t tot[6];
+        PlanRun b;
+        b.nodes = carry.nodes + (uint32_t)block_excl_scan(t.nodes, sh, tot[0]);
+        b.actives = carry.actives + (uint32_t)block_excl_scan(t.actives, sh, tot[1]);
+        b.tiles = carry.tiles + (uint32_t)block_excl_scan(t.tiles, sh, tot[2]);
+        b.chunks = carry.chunks + (uint32_t)block_excl_scan(t.chunks, sh, tot[3]);
+        b.next_pts = carry.next_pts + block_excl_scan(t.next_pts, sh, tot[4]);
+        b.arena_pts = carry.arena_pts + block_excl_scan(t.arena_pts, sh, tot[5]);
+        // capacities are checked on the totals before anything is written (emit guards its own writes as well)
+        if ((uint64_t)carry.nodes + tot[0] > a.cap_nodes || (uint64_t)carry.actives + tot[1] > a.cap_active || (uint64_t)carry.tiles + tot[2] > a.cap_tiles ||
+            (uint64_t)carry.chunks + tot[3] > a.cap_chunks)
+            err = kErrCapacity;
+        if (ai < ps.nactive) {
+            int32_t e2 = 0;
+            uint32_t d2 = 0;
+            plan_active<true>(a, ai, b, e2, d2);
+        }
+        carry.nodes += (uint32_t)tot[0];
+        carry.actives += (uint32_t)tot[1];
+        carry.tiles += (uint32_t)tot[2];
+        carry.chunks += (uint32_t)tot[3];
+        carry.next_pts += tot[4];
+        carry.arena_pts += tot[5];
+    }
+    if (err) atomicMax(&s_err, err);
+    if (deepest) atomicMax(&s_deep, deepest);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool failed = s_err != 0 || st->error != 0;
+        if (s_err && !st->error) st->error = s_err;
+        PassState nx{};
+        if (!failed) {
+            nx.nactive = carry.actives;
+            nx.ntiles = carry.tiles;
+            nx.nchunks = carry.chunks;
+            nx.npoints = carry.next_pts;
+        }
+        st->pass[a.pass + 1] = nx;  // an error stops the following passes: no active nodes
+        st->nnodes = carry.nodes;
+        st->arena_used = carry.arena_pts;
+        if (s_deep > st->deepest_level) st->deepest_level = s_deep;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass: stable multi-way partition of every tile + the next pass's descent, in destination order
+// ------------------------------------------------------------------------------------------------
+// Persistent blocks (16 warps), tiles of 2048 points taken round robin, two shared-memory stages: while the block works on
+// tile i, the TMA unit already fills the other stage with tile i + gridDim (records, colours, digits, the tile's row of the
+// per-digit prefix table and its node's bucket table), so no global-memory latency sits between two tiles.  Warp w owns the
+// contiguous items [128 w, 128 w + 128) of the tile.
+//   stage    five TMA bulk copies per tile (cp.async.bulk global -> shared, completion on the stage's mbarrier), issued by one
+//            thread one tile ahead; that thread also looks up the next tile's node (tile index table + active list) with
+//            loads whose latency is spread over the phases below
+//   rank     per item only the carried digit -> bucket look-up; lanes grouped by bucket with __match_any_sync, per-warp
+//            bucket counts; no arithmetic on positions at all
+//   scan     (one warp) per-bucket totals, exclusive prefix over the buckets (sorted start inside the tile) and over the warps
+//   sort     every warp walks its items in order and writes (item, bucket) at the item's stable sorted position: the tile is
+//            sorted by bucket as a permutation in shared memory
+//   finish   consecutive threads take consecutive sorted positions, i.e. consecutive slots of a destination run: a leaf at
+//            level L+1 stores the carried codes as they are; a destination at level L+2 gets one encode step; a record that
+//            continues is decoded once more and runs the first step (and second digit) of the NEXT pass, whose codes and
+//            digits travel with it.  Threads of a warp share their destination kind except at run boundaries, so the FP64
+//            work is not divergent, and every store is part of a contiguous run (records 16 B, colours 4 B, digits 1 B).
+// The order inside every bucket is the tile order, i.e. input order (stable).
+template <bool WIDE>
+struct PassCfg {
+    static constexpr int threads = 512;
+    static constexpr int warps = threads / 32;
+    static constexpr int warp_items = kTilePoints / warps;  // 128
+    static constexpr int sub_rounds = warp_items / 32;      // 4
+};
+constexpr int kPassBins = 64;
+template <bool WIDE>
+struct PassSmem {
+    static constexpr size_t rec_bytes = WIDE ? 32 : 16;
+    // one stage (everything a tile needs from global memory)
+    static constexpr size_t st_col = (size_t)kTilePoints * rec_bytes;
+    static constexpr size_t st_dig = st_col + ((size_t)kTilePoints + 4) * 4;
+    static constexpr size_t st_pfx = st_dig + (size_t)kTilePoints + 32;
+    static constexpr size_t st_bk = st_pfx + (size_t)kPassBins * 4;
+    static constexpr size_t stage_bytes = (st_bk + (size_t)kPassBins * sizeof(BucketDesc) + 127) & ~(size_t)127;
+    // shared by both stages
+    static constexpr size_t off_perm = 2 * stage_bytes;
+    static constexpr size_t off_cnt = off_perm + (size_t)kTilePoints * 4;
+    static constexpr size_t off_bdst = off_cnt + (size_t)PassCfg<WIDE>::warps * kPassBins * 4;
+    static constexpr size_t off_lutm = off_bdst + (size_t)kPassBins * 16;
+    static constexpr size_t off_desc = off_lutm + (size_t)kPassBins * 4;
+    static constexpr size_t off_nact = off_desc + 2 * 64;  // ActiveDesc of the next tile (cp.async landing zone)
+    static constexpr size_t off_bar = off_nact + 64;
+    static constexpr size_t bytes = off_bar + 16;
+};
+static_assert(2 * PassSmem<false>::bytes + 2048 <= 233472, "two narrow pass blocks must fit one SM (228 KB, 1 KB reserved per block)");
+static_assert(PassSmem<true>::bytes <= 232448, "pass tile exceeds the 227 KB opt-in shared memory of sm_100");
+
+struct PassTile {  // descriptor of a staged tile (shared memory, 64 bytes)
+    double m[3];  // cube min of the active node
+    double e;
+    uint64_t start;
+    uint32_t count, active;
+    uint32_t tile, valid;
+    uint32_t pad[2];
+};
+static_assert(sizeof(PassTile) == 64 && sizeof(ActiveDesc) == 64, "descriptor layout");
+
+// finish one record (see above).  All level constants are plain kernel parameters (PassArgs::e1 ...).
+template <bool WIDE, int FAST>
+__device__ __forceinline__ void finish_record(const PassArgs& a, const double pm[3], uint64_t c[3], unsigned dig, int keep, bool next, unsigned& dig_out,
+                                              unsigned& bad) {
+    typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
+    const unsigned d1 = a.G == 2 ? (dig >> 3) : dig, d2 = dig & 7u;
+    const double e1 = a.e1;
+    double m[3], q[3];
+    // child cube min (node.rs:165-170): x = bit 2, y = bit 1, z = bit 0
+    m[0] = (d1 & 4u) ? pm[0] + e1 : pm[0];
+    m[1] = (d1 & 2u) ? pm[1] + e1 : pm[1];
+    m[2] = (d1 & 1u) ? pm[2] + e1 : pm[2];
+    PCV_ENC_SWITCH(a.enc1, _Pragma("unroll") for (int k = 0; k < 3; ++k) q[k] = decode_axis<ENC>(c[k], m[k], e1);)
+    if (keep == 2) {
+        const double e2 = a.e2, ry2 = a.ry2;
+        m[0] = (d2 & 4u) ? m[0] + e2 : m[0];
+        m[1] = (d2 & 2u) ? m[1] + e2 : m[1];
+        m[2] = (d2 & 1u) ? m[2] + e2 : m[2];
+        if (next) {
+            PCV_ENC_SWITCH(a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) {
+                c[k] = encode_axis<ENC, FAST>(q[k], m[k], e2, ry2, bad);
+                q[k] = decode_axis<ENC>(c[k], m[k], e2);
+            })
+        } else {
+            PCV_ENC_SWITCH(a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) c[k] = encode_axis<ENC, FAST>(q[k], m[k], e2, ry2, bad);)
+            return;
         }
     }
-    // every thread takes the sweep-A notes of its items into registers: the permutation is built in the same array
-    uint32_t info[kSubRounds];
-#pragma unroll
-    for (int s = 0; s < kSubRounds; ++s) info[s] = sinfo[warp * kWarpItems + s * 32 + lane];
-    __syncthreads();
-    // (5) sweep B1: stable sorted position of every item (warp by warp, sub-round by sub-round, rank inside the group)
-    uint32_t* perm = sinfo;  // [tile] item index | bucket << 12, in sorted order
-#pragma unroll
-    for (int s = 0; s < kSubRounds; ++s) {
-        const uint32_t i = warp * kWarpItems + s * 32 + lane;
-        const uint32_t lbv = info[s] & 0xFFFFu, rank = (info[s] >> 16) & 31u, gsize = ((info[s] >> 26) & 31u) + 1u;
-        const int leader = (int)((info[s] >> 21) & 31u);
-        uint32_t old = 0;
-        if (lane == leader && lbv != 0xFFFFu) {
-            old = cnt[warp * nb + lbv];
-            cnt[warp * nb + lbv] = old + gsize;
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        if (lbv != 0xFFFFu) perm[old + rank] = i | (lbv << 12);
-        __syncwarp();
+    if (!next) return;  // leaf at level L+1: the carried codes are the node's codes
+    // first step of the next pass from the node at level Lb = L + G (+ the second digit when that pass resolves two levels)
+    const double eb = a.eb, eh = a.eh, ryh = a.ryh;
+    CodeT code[3];
+    unsigned d;
+    if (a.Gn == 2) {
+        PCV_ENC_SWITCH(a.ench, d = level_step<ENC, FAST, true>(q, m, eb, eh, ryh, code, bad);)
+        d = (d << 3) | level_digit(q, m, eh);
+    } else {
+        PCV_ENC_SWITCH(a.ench, d = level_step<ENC, FAST, false>(q, m, eb, eh, ryh, code, bad);)
     }
-    __syncthreads();
-    // (6) sweep B2: consecutive threads store consecutive records of a bucket's run (next pass segment or leaf arena)
-    for (uint32_t p = tid; p < t.count; p += kScatterThreads) {
+    c[0] = (uint64_t)code[0], c[1] = (uint64_t)code[1], c[2] = (uint64_t)code[2];
+    dig_out = d;
+}
+
+template <bool WIDE, int FAST>
+__device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTile& pt, const unsigned char* srec, const uint32_t* scol, const uint8_t* sdig,
+                                                const uint32_t* perm, const uint4* bdst) {
+    unsigned bad = 0;
+    const double pm[3] = {pt.m[0], pt.m[1], pt.m[2]};
+    const uint32_t count = pt.count;
+    for (uint32_t p = threadIdx.x; p < count; p += PassCfg<WIDE>::threads) {
         const uint32_t e = perm[p], i = e & (kTilePoints - 1), lb = e >> 12;
-        const uint2 bd = bdst[lb];
-        const bool leaf = (bd.y >> 31) != 0;
-        const uint32_t dst = bd.x + (p - (bd.y & 0x7FFFFFFFu));
-        uint64_t c64[3];
+        const uint4 bd = bdst[lb];  // x: slot of the bucket's first record of this tile, y: sorted start, z: keep, w: 1 = leaf arena
+        const bool next = bd.w == 0;
+        const uint32_t dst = bd.x + (p - bd.y);
+        uint64_t c[3];
         uint32_t idx;
-        smem_load_rec<WIDE>(srec, i, c64, idx);
-        store_rec<WIDE>(leaf ? a.arena : a.rec_next, dst, c64, idx);
-        (leaf ? a.col_arena : a.col_next)[dst] = scol[i];
+        smem_load_rec<WIDE>(srec, i, c, idx);
+        unsigned dig_out = 0;
+        if (next || bd.z == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], (int)bd.z, next, dig_out, bad);
+        if (FAST == 1 && bad) continue;  // the block repeats the sweep with the IEEE operator
+        store_rec<WIDE>(next ? a.rec_next : a.arena, dst, c, idx);
+        (next ? a.col_next : a.col_arena)[dst] = scol[i];
+        if (next) a.dig_next[dst] = (uint8_t)dig_out;
+    }
+    return bad;
+}
+
+// Stage a tile: descriptor + the five bulk copies (one thread).  Sources must be 16-byte aligned: the colour / digit copies
+// start up to 3 / 15 entries early.
+template <bool WIDE>
+__device__ __forceinline__ void pass_stage_tile(const PassArgs& a, uint32_t tile, const ActiveDesc& act, uint32_t active, unsigned char* stage, PassTile* desc,
+                                                uint64_t* bar) {
+    constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
+    const uint64_t o = (uint64_t)(tile - act.tile_begin) * kTilePoints;
+    const uint64_t rem = act.count - o;
+    PassTile d;
+    d.m[0] = act.m[0], d.m[1] = act.m[1], d.m[2] = act.m[2];
+    d.e = act.e;
+    d.start = act.start + o;
+    d.count = (uint32_t)(rem < kTilePoints ? rem : kTilePoints);
+    d.active = active;
+    d.tile = tile;
+    d.valid = 1;
+    d.pad[0] = d.pad[1] = 0;
+    *desc = d;
+    const uint32_t coff = (uint32_t)(d.start & 3), doff = (uint32_t)(d.start & 15);
+    const uint32_t rec_bytes = d.count * (uint32_t)recsz;
+    const uint32_t col_bytes = ((coff + d.count) * 4u + 15u) & ~15u;
+    const uint32_t dig_bytes = (doff + d.count + 15u) & ~15u;
+    const uint32_t pfx_bytes = (uint32_t)a.nbins * 4u, bk_bytes = (uint32_t)a.nbins * (uint32_t)sizeof(BucketDesc);
+    mbar_expect_tx(bar, rec_bytes + col_bytes + dig_bytes + pfx_bytes + bk_bytes);
+    tma_bulk_load(stage, reinterpret_cast<const unsigned char*>(a.rec_in) + d.start * recsz, rec_bytes, bar);
+    tma_bulk_load(stage + PassSmem<WIDE>::st_col, a.col_in + (d.start - coff), col_bytes, bar);
+    tma_bulk_load(stage + PassSmem<WIDE>::st_dig, a.dig_in + (d.start - doff), dig_bytes, bar);
+    tma_bulk_load(stage + PassSmem<WIDE>::st_pfx, a.tile_counts + (size_t)tile * a.nbins, pfx_bytes, bar);
+    tma_bulk_load(stage + PassSmem<WIDE>::st_bk, a.buckets + (size_t)active * a.nbins, bk_bytes, bar);
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(const __grid_constant__ PassArgs a) {
+    constexpr int nbmax = kPassBins;
+    constexpr int kThreads = PassCfg<WIDE>::threads, kWarps = PassCfg<WIDE>::warps, kWarpItems = PassCfg<WIDE>::warp_items, kSubRounds = PassCfg<WIDE>::sub_rounds;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* perm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_perm);  // [tile] item | bucket << 12, sorted
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_cnt);    // [warps][nb]
+    uint4* bdst = reinterpret_cast<uint4*>(smem_raw + PassSmem<WIDE>::off_bdst);        // [nb]
+    uint32_t* lutm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_lutm);  // [nb] digit -> bucket (0xFFFF: none)
+    PassTile* descs = reinterpret_cast<PassTile*>(smem_raw + PassSmem<WIDE>::off_desc); // [2]
+    ActiveDesc* snact = reinterpret_cast<ActiveDesc*>(smem_raw + PassSmem<WIDE>::off_nact);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + PassSmem<WIDE>::off_bar);   // [2]
+
+    const PassState ps = a.st->pass[a.pass];
+    const int nb = a.nbins;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (blockIdx.x >= ps.ntiles) return;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        const uint32_t act0 = a.tile_active[blockIdx.x];
+        pass_stage_tile<WIDE>(a, blockIdx.x, a.active[act0], act0, smem_raw, &descs[0], &mbar[0]);
+    }
+    __syncthreads();
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < ps.ntiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it & 1u, par = (it >> 1) & 1u;
+        unsigned char* stage = smem_raw + (size_t)s * PassSmem<WIDE>::stage_bytes;
+        const unsigned char* srec = stage;
+        const PassTile& pt = descs[s];  // stays in shared memory (broadcast reads)
+        const uint32_t* scol = reinterpret_cast<const uint32_t*>(stage + PassSmem<WIDE>::st_col) + (uint32_t)(pt.start & 3);
+        const uint8_t* sdig = stage + PassSmem<WIDE>::st_dig + (uint32_t)(pt.start & 15);
+        const uint32_t* spfx = reinterpret_cast<const uint32_t*>(stage + PassSmem<WIDE>::st_pfx);
+        const BucketDesc* sbk = reinterpret_cast<const BucketDesc*>(stage + PassSmem<WIDE>::st_bk);
+        // the next tile of this block: its node is looked up by one thread, the loads are consumed two phases later
+        const uint32_t ntile = tile + gridDim.x;
+        const bool stage_next = tid == 0 && ntile < ps.ntiles;
+        uint32_t nact = 0;
+        if (stage_next) nact = a.tile_active[ntile];
+
+        mbar_wait(&mbar[s], par);  // this tile's records / colours / digits / tables have landed
+        // (1) bucket tables: inclusive scan over digits of the tile's prefix row (exclusive prefix of the node's earlier tiles),
+        // then per bucket the destination of this tile's first record, what the destination stores and where it lives (warp 0)
+        if (warp == 0) {
+            const int per = (nb + 31) / 32;
+            const int b0 = lane * per, b1 = min(nb, b0 + per);
+            uint32_t sacc = 0;
+            for (int b = b0; b < b1; ++b) sacc += spfx[b];
+            uint32_t incl = sacc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            uint32_t run = incl - sacc;
+            for (int b = b0; b < b1; ++b) {
+                run += spfx[b];
+                lutm[b] = run;  // inclusive over digits (temporarily in lutm)
+            }
+            __syncwarp();
+            uint32_t v[2] = {0, 0};
+            BucketDesc bd[2];
+            for (int j = 0; j < 2; ++j) {
+                const int lb = lane + 32 * j;
+                if (lb < nb) {
+                    bd[j] = sbk[lb];
+                    if (bd[j].b1 != 0) v[j] = (uint32_t)bd[j].dest + (lutm[bd[j].b1 - 1] - (bd[j].b0 ? lutm[bd[j].b0 - 1] : 0u));
+                }
+            }
+            __syncwarp();
+            for (int b = lane; b < nb; b += 32) lutm[b] = 0xFFFFu;  // digits without points keep an invalid bucket
+            __syncwarp();
+            for (int j = 0; j < 2; ++j) {
+                const int lb = lane + 32 * j;
+                if (lb < nb) {
+                    if (bd[j].b1 != 0)
+                        for (uint32_t d = bd[j].b0; d < bd[j].b1; ++d) lutm[d] = (uint32_t)lb;  // every digit of the bucket's range learns its bucket
+                    bdst[lb] = make_uint4(v[j], 0u, bd[j].keep, bd[j].b1 != 0 && bd[j].kind ? 1u : 0u);
+                }
+            }
+        }
+        for (int i = tid; i < kWarps * nbmax; i += kThreads) cnt[i] = 0;
+        __syncthreads();
+
+        // (2) rank: bucket of every item from its carried digit; lanes of a sub-round grouped by bucket once
+        uint32_t info[kSubRounds];
+        {
+            uint32_t lbv[kSubRounds];
+            unsigned mask[kSubRounds];
+            const uint32_t count = pt.count;
+#pragma unroll
+            for (int r = 0; r < kSubRounds; ++r) {
+                const uint32_t i = warp * kWarpItems + r * 32 + lane;
+                lbv[r] = 0xFFFFu;
+                if (i < count) lbv[r] = lutm[sdig[i] & (uint32_t)(nb - 1)];
+            }
+#pragma unroll
+            for (int r = 0; r < kSubRounds; ++r) mask[r] = __match_any_sync(0xffffffffu, lbv[r]);  // independent: their latencies overlap
+#pragma unroll
+            for (int r = 0; r < kSubRounds; ++r) {
+                const uint32_t leader = (uint32_t)__ffs(mask[r]) - 1u, gsize = (uint32_t)__popc(mask[r]), rank = (uint32_t)__popc(mask[r] & ((1u << lane) - 1u));
+                info[r] = lbv[r] | (rank << 16) | (leader << 21) | ((gsize - 1u) << 26);
+                if (lbv[r] != 0xFFFFu && lane == (int)leader) cnt[warp * nbmax + lbv[r]] += gsize;  // one leader per bucket inside the warp: no conflict
+                __syncwarp();
+            }
+        }
+        if (stage_next) {  // the next tile's node descriptor: asynchronous 16-byte copies, consumed after the sort phase
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.active + nact);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<unsigned char*>(snact) + 16 * k)), "l"(src + 16 * k) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        __syncthreads();
+        // (3) per-bucket totals -> exclusive scan over the buckets (sorted start of every bucket) -> per-warp offsets (warp 0)
+        if (warp == 0) {
+            uint32_t tot[2] = {0, 0};
+            for (int j = 0; j < 2; ++j) {
+                const int lb = lane + 32 * j;
+                if (lb < nb) {
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) tot[j] += cnt[w * nbmax + lb];
+                }
+            }
+            // buckets are numbered lane + 32 j: scan j = 0 over the lanes, then j = 1 on top of its total
+            uint32_t excl[2];
+            uint32_t carry = 0;
+            for (int j = 0; j < 2; ++j) {
+                uint32_t incl = tot[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                excl[j] = carry + incl - tot[j];
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            for (int j = 0; j < 2; ++j) {
+                const int lb = lane + 32 * j;
+                if (lb < nb) {
+                    uint32_t run = excl[j];
+                    bdst[lb].y = run;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) {
+                        const uint32_t c = cnt[w * nbmax + lb];
+                        cnt[w * nbmax + lb] = run;
+                        run += c;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (4) sort: stable sorted position of every item (warp by warp, sub-round by sub-round, rank inside the group)
+#pragma unroll
+        for (int r = 0; r < kSubRounds; ++r) {
+            const uint32_t i = warp * kWarpItems + r * 32 + lane;
+            const uint32_t lbv = info[r] & 0xFFFFu, rank = (info[r] >> 16) & 31u, gsize = ((info[r] >> 26) & 31u) + 1u;
+            const int leader = (int)((info[r] >> 21) & 31u);
+            uint32_t old = 0;
+            if (lane == leader && lbv != 0xFFFFu) {
+                old = cnt[warp * nbmax + lbv];
+                cnt[warp * nbmax + lbv] = old + gsize;
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            if (lbv != 0xFFFFu) perm[old + rank] = i | (lbv << 12);
+            __syncwarp();
+        }
+        // the other stage was last read by the previous iteration (which ended in a barrier): refill it now, so that the
+        // copies run under this tile's finish sweep
+        if (stage_next) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            pass_stage_tile<WIDE>(a, ntile, *snact, nact, smem_raw + (size_t)(s ^ 1u) * PassSmem<WIDE>::stage_bytes, &descs[s ^ 1u], &mbar[s ^ 1u]);
+        }
+        __syncthreads();
+        // (5) finish + store in destination order (speculatively through the reciprocal division; repeated with the IEEE
+        // operator if any numerator of the block was outside the proven range - the stores are idempotent)
+        if (a.fast) {
+            const unsigned bad = a.fast == 2 ? pass_finish<WIDE, 2>(a, pt, srec, scol, sdig, perm, bdst) : pass_finish<WIDE, 1>(a, pt, srec, scol, sdig, perm, bdst);
+            if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
+        } else {
+            pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
+        }
+        __syncthreads();  // the stage, perm and the tables are reused
     }
 }
 
@@ -833,7 +962,7 @@ struct CudaBackend : Backend {
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel timing (CUDA events on the launching stream around every launch)
-    enum { K_BBOX = 0, K_HIST, K_SCAN, K_SCATTER, K_PLACE, K_PLY, K_COUNT };
+    enum { K_BBOX = 0, K_INGEST, K_DIGHIST, K_SCAN, K_PLAN, K_PASS, K_PLACE, K_PLY, K_COUNT };
     struct KStat {
         uint64_t launches = 0, bytes = 0;
         double ms = 0;
@@ -844,11 +973,12 @@ struct CudaBackend : Backend {
         int k;
         cudaEvent_t e0, e1;
         uint64_t bytes;
+        int pass;  // split-phase kernels: their byte counts are filled in once the pass's live point count is known
     };
     std::vector<Pending> pending;
-    void prof_begin(int k, uint64_t bytes) {
+    void prof_begin(int k, uint64_t bytes, int pass = -1) {
         if (!profile) return;
-        Pending p{k, nullptr, nullptr, bytes};
+        Pending p{k, nullptr, nullptr, bytes, pass};
         cudaEventCreate(&p.e0);
         cudaEventCreate(&p.e1);
         cudaEventRecord(p.e0, stream);
@@ -930,94 +1060,75 @@ struct CudaBackend : Backend {
     }
     void mark(int what) override { cudaEventRecord(ev[what], stream); }
 
-    template <bool ROOT, bool WIDE, int G>
-    static void allow_smem() {
-        cudaFuncSetAttribute(k_scatter<ROOT, WIDE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<WIDE>::bytes(1 << (3 * G)));
+    void zero(void* d, size_t bytes) override {
+        if (bytes) PCV_CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream));
     }
     static void allow_smem_all() {
-        allow_smem<false, false, 1>(), allow_smem<false, false, 2>(), allow_smem<false, false, 3>();
-        allow_smem<true, false, 1>(), allow_smem<true, false, 2>(), allow_smem<true, false, 3>();
-        allow_smem<false, true, 1>(), allow_smem<false, true, 2>(), allow_smem<false, true, 3>();
-        allow_smem<true, true, 1>(), allow_smem<true, true, 2>(), allow_smem<true, true, 3>();
-    }
-
-    template <bool ROOT, bool WIDE>
-    void launch_hist(const PassArgs& a, size_t sm) {
-        if (a.G == 1)
-            k_hist<ROOT, WIDE, 1><<<a.ntiles, 256, sm, stream>>>(a);
-        else if (a.G == 2)
-            k_hist<ROOT, WIDE, 2><<<a.ntiles, 256, sm, stream>>>(a);
-        else
-            k_hist<ROOT, WIDE, 3><<<a.ntiles, 256, sm, stream>>>(a);
+        cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
+        cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
     }
     // prefetch distance = blocks resident at once (SMs x blocks per SM); 0 disables (PCV_NO_PREFETCH=1 for experiments)
     int sms = 0;
     bool no_prefetch = false;
-    uint32_t resident(int blocks_per_sm) {
+    int sm_count() {
         if (!sms) {
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             no_prefetch = std::getenv("PCV_NO_PREFETCH") != nullptr;
         }
-        return no_prefetch ? 0u : (uint32_t)(sms * blocks_per_sm);
+        return sms;
     }
-    void hist(const PassArgs& a) override {
-        const size_t sm = (size_t)a.nbins * 4;
+    uint32_t resident(int blocks_per_sm) { return (sm_count(), no_prefetch) ? 0u : (uint32_t)(sms * blocks_per_sm); }
+
+    void ingest(const IngestArgs& a) override {
+        const uint32_t grid = std::min<uint32_t>(a.ntiles, (uint32_t)sm_count() * 32u);
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
-        prof_begin(K_HIST, a.npoints * (a.root ? 24 : rec));
-        if (a.root) {
-            if (a.wide)
-                launch_hist<true, true>(a, sm);
-            else
-                launch_hist<true, false>(a, sm);
-        } else {
-            if (a.wide)
-                launch_hist<false, true>(a, sm);
-            else
-                launch_hist<false, false>(a, sm);
-        }
-        prof_end();
-        ++launches;
-        PCV_CUDA_CHECK(cudaGetLastError());
-    }
-    void scan(const PassArgs& a) override {
-        const int th = a.nbins < 32 ? 32 : (a.nbins > 512 ? 512 : a.nbins);
-        prof_begin(K_SCAN, (uint64_t)a.ntiles * a.nbins * 12);
-        k_scan_chunk_sums<<<a.nchunks, th, 0, stream>>>(a);
-        k_scan_nodes<<<a.nactive, th, 0, stream>>>(a);
-        k_scan_tiles<<<a.nchunks, th, 0, stream>>>(a);
-        prof_end();
-        launches += 3;
-        PCV_CUDA_CHECK(cudaGetLastError());
-    }
-    template <bool ROOT, bool WIDE>
-    void launch_scatter(const PassArgs& a, size_t sm) {
-        if (a.G == 1)
-            k_scatter<ROOT, WIDE, 1><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
-        else if (a.G == 2)
-            k_scatter<ROOT, WIDE, 2><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
+        prof_begin(K_INGEST, a.pts.n * (27 + rec + 4 + 1));
+        if (a.wide)
+            k_ingest<true><<<grid, kIngestThreads, 0, stream>>>(a);
         else
-            k_scatter<ROOT, WIDE, 3><<<a.ntiles, ScatterCfg<WIDE>::threads, sm, stream>>>(a);
-    }
-    void scatter(const PassArgs& a) override {
-        const size_t sm = a.wide ? ScatterSmem<true>::bytes(a.nbins) : ScatterSmem<false>::bytes(a.nbins);
-        const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
-        prof_begin(K_SCATTER, a.npoints * ((a.root ? 27 : rec + 4) + rec + 4));
-        if (a.root) {
-            if (a.wide)
-                launch_scatter<true, true>(a, sm);
-            else
-                launch_scatter<true, false>(a, sm);
-        } else {
-            if (a.wide)
-                launch_scatter<false, true>(a, sm);
-            else
-                launch_scatter<false, false>(a, sm);
-        }
+            k_ingest<false><<<grid, kIngestThreads, 0, stream>>>(a);
         prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    // One pass, enqueued without any host synchronisation: live sizes come from the device-resident BuildState, grids are
+    // fixed (persistent / grid-stride) and blocks beyond the live counts exit.
+    void pass(const PassArgs& a) override {
+        const int nsm = sm_count();
+        const int th = a.nbins < 32 ? 32 : a.nbins;
+        prof_begin(K_DIGHIST, 0, a.pass);
+        k_tile_index<<<std::min<uint32_t>(a.cap_chunks, 1024u), 256, 0, stream>>>(a);
+        k_dighist<<<nsm * 16, kDigThreads, 0, stream>>>(a);
+        prof_end();
+        prof_begin(K_SCAN, 0, a.pass);
+        k_scan_chunk_sums<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
+        k_scan_nodes<<<std::min<uint32_t>(a.cap_active, 2048u), th, 0, stream>>>(a);
+        k_scan_tiles<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
+        prof_end();
+        prof_begin(K_PLAN, 0, a.pass);
+        k_plan<<<1, kPlanThreads, 0, stream>>>(a);
+        prof_end();
+        prof_begin(K_PASS, 0, a.pass);
+        if (a.wide)
+            k_pass<true><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)nsm), PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
+        else
+            k_pass<false><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)nsm * 2u), PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
+        prof_end();
+        launches += 7;
+        pass_wide = a.wide;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    bool pass_wide = false;
+    void pass_points(int pass, uint64_t npoints, uint64_t leaf_points) override {
+        const uint64_t rec = pass_wide ? sizeof(RecW) : sizeof(RecN);
+        for (auto& p : pending) {
+            if (p.pass != pass || p.bytes != 0) continue;
+            if (p.k == K_DIGHIST) p.bytes = npoints;
+            if (p.k == K_SCAN) p.bytes = (npoints / kTilePoints + 1) * 64 * 12;
+            if (p.k == K_PASS) p.bytes = npoints * (rec + 4 + 1) + (npoints - leaf_points) * (rec + 4 + 1) + leaf_points * (rec + 4);
+        }
     }
     void place(const PlaceArgs& a_in) override {
         if (a_in.ntiles == 0) return;

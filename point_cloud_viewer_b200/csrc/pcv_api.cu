@@ -361,7 +361,7 @@ int pcv_kernel_stats(pcv_ctx* c, pcv_kernel_stat* out, uint32_t cap, uint32_t* n
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->be->prof_collect();
-    static const char* names[CudaBackend::K_COUNT] = {"k_bbox", "k_hist", "k_scan", "k_scatter", "k_place", "k_ply_unpack"};
+    static const char* names[CudaBackend::K_COUNT] = {"k_bbox", "k_ingest", "k_dighist", "k_scan", "k_plan", "k_pass", "k_place", "k_ply_unpack"};
     uint32_t n = 0;
     for (int k = 0; k < CudaBackend::K_COUNT; ++k) {
         if (n < cap && out) {

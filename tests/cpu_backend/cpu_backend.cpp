@@ -38,122 +38,170 @@ struct CpuBackend : Backend {
             r.c[0] = (uint32_t)c[0], r.c[1] = (uint32_t)c[1], r.c[2] = (uint32_t)c[2], r.idx = idx;
         }
     }
-    static void load_position(const PassArgs& a, const TileDesc& t, const ActiveDesc& act, uint32_t i, double q[3], uint32_t& idx) {
-        const uint64_t g = t.start + i;
-        if (a.root) {
-            q[0] = a.pts.x[g * a.pts.stride];
-            q[1] = a.pts.y[g * a.pts.stride];
-            q[2] = a.pts.z[g * a.pts.stride];
-            idx = (uint32_t)g;
-        } else {
-            uint64_t c[3];
-            load_rec(a.rec_in, g, a.wide, c, idx);
-            for (int k = 0; k < 3; ++k)
-                q[k] = a.lv.fast ? decode1_fast(c[k], act.m[k], act.e, a.lv.enc[a.level]) : decode1(c[k], act.m[k], act.e, a.lv.enc[a.level]);
+    void zero(void* d, size_t b) override { std::memset(d, 0, b); }
+
+    // k_ingest: first step of the chain from the raw position, digits of the first pass
+    void ingest(const IngestArgs& a) override {
+        for (uint64_t g = 0; g < a.pts.n; ++g) {
+            double q[3] = {a.pts.x[g * a.pts.stride], a.pts.y[g * a.pts.stride], a.pts.z[g * a.pts.stride]};
+            double m[3] = {a.root_min[0], a.root_min[1], a.root_min[2]};
+            Step s = a.lv.fast ? descend_fast(q, m, a.lv.edge[0], a.lv.edge[1], a.lv.ry[1], a.lv.enc[1]) : descend(q, m, a.lv.edge[0], a.lv.edge[1], a.lv.enc[1]);
+            unsigned dig = s.digit;
+            if (a.G0 == 2) {
+                double q2[3] = {q[0], q[1], q[2]}, m2[3] = {m[0], m[1], m[2]};
+                Step s2 = a.lv.fast ? descend_fast(q2, m2, a.lv.edge[1], a.lv.edge[2], a.lv.ry[2], a.lv.enc[2]) : descend(q2, m2, a.lv.edge[1], a.lv.edge[2], a.lv.enc[2]);
+                dig = (dig << 3) | s2.digit;
+            }
+            store_rec(a.rec_out, g, a.wide, s.code, (uint32_t)g);
+            a.col_out[g] = (uint32_t)a.pts.rgb[3 * g] | ((uint32_t)a.pts.rgb[3 * g + 1] << 8) | ((uint32_t)a.pts.rgb[3 * g + 2] << 16);
+            a.dig_out[g] = (uint8_t)dig;
         }
-    }
-    static uint32_t load_colour(const PassArgs& a, uint64_t g) {
-        if (a.root) return (uint32_t)a.pts.rgb[3 * g] | ((uint32_t)a.pts.rgb[3 * g + 1] << 8) | ((uint32_t)a.pts.rgb[3 * g + 2] << 16);
-        return a.col_in[g];
-    }
-    static unsigned run_chain(const PassArgs& a, const ActiveDesc& act, double q[3], uint64_t cj[3][3]) {
-        double m[3] = {act.m[0], act.m[1], act.m[2]}, e = act.e;
-        unsigned bin = 0;
-        for (int j = 1; j <= a.G; ++j) {
-            const double eh = a.lv.edge[a.level + j];
-            Step s = a.lv.fast ? descend_fast(q, m, e, eh, a.lv.ry[a.level + j], a.lv.enc[a.level + j]) : descend(q, m, e, eh, a.lv.enc[a.level + j]);
-            bin = (bin << 3) | s.digit;
-            e = eh;
-            for (int k = 0; k < 3; ++k) cj[j - 1][k] = s.code[k];
-        }
-        return bin;
     }
 
-    void hist(const PassArgs& a) override {
-        for (uint32_t b = 0; b < a.ntiles; ++b) {
-            const TileDesc t = tile_of(a, b);
-            const ActiveDesc act = a.d_active[t.active];
-            uint32_t* out = a.d_tile_counts + (size_t)b * a.nbins;
-            for (int k = 0; k < a.nbins; ++k) out[k] = 0;
-            for (uint32_t i = 0; i < t.count; ++i) {
-                double q[3];
-                uint32_t idx;
-                uint64_t cj[3][3];
-                load_position(a, t, act, i, q, idx);
-                out[run_chain(a, act, q, cj)]++;
-            }
+    // k_dighist + k_scan_* + k_plan + k_pass of one pass, sequentially, over the same device-resident state
+    void pass(const PassArgs& a) override {
+        BuildState* st = a.st;
+        const PassState ps = st->pass[a.pass];
+        const int nb = a.nbins;
+        // digit histogram per tile
+        for (uint32_t b = 0; b < ps.ntiles; ++b) {
+            const TileDesc t = tile_of(a.active, ps.nactive, b);
+            uint32_t* out = a.tile_counts + (size_t)b * nb;
+            for (int k = 0; k < nb; ++k) out[k] = 0;
+            for (uint32_t i = 0; i < t.count; ++i) out[a.dig_in[t.start + i] & 63]++;
         }
-    }
-    void scan(const PassArgs& a) override {
-        for (uint32_t ch = 0; ch < a.nchunks; ++ch) {
-            const ChunkDesc c = a.d_chunks[ch];
-            for (int b = 0; b < a.nbins; ++b) {
+        // scan
+        for (uint32_t ch = 0; ch < ps.nchunks; ++ch) {
+            const ChunkDesc c = a.chunks[ch];
+            for (int b = 0; b < nb; ++b) {
                 uint32_t s = 0;
-                for (uint32_t t = 0; t < c.ntiles; ++t) s += a.d_tile_counts[(size_t)(c.tile_begin + t) * a.nbins + b];
-                a.d_chunk_sums[(size_t)ch * a.nbins + b] = s;
+                for (uint32_t t = 0; t < c.ntiles; ++t) s += a.tile_counts[(size_t)(c.tile_begin + t) * nb + b];
+                a.chunk_sums[(size_t)ch * nb + b] = s;
             }
         }
-        for (uint32_t n = 0; n < a.nactive; ++n) {
-            const ActiveDesc act = a.d_active[n];
-            for (int b = 0; b < a.nbins; ++b) {
+        for (uint32_t n = 0; n < ps.nactive; ++n) {
+            const ActiveDesc act = a.active[n];
+            for (int b = 0; b < nb; ++b) {
                 uint64_t run = 0;
                 for (uint32_t c = 0; c < act.nchunks; ++c) {
-                    uint32_t& v = a.d_chunk_sums[(size_t)(act.chunk_begin + c) * a.nbins + b];
+                    uint32_t& v = a.chunk_sums[(size_t)(act.chunk_begin + c) * nb + b];
                     uint32_t old = v;
                     v = (uint32_t)run;
                     run += old;
                 }
-                a.d_node_bins[(size_t)n * a.nbins + b] = run;
+                a.node_bins[(size_t)n * nb + b] = run;
             }
         }
-        for (uint32_t ch = 0; ch < a.nchunks; ++ch) {
-            const ChunkDesc c = a.d_chunks[ch];
-            for (int b = 0; b < a.nbins; ++b) {
-                uint32_t run = a.d_chunk_sums[(size_t)ch * a.nbins + b];
+        for (uint32_t ch = 0; ch < ps.nchunks; ++ch) {
+            const ChunkDesc c = a.chunks[ch];
+            for (int b = 0; b < nb; ++b) {
+                uint32_t run = a.chunk_sums[(size_t)ch * nb + b];
                 for (uint32_t t = 0; t < c.ntiles; ++t) {
-                    uint32_t& v = a.d_tile_counts[(size_t)(c.tile_begin + t) * a.nbins + b];
+                    uint32_t& v = a.tile_counts[(size_t)(c.tile_begin + t) * nb + b];
                     uint32_t old = v;
                     v = run;
                     run += old;
                 }
             }
         }
-    }
-    void scatter(const PassArgs& a) override {
-        const int nb = a.nbins;
-        std::vector<uint32_t> incl(nb), base(nb);
-        std::vector<uint16_t> meta(nb);
-        for (uint32_t blk = 0; blk < a.ntiles; ++blk) {
-            const TileDesc t = tile_of(a, blk);
-            const ActiveDesc act = a.d_active[t.active];
-            const uint32_t* pfx = a.d_tile_counts + (size_t)blk * nb;
-            uint32_t run = 0;
+        // plan (the product's planner function, one active node after the other)
+        PlanRun run{};
+        run.nodes = st->nnodes;
+        run.arena_pts = st->arena_used;
+        int32_t err = 0;
+        uint32_t deepest = st->deepest_level;
+        for (uint32_t ai = 0; ai < ps.nactive; ++ai) {
+            PlanRun cnt{};
+            plan_active<false>(a, ai, cnt, err, deepest);
+            if ((uint64_t)run.nodes + cnt.nodes > a.cap_nodes || (uint64_t)run.actives + cnt.actives > a.cap_active || (uint64_t)run.tiles + cnt.tiles > a.cap_tiles ||
+                (uint64_t)run.chunks + cnt.chunks > a.cap_chunks)
+                err = kErrCapacity;
+            int32_t e2 = 0;
+            uint32_t d2 = 0;
+            plan_active<true>(a, ai, run, e2, d2);  // emit advances the running bases by exactly the node's demand
+        }
+        if (err && !st->error) st->error = err;
+        PassState nx{};
+        if (!st->error) {
+            nx.nactive = run.actives;
+            nx.ntiles = run.tiles;
+            nx.nchunks = run.chunks;
+            nx.npoints = run.next_pts;
+        }
+        st->pass[a.pass + 1] = nx;
+        st->nnodes = run.nodes;
+        st->arena_used = run.arena_pts;
+        st->deepest_level = deepest;
+        if (st->error) return;
+        // partition + the next pass's descent (k_pass), tile by tile in tile order == stable order
+        std::vector<uint32_t> incl(nb), base(nb), lut(nb);
+        std::vector<BucketDesc> bds(nb);
+        for (uint32_t blk = 0; blk < ps.ntiles; ++blk) {
+            const TileDesc t = tile_of(a.active, ps.nactive, blk);
+            const ActiveDesc act = a.active[t.active];
+            const uint32_t* pfx = a.tile_counts + (size_t)blk * nb;
+            uint32_t r = 0;
             for (int b = 0; b < nb; ++b) {
-                run += pfx[b];
-                incl[b] = run;
+                r += pfx[b];
+                incl[b] = r;
+                lut[b] = 0xFFFF;
             }
             for (int lb = 0; lb < nb; ++lb) {
-                const BucketDesc bd = a.d_buckets[(size_t)t.active * nb + lb];
+                const BucketDesc bd = a.buckets[(size_t)t.active * nb + lb];
+                bds[lb] = bd;
                 base[lb] = 0;
-                meta[lb] = 0;
                 if (bd.b1 != 0) {
                     const uint32_t hi = incl[bd.b1 - 1], lo = bd.b0 ? incl[bd.b0 - 1] : 0u;
                     base[lb] = (uint32_t)bd.dest + (hi - lo);
-                    meta[lb] = (uint16_t)(bd.keep | (bd.kind << 8));
+                    for (uint32_t d = bd.b0; d < bd.b1; ++d) lut[d] = (uint32_t)lb;
                 }
             }
-            for (uint32_t i = 0; i < t.count; ++i) {  // tile order == stable order
-                double q[3];
+            for (uint32_t i = 0; i < t.count; ++i) {
+                const uint64_t g = t.start + i;
+                uint64_t c[3];
                 uint32_t idx;
-                uint64_t cj[3][3];
-                load_position(a, t, act, i, q, idx);
-                const unsigned bin = run_chain(a, act, q, cj);
-                const uint32_t lb = a.d_lut[(size_t)t.active * nb + bin];
-                const int keep = meta[lb] & 0xFF;
-                const bool leaf = (meta[lb] >> 8) != 0;
+                load_rec(a.rec_in, g, a.wide, c, idx);
+                const unsigned dig = a.dig_in[g];
+                const uint32_t lb = lut[dig];
+                const BucketDesc& bd = bds[lb];
+                const bool next = bd.kind == 0;
                 const uint32_t dst = base[lb]++;
-                store_rec(leaf ? a.arena : a.rec_next, dst, a.wide, cj[keep - 1], idx);
-                (leaf ? a.col_arena : a.col_next)[dst] = load_colour(a, t.start + i);
+                unsigned dig_out = 0;
+                if (next || bd.keep == 2) {
+                    const int L1 = a.level + 1;
+                    const unsigned d1 = a.G == 2 ? (dig >> 3) : dig, d2 = dig & 7u;
+                    const double e1 = a.lv.edge[L1];
+                    double m[3] = {(d1 & 4u) ? act.m[0] + e1 : act.m[0], (d1 & 2u) ? act.m[1] + e1 : act.m[1], (d1 & 1u) ? act.m[2] + e1 : act.m[2]};
+                    double q[3];
+                    for (int k = 0; k < 3; ++k) q[k] = a.lv.fast ? decode1_fast(c[k], m[k], e1, a.lv.enc[L1]) : decode1(c[k], m[k], e1, a.lv.enc[L1]);
+                    int Lb = L1;
+                    if (bd.keep == 2) {
+                        const int L2 = L1 + 1;
+                        const double e2 = a.lv.edge[L2];
+                        if (d2 & 4u) m[0] = m[0] + e2;
+                        if (d2 & 2u) m[1] = m[1] + e2;
+                        if (d2 & 1u) m[2] = m[2] + e2;
+                        for (int k = 0; k < 3; ++k) {
+                            c[k] = a.lv.fast ? encode1_fast(q[k], m[k], e2, a.lv.ry[L2], a.lv.enc[L2]) : encode1(q[k], m[k], e2, a.lv.enc[L2]);
+                            q[k] = a.lv.fast ? decode1_fast(c[k], m[k], e2, a.lv.enc[L2]) : decode1(c[k], m[k], e2, a.lv.enc[L2]);
+                        }
+                        Lb = L2;
+                    }
+                    if (next) {
+                        Step s = a.lv.fast ? descend_fast(q, m, a.lv.edge[Lb], a.lv.edge[Lb + 1], a.lv.ry[Lb + 1], a.lv.enc[Lb + 1])
+                                           : descend(q, m, a.lv.edge[Lb], a.lv.edge[Lb + 1], a.lv.enc[Lb + 1]);
+                        dig_out = s.digit;
+                        for (int k = 0; k < 3; ++k) c[k] = s.code[k];
+                        if (a.Gn == 2) {
+                            Step s2 = a.lv.fast ? descend_fast(q, m, a.lv.edge[Lb + 1], a.lv.edge[Lb + 2], a.lv.ry[Lb + 2], a.lv.enc[Lb + 2])
+                                                : descend(q, m, a.lv.edge[Lb + 1], a.lv.edge[Lb + 2], a.lv.enc[Lb + 2]);
+                            dig_out = (dig_out << 3) | s2.digit;
+                        }
+                    }
+                }
+                store_rec(next ? a.rec_next : a.arena, dst, a.wide, c, idx);
+                (next ? a.col_next : a.col_arena)[dst] = a.col_in[g];
+                if (next) a.dig_next[dst] = (uint8_t)dig_out;
             }
         }
     }
