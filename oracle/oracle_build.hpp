@@ -9,7 +9,11 @@
 #include <condition_variable>
 #include <mutex>
 #include <set>
+#include <stdexcept>
 #include <thread>
+
+#include <cstdio>
+#include <unistd.h>
 
 #include "oracle_core.hpp"
 
@@ -78,6 +82,56 @@ struct Builder {
     std::map<NodeId, NodeFile> files;
     std::mutex mu;
     std::vector<NodeId> leaves;
+    // "Faithful" variant: like the reference, every node's .xyz / .rgb (/ .intensity) content lives in files of
+    // `disk_dir` between the steps - written when a split / subsample step finishes a node (DataWriter, node_writer.rs:36-89),
+    // read back when the next step consumes it (RawNodeReader, raw.rs:127-216), removed when the node is split
+    // (generation.rs:104-108).  Empty: everything stays in memory (same arithmetic and order, no file round trips).  The
+    // provenance column `src` is this oracle's own extension and never goes to disk.
+    std::string disk_dir;
+
+    static bool put_file(const std::string& path, const void* data, size_t n) {
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) return false;
+        const size_t w = n ? std::fwrite(data, 1, n, f) : 0;
+        std::fclose(f);
+        return w == n;
+    }
+    template <class V>
+    static void get_file(const std::string& path, V& out, size_t elems) {
+        out.resize(elems);
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("oracle (faithful): cannot read " + path);
+        const size_t r = elems ? std::fread(out.data(), sizeof(out[0]), elems, f) : 0;
+        std::fclose(f);
+        if (r != elems) throw std::runtime_error("oracle (faithful): short read " + path);
+    }
+    // A finished node leaves the writer: to disk in the faithful variant (zero-point nodes have no files, node_writer.rs:78-89).
+    void spill(NodeId id, NodeFile& f) const {
+        if (disk_dir.empty() || f.rgb.empty()) return;
+        const std::string stem = disk_dir + "/" + id.to_string();
+        if (!put_file(stem + ".xyz", f.xyz.data(), f.xyz.size()) || !put_file(stem + ".rgb", f.rgb.data(), f.rgb.size()) ||
+            (P.with_intensity && !put_file(stem + ".intensity", f.intensity.data(), f.intensity.size() * 4)))
+            throw std::runtime_error("oracle (faithful): cannot write " + stem);
+        f.disk_points = f.rgb.size() / 3;
+        std::vector<uint8_t>().swap(f.xyz);
+        std::vector<uint8_t>().swap(f.rgb);
+        std::vector<float>().swap(f.intensity);
+    }
+    // A step opens a node for reading: from disk in the faithful variant.
+    void unspill(NodeId id, NodeFile& f, bool remove_files) const {
+        if (disk_dir.empty() || f.disk_points == 0) return;
+        const std::string stem = disk_dir + "/" + id.to_string();
+        const size_t n = f.disk_points;
+        get_file(stem + ".xyz", f.xyz, n * 3 * (size_t)bytes_per_coordinate(f.enc));
+        get_file(stem + ".rgb", f.rgb, n * 3);
+        if (P.with_intensity) get_file(stem + ".intensity", f.intensity, n);
+        f.disk_points = 0;
+        if (remove_files) {
+            ::unlink((stem + ".xyz").c_str());
+            ::unlink((stem + ".rgb").c_str());
+            if (P.with_intensity) ::unlink((stem + ".intensity").c_str());
+        }
+    }
 
     NodeFile new_writer(NodeId id) const {  // generation.rs:39-56 (RawNodeWriter::from_data_provider)
         NodeFile f;
@@ -114,6 +168,7 @@ struct Builder {
             NodeId cid = node_id.child(k);
             int64_t num_written = (int64_t)(children[k].xyz.size() / bytes_per_coordinate(children[k].enc) / 3);
             bool sp = should_split_node(cid, num_written);
+            spill(cid, children[k]);
             {
                 std::lock_guard<std::mutex> g(mu);
                 files[cid] = std::move(children[k]);
@@ -129,6 +184,7 @@ struct Builder {
             f = std::move(files[id]);
             files.erase(id);  // generation.rs:104-108: the split node's own .xyz is removed
         }
+        unspill(id, f, true);
         std::vector<NodeId> leaf_nodes, split_nodes;
         size_t n = (size_t)f.num_points();
         bool wi = P.with_intensity;
@@ -153,6 +209,7 @@ struct Builder {
                 if (it == files.end()) continue;  // NodeNotFound -> continue (generation.rs:207-211)
                 child = std::move(it->second);
             }
+            unspill(child_id, child, true);  // the child is rewritten below (generation.rs:216-238)
             size_t n = (size_t)child.num_points();
             NodeFile child_writer = new_writer(child_id);
             for (size_t j = 0; j < n; ++j) {  // generation.rs:220-238
@@ -163,6 +220,7 @@ struct Builder {
                     node_append(child_writer, pt, P.with_intensity);
             }
             int64_t nw = (int64_t)(child_writer.xyz.size() / bytes_per_coordinate(child_writer.enc) / 3);
+            spill(child_id, child_writer);
             {
                 std::lock_guard<std::mutex> g(mu);
                 if (nw == 0)
@@ -174,6 +232,7 @@ struct Builder {
         }
         int64_t pn = (int64_t)(parent_writer.xyz.size() / bytes_per_coordinate(parent_writer.enc) / 3);
         if (node_id.level() == 0) out.push_back({node_id, pn});  // generation.rs:246-251
+        spill(node_id, parent_writer);
         std::lock_guard<std::mutex> g(mu);
         if (pn == 0)
             files.erase(node_id);

@@ -7,6 +7,7 @@
 #include "oracle_disk.hpp"
 #include "oracle_ply.hpp"
 #include "oracle_query.hpp"
+#include "../include/pcv_synth.h"  // input-data generators shared with the benchmark (no algorithm code)
 
 using namespace orc;
 
@@ -77,6 +78,50 @@ void* orc_build(uint64_t n, const double* x, const double* y, const double* z, u
     return h;
 }
 double orc_build_seconds(void* hp) { return ((Handle*)hp)->build_seconds; }
+
+// The "faithful" variant of build_octree: node contents round-trip through files of `dir` between the steps, as in the
+// reference (generation.rs:39-126,195-253); the directory ends up holding the finished octree (node files + meta.pb,
+// generation.rs:399-402).  Returns the build time in seconds (< 0 on failure).  Same arithmetic and results as orc_build.
+double orc_build_faithful(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, const uint8_t* rgb, const float* intensity,
+                          double resolution, const double* bbox_min, const double* bbox_max, int64_t max_points_per_node, int num_threads, const char* dir,
+                          uint64_t* num_nodes_out) {
+    try {
+        Builder b;
+        b.num_threads = num_threads > 0 ? num_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        b.P.resolution = resolution;
+        b.P.bbox = Aabb::make({bbox_min[0], bbox_min[1], bbox_min[2]}, {bbox_max[0], bbox_max[1], bbox_max[2]});
+        b.P.with_intensity = intensity != nullptr;
+        if (max_points_per_node > 0) b.P.max_points_per_node = max_points_per_node;
+        b.disk_dir = dir;
+        auto t0 = std::chrono::steady_clock::now();
+        Octree oct = b.build((size_t)n, x, y, z, (size_t)stride, rgb, intensity);
+        const std::string m = meta_pb(oct);
+        if (!write_file(std::string(dir) + "/meta.pb", m.data(), m.size())) return -1.0;
+        if (num_nodes_out) *num_nodes_out = oct.nodes.size();
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } catch (const std::exception&) {
+        return -1.0;
+    }
+}
+
+// Synthetic inputs (include/pcv_synth.h), generated on `num_threads` host threads.
+void orc_synth_points(int kind, uint64_t seed, uint64_t first, uint64_t n, double* x, double* y, double* z, uint8_t* rgb, int num_threads) {
+    const int nt = num_threads > 0 ? num_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=] {
+            const uint64_t lo = n * (uint64_t)t / (uint64_t)nt, hi = n * (uint64_t)(t + 1) / (uint64_t)nt;
+            for (uint64_t i = lo; i < hi; ++i) {
+                double p[3];
+                uint8_t c[3];
+                pcv::synth_point(kind, seed, first + i, p, c);
+                x[i] = p[0], y[i] = p[1], z[i] = p[2];
+                rgb[3 * i] = c[0], rgb[3 * i + 1] = c[1], rgb[3 * i + 2] = c[2];
+            }
+        });
+    for (auto& t : th) t.join();
+}
+void orc_synth_bbox(int kind, double* bbox_min, double* bbox_max, double* resolution) { pcv::synth_bbox(kind, bbox_min, bbox_max, resolution); }
 int orc_max_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
 
 void orc_free(void* hp) { delete (Handle*)hp; }
@@ -271,6 +316,58 @@ int64_t orc_query(void* hp, const orc_location* l, const double* filters, int nf
         if (src) std::memcpy(src, out.src.data(), out.src.size() * 8);
     }
     return n;
+}
+
+// ParallelIterator::try_for_each_batch (iterator.rs:255-333) as bench.py's CPU baseline of the query path: `num_threads`
+// workers steal nodes from a shared queue (crossbeam deque in the reference), each decodes + culls its node through the same
+// FilteredIterator restatement as orc_query and re-chunks into batches of `batch_size` that the consumer only counts.  Runs the
+// locations one after the other (one PointQuery per call in the reference, point_cloud_client/src/lib.rs:42-70).  Returns seconds.
+double orc_query_batch_timed(void* hp, const orc_location* locs, uint32_t nloc, int num_threads, uint64_t batch_size, uint64_t* tested_out,
+                             uint64_t* returned_out, uint64_t* bytes_out) {
+    Handle* h = (Handle*)hp;
+    const int nt = std::max(1, num_threads);
+    uint64_t tested = 0, returned = 0, bytes = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t li = 0; li < nloc; ++li) {
+        const Location loc = to_loc(&locs[li]);
+        const std::vector<NodeId> ids = nodes_in_location(h->oct, loc);
+        std::atomic<size_t> next{0};
+        std::atomic<uint64_t> ret{0};
+        std::vector<std::thread> th;
+        const int workers = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, ids.size()));
+        for (int t = 0; t < workers; ++t)
+            th.emplace_back([&] {
+                std::vector<Interval> none;
+                QueryOut buf;
+                uint64_t mine = 0;
+                for (;;) {
+                    const size_t k = next.fetch_add(1);
+                    if (k >= ids.size()) break;
+                    query_node(h->oct, ids[k], loc, none, buf);
+                    while (buf.src.size() >= batch_size) {  // PointStream::push_points_and_callback (iterator.rs:159-165): split_off a full batch
+                        QueryOut rest;
+                        rest.xyz.assign(buf.xyz.begin() + 3 * batch_size, buf.xyz.end());
+                        rest.rgb.assign(buf.rgb.begin() + 3 * batch_size, buf.rgb.end());
+                        rest.src.assign(buf.src.begin() + batch_size, buf.src.end());
+                        mine += batch_size;
+                        buf = std::move(rest);
+                    }
+                }
+                mine += buf.src.size();
+                ret += mine;
+            });
+        for (auto& t : th) t.join();
+        for (NodeId id : ids) {
+            const NodeMeta& m = h->oct.nodes[id];
+            tested += (uint64_t)m.num_points;
+            bytes += (uint64_t)m.num_points * (3ull * (uint64_t)bytes_per_coordinate(m.enc) + 3ull);
+        }
+        returned += ret.load();
+    }
+    if (tested_out) *tested_out = tested;
+    if (returned_out) *returned_out = returned;
+    if (bytes_out) *bytes_out = bytes + 27ull * returned;
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 int orc_xray_tile(void* hp, const double* bbox_min, const double* bbox_max, uint32_t w, uint32_t hgt, const double* query_from_global7,

@@ -258,6 +258,7 @@ struct NodeFile {
     std::vector<uint8_t> rgb;
     std::vector<float> intensity;
     std::vector<uint64_t> src;
+    size_t disk_points = 0;  // faithful build variant: the content currently lives in the node's files (oracle_build.hpp)
     int64_t num_points() const { return (int64_t)(rgb.size() / 3); }  // on_disk.rs:23-33
 };
 

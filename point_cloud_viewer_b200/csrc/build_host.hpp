@@ -111,7 +111,7 @@ struct LeafTile {
     uint32_t count;
 };
 
-constexpr uint32_t kTilePoints = 2048;   // partition tile
+constexpr uint32_t kTilePoints = 1792;   // partition tile: 8 warps x 7 sub-rounds of 32 (kernels_build.cuh)
 constexpr uint32_t kChunkTiles = 256;    // tiles per scan chunk
 constexpr uint32_t kPlaceTile = 2048;    // place tile
 constexpr int kMaxPasses = kMaxLevels;   // a pass resolves at least one level
@@ -125,6 +125,7 @@ struct PassState {
 struct BuildState {
     uint32_t nnodes;
     int32_t error;         // 0, or a BuildError code raised on the device (kErr*)
+    int32_t plan_error, pad0;
     uint64_t arena_used;
     uint32_t deepest_level, pad;
     PassState pass[kMaxPasses + 1];
@@ -147,6 +148,12 @@ struct ShardSpec {
 // previous pass (or the ingest kernel) still had the decoded position in registers.  The pass therefore ranks by digit
 // without any arithmetic, and only then - in destination order - finishes the codes each destination stores and, for
 // points that continue, runs the next pass's descent.  Every level of the re-quantising chain is encoded exactly once.
+// Running totals of one pass of the planner (plan_active below).
+struct PlanRun {
+    uint32_t nodes, actives, tiles, chunks;
+    uint64_t next_pts, arena_pts;
+};
+
 struct IngestArgs {
     PointsView pts;
     void* rec_out;       // codes at level 1 (RecN / RecW), idx = input position
@@ -186,6 +193,7 @@ struct PassArgs {
     uint32_t* chunk_sums;   // [chunks][nbins]
     uint64_t* node_bins;    // [active][nbins]
     BucketDesc* buckets;    // [active][nbins]
+    PlanRun* plan_runs;  // [active] per-node demand, then bases (device backends that plan in several kernels)
     DevNode* nodes;
     uint32_t cap_active, cap_nodes, cap_tiles, cap_chunks;
     // split rule (generation.rs:128-150) + sharding
@@ -249,11 +257,6 @@ PCV_HD LeafTile leaf_tile_of(const PlaceArgs& a, uint32_t b) {
 // or a node of the next pass, where it starts, plus the node table entries, the next pass's active list and scan chunks.
 // Running totals of one pass: in counting mode they start at zero and return the node's demand; in emit mode they start at
 // the node's exclusive prefix (and the global bases) and every structure is written.
-struct PlanRun {
-    uint32_t nodes, actives, tiles, chunks;
-    uint64_t next_pts, arena_pts;
-};
-
 template <bool EMIT>
 PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& err, uint32_t& deepest) {
     const ActiveDesc act = a.active[ai];
@@ -548,6 +551,7 @@ class BuildPlan {
             uint32_t* chunk_sums = (uint32_t*)dalloc((size_t)cap_chunks * 64 * 4);
             uint64_t* node_bins = (uint64_t*)dalloc((size_t)cap_active * 64 * 8);
             BucketDesc* buckets = (BucketDesc*)dalloc((size_t)cap_active * 64 * sizeof(BucketDesc));
+            PlanRun* plan_runs = (PlanRun*)dalloc((size_t)cap_active * sizeof(PlanRun));
             DevNode* d_nodes = (DevNode*)dalloc((size_t)cap_nodes * sizeof(DevNode));
             uint64_t* d_shard = nullptr;
             if (shard.k) {
@@ -627,6 +631,7 @@ class BuildPlan {
                 pa.chunk_sums = chunk_sums;
                 pa.node_bins = node_bins;
                 pa.buckets = buckets;
+                pa.plan_runs = plan_runs;
                 pa.nodes = d_nodes;
                 pa.cap_active = cap_active;
                 pa.cap_nodes = cap_nodes;

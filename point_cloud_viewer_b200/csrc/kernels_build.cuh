@@ -304,37 +304,53 @@ __device__ __forceinline__ TileDesc tile_lookup(const PassArgs& a, uint32_t tile
     return TileDesc{act.start + o, (uint32_t)(rem < kTilePoints ? rem : kTilePoints), i};
 }
 
-constexpr int kDigThreads = 128;
+// One warp per tile, no block-level synchronisation: 64 bytes of digits per lane (four independent 16-byte loads in flight),
+// warp-private histogram in shared memory.
+constexpr int kDigThreads = 256;
 __global__ void __launch_bounds__(kDigThreads) k_dighist(const __grid_constant__ PassArgs a) {
-    __shared__ uint32_t h[kDigThreads / 32][64];
+    __shared__ uint32_t hs[kDigThreads / 32][64];
     const PassState ps = a.st->pass[a.pass];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (uint32_t tile = blockIdx.x; tile < ps.ntiles; tile += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* h = hs[warp];
+    const uint32_t nwarps = gridDim.x * (kDigThreads / 32);
+    for (uint32_t tile = blockIdx.x * (kDigThreads / 32) + warp; tile < ps.ntiles; tile += nwarps) {
         const TileDesc t = tile_lookup(a, tile);
-        for (int b = tid; b < (kDigThreads / 32) * 64; b += kDigThreads) (&h[0][0])[b] = 0;
-        __syncthreads();
+        h[lane] = 0;
+        h[lane + 32] = 0;
+        __syncwarp();
         // aligned 16-byte loads over the covering range, bytes outside [start, start + count) masked
         const uint64_t lo = t.start, hi = t.start + t.count, base = lo & ~(uint64_t)15;
-        const uint32_t nvec = (uint32_t)((hi - base + 15) >> 4);
-        for (uint32_t v = tid; v < nvec; v += kDigThreads) {
-            const uint64_t p0 = base + 16ull * v;
-            const uint4 w = __ldcg(reinterpret_cast<const uint4*>(a.dig_in + p0));
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t nvec = (uint32_t)((hi - base + 15) >> 4);  // <= 129
+        uint4 w[5];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint64_t p = p0 + j;
-                if (p >= lo && p < hi) atomicAdd(&h[warp][(ws[j >> 2] >> (8 * (j & 3))) & 63u], 1u);
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t v = lane + 32 * k;
+            w[k] = make_uint4(0, 0, 0, 0);
+            if (v < nvec) w[k] = __ldcg(reinterpret_cast<const uint4*>(a.dig_in + base + 16ull * v));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t v = lane + 32 * k;
+            if (v < nvec) {
+                const uint64_t p0 = base + 16ull * v;
+                const uint32_t ws[4] = {w[k].x, w[k].y, w[k].z, w[k].w};
+                if (p0 >= lo && p0 + 16 <= hi) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(&h[(ws[j >> 2] >> (8 * (j & 3))) & 63u], 1u);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint64_t p = p0 + j;
+                        if (p >= lo && p < hi) atomicAdd(&h[(ws[j >> 2] >> (8 * (j & 3))) & 63u], 1u);
+                    }
+                }
             }
         }
-        __syncthreads();
+        __syncwarp();
         uint32_t* out = a.tile_counts + (size_t)tile * a.nbins;
-        for (int b = tid; b < a.nbins; b += kDigThreads) {
-            uint32_t sacc = 0;
-#pragma unroll
-            for (int w8 = 0; w8 < kDigThreads / 32; ++w8) sacc += h[w8][b];
-            out[b] = sacc;
-        }
-        __syncthreads();
+        if (lane < a.nbins) out[lane] = h[lane];
+        if (lane + 32 < a.nbins) out[lane + 32] = h[lane + 32];
+        __syncwarp();
     }
 }
 
@@ -358,7 +374,18 @@ __global__ void k_scan_nodes(const __grid_constant__ PassArgs a) {
         for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
             uint64_t run = 0;
             uint32_t* p = a.chunk_sums + (size_t)act.chunk_begin * a.nbins + b;
-            for (uint32_t c = 0; c < act.nchunks; ++c) {
+            uint32_t c = 0;
+            for (; c + 8 <= act.nchunks; c += 8) {  // eight independent loads in flight, then the dependent prefix
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(c + u) * a.nbins];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    p[(size_t)(c + u) * a.nbins] = (uint32_t)run;
+                    run += v[u];
+                }
+            }
+            for (; c < act.nchunks; ++c) {
                 uint32_t v = p[(size_t)c * a.nbins];
                 p[(size_t)c * a.nbins] = (uint32_t)run;
                 run += v;
@@ -374,7 +401,18 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
         for (int b = threadIdx.x; b < a.nbins; b += blockDim.x) {
             uint32_t run = a.chunk_sums[(size_t)ch * a.nbins + b];
             uint32_t* p = a.tile_counts + (size_t)c.tile_begin * a.nbins + b;
-            for (uint32_t t = 0; t < c.ntiles; ++t) {
+            uint32_t t = 0;
+            for (; t + 8 <= c.ntiles; t += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(t + u) * a.nbins];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    p[(size_t)(t + u) * a.nbins] = run;
+                    run += v[u];
+                }
+            }
+            for (; t < c.ntiles; ++t) {
                 uint32_t v = p[(size_t)t * a.nbins];
                 p[(size_t)t * a.nbins] = run;
                 run += v;
@@ -386,7 +424,10 @@ __global__ void k_scan_tiles(const __grid_constant__ PassArgs a) {
 // ------------------------------------------------------------------------------------------------
 // plan: leaf / split decisions, bucket tables, node table, next pass's active list - one block, no host round trip
 // ------------------------------------------------------------------------------------------------
+// Three small kernels: per-active-node demand (many blocks: the per-node logic diverges, so it is spread over the SMs), an
+// exclusive scan of the demands in one block, and the emission with every node's bases.
 constexpr int kPlanThreads = 1024;
+constexpr int kPlanNodeThreads = 32;
 __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* sh /* [33] */, uint64_t& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t incl = v;
@@ -413,28 +454,34 @@ __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* sh /* 
     return incl - v + sh[warp];
 }
 
-__global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(kPlanNodeThreads) k_plan_count(const __grid_constant__ PassArgs a) {
+    const PassState ps = a.st->pass[a.pass];
+    for (uint32_t ai = blockIdx.x * kPlanNodeThreads + threadIdx.x; ai < ps.nactive; ai += gridDim.x * kPlanNodeThreads) {
+        PlanRun t{};
+        int32_t err = 0;
+        uint32_t deepest = 0;
+        plan_active<false>(a, ai, t, err, deepest);
+        a.plan_runs[ai] = t;
+        if (err) atomicMax(&a.st->plan_error, err);
+        if (deepest) atomicMax(&a.st->deepest_level, deepest);
+    }
+}
+
+__global__ void __launch_bounds__(kPlanThreads) k_plan_scan(const __grid_constant__ PassArgs a) {
     __shared__ uint64_t sh[33];
-    __shared__ int32_t s_err;
-    __shared__ uint32_t s_deep;
     BuildState* st = a.st;
     const PassState ps = st->pass[a.pass];
-    if (threadIdx.x == 0) {
-        s_err = 0;
-        s_deep = 0;
-    }
     PlanRun carry;  // global bases of this pass
     carry.nodes = st->nnodes;
     carry.actives = 0, carry.tiles = 0, carry.chunks = 0;
     carry.next_pts = 0;
     carry.arena_pts = st->arena_used;
+    const int32_t err_in = st->plan_error;
     __syncthreads();
-    int32_t err = 0;
-    uint32_t deepest = 0;
     for (uint32_t base = 0; base < ps.nactive; base += kPlanThreads) {
         const uint32_t ai = base + threadIdx.x;
         PlanRun t{};
-        if (ai < ps.nactive) plan_active<false>(a, ai, t, err, deepest);
+        if (ai < ps.nactive) t = a.plan_runs[ai];
         uint64_t tot[6];
         PlanRun b;
         b.nodes = carry.nodes + (uint32_t)block_excl_scan(t.nodes, sh, tot[0]);
@@ -443,15 +490,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ P
         b.chunks = carry.chunks + (uint32_t)block_excl_scan(t.chunks, sh, tot[3]);
         b.next_pts = carry.next_pts + block_excl_scan(t.next_pts, sh, tot[4]);
         b.arena_pts = carry.arena_pts + block_excl_scan(t.arena_pts, sh, tot[5]);
-        // capacities are checked on the totals before anything is written (emit guards its own writes as well)
-        if ((uint64_t)carry.nodes + tot[0] > a.cap_nodes || (uint64_t)carry.actives + tot[1] > a.cap_active || (uint64_t)carry.tiles + tot[2] > a.cap_tiles ||
-            (uint64_t)carry.chunks + tot[3] > a.cap_chunks)
-            err = kErrCapacity;
-        if (ai < ps.nactive) {
-            int32_t e2 = 0;
-            uint32_t d2 = 0;
-            plan_active<true>(a, ai, b, e2, d2);
-        }
+        if (ai < ps.nactive) a.plan_runs[ai] = b;  // the node's bases
         carry.nodes += (uint32_t)tot[0];
         carry.actives += (uint32_t)tot[1];
         carry.tiles += (uint32_t)tot[2];
@@ -459,12 +498,12 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ P
         carry.next_pts += tot[4];
         carry.arena_pts += tot[5];
     }
-    if (err) atomicMax(&s_err, err);
-    if (deepest) atomicMax(&s_deep, deepest);
-    __syncthreads();
     if (threadIdx.x == 0) {
-        const bool failed = s_err != 0 || st->error != 0;
-        if (s_err && !st->error) st->error = s_err;
+        int32_t err = err_in;
+        // capacities are checked on the totals (the emit kernel guards its own writes as well)
+        if (!err && (carry.nodes > a.cap_nodes || carry.actives > a.cap_active || carry.tiles > a.cap_tiles || carry.chunks > a.cap_chunks)) err = kErrCapacity;
+        const bool failed = err != 0 || st->error != 0;
+        if (err && !st->error) st->error = err;
         PassState nx{};
         if (!failed) {
             nx.nactive = carry.actives;
@@ -475,23 +514,36 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ P
         st->pass[a.pass + 1] = nx;  // an error stops the following passes: no active nodes
         st->nnodes = carry.nodes;
         st->arena_used = carry.arena_pts;
-        if (s_deep > st->deepest_level) st->deepest_level = s_deep;
+    }
+}
+
+__global__ void __launch_bounds__(kPlanNodeThreads) k_plan_emit(const __grid_constant__ PassArgs a) {
+    const PassState ps = a.st->pass[a.pass];
+    for (uint32_t ai = blockIdx.x * kPlanNodeThreads + threadIdx.x; ai < ps.nactive; ai += gridDim.x * kPlanNodeThreads) {
+        PlanRun b = a.plan_runs[ai];
+        int32_t e2 = 0;
+        uint32_t d2 = 0;
+        plan_active<true>(a, ai, b, e2, d2);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // pass: stable multi-way partition of every tile + the next pass's descent, in destination order
 // ------------------------------------------------------------------------------------------------
-// Persistent blocks (16 warps), tiles of 2048 points taken round robin, two shared-memory stages: while the block works on
-// tile i, the TMA unit already fills the other stage with tile i + gridDim (records, colours, digits, the tile's row of the
-// per-digit prefix table and its node's bucket table), so no global-memory latency sits between two tiles.  Warp w owns the
-// contiguous items [128 w, 128 w + 128) of the tile.
-//   stage    five TMA bulk copies per tile (cp.async.bulk global -> shared, completion on the stage's mbarrier), issued by one
-//            thread one tile ahead; that thread also looks up the next tile's node (tile index table + active list) with
-//            loads whose latency is spread over the phases below
+// Persistent blocks of 8 warps, four per SM (independent barrier domains that cover each other's phases), tiles of 1792
+// points taken round robin.  Warp w owns the contiguous items [224 w, 224 w + 224) of the tile.
+//   stage    TMA bulk copies (cp.async.bulk global -> shared, completion on mbarriers) in two groups: the small part a tile's
+//            ranking needs - its digits, its row of the per-digit prefix table and its node's bucket table, 3 KB, double
+//            buffered and requested a whole tile ahead - and the big part only the finish sweep needs - records and colours,
+//            36 KB, requested as soon as the previous tile's finish sweep has released the buffer, so that it lands while the
+//            tile is being ranked and sorted.  The node of the NEXT tile is looked up during the current one (tile index table
+//            + an asynchronous copy of the active-list entry): no global-memory latency sits on the path between two tiles
+//   tables   64 threads: per bucket the slot of this tile's first record (bucket start + the node's earlier tiles) and the
+//            digit -> bucket map
 //   rank     per item only the carried digit -> bucket look-up; lanes grouped by bucket with __match_any_sync, per-warp
 //            bucket counts; no arithmetic on positions at all
-//   scan     (one warp) per-bucket totals, exclusive prefix over the buckets (sorted start inside the tile) and over the warps
+//   scan     (one warp) per-bucket totals, exclusive prefix over the buckets (sorted start inside the tile) and over the warps;
+//            per bucket the three store base addresses, so that a store address is base + sorted position * size
 //   sort     every warp walks its items in order and writes (item, bucket) at the item's stable sorted position: the tile is
 //            sorted by bucket as a permutation in shared memory
 //   finish   consecutive threads take consecutive sorted positions, i.e. consecutive slots of a destination run: a leaf at
@@ -502,33 +554,43 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ P
 // The order inside every bucket is the tile order, i.e. input order (stable).
 template <bool WIDE>
 struct PassCfg {
-    static constexpr int threads = 512;
+    static constexpr int threads = 256;
     static constexpr int warps = threads / 32;
-    static constexpr int warp_items = kTilePoints / warps;  // 128
-    static constexpr int sub_rounds = warp_items / 32;      // 4
+    static constexpr int warp_items = kTilePoints / warps;  // 224
+    static constexpr int sub_rounds = warp_items / 32;      // 7
+    static constexpr int blocks_per_sm = WIDE ? 2 : 4;
+    static_assert(warps * sub_rounds * 32 == (int)kTilePoints, "the tile must be a whole number of sub-rounds per warp");
 };
 constexpr int kPassBins = 64;
+struct PassBucket {  // per bucket of the current tile (shared memory, 32 bytes)
+    unsigned long long rec, col, dig;  // store address of sorted position 0 (the bucket's run starts at `start`)
+    uint32_t start;                    // sorted position of the bucket's first record
+    uint32_t kk;                       // keep | leaf << 8
+};
 template <bool WIDE>
 struct PassSmem {
     static constexpr size_t rec_bytes = WIDE ? 32 : 16;
-    // one stage (everything a tile needs from global memory)
-    static constexpr size_t st_col = (size_t)kTilePoints * rec_bytes;
-    static constexpr size_t st_dig = st_col + ((size_t)kTilePoints + 4) * 4;
-    static constexpr size_t st_pfx = st_dig + (size_t)kTilePoints + 32;
-    static constexpr size_t st_bk = st_pfx + (size_t)kPassBins * 4;
-    static constexpr size_t stage_bytes = (st_bk + (size_t)kPassBins * sizeof(BucketDesc) + 127) & ~(size_t)127;
-    // shared by both stages
-    static constexpr size_t off_perm = 2 * stage_bytes;
+    // big part of a staged tile: records + colours (single buffer)
+    static constexpr size_t off_col = (size_t)kTilePoints * rec_bytes;
+    static constexpr size_t big_bytes = off_col + ((size_t)kTilePoints + 4) * 4;
+    // small part: digits + prefix row + bucket table (two buffers)
+    static constexpr size_t sm_pfx = (size_t)kTilePoints + 32;
+    static constexpr size_t sm_bk = sm_pfx + (size_t)kPassBins * 4;
+    static constexpr size_t small_bytes = sm_bk + (size_t)kPassBins * sizeof(BucketDesc);
+    static constexpr size_t off_small = big_bytes;
+    static constexpr size_t off_perm = off_small + 2 * small_bytes;
     static constexpr size_t off_cnt = off_perm + (size_t)kTilePoints * 4;
     static constexpr size_t off_bdst = off_cnt + (size_t)PassCfg<WIDE>::warps * kPassBins * 4;
-    static constexpr size_t off_lutm = off_bdst + (size_t)kPassBins * 16;
-    static constexpr size_t off_desc = off_lutm + (size_t)kPassBins * 4;
-    static constexpr size_t off_nact = off_desc + 2 * 64;  // ActiveDesc of the next tile (cp.async landing zone)
-    static constexpr size_t off_bar = off_nact + 64;
-    static constexpr size_t bytes = off_bar + 16;
+    static constexpr size_t off_lutm = off_bdst + (size_t)kPassBins * sizeof(PassBucket);
+    static constexpr size_t off_first = off_lutm + (size_t)kPassBins * 4;  // [nb] slot of the bucket's first record of this tile
+    static constexpr size_t off_desc = off_first + (size_t)kPassBins * 4;  // [2]
+    static constexpr size_t off_nact = off_desc + 2 * 64;                  // ActiveDesc of the next tile (cp.async landing zone)
+    static constexpr size_t off_bar = off_nact + 64;                       // [3]: small[0], small[1], big
+    static constexpr size_t bytes = off_bar + 32;
+    static_assert(big_bytes % 16 == 0 && small_bytes % 16 == 0 && sm_pfx % 16 == 0, "bulk copy destinations must be 16-byte aligned");
 };
-static_assert(2 * PassSmem<false>::bytes + 2048 <= 233472, "two narrow pass blocks must fit one SM (228 KB, 1 KB reserved per block)");
-static_assert(PassSmem<true>::bytes <= 232448, "pass tile exceeds the 227 KB opt-in shared memory of sm_100");
+static_assert(4 * (PassSmem<false>::bytes + 1024) <= 233472, "four narrow pass blocks must fit one SM (228 KB, 1 KB reserved per block)");
+static_assert(2 * (PassSmem<true>::bytes + 1024) <= 233472, "two wide pass blocks must fit one SM");
 
 struct PassTile {  // descriptor of a staged tile (shared memory, 64 bytes)
     double m[3];  // cube min of the active node
@@ -538,7 +600,7 @@ struct PassTile {  // descriptor of a staged tile (shared memory, 64 bytes)
     uint32_t tile, valid;
     uint32_t pad[2];
 };
-static_assert(sizeof(PassTile) == 64 && sizeof(ActiveDesc) == 64, "descriptor layout");
+static_assert(sizeof(PassTile) == 64 && sizeof(ActiveDesc) == 64 && sizeof(PassBucket) == 32, "descriptor layout");
 
 // finish one record (see above).  All level constants are plain kernel parameters (PassArgs::e1 ...).
 template <bool WIDE, int FAST>
@@ -585,71 +647,79 @@ __device__ __forceinline__ void finish_record(const PassArgs& a, const double pm
 
 template <bool WIDE, int FAST>
 __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTile& pt, const unsigned char* srec, const uint32_t* scol, const uint8_t* sdig,
-                                                const uint32_t* perm, const uint4* bdst) {
+                                                const uint32_t* perm, const PassBucket* bdst) {
+    constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
     unsigned bad = 0;
     const double pm[3] = {pt.m[0], pt.m[1], pt.m[2]};
     const uint32_t count = pt.count;
+#pragma unroll 2
     for (uint32_t p = threadIdx.x; p < count; p += PassCfg<WIDE>::threads) {
-        const uint32_t e = perm[p], i = e & (kTilePoints - 1), lb = e >> 12;
-        const uint4 bd = bdst[lb];  // x: slot of the bucket's first record of this tile, y: sorted start, z: keep, w: 1 = leaf arena
-        const bool next = bd.w == 0;
-        const uint32_t dst = bd.x + (p - bd.y);
+        const uint32_t e = perm[p], i = e & 2047u, lb = e >> 12;
+        const PassBucket bd = bdst[lb];
+        const bool next = (bd.kk >> 8) == 0;
+        const int keep = (int)(bd.kk & 0xFFu);
         uint64_t c[3];
         uint32_t idx;
         smem_load_rec<WIDE>(srec, i, c, idx);
         unsigned dig_out = 0;
-        if (next || bd.z == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], (int)bd.z, next, dig_out, bad);
+        if (next || keep == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], keep, next, dig_out, bad);
         if (FAST == 1 && bad) continue;  // the block repeats the sweep with the IEEE operator
-        store_rec<WIDE>(next ? a.rec_next : a.arena, dst, c, idx);
-        (next ? a.col_next : a.col_arena)[dst] = scol[i];
-        if (next) a.dig_next[dst] = (uint8_t)dig_out;
+        store_rec<WIDE>(reinterpret_cast<void*>(bd.rec + (unsigned long long)p * recsz), 0, c, idx);
+        *reinterpret_cast<uint32_t*>(bd.col + 4ull * p) = scol[i];
+        if (next) *reinterpret_cast<uint8_t*>(bd.dig + p) = (uint8_t)dig_out;
     }
     return bad;
 }
 
-// Stage a tile: descriptor + the five bulk copies (one thread).  Sources must be 16-byte aligned: the colour / digit copies
-// start up to 3 / 15 entries early.
+// The two bulk-copy groups of a tile (one thread).  Sources must be 16-byte aligned: the colour / digit copies start up to
+// 3 / 15 entries early.
 template <bool WIDE>
-__device__ __forceinline__ void pass_stage_tile(const PassArgs& a, uint32_t tile, const ActiveDesc& act, uint32_t active, unsigned char* stage, PassTile* desc,
-                                                uint64_t* bar) {
-    constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
-    const uint64_t o = (uint64_t)(tile - act.tile_begin) * kTilePoints;
-    const uint64_t rem = act.count - o;
-    PassTile d;
-    d.m[0] = act.m[0], d.m[1] = act.m[1], d.m[2] = act.m[2];
-    d.e = act.e;
-    d.start = act.start + o;
-    d.count = (uint32_t)(rem < kTilePoints ? rem : kTilePoints);
-    d.active = active;
-    d.tile = tile;
-    d.valid = 1;
-    d.pad[0] = d.pad[1] = 0;
-    *desc = d;
-    const uint32_t coff = (uint32_t)(d.start & 3), doff = (uint32_t)(d.start & 15);
-    const uint32_t rec_bytes = d.count * (uint32_t)recsz;
-    const uint32_t col_bytes = ((coff + d.count) * 4u + 15u) & ~15u;
+__device__ __forceinline__ void pass_stage_small(const PassArgs& a, const PassTile& d, unsigned char* sm, uint64_t* bar) {
+    const uint32_t doff = (uint32_t)(d.start & 15);
     const uint32_t dig_bytes = (doff + d.count + 15u) & ~15u;
     const uint32_t pfx_bytes = (uint32_t)a.nbins * 4u, bk_bytes = (uint32_t)a.nbins * (uint32_t)sizeof(BucketDesc);
-    mbar_expect_tx(bar, rec_bytes + col_bytes + dig_bytes + pfx_bytes + bk_bytes);
-    tma_bulk_load(stage, reinterpret_cast<const unsigned char*>(a.rec_in) + d.start * recsz, rec_bytes, bar);
-    tma_bulk_load(stage + PassSmem<WIDE>::st_col, a.col_in + (d.start - coff), col_bytes, bar);
-    tma_bulk_load(stage + PassSmem<WIDE>::st_dig, a.dig_in + (d.start - doff), dig_bytes, bar);
-    tma_bulk_load(stage + PassSmem<WIDE>::st_pfx, a.tile_counts + (size_t)tile * a.nbins, pfx_bytes, bar);
-    tma_bulk_load(stage + PassSmem<WIDE>::st_bk, a.buckets + (size_t)active * a.nbins, bk_bytes, bar);
+    mbar_expect_tx(bar, dig_bytes + pfx_bytes + bk_bytes);
+    tma_bulk_load(sm, a.dig_in + (d.start - doff), dig_bytes, bar);
+    tma_bulk_load(sm + PassSmem<WIDE>::sm_pfx, a.tile_counts + (size_t)d.tile * a.nbins, pfx_bytes, bar);
+    tma_bulk_load(sm + PassSmem<WIDE>::sm_bk, a.buckets + (size_t)d.active * a.nbins, bk_bytes, bar);
+}
+template <bool WIDE>
+__device__ __forceinline__ void pass_stage_big(const PassArgs& a, const PassTile& d, unsigned char* smem_raw, uint64_t* bar) {
+    constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
+    const uint32_t coff = (uint32_t)(d.start & 3);
+    const uint32_t rec_bytes = d.count * (uint32_t)recsz;
+    const uint32_t col_bytes = ((coff + d.count) * 4u + 15u) & ~15u;
+    mbar_expect_tx(bar, rec_bytes + col_bytes);
+    tma_bulk_load(smem_raw, reinterpret_cast<const unsigned char*>(a.rec_in) + d.start * recsz, rec_bytes, bar);
+    tma_bulk_load(smem_raw + PassSmem<WIDE>::off_col, a.col_in + (d.start - coff), col_bytes, bar);
+}
+__device__ __forceinline__ void pass_make_desc(PassTile* desc, uint32_t tile, const ActiveDesc& act, uint32_t active) {
+    const uint64_t o = (uint64_t)(tile - act.tile_begin) * kTilePoints;
+    const uint64_t rem = act.count - o;
+    desc->m[0] = act.m[0], desc->m[1] = act.m[1], desc->m[2] = act.m[2];
+    desc->e = act.e;
+    desc->start = act.start + o;
+    desc->count = (uint32_t)(rem < kTilePoints ? rem : kTilePoints);
+    desc->active = active;
+    desc->tile = tile;
+    desc->valid = 1;
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_per_sm) k_pass(const __grid_constant__ PassArgs a) {
     constexpr int nbmax = kPassBins;
     constexpr int kThreads = PassCfg<WIDE>::threads, kWarps = PassCfg<WIDE>::warps, kWarpItems = PassCfg<WIDE>::warp_items, kSubRounds = PassCfg<WIDE>::sub_rounds;
+    constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t* perm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_perm);  // [tile] item | bucket << 12, sorted
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_cnt);    // [warps][nb]
-    uint4* bdst = reinterpret_cast<uint4*>(smem_raw + PassSmem<WIDE>::off_bdst);        // [nb]
-    uint32_t* lutm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_lutm);  // [nb] digit -> bucket (0xFFFF: none)
-    PassTile* descs = reinterpret_cast<PassTile*>(smem_raw + PassSmem<WIDE>::off_desc); // [2]
+    const unsigned char* srec = smem_raw;
+    uint32_t* perm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_perm);       // [tile] item | bucket << 12, sorted
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_cnt);         // [warps][nb]
+    PassBucket* bdst = reinterpret_cast<PassBucket*>(smem_raw + PassSmem<WIDE>::off_bdst);   // [nb]
+    uint32_t* lutm = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_lutm);       // [nb] digit -> bucket
+    uint32_t* bfirst = reinterpret_cast<uint32_t*>(smem_raw + PassSmem<WIDE>::off_first);    // [nb]
+    PassTile* descs = reinterpret_cast<PassTile*>(smem_raw + PassSmem<WIDE>::off_desc);      // [2]
     ActiveDesc* snact = reinterpret_cast<ActiveDesc*>(smem_raw + PassSmem<WIDE>::off_nact);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + PassSmem<WIDE>::off_bar);   // [2]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + PassSmem<WIDE>::off_bar);        // small[0], small[1], big
 
     const PassState ps = a.st->pass[a.pass];
     const int nb = a.nbins;
@@ -658,76 +728,53 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(c
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         const uint32_t act0 = a.tile_active[blockIdx.x];
-        pass_stage_tile<WIDE>(a, blockIdx.x, a.active[act0], act0, smem_raw, &descs[0], &mbar[0]);
+        pass_make_desc(&descs[0], blockIdx.x, a.active[act0], act0);
+        pass_stage_small<WIDE>(a, descs[0], smem_raw + PassSmem<WIDE>::off_small, &mbar[0]);
+        pass_stage_big<WIDE>(a, descs[0], smem_raw, &mbar[2]);
     }
     __syncthreads();
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < ps.ntiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it & 1u, par = (it >> 1) & 1u;
-        unsigned char* stage = smem_raw + (size_t)s * PassSmem<WIDE>::stage_bytes;
-        const unsigned char* srec = stage;
+        const uint32_t s = it & 1u;
         const PassTile& pt = descs[s];  // stays in shared memory (broadcast reads)
-        const uint32_t* scol = reinterpret_cast<const uint32_t*>(stage + PassSmem<WIDE>::st_col) + (uint32_t)(pt.start & 3);
-        const uint8_t* sdig = stage + PassSmem<WIDE>::st_dig + (uint32_t)(pt.start & 15);
-        const uint32_t* spfx = reinterpret_cast<const uint32_t*>(stage + PassSmem<WIDE>::st_pfx);
-        const BucketDesc* sbk = reinterpret_cast<const BucketDesc*>(stage + PassSmem<WIDE>::st_bk);
-        // the next tile of this block: its node is looked up by one thread, the loads are consumed two phases later
+        const unsigned char* sm = smem_raw + PassSmem<WIDE>::off_small + (size_t)s * PassSmem<WIDE>::small_bytes;
+        const uint32_t* scol = reinterpret_cast<const uint32_t*>(smem_raw + PassSmem<WIDE>::off_col) + (uint32_t)(pt.start & 3);
+        const uint8_t* sdig = sm + (uint32_t)(pt.start & 15);
+        const uint32_t* spfx = reinterpret_cast<const uint32_t*>(sm + PassSmem<WIDE>::sm_pfx);
+        const BucketDesc* sbk = reinterpret_cast<const BucketDesc*>(sm + PassSmem<WIDE>::sm_bk);
+        // the next tile of this block: its node is looked up by one thread, the loads are consumed phases later
         const uint32_t ntile = tile + gridDim.x;
         const bool stage_next = tid == 0 && ntile < ps.ntiles;
         uint32_t nact = 0;
         if (stage_next) nact = a.tile_active[ntile];
-
-        mbar_wait(&mbar[s], par);  // this tile's records / colours / digits / tables have landed
-        // (1) bucket tables: inclusive scan over digits of the tile's prefix row (exclusive prefix of the node's earlier tiles),
-        // then per bucket the destination of this tile's first record, what the destination stores and where it lives (warp 0)
-        if (warp == 0) {
-            const int per = (nb + 31) / 32;
-            const int b0 = lane * per, b1 = min(nb, b0 + per);
-            uint32_t sacc = 0;
-            for (int b = b0; b < b1; ++b) sacc += spfx[b];
-            uint32_t incl = sacc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            uint32_t run = incl - sacc;
-            for (int b = b0; b < b1; ++b) {
-                run += spfx[b];
-                lutm[b] = run;  // inclusive over digits (temporarily in lutm)
-            }
-            __syncwarp();
-            uint32_t v[2] = {0, 0};
-            BucketDesc bd[2];
-            for (int j = 0; j < 2; ++j) {
-                const int lb = lane + 32 * j;
-                if (lb < nb) {
-                    bd[j] = sbk[lb];
-                    if (bd[j].b1 != 0) v[j] = (uint32_t)bd[j].dest + (lutm[bd[j].b1 - 1] - (bd[j].b0 ? lutm[bd[j].b0 - 1] : 0u));
-                }
-            }
-            __syncwarp();
-            for (int b = lane; b < nb; b += 32) lutm[b] = 0xFFFFu;  // digits without points keep an invalid bucket
-            __syncwarp();
-            for (int j = 0; j < 2; ++j) {
-                const int lb = lane + 32 * j;
-                if (lb < nb) {
-                    if (bd[j].b1 != 0)
-                        for (uint32_t d = bd[j].b0; d < bd[j].b1; ++d) lutm[d] = (uint32_t)lb;  // every digit of the bucket's range learns its bucket
-                    bdst[lb] = make_uint4(v[j], 0u, bd[j].keep, bd[j].b1 != 0 && bd[j].kind ? 1u : 0u);
-                }
-            }
-        }
         for (int i = tid; i < kWarps * nbmax; i += kThreads) cnt[i] = 0;
+
+        mbar_wait(&mbar[s], (it >> 1) & 1u);  // digits, prefix row and bucket table of this tile (requested a tile ago)
+        // (1) tables, one thread per bucket: the slot of this tile's first record = bucket start + the records of the bucket's
+        // digits in the node's earlier tiles; every digit of the bucket's range learns its bucket.  (A digit without a bucket has
+        // no points in the node, so its map entry is never read.)
+        if (tid < nb) {
+            const BucketDesc bd = sbk[tid];
+            uint32_t v = 0;
+            if (bd.b1 != 0) {
+                v = (uint32_t)bd.dest;
+                for (uint32_t d = bd.b0; d < bd.b1; ++d) {
+                    v += spfx[d];
+                    lutm[d] = (uint32_t)tid;
+                }
+            }
+            bfirst[tid] = v;
+        }
         __syncthreads();
 
-        // (2) rank: bucket of every item from its carried digit; lanes of a sub-round grouped by bucket once
+        // (2) rank: bucket of every item from its carried digit; lanes of a sub-round grouped by bucket
         uint32_t info[kSubRounds];
         {
+            const uint32_t count = pt.count;
             uint32_t lbv[kSubRounds];
             unsigned mask[kSubRounds];
-            const uint32_t count = pt.count;
 #pragma unroll
             for (int r = 0; r < kSubRounds; ++r) {
                 const uint32_t i = warp * kWarpItems + r * 32 + lane;
@@ -752,7 +799,8 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(c
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         __syncthreads();
-        // (3) per-bucket totals -> exclusive scan over the buckets (sorted start of every bucket) -> per-warp offsets (warp 0)
+        // (3) per-bucket totals -> exclusive scan over the buckets (sorted start of every bucket) -> per-warp offsets and the
+        // bucket's store bases (warp 0)
         if (warp == 0) {
             uint32_t tot[2] = {0, 0};
             for (int j = 0; j < 2; ++j) {
@@ -779,7 +827,16 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(c
                 const int lb = lane + 32 * j;
                 if (lb < nb) {
                     uint32_t run = excl[j];
-                    bdst[lb].y = run;
+                    const BucketDesc bd = sbk[lb];
+                    const bool leaf = bd.b1 != 0 && bd.kind;
+                    const long long first = (long long)bfirst[lb] - (long long)run;  // slot of sorted position 0
+                    PassBucket pb;
+                    pb.rec = (unsigned long long)(leaf ? a.arena : a.rec_next) + (unsigned long long)(first * (long long)recsz);
+                    pb.col = (unsigned long long)(leaf ? a.col_arena : a.col_next) + (unsigned long long)(first * 4);
+                    pb.dig = (unsigned long long)a.dig_next + (unsigned long long)first;
+                    pb.start = run;
+                    pb.kk = (uint32_t)bd.keep | (leaf ? 0x100u : 0u);
+                    bdst[lb] = pb;
 #pragma unroll
                     for (int w = 0; w < kWarps; ++w) {
                         const uint32_t c = cnt[w * nbmax + lb];
@@ -805,22 +862,27 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, WIDE ? 1 : 2) k_pass(c
             if (lbv != 0xFFFFu) perm[old + rank] = i | (lbv << 12);
             __syncwarp();
         }
-        // the other stage was last read by the previous iteration (which ended in a barrier): refill it now, so that the
-        // copies run under this tile's finish sweep
+        // the other small buffer was last read by the previous tile: request the next tile's digits and tables now, a whole
+        // tile ahead of their use
         if (stage_next) {
             asm volatile("cp.async.wait_all;" ::: "memory");
-            pass_stage_tile<WIDE>(a, ntile, *snact, nact, smem_raw + (size_t)(s ^ 1u) * PassSmem<WIDE>::stage_bytes, &descs[s ^ 1u], &mbar[s ^ 1u]);
+            pass_make_desc(&descs[s ^ 1u], ntile, *snact, nact);
+            pass_stage_small<WIDE>(a, descs[s ^ 1u], smem_raw + PassSmem<WIDE>::off_small + (size_t)(s ^ 1u) * PassSmem<WIDE>::small_bytes, &mbar[s ^ 1u]);
         }
         __syncthreads();
         // (5) finish + store in destination order (speculatively through the reciprocal division; repeated with the IEEE
         // operator if any numerator of the block was outside the proven range - the stores are idempotent)
-        if (a.fast) {
-            const unsigned bad = a.fast == 2 ? pass_finish<WIDE, 2>(a, pt, srec, scol, sdig, perm, bdst) : pass_finish<WIDE, 1>(a, pt, srec, scol, sdig, perm, bdst);
+        mbar_wait(&mbar[2], it & 1u);  // records and colours: requested when the previous tile's sweep ended
+        if (a.fast == 2) {
+            pass_finish<WIDE, 2>(a, pt, srec, scol, sdig, perm, bdst);  // no per-numerator checks: nothing to repeat
+        } else if (a.fast == 1) {
+            const unsigned bad = pass_finish<WIDE, 1>(a, pt, srec, scol, sdig, perm, bdst);
             if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
         } else {
             pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
         }
-        __syncthreads();  // the stage, perm and the tables are reused
+        __syncthreads();  // records, colours, perm and the tables are reused
+        if (stage_next) pass_stage_big<WIDE>(a, descs[s ^ 1u], smem_raw, &mbar[2]);
     }
 }
 
@@ -1100,7 +1162,7 @@ struct CudaBackend : Backend {
         const int th = a.nbins < 32 ? 32 : a.nbins;
         prof_begin(K_DIGHIST, 0, a.pass);
         k_tile_index<<<std::min<uint32_t>(a.cap_chunks, 1024u), 256, 0, stream>>>(a);
-        k_dighist<<<nsm * 16, kDigThreads, 0, stream>>>(a);
+        k_dighist<<<nsm * 8, kDigThreads, 0, stream>>>(a);
         prof_end();
         prof_begin(K_SCAN, 0, a.pass);
         k_scan_chunk_sums<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
@@ -1108,15 +1170,20 @@ struct CudaBackend : Backend {
         k_scan_tiles<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
         prof_end();
         prof_begin(K_PLAN, 0, a.pass);
-        k_plan<<<1, kPlanThreads, 0, stream>>>(a);
+        {
+            const uint32_t pg = std::min<uint32_t>((a.cap_active + kPlanNodeThreads - 1) / kPlanNodeThreads, (uint32_t)nsm * 8u);
+            k_plan_count<<<pg, kPlanNodeThreads, 0, stream>>>(a);
+            k_plan_scan<<<1, kPlanThreads, 0, stream>>>(a);
+            k_plan_emit<<<pg, kPlanNodeThreads, 0, stream>>>(a);
+        }
         prof_end();
         prof_begin(K_PASS, 0, a.pass);
         if (a.wide)
-            k_pass<true><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)nsm), PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
+            k_pass<true><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<true>::blocks_per_sm)), PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
         else
-            k_pass<false><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)nsm * 2u), PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
+            k_pass<false><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<false>::blocks_per_sm)), PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
         prof_end();
-        launches += 7;
+        launches += 9;
         pass_wide = a.wide;
         PCV_CUDA_CHECK(cudaGetLastError());
     }

@@ -634,30 +634,9 @@ int pcv_synth_points_host(int kind, uint64_t seed, uint64_t first, uint64_t n, d
 
 int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* resolution) {
     if (!bbox_min || !bbox_max) return fail(PCV_ERR_INVALID, "null argument");
-    if (kind == PCV_SYNTH_SLAB_ECEF) {
-        // SyntheticData::bbox (synthetic_data.rs:46-50): Aabb of the 8 transformed slab corners
-        const SynthFrame f = slab_frame();
-        for (int i = 0; i < 8; ++i) {
-            double l[3] = {(i & 1) ? 100.0 : -100.0, (i & 2) ? 100.0 : -100.0, (i & 4) ? 10.0 : -10.0}, p[3];
-            frame_apply(f, l, p);
-            for (int a = 0; a < 3; ++a) {
-                bbox_min[a] = i ? std::fmin(bbox_min[a], p[a]) : p[a];
-                bbox_max[a] = i ? std::fmax(bbox_max[a], p[a]) : p[a];
-            }
-        }
-        if (resolution) *resolution = 0.001;  // point_cloud_test/src/lib.rs:45
-        return PCV_OK;
-    }
-    if (kind == PCV_SYNTH_GAUSS_CLUSTERS) {
-        const double gmin[3] = {300000.125, -200000.5, 1000.25};
-        for (int a = 0; a < 3; ++a) {
-            bbox_min[a] = gmin[a];
-            bbox_max[a] = gmin[a] + 1024.0;
-        }
-        if (resolution) *resolution = 1024.0 / 1048576.0;
-        return PCV_OK;
-    }
-    return fail(PCV_ERR_INVALID, "unknown synthetic kind %d", kind);
+    if (kind != PCV_SYNTH_SLAB_ECEF && kind != PCV_SYNTH_GAUSS_CLUSTERS) return fail(PCV_ERR_INVALID, "unknown synthetic kind %d", kind);
+    synth_bbox(kind, bbox_min, bbox_max, resolution);
+    return PCV_OK;
 }
 
 }  // extern "C"

@@ -52,6 +52,11 @@ def lib():
         dp, u8p, fp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint64)
         L.orc_build.restype = C.c_void_p
         L.orc_build.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, dp, dp, C.c_int64, C.c_int]
+        L.orc_build_faithful.restype = C.c_double
+        L.orc_build_faithful.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, dp, dp, C.c_int64, C.c_int,
+                                         C.c_char_p, u64p]
+        L.orc_synth_points.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_synth_bbox.argtypes = [C.c_int, dp, dp, dp]
         L.orc_build_seconds.restype = C.c_double
         L.orc_build_seconds.argtypes = [C.c_void_p]
         L.orc_free.argtypes = [C.c_void_p]
@@ -88,6 +93,8 @@ def lib():
         L.orc_visible_nodes.argtypes = [C.c_void_p, dp, C.c_void_p, C.c_int64]
         L.orc_query.restype = C.c_int64
         L.orc_query.argtypes = [C.c_void_p, LP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_query_batch_timed.restype = C.c_double
+        L.orc_query_batch_timed.argtypes = [C.c_void_p, LP, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p]
         L.orc_xray_tile_attr.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
         L.orc_xray_tile.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_write_dir.argtypes = [C.c_void_p, C.c_char_p]
@@ -208,6 +215,16 @@ class OracleOctree:
     def write_dir(self, d):
         assert lib().orc_write_dir(self.h, d.encode()) == 0
 
+    def query_batch_timed(self, locs, num_threads, batch_size=500000):
+        """ParallelIterator port over `locs` with `num_threads` workers: dict(seconds, tested, returned, bytes = B_query of SURVEY 8d)."""
+        arr = (Location * len(locs))()
+        for i, l in enumerate(locs):
+            for f, _ in Location._fields_:
+                setattr(arr[i], f, getattr(l, f))
+        t, r, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        s = lib().orc_query_batch_timed(self.h, arr, len(locs), int(num_threads), int(batch_size), C.byref(t), C.byref(r), C.byref(b))
+        return dict(seconds=s, tested=t.value, returned=r.value, bytes=b.value)
+
     def nodes_data_blob(self, names):
         """The web viewer's /nodes_data reply for the named nodes (backend.rs:92-165); KeyError(name) if one has no files."""
         ids = np.array([v for nm in names for v in id_from_str(nm)], np.uint64)
@@ -229,6 +246,36 @@ def build(x, y, z, rgb, resolution, bbox_min, bbox_max, intensity=None, max_poin
     rgb = np.ascontiguousarray(rgb, np.uint8)
     h = lib().orc_build(n, _ptr(x), _ptr(y), _ptr(z), stride, _ptr(rgb), _ptr(intensity), float(resolution), _d(bbox_min), _d(bbox_max), int(max_points_per_node), int(num_threads))
     return OracleOctree(h)
+
+
+def build_faithful(x, y, z, rgb, resolution, bbox_min, bbox_max, directory, intensity=None, max_points_per_node=100000, num_threads=0, stride=1):
+    """build_octree with the reference's file round trips: node files + meta.pb are left in `directory`.  Returns (seconds, nodes)."""
+    n = len(rgb) // 3 if rgb.ndim == 1 else rgb.shape[0]
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    nn = C.c_uint64()
+    t = lib().orc_build_faithful(n, _ptr(x), _ptr(y), _ptr(z), stride, _ptr(rgb), _ptr(intensity), float(resolution), _d(bbox_min), _d(bbox_max),
+                                 int(max_points_per_node), int(num_threads), os.fsencode(directory), C.byref(nn))
+    if t < 0:
+        raise IOError("oracle faithful build failed in " + directory)
+    return t, nn.value
+
+
+SYNTH_SLAB_ECEF, SYNTH_GAUSS_CLUSTERS = 1, 2
+
+
+def synth_points(kind, seed, first, n, num_threads=0):
+    """The benchmark's input generators (include/pcv_synth.h) on host threads: x, y, z (f64) and rgb (n*3 u8)."""
+    n = int(n)
+    x, y, z = np.empty(n), np.empty(n), np.empty(n)
+    rgb = np.empty(3 * n, np.uint8)
+    lib().orc_synth_points(kind, seed, first, n, _ptr(x), _ptr(y), _ptr(z), _ptr(rgb), num_threads)
+    return x, y, z, rgb
+
+
+def synth_bbox(kind):
+    mn, mx, res = (C.c_double * 3)(), (C.c_double * 3)(), C.c_double()
+    lib().orc_synth_bbox(kind, mn, mx, C.byref(res))
+    return np.array(mn), np.array(mx), res.value
 
 
 def load_dir(d):
