@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — build_octree (+ frustum query) throughput on B200, one JSON line on rank 0.
+"""bench.py — build_octree (+ frustum query, X-ray tiles) throughput on B200, one JSON line on rank 0.
 
   python bench.py --gpus N --steps K --warmup W          the CUDA path (this repo)
-  python bench.py --impl reference --gpus N ...           the reference's CPU algorithm (oracle port) on host cores
+  python bench.py --impl reference --gpus N ...           the reference's CPU algorithm (oracle port) on the host cores
 
-A step = one build_octree over one batch of synthetic points (BASELINE.json config 2: Gaussian clusters in a
-1024 m cube, resolution 1024/2^20 -> depth 20).  At N=1 the batch is 1e9 points; at N>1 every rank owns 1e9
-points of the same global index space (weak scaling; config 4), bucketed by octree path prefix with one NCCL
-all-to-all.  `value` = points / device time with the inputs already in HBM; `e2e` = the same build through the
-C-ABI host entry point: pinned host buffers -> H2D -> build -> D2H of the node arrays, all inside the timed region.
+A step = one build_octree over one batch of synthetic points (BASELINE.json config 2: Gaussian clusters in a 1024 m cube,
+resolution 1024/2^20 -> depth 20, 1e9 points per GPU).  At N > 1 every rank owns the same number of points of one global index
+space (weak scaling; config 4 = 8e9 points on 8 GPUs): the points shard by level-2 octree prefix and move once to their owners
+over NVLink (one fused rank + peer-store kernel, CUDA-IPC mapped receive slabs; NCCL carries only the small all-reduces).
+`value` = points / device time of the step (a CUDA event pair around the call, host planning included, max over ranks) with the
+inputs resident in HBM; `e2e` = the same build through the C-ABI host entry point: pinned host buffers -> H2D -> build -> D2H
+of the node arrays, all inside the timed region.  Next to it (N = 1): per-kernel roofline from CUDA events on the library's
+stream, the frustum query and X-ray tile workloads (configs 3 and 5) with their own rooflines and CPU baselines, the reference's
+own bench sizes (config 1) and a parity verdict of the GPU octree against the oracle on a sample of the same generator.
+
+The reference arm never loads the CUDA library: generator, in-memory and file-backed ("faithful") builds all come from oracle/.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
-import threading
+import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -24,6 +31,7 @@ sys.path.insert(0, ROOT)
 SEED = 1
 METRIC = "build_octree Mpoints/sec"
 UNIT = "Mpoints/s"
+SLAB_SEED = 80293751232  # point_cloud_test/src/lib.rs:46
 
 
 def _peaks():
@@ -81,57 +89,94 @@ def workload_config(n, world, args):
     """The `config` object of the JSON line - shared by both arms so that the reference arm names the same workload."""
     return {
         "workload": "build_octree on %d synthetic Gaussian-cluster points per GPU (BASELINE config %d), resolution 1024/2^20 (depth 20), XYZ f64 SoA + RGB" % (n, 2 if world == 1 else 4),
-        "points_per_gpu": n, "levels_per_pass": args.levels_per_pass, "max_points_per_node": 100000,
+        "points_per_gpu": n, "levels_per_pass": 2, "max_points_per_node": 100000,
         "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (27.0 * n / 1e9),
-        "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix; one fused pack+exchange kernel stores every point into its owner's memory over NVLink (CUDA IPC peer mapping), NCCL only for the small all-reduces" % args.prefix_levels,
+        "parallelism": "single GPU" if world == 1 else "points shard by level-%d octree prefix; one fused rank + peer-store kernel moves every point into its owner's memory over NVLink (CUDA IPC), NCCL only for the small all-reduces" % args.prefix_levels,
     }
 
 
+def _shm_dir():
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    return tempfile.mkdtemp(prefix="pcv_bench_", dir=d)
+
+
+def cpu_build_times(O, x, y, z, rgb3, res, bmin, bmax, cores, steps_mem, steps_faithful):
+    """Oracle build_octree, both variants: in memory and with the reference's file round trips (/dev/shm)."""
+    tm, tf = [], []
+    for _ in range(steps_mem):
+        t0 = time.perf_counter()
+        o = O.build(x, y, z, rgb3, res, bmin, bmax, num_threads=cores)
+        tm.append(time.perf_counter() - t0)
+        del o
+    for _ in range(steps_faithful):
+        d = _shm_dir()
+        try:
+            t0 = time.perf_counter()
+            O.build_faithful(x, y, z, rgb3, res, bmin, bmax, d, num_threads=cores)
+            tf.append(time.perf_counter() - t0)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return tm, tf
+
+
+def config1_cpu(O, cores):
+    """The reference's own bench shapes (point_cloud_test/benches/main.rs:10-19, src/lib.rs:42-61): 1e5 and 1e6 slab points,
+    resolution 0.001, on the oracle (both variants)."""
+    out = {}
+    bmin, bmax, res = O.synth_bbox(O.SYNTH_SLAB_ECEF)
+    th = min(cores, 10)  # build_octree's default: 10 rayon threads (src/bin/build_octree.rs:37)
+    for n in (100_000, 1_000_000):
+        x, y, z, rgb = O.synth_points(O.SYNTH_SLAB_ECEF, SLAB_SEED, 0, n, num_threads=cores)
+        tm, tf = cpu_build_times(O, x, y, z, rgb.reshape(-1, 3), res, bmin, bmax, th, 3, 2)
+        out[str(n)] = {"in_memory_ms": min(tm) * 1e3, "faithful_ms": min(tf) * 1e3, "Mpoints_per_s": n / min(min(tm), min(tf)) / 1e6, "threads": th}
+    return out
+
+
 def run_reference(args):
-    """The reference's own algorithm on the host cores: the oracle (C++ restatement of build_octree, same task
-    structure: serial root split, one task per split node, per-level parallel subsampling; in-memory variant, i.e.
-    without the reference's file round trips).  Each step builds a bounded sample of the same workload."""
+    """The reference's own algorithm on the host cores: the oracle (C++ restatement of build_octree with the reference's task
+    structure: serial root split, one task per split node, per-level parallel subsampling), in memory and file-backed.  Each
+    step builds a bounded sample (default 1e8 points) of the N = 1 workload; the line's value is the faster variant."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
-
     import oracle_api as O
-    import point_cloud_viewer_b200 as pcv
 
     n = int(args.ref_points)
-    x, y, z, rgb = pcv.synth_points_host(pcv.SYNTH_GAUSS_CLUSTERS, SEED, 0, n)
-    bmin, bmax, res = pcv.synth_bbox(pcv.SYNTH_GAUSS_CLUSTERS)
     cores = os.cpu_count() or 1
+    x, y, z, rgb = O.synth_points(O.SYNTH_GAUSS_CLUSTERS, SEED, 0, n, num_threads=cores)
+    bmin, bmax, res = O.synth_bbox(O.SYNTH_GAUSS_CLUSTERS)
     rgb3 = rgb.reshape(-1, 3)
-    for _ in range(args.warmup):
-        O.build(x, y, z, rgb3, res, bmin, bmax, num_threads=cores)
-    t = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        o = O.build(x, y, z, rgb3, res, bmin, bmax, num_threads=cores)
-        t.append(time.perf_counter() - t0)
-        del o
-    ms = sum(t) / len(t) * 1e3
+    cpu_build_times(O, x, y, z, rgb3, res, bmin, bmax, cores, min(args.warmup, 1), 0)
+    tm, tf = cpu_build_times(O, x, y, z, rgb3, res, bmin, bmax, cores, args.steps, min(args.steps, 3))
+    ms_mem, ms_f = sum(tm) / len(tm) * 1e3, sum(tf) / len(tf) * 1e3
+    ms = min(ms_mem, ms_f)
     v = n / (ms * 1e3)
-    sample = "first %d points of the same generator per step (in-memory oracle port, %d threads)" % (n, cores)
-    print(json.dumps({
+    full = int(args.points)
+    sample = "first %d points of the same generator per step, %d threads; in-memory %.0f ms (%d steps), faithful (/dev/shm node files) %.0f ms (%d steps); value = the faster" % (
+        n, cores, ms_mem, len(tm), ms_f, len(tf))
+    cfg = workload_config(full, args.gpus, args)
+    cfg.update(sample_points_per_step=n, same_config=(n == full),
+               note="the reference's CPU algorithm (oracle port) timed on a bounded sample of this workload: the ratio to the GPU arm extrapolates the per-point rate")
+    line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(int(args.points) if args.gpus == 1 or args.points_multi <= 0 else int(args.points_multi), args.gpus, args),
-                       sample_points_per_step=n, note="the reference's CPU algorithm (oracle port) timed on a bounded sample of this workload"),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "variants": {"in_memory_Mpoints_per_s": n / (ms_mem * 1e3), "faithful_Mpoints_per_s": n / (ms_f * 1e3)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    try:
+        line["config1"] = config1_cpu(O, cores)
+    except Exception as e:
+        line["config1"] = {"error": str(e)[:200]}
+    print(json.dumps(line))
 
 
-def make_frusta(pcv, bmin, bmax, count, far, seed=7):
+def make_frusta(G, bmin, bmax, count, far, seed=7):
     """eye uniform in the bbox, orientation = normalised 4-vector of Irwin-Hall variates,
     Perspective3(aspect 1.0, fovy 1.2, near 0.1, far) as in point_cloud_test/src/queries.rs:38-44."""
     import numpy as np
 
-    G = pcv.geometry
     rng = np.random.default_rng(seed)
     locs = []
     persp = G.Perspective.new_fov(1.0, 1.2, 0.1, far)
@@ -197,6 +242,35 @@ def bench_ply(ctx, pcv, n, peak):
             os.remove(path)
 
 
+def bench_config1(ctx, pcv, torch, O, cores):
+    """BASELINE config 1 on the GPU: the reference's bench shapes (1e5 and 1e6 slab points) through the host entry point
+    (pageable numpy arrays in, octree resident) and device resident, next to the oracle on the host cores."""
+    out = {}
+    bmin, bmax, res = pcv.synth_bbox(pcv.SYNTH_SLAB_ECEF)
+    cpu = config1_cpu(O, cores)
+    for n in (100_000, 1_000_000):
+        x, y, z, rgb = O.synth_points(O.SYNTH_SLAB_ECEF, SLAB_SEED, 0, n, num_threads=cores)
+        dx, dy, dz = [torch.from_numpy(a).cuda() for a in (x, y, z)]
+        drgb = torch.from_numpy(rgb).cuda()
+        host_ms, dev_ms = [], []
+        nodes = 0
+        for i in range(6):
+            t0 = time.perf_counter()
+            t = ctx.build_octree(x, y, z, rgb, res, bmin, bmax)
+            host_ms.append((time.perf_counter() - t0) * 1e3)
+            nodes = int(t.num_nodes)
+            t.free()
+            t0 = time.perf_counter()
+            t = ctx.build_octree(dx.data_ptr(), dy.data_ptr(), dz.data_ptr(), drgb.data_ptr(), res, bmin, bmax, n=n, device=True)
+            dev_ms.append((time.perf_counter() - t0) * 1e3)
+            t.free()
+        h, d = min(host_ms[1:]), min(dev_ms[1:])
+        c = cpu[str(n)]
+        out[str(n)] = {"gpu_host_api_ms": h, "gpu_device_resident_ms": d, "gpu_Mpoints_per_s_host_api": n / (h * 1e3), "gpu_Mpoints_per_s_device": n / (d * 1e3),
+                       "octree_nodes": nodes, "cpu": c, "speedup_host_api_vs_cpu": min(c["in_memory_ms"], c["faithful_ms"]) / h}
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -212,22 +286,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = int(args.points)
-    if world > 1 and args.points_multi > 0:
-        # The sharded build stages every point twice (send + receive buffers, 35 B/pt each) next to the input (27 B/pt)
-        # and the build's working set (~80 B/pt): 1e9 points per GPU would need ~177 GB of the 180 GB.  N > 1 therefore
-        # runs a fixed 5e8 points per GPU (weak scaling across N = 2, 4, 8); N = 1 keeps BASELINE config 2 (1e9).
-        n = int(args.points_multi)
     kind = pcv.SYNTH_GAUSS_CLUSTERS
     bmin, bmax, res = pcv.synth_bbox(kind)
-    ctx = pcv.Context(local, levels_per_pass=args.levels_per_pass)
+    ctx = pcv.Context(local)
 
-    def make_input():
-        xs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
-        c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
-        ctx.synth_points_device(kind, SEED, rank * n, n, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
+    def make_input(count, first):
+        xs = [torch.empty(count, dtype=torch.float64, device=dev) for _ in range(3)]
+        c = torch.empty(count * 3, dtype=torch.uint8, device=dev)
+        ctx.synth_points_device(kind, SEED, first, count, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
         return xs[0], xs[1], xs[2], c
-
-    x, y, z, rgb = make_input()
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,8 +302,19 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    out_extra = {}
     if world > 1:
         from point_cloud_viewer_b200 import distributed as D
+
+        # ---- multi-GPU parity, inside the measured run: sharded vs single-GPU vs oracle on a small global sample ----
+        try:
+            out_extra["parity_check"] = D.parity_check(ctx, world, rank, dev, kind, SEED, int(args.parity_points), res, bmin, bmax, args.prefix_levels, ROOT)
+        except Exception as e:
+            out_extra["parity_check"] = {"equal": False, "error": str(e)[:300]}
+
+    x, y, z, rgb = make_input(n, rank * n)
+
+    if world > 1:
 
         def step():
             return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
@@ -255,28 +333,28 @@ def run_ours(args):
         sampler.start()
     dev_ms = 0.0
     wall_ms = 0.0
+    lib_ms = 0.0
     last = None
     for _ in range(args.steps):
         if last is not None:
             last.free()
         barrier()
+        # The library works on its own stream and every step ends in a host-visible synchronisation, so an event pair on the
+        # current stream brackets exactly the device timeline of the step, host planning gaps included (same clock at every N).
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         w0 = time.perf_counter()
         last = step()
         torch.cuda.synchronize()
         e1.record()
-        barrier()
+        torch.cuda.synchronize()
         wall_ms += (time.perf_counter() - w0) * 1e3
+        dev_ms += e0.elapsed_time(e1)
         if world == 1:
-            dev_ms += ctx.last_build_stats()["ms_total"]
-        else:
-            # every phase of a sharded step ends in a host-visible synchronisation (histogram read-back, all-to-all, build),
-            # so the event pair on the current stream brackets exactly the device timeline of the step
-            dev_ms += e0.elapsed_time(e1)
+            lib_ms += ctx.last_build_stats()["ms_total"]
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launch_count() - launches0
-    # device time of the K steps: CUDA events on the library's stream around every build, max over ranks
     tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -290,12 +368,27 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, world, args),
-        "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": int(launches), "octree_nodes": nodes, "deepest_level": int(stats["deepest_level"]),
+        "wall_ms_per_step": wall_ms / args.steps, "gpu_launches": int(launches), "octree_nodes": nodes, "deepest_level": int(stats.get("deepest_level", 0)),
         "clocks": clocks,
     }
+    out.update(out_extra)
+    if world == 1:
+        out["library_event_ms_per_step"] = lib_ms / args.steps
+    if world > 1:
+        # full-size invariants of the sharded result, all-reduced: every point exactly once (count, sum and sum of squares of the
+        # global source indices), and the per-phase breakdown of the last step
+        try:
+            out["full_size_check"] = D.full_size_check(last, world, n, dev)
+        except Exception as e:
+            out["full_size_check"] = {"ok": False, "error": str(e)[:300]}
+        out["phases_ms"] = getattr(last, "phases_ms", None)
 
     if world == 1 and not args.no_extras:
         peak, peak_src = _peaks()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+
+        cores = os.cpu_count() or 1
         # ---- roofline of the dominant kernel: one extra build with CUDA events around every launch ----
         ctx.set_profiling(True)
         t = step()
@@ -315,29 +408,22 @@ def run_ours(args):
             "bound": "hbm", "kernel": tname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "launches": tst["launches"], "avg_launch_ms": tst["ms"] / max(1, tst["launches"]),
             "algorithmic_bytes_per_launch": tst["algorithmic_bytes"] / max(1, tst["launches"]),
-            "note": "the descent inside k_hist/k_scatter is IEEE binary64 divide+FMA per level per axis (reference codec semantics): FP64-issue bound before HBM bound; see DESIGN.md",
+            "note": "per-kernel bytes are the pass-local reads + writes (records 16 B + colour 4 B + digit 1 B per point and pass); whole_build uses the SURVEY 8(d) compulsory bytes: 27 N + sum over nodes of n (3 bpc + 3)",
             "whole_build": {"algorithmic_bytes": int(stats["algorithmic_bytes"]), "achieved": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9,
                             "frac": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9 / peak},
             "kernels": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for k, v in ks.items()},
         }
 
-        # ---- secondary metric: frustum-culled point query over the resident octree (BASELINE config 3) ----
+        # ---- BASELINE config 3: frustum-culled point query over the resident octree ----
         try:
-            fq = {}
-            for label, far in (("far10", 10.0), ("far0.1E", 102.4)):
-                locs = make_frusta(pcv, bmin, bmax, args.frusta if far < 50 else max(1, args.frusta // 10), far)
-                last.query_batch_device(locs[:8])  # warm-up (tables, pool)
-                l0 = ctx.kernel_launch_count()
-                torch.cuda.synchronize()
-                q0 = time.perf_counter()
-                counts, tested = last.query_batch_device(locs)
-                torch.cuda.synchronize()
-                qms = (time.perf_counter() - q0) * 1e3
-                fq[label] = {"frusta": len(locs), "tested_points": int(tested.sum()), "returned_points": int(counts.sum()), "ms": qms,
-                             "Mpoints_per_s_tested": float(tested.sum()) / (qms * 1e3), "gpu_launches": int(ctx.kernel_launch_count() - l0)}
-            out["frustum_query"] = fq
+            out["frustum_query"] = bench_query(ctx, pcv, torch, O, last, args, bmin, bmax, peak, cores, res)
         except Exception as e:  # never lose the build line
-            out["frustum_query"] = {"error": str(e)[:200]}
+            out["frustum_query"] = {"error": str(e)[:300]}
+        # ---- BASELINE config 5: X-ray leaf tiles over the resident octree ----
+        try:
+            out["xray"] = bench_xray(ctx, pcv, torch, O, last, args, bmin, bmax, peak, cores, res)
+        except Exception as e:
+            out["xray"] = {"error": str(e)[:300]}
 
         # ---- e2e: the reference-facing call with HOST buffers (H2D + build + D2H inside the timed region) ----
         last.free()
@@ -356,17 +442,11 @@ def run_ours(args):
             orgb = torch.empty(ne * 3, dtype=torch.uint8, pin_memory=True)
 
             def e2e_step():
-                q0 = time.perf_counter()
                 t = ctx.build_octree(hx.data_ptr(), hy.data_ptr(), hz.data_ptr(), hrgb.data_ptr(), res, bmin, bmax, n=ne)
-                q1 = time.perf_counter()
                 assert t.xyz_bytes <= oxyz.numel()
                 t.download(xyz=oxyz.data_ptr(), rgb=orgb.data_ptr(), want_src=False)  # what build_octree leaves on disk: .xyz + .rgb + meta
-                q2 = time.perf_counter()
                 b = (t.xyz_bytes + ne * 3 + 80 * t.num_nodes, t.num_nodes)
                 t.free()
-                if os.environ.get("PCV_TIMING"):
-                    print("[e2e] build call %.1f ms, download %.1f ms (%.2f GB), free %.1f ms" % ((q1 - q0) * 1e3, (q2 - q1) * 1e3, b[0] / 1e9, (time.perf_counter() - q2) * 1e3),
-                          file=sys.stderr)
                 return b
 
             e2e_step()  # two warm-up calls: the stream-ordered pool grows to hold the 27 GB staging copy
@@ -380,25 +460,45 @@ def run_ours(args):
             ems = (time.perf_counter() - w0) * 1e3 / esteps
             out["e2e"] = {"value": ne / (ems * 1e3), "unit": UNIT, "h2d_bytes_per_step": int(27 * ne), "d2h_bytes_per_step": int(d2h), "ms_per_step": ems, "steps": esteps,
                           "note": "pcv_build_octree(host SoA, pinned) + pcv_octree_download(pinned): node table, .xyz codes and .rgb of every node"}
+            del hx, hy, hz, hrgb, oxyz, orgb
         except Exception as e:
             out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": str(e)[:200]}
 
-        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample; and the parity verdict on that sample ----
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import oracle_api as O
-
             nc = int(args.cpu_points)
-            cx, cy, cz, crgb = pcv.synth_points_host(kind, SEED, 0, nc)
-            cores = os.cpu_count() or 1
+            cx, cy, cz, crgb = O.synth_points(O.SYNTH_GAUSS_CLUSTERS, SEED, 0, nc, num_threads=cores)
             t0 = time.perf_counter()
             o = O.build(cx, cy, cz, crgb.reshape(-1, 3), res, bmin, bmax, num_threads=cores)
             ct = time.perf_counter() - t0
+            d = _shm_dir()
+            try:
+                ft, _ = O.build_faithful(cx, cy, cz, crgb.reshape(-1, 3), res, bmin, bmax, d, num_threads=cores)
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+            best = min(ct, ft)
+            out["cpu_baseline"] = {"value": nc / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "first %d points of the same generator, one build per variant (oracle port of build_octree, %d threads): in-memory %.2f s, faithful (/dev/shm node files) %.2f s; value = the faster" % (nc, cores, ct, ft)}
+            try:
+                from parity import compare_trees
+
+                gt = ctx.build_octree(cx, cy, cz, crgb, res, bmin, bmax)
+                compare_trees(o, gt)
+                deep = max(len(nm) - 1 for nm in o.nodes)
+                out["parity_check"] = {"n": nc, "equal": True, "nodes": len(o.nodes), "deepest_level": deep,
+                                       "what": "GPU octree of the first n points of the benchmark generator == oracle: node set, counts, encodings, cubes, per-slot source index, colours, position codes"}
+                gt.free()
+            except AssertionError as e:
+                out["parity_check"] = {"n": nc, "equal": False, "error": str(e)[:300]}
             del o
-            out["cpu_baseline"] = {"value": nc / ct / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "first %d points of the same generator, one build (in-memory oracle port of build_octree, %d threads, %.1f s)" % (nc, cores, ct)}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + str(e)[:160]}
+
+        # ---- BASELINE config 1: the reference's own bench sizes on both sides ----
+        try:
+            out["config1"] = bench_config1(ctx, pcv, torch, O, cores)
+        except Exception as e:
+            out["config1"] = {"error": str(e)[:300]}
 
         # ---- PLY input path: file -> pinned ring -> H2D -> k_ply_unpack (+ fused bounding box) ----
         try:
@@ -416,20 +516,106 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def bench_query(ctx, pcv, torch, O, tree, args, bmin, bmax, peak, cores, res):
+    """Config 3: 1000 random frusta (two far planes) over the resident 1e9-point octree.  Device time from the library's CUDA
+    events; bytes = B_query of SURVEY 8(d) (decode read of every tested point + 27 B per survivor).  CPU baseline: the oracle's
+    ParallelIterator port (cores - 1 threads, point_cloud_client/src/lib.rs:67) over an octree of the first --cpu-points points."""
+    G = pcv.geometry
+    fq = {}
+    sets = (("far10", 10.0, args.frusta), ("far0.1E", 102.4, args.frusta))
+    for label, far, count in sets:
+        locs = make_frusta(G, bmin, bmax, count, far)
+        tree.query_batch_device(locs[:8])  # warm-up (tables, pool)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            q0 = time.perf_counter()
+            counts, tested = tree.query_batch_device(locs)
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - q0) * 1e3
+            qs = tree.last_query_stats()
+            if best is None or qs["ms_device"] < best[0]["ms_device"]:
+                best = (qs, wall, counts, tested)
+        qs, wall, counts, tested = best
+        gbps = qs["algorithmic_bytes"] / (qs["ms_device"] * 1e-3) / 1e9 if qs["ms_device"] > 0 else 0.0
+        fq[label] = {"frusta": len(locs), "tested_points": int(tested.sum()), "returned_points": int(counts.sum()), "ms_device": qs["ms_device"], "ms_wall": wall,
+                     "Mpoints_per_s_tested": float(tested.sum()) / (qs["ms_device"] * 1e3), "gpu_launches": int(qs["kernel_launches"]),
+                     "roofline": {"bound": "hbm", "kernel": "k_cull", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak,
+                                  "algorithmic_bytes": int(qs["algorithmic_bytes"]), "cull_kernel_ms": qs["ms_cull"]}}
+    # CPU baseline on a sample octree (the oracle cannot hold 1e9 points in this run's time budget)
+    nc = int(args.cpu_points)
+    cx, cy, cz, crgb = O.synth_points(O.SYNTH_GAUSS_CLUSTERS, SEED, 0, nc, num_threads=cores)
+    o = O.build(cx, cy, cz, crgb.reshape(-1, 3), res, bmin, bmax, num_threads=cores)
+    gt = ctx.build_octree(cx, cy, cz, crgb, res, bmin, bmax)
+    for label, far, count in sets:
+        locs = make_frusta(G, bmin, bmax, min(count, 200), far)
+        r = o.query_batch_timed(locs, max(1, cores - 1))
+        gc, gtst = gt.query_batch_device(locs)
+        qs = gt.last_query_stats()
+        fq[label]["cpu_baseline"] = {"value": r["tested"] / r["seconds"] / 1e6 if r["seconds"] > 0 else None, "unit": "Mpoints/s tested", "cores": max(1, cores - 1), "kind": "port",
+                                     "sample": "%d frusta over the octree of the first %d points (oracle ParallelIterator port)" % (len(locs), nc),
+                                     "tested_points": r["tested"], "returned_points": r["returned"], "seconds": r["seconds"],
+                                     "gpu_same_sample": {"tested_points": int(gtst.sum()), "returned_points": int(gc.sum()), "ms_device": qs["ms_device"],
+                                                         "equal_counts": bool(int(gtst.sum()) == r["tested"] and int(gc.sum()) == r["returned"])}}
+    gt.free()
+    return fq
+
+
+def bench_xray(ctx, pcv, torch, O, tree, args, bmin, bmax, peak, cores, res):
+    """Config 5: the 16 leaf tiles (4 x 4 tiles of 256 m, 4096 x 4096 px of 0.0625 m) of the X-ray quadtree over the resident
+    octree (xray/src/generation.rs:515-548,618-654), XRay colouring; bytes = B_xray of SURVEY 8(d)."""
+    tile_px = int(args.xray_px)
+    e = float(bmax[0] - bmin[0])
+    nt = 4
+    ts = e / nt
+    ms, pts, byts, nonempty = 0.0, 0, 0, 0
+    for iy in range(nt):
+        for ix in range(nt):
+            tmin = (bmin[0] + ix * ts, bmin[1] + iy * ts, bmin[2])
+            tmax = (bmin[0] + (ix + 1) * ts, bmin[1] + (iy + 1) * ts, bmax[2])
+            anyp, _rgba, _ = tree.xray_tile(tmin, tmax, tile_px, tile_px, None, want_bits=False)
+            xs = tree.last_xray_stats()
+            ms += xs["ms_device"]
+            pts += xs["points"]
+            byts += xs["algorithmic_bytes"]
+            nonempty += 1 if anyp else 0
+    gbps = byts / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    out = {"tiles": nt * nt, "tile_px": tile_px, "non_empty_tiles": nonempty, "points": int(pts), "ms_device": ms, "Mpoints_per_s": pts / (ms * 1e3) if ms > 0 else None,
+           "roofline": {"bound": "hbm", "kernel": "k_xray_*", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak, "algorithmic_bytes": int(byts)}}
+    # CPU baseline: the oracle's xray_from_points on a sample octree, one tile per core like the reference's rayon tile loop
+    nc = int(args.cpu_points)
+    cx, cy, cz, crgb = O.synth_points(O.SYNTH_GAUSS_CLUSTERS, SEED, 0, nc, num_threads=cores)
+    o = O.build(cx, cy, cz, crgb.reshape(-1, 3), res, bmin, bmax, num_threads=cores)
+    px = min(tile_px, 1024)
+    t0 = time.perf_counter()
+    tmin, tmax = (bmin[0], bmin[1], bmin[2]), (bmin[0] + ts, bmin[1] + ts, bmax[2])
+    o.xray_tile(tmin, tmax, px, px)
+    ct = time.perf_counter() - t0
+    loc = pcv.geometry.aabb(tmin, tmax)
+    ol = O.Location()
+    for f, _ in O.Location._fields_:
+        setattr(ol, f, getattr(loc, f))
+    npts = len(o.query(ol)["src"])
+    out["cpu_baseline"] = {"value": npts / ct / 1e6 if ct > 0 else None, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                           "sample": "one %d x %d leaf tile over the octree of the first %d points (%d points in the tile, %.2f s; the reference runs one tile per core)" % (px, px, nc, npts, ct)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=float, default=1e9, help="points per GPU per step")
-    ap.add_argument("--points-multi", type=float, default=5e8, help="points per GPU per step when --gpus > 1 (0: use --points)")
-    ap.add_argument("--levels-per-pass", type=int, default=2)
+    ap.add_argument("--points", type=float, default=1e9, help="points per GPU per step (the same at every N)")
+    ap.add_argument("--levels-per-pass", type=int, default=2, help="(accepted for compatibility: the split phase resolves two levels per pass)")
     ap.add_argument("--prefix-levels", type=int, default=2)
     ap.add_argument("--frusta", type=int, default=1000)
+    ap.add_argument("--xray-px", type=int, default=4096)
     ap.add_argument("--cpu-points", type=float, default=2e7)
+    ap.add_argument("--parity-points", type=float, default=1.6e7, help="global sample of the N > 1 parity check (sharded vs single GPU vs oracle)")
     ap.add_argument("--ply-points", type=float, default=1e8, help="points of the synthetic PLY file for the ingest measurement")
-    ap.add_argument("--ref-points", type=float, default=2e7, help="points of the bounded sample each --impl reference step builds")
+    ap.add_argument("--ref-points", type=float, default=1e8, help="points of the bounded sample each --impl reference step builds")
     ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the timed build steps (no roofline / query / e2e / CPU legs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

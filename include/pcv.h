@@ -153,11 +153,31 @@ int pcv_query_points(const pcv_octree* o, const pcv_location* loc, const pcv_int
 int pcv_query_batch_device(const pcv_octree* o, const pcv_location* locs, uint32_t nloc, const pcv_interval* filters,
                            uint32_t nfilt, uint64_t* counts_out, uint64_t* tested_out);
 
+/* Timing / traffic of the last pcv_query_batch_device call on the context (CUDA events on the context's stream). */
+typedef struct pcv_query_stats {
+    float ms_device;            /* first kernel to last kernel of the call                                   */
+    float ms_select;            /* node selection: per-level frontier kernels + work-list build              */
+    float ms_cull;              /* the culling kernel                                                        */
+    uint32_t kernel_launches;
+    uint64_t algorithmic_bytes; /* SURVEY 8(d) B_query: sum over visited (location, node) of n (3 bpc + 3) + 27 per survivor */
+    uint64_t tested_points, returned_points, stored_points; /* stored <= returned: survivors beyond the output capacity are only counted */
+    uint64_t visited_pairs;     /* (location, node) pairs with points that were culled                       */
+} pcv_query_stats;
+int pcv_last_query_stats(pcv_ctx* ctx, pcv_query_stats* out);
+
 /* ---- a19: X-ray leaf tile (xray/src/generation.rs:108-127,159-198,464-513) ------------------ */
 /* query_from_global: 7 doubles or NULL.  rgba_out: w*h*4.  Returns any_points_out=0 for an empty tile
  * (the reference returns None). zbits_out (optional): w*h*32 u32 z-bucket bitsets. */
 int pcv_xray_tile(const pcv_octree* o, const double tile_min[3], const double tile_max[3], uint32_t w, uint32_t h,
                   const double* query_from_global, uint8_t* rgba_out, uint32_t* zbits_out, int* any_points_out);
+/* Timing / traffic of the last pcv_xray_tile[_attr] call on the context. */
+typedef struct pcv_xray_stats {
+    float ms_device;            /* CUDA events around the call's kernels                                    */
+    uint32_t kernel_launches;
+    uint64_t points;            /* points of the nodes the tile intersects (decoded + tested)               */
+    uint64_t algorithmic_bytes; /* SURVEY 8(d) B_xray: sum over nodes of n (3 bpc + 3) + 4 W H               */
+} pcv_xray_stats;
+int pcv_last_xray_stats(pcv_ctx* ctx, pcv_xray_stats* out);
 /* The other ColoringStrategyKinds (xray/src/generation.rs:76-97): point colour mean (:294-363), intensity mean brightened
  * by ln(mean - min) / ln(max - min) (:210-290; p0 = min, p1 = max), height standard deviation through the Jet (0) or
  * Purplish (1) colormap (:365-405, xray/src/colormap.rs; p0 = max_stddev).  Binning = None.  The reference accumulates in

@@ -438,6 +438,17 @@ class Octree:
         N.check(N.lib().pcv_query_batch_device(self.h, arr, len(locs), _p(f) if nf else None, nf, _p(counts), _p(tested)))
         return counts, tested
 
+    def last_query_stats(self):
+        """Timing / traffic of the last query_batch_device call (pcv_query_stats)."""
+        st = N.QueryStats()
+        N.check(N.lib().pcv_last_query_stats(self.ctx.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in N.QueryStats._fields_}
+
+    def last_xray_stats(self):
+        st = N.XrayStats()
+        N.check(N.lib().pcv_last_xray_stats(self.ctx.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in N.XrayStats._fields_}
+
     def xray_tile(self, tile_min, tile_max, w, h, query_from_global=None, want_bits=False):
         rgba = np.zeros((h, w, 4), np.uint8)
         zb = np.zeros((h, w, 32), np.uint32) if want_bits else None

@@ -96,6 +96,19 @@ class BuildStats(C.Structure):
     ]
 
 
+class QueryStats(C.Structure):
+    """pcv_query_stats (include/pcv.h)."""
+
+    _fields_ = [("ms_device", C.c_float), ("ms_select", C.c_float), ("ms_cull", C.c_float), ("kernel_launches", C.c_uint32), ("algorithmic_bytes", C.c_uint64),
+                ("tested_points", C.c_uint64), ("returned_points", C.c_uint64), ("stored_points", C.c_uint64), ("visited_pairs", C.c_uint64)]
+
+
+class XrayStats(C.Structure):
+    """pcv_xray_stats (include/pcv.h)."""
+
+    _fields_ = [("ms_device", C.c_float), ("kernel_launches", C.c_uint32), ("points", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("ms", C.c_double)]
 
@@ -133,6 +146,8 @@ SYMBOLS = [
     ("pcv_visible_nodes", C.c_int, [C.c_void_p, _dp, C.c_void_p, C.c_uint64, _u64p]),
     ("pcv_query_points", C.c_int, [C.c_void_p, C.POINTER(Location), C.c_void_p, C.c_uint32, C.c_uint64, BATCH_CB, C.c_void_p]),
     ("pcv_query_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    ("pcv_last_query_stats", C.c_int, [C.c_void_p, C.POINTER(QueryStats)]),
+    ("pcv_last_xray_stats", C.c_int, [C.c_void_p, C.POINTER(XrayStats)]),
     ("pcv_xray_tile", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     ("pcv_xray_tile_attr", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     ("pcv_prefix_histogram_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p]),

@@ -786,7 +786,7 @@ class BuildPlan {
         }
         leaf_tile_begin.push_back(nplace_tiles);
         const auto ts3 = tnow();
-        R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
+        R.d_xyz = (uint8_t*)be.dmalloc(boff + 32);  // + slack: the query kernels stage whole 16-byte granules
         R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
         R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);
         R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
@@ -988,7 +988,7 @@ inline BuildResult assemble_top(Backend& be, double resolution, const double bmi
     pl.ntiles = nplace_tiles;
     pl.npoints = npoints;
     pl.xyz_bytes = boff;
-    R.d_xyz = (uint8_t*)be.dmalloc(std::max<uint64_t>(boff, 16));
+    R.d_xyz = (uint8_t*)be.dmalloc(boff + 32);  // + slack: the query kernels stage whole 16-byte granules
     R.d_rgb = (uint8_t*)be.dmalloc(std::max<uint64_t>(npoints * 3, 16));
     R.d_src = (uint32_t*)be.dmalloc(std::max<uint64_t>(npoints * 4, 16));
     R.d_intensity = intensity ? (float*)be.dmalloc(std::max<uint64_t>(npoints * 4, 16)) : nullptr;

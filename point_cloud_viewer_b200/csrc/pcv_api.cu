@@ -221,7 +221,6 @@ static pcv_octree* octree_from_result(pcv_ctx* c, BuildResult& R, double resolut
         m.cube_edge = x.e;
         m.point_offset = x.out_point_off;
         m.xyz_byte_offset = x.out_xyz_off;
-        o->idx[{m.id_high, m.id_low}] = (uint32_t)o->nodes.size();
         o->nodes.push_back(m);
         o->nsub.push_back(x.n_sub);
     }
@@ -315,6 +314,7 @@ void pcv_octree_free(pcv_octree* o) {
     c->be->dfree(o->d_intensity);
     c->be->dfree(o->d_src);
     c->be->dfree(o->d_qnodes);
+    c->be->dfree(o->d_children);
     cudaStreamSynchronize(c->stream);
     delete o;
 }
@@ -550,7 +550,6 @@ int pcv_octree_load_dir(pcv_ctx* c, const char* dir, pcv_octree** out) {
         m.xyz_byte_offset = boff;
         poff += (uint64_t)p.num_points;
         boff += (uint64_t)p.num_points * 3 * (uint64_t)enc_bytes(p.enc);
-        o->idx[{p.hi, p.lo}] = (uint32_t)o->nodes.size();
         o->nodes.push_back(m);
     }
     o->n = poff;
@@ -582,7 +581,7 @@ int pcv_octree_load_dir(pcv_ctx* c, const char* dir, pcv_octree** out) {
     {
         std::lock_guard<std::mutex> g(c->mu);
         CU(cudaSetDevice(c->device));
-        o->d_xyz = (uint8_t*)c->be->dmalloc(std::max<uint64_t>(boff, 16));
+        o->d_xyz = (uint8_t*)c->be->dmalloc(boff + 32);  // + slack: the query kernels stage whole 16-byte granules
         o->d_rgb = (uint8_t*)c->be->dmalloc(std::max<uint64_t>(poff * 3, 16));
         o->d_src = (uint32_t*)c->be->dmalloc(std::max<uint64_t>(poff * 4, 16));
         if (boff) c->be->h2d(o->d_xyz, xyz.data(), boff);

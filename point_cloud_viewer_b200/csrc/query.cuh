@@ -152,8 +152,46 @@ __device__ __forceinline__ bool loc_contains(const QueryGeom& g, double x, doubl
         return g.aabb_min[0] <= x && g.aabb_min[1] <= y && g.aabb_min[2] <= z && x < g.aabb_max[0] && y < g.aabb_max[1] && z < g.aabb_max[2];
     }
     if (g.kind == PCV_LOC_FRUSTUM) {  // frustum.rs:120-125
-        const V3 c = mat4_transform_point(g.clip_from_query, V3{x, y, z});
-        const double mn = fmin(fmin(c.x, c.y), c.z), mx = fmax(fmax(c.x, c.y), c.z);
+        // q = clip_from_query.transform_point(p) divides by the homogeneous w, then every component must lie strictly inside
+        // (-1, 1).  The three IEEE divisions dominate the point test, and they only matter within an ulp of the planes:
+        // |fl(r / w)| < 1  <=>  |r / w| < 1 - 2^-54 (the midpoint below 1 rounds to 1), so with T = fl(|w| (1 - 2^-52)) <
+        // |w| (1 - 2^-54):  |r| <= T is certainly inside,  |r| >= |w| certainly outside;  only the band in between (and
+        // w == 0, tiny, huge or NaN) takes the divisions.  Same result as the reference's arithmetic for every input.
+        const double* m = g.clip_from_query;
+        double n = m[3] * x;
+        n = n + m[7] * y;
+        n = n + m[11] * z;
+        n = n + m[15];
+        double r[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double a = m[i] * x;
+            a = m[4 + i] * y + a;
+            a = m[8 + i] * z + a;
+            r[i] = a + m[12 + i];
+        }
+        const double an = fabs(n);
+        if (an > 1e-290 && an < 1e300) {
+            const double T = an * 0.99999999999999977795539507496869;  // 1 - 2^-52
+            bool sure = true, inside = true;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const double ar = fabs(r[i]);
+                if (ar >= an)
+                    inside = false;
+                else if (!(ar <= T))
+                    sure = false;
+            }
+            if (!inside) return false;
+            if (sure) return true;
+        }
+        double c[3] = {r[0], r[1], r[2]};
+        if (n != 0.0) {
+            c[0] = r[0] / n;
+            c[1] = r[1] / n;
+            c[2] = r[2] / n;
+        }
+        const double mn = fmin(fmin(c[0], c[1]), c[2]), mx = fmax(fmax(c[0], c[1]), c[2]);
         return mn > -1.0 && mx < 1.0;
     }
     if (g.kind == PCV_LOC_OBB) {  // obb.rs:83-90
@@ -322,6 +360,195 @@ __global__ void k_tile_totals(const QTile* tiles, const uint32_t* keep_counts, u
     atomicAdd(&tested[tiles[i].loc], (unsigned long long)tiles[i].count);
 }
 
+// ---- batched query: hierarchical node selection + single-pass culling ---------------------------------------------
+// nodes_in_location for many locations at once, level by level like NodeIdsIterator (octree_iterator.rs:30-43): a frontier of
+// (location, node) pairs; every pair is tested once (sat.rs:174-194), a pair that is not Out joins the work list (if the node
+// holds points) and hands its existing children to the next level's frontier.  Only visited nodes are ever tested - the
+// all-pairs kernel above (k_sat_nodes) stays for the single-location entry points that need the BFS order.
+struct LocProj {
+    double a[26][2];  // projections of the location's 8 corners on each of its cached axes
+};
+__global__ void __launch_bounds__(32) k_loc_proj(const QueryGeom* __restrict__ geoms, LocProj* __restrict__ out) {
+    project_location(geoms[blockIdx.x], out[blockIdx.x].a);
+}
+struct BfsArgs {
+    const QueryGeom* geoms;
+    const LocProj* proj;
+    const QNode* nodes;
+    const int32_t* children;  // [nnodes][8]
+    const uint2* fin;
+    uint2* fout;
+    const uint32_t* nin;   // size of the incoming frontier (device resident)
+    uint32_t* nout;
+    uint32_t cap;          // frontier / pair list capacity
+    uint2* pairs;          // (location, node) pairs to cull
+    uint32_t* npairs;
+    unsigned long long* ntiles;
+    unsigned long long* tested;  // [nloc] points of the nodes the location visits
+    unsigned long long* bytes;   // sum of n * (3 bpc + 3) over the visited pairs
+    int* overflow;
+};
+constexpr uint32_t kQueryTileBfs = 2048;
+__global__ void __launch_bounds__(256) k_bfs_level(const __grid_constant__ BfsArgs a) {
+    const uint32_t n = min(*a.nin, a.cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 pr = a.fin[i];
+        const QueryGeom& g = a.geoms[pr.x];
+        const QNode nd = a.nodes[pr.y];
+        uint8_t rel = REL_IN;
+        if (g.kind != PCV_LOC_ALL) rel = sat_cube(g, a.proj[pr.x].a, nd.m, nd.e);
+        if (rel == REL_OUT) continue;
+        if (nd.n) {
+            const uint32_t k = atomicAdd(a.npairs, 1u);
+            if (k < a.cap)
+                a.pairs[k] = pr;
+            else
+                *a.overflow = 1;
+            atomicAdd(a.ntiles, (unsigned long long)((nd.n + kQueryTileBfs - 1) / kQueryTileBfs));
+            atomicAdd(&a.tested[pr.x], (unsigned long long)nd.n);
+            atomicAdd(a.bytes, (unsigned long long)nd.n * (3ull * (unsigned long long)enc_bytes(nd.enc) + 3ull));
+        }
+        const int32_t* ch = a.children + (size_t)pr.y * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int32_t cn = ch[c];
+            if (cn < 0) continue;
+            const uint32_t k = atomicAdd(a.nout, 1u);
+            if (k < a.cap)
+                a.fout[k] = make_uint2(pr.x, (uint32_t)cn);
+            else
+                *a.overflow = 1;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_bfs_seed(uint2* f, uint32_t nloc, uint32_t root, uint32_t* n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nloc) f[i] = make_uint2(i, root);
+    if (i == 0) *n = nloc;
+}
+__global__ void __launch_bounds__(256) k_pairs_to_tiles(const uint2* __restrict__ pairs, const uint32_t* __restrict__ npairs, uint32_t cap,
+                                                        const QNode* __restrict__ nodes, unsigned long long* __restrict__ cursor, QTile* __restrict__ tiles) {
+    const uint32_t n = min(*npairs, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[i];
+        const uint32_t cnt = nodes[pr.y].n;
+        const uint32_t nt = (cnt + kQueryTile - 1) / kQueryTile;
+        const unsigned long long base = atomicAdd(cursor, (unsigned long long)nt);
+        for (uint32_t k = 0; k < nt; ++k) tiles[base + k] = QTile{pr.x, pr.y, k * kQueryTile, min(kQueryTile, cnt - k * kQueryTile)};
+    }
+}
+
+// FilteredIterator (iterator.rs:96-119) over one tile, in ONE pass: the tile's position bytes are staged in shared memory with
+// 16-byte loads (node blocks and 2048-point tiles are 16-byte aligned), every point is decoded and tested once, the block
+// reserves the output range of its survivors with one atomic and then writes them compacted (the order inside the tile is
+// kept; tiles land in the order they finish - the batched form only promises per-location totals and the compacted set).
+// Survivors beyond `cap` are counted but not stored.
+struct CullFusedArgs {
+    CullArgs c;
+    unsigned long long* cursor;  // output slots handed out so far
+    unsigned long long cap;
+    unsigned long long* kept;    // [nloc]
+};
+constexpr uint32_t kCullStage = kQueryTile * 12 + 32;  // F32 codes: the widest staged encoding
+__device__ __forceinline__ void decode_staged(const uint8_t* s, uint32_t i, const QNode& nd, double p[3]) {
+    if (nd.enc == ENC_U8) {
+        const uint8_t* q = s + 3 * i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = decode_axis<ENC_U8>(q[k], nd.m[k], nd.e);
+    } else if (nd.enc == ENC_U16) {
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(s) + 3 * i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = decode_axis<ENC_U16>(q[k], nd.m[k], nd.e);
+    } else {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(s) + 3 * i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = decode_axis<ENC_F32>(q[k], nd.m[k], nd.e);
+    }
+}
+__global__ void __launch_bounds__(256) k_cull_fused(const __grid_constant__ CullFusedArgs f, uint32_t ntiles) {
+    __shared__ __align__(16) uint8_t sxyz[kCullStage];
+    __shared__ uint32_t wcnt[kQueryTile / 256][8];
+    __shared__ unsigned long long sbase;
+    const CullArgs& a = f.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const QTile t = a.tiles[ti];
+        const QueryGeom& g = a.geoms[t.loc];
+        const QNode nd = a.nodes[t.node];
+        const bool staged = nd.enc != ENC_F64;
+        const int bpc = enc_bytes(nd.enc);
+        const uint8_t* src = a.xyz + nd.xyz_off + (uint64_t)t.first * 3 * bpc;
+        if (staged) {
+            const uint32_t nvec = (t.count * 3u * (uint32_t)bpc + 15u) >> 4;
+            for (uint32_t v = threadIdx.x; v < nvec; v += 256) reinterpret_cast<uint4*>(sxyz)[v] = __ldcg(reinterpret_cast<const uint4*>(src) + v);
+        }
+        __syncthreads();
+        uint32_t keepbits = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < kQueryTile / 256; ++r) {
+            const uint32_t i = r * 256 + threadIdx.x;
+            bool keep = false;
+            if (i < t.count) {
+                double p[3];
+                if (staged) {
+                    decode_staged(sxyz, i, nd, p);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(src + ((size_t)i * 3 + k) * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+                }
+                keep = loc_contains(g, p[0], p[1], p[2]);
+                if (a.nfilt) {
+                    const double v = (double)a.intensity[nd.point_off + t.first + i];  // iterator.rs:82-91
+                    for (uint32_t q = 0; q < a.nfilt; ++q) keep = keep && (a.filters[q].lo <= v && v <= a.filters[q].hi);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) wcnt[r][warp] = __popc(bal);
+            if (keep) keepbits |= 1u << r;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // exclusive prefix over (round, warp); one atomic reserves the tile's output range
+            uint32_t run = 0;
+            for (uint32_t r = 0; r < kQueryTile / 256; ++r)
+                for (int w = 0; w < 8; ++w) {
+                    const uint32_t c = wcnt[r][w];
+                    wcnt[r][w] = run;
+                    run += c;
+                }
+            sbase = run ? atomicAdd(f.cursor, (unsigned long long)run) : 0ull;
+            if (run) atomicAdd(&f.kept[t.loc], (unsigned long long)run);
+        }
+        __syncthreads();
+        const unsigned long long base = sbase;
+#pragma unroll
+        for (uint32_t r = 0; r < kQueryTile / 256; ++r) {
+            const bool keep = (keepbits >> r) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (!keep) continue;
+            const unsigned long long dst = base + wcnt[r][warp] + __popc(bal & ((1u << lane) - 1u));
+            if (dst >= f.cap) continue;
+            const uint32_t i = r * 256 + threadIdx.x;
+            double p[3];
+            if (staged) {
+                decode_staged(sxyz, i, nd, p);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(src + ((size_t)i * 3 + k) * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+            }
+            const uint64_t sp = nd.point_off + t.first + i;
+            a.out_xyz[3 * dst] = p[0];
+            a.out_xyz[3 * dst + 1] = p[1];
+            a.out_xyz[3 * dst + 2] = p[2];
+            a.out_rgb[3 * dst] = a.rgb[3 * sp];
+            a.out_rgb[3 * dst + 1] = a.rgb[3 * sp + 1];
+            a.out_rgb[3 * dst + 2] = a.rgb[3 * sp + 2];
+            if (a.out_intensity) a.out_intensity[dst] = a.intensity[sp];
+            a.out_src[dst] = a.src[sp];
+        }
+        __syncthreads();  // sxyz and wcnt are reused by the next tile
+    }
+}
+
 // ---- X-ray -----------------------------------------------------------------------------------------
 struct XrayArgs {
     QueryGeom geom;
@@ -374,6 +601,114 @@ __global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ Xray
         }
     }
     if (__syncthreads_or(seen) && threadIdx.x == 0) atomicExch(a.any, 1);
+}
+
+// The same accumulation with the z-bucket sets in SHARED memory (the global-memory form above needs 128 B per pixel: 2 GiB for
+// a 4096 x 4096 tile, written and read once more than it is used).  The points are first binned by 32 x 32 pixel sub-tile of
+// the image with a counting sort of 4-byte keys (k_xray_bin<0>: count, k_xray_bin<1>: place; octree nodes are spatially
+// coherent, so the lanes of a warp mostly share their sub-tile and the atomics are issued once per warp and sub-tile), then
+// one block per non-empty sub-tile ORs its keys into 1024 pixels x 1024 bits of shared memory (128 KB) and resolves them to
+// RGBA itself.  Per-point arithmetic and the pixel / bucket indices are exactly those of k_xray_accum.
+constexpr uint32_t kXraySub = 32;  // sub-tile edge in pixels
+struct XrayBinArgs {
+    XrayArgs x;               // geom, nodes, tiles, xyz, tile box, transform, w, h, any
+    uint32_t ntiles;
+    uint32_t sub_w;           // sub-tiles per row
+    uint32_t* sub_count;      // [nsub] points per sub-tile; after the scan: exclusive offsets
+    uint32_t* sub_cursor;     // [nsub] place pass: keys written so far
+    uint32_t* keys;           // ly << 16 | lx << 11 | min(z, 1024)
+};
+template <int PLACE>
+__global__ void __launch_bounds__(256) k_xray_bin(const __grid_constant__ XrayBinArgs b) {
+    const XrayArgs& a = b.x;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t ti = blockIdx.x; ti < b.ntiles; ti += gridDim.x) {
+        const QTile t = a.tiles[ti];
+        const QNode nd = a.nodes[t.node];
+        const int bpc = enc_bytes(nd.enc);
+        for (uint32_t i0 = 0; i0 < t.count; i0 += blockDim.x) {
+            const uint32_t i = i0 + threadIdx.x;
+            uint32_t sub = 0xFFFFFFFFu, key = 0;
+            if (i < t.count) {
+                const uint8_t* s = a.xyz + nd.xyz_off + (uint64_t)(t.first + i) * 3 * bpc;
+                double p[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(s + k * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+                if (loc_contains(a.geom, p[0], p[1], p[2])) {
+                    if (a.has_q) {  // generation.rs:493-497
+                        const V3 q = iso_apply(a.query_from_global, V3{p[0], p[1], p[2]});
+                        p[0] = q.x, p[1] = q.y, p[2] = q.z;
+                    }
+                    // process_point_data, generation.rs:108-127 (`as u32` saturates, NaN -> 0)
+                    const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
+                    const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
+                    const uint32_t z = rust_as_u32_dev(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
+                    if (x < a.w && y < a.h) {
+                        sub = (y / kXraySub) * b.sub_w + (x / kXraySub);
+                        key = ((y % kXraySub) << 16) | ((x % kXraySub) << 11) | min(z, 1024u);
+                    }
+                }
+            }
+            // one atomic per warp and distinct sub-tile
+            const unsigned mask = __match_any_sync(0xffffffffu, sub);
+            if (sub != 0xFFFFFFFFu) {
+                const int leader = __ffs(mask) - 1;
+                const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+                if (PLACE) {
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&b.sub_cursor[sub], (uint32_t)__popc(mask));
+                    base = __shfl_sync(mask, base, leader);
+                    b.keys[b.sub_count[sub] + base + rank] = key;
+                } else if (lane == leader) {
+                    atomicAdd(&b.sub_count[sub], (uint32_t)__popc(mask));
+                }
+            }
+        }
+    }
+}
+struct XraySubArgs {
+    const uint32_t* sub_id;     // [nsub_nonempty] sub-tile index
+    const uint32_t* sub_off;    // [nsub + 1] exclusive offsets into keys
+    const uint32_t* keys;
+    const uint8_t* grey;        // [1026]
+    uint8_t* rgba;              // w * h * 4, zero-initialised
+    uint32_t* zbits_out;        // optional: w * h * 32, zero-initialised
+    uint32_t sub_w, w, h;
+};
+__global__ void __launch_bounds__(512, 1) k_xray_subtile(const __grid_constant__ XraySubArgs b) {
+    extern __shared__ __align__(16) uint32_t sbits[];  // [1024 pixels][32 words]
+    __shared__ uint8_t sover[kXraySub * kXraySub];
+    const uint32_t sid = b.sub_id[blockIdx.x];
+    const uint32_t px0 = (sid % b.sub_w) * kXraySub, py0 = (sid / b.sub_w) * kXraySub;
+    for (uint32_t i = threadIdx.x; i < kXraySub * kXraySub * 32; i += blockDim.x) sbits[i] = 0;
+    for (uint32_t i = threadIdx.x; i < kXraySub * kXraySub; i += blockDim.x) sover[i] = 0;
+    __syncthreads();
+    const uint32_t k0 = b.sub_off[sid], k1 = b.sub_off[sid + 1];
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        const uint32_t key = __ldcs(b.keys + k);
+        const uint32_t lp = (key >> 16) * kXraySub + ((key >> 11) & 31u), z = key & 2047u;
+        if (z < 1024)
+            atomicOr(&sbits[lp * 32 + (z >> 5)], 1u << (z & 31));
+        else
+            sover[lp] = 1;
+    }
+    __syncthreads();
+    // resolve: popcount of the pixel's bucket set -> grey (generation.rs:186-197)
+    for (uint32_t lp = threadIdx.x; lp < kXraySub * kXraySub; lp += blockDim.x) {
+        const uint32_t x = px0 + (lp % kXraySub), y = py0 + (lp / kXraySub);
+        if (x >= b.w || y >= b.h) continue;
+        uint32_t cnt = sover[lp];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) cnt += __popc(sbits[lp * 32 + ((k + lp) & 31)]);  // rotated start: no 32-way bank conflict
+        if (cnt) {
+            const uint8_t gv = b.grey[cnt];
+            reinterpret_cast<uchar4*>(b.rgba)[(size_t)y * b.w + x] = make_uchar4(gv, gv, gv, 255);
+        }
+        if (b.zbits_out) {
+            uint32_t* o = b.zbits_out + ((size_t)y * b.w + x) * 32;
+            for (int k = 0; k < 32; ++k) o[k] = sbits[lp * 32 + k];
+        }
+    }
 }
 
 // grey[count] LUT is computed on the host with libm log (generation.rs:186-197) so the cast boundary matches.

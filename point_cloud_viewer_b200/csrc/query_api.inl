@@ -62,6 +62,8 @@ void ensure_tables(pcv_octree* o) {
     if (n) {
         o->d_qnodes = c->be->dmalloc(n * sizeof(QNode));
         c->be->h2d(o->d_qnodes, qn.data(), n * sizeof(QNode));
+        o->d_children = (int32_t*)c->be->dmalloc(n * 8 * sizeof(int32_t));
+        c->be->h2d(o->d_children, o->children_of.data(), n * 8 * sizeof(int32_t));
     }
     o->tables_ready = true;
 }
@@ -410,54 +412,155 @@ int pcv_query_batch_device(const pcv_octree* oc, const pcv_location* locs, uint3
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     ensure_tables(o);
+    c->qstats = pcv_query_stats{};
     if (nloc == 0) return PCV_OK;
     std::vector<QueryGeom> geoms(nloc);
     for (uint32_t i = 0; i < nloc; ++i) {
         if (locs[i].kind < 0 || locs[i].kind > 3) return fail(PCV_ERR_INVALID, "unknown location kind %d", locs[i].kind);
-        geoms[i] = make_query_geom(locs[i]);
+        geoms[i] = make_query_geom(locs[i]);  // per-location axis caching (sat.rs:111-143), host side: O(1) per location
     }
-    Scratch s(c);
-    const QueryGeom* dg = nullptr;
-    const uint8_t* dpass = run_sat_device(o, geoms, s, &dg);
     const uint32_t nn = (uint32_t)o->nodes.size();
-    std::vector<unsigned long long> zeros(nloc, 0);
-    unsigned long long* dk = s.upload(zeros.data(), nloc);
-    unsigned long long* dt = s.upload(zeros.data(), nloc);
-    if (dpass) {
-        // work list built on the device: count tiles, allocate, fill (one atomic per (location, node) pair)
-        const uint64_t npairs = (uint64_t)nn * nloc;
-        unsigned long long two[2] = {0, 0};
-        unsigned long long* dcnt = s.upload(two, 2);
-        const uint32_t gb = (uint32_t)((npairs + 255) / 256);
-        k_count_tiles<<<gb, 256, 0, c->stream>>>(dpass, (const QNode*)o->d_qnodes, nn, npairs, dcnt);
-        c->be->launches++;
-        unsigned long long ntl = 0;
-        c->be->d2h(&ntl, dcnt, 8);
-        if (ntl >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "work list too large (%llu tiles); split the batch", ntl);
-        if (ntl) {
-            QTile* dtiles = s.alloc<QTile>(ntl);
-            k_fill_tiles<<<gb, 256, 0, c->stream>>>(dpass, (const QNode*)o->d_qnodes, nn, npairs, dcnt + 1, dtiles);
-            c->be->launches++;
-            CU(cudaGetLastError());
-            std::vector<QTile> none;
-            run_cull(o, dg, none, filters, nfilt, s, dk, dt, dtiles, ntl);
-        }
-    }
-    std::vector<unsigned long long> hk(nloc), ht(nloc);
-    c->be->d2h(hk.data(), dk, (size_t)nloc * 8);
-    c->be->d2h(ht.data(), dt, (size_t)nloc * 8);
     for (uint32_t i = 0; i < nloc; ++i) {
+        if (counts_out) counts_out[i] = 0;
+        if (tested_out) tested_out[i] = 0;
+    }
+    if (nn == 0) return PCV_OK;
+    const uint64_t l0 = c->be->launches;
+    Scratch s(c);
+    const QueryGeom* dg = s.upload(geoms.data(), geoms.size());
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(ev[0], c->stream));
+    // ---- node selection: level-synchronous frontier over all locations ----
+    LocProj* dproj = s.alloc<LocProj>(nloc);
+    k_loc_proj<<<nloc, 32, 0, c->stream>>>(dg, dproj);
+    int maxl = 0;
+    for (const auto& m : o->nodes) maxl = std::max(maxl, m.level);
+    const uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)nloc * nn, 48ull << 20);
+    uint2* fr[2] = {s.alloc<uint2>(cap), s.alloc<uint2>(cap)};
+    uint2* dpairs = s.alloc<uint2>(cap);
+    // counters: [0 .. maxl + 1] frontier sizes, then npairs (u32); ntiles, bytes, cursor, out cursor (u64); overflow
+    uint32_t* dcnt32 = s.alloc<uint32_t>((size_t)maxl + 4);
+    unsigned long long* dcnt64 = s.alloc<unsigned long long>(4);
+    int* dover = s.alloc<int>(1);
+    unsigned long long* dk = s.alloc<unsigned long long>(nloc);
+    unsigned long long* dt = s.alloc<unsigned long long>(nloc);
+    c->be->zero(dcnt32, ((size_t)maxl + 4) * 4);
+    c->be->zero(dcnt64, 4 * 8);
+    c->be->zero(dover, 4);
+    c->be->zero(dk, (size_t)nloc * 8);
+    c->be->zero(dt, (size_t)nloc * 8);
+    const int root = o->find(0, 0);
+    if (root < 0) return fail(PCV_ERR_INVALID, "octree without a root node");
+    k_bfs_seed<<<(nloc + 255) / 256, 256, 0, c->stream>>>(fr[0], nloc, (uint32_t)root, dcnt32);
+    uint32_t* dnpairs = dcnt32 + maxl + 2;
+    for (int L = 0; L <= maxl; ++L) {
+        BfsArgs b{};
+        b.geoms = dg;
+        b.proj = dproj;
+        b.nodes = (const QNode*)o->d_qnodes;
+        b.children = o->d_children;
+        b.fin = fr[L & 1];
+        b.fout = fr[(L + 1) & 1];
+        b.nin = dcnt32 + L;
+        b.nout = dcnt32 + L + 1;
+        b.cap = cap;
+        b.pairs = dpairs;
+        b.npairs = dnpairs;
+        b.ntiles = dcnt64;
+        b.tested = dt;
+        b.bytes = dcnt64 + 1;
+        b.overflow = dover;
+        k_bfs_level<<<c->sm_count * 4, 256, 0, c->stream>>>(b);
+    }
+    c->be->launches += 3 + (uint64_t)maxl;
+    CU(cudaGetLastError());
+    unsigned long long h64[4];
+    uint32_t npairs = 0;
+    int over = 0;
+    c->be->d2h(h64, dcnt64, sizeof h64);
+    c->be->d2h(&npairs, dnpairs, 4);
+    c->be->d2h(&over, dover, 4);
+    if (over) return fail(PCV_ERR_UNSUPPORTED, "batched query visits more than %u (location, node) pairs per level; split the batch", cap);
+    const unsigned long long ntl = h64[0];
+    if (ntl >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "work list too large (%llu tiles); split the batch", ntl);
+    std::vector<unsigned long long> hk(nloc, 0), ht(nloc, 0);
+    unsigned long long stored = 0;
+    if (ntl) {
+        QTile* dtiles = s.alloc<QTile>(ntl);
+        k_pairs_to_tiles<<<c->sm_count * 4, 256, 0, c->stream>>>(dpairs, dnpairs, cap, (const QNode*)o->d_qnodes, dcnt64 + 2, dtiles);
+        CU(cudaEventRecord(ev[1], c->stream));
+        // ---- single-pass cull: survivors compacted into one output set (capacity bounded; the rest is counted only) ----
+        unsigned long long tested_total = 0;
+        c->be->d2h(ht.data(), dt, (size_t)nloc * 8);
+        for (auto v : ht) tested_total += v;
+        const unsigned long long outcap = std::min<unsigned long long>(tested_total, 192ull << 20);
+        CullFusedArgs f{};
+        f.c.geoms = dg;
+        f.c.nodes = (const QNode*)o->d_qnodes;
+        f.c.tiles = dtiles;
+        f.c.xyz = o->d_xyz;
+        f.c.rgb = o->d_rgb;
+        f.c.intensity = o->d_intensity;
+        f.c.src = o->d_src;
+        f.c.filters = nfilt ? s.upload(filters, nfilt) : nullptr;
+        f.c.nfilt = nfilt;
+        f.c.out_xyz = s.alloc<double>(3 * outcap + 1);
+        f.c.out_rgb = s.alloc<uint8_t>(3 * outcap + 1);
+        f.c.out_intensity = o->d_intensity ? s.alloc<float>(outcap + 1) : nullptr;
+        f.c.out_src = s.alloc<uint32_t>(outcap + 1);
+        f.cursor = dcnt64 + 3;
+        f.cap = outcap;
+        f.kept = dk;
+        CU(cudaEventRecord(ev[2], c->stream));
+        k_cull_fused<<<(uint32_t)std::min<unsigned long long>(ntl, (unsigned long long)c->sm_count * 16), 256, 0, c->stream>>>(f, (uint32_t)ntl);
+        CU(cudaEventRecord(ev[3], c->stream));
+        c->be->launches += 2;
+        CU(cudaGetLastError());
+        c->be->d2h(hk.data(), dk, (size_t)nloc * 8);
+        unsigned long long cur = 0;
+        c->be->d2h(&cur, dcnt64 + 3, 8);
+        stored = std::min(cur, outcap);
+    } else {
+        CU(cudaEventRecord(ev[1], c->stream));
+        CU(cudaEventRecord(ev[2], c->stream));
+        CU(cudaEventRecord(ev[3], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    pcv_query_stats& q = c->qstats;
+    cudaEventElapsedTime(&q.ms_device, ev[0], ev[3]);
+    cudaEventElapsedTime(&q.ms_select, ev[0], ev[1]);
+    cudaEventElapsedTime(&q.ms_cull, ev[2], ev[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    q.kernel_launches = (uint32_t)(c->be->launches - l0);
+    q.visited_pairs = npairs;
+    for (uint32_t i = 0; i < nloc; ++i) {
+        q.tested_points += ht[i];
+        q.returned_points += hk[i];
         if (counts_out) counts_out[i] = hk[i];
         if (tested_out) tested_out[i] = ht[i];
     }
+    q.stored_points = stored;
+    q.algorithmic_bytes = h64[1] + 27ull * q.returned_points;
     return PCV_OK;
     API_CATCH
+}
+
+int pcv_last_query_stats(pcv_ctx* c, pcv_query_stats* out) {
+    if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
+    *out = c->qstats;
+    return PCV_OK;
+}
+int pcv_last_xray_stats(pcv_ctx* c, pcv_xray_stats* out) {
+    if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
+    *out = c->xstats;
+    return PCV_OK;
 }
 
 // Shared by the X-ray entry points: the tile's location (Aabb, or Obb when a query_from_global transform is given), the nodes
 // it intersects, their point tiles, and the kernel arguments that do not depend on the colouring strategy.
 static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, Scratch& s,
-                         XrayArgs& a, size_t& ntiles) {
+                         XrayArgs& a, std::vector<uint32_t>* hit_nodes, size_t* ntiles_out = nullptr) {
     // location: Aabb(bbox), or Obb::from(bbox).transformed(query_from_global.inverse())  (xray generation.rs:471-477)
     pcv_location loc{};
     double bmin[3], bmax[3];
@@ -508,7 +611,10 @@ static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const 
     std::vector<uint8_t> pass = run_sat(o, geoms, s, nullptr);
     std::vector<QTile> tiles;
     for (size_t i = 0; i < pass.size(); ++i)
-        if (pass[i] && o->nodes[i].num_points > 0) make_tiles(o, 0, (uint32_t)i, tiles);
+        if (pass[i] && o->nodes[i].num_points > 0) {
+            if (hit_nodes) hit_nodes->push_back((uint32_t)i);
+            make_tiles(o, 0, (uint32_t)i, tiles);
+        }
     a = XrayArgs{};
     a.geom = geoms[0];
     a.nodes = (const QNode*)o->d_qnodes;
@@ -522,7 +628,7 @@ static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const 
     if (qfg) memcpy(a.query_from_global, qfg, sizeof(double) * 7);
     a.w = w;
     a.h = h;
-    ntiles = tiles.size();
+    if (ntiles_out) *ntiles_out = tiles.size();
     (void)c;
 }
 
@@ -535,17 +641,23 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
     ensure_tables(o);
+    c->xstats = pcv_xray_stats{};
+    const uint64_t l0 = c->be->launches;
     Scratch s(c);
-    XrayArgs a{};
+    XrayBinArgs bin{};
+    XrayArgs& a = bin.x;
+    std::vector<uint32_t> hit;  // nodes of the tile's location that hold points
     size_t ntiles = 0;
-    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, a, ntiles);
+    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, a, &hit, &ntiles);
     const size_t npix = (size_t)w * h;
-    a.zbits = s.alloc<uint32_t>(npix * 32);
-    a.zover = s.alloc<uint8_t>(npix);
-    a.any = s.alloc<int>(1);
-    CU(cudaMemsetAsync(a.zbits, 0, npix * 128, c->stream));
-    CU(cudaMemsetAsync(a.zover, 0, npix, c->stream));
-    CU(cudaMemsetAsync(a.any, 0, 4, c->stream));
+    uint64_t pts = 0, bytes = 0;
+    for (uint32_t k : hit) {
+        const pcv_node_meta& m = o->nodes[k];
+        pts += (uint64_t)m.num_points;
+        bytes += (uint64_t)m.num_points * (3ull * (uint64_t)enc_bytes(m.position_encoding) + 3ull);
+    }
+    if (pts >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-1 points in one X-ray tile");
+    const uint32_t sw = (w + kXraySub - 1) / kXraySub, sh = (h + kXraySub - 1) / kXraySub, nsub = sw * sh;
     uint8_t grey[1026];
     grey[0] = 0;
     const double max_sat = std::log(1024.0);  // generation.rs:165-171
@@ -553,20 +665,63 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
         const double v = (1. - std::log((double)n) / max_sat) * 255.;
         grey[n] = v != v || v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)v);  // `as u8`
     }
-    const uint8_t* dgrey = s.upload(grey, 1026);
-    uint8_t* drgba = s.alloc<uint8_t>(npix * 4);
-    if (ntiles) {
-        k_xray_accum<<<(uint32_t)ntiles, 256, 0, c->stream>>>(a);
-        c->be->launches++;
-    }
-    k_xray_resolve<<<(uint32_t)((npix + 255) / 256), 256, 0, c->stream>>>(a.zbits, a.zover, dgrey, (uint32_t)npix, drgba);
-    c->be->launches++;
-    CU(cudaGetLastError());
+    a.any = s.alloc<int>(1);
+    bin.ntiles = (uint32_t)ntiles;
+    bin.sub_w = sw;
+    bin.sub_count = s.alloc<uint32_t>((size_t)nsub + 1);
+    bin.sub_cursor = s.alloc<uint32_t>((size_t)nsub + 1);
+    bin.keys = s.alloc<uint32_t>(std::max<uint64_t>(pts, 1));
+    XraySubArgs sb{};
+    sb.grey = s.upload(grey, 1026);
+    sb.rgba = s.alloc<uint8_t>(npix * 4);
+    sb.zbits_out = zbits_out ? s.alloc<uint32_t>(npix * 32) : nullptr;
+    sb.sub_w = sw;
+    sb.w = w;
+    sb.h = h;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->stream));
+    CU(cudaMemsetAsync(sb.rgba, 0, npix * 4, c->stream));
+    CU(cudaMemsetAsync(bin.sub_count, 0, ((size_t)nsub + 1) * 4, c->stream));
+    CU(cudaMemsetAsync(bin.sub_cursor, 0, ((size_t)nsub + 1) * 4, c->stream));
+    if (sb.zbits_out) CU(cudaMemsetAsync(sb.zbits_out, 0, npix * 128, c->stream));
     int any = 0;
-    c->be->d2h(&any, a.any, 4);
-    c->be->d2h(rgba_out, drgba, npix * 4);
-    if (zbits_out) c->be->d2h(zbits_out, a.zbits, npix * 128);
+    if (ntiles) {
+        const uint32_t grid = (uint32_t)std::min<size_t>(ntiles, (size_t)c->sm_count * 16);
+        k_xray_bin<0><<<grid, 256, 0, c->stream>>>(bin);
+        unsigned long long* dtot = s.alloc<unsigned long long>(1);
+        k_scan_u32<<<1, 1024, 0, c->stream>>>(bin.sub_count, nsub + 1, dtot);  // exclusive offsets; entry nsub = total
+        k_xray_bin<1><<<grid, 256, 0, c->stream>>>(bin);
+        c->be->launches += 3;
+        CU(cudaGetLastError());
+        // the non-empty sub-tiles (host: 4 bytes per sub-tile)
+        std::vector<uint32_t> off((size_t)nsub + 1), ids;
+        c->be->d2h(off.data(), bin.sub_count, ((size_t)nsub + 1) * 4);
+        for (uint32_t i = 0; i < nsub; ++i)
+            if (off[i + 1] > off[i]) ids.push_back(i);
+        any = !ids.empty();
+        if (!ids.empty()) {
+            sb.sub_id = s.upload(ids.data(), ids.size());
+            sb.sub_off = bin.sub_count;
+            sb.keys = bin.keys;
+            const size_t sm = (size_t)kXraySub * kXraySub * 128;
+            CU(cudaFuncSetAttribute(k_xray_subtile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_xray_subtile<<<(uint32_t)ids.size(), 512, sm, c->stream>>>(sb);
+            c->be->launches++;
+        }
+    }
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaGetLastError());
+    c->be->d2h(rgba_out, sb.rgba, npix * 4);
+    if (zbits_out) c->be->d2h(zbits_out, sb.zbits_out, npix * 128);
     if (any_out) *any_out = any;
+    cudaEventElapsedTime(&c->xstats.ms_device, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->xstats.kernel_launches = (uint32_t)(c->be->launches - l0);
+    c->xstats.points = pts;
+    c->xstats.algorithmic_bytes = bytes + 4ull * npix;
     return PCV_OK;
     API_CATCH
 }
@@ -589,7 +744,7 @@ int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double 
     Scratch s(c);
     XrayAttrArgs b{};
     size_t ntiles = 0;
-    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, b.x, ntiles);
+    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, b.x, nullptr, &ntiles);
     const size_t npix = (size_t)w * h;
     b.x.any = s.alloc<int>(1);
     b.rgb = o->d_rgb;
