@@ -271,6 +271,92 @@ def bench_config1(ctx, pcv, torch, O, cores):
     return out
 
 
+def multi_gpu_parity_check(ctx, pcv, D, torch, dist, world, rank, dev, n_global, res, bmin, bmax, k):
+    """Inside the measured multi-GPU run: the sharded build of this run's N ranks == the single-GPU build == the oracle, bit for bit
+    (node set, counts, encodings, cubes, per-slot global source index, colours, position codes), on n_global points of the
+    benchmark generator (they include the identical-point blocks that reach level 20)."""
+    import numpy as np
+
+    kind = pcv.SYNTH_GAUSS_CLUSTERS
+    n = n_global // world
+    xs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+    c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+    ctx.synth_points_device(kind, SEED, rank * n, n, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
+    comm = D.TorchComm(dev)
+    tree = D.build_octree_sharded(ctx, xs[0], xs[1], xs[2], c, None, rank * n, res, bmin, bmax, prefix_levels=k)
+    merged = tree.gather_all(comm)  # collective; rank 0 receives every final node
+    kk = tree.k
+    tree.free()
+    verdict = {}
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+
+        N = n * world
+        X, Y, Z, RGB = O.synth_points(O.SYNTH_GAUSS_CLUSTERS, SEED, 0, N)
+        single = ctx.build_octree(X, Y, Z, RGB, res, bmin, bmax)
+        ref = O.build(X, Y, Z, RGB.reshape(-1, 3), res, bmin, bmax)
+        try:
+            from parity import compare_trees
+
+            compare_trees(ref, single)  # single GPU == oracle
+            assert set(single.nodes) == set(merged), "node sets differ: %s" % sorted(set(single.nodes) ^ set(merged))[:6]
+            for name, m in single.nodes.items():  # sharded == single GPU
+                g = merged[name]
+                assert (g["num_points"], g["enc"], tuple(g["cube"])) == (m["num_points"], m["enc"], tuple(m["cube"])), name
+                if m["num_points"]:
+                    sx, sc, si, ss = single.node_data(name)
+                    assert np.array_equal(ss, g["src"]), (name, "src index order")
+                    assert np.array_equal(sx, g["xyz"]) and np.array_equal(sc, g["rgb"]), (name, "codes / colours")
+            verdict = {"n": N, "ranks": world, "prefix_levels": kk, "equal": True, "nodes": len(merged), "deepest_level": max(len(nm) - 1 for nm in merged),
+                       "what": "sharded build over this run's ranks == single-GPU build == oracle: node set, counts, encodings, cubes, per-slot global source index, colours, position codes"}
+        except AssertionError as e:
+            verdict = {"n": N, "ranks": world, "equal": False, "error": str(e)[:300]}
+        single.free()
+    dist.barrier()
+    return verdict
+
+
+def full_size_check(tree, D, torch, dist, world, n, dev):
+    """Size-independent invariants of the full-size sharded result, all-reduced over the ranks: every input point appears
+    exactly once in the final nodes (count, sum and sum of squares of the global source indices, mod 2^64)."""
+    import ctypes as C
+    import numpy as np
+
+    import point_cloud_viewer_b200 as pcv
+    from point_cloud_viewer_b200 import _native as N
+
+    comm = D.TorchComm(dev)
+    r_idx = tree.resolve_provenance(comm).to(torch.int64)  # collective
+
+    def sums(octree, index, min_level):
+        meta = octree.meta
+        if octree.num_points == 0 or len(meta) == 0:
+            return 0, 0, 0
+        p = [C.c_void_p() for _ in range(4)]
+        N.check(N.lib().pcv_octree_device_arrays(octree.h, *[C.byref(v) for v in p]))
+        src = torch.as_tensor(D._RawCuda(p[3].value, (octree.num_points,), "<i4"), device=dev).to(torch.int64)
+        order = np.argsort(meta["point_offset"], kind="stable")
+        lev = torch.from_numpy(meta["level"][order].astype(np.int64)).to(dev)
+        cnt = torch.from_numpy(meta["num_points"][order].astype(np.int64)).to(dev)
+        keep = torch.repeat_interleave(lev >= min_level, cnt)
+        g = index[src[keep]]
+        return int(keep.sum()), int(g.sum()), int((g * g).sum())  # int64 wrap-around arithmetic
+
+    c0, s0, q0 = sums(tree.local, r_idx, tree.k)
+    if tree.top is not None:
+        ti = torch.from_numpy(np.asarray(tree.top_index, np.uint64).astype(np.int64)).to(dev)
+        c1, s1, q1 = sums(tree.top, ti, 0)
+        c0, s0, q0 = c0 + c1, s0 + s1, q0 + q1
+    wrap = lambda v: ((v + 2 ** 63) % 2 ** 64) - 2 ** 63
+    t = torch.tensor([c0, wrap(s0), wrap(q0)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    NT = world * n
+    want = [NT, wrap(NT * (NT - 1) // 2), wrap((NT - 1) * NT * (2 * NT - 1) // 6)]
+    got = [int(v) for v in t]
+    return {"ok": got == want, "points": got[0], "expected_points": NT, "sum_idx_ok": got[1] == want[1], "sum_idx_sq_ok": got[2] == want[2]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -308,7 +394,7 @@ def run_ours(args):
 
         # ---- multi-GPU parity, inside the measured run: sharded vs single-GPU vs oracle on a small global sample ----
         try:
-            out_extra["parity_check"] = D.parity_check(ctx, world, rank, dev, kind, SEED, int(args.parity_points), res, bmin, bmax, args.prefix_levels, ROOT)
+            out_extra["parity_check"] = multi_gpu_parity_check(ctx, pcv, D, torch, dist, world, rank, dev, int(args.parity_points), res, bmin, bmax, args.prefix_levels)
         except Exception as e:
             out_extra["parity_check"] = {"equal": False, "error": str(e)[:300]}
 
@@ -378,7 +464,7 @@ def run_ours(args):
         # full-size invariants of the sharded result, all-reduced: every point exactly once (count, sum and sum of squares of the
         # global source indices), and the per-phase breakdown of the last step
         try:
-            out["full_size_check"] = D.full_size_check(last, world, n, dev)
+            out["full_size_check"] = full_size_check(last, D, torch, dist, world, n, dev)
         except Exception as e:
             out["full_size_check"] = {"ok": False, "error": str(e)[:300]}
         out["phases_ms"] = getattr(last, "phases_ms", None)

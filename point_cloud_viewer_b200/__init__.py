@@ -198,6 +198,45 @@ class Context:
     def ipc_close(self, ptr):
         N.check(N.lib().pcv_ipc_close(self.h, ptr))
 
+    # ---- exchange of ingested records (pcv.h: pcv_shard_*) ----
+    def shard_ingest(self, x, y, z, rgb, intensity, n, resolution, bbox_min, bbox_max, k):
+        """Ingest step + digit histogram of the local points: (level-k cell counts, send handle)."""
+        pts = N.Points(_p(x), _p(y), _p(z), 1, _p(rgb), _p(intensity), int(n))
+        counts = np.zeros(8 ** k, np.uint64)
+        h = C.c_void_p()
+        N.check(N.lib().pcv_shard_ingest_device(self.h, C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), k, _p(counts), C.byref(h)))
+        return counts, h
+
+    def shard_exchange(self, send, k, cell_to_rank, nranks, dst_first, dst_rec, dst_col, dst_dig, dst_intensity=None):
+        c2r = np.ascontiguousarray(cell_to_rank, np.int32)
+        first = np.ascontiguousarray(dst_first, np.uint64)
+        arr = lambda lst: (C.c_void_p * nranks)(*[int(v) if v else None for v in lst])
+        counts = np.zeros(nranks, np.uint64)
+        N.check(N.lib().pcv_shard_exchange_device(send, k, _p(c2r), nranks, _p(first), arr(dst_rec), arr(dst_col), arr(dst_dig),
+                                                  arr(dst_intensity) if dst_intensity is not None else None, _p(counts)))
+        return counts
+
+    def shard_send_info(self, send):
+        w, g = C.c_int(), C.c_int()
+        N.check(N.lib().pcv_shard_send_info(send, C.byref(w), C.byref(g)))
+        return bool(w.value), g.value
+
+    def shard_send_dest(self, send):
+        p, n = C.c_void_p(), C.c_uint64()
+        N.check(N.lib().pcv_shard_send_dest(send, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def shard_send_free(self, send):
+        N.lib().pcv_shard_send_free(send)
+
+    def build_octree_from_records(self, rec_ptr, col_ptr, dig_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
+        """The owner's part of a sharded build over the records its peers stored into its slab."""
+        pc = np.ascontiguousarray(prefix_counts, np.uint64)
+        out = C.c_void_p()
+        N.check(N.lib().pcv_build_octree_from_records_device(self.h, rec_ptr, col_ptr, dig_ptr, intensity_ptr, int(n), float(resolution), _d3(bbox_min), _d3(bbox_max),
+                                                             k, _p(pc), C.byref(out)))
+        return Octree(self, out)
+
     def build_octree_sharded_device_soa(self, x_ptr, y_ptr, z_ptr, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
         """Local part of a sharded build from SoA device arrays (the layout the fused exchange delivers)."""
         pts = N.Points(x_ptr, y_ptr, z_ptr, 1, rgb_ptr, intensity_ptr, int(n))

@@ -160,6 +160,13 @@ SYMBOLS = [
     ("pcv_ipc_free", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcv_ipc_open", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_ipc_close", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("pcv_shard_ingest_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("pcv_shard_exchange_device", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_shard_send_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("pcv_shard_send_dest", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p]),
+    ("pcv_shard_send_free", None, [C.c_void_p]),
+    ("pcv_build_octree_from_records_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p,
+                                                       C.POINTER(C.c_void_p)]),
     ("pcv_build_octree_sharded_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_octree_node_nsub", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
     ("pcv_octree_nsub_all", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

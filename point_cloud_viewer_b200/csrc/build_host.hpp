@@ -139,7 +139,7 @@ enum : int32_t { kErrHistMismatch = 1, kErrTooDeep = 2, kErrCapacity = 3 };
 struct ShardSpec {
     int k = 0;
     const uint64_t* counts = nullptr;
-    static size_t level_offset(int level) { return (((size_t)1 << (3 * level)) - 8) / 7; }
+    PCV_HD static size_t level_offset(int level) { return (((size_t)1 << (3 * level)) - 8) / 7; }
     uint64_t count_at(int level, uint64_t index) const { return counts[level_offset(level) + index]; }
 };
 
@@ -373,6 +373,7 @@ struct Backend {
     virtual void zero(void* d, size_t bytes) = 0;
     virtual void ingest(const IngestArgs& a) = 0;   // raw points -> level-1 records + first digits
     virtual void pass(const PassArgs& a) = 0;       // digit histogram + scan + plan + partition of one pass (asynchronous)
+    virtual void hist_scan(const PassArgs& a) {}    // only the digit histogram + scan of a pass (sharded build: the sender's side)
     virtual void place(const PlaceArgs& a) = 0;
     virtual void mark(int what) {}  // timing hooks: 0 partition start, 1 partition end / place start, 2 place end
     virtual void pass_points(int pass, uint64_t npoints, uint64_t leaf_points) {}  // profiling: live point counts, known after the read-back
@@ -467,11 +468,22 @@ struct BuildError : std::runtime_error {
     BuildError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
 };
 
+// Records that already went through the ingest step on another GPU (sharded build): level-1 codes + the first pass's digits
+// of `n` points, in this context's memory; idx of record i must be i.  The build then starts at its first partition pass.
+struct ExternalRecords {
+    const void* rec = nullptr;
+    const uint32_t* col = nullptr;
+    const uint8_t* dig = nullptr;
+    uint64_t n = 0;
+    bool present = false;
+};
+
 class BuildPlan {
    public:
     Backend& be;
     uint64_t max_points;
     ShardSpec shard;
+    ExternalRecords ext;
     BuildPlan(Backend& b, uint64_t max_points_per_node, int /*levels_per_pass: the split phase resolves two levels per pass*/)
         : be(b), max_points(max_points_per_node ? max_points_per_node : 100000) {}
 
@@ -538,9 +550,11 @@ class BuildPlan {
         std::vector<HNode>& nodes = R.nodes;
         BuildState hs{};
         try {
-            void* bufs[2] = {dalloc((size_t)N * rec_bytes + 64), dalloc((size_t)N * rec_bytes + 64)};
-            uint32_t* cols[2] = {(uint32_t*)dalloc((size_t)N * 4 + 64), (uint32_t*)dalloc((size_t)N * 4 + 64)};  // + slack: bulk copies read whole 16-byte granules
-            uint8_t* digs[2] = {(uint8_t*)dalloc((size_t)N + 64), (uint8_t*)dalloc((size_t)N + 64)};
+            // ping-pong buffers; with external records the first of each pair is the caller's (read only, never freed here)
+            void* bufs[2] = {ext.present ? const_cast<void*>(ext.rec) : dalloc((size_t)N * rec_bytes + 64), dalloc((size_t)N * rec_bytes + 64)};
+            uint32_t* cols[2] = {ext.present ? const_cast<uint32_t*>(ext.col) : (uint32_t*)dalloc((size_t)N * 4 + 64),
+                                 (uint32_t*)dalloc((size_t)N * 4 + 64)};  // + slack: bulk copies read whole 16-byte granules
+            uint8_t* digs[2] = {ext.present ? const_cast<uint8_t*>(ext.dig) : (uint8_t*)dalloc((size_t)N + 64), (uint8_t*)dalloc((size_t)N + 64)};
             arena = dalloc((size_t)N * rec_bytes);
             col_arena = (uint32_t*)dalloc((size_t)N * 4 + 64);
             BuildState* d_st = (BuildState*)dalloc(sizeof(BuildState));
@@ -599,7 +613,7 @@ class BuildPlan {
             ia.ntiles = nt0;
             ia.lv = lv;
             for (int a = 0; a < 3; ++a) ia.root_min[a] = bmin[a];
-            be.ingest(ia);
+            if (!ext.present) be.ingest(ia);
 
             // Small inputs: read the state back after every pass and stop at the first pass without active nodes (a few empty
             // launches cost more than the build of a 1e5-point cloud).  Large inputs: enqueue everything, one read-back at the end.
@@ -665,7 +679,16 @@ class BuildPlan {
             if (hs.error == kErrTooDeep) throw BuildError(-6, "octree deeper than 40 levels is not representable in NodeId");
             if (hs.error == kErrHistMismatch) throw BuildError(-2, "internal: histogram total mismatch");
             if (hs.error) throw BuildError(-2, "internal: planner capacity exceeded");
-            if (hs.arena_used != N) throw BuildError(-2, "internal: the split phase lost points");
+            if (hs.arena_used != N) {
+                if (std::getenv("PCV_TIMING")) {
+                    fprintf(stderr, "[pcv] lost points: arena %llu of %llu, nodes %u, launched %zu of %zu passes\n", (unsigned long long)hs.arena_used, (unsigned long long)N,
+                            hs.nnodes, launched, sched.size());
+                    for (size_t p = 0; p <= launched; ++p)
+                        fprintf(stderr, "[pcv]   pass %zu: nactive %u ntiles %u nchunks %u npoints %llu\n", p, hs.pass[p].nactive, hs.pass[p].ntiles, hs.pass[p].nchunks,
+                                (unsigned long long)hs.pass[p].npoints);
+                }
+                throw BuildError(-2, "internal: the split phase lost points");
+            }
             for (size_t p = 0; p < launched; ++p) {
                 if (hs.pass[p].nactive) R.passes++;
                 be.pass_points((int)p, hs.pass[p].npoints, hs.pass[p].npoints - hs.pass[p + 1].npoints);

@@ -1160,15 +1160,7 @@ struct CudaBackend : Backend {
     void pass(const PassArgs& a) override {
         const int nsm = sm_count();
         const int th = a.nbins < 32 ? 32 : a.nbins;
-        prof_begin(K_DIGHIST, 0, a.pass);
-        k_tile_index<<<std::min<uint32_t>(a.cap_chunks, 1024u), 256, 0, stream>>>(a);
-        k_dighist<<<nsm * 8, kDigThreads, 0, stream>>>(a);
-        prof_end();
-        prof_begin(K_SCAN, 0, a.pass);
-        k_scan_chunk_sums<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
-        k_scan_nodes<<<std::min<uint32_t>(a.cap_active, 2048u), th, 0, stream>>>(a);
-        k_scan_tiles<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
-        prof_end();
+        hist_scan_launch(a);
         prof_begin(K_PLAN, 0, a.pass);
         {
             const uint32_t pg = std::min<uint32_t>((a.cap_active + kPlanNodeThreads - 1) / kPlanNodeThreads, (uint32_t)nsm * 8u);
@@ -1185,6 +1177,24 @@ struct CudaBackend : Backend {
         prof_end();
         launches += 9;
         pass_wide = a.wide;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    void hist_scan_launch(const PassArgs& a) {
+        const int nsm = sm_count();
+        const int th = a.nbins < 32 ? 32 : a.nbins;
+        prof_begin(K_DIGHIST, 0, a.pass);
+        k_tile_index<<<std::min<uint32_t>(a.cap_chunks, 1024u), 256, 0, stream>>>(a);
+        k_dighist<<<nsm * 8, kDigThreads, 0, stream>>>(a);
+        prof_end();
+        prof_begin(K_SCAN, 0, a.pass);
+        k_scan_chunk_sums<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
+        k_scan_nodes<<<std::min<uint32_t>(a.cap_active, 2048u), th, 0, stream>>>(a);
+        k_scan_tiles<<<std::min<uint32_t>(a.cap_chunks, 2048u), th, 0, stream>>>(a);
+        prof_end();
+    }
+    void hist_scan(const PassArgs& a) override {
+        hist_scan_launch(a);
+        launches += 5;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
     bool pass_wide = false;

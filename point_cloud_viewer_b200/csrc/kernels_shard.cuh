@@ -304,6 +304,173 @@ __global__ void __launch_bounds__(256) k_pack_exchange_sorted(const __grid_const
 }
 
 // packed colours (as exchanged) -> the r, g, b byte array the build takes
+// ---- exchange of ingested records (the multi-GPU path of round 2) ------------------------------------------------------------
+// Every rank runs the ingest step on its own slice (level-1 codes + the digits of levels 1..2, kernels_build.cuh) and then moves
+// each record ONCE, as it is, into the receive slab of the rank that owns its level-k cell: 21 bytes per point over NVLink
+// (record 16 B + colour 4 B + digit 1 B [+ intensity 4 B]) instead of the 40-byte raw point, and the owner's build starts at its
+// first partition pass without repeating any arithmetic.  The kernel is the partition kernel's tile machinery with the
+// destination rank as the bucket: stage the tile (TMA), rank by bucket with __match_any_sync, sort the tile by destination in
+// shared memory, then store whole runs straight into the peers' memory (CUDA-IPC mapped slabs), so that the stores are full
+// lines on the link and overlap the ranking of the next tiles.  Inside a destination the order is (source rank, local index),
+// i.e. global index order - the reference's stable stream order.  idx of a stored record = its slot in the destination slab.
+constexpr int kExThreads = 256;
+struct ExchangeArgs {
+    const void* rec;
+    const uint32_t* col;
+    const uint8_t* dig;
+    const float* intensity;       // optional
+    const uint32_t* tile_counts;  // [ntiles][nbins] exclusive prefix over the earlier tiles, per digit (scan of the ingest's histogram)
+    uint64_t n;
+    uint32_t ntiles;
+    int nbins;                    // digits per record: 8 or 64
+    int cell_shift;               // level-k cell = digit >> cell_shift
+    int nranks;
+    bool wide;
+    uint8_t cell_to_rank[64];
+    unsigned long long dst_first[kMaxRanks];  // first slot of this source's block in every destination
+    void* dst_rec[kMaxRanks];
+    uint32_t* dst_col[kMaxRanks];
+    uint8_t* dst_dig[kMaxRanks];
+    float* dst_intensity[kMaxRanks];
+    uint8_t* dest_out;            // [n] destination rank of every local point (kept by the sender: provenance look-ups)
+};
+struct ExSmem {
+    static constexpr size_t rec_bytes = 16;
+    static constexpr size_t off_col = (size_t)kTilePoints * 32;  // sized for wide records
+    static constexpr size_t off_dig = off_col + ((size_t)kTilePoints + 4) * 4;
+    static constexpr size_t off_pfx = off_dig + (size_t)kTilePoints + 32;
+    static constexpr size_t off_perm = off_pfx + 64 * 4;
+    static constexpr size_t off_cnt = off_perm + (size_t)kTilePoints * 4;
+    static constexpr size_t off_first = off_cnt + (size_t)(kExThreads / 32) * kMaxRanks * 4;
+    static constexpr size_t off_start = off_first + (size_t)kMaxRanks * 8;
+    static constexpr size_t off_c2r = off_start + (size_t)kMaxRanks * 4;
+    static constexpr size_t off_bar = off_c2r + 64;
+    static constexpr size_t bytes = off_bar + 16;
+};
+template <bool WIDE>
+__global__ void __launch_bounds__(kExThreads, 2) k_exchange_records(const __grid_constant__ ExchangeArgs a) {
+    constexpr int kWarps = kExThreads / 32, kWarpItems = kTilePoints / kWarps, kSubRounds = kWarpItems / 32;
+    constexpr size_t recsz = WIDE ? 32 : 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned char* srec = smem_raw;
+    uint32_t* scol_base = reinterpret_cast<uint32_t*>(smem_raw + ExSmem::off_col);
+    uint8_t* sdig_base = smem_raw + ExSmem::off_dig;
+    uint32_t* spfx = reinterpret_cast<uint32_t*>(smem_raw + ExSmem::off_pfx);
+    uint32_t* perm = reinterpret_cast<uint32_t*>(smem_raw + ExSmem::off_perm);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + ExSmem::off_cnt);                     // [warps][kMaxRanks]
+    unsigned long long* rfirst = reinterpret_cast<unsigned long long*>(smem_raw + ExSmem::off_first);  // [ranks] slot of sorted position 0
+    uint32_t* rstart = reinterpret_cast<uint32_t*>(smem_raw + ExSmem::off_start);               // [ranks] sorted start
+    uint8_t* c2r = smem_raw + ExSmem::off_c2r;  // shared-memory copy: a per-thread indexed read of the kernel parameters is slow
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + ExSmem::off_bar);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nr = a.nranks;
+    if (tid < 64) c2r[tid] = a.cell_to_rank[tid];
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t par = 0;
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const uint64_t start = (uint64_t)tile * kTilePoints;
+        const uint64_t rem = a.n - start;
+        const uint32_t count = (uint32_t)(rem < kTilePoints ? rem : kTilePoints);
+        const uint32_t coff = (uint32_t)(start & 3), doff = (uint32_t)(start & 15);
+        const uint32_t* scol = scol_base + coff;
+        const uint8_t* sdig = sdig_base + doff;
+        if (tid == 0) {
+            const uint32_t rec_bytes = count * (uint32_t)recsz;
+            const uint32_t col_bytes = ((coff + count) * 4u + 15u) & ~15u;
+            const uint32_t dig_bytes = (doff + count + 15u) & ~15u;
+            const uint32_t pfx_bytes = (uint32_t)a.nbins * 4u;
+            mbar_expect_tx(mbar, rec_bytes + col_bytes + dig_bytes + pfx_bytes);
+            tma_bulk_load(smem_raw, reinterpret_cast<const unsigned char*>(a.rec) + start * recsz, rec_bytes, mbar);
+            tma_bulk_load(scol_base, a.col + (start - coff), col_bytes, mbar);
+            tma_bulk_load(sdig_base, a.dig + (start - doff), dig_bytes, mbar);
+            tma_bulk_load(spfx, a.tile_counts + (size_t)tile * a.nbins, pfx_bytes, mbar);
+        }
+        for (int i = tid; i < kWarps * kMaxRanks; i += kExThreads) cnt[i] = 0;
+        mbar_wait(mbar, par);
+        par ^= 1u;
+        __syncthreads();
+        // rank of every item from its digit; lanes grouped by destination
+        uint32_t info[kSubRounds];
+#pragma unroll
+        for (int r = 0; r < kSubRounds; ++r) {
+            const uint32_t i = warp * kWarpItems + r * 32 + lane;
+            uint32_t lbv = 0xFFFFu;
+            if (i < count) lbv = c2r[(sdig[i] & (uint32_t)(a.nbins - 1)) >> a.cell_shift];
+            const unsigned mask = __match_any_sync(0xffffffffu, lbv);
+            const uint32_t leader = (uint32_t)__ffs(mask) - 1u, gsize = (uint32_t)__popc(mask), rank = (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            info[r] = lbv | (rank << 16) | (leader << 21) | ((gsize - 1u) << 26);
+            if (lbv != 0xFFFFu && lane == (int)leader) cnt[warp * kMaxRanks + lbv] += gsize;
+            __syncwarp();
+        }
+        __syncthreads();
+        if (warp == 0) {  // per destination: total, sorted start, slot of sorted position 0, per-warp offsets
+            uint32_t tot[2] = {0, 0};
+            unsigned long long early[2] = {0, 0};  // records of this source for the destination in earlier tiles
+            for (int j = 0; j < 2; ++j) {
+                const int lb = lane + 32 * j;
+                if (lb < nr) {
+                    for (int w = 0; w < kWarps; ++w) tot[j] += cnt[w * kMaxRanks + lb];
+                    for (int d = 0; d < a.nbins; ++d)
+                        if (c2r[d >> a.cell_shift] == lb) early[j] += spfx[d];
+                }
+            }
+            uint32_t carry = 0;
+            for (int j = 0; j < 2; ++j) {
+                uint32_t incl = tot[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                const uint32_t excl = carry + incl - tot[j];
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                const int lb = lane + 32 * j;
+                if (lb < nr) {
+                    rstart[lb] = excl;
+                    rfirst[lb] = a.dst_first[lb] + early[j];
+                    uint32_t run = excl;
+                    for (int w = 0; w < kWarps; ++w) {
+                        const uint32_t c = cnt[w * kMaxRanks + lb];
+                        cnt[w * kMaxRanks + lb] = run;
+                        run += c;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSubRounds; ++r) {
+            const uint32_t i = warp * kWarpItems + r * 32 + lane;
+            const uint32_t lbv = info[r] & 0xFFFFu, rank = (info[r] >> 16) & 31u, gsize = ((info[r] >> 26) & 31u) + 1u;
+            const int leader = (int)((info[r] >> 21) & 31u);
+            uint32_t old = 0;
+            if (lane == leader && lbv != 0xFFFFu) {
+                old = cnt[warp * kMaxRanks + lbv];
+                cnt[warp * kMaxRanks + lbv] = old + gsize;
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            if (lbv != 0xFFFFu) perm[old + rank] = i | (lbv << 12);
+            __syncwarp();
+        }
+        __syncthreads();
+        // whole runs into the owners' slabs (peer memory over NVLink, or local memory for the own rank)
+        for (uint32_t p = tid; p < count; p += kExThreads) {
+            const uint32_t e = perm[p], i = e & 2047u, lb = e >> 12;
+            const unsigned long long slot = rfirst[lb] + (p - rstart[lb]);
+            uint64_t c[3];
+            uint32_t idx;
+            smem_load_rec<WIDE>(srec, i, c, idx);
+            store_rec<WIDE>(a.dst_rec[lb], slot, c, (uint32_t)slot);
+            a.dst_col[lb][slot] = scol[i];
+            a.dst_dig[lb][slot] = sdig[i];
+            if (a.intensity) a.dst_intensity[lb][slot] = a.intensity[start + i];
+            a.dest_out[start + i] = (uint8_t)lb;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_unpack_colours(const uint32_t* __restrict__ col, uint64_t n, uint8_t* __restrict__ rgb) {
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {

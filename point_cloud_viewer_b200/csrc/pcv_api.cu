@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <string>
+#include <memory>
 #include <thread>
 
 #include "../../include/pcv.h"
@@ -228,7 +229,7 @@ static pcv_octree* octree_from_result(pcv_ctx* c, BuildResult& R, double resolut
 }
 
 static int build_impl(pcv_ctx* c, const PointsView& v, double resolution, const double bmin_in[3], const double bmax_in[3],
-                      pcv_octree** out, const ShardSpec* shard = nullptr) {
+                      pcv_octree** out, const ShardSpec* shard = nullptr, const ExternalRecords* ext = nullptr) {
     double bmin[3], bmax[3];
     for (int a = 0; a < 3; ++a) {
         bmin[a] = std::fmin(bmin_in[a], bmax_in[a]);
@@ -243,6 +244,7 @@ static int build_impl(pcv_ctx* c, const PointsView& v, double resolution, const 
     CU(cudaEventRecord(e0, c->stream));
     BuildPlan plan(be, c->cfg.max_points_per_node, (int)c->cfg.levels_per_pass);
     if (shard) plan.shard = *shard;
+    if (ext) plan.ext = *ext;
     BuildResult R = plan.run(v, resolution, bmin, bmax);
     CU(cudaEventRecord(e1, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -278,6 +278,235 @@ int pcv_build_octree_sharded_device(pcv_ctx* c, const pcv_points* dp, double res
     API_CATCH
 }
 
+struct pcv_shard_send {
+    pcv_ctx* ctx = nullptr;
+    uint64_t n = 0;
+    bool wide = false, has_intensity = false;
+    int G0 = 2, nbins = 64;
+    uint32_t ntiles = 0;
+    void* rec = nullptr;
+    uint32_t* col = nullptr;
+    uint8_t* dig = nullptr;
+    const float* intensity = nullptr;  // the caller's array (not owned)
+    uint32_t* tile_counts = nullptr;
+    uint8_t* dest = nullptr;
+    std::vector<uint64_t> bins;  // points per digit of the local points
+    std::vector<void*> owned;
+};
+
+int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution, const double bmin_in[3], const double bmax_in[3], uint32_t k,
+                            uint64_t* counts_out, pcv_shard_send** out) {
+    if (!c || !dp || !bmin_in || !bmax_in || !counts_out || !out) return fail(PCV_ERR_INVALID, "null argument");
+    if (k < 1 || k > 2) return fail(PCV_ERR_INVALID, "prefix levels k must be 1 or 2");
+    *out = nullptr;
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    double bmin[3], bmax[3];
+    for (int a = 0; a < 3; ++a) {
+        bmin[a] = std::fmin(bmin_in[a], bmax_in[a]);
+        bmax[a] = std::fmax(bmin_in[a], bmax_in[a]);
+    }
+    const PointsView v = view_of(dp);
+    const uint64_t n = v.n;
+    for (uint64_t i = 0; i < ((uint64_t)1 << (3 * k)); ++i) counts_out[i] = 0;
+    if (n >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-2 points per context");
+    if (n && !v.rgb) return fail(PCV_ERR_INVALID, "color is mandatory");
+    const double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
+    const LevelTable lv = make_level_table(E, resolution, bmin);
+    if ((int)k > lv.last_level) return fail(PCV_ERR_INVALID, "prefix levels exceed the depth of the octree");
+    std::unique_ptr<pcv_shard_send> sd(new pcv_shard_send());
+    sd->ctx = c;
+    sd->n = n;
+    sd->has_intensity = v.intensity != nullptr;
+    sd->intensity = v.intensity;
+    for (int L = 1; L <= lv.last_level; ++L) sd->wide = sd->wide || lv.enc[L] == ENC_F64;
+    sd->G0 = std::min(2, lv.last_level);
+    sd->nbins = 1 << (3 * sd->G0);
+    if (n == 0) {
+        *out = sd.release();
+        return PCV_OK;
+    }
+    CudaBackend& be = *c->be;
+    auto dalloc = [&](size_t bytes) {
+        void* p = be.dmalloc(bytes);
+        sd->owned.push_back(p);
+        return p;
+    };
+    const size_t rec_bytes = sd->wide ? sizeof(RecW) : sizeof(RecN);
+    const uint32_t nt = (uint32_t)((n + kTilePoints - 1) / kTilePoints), nch = (nt + kChunkTiles - 1) / kChunkTiles;
+    sd->ntiles = nt;
+    sd->rec = dalloc((size_t)n * rec_bytes + 64);
+    sd->col = (uint32_t*)dalloc((size_t)n * 4 + 64);
+    sd->dig = (uint8_t*)dalloc((size_t)n + 64);
+    sd->dest = (uint8_t*)dalloc((size_t)n + 64);
+    sd->tile_counts = (uint32_t*)dalloc((size_t)nt * 64 * 4);
+    IngestArgs ia{};
+    ia.pts = v;
+    ia.rec_out = sd->rec;
+    ia.col_out = sd->col;
+    ia.dig_out = sd->dig;
+    ia.G0 = sd->G0;
+    ia.wide = sd->wide;
+    ia.ntiles = nt;
+    ia.lv = lv;
+    for (int a = 0; a < 3; ++a) ia.root_min[a] = bmin[a];
+    be.ingest(ia);
+    // per-tile digit histogram + exclusive prefix over the tiles (one "node": all local points), as a partition pass would
+    Scratch s(c);
+    BuildState hs{};
+    hs.nnodes = 1;
+    hs.pass[0].nactive = 1;
+    hs.pass[0].ntiles = nt;
+    hs.pass[0].nchunks = nch;
+    hs.pass[0].npoints = n;
+    BuildState* dst = s.upload(&hs, 1);
+    ActiveDesc a0{};
+    a0.count = n;
+    a0.nchunks = nch;
+    const ActiveDesc* dact = s.upload(&a0, 1);
+    std::vector<ChunkDesc> c0;
+    for (uint32_t o = 0; o < nt; o += kChunkTiles) c0.push_back(ChunkDesc{o, std::min(kChunkTiles, nt - o), 0u, o == 0 ? 1u : 0u});
+    const ChunkDesc* dch = s.upload(c0.data(), c0.size());
+    PassArgs pa{};
+    pa.pass = 0;
+    pa.G = sd->G0;
+    pa.nbins = sd->nbins;
+    pa.dig_in = sd->dig;
+    pa.st = dst;
+    pa.active = dact;
+    pa.chunks = dch;
+    pa.tile_counts = sd->tile_counts;
+    pa.tile_active = s.alloc<uint32_t>(nt);
+    pa.chunk_sums = s.alloc<uint32_t>((size_t)nch * 64);
+    pa.node_bins = s.alloc<uint64_t>(64);
+    pa.cap_active = 1;
+    pa.cap_chunks = nch;
+    pa.cap_tiles = nt;
+    be.hist_scan(pa);
+    std::vector<uint64_t> bins(64, 0);
+    be.d2h(bins.data(), pa.node_bins, (size_t)sd->nbins * 8);
+    const int shift = 3 * (sd->G0 - (int)k);  // digits carry G0 levels; the shard level may be shallower
+    if (shift < 0) return fail(PCV_ERR_INVALID, "prefix levels exceed the levels of the first pass");
+    for (int d = 0; d < sd->nbins; ++d) counts_out[d >> shift] += bins[(size_t)d];
+    sd->bins = bins;
+    *out = sd.release();
+    return PCV_OK;
+    API_CATCH
+}
+
+void pcv_shard_send_free(pcv_shard_send* s) {
+    if (!s) return;
+    pcv_ctx* c = s->ctx;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        cudaSetDevice(c->device);
+        for (void* p : s->owned) c->be->dfree(p);
+    }
+    delete s;
+}
+
+int pcv_shard_send_info(const pcv_shard_send* s, int* wide_records, int* digit_levels) {
+    if (!s) return fail(PCV_ERR_INVALID, "null argument");
+    if (wide_records) *wide_records = s->wide ? 1 : 0;
+    if (digit_levels) *digit_levels = s->G0;
+    return PCV_OK;
+}
+
+int pcv_shard_send_dest(const pcv_shard_send* s, const uint8_t** dev_dest, uint64_t* n) {
+    if (!s || !dev_dest || !n) return fail(PCV_ERR_INVALID, "null argument");
+    *dev_dest = s->dest;
+    *n = s->n;
+    return PCV_OK;
+}
+
+int pcv_shard_exchange_device(pcv_shard_send* sd, uint32_t k, const int32_t* cell_to_rank, uint32_t nranks, const uint64_t* dst_first, void* const* dst_rec,
+                              void* const* dst_col, void* const* dst_dig, void* const* dst_intensity, uint64_t* rank_counts_out) {
+    if (!sd || !cell_to_rank || !dst_first || !dst_rec || !dst_col || !dst_dig || !rank_counts_out) return fail(PCV_ERR_INVALID, "null argument");
+    if (nranks == 0 || nranks > (uint32_t)kMaxRanks) return fail(PCV_ERR_INVALID, "nranks must be 1..%d", kMaxRanks);
+    if (k < 1 || (int)k > sd->G0) return fail(PCV_ERR_INVALID, "prefix levels must be 1..%d", sd->G0);
+    if (sd->has_intensity && !dst_intensity) return fail(PCV_ERR_INVALID, "the points carry intensity: dst_intensity is required");
+    API_TRY
+    pcv_ctx* c = sd->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = 0;
+    if (sd->n == 0) return PCV_OK;
+    ExchangeArgs a{};
+    a.rec = sd->rec;
+    a.col = sd->col;
+    a.dig = sd->dig;
+    a.intensity = sd->has_intensity ? sd->intensity : nullptr;
+    a.tile_counts = sd->tile_counts;
+    a.n = sd->n;
+    a.ntiles = sd->ntiles;
+    a.nbins = sd->nbins;
+    a.cell_shift = 3 * (sd->G0 - (int)k);
+    a.nranks = (int)nranks;
+    a.wide = sd->wide;
+    const int ncell = 1 << (3 * k);
+    for (int i = 0; i < 64; ++i) a.cell_to_rank[i] = 0;
+    for (int i = 0; i < ncell; ++i) {
+        if (cell_to_rank[i] < 0 || cell_to_rank[i] >= (int32_t)nranks) return fail(PCV_ERR_INVALID, "cell_to_rank[%d] out of range", i);
+        a.cell_to_rank[i] = (uint8_t)cell_to_rank[i];
+    }
+    for (uint32_t r = 0; r < nranks; ++r) {
+        a.dst_first[r] = dst_first[r];
+        a.dst_rec[r] = dst_rec[r];
+        a.dst_col[r] = (uint32_t*)dst_col[r];
+        a.dst_dig[r] = (uint8_t*)dst_dig[r];
+        a.dst_intensity[r] = dst_intensity ? (float*)dst_intensity[r] : nullptr;
+    }
+    a.dest_out = sd->dest;
+    const uint32_t grid = std::min<uint32_t>(sd->ntiles, (uint32_t)c->sm_count * 2u);
+    if (sd->wide) {
+        CU(cudaFuncSetAttribute(k_exchange_records<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ExSmem::bytes));
+        k_exchange_records<true><<<grid, kExThreads, ExSmem::bytes, c->stream>>>(a);
+    } else {
+        CU(cudaFuncSetAttribute(k_exchange_records<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ExSmem::bytes));
+        k_exchange_records<false><<<grid, kExThreads, ExSmem::bytes, c->stream>>>(a);
+    }
+    c->be->launches++;
+    CU(cudaGetLastError());
+    for (int d = 0; d < sd->nbins; ++d) rank_counts_out[a.cell_to_rank[d >> a.cell_shift]] += sd->bins[(size_t)d];
+    CU(cudaStreamSynchronize(c->stream));  // every store of this rank has been issued and completed
+    // the records are consumed: only the per-point destination (provenance look-ups) stays with the handle
+    for (void*& p : sd->owned)
+        if (p != (void*)sd->dest) {
+            c->be->dfree(p);
+            p = nullptr;
+        }
+    sd->rec = nullptr, sd->col = nullptr, sd->dig = nullptr, sd->tile_counts = nullptr;
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_build_octree_from_records_device(pcv_ctx* c, void* rec, uint32_t* col, uint8_t* dig, const float* intensity, uint64_t n, double resolution,
+                                         const double bmin_in[3], const double bmax_in[3], uint32_t k, const uint64_t* prefix_counts, pcv_octree** out) {
+    if (!c || !bmin_in || !bmax_in || !prefix_counts || !out || (n && (!rec || !col || !dig))) return fail(PCV_ERR_INVALID, "null argument");
+    if (k < 1 || k > 3) return fail(PCV_ERR_INVALID, "prefix levels k must be 1..3");
+    *out = nullptr;
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ShardSpec sp;
+    sp.k = (int)k;
+    sp.counts = prefix_counts;
+    ExternalRecords ext;
+    ext.rec = rec;
+    ext.col = col;
+    ext.dig = dig;
+    ext.n = n;
+    ext.present = true;
+    PointsView v{};
+    v.stride = 1;
+    v.n = n;
+    v.intensity = intensity;
+    v.rgb = reinterpret_cast<const uint8_t*>(col);  // non-null marker: colours travel inside the records
+    return build_impl(c, v, resolution, bmin_in, bmax_in, out, &sp, &ext);
+    API_CATCH
+}
+
 int pcv_octree_node_nsub(const pcv_octree* o, uint64_t hi, uint64_t lo, uint64_t* nsub_out) {
     if (!o || !nsub_out) return fail(PCV_ERR_INVALID, "null argument");
     const int i = o->find(hi, lo);

@@ -6,10 +6,13 @@ below any octree prefix and the subsample phase only couples a parent with its 8
   1. all-reduce the 8^k histogram of level-k prefix cells (first k steps of the re-quantising descent on the raw
      positions - the cell the single-GPU build would route the point to);
   2. greedily balance the non-empty cells over the ranks (largest first);
-  3. stable pack by destination rank and ONE exchange (xyz, rgb, intensity, global index); every receiver holds the
-     source ranks' blocks in rank order, which is global index order, i.e. the reference's stable stream order.  On
-     GPUs pack and exchange are one kernel that stores straight into the owners' memory over NVLink (CUDA-IPC peer
-     mapping, `CudaOps.pack_exchange`); the staged variant (send buffers + all_to_all_single) serves the CPU tests;
+  3. ONE exchange; every receiver holds the source ranks' blocks in rank order, which is global index order, i.e. the
+     reference's stable stream order.  On GPUs every rank first runs the ingest step of the build on its own points
+     (level-1 codes + the digits of levels 1..2, whose histogram IS the cell histogram of step 1) and one kernel then
+     ranks the records by destination and stores them straight into the owners' memory over NVLink (CUDA-IPC peer mapping,
+     `CudaOps.ingest` / `exchange_records`): 21 bytes per point cross the link, and the owner's build starts at its first
+     partition pass - no arithmetic is repeated.  The staged variant (raw points packed into send buffers +
+     all_to_all_single) serves the CPU tests;
   4. every rank builds the sub-trees of its cells independently (global bounding cube; the nodes above level k take
      their split decision from the global counts);
   5. the <= 1 + 8 + 64 nodes above level k are assembled on rank 0 from the children's every-8th points (collected,
@@ -217,6 +220,34 @@ class CudaOps:
         idx = torch.as_tensor(_RawCuda(mine["idx"], (max(n, 1),), "<i8"), device=self.device)[:n].clone()  # the slab is reused by the next step
         return PeerReceive(n, mine["x"], mine["y"], mine["z"], rgb, mine["intensity"] if self.intensity is not None else None, idx)
 
+    # ---- round 2: exchange of ingested records (pcv.h pcv_shard_*) ----
+    def ingest(self, k):
+        """Ingest step + digit histogram of the local points -> level-k cell counts (the send handle stays with the ops)."""
+        counts, self.send = self.ctx.shard_ingest(self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr(), self.rgb.data_ptr(),
+                                                  self.intensity.data_ptr() if self.intensity is not None else None, self.n, self.res, self.bmin, self.bmax, k)
+        self.wide, self.digit_levels = self.ctx.shard_send_info(self.send)
+        return counts
+
+    def exchange_records(self, k, cell_to_rank, nranks, comm, send_counts):
+        """One kernel: every local record into its owner's slab.  Returns (RecordSlab, n received, count matrix)."""
+        M = comm.all_gather_counts(send_counts)  # M[s][d]: points rank s sends to rank d; identical on every rank
+        need = M.sum(0)
+        slab = RecordSlab.get(self.ctx, comm, int(need.max()), self.wide, self.intensity is not None)
+        rank = comm.rank
+        first = [int(M[:rank, d].sum()) for d in range(nranks)]
+        A = [slab.arrays(d) for d in range(nranks)]
+        comm.barrier()  # no peer is still using its slab as build scratch
+        counts = self.ctx.shard_exchange(self.send, k, cell_to_rank, nranks, first, [a["rec"] for a in A], [a["col"] for a in A], [a["dig"] for a in A],
+                                         [a["intensity"] for a in A] if self.intensity is not None else None)
+        assert [int(c) for c in counts] == [int(v) for v in M[rank]], "local histogram and exchange disagree"
+        comm.barrier()  # every rank's stores have landed (each kernel completed before its rank entered the barrier)
+        return slab, int(need[rank]), M
+
+    def build_from_records(self, slab, n, k, prefix_counts):
+        a = slab.arrays(slab.rank)
+        return self.ctx.build_octree_from_records(a["rec"] if n else 0, a["col"] if n else 0, a["dig"] if n else 0,
+                                                  a["intensity"] if (self.intensity is not None and n) else None, n, self.res, self.bmin, self.bmax, k, prefix_counts)
+
     def build_sharded_soa(self, recv, k, prefix_counts):
         n = recv.n
         return self.ctx.build_octree_sharded_device_soa(recv.x if n else 0, recv.y if n else 0, recv.z if n else 0, recv.rgb.data_ptr() if n else 0,
@@ -284,6 +315,79 @@ class PeerSlab:
         PeerSlab._cache.pop(id(self.ctx), None)
 
 
+class RecordSlab:
+    """Per-rank receive slab for ingested records, in exportable device memory mapped into every peer process through CUDA IPC.
+    All ranks use the same capacity (so that the sub-array offsets of a peer's slab are known): records (16 or 32 B) | packed
+    colour (4 B) | intensity (4 B, optional) | digits (1 B), each section with 256 bytes of slack (bulk copies read whole
+    16-byte granules).  Re-created collectively, and rarely, when a step needs more room."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, ctx, comm, need_points, wide, with_intensity):
+        cur = cls._cache.get(id(ctx))
+        if cur is not None and cur.cap >= need_points and cur.world == comm.world and cur.wide == wide and cur.with_intensity == with_intensity:
+            return cur
+        if cur is not None:
+            cur.close(comm)
+        cap = ((int(need_points * 1.05) + 4096 + 4095) // 4096) * 4096
+        cls._cache[id(ctx)] = slab = cls(ctx, comm, cap, wide, with_intensity)
+        return slab
+
+    def __init__(self, ctx, comm, cap, wide, with_intensity):
+        self.ctx, self.cap, self.world, self.rank, self.wide, self.with_intensity = ctx, cap, comm.world, comm.rank, wide, with_intensity
+        rs = 32 if wide else 16
+        self.off_col = rs * cap + 256
+        self.off_int = self.off_col + 4 * cap + 256
+        self.off_dig = self.off_int + (4 * cap + 256 if with_intensity else 0)
+        self.bytes = self.off_dig + cap + 256
+        self.ptr, handle = ctx.ipc_alloc(self.bytes)
+        handles = comm.all_gather_objects(handle)
+        self.peer = [self.ptr if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        comm.barrier()
+
+    def arrays(self, r):
+        b = self.peer[r]
+        return {"rec": b, "col": b + self.off_col, "intensity": b + self.off_int, "dig": b + self.off_dig}
+
+    def close(self, comm):
+        comm.barrier()  # nobody is still writing into a slab that is about to disappear
+        for r, p in enumerate(self.peer):
+            if r != self.rank:
+                self.ctx.ipc_close(p)
+        comm.barrier()
+        self.ctx.ipc_free(self.ptr)
+        RecordSlab._cache.pop(id(self.ctx), None)
+
+
+class LazyIndex:
+    """Global source index of every received record, materialised on first use (a collective over `comm`): the exchange is stable,
+    so the block a source rank wrote into this rank's slab holds, in order, exactly those of its points whose destination is
+    this rank - each source lists their global indices from its per-point destination array and one all-to-all delivers them."""
+
+    def __init__(self, ctx, send, index_base, n_local, M, comm):
+        self.ctx, self.send, self.base, self.n_local, self.M, self.comm = ctx, send, int(index_base), int(n_local), M, comm
+        self.value = None
+
+    def resolve(self):
+        if self.value is not None:
+            return self.value
+        import torch
+
+        dev, comm = self.comm.device, self.comm
+        ptr, n = self.ctx.shard_send_dest(self.send)
+        dest = torch.as_tensor(_RawCuda(ptr, (max(n, 1),), "|u1"), device=dev)[:n] if n else torch.zeros(0, dtype=torch.uint8, device=dev)
+        parts = [torch.nonzero(dest == d).flatten() + self.base for d in range(comm.world)]
+        send = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+        sc, rc = [int(v) for v in self.M[comm.rank]], [int(v) for v in self.M[:, comm.rank]]
+        assert [int(p.numel()) for p in parts] == sc, "destination array and count matrix disagree"
+        self.value = comm.all_to_all(send, sc, rc)
+        return self.value
+
+    def numel(self):
+        return int(self.M[:, self.comm.rank].sum())
+
+
 class ShardedOctree:
     """The result on one rank: `local` holds the sub-trees of this rank's cells (levels >= k) plus its collector
     content; `top` (rank 0 only) holds the nodes of levels < k.  The global octree is the union of every rank's
@@ -291,7 +395,8 @@ class ShardedOctree:
 
     def __init__(self, local, top, k, recv_index, top_index, cell_to_rank, rank, stats=None):
         self.local, self.top, self.k = local, top, k
-        self.recv_index, self.top_index = recv_index, top_index
+        self._recv_index, self._top_index = recv_index, top_index
+        self.send_handle = None  # (ctx, handle): the sender-side per-point destinations, kept for provenance look-ups
         self.cell_to_rank, self.rank = cell_to_rank, rank
         self.stats = stats or {}
         self._nodes = None
@@ -306,10 +411,42 @@ class ShardedOctree:
                 self._nodes.update(self.top.nodes)
         return self._nodes
 
+    @property
+    def recv_index(self):
+        """Global source index per received record.  COLLECTIVE on first use when the build exchanged ingested records."""
+        if isinstance(self._recv_index, LazyIndex):
+            self._recv_index = self._recv_index.resolve()
+        return self._recv_index
+
+    def resolve_provenance(self, comm):
+        """Collective: global source indices of the received records (every rank) and of the top nodes' points (rank 0)."""
+        r_idx = self.recv_index
+        if isinstance(self._top_index, dict):  # lazily gathered: {(collector, child): (owner rank, slots)} of every rank's own pieces
+            mine = {key: _take(r_idx, slots) for key, slots in self._top_index.get("mine", {}).items()}
+            parts = comm.all_gather_objects(mine)
+            if self.rank == 0:
+                allp = {}
+                for part in parts:
+                    allp.update(part)
+                keys = sorted(allp)
+                self._top_index = np.concatenate([np.asarray(allp[kk], np.uint64) for kk in keys]) if keys else np.zeros(0, np.uint64)
+            else:
+                self._top_index = None
+        return r_idx
+
+    @property
+    def top_index(self):
+        assert not isinstance(self._top_index, dict), "call resolve_provenance(comm) first (collective)"
+        return self._top_index
+
     def free(self):
         self.local.free()
         if self.top is not None:
             self.top.free()
+        if self.send_handle is not None:
+            ctx, h = self.send_handle
+            ctx.shard_send_free(h)
+            self.send_handle = None
 
     def node_arrays(self, name):
         """(xyz bytes, rgb, intensity, GLOBAL source index) of one of this rank's final nodes."""
@@ -321,6 +458,7 @@ class ShardedOctree:
 
     def gather_all(self, comm):
         """Test helper: every final node with its content on rank 0 (small clouds only)."""
+        self.resolve_provenance(comm)
         mine = {}
         for name, m in self.nodes.items():
             d = dict(num_points=m["num_points"], enc=m["enc"], cube=tuple(m["cube"]))
@@ -351,13 +489,8 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
 
     marks = [("start", time.perf_counter())]
 
-    def mark(name):
-        if os.environ.get("PCV_TIMING"):
-            if hasattr(comm, "device") and getattr(comm.device, "type", "cpu") == "cuda":
-                import torch
-
-                torch.cuda.synchronize()
-            marks.append((name, time.perf_counter()))
+    def mark(name):  # every phase ends in a host-visible synchronisation of the library's stream, so wall marks are device times
+        marks.append((name, time.perf_counter()))
 
     res, bmin, bmax = ops.res, np.asarray(ops.bmin, np.float64), np.asarray(ops.bmax, np.float64)
     lo, hi = np.minimum(bmin, bmax), np.maximum(bmin, bmax)
@@ -367,6 +500,9 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
     # (0) the bounding box is an argument of build_octree (generation.rs:292); the all-reduced box of the data is only
     # checked against it (find_bounding_box would be the producer in build_octree_from_file).
     k = int(prefix_levels)
+    records = hasattr(ops, "ingest") and not os.environ.get("PCV_NO_FUSED_EXCHANGE") and k <= 2
+    if records:
+        return _build_sharded_records(ops, comm, index_base, k, max_points_per_node, root_edge, marks, mark)
     if hasattr(ops, "prefix_histogram_bbox"):  # one pass over the positions for both
         local_hist, lmn, lmx = ops.prefix_histogram_bbox(k)
     else:
@@ -403,6 +539,32 @@ def build_sharded(ops, comm, index_base, prefix_levels=2, max_points_per_node=10
         local, r_idx = _staged_exchange_and_build(ops, comm, k, c2r, nranks, index_base, prefix_counts, mark)
     stats = local.ctx.last_build_stats() if hasattr(local, "ctx") and hasattr(local.ctx, "last_build_stats") else {}
     return _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts, stats, inside, marks, mark)
+
+
+def _build_sharded_records(ops, comm, index_base, k, max_points_per_node, root_edge, marks, mark):
+    """GPU path: ingest locally, exchange the records once over peer memory, build from the received records."""
+    nranks, rank = comm.world, comm.rank
+    local_hist = np.asarray(ops.ingest(k), np.uint64)
+    mark("ingest + histogram")
+    counts_k = comm.all_reduce_sum_u64(local_hist)
+    k2 = usable_prefix_levels(counts_k, k, root_edge, ops.res, max_points_per_node)
+    if k2 < k:
+        counts_k = counts_k.reshape(8 ** k2, -1).sum(1).astype(np.uint64)
+        local_hist = local_hist.reshape(8 ** k2, -1).sum(1).astype(np.uint64)
+        k = k2
+    prefix_counts = concat_counts(level_counts(counts_k, k))
+    c2r = assign_cells(counts_k, nranks)
+    send_counts = np.array([int(local_hist[c2r == d].sum()) for d in range(nranks)], np.int64)
+    mark("all-reduce + plan")
+    slab, n_recv, M = ops.exchange_records(k, c2r, nranks, comm, send_counts)
+    mark("exchange")
+    local = ops.build_from_records(slab, n_recv, k, prefix_counts)
+    mark("local build")
+    stats = local.ctx.last_build_stats()
+    r_idx = LazyIndex(ops.ctx, ops.send, index_base, ops.n, M, comm)
+    out = _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts, stats, None, marks, mark)
+    out.send_handle = (ops.ctx, ops.send)
+    return out
 
 
 def _staged_exchange_and_build(ops, comm, k, c2r, nranks, index_base, prefix_counts, mark):
@@ -457,9 +619,11 @@ def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts
         fetch = local.node_data
     unit_nsub = comm.all_reduce_sum_u64(unit_nsub)
     pieces = {}
+    lazy = isinstance(r_idx, LazyIndex)
+    lazy_slots = {}
     for pidx, key, npts, enc in collectors:
         cx, cr, ci, cs = fetch(key)
-        gsrc = _take(r_idx, cs)
+        gsrc = np.asarray(cs, np.uint64) if lazy else _take(r_idx, cs)  # lazy: slots now, global indices on demand
         bpc = ENC_BYTES[enc]
         off = 0
         for c in range(8):
@@ -467,7 +631,10 @@ def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts
             if c2r[cell] != rank or unit_nsub[cell] == 0:
                 continue
             cnt = (int(unit_nsub[cell]) + 7) // 8
-            pieces[(pidx, c)] = (cx[off * 3 * bpc:(off + cnt) * 3 * bpc].copy(), cr[off * 3:(off + cnt) * 3].copy(), None if ci is None else ci[off:off + cnt].copy(), gsrc[off:off + cnt].copy())
+            pieces[(pidx, c)] = (cx[off * 3 * bpc:(off + cnt) * 3 * bpc].copy(), cr[off * 3:(off + cnt) * 3].copy(), None if ci is None else ci[off:off + cnt].copy(),
+                                 None if lazy else gsrc[off:off + cnt].copy())
+            if lazy:
+                lazy_slots[(pidx, c)] = gsrc[off:off + cnt].copy()
             off += cnt
         assert off == npts, (pidx, off, npts)
     gathered = comm.all_gather_objects(pieces)
@@ -478,15 +645,19 @@ def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts
             allp.update(part)
         keys = sorted(allp)
         cat = lambda i, dt: np.concatenate([np.asarray(allp[kk][i]) for kk in keys]).astype(dt) if keys else np.zeros(0, dt)
-        t_xyz, t_rgb, top_index = cat(0, np.uint8), cat(1, np.uint8), cat(3, np.uint64)
+        t_xyz, t_rgb = cat(0, np.uint8), cat(1, np.uint8)
+        top_index = None if lazy else cat(3, np.uint64)
         t_int = cat(2, np.float32) if (keys and allp[keys[0]][2] is not None) else None
         top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
+    if lazy:
+        top_index = {"mine": lazy_slots}
     mark("top assembly")
     if os.environ.get("PCV_TIMING") and rank == 0:
         print("[pcv sharded] " + "  ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), flush=True)
     out = ShardedOctree(local, top, k, r_idx, top_index, c2r, rank, stats)
     out.bbox_inside = inside
     out.recv_points = int(r_idx.numel()) if hasattr(r_idx, "numel") else len(r_idx)
+    out.phases_ms = {marks[i][0]: (marks[i][1] - marks[i - 1][1]) * 1e3 for i in range(1, len(marks))}
     return out
 
 
