@@ -500,6 +500,9 @@ def run_ours(args):
             "kernels": {k: {"launches": v["launches"], "ms": v["ms"], "GBps": (v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for k, v in ks.items()},
         }
 
+        if args.roofline_only:
+            print(json.dumps(out))
+            return
         # ---- BASELINE config 3: frustum-culled point query over the resident octree ----
         try:
             out["frustum_query"] = bench_query(ctx, pcv, torch, O, last, args, bmin, bmax, peak, cores, res)
@@ -703,6 +706,7 @@ def main():
     ap.add_argument("--ply-points", type=float, default=1e8, help="points of the synthetic PLY file for the ingest measurement")
     ap.add_argument("--ref-points", type=float, default=1e8, help="points of the bounded sample each --impl reference step builds")
     ap.add_argument("--no-extras", action="store_true", help="profiling runs: only the timed build steps (no roofline / query / e2e / CPU legs)")
+    ap.add_argument("--roofline-only", action="store_true", help="development runs: timed steps + per-kernel roofline, none of the other legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

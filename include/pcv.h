@@ -223,15 +223,17 @@ int pcv_ipc_free(pcv_ctx* ctx, void* dev_ptr);
 int pcv_ipc_open(pcv_ctx* ctx, const uint8_t handle[64], void** dev_ptr);
 int pcv_ipc_close(pcv_ctx* ctx, void* dev_ptr);
 /* ---- exchange of ingested records: every rank runs the first step of the chain on its own points, the
- * records (level-1 codes 16 B + colour 4 B + digits 1 B [+ intensity 4 B]) move once into the owners' receive slabs, and every
- * owner's build starts at its first partition pass - nothing is computed twice and 21 instead of 40 bytes per point cross NVLink.
+ * records (three level-1 codes 12 B + packed colour 4 B as one 16-byte record, digits 1 B [+ intensity 4 B]; Float64 trees: 32-byte
+ * records + a separate colour array) move once into the owners' receive slabs, and every owner's build starts at its first
+ * partition pass - nothing is computed twice and 17 instead of 40 bytes per point cross NVLink.
  *   pcv_shard_ingest_device   ingest kernel + per-tile digit histogram of the local points; counts_out = their 8^k level-k cells
  *   pcv_shard_exchange_device one kernel: rank every record by destination and store it straight into the destination slab
  *                             (dst_*[r] = rank r's slab arrays as mapped in THIS process, capacity + 64 bytes of slack each;
  *                             dst_first[r] = first slot of this rank's block in them).  idx of a stored record = its slot.
  *                             Returns after the kernel has completed; the caller then runs one inter-process barrier.
  *   pcv_shard_send_dest       per local point the rank it went to (device, n bytes; valid until pcv_shard_send_free)
- *   pcv_build_octree_from_records_device  the owner's build over its slab (the slab is reused as scratch by the build). */
+ *   pcv_build_octree_from_records_device  the owner's build over its slab (dev_col == NULL: narrow records carrying their colour,
+ *                             as pcv_shard_exchange_device stores them; the slab is reused as scratch by the build). */
 typedef struct pcv_shard_send pcv_shard_send;
 int pcv_shard_ingest_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3], const double bbox_max[3],
                             uint32_t k, uint64_t* counts_out /* 8^k, host */, pcv_shard_send** out);

@@ -212,7 +212,7 @@ class Context:
         first = np.ascontiguousarray(dst_first, np.uint64)
         arr = lambda lst: (C.c_void_p * nranks)(*[int(v) if v else None for v in lst])
         counts = np.zeros(nranks, np.uint64)
-        N.check(N.lib().pcv_shard_exchange_device(send, k, _p(c2r), nranks, _p(first), arr(dst_rec), arr(dst_col), arr(dst_dig),
+        N.check(N.lib().pcv_shard_exchange_device(send, k, _p(c2r), nranks, _p(first), arr(dst_rec), arr(dst_col) if dst_col is not None else None, arr(dst_dig),
                                                   arr(dst_intensity) if dst_intensity is not None else None, _p(counts)))
         return counts
 

@@ -170,6 +170,7 @@ struct PassArgs {
     int pass, level, G, nbins;  // level L of the pass's active nodes; G = levels it resolves (1 or 2); nbins = 8^G
     int Gn;                     // levels the following pass resolves (0: there is none - every destination is a leaf)
     bool wide;
+    bool rec_has_col;  // first pass over exchanged (narrow) records: a record's 4th word is the packed colour, its idx is its position
     // per-pass level constants as plain scalars (a dynamically indexed read of `lv` in a kernel is an indexed constant load
     // per use): levels L+1, L+2 and, for records that continue, the node level Lb = L+G and its child level
     double e1, e2, ry2, eb, eh, ryh;
@@ -442,6 +443,16 @@ inline LevelTable make_level_table(double root_edge, double resolution, const do
         }
         if (ok) t.fast = 2;
     }
+    // Power-of-two edges (a root edge of 2^j halves exactly down to the last level): the division by an edge is an exact
+    // scaling for every operand, so the kernels multiply by 2^-j and need neither reciprocal refinement nor range checks.
+    if (t.fast && !std::getenv("PCV_NO_POW2")) {
+        bool pow2 = true;
+        for (int L = 0; L <= std::min(t.last_level + 1, kMaxLevels - 1) && pow2; ++L) {
+            int ex = 0;
+            pow2 = std::isnormal(t.edge[L]) && std::frexp(t.edge[L], &ex) == 0.5 && std::isnormal(t.ry[L]) && t.ry[L] * t.edge[L] == 1.0;
+        }
+        if (pow2) t.fast = 3;
+    }
     return t;
 }
 
@@ -476,6 +487,7 @@ struct ExternalRecords {
     const uint8_t* dig = nullptr;
     uint64_t n = 0;
     bool present = false;
+    bool col_in_record = false;  // narrow records as they cross the link: {code x 3, packed colour}; idx == position is implied
 };
 
 class BuildPlan {
@@ -552,7 +564,7 @@ class BuildPlan {
         try {
             // ping-pong buffers; with external records the first of each pair is the caller's (read only, never freed here)
             void* bufs[2] = {ext.present ? const_cast<void*>(ext.rec) : dalloc((size_t)N * rec_bytes + 64), dalloc((size_t)N * rec_bytes + 64)};
-            uint32_t* cols[2] = {ext.present ? const_cast<uint32_t*>(ext.col) : (uint32_t*)dalloc((size_t)N * 4 + 64),
+            uint32_t* cols[2] = {(ext.present && ext.col) ? const_cast<uint32_t*>(ext.col) : (uint32_t*)dalloc((size_t)N * 4 + 64),
                                  (uint32_t*)dalloc((size_t)N * 4 + 64)};  // + slack: bulk copies read whole 16-byte granules
             uint8_t* digs[2] = {ext.present ? const_cast<uint8_t*>(ext.dig) : (uint8_t*)dalloc((size_t)N + 64), (uint8_t*)dalloc((size_t)N + 64)};
             arena = dalloc((size_t)N * rec_bytes);
@@ -627,6 +639,7 @@ class BuildPlan {
                 pa.nbins = 1 << (3 * pa.G);
                 pa.Gn = p + 1 < sched.size() ? sched[p + 1].G : 0;
                 pa.wide = wide;
+                pa.rec_has_col = ext.present && ext.col_in_record && p == 0;
                 pa.rec_in = bufs[p & 1];
                 pa.rec_next = bufs[(p + 1) & 1];
                 pa.arena = arena;

@@ -26,7 +26,9 @@ __device__ __forceinline__ unsigned div_bad(double a) {
 // Raw input coordinate admissible for the unchecked fast sequence (FAST == 2)?  |x| < 2^400, which also rejects inf / NaN.
 __device__ __forceinline__ unsigned input_bad(double x) { return fabs(x) < 2.582249878086908589655919172003011874329705792829223512830659e120 ? 0u : 1u; }
 
-// FAST: 0 = IEEE division; 1 = reciprocal sequence, every numerator range-checked (flag -> the caller redoes with 0);
+// FAST: 3 = every edge of the tree is a power of two (LevelTable::fast == 3): a / e is the exact scaling a * 2^-j for EVERY
+// input (zero, subnormal, inf, NaN included: both are the correctly rounded value of the same real number), no guard at all;
+// 0 = IEEE division; 1 = reciprocal sequence, every numerator range-checked (flag -> the caller redoes with 0);
 // 2 = reciprocal sequence without per-numerator checks: the host proved that every cube of the tree keeps all
 // coordinates at magnitudes in [2^-300, 2^301) (LevelTable::fast == 2), so q - m is exactly 0 or in [2^-353, 2^500)
 // once the raw inputs passed input_bad() in the root pass.
@@ -38,7 +40,9 @@ __device__ __forceinline__ uint64_t axis_step(double& q, double& m, double e_cur
     m = bit ? m + e_half : m;
     const double a = q - m;
     double t;
-    if (FAST) {
+    if (FAST == 3) {
+        t = a * ry;
+    } else if (FAST) {
         if (FAST == 1) bad |= div_bad(a);
         const double q0 = a * ry;
         const double q1 = fma(fma(-q0, e_half, a), ry, q0);
@@ -103,7 +107,9 @@ template <int ENC, int FAST>
 __device__ __forceinline__ uint64_t encode_axis(double value, double mn, double edge, double ry, unsigned& bad) {
     const double a = value - mn;
     double t;
-    if (FAST) {
+    if (FAST == 3) {
+        t = a * ry;
+    } else if (FAST) {
         if (FAST == 1) bad |= div_bad(a);
         const double q0 = a * ry;
         const double q1 = fma(fma(-q0, edge, a), ry, q0);

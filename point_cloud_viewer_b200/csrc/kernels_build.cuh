@@ -238,7 +238,7 @@ __device__ __forceinline__ unsigned ingest_tile(const IngestArgs& a, uint64_t st
 }
 
 template <bool WIDE>
-__global__ void __launch_bounds__(kIngestThreads) k_ingest(const __grid_constant__ IngestArgs a) {
+__global__ void __launch_bounds__(kIngestThreads, 4) k_ingest(const __grid_constant__ IngestArgs a) {
     __shared__ __align__(16) uint8_t srgb[kRgbStage];
     __shared__ __align__(16) uint32_t scol[kTilePoints];
     const int tid = threadIdx.x;
@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(kIngestThreads) k_ingest(const __grid_constant
             }
             __syncthreads();
         }
-        if (a.lv.fast) {
+        if (a.lv.fast == 3) {
+            ingest_tile<WIDE, 3>(a, start, count, scol);  // power-of-two edges: exact for every input, nothing to repeat
+        } else if (a.lv.fast) {
             const unsigned bad = a.lv.fast == 2 ? ingest_tile<WIDE, 2>(a, start, count, scol) : ingest_tile<WIDE, 1>(a, start, count, scol);
             if (__syncthreads_or((int)bad)) ingest_tile<WIDE, 0>(a, start, count, scol);  // a numerator outside the proven range: IEEE operator (same stores)
         } else {
@@ -659,13 +661,19 @@ __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTil
         const bool next = (bd.kk >> 8) == 0;
         const int keep = (int)(bd.kk & 0xFFu);
         uint64_t c[3];
-        uint32_t idx;
+        uint32_t idx, colour;
         smem_load_rec<WIDE>(srec, i, c, idx);
+        if (!WIDE && a.rec_has_col) {  // exchanged record: {codes, colour}; the record's index is its position in the slab
+            colour = idx;
+            idx = (uint32_t)pt.start + i;
+        } else {
+            colour = scol[i];
+        }
         unsigned dig_out = 0;
         if (next || keep == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], keep, next, dig_out, bad);
         if (FAST == 1 && bad) continue;  // the block repeats the sweep with the IEEE operator
         store_rec<WIDE>(reinterpret_cast<void*>(bd.rec + (unsigned long long)p * recsz), 0, c, idx);
-        *reinterpret_cast<uint32_t*>(bd.col + 4ull * p) = scol[i];
+        *reinterpret_cast<uint32_t*>(bd.col + 4ull * p) = colour;
         if (next) *reinterpret_cast<uint8_t*>(bd.dig + p) = (uint8_t)dig_out;
     }
     return bad;
@@ -688,10 +696,11 @@ __device__ __forceinline__ void pass_stage_big(const PassArgs& a, const PassTile
     constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
     const uint32_t coff = (uint32_t)(d.start & 3);
     const uint32_t rec_bytes = d.count * (uint32_t)recsz;
-    const uint32_t col_bytes = ((coff + d.count) * 4u + 15u) & ~15u;
+    const bool with_col = WIDE || !a.rec_has_col;
+    const uint32_t col_bytes = with_col ? (((coff + d.count) * 4u + 15u) & ~15u) : 0u;
     mbar_expect_tx(bar, rec_bytes + col_bytes);
     tma_bulk_load(smem_raw, reinterpret_cast<const unsigned char*>(a.rec_in) + d.start * recsz, rec_bytes, bar);
-    tma_bulk_load(smem_raw + PassSmem<WIDE>::off_col, a.col_in + (d.start - coff), col_bytes, bar);
+    if (with_col) tma_bulk_load(smem_raw + PassSmem<WIDE>::off_col, a.col_in + (d.start - coff), col_bytes, bar);
 }
 __device__ __forceinline__ void pass_make_desc(PassTile* desc, uint32_t tile, const ActiveDesc& act, uint32_t active) {
     const uint64_t o = (uint64_t)(tile - act.tile_begin) * kTilePoints;
@@ -873,7 +882,9 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_
         // (5) finish + store in destination order (speculatively through the reciprocal division; repeated with the IEEE
         // operator if any numerator of the block was outside the proven range - the stores are idempotent)
         mbar_wait(&mbar[2], it & 1u);  // records and colours: requested when the previous tile's sweep ended
-        if (a.fast == 2) {
+        if (a.fast == 3) {
+            pass_finish<WIDE, 3>(a, pt, srec, scol, sdig, perm, bdst);  // power-of-two edges: exact scaling, nothing to repeat
+        } else if (a.fast == 2) {
             pass_finish<WIDE, 2>(a, pt, srec, scol, sdig, perm, bdst);  // no per-numerator checks: nothing to repeat
         } else if (a.fast == 1) {
             const unsigned bad = pass_finish<WIDE, 1>(a, pt, srec, scol, sdig, perm, bdst);
@@ -1000,7 +1011,9 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
         place_movers<WIDE>(a, lt, leaf, true);
         return;
     }
-    if (a.fast) {
+    if (a.fast == 3) {
+        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 3>(a, lt, leaf);)
+    } else if (a.fast) {
         unsigned bad = 0;
         if (a.fast == 2) {
             PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, 2>(a, lt, leaf);)

@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(256) k_pack_exchange_sorted(const __grid_const
 // packed colours (as exchanged) -> the r, g, b byte array the build takes
 // ---- exchange of ingested records (the multi-GPU path of round 2) ------------------------------------------------------------
 // Every rank runs the ingest step on its own slice (level-1 codes + the digits of levels 1..2, kernels_build.cuh) and then moves
-// each record ONCE, as it is, into the receive slab of the rank that owns its level-k cell: 21 bytes per point over NVLink
-// (record 16 B + colour 4 B + digit 1 B [+ intensity 4 B]) instead of the 40-byte raw point, and the owner's build starts at its
+// each record ONCE into the receive slab of the rank that owns its level-k cell: 17 bytes per point over NVLink (three codes
+// 12 B + packed colour 4 B in one 16-byte store, digits 1 B [+ intensity 4 B]; the record's index is its slot in the slab and is
+// not transmitted) instead of the 40-byte raw point, and the owner's build starts at its
 // first partition pass without repeating any arithmetic.  The kernel is the partition kernel's tile machinery with the
 // destination rank as the bucket: stage the tile (TMA), rank by bucket with __match_any_sync, sort the tile by destination in
 // shared memory, then store whole runs straight into the peers' memory (CUDA-IPC mapped slabs), so that the stores are full
@@ -461,8 +462,12 @@ __global__ void __launch_bounds__(kExThreads, 2) k_exchange_records(const __grid
             uint64_t c[3];
             uint32_t idx;
             smem_load_rec<WIDE>(srec, i, c, idx);
-            store_rec<WIDE>(a.dst_rec[lb], slot, c, (uint32_t)slot);
-            a.dst_col[lb][slot] = scol[i];
+            if (WIDE) {
+                store_rec<WIDE>(a.dst_rec[lb], slot, c, (uint32_t)slot);
+                a.dst_col[lb][slot] = scol[i];
+            } else {  // on the wire a narrow record is {code x 3, packed colour}: its index is its slot, which the owner knows
+                store_rec<WIDE>(a.dst_rec[lb], slot, c, scol[i]);
+            }
             a.dst_dig[lb][slot] = sdig[i];
             if (a.intensity) a.dst_intensity[lb][slot] = a.intensity[start + i];
             a.dest_out[start + i] = (uint8_t)lb;

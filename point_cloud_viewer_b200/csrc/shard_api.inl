@@ -422,7 +422,8 @@ int pcv_shard_send_dest(const pcv_shard_send* s, const uint8_t** dev_dest, uint6
 
 int pcv_shard_exchange_device(pcv_shard_send* sd, uint32_t k, const int32_t* cell_to_rank, uint32_t nranks, const uint64_t* dst_first, void* const* dst_rec,
                               void* const* dst_col, void* const* dst_dig, void* const* dst_intensity, uint64_t* rank_counts_out) {
-    if (!sd || !cell_to_rank || !dst_first || !dst_rec || !dst_col || !dst_dig || !rank_counts_out) return fail(PCV_ERR_INVALID, "null argument");
+    if (!sd || !cell_to_rank || !dst_first || !dst_rec || !dst_dig || !rank_counts_out) return fail(PCV_ERR_INVALID, "null argument");
+    if (sd->wide && !dst_col) return fail(PCV_ERR_INVALID, "wide (Float64) records travel with a separate colour array: dst_col is required");
     if (nranks == 0 || nranks > (uint32_t)kMaxRanks) return fail(PCV_ERR_INVALID, "nranks must be 1..%d", kMaxRanks);
     if (k < 1 || (int)k > sd->G0) return fail(PCV_ERR_INVALID, "prefix levels must be 1..%d", sd->G0);
     if (sd->has_intensity && !dst_intensity) return fail(PCV_ERR_INVALID, "the points carry intensity: dst_intensity is required");
@@ -453,7 +454,7 @@ int pcv_shard_exchange_device(pcv_shard_send* sd, uint32_t k, const int32_t* cel
     for (uint32_t r = 0; r < nranks; ++r) {
         a.dst_first[r] = dst_first[r];
         a.dst_rec[r] = dst_rec[r];
-        a.dst_col[r] = (uint32_t*)dst_col[r];
+        a.dst_col[r] = dst_col ? (uint32_t*)dst_col[r] : nullptr;
         a.dst_dig[r] = (uint8_t*)dst_dig[r];
         a.dst_intensity[r] = dst_intensity ? (float*)dst_intensity[r] : nullptr;
     }
@@ -483,7 +484,7 @@ int pcv_shard_exchange_device(pcv_shard_send* sd, uint32_t k, const int32_t* cel
 
 int pcv_build_octree_from_records_device(pcv_ctx* c, void* rec, uint32_t* col, uint8_t* dig, const float* intensity, uint64_t n, double resolution,
                                          const double bmin_in[3], const double bmax_in[3], uint32_t k, const uint64_t* prefix_counts, pcv_octree** out) {
-    if (!c || !bmin_in || !bmax_in || !prefix_counts || !out || (n && (!rec || !col || !dig))) return fail(PCV_ERR_INVALID, "null argument");
+    if (!c || !bmin_in || !bmax_in || !prefix_counts || !out || (n && (!rec || !dig))) return fail(PCV_ERR_INVALID, "null argument");
     if (k < 1 || k > 3) return fail(PCV_ERR_INVALID, "prefix levels k must be 1..3");
     *out = nullptr;
     API_TRY
@@ -498,11 +499,12 @@ int pcv_build_octree_from_records_device(pcv_ctx* c, void* rec, uint32_t* col, u
     ext.dig = dig;
     ext.n = n;
     ext.present = true;
+    ext.col_in_record = col == nullptr;  // narrow records as exchanged: {code x 3, colour}
     PointsView v{};
     v.stride = 1;
     v.n = n;
     v.intensity = intensity;
-    v.rgb = reinterpret_cast<const uint8_t*>(col);  // non-null marker: colours travel inside the records
+    v.rgb = reinterpret_cast<const uint8_t*>(rec);  // non-null marker: colours travel with the records
     return build_impl(c, v, resolution, bmin_in, bmax_in, out, &sp, &ext);
     API_CATCH
 }

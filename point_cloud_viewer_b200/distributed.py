@@ -22,6 +22,8 @@ The compute steps are CUDA kernels behind the C ABI (`CudaOps`); the collectives
 The orchestration below is backend-neutral so that tests can run it on 2 CPU processes over gloo with the test-only
 sequential stand-ins for the kernels.
 """
+import sys
+
 import numpy as np
 
 from . import ENC_BYTES
@@ -125,6 +127,17 @@ class TorchComm:
         s = torch.from_numpy(np.asarray(counts, np.int64)).to(self.device)
         out = torch.empty((self.world, s.numel()), dtype=torch.int64, device=self.device)
         self.dist.all_gather_into_tensor(out, s)
+        return out.cpu().numpy()
+
+    def all_gather_bytes(self, buf, nbytes_max):
+        """(world, nbytes_max) uint8 matrix: row r = rank r's byte buffer, zero padded (one tensor collective, no pickling)."""
+        import torch
+
+        t = torch.zeros(nbytes_max, dtype=torch.uint8, device=self.device)
+        if len(buf):
+            t[: len(buf)] = torch.from_numpy(np.ascontiguousarray(buf, np.uint8)).to(self.device)
+        out = torch.empty((self.world, nbytes_max), dtype=torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy()
 
     def barrier(self):
@@ -237,7 +250,7 @@ class CudaOps:
         first = [int(M[:rank, d].sum()) for d in range(nranks)]
         A = [slab.arrays(d) for d in range(nranks)]
         comm.barrier()  # no peer is still using its slab as build scratch
-        counts = self.ctx.shard_exchange(self.send, k, cell_to_rank, nranks, first, [a["rec"] for a in A], [a["col"] for a in A], [a["dig"] for a in A],
+        counts = self.ctx.shard_exchange(self.send, k, cell_to_rank, nranks, first, [a["rec"] for a in A], [a["col"] for a in A] if self.wide else None, [a["dig"] for a in A],
                                          [a["intensity"] for a in A] if self.intensity is not None else None)
         assert [int(c) for c in counts] == [int(v) for v in M[rank]], "local histogram and exchange disagree"
         comm.barrier()  # every rank's stores have landed (each kernel completed before its rank entered the barrier)
@@ -245,7 +258,7 @@ class CudaOps:
 
     def build_from_records(self, slab, n, k, prefix_counts):
         a = slab.arrays(slab.rank)
-        return self.ctx.build_octree_from_records(a["rec"] if n else 0, a["col"] if n else 0, a["dig"] if n else 0,
+        return self.ctx.build_octree_from_records(a["rec"] if n else 0, (a["col"] if n else 0) if slab.wide else None, a["dig"] if n else 0,
                                                   a["intensity"] if (self.intensity is not None and n) else None, n, self.res, self.bmin, self.bmax, k, prefix_counts)
 
     def build_sharded_soa(self, recv, k, prefix_counts):
@@ -337,6 +350,7 @@ class RecordSlab:
     def __init__(self, ctx, comm, cap, wide, with_intensity):
         self.ctx, self.cap, self.world, self.rank, self.wide, self.with_intensity = ctx, cap, comm.world, comm.rank, wide, with_intensity
         rs = 32 if wide else 16
+        # build scratch: the owner's partition passes ping-pong through the slab, so the colour section exists either way
         self.off_col = rs * cap + 256
         self.off_int = self.off_col + 4 * cap + 256
         self.off_dig = self.off_int + (4 * cap + 256 if with_intensity else 0)
@@ -637,23 +651,66 @@ def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts
                 lazy_slots[(pidx, c)] = gsrc[off:off + cnt].copy()
             off += cnt
         assert off == npts, (pidx, off, npts)
-    gathered = comm.all_gather_objects(pieces)
     top, top_index = None, None
-    if rank == 0:
-        allp = {}
-        for part in gathered:
-            allp.update(part)
-        keys = sorted(allp)
-        cat = lambda i, dt: np.concatenate([np.asarray(allp[kk][i]) for kk in keys]).astype(dt) if keys else np.zeros(0, dt)
-        t_xyz, t_rgb = cat(0, np.uint8), cat(1, np.uint8)
-        top_index = None if lazy else cat(3, np.uint64)
-        t_int = cat(2, np.float32) if (keys and allp[keys[0]][2] is not None) else None
-        top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
+    if hasattr(comm, "all_gather_bytes") and lazy:
+        # Every rank can derive every rank's piece list (cell order) from the all-reduced unit sizes and the cell -> rank map, so
+        # the collectors' content travels as ONE padded byte tensor per rank: [xyz of its pieces | rgb | intensity].
+        has_int = getattr(ops, "intensity", None) is not None
+        enc_all = comm.all_gather_counts([max([e for _, _, _, e in collectors], default=0)])
+        bpc = ENC_BYTES[int(enc_all.max())] if int(enc_all.max()) else 1
+        owned = [[] for _ in range(nranks)]  # per rank: (cell, count) in cell order
+        for cell in range(8 ** k):
+            if unit_nsub[cell]:
+                owned[int(c2r[cell])].append((cell, (int(unit_nsub[cell]) + 7) // 8))
+        per_pt = 3 * bpc + 3 + (4 if has_int else 0)
+        nbytes = [sum(c for _, c in lst) * per_pt for lst in owned]
+        mine = owned[rank]
+        parts = [[], [], []]
+        for cell, cnt in mine:
+            px, pr, pi, _ = pieces[(cell // 8, cell % 8)]
+            assert len(pr) == 3 * cnt, (cell, len(pr), cnt)
+            parts[0].append(np.asarray(px, np.uint8))
+            parts[1].append(np.asarray(pr, np.uint8))
+            if has_int:
+                parts[2].append(np.asarray(pi, np.float32).view(np.uint8))
+        buf = np.concatenate([a for grp in parts for a in grp]) if mine else np.zeros(0, np.uint8)
+        assert len(buf) == nbytes[rank]
+        allb = comm.all_gather_bytes(buf, max(max(nbytes), 16))
+        if rank == 0:
+            xs, rs, its = {}, {}, {}
+            for r in range(nranks):
+                tot = sum(c for _, c in owned[r])
+                row, ox, orr, oi = allb[r], 0, tot * 3 * bpc, tot * (3 * bpc + 3)
+                for cell, cnt in owned[r]:
+                    xs[cell] = row[ox:ox + cnt * 3 * bpc]
+                    rs[cell] = row[orr:orr + cnt * 3]
+                    ox += cnt * 3 * bpc
+                    orr += cnt * 3
+                    if has_int:
+                        its[cell] = row[oi:oi + cnt * 4]
+                        oi += cnt * 4
+            cells = sorted(xs)
+            t_xyz = np.concatenate([xs[c] for c in cells]) if cells else np.zeros(0, np.uint8)
+            t_rgb = np.concatenate([rs[c] for c in cells]) if cells else np.zeros(0, np.uint8)
+            t_int = np.concatenate([its[c] for c in cells]).view(np.float32) if (cells and has_int) else None
+            top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
+    else:
+        gathered = comm.all_gather_objects(pieces)
+        if rank == 0:
+            allp = {}
+            for part in gathered:
+                allp.update(part)
+            keys = sorted(allp)
+            cat = lambda i, dt: np.concatenate([np.asarray(allp[kk][i]) for kk in keys]).astype(dt) if keys else np.zeros(0, dt)
+            t_xyz, t_rgb = cat(0, np.uint8), cat(1, np.uint8)
+            top_index = None if lazy else cat(3, np.uint64)
+            t_int = cat(2, np.float32) if (keys and allp[keys[0]][2] is not None) else None
+            top = ops.assemble_top(k, prefix_counts, unit_nsub, t_xyz, t_rgb, t_int)
     if lazy:
         top_index = {"mine": lazy_slots}
     mark("top assembly")
     if os.environ.get("PCV_TIMING") and rank == 0:
-        print("[pcv sharded] " + "  ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), flush=True)
+        print("[pcv sharded] " + "  ".join("%s %.1f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3) for i in range(1, len(marks))), file=sys.stderr, flush=True)
     out = ShardedOctree(local, top, k, r_idx, top_index, c2r, rank, stats)
     out.bbox_inside = inside
     out.recv_points = int(r_idx.numel()) if hasattr(r_idx, "numel") else len(r_idx)

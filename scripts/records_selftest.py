@@ -25,14 +25,11 @@ rec = torch.zeros(cap * (32 if wide else 16) + 256, dtype=torch.uint8, device=de
 col = torch.zeros(cap + 64, dtype=torch.int32, device=dev)
 dig = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
 c2r = np.zeros(8 ** k, np.int32)
-got = ctx.shard_exchange(send, k, c2r, 1, [0], [rec.data_ptr()], [col.data_ptr()], [dig.data_ptr()])
+got = ctx.shard_exchange(send, k, c2r, 1, [0], [rec.data_ptr()], [col.data_ptr()] if wide else None, [dig.data_ptr()])
 assert int(got[0]) == n
 torch.cuda.synchronize()
-idx = rec.view(torch.int32)[: n * 4].view(n, 4)[:, 3] if not wide else None
-if idx is not None:
-    assert torch.equal(idx.cpu(), torch.arange(n, dtype=torch.int32)), "record idx must be the slot"
 pc = D.concat_counts(D.level_counts(counts, k))
-local = ctx.build_octree_from_records(rec.data_ptr(), col.data_ptr(), dig.data_ptr(), None, n, res, bmin, bmax, k, pc)
+local = ctx.build_octree_from_records(rec.data_ptr(), col.data_ptr() if wide else None, dig.data_ptr(), None, n, res, bmin, bmax, k, pc)
 single = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
 bad = 0
 for name, m in single.nodes.items():
