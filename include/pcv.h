@@ -48,7 +48,7 @@ enum { PCV_ENC_UINT8 = 1, PCV_ENC_UINT16 = 2, PCV_ENC_FLOAT32 = 3, PCV_ENC_FLOAT
 
 typedef struct pcv_config {
     uint64_t max_points_per_node; /* MAX_POINTS_PER_NODE, generation.rs:37; 0 -> 100000          */
-    uint32_t levels_per_pass;     /* octree levels resolved per partition pass (1..3); 0 -> 3    */
+    uint32_t levels_per_pass;     /* kept for ABI stability: the split phase resolves 2 levels/pass */
     uint32_t reserved;
 } pcv_config;
 
@@ -127,6 +127,12 @@ int pcv_octree_node_data(const pcv_octree* o, uint64_t id_high, uint64_t id_low,
  * position bytes, padding, colour bytes, padding.  ids_hi_lo = num_nodes x (high, low).  out == NULL: size query.
  * An unknown id or a node without points is PCV_ERR_NOT_FOUND (get_node_data -> NodeNotFound: no files). */
 int pcv_nodes_data_blob(const pcv_octree* o, const uint64_t* ids_hi_lo, uint32_t num_nodes, void* out, uint64_t cap, uint64_t* size_out);
+/* LOD draw order (sdl_viewer/src/node_drawer.rs:34-43,185-205: the viewer shuffles every node it loads so that "the first N"
+ * points are a uniform subsample; octree/mod.rs:286-287 asks for that order to be applied when the node is written).
+ * pcv_octree_shuffle_nodes permutes positions, colours, intensity and provenance of every node in place (on the GPU) with the
+ * keyed permutation pcv_lod_order(seed, node id, n) returns on the host: shuffled[i] = original[new_order[i]] (`reshuffle`). */
+int pcv_octree_shuffle_nodes(pcv_octree* o, uint64_t seed);
+int pcv_lod_order(uint64_t seed, uint64_t id_high, uint64_t id_low, uint64_t n, uint64_t* new_order_out);
 /* All nodes at once into caller (ideally pinned) buffers: node n occupies points [point_offset, +num_points) and
  * bytes [xyz_byte_offset, +num_points*3*bpc) of these arrays (offsets from pcv_octree_nodes; no particular order). */
 int pcv_octree_download(const pcv_octree* o, void* xyz_out, uint8_t* rgb_out, float* intensity_out, uint64_t* src_index_out);
@@ -260,6 +266,29 @@ int pcv_octree_nsub_all(const pcv_octree* o, uint64_t* out, uint64_t cap); /* sa
 int pcv_assemble_top(pcv_ctx* ctx, double resolution, const double bbox_min[3], const double bbox_max[3], uint32_t k,
                      const uint64_t* prefix_counts, const uint64_t* unit_nsub /* 8^k */, const void* xyz_codes, const uint8_t* rgb,
                      const float* intensity, uint64_t npoints, pcv_octree** out);
+
+/* ---- the whole sharded build as ONE call per rank.  The three collectives come from the caller (NCCL, MPI,
+ * torch.distributed ...: anything that offers them over host buffers), everything else - ingest, global histogram, cells -> ranks,
+ * the slab set-up over CUDA IPC (cached per context), the fused record exchange over NVLink, the owner's build, the assembly of the
+ * nodes above level k on rank 0 - happens behind this boundary.  Every callback returns 0 on success.  All ranks must call with the
+ * same resolution / bbox / prefix_levels (1 or 2); one process per GPU on one node.
+ *   local_out: this rank's nodes of levels >= k (and the collectors it contributed to); top_out: rank 0 only, levels < k
+ *   k_out: the prefix depth actually used (<= prefix_levels, distributed.py usable_prefix_levels)
+ *   cell_to_rank_out / unit_nsub_out: optional, 8^prefix_levels entries each (the first 8^k are written)
+ *   send_out: optional; when given, the caller owns the handle (pcv_shard_send_dest gives per local point the rank it went to,
+ *   which together with the count matrix reconstructs the provenance of every slab slot) and frees it with pcv_shard_send_free. */
+typedef struct pcv_comm {
+    void* user;
+    int rank, world;
+    int (*allreduce_sum_u64)(void* user, uint64_t* inout, uint64_t count);
+    int (*allgather)(void* user, const void* send, uint64_t bytes, void* recv /* world * bytes, rank order */);
+    int (*barrier)(void* user);
+} pcv_comm;
+int pcv_build_octree_sharded(pcv_ctx* ctx, const pcv_comm* comm, const pcv_points* dev_points, double resolution, const double bbox_min[3],
+                             const double bbox_max[3], uint32_t prefix_levels, pcv_octree** local_out, pcv_octree** top_out, uint32_t* k_out,
+                             int32_t* cell_to_rank_out, uint64_t* unit_nsub_out, pcv_shard_send** send_out);
+/* Releases the receive slab pcv_build_octree_sharded caches on the context (collective: every rank calls it). */
+int pcv_sharded_release(pcv_ctx* ctx, const pcv_comm* comm);
 
 /* ---- PLY input: src/read_write/ply.rs:126-229 (parse_header), :327-450
  * (PlyIterator::from_file), :453-556 (batches), src/octree/generation.rs:256-287 (find_bounding_box,

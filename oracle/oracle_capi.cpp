@@ -370,6 +370,19 @@ double orc_query_batch_timed(void* hp, const orc_location* locs, uint32_t nloc, 
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// reshuffle (sdl_viewer/src/node_drawer.rs:34-43): new_data = concat(old_data[i * bpv .. (i + 1) * bpv] for i in new_order).
+int orc_reshuffle(const uint64_t* new_order, uint64_t n, const uint8_t* old_data, uint64_t old_len, uint64_t bytes_per_vertex, uint8_t* new_data) {
+    if (n * bytes_per_vertex != old_len) return -1;  // assert_eq!(new_order.len() * bytes_per_vertex, old_data.len())
+    uint64_t o = 0;
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t i = new_order[k] * bytes_per_vertex;
+        if (i + bytes_per_vertex > old_len) return -2;
+        std::memcpy(new_data + o, old_data + i, bytes_per_vertex);
+        o += bytes_per_vertex;
+    }
+    return o == old_len ? 0 : -3;
+}
+
 int orc_xray_tile(void* hp, const double* bbox_min, const double* bbox_max, uint32_t w, uint32_t hgt, const double* query_from_global7,
                   uint8_t* rgba_out, uint32_t* zbits_out, uint8_t* zover_out) {
     Handle* h = (Handle*)hp;

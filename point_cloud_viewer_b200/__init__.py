@@ -229,6 +229,21 @@ class Context:
     def shard_send_free(self, send):
         N.lib().pcv_shard_send_free(send)
 
+    def build_octree_sharded(self, comm_struct, x_ptr, y_ptr, z_ptr, stride, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, prefix_levels=2, keep_send=True):
+        """pcv_build_octree_sharded: the whole multi-GPU build in one C call per rank; `comm_struct` is a _native.Comm.
+        Returns (local Octree, top Octree or None, k, cell_to_rank, unit_nsub, send handle or None)."""
+        pts = N.Points(x_ptr, y_ptr, z_ptr, stride, rgb_ptr, intensity_ptr, int(n))
+        local, top, send, k = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        c2r = np.zeros(8 ** prefix_levels, np.int32)
+        un = np.zeros(8 ** prefix_levels, np.uint64)
+        N.check(N.lib().pcv_build_octree_sharded(self.h, C.addressof(comm_struct), C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), prefix_levels,
+                                                 C.byref(local), C.byref(top), C.byref(k), _p(c2r), _p(un), C.byref(send) if keep_send else None))
+        kk = int(k.value)
+        return (Octree(self, local), Octree(self, top) if top.value else None, kk, c2r[: 8 ** kk].copy(), un[: 8 ** kk].copy(), send if keep_send else None)
+
+    def sharded_release(self, comm_struct):
+        N.check(N.lib().pcv_sharded_release(self.h, C.addressof(comm_struct)))
+
     def build_octree_from_records(self, rec_ptr, col_ptr, dig_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, k, prefix_counts):
         """The owner's part of a sharded build over the records its peers stored into its slab."""
         pc = np.ascontiguousarray(prefix_counts, np.uint64)
@@ -295,6 +310,14 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+def lod_order(seed, name, n):
+    """new_order of node `name` with n points: shuffled[i] = original[new_order[i]] (reshuffle, node_drawer.rs:34-43)."""
+    hi, lo = node_id_from_name(name)
+    out = np.zeros(max(int(n), 1), np.uint64)
+    N.check(N.lib().pcv_lod_order(int(seed), hi, lo, int(n), _p(out)))
+    return out[: int(n)]
 
 
 def synth_points_host(kind, seed, first, n):
@@ -402,6 +425,10 @@ class Octree:
             out = np.zeros(max(size.value, 1), np.uint8)
         N.check(N.lib().pcv_nodes_data_blob(self.h, _p(ids), len(names), _p(out), out.nbytes if hasattr(out, "nbytes") else len(out), C.byref(size)))
         return out[: size.value]
+
+    def shuffle_nodes(self, seed):
+        """Apply the viewers' random draw order to every node, once, on the GPU (node_drawer.rs:185-205; mod.rs:286-287)."""
+        N.check(N.lib().pcv_octree_shuffle_nodes(self.h, int(seed)))
 
     def node_nsub(self, name):
         m = self.nodes[name]

@@ -113,6 +113,15 @@ class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("ms", C.c_double)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Comm(C.Structure):  # pcv_comm
+    _fields_ = [("user", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("allreduce_sum_u64", ALLREDUCE_FN), ("allgather", ALLGATHER_FN), ("barrier", BARRIER_FN)]
+
+
 class PlyInfo(C.Structure):
     """pcv_ply_info (include/pcv.h)."""
 
@@ -138,6 +147,8 @@ SYMBOLS = [
     ("pcv_octree_nodes", C.c_int, [C.c_void_p, C.POINTER(NodeMeta), C.c_uint64]),
     ("pcv_octree_node_data", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_nodes_data_blob", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, _u64p]),
+    ("pcv_octree_shuffle_nodes", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("pcv_lod_order", C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     ("pcv_octree_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_octree_device_arrays", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("pcv_octree_write_dir", C.c_int, [C.c_void_p, C.c_char_p]),
@@ -167,6 +178,9 @@ SYMBOLS = [
     ("pcv_shard_send_free", None, [C.c_void_p]),
     ("pcv_build_octree_from_records_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p,
                                                        C.POINTER(C.c_void_p)]),
+    ("pcv_build_octree_sharded", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("pcv_sharded_release", C.c_int, [C.c_void_p, C.c_void_p]),
     ("pcv_build_octree_sharded_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_octree_node_nsub", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),
     ("pcv_octree_nsub_all", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),

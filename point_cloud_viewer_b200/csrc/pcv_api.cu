@@ -47,6 +47,8 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) throw BuildError(PCV_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #x); \
     } while (0)
 
+static void sharded_forget(pcv_ctx* c);  // sharded_build.inl: drops the slab a context still caches (no collective)
+
 extern "C" {
 
 const char* pcv_last_error(void) { return g_err.c_str(); }
@@ -95,6 +97,7 @@ void pcv_destroy(pcv_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    sharded_forget(c);
     c->be->dfree(c->shard_cells);
     cudaStreamSynchronize(c->stream);
     delete c->be;
@@ -645,3 +648,4 @@ int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* res
 #include "query_api.inl"
 #include "ply_api.inl"
 #include "shard_api.inl"
+#include "sharded_build.inl"

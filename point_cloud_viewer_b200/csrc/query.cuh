@@ -13,6 +13,7 @@
 
 #include "chain.h"
 #include "geometry_host.hpp"
+#include "lod_order.h"
 
 namespace pcv {
 
@@ -360,6 +361,55 @@ __global__ void k_tile_totals(const QTile* tiles, const uint32_t* keep_counts, u
     atomicAdd(&tested[tiles[i].loc], (unsigned long long)tiles[i].count);
 }
 
+// ---- LOD draw order applied at build time (lod_order.h): gather every node's points into their shuffled order ------------------
+struct LodArgs {
+    const QNode* nodes;
+    const QTile* tiles;  // (node, first, count) pieces of every node; loc unused
+    const uint64_t* keys;  // [nnodes] permutation key of every node
+    const uint8_t* xyz;
+    const uint8_t* rgb;
+    const float* intensity;
+    const uint32_t* src;
+    uint8_t* out_xyz;
+    uint8_t* out_rgb;
+    float* out_intensity;
+    uint32_t* out_src;
+};
+__global__ void __launch_bounds__(256) k_lod_shuffle(const __grid_constant__ LodArgs a, uint32_t ntiles) {
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const QTile t = a.tiles[ti];
+        const QNode nd = a.nodes[t.node];
+        const uint64_t key = a.keys[t.node];
+        const int bpc = enc_bytes(nd.enc);
+        for (uint32_t k = threadIdx.x; k < t.count; k += blockDim.x) {
+            const uint32_t i = t.first + k, j = lod_order(key, nd.n, i);  // new[i] = old[j]
+            const uint8_t* sx = a.xyz + nd.xyz_off + (uint64_t)j * 3 * bpc;
+            uint8_t* dx = a.out_xyz + nd.xyz_off + (uint64_t)i * 3 * bpc;
+            if (bpc == 1) {
+                dx[0] = sx[0], dx[1] = sx[1], dx[2] = sx[2];
+            } else if (bpc == 2) {
+                const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sx);
+                uint16_t* d16 = reinterpret_cast<uint16_t*>(dx);
+                d16[0] = s16[0], d16[1] = s16[1], d16[2] = s16[2];
+            } else if (bpc == 4) {
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sx);
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(dx);
+                d32[0] = s32[0], d32[1] = s32[1], d32[2] = s32[2];
+            } else {
+                const uint64_t* s64 = reinterpret_cast<const uint64_t*>(sx);
+                uint64_t* d64 = reinterpret_cast<uint64_t*>(dx);
+                d64[0] = s64[0], d64[1] = s64[1], d64[2] = s64[2];
+            }
+            const uint64_t sp = nd.point_off + j, dp = nd.point_off + i;
+            a.out_rgb[3 * dp] = a.rgb[3 * sp];
+            a.out_rgb[3 * dp + 1] = a.rgb[3 * sp + 1];
+            a.out_rgb[3 * dp + 2] = a.rgb[3 * sp + 2];
+            a.out_src[dp] = a.src[sp];
+            if (a.out_intensity) a.out_intensity[dp] = a.intensity[sp];
+        }
+    }
+}
+
 // ---- batched query: hierarchical node selection + single-pass culling ---------------------------------------------
 // nodes_in_location for many locations at once, level by level like NodeIdsIterator (octree_iterator.rs:30-43): a frontier of
 // (location, node) pairs; every pair is tested once (sat.rs:174-194), a pair that is not Out joins the work list (if the node
@@ -439,10 +489,10 @@ __global__ void __launch_bounds__(256) k_pairs_to_tiles(const uint2* __restrict_
 }
 
 // FilteredIterator (iterator.rs:96-119) over one tile, in ONE pass: the tile's position bytes are staged in shared memory with
-// 16-byte loads (node blocks and 2048-point tiles are 16-byte aligned), every point is decoded and tested once, the block
-// reserves the output range of its survivors with one atomic and then writes them compacted (the order inside the tile is
-// kept; tiles land in the order they finish - the batched form only promises per-location totals and the compacted set).
-// Survivors beyond `cap` are counted but not stored.
+// 16-byte loads (node blocks and 2048-point tiles are 16-byte aligned), every point is decoded and tested once; per round of
+// 256 points the block counts its survivors with ballots, reserves their output range with one atomic, stages them in shared
+// memory and copies them out as contiguous words (the order inside a round is kept; rounds land in the order they finish -
+// the batched form only promises per-location totals and the compacted set).  Survivors beyond `cap` are counted, not stored.
 struct CullFusedArgs {
     CullArgs c;
     unsigned long long* cursor;  // output slots handed out so far
@@ -467,7 +517,12 @@ __device__ __forceinline__ void decode_staged(const uint8_t* s, uint32_t i, cons
 }
 __global__ void __launch_bounds__(256) k_cull_fused(const __grid_constant__ CullFusedArgs f, uint32_t ntiles) {
     __shared__ __align__(16) uint8_t sxyz[kCullStage];
-    __shared__ uint32_t wcnt[kQueryTile / 256][8];
+    // survivors of one round of 256 points, staged so that the copy-out is contiguous 8 / 4 / 1-byte-per-lane stores
+    __shared__ __align__(16) double st_xyz[256 * 3];
+    __shared__ uint32_t st_src[256];
+    __shared__ float st_int[256];
+    __shared__ uint8_t st_rgb[256 * 3];
+    __shared__ uint32_t wcnt[8];
     __shared__ unsigned long long sbase;
     const CullArgs& a = f.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -483,13 +538,12 @@ __global__ void __launch_bounds__(256) k_cull_fused(const __grid_constant__ Cull
             for (uint32_t v = threadIdx.x; v < nvec; v += 256) reinterpret_cast<uint4*>(sxyz)[v] = __ldcg(reinterpret_cast<const uint4*>(src) + v);
         }
         __syncthreads();
-        uint32_t keepbits = 0;
-#pragma unroll
-        for (uint32_t r = 0; r < kQueryTile / 256; ++r) {
-            const uint32_t i = r * 256 + threadIdx.x;
+        uint32_t kept_tile = 0;  // thread 0 only
+        for (uint32_t r0 = 0; r0 < t.count; r0 += 256) {
+            const uint32_t i = r0 + threadIdx.x;
             bool keep = false;
+            double p[3] = {0, 0, 0};
             if (i < t.count) {
-                double p[3];
                 if (staged) {
                     decode_staged(sxyz, i, nd, p);
                 } else {
@@ -503,49 +557,48 @@ __global__ void __launch_bounds__(256) k_cull_fused(const __grid_constant__ Cull
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) wcnt[r][warp] = __popc(bal);
-            if (keep) keepbits |= 1u << r;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {  // exclusive prefix over (round, warp); one atomic reserves the tile's output range
-            uint32_t run = 0;
-            for (uint32_t r = 0; r < kQueryTile / 256; ++r)
-                for (int w = 0; w < 8; ++w) {
-                    const uint32_t c = wcnt[r][w];
-                    wcnt[r][w] = run;
-                    run += c;
-                }
-            sbase = run ? atomicAdd(f.cursor, (unsigned long long)run) : 0ull;
-            if (run) atomicAdd(&f.kept[t.loc], (unsigned long long)run);
-        }
-        __syncthreads();
-        const unsigned long long base = sbase;
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t before = 0, total = 0;
 #pragma unroll
-        for (uint32_t r = 0; r < kQueryTile / 256; ++r) {
-            const bool keep = (keepbits >> r) & 1u;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (!keep) continue;
-            const unsigned long long dst = base + wcnt[r][warp] + __popc(bal & ((1u << lane) - 1u));
-            if (dst >= f.cap) continue;
-            const uint32_t i = r * 256 + threadIdx.x;
-            double p[3];
-            if (staged) {
-                decode_staged(sxyz, i, nd, p);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) p[k] = decode1_fast(load_code(src + ((size_t)i * 3 + k) * bpc, nd.enc), nd.m[k], nd.e, nd.enc);
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = wcnt[w];
+                if (w < warp) before += c;
+                total += c;
             }
-            const uint64_t sp = nd.point_off + t.first + i;
-            a.out_xyz[3 * dst] = p[0];
-            a.out_xyz[3 * dst + 1] = p[1];
-            a.out_xyz[3 * dst + 2] = p[2];
-            a.out_rgb[3 * dst] = a.rgb[3 * sp];
-            a.out_rgb[3 * dst + 1] = a.rgb[3 * sp + 1];
-            a.out_rgb[3 * dst + 2] = a.rgb[3 * sp + 2];
-            if (a.out_intensity) a.out_intensity[dst] = a.intensity[sp];
-            a.out_src[dst] = a.src[sp];
+            if (total == 0) {  // uniform: nothing survived this round
+                __syncthreads();
+                continue;
+            }
+            if (threadIdx.x == 0) {
+                sbase = atomicAdd(f.cursor, (unsigned long long)total);  // one reservation per round: the round's survivors stay contiguous
+                kept_tile += total;
+            }
+            if (keep) {
+                const uint32_t li = before + __popc(bal & ((1u << lane) - 1u));
+                const uint64_t sp = nd.point_off + t.first + i;
+                st_xyz[3 * li] = p[0];
+                st_xyz[3 * li + 1] = p[1];
+                st_xyz[3 * li + 2] = p[2];
+                st_rgb[3 * li] = a.rgb[3 * sp];
+                st_rgb[3 * li + 1] = a.rgb[3 * sp + 1];
+                st_rgb[3 * li + 2] = a.rgb[3 * sp + 2];
+                st_src[li] = a.src[sp];
+                if (a.out_intensity) st_int[li] = a.intensity[sp];
+            }
+            __syncthreads();
+            const unsigned long long base = sbase;
+            const uint32_t room = base >= f.cap ? 0u : (uint32_t)min((unsigned long long)total, f.cap - base);
+            for (uint32_t k = threadIdx.x; k < 3 * room; k += 256) a.out_xyz[3 * base + k] = st_xyz[k];
+            for (uint32_t k = threadIdx.x; k < 3 * room; k += 256) a.out_rgb[3 * base + k] = st_rgb[k];
+            for (uint32_t k = threadIdx.x; k < room; k += 256) {
+                a.out_src[base + k] = st_src[k];
+                if (a.out_intensity) a.out_intensity[base + k] = st_int[k];
+            }
+            __syncthreads();  // the staging arrays and wcnt are reused by the next round
         }
-        __syncthreads();  // sxyz and wcnt are reused by the next tile
+        if (threadIdx.x == 0 && kept_tile) atomicAdd(&f.kept[t.loc], (unsigned long long)kept_tile);
+        __syncthreads();  // sxyz is reused by the next tile
     }
 }
 

@@ -546,6 +546,57 @@ int pcv_query_batch_device(const pcv_octree* oc, const pcv_location* locs, uint3
     API_CATCH
 }
 
+int pcv_lod_order(uint64_t seed, uint64_t id_high, uint64_t id_low, uint64_t n, uint64_t* new_order_out) {
+    if (n && !new_order_out) return fail(PCV_ERR_INVALID, "null argument");
+    if (n >= 0xFFFFFFFFull) return fail(PCV_ERR_UNSUPPORTED, "node too large");
+    const uint64_t key = lod_node_key(seed, id_high, id_low);
+    for (uint64_t i = 0; i < n; ++i) new_order_out[i] = lod_order(key, (uint32_t)n, (uint32_t)i);
+    return PCV_OK;
+}
+
+int pcv_octree_shuffle_nodes(pcv_octree* o, uint64_t seed) {
+    if (!o) return fail(PCV_ERR_INVALID, "null octree");
+    API_TRY
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ensure_tables(o);
+    if (o->n == 0) return PCV_OK;
+    Scratch s(c);
+    std::vector<QTile> tiles;
+    std::vector<uint64_t> keys(o->nodes.size());
+    for (size_t i = 0; i < o->nodes.size(); ++i) {
+        keys[i] = lod_node_key(seed, o->nodes[i].id_high, o->nodes[i].id_low);
+        if (o->nodes[i].num_points > 0) make_tiles(o, 0, (uint32_t)i, tiles);
+    }
+    LodArgs a{};
+    a.nodes = (const QNode*)o->d_qnodes;
+    a.tiles = s.upload(tiles.data(), tiles.size());
+    a.keys = s.upload(keys.data(), keys.size());
+    a.xyz = o->d_xyz;
+    a.rgb = o->d_rgb;
+    a.intensity = o->d_intensity;
+    a.src = o->d_src;
+    a.out_xyz = (uint8_t*)c->be->dmalloc(o->xyz_bytes + 32);
+    a.out_rgb = (uint8_t*)c->be->dmalloc(o->n * 3);
+    a.out_src = (uint32_t*)c->be->dmalloc(o->n * 4 + 64);
+    a.out_intensity = o->d_intensity ? (float*)c->be->dmalloc(o->n * 4) : nullptr;
+    k_lod_shuffle<<<(uint32_t)std::min<size_t>(tiles.size(), (size_t)c->sm_count * 16), 256, 0, c->stream>>>(a, (uint32_t)tiles.size());
+    c->be->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->be->dfree(o->d_xyz);
+    c->be->dfree(o->d_rgb);
+    c->be->dfree(o->d_src);
+    c->be->dfree(o->d_intensity);
+    o->d_xyz = a.out_xyz;
+    o->d_rgb = a.out_rgb;
+    o->d_src = a.out_src;
+    o->d_intensity = a.out_intensity;
+    return PCV_OK;
+    API_CATCH
+}
+
 int pcv_last_query_stats(pcv_ctx* c, pcv_query_stats* out) {
     if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
     *out = c->qstats;

@@ -718,6 +718,90 @@ def _finish_sharded(ops, comm, local, r_idx, k, c2r, nranks, rank, prefix_counts
     return out
 
 
+def make_c_comm(comm):
+    """pcv_comm over a TorchComm (or any object with all_reduce_sum_u64 / all_gather_bytes / barrier): the three collectives
+    pcv_build_octree_sharded needs, as C callbacks over host buffers.  Keep the returned struct alive for the call."""
+    import ctypes as C
+
+    from . import _native as N
+
+    def allreduce(_user, ptr, count):
+        try:
+            a = np.ctypeslib.as_array(ptr, shape=(int(count),))
+            a[:] = comm.all_reduce_sum_u64(a.copy())
+            return 0
+        except Exception:  # noqa: BLE001 - an exception must not unwind through the C frame
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    def allgather(_user, send, nbytes, recv):
+        try:
+            nbytes = int(nbytes)
+            src = np.frombuffer((C.c_uint8 * nbytes).from_address(send), np.uint8)
+            out = comm.all_gather_bytes(src, nbytes)
+            C.memmove(recv, out.ctypes.data, comm.world * nbytes)
+            return 0
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    def barrier(_user):
+        try:
+            comm.barrier()
+            return 0
+        except Exception:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            return 1
+
+    cs = N.Comm(None, comm.rank, comm.world, N.ALLREDUCE_FN(allreduce), N.ALLGATHER_FN(allgather), N.BARRIER_FN(barrier))
+    return cs
+
+
+def build_octree_sharded_native(ctx, x, y, z, rgb, intensity, index_base, resolution, bbox_min, bbox_max, prefix_levels=2, comm=None):
+    """Same result as build_octree_sharded, but the whole orchestration runs inside the C library (pcv_build_octree_sharded):
+    Python only lends it torch.distributed's collectives.  This is the call a non-Python host makes with its own NCCL / MPI."""
+    comm = comm or TorchComm(x.device)
+    cs = make_c_comm(comm)
+    n = int(x.numel())
+    local, top, k, c2r, unit_nsub, send = ctx.build_octree_sharded(cs, x.data_ptr(), y.data_ptr(), z.data_ptr(), 1, rgb.data_ptr(),
+                                                                   intensity.data_ptr() if intensity is not None else None, n, resolution, bbox_min, bbox_max,
+                                                                   prefix_levels)
+    stats = ctx.last_build_stats()
+    # provenance, all on demand: count matrix from the per-point destinations, slots of the top pieces from the local tree
+    import torch
+
+    ptr, nd = ctx.shard_send_dest(send)
+    dest = torch.as_tensor(_RawCuda(ptr, (max(nd, 1),), "|u1"), device=x.device)[:nd] if nd else torch.zeros(0, dtype=torch.uint8, device=x.device)
+    sc = torch.bincount(dest.to(torch.int64), minlength=comm.world).cpu().numpy().astype(np.int64)
+    M = np.asarray(comm.all_gather_counts(sc)).reshape(comm.world, comm.world)
+    r_idx = LazyIndex(ctx, send, index_base, n, M, comm)
+    lazy_slots = {}
+    meta = local.meta
+    idx_mask = (1 << 60) - 1
+    for i in np.nonzero((meta["level"] == k - 1) & (meta["num_points"] > 0))[0]:
+        pidx = int(meta["id_low"][i] & idx_mask) if k > 1 else 0
+        cs_ = np.asarray(local.node_data_at(int(i))[3], np.uint64)
+        off = 0
+        for c in range(8):
+            cell = pidx * 8 + c
+            if c2r[cell] != comm.rank or unit_nsub[cell] == 0:
+                continue
+            cnt = (int(unit_nsub[cell]) + 7) // 8
+            lazy_slots[(pidx, c)] = cs_[off:off + cnt].copy()
+            off += cnt
+    out = ShardedOctree(local, top, k, r_idx, {"mine": lazy_slots}, c2r, comm.rank, stats)
+    out.send_handle = (ctx, send)
+    out.recv_points = r_idx.numel()
+    out.c_comm = cs  # keeps the callbacks alive as long as the tree (pcv_sharded_release takes the same struct)
+    return out
+
+
 def build_octree_sharded(ctx, x, y, z, rgb, intensity, index_base, resolution, bbox_min, bbox_max, prefix_levels=2, max_points_per_node=100000,
                          consume_input=False):
     """GPU entry point used by bench.py: torch cuda tensors in, ShardedOctree out (torch.distributed must be initialised).

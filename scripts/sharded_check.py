@@ -23,10 +23,13 @@ rgb = torch.empty(n * 3, dtype=torch.uint8, device=dev)
 ctx.synth_points_device(kind, 3, rank * n, n, x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr())
 single = None
 # fused pack+exchange over peer memory (twice: the second step reuses the IPC slab), then the staged NCCL all-to-all path
-for mode in ("fused", "fused", "staged"):
+for mode in ("fused", "fused", "native", "native", "staged"):
   if mode == "staged":
       os.environ["PCV_NO_FUSED_EXCHANGE"] = "1"
-  tree = D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=k, max_points_per_node=maxpts)
+  if mode == "native":  # the whole orchestration inside the C library (pcv_build_octree_sharded), Python lends the collectives
+      tree = D.build_octree_sharded_native(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=k)
+  else:
+      tree = D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=k, max_points_per_node=maxpts)
   merged = tree.gather_all(D.TorchComm(dev))
   tree.free()
   if rank == 0:

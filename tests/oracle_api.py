@@ -93,6 +93,7 @@ def lib():
         L.orc_visible_nodes.argtypes = [C.c_void_p, dp, C.c_void_p, C.c_int64]
         L.orc_query.restype = C.c_int64
         L.orc_query.argtypes = [C.c_void_p, LP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_reshuffle.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_query_batch_timed.restype = C.c_double
         L.orc_query_batch_timed.argtypes = [C.c_void_p, LP, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p]
         L.orc_xray_tile_attr.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
@@ -276,6 +277,16 @@ def synth_bbox(kind):
     mn, mx, res = (C.c_double * 3)(), (C.c_double * 3)(), C.c_double()
     lib().orc_synth_bbox(kind, mn, mx, C.byref(res))
     return np.array(mn), np.array(mx), res.value
+
+
+def reshuffle(new_order, old_data, bytes_per_vertex):
+    """sdl_viewer's reshuffle (node_drawer.rs:34-43)."""
+    order = np.ascontiguousarray(new_order, np.uint64)
+    old = np.ascontiguousarray(old_data).view(np.uint8).reshape(-1)
+    out = np.zeros(len(old), np.uint8)
+    rc = lib().orc_reshuffle(_ptr(order), len(order), _ptr(old), len(old), int(bytes_per_vertex), _ptr(out))
+    assert rc == 0, rc
+    return out
 
 
 def load_dir(d):
