@@ -82,7 +82,17 @@ struct BucketDesc {
     uint16_t b0, b1;  // digit range [b0,b1) it collects (contiguous: a whole sub-tree); b1 == 0: unused entry
     uint8_t keep;     // 1..G: which level's codes the destination stores
     uint8_t kind;     // 0 = next pass segment, 1 = leaf arena
-    uint16_t pad;
+    uint16_t owner;   // fused exchange pass only: 1 + rank whose buffers the bucket lives in (0: this context's)
+};
+// Fused exchange pass (sharded build): the first partition pass of a SENDER writes every bucket straight into its owner's
+// buffers - as mapped in the sender's address space (own memory or CUDA-IPC peer memory).
+struct RemoteBufs {
+    void* rec_next;
+    uint32_t* col_next;   // wide records only (narrow ones carry the colour in the record)
+    uint8_t* dig_next;
+    void* arena;
+    uint32_t* col_arena;
+    float* intensity;     // indexed by slot, or null
 };
 // Node table entry, appended on the device by the planner (parents before children).
 struct DevNode {
@@ -171,6 +181,10 @@ struct PassArgs {
     int Gn;                     // levels the following pass resolves (0: there is none - every destination is a leaf)
     bool wide;
     bool rec_has_col;  // first pass over exchanged (narrow) records: a record's 4th word is the packed colour, its idx is its position
+    bool holes;        // planner: leaf buckets advance the next-pass offset as well, so that a record's position in the next pass's
+                       // input is its slot in cell-major order over ALL buckets (fused exchange pass: idx == position is implied)
+    const RemoteBufs* remote;  // fused exchange pass (device array indexed by BucketDesc::owner - 1), else null
+    const float* int_in;       // fused exchange pass: the sender's intensities by input position, or null
     // per-pass level constants as plain scalars (a dynamically indexed read of `lv` in a kernel is an indexed constant load
     // per use): levels L+1, L+2 and, for records that continue, the node level Lb = L+G and its child level
     double e1, e2, ry2, eb, eh, ryh;
@@ -304,6 +318,7 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
             bd.dest = run.arena_pts;
             if (EMIT && node_index < a.cap_nodes) a.nodes[node_index].arena_off = run.arena_pts;
             run.arena_pts += cnt;
+            if (a.holes) run.next_pts += cnt;
             if ((uint32_t)level > deepest) deepest = (uint32_t)level;
         }
         if (EMIT) bk[nlocal] = bd;
@@ -375,6 +390,7 @@ struct Backend {
     virtual void ingest(const IngestArgs& a) = 0;   // raw points -> level-1 records + first digits
     virtual void pass(const PassArgs& a) = 0;       // digit histogram + scan + plan + partition of one pass (asynchronous)
     virtual void hist_scan(const PassArgs& a) {}    // only the digit histogram + scan of a pass (sharded build: the sender's side)
+    virtual void plan(const PassArgs& a) {}         // only the planner of a pass (sharded build: the owner's side of the fused exchange pass)
     virtual void place(const PlaceArgs& a) = 0;
     virtual void mark(int what) {}  // timing hooks: 0 partition start, 1 partition end / place start, 2 place end
     virtual void pass_points(int pass, uint64_t npoints, uint64_t leaf_points) {}  // profiling: live point counts, known after the read-back
@@ -488,6 +504,14 @@ struct ExternalRecords {
     uint64_t n = 0;
     bool present = false;
     bool col_in_record = false;  // narrow records as they cross the link: {code x 3, packed colour}; idx == position is implied
+    // Fused exchange pass: the senders already ran the first partition pass into this context's buffers.  `rec` / `col` / `dig`
+    // then are the NEXT pass's input (n slots in cell-major order, holes where a level-2 cell is a leaf), `arena` / `col_arena`
+    // (capacity n records) hold the leaf cells' records at the offsets the planner assigns, and `first_bins` (host, 64 entries)
+    // is what the first pass's digit histogram would have been: the points this context owns per level-2 cell.
+    bool after_first_pass = false;
+    void* arena = nullptr;
+    uint32_t* col_arena = nullptr;
+    const uint64_t* first_bins = nullptr;
 };
 
 class BuildPlan {
@@ -551,6 +575,9 @@ class BuildPlan {
         const uint32_t cap_active = (uint32_t)cap_active64, cap_tiles = (uint32_t)cap_tiles64, cap_chunks = (uint32_t)cap_chunks64,
                        cap_nodes = (uint32_t)cap_nodes64;
 
+        const bool fused = ext.present && ext.after_first_pass;
+        if (fused && (shard.k != 2 || sched[0].G != 2 || !ext.arena || !ext.col_arena || !ext.first_bins))
+            throw BuildError(-1, "a fused exchange pass needs a level-2 sharding, a two-level first pass and the owner's arena");
         std::vector<void*> owned;
         auto dalloc = [&](size_t bytes) {
             void* p = be.dmalloc(bytes);
@@ -563,12 +590,23 @@ class BuildPlan {
         BuildState hs{};
         try {
             // ping-pong buffers; with external records the first of each pair is the caller's (read only, never freed here)
-            void* bufs[2] = {ext.present ? const_cast<void*>(ext.rec) : dalloc((size_t)N * rec_bytes + 64), dalloc((size_t)N * rec_bytes + 64)};
-            uint32_t* cols[2] = {(ext.present && ext.col) ? const_cast<uint32_t*>(ext.col) : (uint32_t*)dalloc((size_t)N * 4 + 64),
-                                 (uint32_t*)dalloc((size_t)N * 4 + 64)};  // + slack: bulk copies read whole 16-byte granules
-            uint8_t* digs[2] = {ext.present ? const_cast<uint8_t*>(ext.dig) : (uint8_t*)dalloc((size_t)N + 64), (uint8_t*)dalloc((size_t)N + 64)};
-            arena = dalloc((size_t)N * rec_bytes);
-            col_arena = (uint32_t*)dalloc((size_t)N * 4 + 64);
+            // (after a fused exchange pass the caller's buffers are the SECOND of each pair: the first pass has been run into them)
+            const int xb = ext.present ? (ext.after_first_pass ? 1 : 0) : -1;
+            void* bufs[2];
+            uint32_t* cols[2];
+            uint8_t* digs[2];
+            for (int b = 0; b < 2; ++b) {
+                bufs[b] = b == xb ? const_cast<void*>(ext.rec) : dalloc((size_t)N * rec_bytes + 64);
+                cols[b] = (b == xb && ext.col) ? const_cast<uint32_t*>(ext.col) : (uint32_t*)dalloc((size_t)N * 4 + 64);  // + slack: bulk copies read whole 16-byte granules
+                digs[b] = b == xb ? const_cast<uint8_t*>(ext.dig) : (uint8_t*)dalloc((size_t)N + 64);
+            }
+            if (fused) {
+                arena = ext.arena;
+                col_arena = ext.col_arena;
+            } else {
+                arena = dalloc((size_t)N * rec_bytes);
+                col_arena = (uint32_t*)dalloc((size_t)N * 4 + 64);
+            }
             BuildState* d_st = (BuildState*)dalloc(sizeof(BuildState));
             ActiveDesc* act[2] = {(ActiveDesc*)dalloc((size_t)cap_active * sizeof(ActiveDesc)), (ActiveDesc*)dalloc((size_t)cap_active * sizeof(ActiveDesc))};
             ChunkDesc* chk[2] = {(ChunkDesc*)dalloc((size_t)cap_chunks * sizeof(ChunkDesc)), (ChunkDesc*)dalloc((size_t)cap_chunks * sizeof(ChunkDesc))};
@@ -639,7 +677,8 @@ class BuildPlan {
                 pa.nbins = 1 << (3 * pa.G);
                 pa.Gn = p + 1 < sched.size() ? sched[p + 1].G : 0;
                 pa.wide = wide;
-                pa.rec_has_col = ext.present && ext.col_in_record && p == 0;
+                pa.rec_has_col = ext.present && ext.col_in_record && p == (fused ? 1u : 0u);
+                pa.holes = fused && p == 0;
                 pa.rec_in = bufs[p & 1];
                 pa.rec_next = bufs[(p + 1) & 1];
                 pa.arena = arena;
@@ -676,7 +715,12 @@ class BuildPlan {
                     pa.enc1 = lv.enc[L1], pa.enc2 = lv.enc[L2], pa.ench = lv.enc[Lh];
                     pa.fast = lv.fast;
                 }
-                be.pass(pa);
+                if (fused && p == 0) {  // the senders ran this pass's partition: only its plan is made here, from the known cell counts
+                    be.h2d(node_bins, ext.first_bins, 64 * sizeof(uint64_t));
+                    be.plan(pa);
+                } else {
+                    be.pass(pa);
+                }
                 ++launched;
                 if (poll) {
                     const auto tw0 = std::chrono::steady_clock::now();
@@ -731,7 +775,7 @@ class BuildPlan {
             R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
             // the ping-pong buffers and the planner's tables are dead now; the arena lives until the placement is done
             for (auto& p : owned) {
-                if (p && p != arena && p != (void*)col_arena) {
+                if (p && p != arena && p != (void*)col_arena) {  // (a fused build's arena is the caller's and not in `owned`)
                     be.dfree(p);
                     p = nullptr;
                 }
@@ -787,8 +831,7 @@ class BuildPlan {
             algo_xyz += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
         }
         if (poff != pts.n) {
-            be.dfree(arena);
-            be.dfree(col_arena);
+            if (!fused) be.dfree(arena), be.dfree(col_arena);
             throw BuildError(-2, "internal: subsample plan does not conserve points");
         }
         R.xyz_bytes = boff;
@@ -854,8 +897,7 @@ class BuildPlan {
             return nodes[a].index < nodes[b].index;
         });
         free_scratch();
-        be.dfree(arena);
-        be.dfree(col_arena);
+        if (!fused) be.dfree(arena), be.dfree(col_arena);
         R.host_ms_plan += tms(ts0, ts5);
         if (dbg)
             fprintf(stderr, "[pcv timing] passes %u  wait %.2f | plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", R.passes,

@@ -569,6 +569,11 @@ struct PassBucket {  // per bucket of the current tile (shared memory, 32 bytes)
     uint32_t start;                    // sorted position of the bucket's first record
     uint32_t kk;                       // keep | leaf << 8
 };
+struct PassBucketExt {  // fused exchange pass: what a bucket needs beyond PassBucket
+    unsigned long long inten;  // store address of sorted position 0 in the owner's intensity array (indexed by slot)
+    uint32_t slot0;            // slot of sorted position 0 (mod 2^32)
+    uint32_t pad;
+};
 template <bool WIDE>
 struct PassSmem {
     static constexpr size_t rec_bytes = WIDE ? 32 : 16;
@@ -588,7 +593,8 @@ struct PassSmem {
     static constexpr size_t off_desc = off_first + (size_t)kPassBins * 4;  // [2]
     static constexpr size_t off_nact = off_desc + 2 * 64;                  // ActiveDesc of the next tile (cp.async landing zone)
     static constexpr size_t off_bar = off_nact + 64;                       // [3]: small[0], small[1], big
-    static constexpr size_t bytes = off_bar + 32;
+    static constexpr size_t off_bext = off_bar + 32;                       // [nb] fused exchange pass only: slot / intensity bases
+    static constexpr size_t bytes = off_bext + (size_t)kPassBins * sizeof(PassBucketExt);
     static_assert(big_bytes % 16 == 0 && small_bytes % 16 == 0 && sm_pfx % 16 == 0, "bulk copy destinations must be 16-byte aligned");
 };
 static_assert(4 * (PassSmem<false>::bytes + 1024) <= 233472, "four narrow pass blocks must fit one SM (228 KB, 1 KB reserved per block)");
@@ -647,9 +653,9 @@ __device__ __forceinline__ void finish_record(const PassArgs& a, const double pm
     dig_out = d;
 }
 
-template <bool WIDE, int FAST>
+template <bool WIDE, int FAST, bool REMOTE>
 __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTile& pt, const unsigned char* srec, const uint32_t* scol, const uint8_t* sdig,
-                                                const uint32_t* perm, const PassBucket* bdst) {
+                                                const uint32_t* perm, const PassBucket* bdst, const PassBucketExt* bext) {
     constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
     unsigned bad = 0;
     const double pm[3] = {pt.m[0], pt.m[1], pt.m[2]};
@@ -672,6 +678,21 @@ __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTil
         unsigned dig_out = 0;
         if (next || keep == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], keep, next, dig_out, bad);
         if (FAST == 1 && bad) continue;  // the block repeats the sweep with the IEEE operator
+        if (REMOTE) {
+            // The destination is the owner's memory.  A record that continues is stored in the wire format of the exchange
+            // (narrow: {codes, colour}, its index implied by its position = its slot); a leaf record carries its slot explicitly.
+            const PassBucketExt bx = bext[lb];
+            const uint32_t slot = bx.slot0 + p;
+            if (!WIDE && next) {
+                store_rec<WIDE>(reinterpret_cast<void*>(bd.rec + (unsigned long long)p * recsz), 0, c, colour);
+            } else {
+                store_rec<WIDE>(reinterpret_cast<void*>(bd.rec + (unsigned long long)p * recsz), 0, c, slot);
+                *reinterpret_cast<uint32_t*>(bd.col + 4ull * p) = colour;
+            }
+            if (next) *reinterpret_cast<uint8_t*>(bd.dig + p) = (uint8_t)dig_out;
+            if (a.int_in) *reinterpret_cast<float*>(bx.inten + 4ull * p) = a.int_in[idx];
+            continue;
+        }
         store_rec<WIDE>(reinterpret_cast<void*>(bd.rec + (unsigned long long)p * recsz), 0, c, idx);
         *reinterpret_cast<uint32_t*>(bd.col + 4ull * p) = colour;
         if (next) *reinterpret_cast<uint8_t*>(bd.dig + p) = (uint8_t)dig_out;
@@ -714,7 +735,7 @@ __device__ __forceinline__ void pass_make_desc(PassTile* desc, uint32_t tile, co
     desc->valid = 1;
 }
 
-template <bool WIDE>
+template <bool WIDE, bool REMOTE>
 __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_per_sm) k_pass(const __grid_constant__ PassArgs a) {
     constexpr int nbmax = kPassBins;
     constexpr int kThreads = PassCfg<WIDE>::threads, kWarps = PassCfg<WIDE>::warps, kWarpItems = PassCfg<WIDE>::warp_items, kSubRounds = PassCfg<WIDE>::sub_rounds;
@@ -729,6 +750,7 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_
     PassTile* descs = reinterpret_cast<PassTile*>(smem_raw + PassSmem<WIDE>::off_desc);      // [2]
     ActiveDesc* snact = reinterpret_cast<ActiveDesc*>(smem_raw + PassSmem<WIDE>::off_nact);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + PassSmem<WIDE>::off_bar);        // small[0], small[1], big
+    PassBucketExt* bext = reinterpret_cast<PassBucketExt*>(smem_raw + PassSmem<WIDE>::off_bext);
 
     const PassState ps = a.st->pass[a.pass];
     const int nb = a.nbins;
@@ -840,9 +862,24 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_
                     const bool leaf = bd.b1 != 0 && bd.kind;
                     const long long first = (long long)bfirst[lb] - (long long)run;  // slot of sorted position 0
                     PassBucket pb;
+                    if (REMOTE) {
+                        // the bucket lives in its owner's buffers; a leaf bucket's descriptor carries its slot base in the high word
+                        RemoteBufs rb{};
+                        if (bd.b1 != 0) rb = a.remote[bd.owner - 1u];
+                        pb.rec = (unsigned long long)(leaf ? rb.arena : rb.rec_next) + (unsigned long long)(first * (long long)recsz);
+                        pb.col = (unsigned long long)(leaf ? rb.col_arena : rb.col_next) + (unsigned long long)(first * 4);
+                        pb.dig = (unsigned long long)rb.dig_next + (unsigned long long)first;
+                        const long long slot0 = leaf ? first + (long long)(bd.dest >> 32) - (long long)(uint32_t)bd.dest : first;
+                        PassBucketExt bx;
+                        bx.inten = (unsigned long long)rb.intensity + (unsigned long long)(slot0 * 4);
+                        bx.slot0 = (uint32_t)slot0;
+                        bx.pad = 0;
+                        bext[lb] = bx;
+                    } else {
                     pb.rec = (unsigned long long)(leaf ? a.arena : a.rec_next) + (unsigned long long)(first * (long long)recsz);
                     pb.col = (unsigned long long)(leaf ? a.col_arena : a.col_next) + (unsigned long long)(first * 4);
                     pb.dig = (unsigned long long)a.dig_next + (unsigned long long)first;
+                    }
                     pb.start = run;
                     pb.kk = (uint32_t)bd.keep | (leaf ? 0x100u : 0u);
                     bdst[lb] = pb;
@@ -883,14 +920,14 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_
         // operator if any numerator of the block was outside the proven range - the stores are idempotent)
         mbar_wait(&mbar[2], it & 1u);  // records and colours: requested when the previous tile's sweep ended
         if (a.fast == 3) {
-            pass_finish<WIDE, 3>(a, pt, srec, scol, sdig, perm, bdst);  // power-of-two edges: exact scaling, nothing to repeat
+            pass_finish<WIDE, 3, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);  // power-of-two edges: exact scaling, nothing to repeat
         } else if (a.fast == 2) {
-            pass_finish<WIDE, 2>(a, pt, srec, scol, sdig, perm, bdst);  // no per-numerator checks: nothing to repeat
+            pass_finish<WIDE, 2, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);  // no per-numerator checks: nothing to repeat
         } else if (a.fast == 1) {
-            const unsigned bad = pass_finish<WIDE, 1>(a, pt, srec, scol, sdig, perm, bdst);
-            if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
+            const unsigned bad = pass_finish<WIDE, 1, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
+            if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
         } else {
-            pass_finish<WIDE, 0>(a, pt, srec, scol, sdig, perm, bdst);
+            pass_finish<WIDE, 0, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
         }
         __syncthreads();  // records, colours, perm and the tables are reused
         if (stage_next) pass_stage_big<WIDE>(a, descs[s ^ 1u], smem_raw, &mbar[2]);
@@ -1139,8 +1176,10 @@ struct CudaBackend : Backend {
         if (bytes) PCV_CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream));
     }
     static void allow_smem_all() {
-        cudaFuncSetAttribute(k_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
-        cudaFuncSetAttribute(k_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
+        cudaFuncSetAttribute(k_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
+        cudaFuncSetAttribute(k_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
+        cudaFuncSetAttribute(k_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
+        cudaFuncSetAttribute(k_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
     }
     // prefetch distance = blocks resident at once (SMs x blocks per SM); 0 disables (PCV_NO_PREFETCH=1 for experiments)
     int sms = 0;
@@ -1171,24 +1210,48 @@ struct CudaBackend : Backend {
     // One pass, enqueued without any host synchronisation: live sizes come from the device-resident BuildState, grids are
     // fixed (persistent / grid-stride) and blocks beyond the live counts exit.
     void pass(const PassArgs& a) override {
-        const int nsm = sm_count();
-        const int th = a.nbins < 32 ? 32 : a.nbins;
         hist_scan_launch(a);
+        plan_launch(a);
+        partition_launch(a);
+        launches += 9;
+        pass_wide = a.wide;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    void plan_launch(const PassArgs& a) {
+        const int nsm = sm_count();
         prof_begin(K_PLAN, 0, a.pass);
-        {
-            const uint32_t pg = std::min<uint32_t>((a.cap_active + kPlanNodeThreads - 1) / kPlanNodeThreads, (uint32_t)nsm * 8u);
-            k_plan_count<<<pg, kPlanNodeThreads, 0, stream>>>(a);
-            k_plan_scan<<<1, kPlanThreads, 0, stream>>>(a);
-            k_plan_emit<<<pg, kPlanNodeThreads, 0, stream>>>(a);
+        const uint32_t pg = std::min<uint32_t>((a.cap_active + kPlanNodeThreads - 1) / kPlanNodeThreads, (uint32_t)nsm * 8u);
+        k_plan_count<<<pg, kPlanNodeThreads, 0, stream>>>(a);
+        k_plan_scan<<<1, kPlanThreads, 0, stream>>>(a);
+        k_plan_emit<<<pg, kPlanNodeThreads, 0, stream>>>(a);
+        prof_end();
+    }
+    void plan(const PassArgs& a) override {
+        plan_launch(a);
+        launches += 3;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    // the partition kernel of a pass; a.remote != null: the fused exchange pass of a sharded build (buckets in their owners' memory)
+    void partition_launch(const PassArgs& a) {
+        const int nsm = sm_count();
+        prof_begin(K_PASS, 0, a.pass);
+        const uint32_t gw = std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<true>::blocks_per_sm));
+        const uint32_t gn = std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<false>::blocks_per_sm));
+        if (a.remote) {
+            if (a.wide)
+                k_pass<true, true><<<gw, PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
+            else
+                k_pass<false, true><<<gn, PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
+        } else if (a.wide) {
+            k_pass<true, false><<<gw, PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
+        } else {
+            k_pass<false, false><<<gn, PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
         }
         prof_end();
-        prof_begin(K_PASS, 0, a.pass);
-        if (a.wide)
-            k_pass<true><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<true>::blocks_per_sm)), PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
-        else
-            k_pass<false><<<std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<false>::blocks_per_sm)), PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
-        prof_end();
-        launches += 9;
+    }
+    void partition(const PassArgs& a) {
+        partition_launch(a);
+        ++launches;
         pass_wide = a.wide;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
