@@ -271,6 +271,12 @@ def bench_config1(ctx, pcv, torch, O, cores):
     return out
 
 
+def sharded_builder(D):
+    """The multi-GPU build: one C call per rank (pcv_build_octree_sharded; torch.distributed only lends its collectives).
+    PCV_PY_ORCH=1 runs the same steps orchestrated from Python instead (exchange of ingested records, no fused pass)."""
+    return D.build_octree_sharded if os.environ.get("PCV_PY_ORCH") else D.build_octree_sharded_native
+
+
 def multi_gpu_parity_check(ctx, pcv, D, torch, dist, world, rank, dev, n_global, res, bmin, bmax, k):
     """Inside the measured multi-GPU run: the sharded build of this run's N ranks == the single-GPU build == the oracle, bit for bit
     (node set, counts, encodings, cubes, per-slot global source index, colours, position codes), on n_global points of the
@@ -283,7 +289,7 @@ def multi_gpu_parity_check(ctx, pcv, D, torch, dist, world, rank, dev, n_global,
     c = torch.empty(n * 3, dtype=torch.uint8, device=dev)
     ctx.synth_points_device(kind, SEED, rank * n, n, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), c.data_ptr())
     comm = D.TorchComm(dev)
-    tree = D.build_octree_sharded(ctx, xs[0], xs[1], xs[2], c, None, rank * n, res, bmin, bmax, prefix_levels=k)
+    tree = sharded_builder(D)(ctx, xs[0], xs[1], xs[2], c, None, rank * n, res, bmin, bmax, prefix_levels=k)
     merged = tree.gather_all(comm)  # collective; rank 0 receives every final node
     kk = tree.k
     tree.free()
@@ -403,7 +409,7 @@ def run_ours(args):
     if world > 1:
 
         def step():
-            return D.build_octree_sharded(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
+            return sharded_builder(D)(ctx, x, y, z, rgb, None, rank * n, res, bmin, bmax, prefix_levels=args.prefix_levels)
     else:
 
         def step():

@@ -252,6 +252,30 @@ void pcv_shard_send_free(pcv_shard_send* s);
 int pcv_build_octree_from_records_device(pcv_ctx* ctx, void* dev_rec, uint32_t* dev_col, uint8_t* dev_dig, const float* dev_intensity, uint64_t n,
                                          double resolution, const double bbox_min[3], const double bbox_max[3], uint32_t k,
                                          const uint64_t* prefix_counts, pcv_octree** out);
+/* ---- fused exchange pass: the sender's first partition pass (root -> level-2 cells, two levels of the chain finished, the next
+ * pass's first step done) stores every bucket straight into the buffers of the cell's owner - peer memory over NVLink - so the
+ * transfer overlaps the partition tile by tile and the owner's build starts at its SECOND pass.  Narrow records that continue travel
+ * as {codes, colour} + 1 digit byte (17 B per point), their index implied by their position (= slot); records of level-2 leaves go
+ * to the owner's arena with an explicit slot.  Needs prefix depth 2; everything follows from the gathered histograms:
+ *   hist_all[s * 64 + c]  points of sender s in level-2 cell c (all-gather of pcv_shard_ingest_device's counts at k = 2)
+ *   dst[r]                rank r's buffers as mapped in THIS process (capacity >= slots_out[r] entries + 64 bytes of slack each)
+ *   slots_out[r]          slots rank r owns; first_bins_out: this rank's own per-cell counts (input of the owner's build)
+ * Returns PCV_ERR_UNSUPPORTED when the layout does not allow it (the caller then uses pcv_shard_exchange_device). */
+typedef struct pcv_shard_bufs {
+    void* rec_next;   /* slots x 16 B (32 B for wide records) */
+    void* col_next;   /* wide records only: slots x 4 B, else NULL */
+    void* dig_next;   /* slots x 1 B */
+    void* arena;      /* slots x 16 / 32 B: leaf records (the whole build's leaf arena) */
+    void* col_arena;  /* slots x 4 B */
+    void* intensity;  /* slots x 4 B or NULL */
+} pcv_shard_bufs;
+int pcv_shard_pass_device(pcv_shard_send* s, uint32_t nranks, uint32_t rank, const int32_t* cell_to_rank /* 64 */, const uint64_t* hist_all,
+                          const pcv_shard_bufs* dst /* nranks */, uint64_t* slots_out /* nranks or NULL */, uint64_t* first_bins_out /* 64 or NULL */);
+/* after pcv_shard_pass_device: per local point its level-2 cell (device, n bytes; valid until pcv_shard_send_free) */
+int pcv_shard_send_cells(const pcv_shard_send* s, const uint8_t** dev_cells, uint64_t* n);
+/* the owner's build after every sender's pcv_shard_pass_device has completed (one inter-process barrier in between) */
+int pcv_build_octree_after_pass_device(pcv_ctx* ctx, const pcv_shard_bufs* own, uint64_t nslots, const uint64_t* first_bins /* 64 */, double resolution,
+                                       const double bbox_min[3], const double bbox_max[3], const uint64_t* prefix_counts /* levels 1..2 */, pcv_octree** out);
 /* Local part of a sharded build: like pcv_build_octree_device, but nodes of levels <= k take their split decision from
  * the GLOBAL counts (`prefix_counts`: levels 1..k concatenated, 8 + 64 + .. entries, host), and the nodes of level k-1
  * collect the every-8th points of their local children for pcv_assemble_top. */
@@ -275,8 +299,11 @@ int pcv_assemble_top(pcv_ctx* ctx, double resolution, const double bbox_min[3], 
  *   local_out: this rank's nodes of levels >= k (and the collectors it contributed to); top_out: rank 0 only, levels < k
  *   k_out: the prefix depth actually used (<= prefix_levels, distributed.py usable_prefix_levels)
  *   cell_to_rank_out / unit_nsub_out: optional, 8^prefix_levels entries each (the first 8^k are written)
- *   send_out: optional; when given, the caller owns the handle (pcv_shard_send_dest gives per local point the rank it went to,
- *   which together with the count matrix reconstructs the provenance of every slab slot) and frees it with pcv_shard_send_free. */
+ *   recv_points_out: optional, the points this rank owns
+ *   send_out: optional; when given, the caller owns the handle and frees it with pcv_shard_send_free.  It keeps one byte per
+ *   local point - its level-2 cell (pcv_shard_send_cells) after the fused exchange pass, else the rank it went to
+ *   (pcv_shard_send_dest) - which together with the gathered histograms reconstructs the provenance of every slot.
+ * PCV_NO_FUSED_PASS=1 (environment) forces the exchange of ingested records + the owner's full build. */
 typedef struct pcv_comm {
     void* user;
     int rank, world;
@@ -286,7 +313,11 @@ typedef struct pcv_comm {
 } pcv_comm;
 int pcv_build_octree_sharded(pcv_ctx* ctx, const pcv_comm* comm, const pcv_points* dev_points, double resolution, const double bbox_min[3],
                              const double bbox_max[3], uint32_t prefix_levels, pcv_octree** local_out, pcv_octree** top_out, uint32_t* k_out,
-                             int32_t* cell_to_rank_out, uint64_t* unit_nsub_out, pcv_shard_send** send_out);
+                             int32_t* cell_to_rank_out, uint64_t* unit_nsub_out, uint64_t* recv_points_out, pcv_shard_send** send_out);
+/* Wall-clock milliseconds of the last pcv_build_octree_sharded on this context, per phase (each ends in a stream synchronisation or
+ * a barrier): ingest + histogram, all-reduce + plan (+ slab set-up on the first call), exchange, local build, top assembly;
+ * out[5] = 1 when the exchange was the fused exchange pass. */
+int pcv_sharded_phases(pcv_ctx* ctx, double out[6]);
 /* Releases the receive slab pcv_build_octree_sharded caches on the context (collective: every rank calls it). */
 int pcv_sharded_release(pcv_ctx* ctx, const pcv_comm* comm);
 

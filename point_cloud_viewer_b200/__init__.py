@@ -231,15 +231,33 @@ class Context:
 
     def build_octree_sharded(self, comm_struct, x_ptr, y_ptr, z_ptr, stride, rgb_ptr, intensity_ptr, n, resolution, bbox_min, bbox_max, prefix_levels=2, keep_send=True):
         """pcv_build_octree_sharded: the whole multi-GPU build in one C call per rank; `comm_struct` is a _native.Comm.
-        Returns (local Octree, top Octree or None, k, cell_to_rank, unit_nsub, send handle or None)."""
+        Returns (local Octree, top Octree or None, k, cell_to_rank, unit_nsub, points owned, send handle or None)."""
         pts = N.Points(x_ptr, y_ptr, z_ptr, stride, rgb_ptr, intensity_ptr, int(n))
-        local, top, send, k = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        local, top, send, k, nrecv = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint64()
         c2r = np.zeros(8 ** prefix_levels, np.int32)
         un = np.zeros(8 ** prefix_levels, np.uint64)
         N.check(N.lib().pcv_build_octree_sharded(self.h, C.addressof(comm_struct), C.byref(pts), float(resolution), _d3(bbox_min), _d3(bbox_max), prefix_levels,
-                                                 C.byref(local), C.byref(top), C.byref(k), _p(c2r), _p(un), C.byref(send) if keep_send else None))
+                                                 C.byref(local), C.byref(top), C.byref(k), _p(c2r), _p(un), C.byref(nrecv), C.byref(send) if keep_send else None))
         kk = int(k.value)
-        return (Octree(self, local), Octree(self, top) if top.value else None, kk, c2r[: 8 ** kk].copy(), un[: 8 ** kk].copy(), send if keep_send else None)
+        return (Octree(self, local), Octree(self, top) if top.value else None, kk, c2r[: 8 ** kk].copy(), un[: 8 ** kk].copy(), int(nrecv.value),
+                send if keep_send else None)
+
+    def shard_send_cells(self, send):
+        """(device pointer, n) of the per-point level-2 cells a fused exchange pass leaves with the handle; None if the handle went
+        through the exchange of ingested records instead."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        if N.lib().pcv_shard_send_cells(send, C.byref(ptr), C.byref(n)) != 0:
+            return None
+        return (ptr.value or 0), int(n.value)
+
+    def sharded_phases(self):
+        """Per-phase wall-clock milliseconds of the last build_octree_sharded on this context."""
+        out = (C.c_double * 6)()
+        N.check(N.lib().pcv_sharded_phases(self.h, out))
+        names = ("ingest + histogram", "all-reduce + plan", "exchange", "local build", "top assembly")
+        d = {nm: float(out[i]) for i, nm in enumerate(names)}
+        d["fused_exchange_pass"] = bool(out[5])
+        return d
 
     def sharded_release(self, comm_struct):
         N.check(N.lib().pcv_sharded_release(self.h, C.addressof(comm_struct)))

@@ -472,6 +472,15 @@ inline LevelTable make_level_table(double root_edge, double resolution, const do
     return t;
 }
 
+// PassArgs::e1 .. fast from the level table (pa.level and pa.G must be set)
+inline void set_level_constants(PassArgs& pa, const LevelTable& lv) {
+    const int L1 = pa.level + 1, L2 = std::min(pa.level + 2, kMaxLevels - 1), Lb = pa.level + pa.G, Lh = std::min(Lb + 1, kMaxLevels - 1);
+    pa.e1 = lv.edge[L1], pa.e2 = lv.edge[L2], pa.ry2 = lv.ry[L2];
+    pa.eb = lv.edge[Lb], pa.eh = lv.edge[Lh], pa.ryh = lv.ry[Lh];
+    pa.enc1 = lv.enc[L1], pa.enc2 = lv.enc[L2], pa.ench = lv.enc[Lh];
+    pa.fast = lv.fast;
+}
+
 struct BuildResult {
     std::vector<HNode> nodes;     // creation order (parents before children)
     std::vector<int> sorted;      // node indices sorted by NodeId
@@ -708,13 +717,7 @@ class BuildPlan {
                 pa.shard_k = shard.k;
                 pa.shard_counts = d_shard;
                 pa.lv = lv;
-                {
-                    const int L1 = pa.level + 1, L2 = std::min(pa.level + 2, kMaxLevels - 1), Lb = pa.level + pa.G, Lh = std::min(Lb + 1, kMaxLevels - 1);
-                    pa.e1 = lv.edge[L1], pa.e2 = lv.edge[L2], pa.ry2 = lv.ry[L2];
-                    pa.eb = lv.edge[Lb], pa.eh = lv.edge[Lh], pa.ryh = lv.ry[Lh];
-                    pa.enc1 = lv.enc[L1], pa.enc2 = lv.enc[L2], pa.ench = lv.enc[Lh];
-                    pa.fast = lv.fast;
-                }
+                set_level_constants(pa, lv);
                 if (fused && p == 0) {  // the senders ran this pass's partition: only its plan is made here, from the known cell counts
                     be.h2d(node_bins, ext.first_bins, 64 * sizeof(uint64_t));
                     be.plan(pa);

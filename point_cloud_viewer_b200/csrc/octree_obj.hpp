@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <map>
 #include <mutex>
 #include <string>

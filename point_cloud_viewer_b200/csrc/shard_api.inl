@@ -290,6 +290,10 @@ struct pcv_shard_send {
     const float* intensity = nullptr;  // the caller's array (not owned)
     uint32_t* tile_counts = nullptr;
     uint8_t* dest = nullptr;
+    uint32_t* tile_active = nullptr;
+    LevelTable lv;
+    double bmin[3] = {0, 0, 0}, root_edge = 0, resolution = 0;
+    bool fused_done = false;     // pcv_shard_pass_device ran: `dig` (the level-2 cell of every local point) is what stays for provenance
     std::vector<uint64_t> bins;  // points per digit of the local points
     std::vector<void*> owned;
 };
@@ -323,6 +327,10 @@ int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution,
     for (int L = 1; L <= lv.last_level; ++L) sd->wide = sd->wide || lv.enc[L] == ENC_F64;
     sd->G0 = std::min(2, lv.last_level);
     sd->nbins = 1 << (3 * sd->G0);
+    sd->lv = lv;
+    sd->root_edge = E;
+    sd->resolution = resolution;
+    for (int a = 0; a < 3; ++a) sd->bmin[a] = bmin[a];
     if (n == 0) {
         *out = sd.release();
         return PCV_OK;
@@ -377,7 +385,8 @@ int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution,
     pa.active = dact;
     pa.chunks = dch;
     pa.tile_counts = sd->tile_counts;
-    pa.tile_active = s.alloc<uint32_t>(nt);
+    sd->tile_active = (uint32_t*)dalloc((size_t)nt * 4);
+    pa.tile_active = sd->tile_active;
     pa.chunk_sums = s.alloc<uint32_t>((size_t)nch * 64);
     pa.node_bins = s.alloc<uint64_t>(64);
     pa.cap_active = 1;
@@ -479,6 +488,190 @@ int pcv_shard_exchange_device(pcv_shard_send* sd, uint32_t k, const int32_t* cel
         }
     sd->rec = nullptr, sd->col = nullptr, sd->dig = nullptr, sd->tile_counts = nullptr;
     return PCV_OK;
+    API_CATCH
+}
+
+// ---- fused exchange pass: the sender's FIRST PARTITION PASS writes into the owners' buffers --------------------
+// Instead of moving the ingested records to their owner and partitioning them there, every sender runs the first two-level
+// partition pass (root -> level-2 cells: rank by the carried digits, finish the level-2 codes, run the next pass's first step) on
+// its own records and stores each bucket - a level-2 cell - straight into the buffers of the cell's owner over NVLink.  The layout
+// on an owner is what its own first pass would have produced from (source rank, local index)-ordered input: cells in index order,
+// inside a cell the senders in rank order.  All of it follows from the gathered per-sender histograms, so nothing is negotiated.
+namespace {
+struct FusedLayout {
+    uint64_t slot_start[64];  // per cell: first slot (cell-major over ALL the owner's cells) on its owner
+    uint64_t arena_off[64];   // leaf cells: first record in the owner's arena
+    bool split[64];
+    uint64_t total[64];
+    uint64_t slots[kMaxRanks];
+};
+// nullptr on success, else why the fused pass cannot be used (the caller falls back to the exchange of ingested records)
+const char* fused_layout(const LevelTable& lv, double resolution, uint64_t max_points, int nranks, const int32_t* c2r, const uint64_t* hist_all, FusedLayout& L) {
+    if (lv.last_level < 2) return "the octree has fewer than two levels";
+    for (int c = 0; c < 64; ++c) {
+        L.total[c] = 0;
+        for (int s = 0; s < nranks; ++s) L.total[c] += hist_all[(size_t)s * 64 + c];
+    }
+    for (int k1 = 0; k1 < 8; ++k1) {  // every non-empty level-1 node must split (distributed.py usable_prefix_levels guarantees it for k = 2)
+        uint64_t t = 0;
+        for (int k2 = 0; k2 < 8; ++k2) t += L.total[k1 * 8 + k2];
+        if (t && !(t > max_points && lv.edge[1] > resolution)) return "a level-1 node does not split";
+    }
+    for (int r = 0; r < nranks; ++r) {
+        uint64_t slot = 0, arena = 0;
+        for (int c = 0; c < 64; ++c) {
+            if (c2r[c] != r || !L.total[c]) continue;
+            L.slot_start[c] = slot;
+            L.split[c] = L.total[c] > max_points && lv.edge[2] > resolution;  // should_split_node on the global count (generation.rs:128-150)
+            L.arena_off[c] = arena;
+            if (!L.split[c]) arena += L.total[c];
+            slot += L.total[c];
+        }
+        if (slot >= 0xFFFFFFFFull) return "an owner would receive 2^32 points or more";
+        L.slots[r] = slot;
+    }
+    return nullptr;
+}
+}  // namespace
+
+int pcv_shard_pass_device(pcv_shard_send* sd, uint32_t nranks, uint32_t rank, const int32_t* cell_to_rank, const uint64_t* hist_all, const pcv_shard_bufs* dst,
+                          uint64_t* slots_out, uint64_t* first_bins_out) {
+    if (!sd || !cell_to_rank || !hist_all || !dst) return fail(PCV_ERR_INVALID, "null argument");
+    if (nranks == 0 || nranks > (uint32_t)kMaxRanks || rank >= nranks) return fail(PCV_ERR_INVALID, "nranks must be 1..%d and rank below it", kMaxRanks);
+    if (sd->G0 != 2) return fail(PCV_ERR_UNSUPPORTED, "the fused exchange pass needs a two-level first pass");
+    static_assert(sizeof(pcv_shard_bufs) == sizeof(RemoteBufs), "pcv_shard_bufs mirrors RemoteBufs");
+    API_TRY
+    pcv_ctx* c = sd->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < 64; ++i)
+        if (cell_to_rank[i] < 0 || cell_to_rank[i] >= (int32_t)nranks) return fail(PCV_ERR_INVALID, "cell_to_rank[%d] out of range", i);
+    for (int d = 0; d < 64; ++d)
+        if (hist_all[(size_t)rank * 64 + d] != sd->bins[(size_t)d]) return fail(PCV_ERR_INVALID, "hist_all[rank] is not this handle's histogram");
+    FusedLayout L{};
+    const uint64_t max_points = c->cfg.max_points_per_node ? c->cfg.max_points_per_node : 100000;
+    if (const char* why = fused_layout(sd->lv, sd->resolution, max_points, (int)nranks, cell_to_rank, hist_all, L)) return fail(PCV_ERR_UNSUPPORTED, "%s", why);
+    if (slots_out)
+        for (uint32_t r = 0; r < nranks; ++r) slots_out[r] = L.slots[r];
+    if (first_bins_out)
+        for (int cell = 0; cell < 64; ++cell) first_bins_out[cell] = cell_to_rank[cell] == (int32_t)rank ? L.total[cell] : 0;
+    if (sd->n == 0) {
+        sd->fused_done = true;
+        return PCV_OK;
+    }
+    for (uint32_t r = 0; r < nranks; ++r) {
+        if (!L.slots[r]) continue;
+        if (!dst[r].rec_next || !dst[r].dig_next || !dst[r].arena || !dst[r].col_arena || (sd->wide && !dst[r].col_next) || (sd->has_intensity && !dst[r].intensity))
+            return fail(PCV_ERR_INVALID, "destination buffers of rank %u are incomplete", r);
+    }
+    CudaBackend& be = *c->be;
+    Scratch s(c);
+    // this sender's bucket table: one bucket per non-empty local cell, in the owner's buffers behind the lower ranks' records
+    std::vector<BucketDesc> bk(64, BucketDesc{});
+    int nb = 0;
+    for (int cell = 0; cell < 64; ++cell) {
+        if (!sd->bins[(size_t)cell]) continue;
+        uint64_t pre = 0;
+        for (uint32_t r = 0; r < rank; ++r) pre += hist_all[(size_t)r * 64 + cell];
+        BucketDesc b{};
+        b.b0 = (uint16_t)cell;
+        b.b1 = (uint16_t)(cell + 1);
+        b.keep = 2;
+        b.owner = (uint16_t)(cell_to_rank[cell] + 1);
+        if (L.split[cell]) {
+            b.kind = 0;
+            b.dest = L.slot_start[cell] + pre;
+        } else {
+            b.kind = 1;
+            b.dest = (L.arena_off[cell] + pre) | ((L.slot_start[cell] + pre) << 32);
+        }
+        bk[(size_t)nb++] = b;
+    }
+    std::vector<RemoteBufs> rb(nranks);
+    for (uint32_t r = 0; r < nranks; ++r) std::memcpy(&rb[r], &dst[r], sizeof(RemoteBufs));
+    BuildState hs{};
+    hs.nnodes = 1;
+    hs.pass[0].nactive = 1;
+    hs.pass[0].ntiles = sd->ntiles;
+    hs.pass[0].nchunks = (sd->ntiles + kChunkTiles - 1) / kChunkTiles;
+    hs.pass[0].npoints = sd->n;
+    ActiveDesc a0{};
+    for (int a = 0; a < 3; ++a) a0.m[a] = sd->bmin[a];
+    a0.e = sd->root_edge;
+    a0.count = sd->n;
+    a0.nchunks = hs.pass[0].nchunks;
+    PassArgs pa{};
+    pa.pass = 0;
+    pa.level = 0;
+    pa.G = 2;
+    pa.nbins = 64;
+    pa.Gn = std::min(2, sd->lv.last_level - 2);
+    pa.wide = sd->wide;
+    pa.remote = s.upload(rb.data(), rb.size());
+    pa.int_in = sd->has_intensity ? sd->intensity : nullptr;
+    pa.rec_in = sd->rec;
+    pa.col_in = sd->col;
+    pa.dig_in = sd->dig;
+    pa.st = s.upload(&hs, 1);
+    pa.active = s.upload(&a0, 1);
+    pa.tile_active = sd->tile_active;
+    pa.tile_counts = sd->tile_counts;
+    pa.buckets = s.upload(bk.data(), bk.size());
+    pa.cap_active = 1;
+    pa.cap_tiles = sd->ntiles;
+    pa.resolution = sd->resolution;
+    pa.lv = sd->lv;
+    set_level_constants(pa, sd->lv);
+    be.partition(pa);
+    CU(cudaStreamSynchronize(c->stream));  // every store of this rank has been issued and completed
+    // the records are consumed; the digits - the level-2 cell of every local point - stay for provenance look-ups
+    for (void*& p : sd->owned)
+        if (p != (void*)sd->dig) {
+            be.dfree(p);
+            p = nullptr;
+        }
+    sd->rec = nullptr, sd->col = nullptr, sd->tile_counts = nullptr, sd->tile_active = nullptr, sd->dest = nullptr;
+    sd->fused_done = true;
+    return PCV_OK;
+    API_CATCH
+}
+
+int pcv_shard_send_cells(const pcv_shard_send* s, const uint8_t** dev_cells, uint64_t* n) {
+    if (!s || !dev_cells || !n) return fail(PCV_ERR_INVALID, "null argument");
+    if (!s->fused_done) return fail(PCV_ERR_INVALID, "the handle did not run pcv_shard_pass_device");
+    *dev_cells = s->dig;
+    *n = s->n;
+    return PCV_OK;
+}
+
+int pcv_build_octree_after_pass_device(pcv_ctx* c, const pcv_shard_bufs* own, uint64_t nslots, const uint64_t* first_bins, double resolution,
+                                       const double bmin_in[3], const double bmax_in[3], const uint64_t* prefix_counts, pcv_octree** out) {
+    if (!c || !own || !first_bins || !bmin_in || !bmax_in || !prefix_counts || !out) return fail(PCV_ERR_INVALID, "null argument");
+    if (nslots && (!own->rec_next || !own->dig_next || !own->arena || !own->col_arena)) return fail(PCV_ERR_INVALID, "incomplete buffers");
+    *out = nullptr;
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    ShardSpec sp;
+    sp.k = 2;
+    sp.counts = prefix_counts;
+    ExternalRecords ext;
+    ext.rec = own->rec_next;
+    ext.col = (uint32_t*)own->col_next;
+    ext.dig = (uint8_t*)own->dig_next;
+    ext.n = nslots;
+    ext.present = true;
+    ext.col_in_record = own->col_next == nullptr;
+    ext.after_first_pass = true;
+    ext.arena = own->arena;
+    ext.col_arena = (uint32_t*)own->col_arena;
+    ext.first_bins = first_bins;
+    PointsView v{};
+    v.stride = 1;
+    v.n = nslots;
+    v.intensity = (const float*)own->intensity;
+    v.rgb = reinterpret_cast<const uint8_t*>(own->rec_next);  // non-null marker: colours travel with the records
+    return build_impl(c, v, resolution, bmin_in, bmax_in, out, &sp, &ext);
     API_CATCH
 }
 

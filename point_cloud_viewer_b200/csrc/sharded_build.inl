@@ -15,14 +15,22 @@ struct ShardSlab {
     int world = 0;
     bool wide = false, with_int = false;
     std::vector<void*> peer;
-    uint64_t off_col = 0, off_int = 0, off_dig = 0, bytes = 0;
+    // one allocation per rank: next-pass records | their colours (wide records only) | intensities | digits | leaf arena | its colours
+    uint64_t off_col = 0, off_int = 0, off_dig = 0, off_arena = 0, off_acol = 0, bytes = 0;
     void* rec(int r) const { return peer[(size_t)r]; }
     void* col(int r) const { return (uint8_t*)peer[(size_t)r] + off_col; }
     void* inten(int r) const { return (uint8_t*)peer[(size_t)r] + off_int; }
     void* dig(int r) const { return (uint8_t*)peer[(size_t)r] + off_dig; }
+    pcv_shard_bufs bufs(int r) const {
+        uint8_t* b = (uint8_t*)peer[(size_t)r];
+        return pcv_shard_bufs{b, wide ? b + off_col : nullptr, b + off_dig, b + off_arena, b + off_acol, with_int ? b + off_int : nullptr};
+    }
 };
 std::mutex g_slab_mu;
 std::map<pcv_ctx*, ShardSlab> g_slabs;
+// wall-clock phases of the last pcv_build_octree_sharded per context (every phase ends in a stream synchronisation or a barrier):
+// ingest + histogram, all-reduce + plan, exchange, local build, top assembly; [5] = 1 if the fused exchange pass ran
+std::map<pcv_ctx*, std::array<double, 6>> g_phases;
 
 #define COMM(x)                                                                                    \
     do {                                                                                           \
@@ -97,7 +105,9 @@ ShardSlab& slab_for(pcv_ctx* c, const pcv_comm* comm, uint64_t need, bool wide, 
     s.off_col = rs * s.cap + 256;
     s.off_int = s.off_col + 4 * s.cap + 256;
     s.off_dig = s.off_int + (with_int ? 4 * s.cap + 256 : 0);
-    s.bytes = s.off_dig + s.cap + 256;
+    s.off_arena = s.off_dig + ((s.cap + 256 + 255) / 256) * 256;
+    s.off_acol = s.off_arena + rs * s.cap + 256;
+    s.bytes = s.off_acol + 4 * s.cap + 256;
     uint8_t handle[64];
     PCVX(pcv_ipc_alloc(c, s.bytes, &s.ptr, handle));
     std::vector<uint8_t> all((size_t)comm->world * 64);
@@ -124,13 +134,14 @@ static void sharded_forget(pcv_ctx* c) {
         if (s.peer[(size_t)r] && s.peer[(size_t)r] != s.ptr) cudaIpcCloseMemHandle(s.peer[(size_t)r]);
     if (s.ptr) cudaFree(s.ptr);
     g_slabs.erase(it);
+    g_phases.erase(c);
 }
 
 extern "C" {
 
 int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points* dp, double resolution, const double bmin_in[3], const double bmax_in[3],
                              uint32_t prefix_levels, pcv_octree** local_out, pcv_octree** top_out, uint32_t* k_out, int32_t* cell_to_rank_out, uint64_t* unit_nsub_out,
-                             pcv_shard_send** send_out) {
+                             uint64_t* recv_points_out, pcv_shard_send** send_out) {
     if (!c || !comm || !dp || !bmin_in || !bmax_in || !local_out || !top_out) return fail(PCV_ERR_INVALID, "null argument");
     if (!comm->allreduce_sum_u64 || !comm->allgather || !comm->barrier || comm->world < 1 || comm->rank < 0 || comm->rank >= comm->world || comm->world > kMaxRanks)
         return fail(PCV_ERR_INVALID, "invalid communicator");
@@ -140,6 +151,13 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     pcv_shard_send* send = nullptr;
     API_TRY
     const int R = comm->world, me = comm->rank;
+    std::array<double, 6> ph{};
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](int i) {
+        const auto t = std::chrono::steady_clock::now();
+        ph[(size_t)i] += std::chrono::duration<double, std::milli>(t - t_last).count();
+        t_last = t;
+    };
     double bmin[3], bmax[3];
     for (int a = 0; a < 3; ++a) {
         bmin[a] = std::fmin(bmin_in[a], bmax_in[a]);
@@ -150,6 +168,7 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     // (1) local ingest + histogram, global histogram
     std::vector<uint64_t> local_hist((size_t)1 << (3 * k), 0);
     PCVX(pcv_shard_ingest_device(c, dp, resolution, bmin, bmax, (uint32_t)k, local_hist.data(), &send));
+    mark(0);
     std::vector<uint64_t> counts_k = local_hist;
     COMM(comm->allreduce_sum_u64(comm->user, counts_k.data(), counts_k.size()));
     const int k2 = usable_prefix_levels(counts_k, k, E, resolution, c->cfg.max_points_per_node);
@@ -179,7 +198,32 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     PCVX(pcv_shard_send_info(send, &wide, nullptr));
     const bool with_int = dp->intensity != nullptr;
     ShardSlab& slab = slab_for(c, comm, need, wide != 0, with_int);
-    // (3) one kernel: every record into its owner's slab
+    mark(1);
+    // (3a) fused exchange pass: every sender's first partition pass stores into the owners' buffers; the owner's build starts at
+    // its second pass.  Falls back to (3b) when the layout does not allow it (same decision on every rank: same inputs).
+    pcv_octree* local = nullptr;
+    bool fused = k == 2 && !std::getenv("PCV_NO_FUSED_PASS");
+    if (fused) {
+        std::vector<uint64_t> hist_all((size_t)R * 64), first_bins(64, 0), slots((size_t)R, 0);
+        COMM(comm->allgather(comm->user, local_hist.data(), 64 * 8, hist_all.data()));
+        std::vector<pcv_shard_bufs> dst((size_t)R);
+        for (int d = 0; d < R; ++d) dst[(size_t)d] = slab.bufs(d);
+        COMM(comm->barrier(comm->user));  // no peer is still building out of its slab
+        const int rc = pcv_shard_pass_device(send, (uint32_t)R, (uint32_t)me, c2r.data(), hist_all.data(), dst.data(), slots.data(), first_bins.data());
+        if (rc == PCV_ERR_UNSUPPORTED) {
+            fused = false;
+        } else {
+            PCVX(rc);
+            if (slots[(size_t)me] != n_recv) throw BuildError(PCV_ERR_CUDA, "internal: slot count and count matrix disagree");
+            COMM(comm->barrier(comm->user));  // every rank's stores have landed
+            mark(2);
+            ph[5] = 1;
+            const pcv_shard_bufs own = slab.bufs(me);
+            PCVX(pcv_build_octree_after_pass_device(c, &own, n_recv, first_bins.data(), resolution, bmin, bmax, prefix_counts.data(), &local));
+        }
+    }
+    if (!fused) {
+    // (3b) one kernel: every ingested record into its owner's slab
     std::vector<uint64_t> first((size_t)R, 0), got((size_t)R, 0);
     std::vector<void*> drec((size_t)R), dcol((size_t)R), ddig((size_t)R), dint((size_t)R);
     for (int d = 0; d < R; ++d) {
@@ -195,12 +239,14 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     for (int d = 0; d < R; ++d)
         if (got[(size_t)d] != M[(size_t)me * R + d]) throw BuildError(PCV_ERR_CUDA, "internal: local histogram and exchange disagree");
     COMM(comm->barrier(comm->user));  // every rank's stores have landed
+    mark(2);
     // (4) the owner's build
-    pcv_octree* local = nullptr;
     PCVX(pcv_build_octree_from_records_device(c, n_recv ? slab.rec(me) : nullptr, (wide && n_recv) ? (uint32_t*)slab.col(me) : nullptr, n_recv ? (uint8_t*)slab.dig(me) : nullptr,
                                               (with_int && n_recv) ? (const float*)slab.inten(me) : nullptr, n_recv, resolution, bmin, bmax, (uint32_t)k,
                                               prefix_counts.data(), &local));
+    }
     *local_out = local;
+    mark(3);
     // (5) top of the tree: unit sizes, collectors' content -> rank 0
     const size_t ncell = (size_t)1 << (3 * k);
     std::vector<uint64_t> unit_nsub(ncell, 0);
@@ -283,7 +329,16 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
         PCVX(pcv_assemble_top(c, resolution, bmin, bmax, (uint32_t)k, prefix_counts.data(), unit_nsub.data(), tx.data(), tr.data(), with_int ? tin.data() : nullptr, npts,
                               top_out));
     }
+    mark(4);
+    {
+        std::lock_guard<std::mutex> g(g_slab_mu);
+        g_phases[c] = ph;
+    }
+    if (std::getenv("PCV_TIMING") && me == 0)
+        fprintf(stderr, "[pcv sharded C] ingest + histogram %.1f  all-reduce + plan %.1f  exchange%s %.1f  local build %.1f  top assembly %.1f ms\n", ph[0], ph[1],
+                ph[5] != 0 ? " (fused pass)" : "", ph[2], ph[3], ph[4]);
     if (k_out) *k_out = (uint32_t)k;
+    if (recv_points_out) *recv_points_out = n_recv;
     if (cell_to_rank_out) std::memcpy(cell_to_rank_out, c2r.data(), ncell * sizeof(int32_t));
     if (unit_nsub_out) std::memcpy(unit_nsub_out, unit_nsub.data(), ncell * sizeof(uint64_t));
     if (send_out)
@@ -300,6 +355,15 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
         if (send) pcv_shard_send_free(send);
         return fail(PCV_ERR_INVALID, "%s", e.what());
     }
+}
+
+int pcv_sharded_phases(pcv_ctx* c, double out[6]) {
+    if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> g(g_slab_mu);
+    auto it = g_phases.find(c);
+    if (it == g_phases.end()) return fail(PCV_ERR_NOT_FOUND, "no sharded build has run on this context");
+    for (int i = 0; i < 6; ++i) out[i] = it->second[(size_t)i];
+    return PCV_OK;
 }
 
 int pcv_sharded_release(pcv_ctx* c, const pcv_comm* comm) {

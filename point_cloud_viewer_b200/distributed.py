@@ -402,6 +402,57 @@ class LazyIndex:
         return int(self.M[:, self.comm.rank].sum())
 
 
+class LazyCellIndex(LazyIndex):
+    """Provenance after a fused exchange pass: a slot on an owner is (cell-major over the owner's cells, sender rank, local order),
+    so each sender derives the slot of every local point from its level-2 cell (one byte per point, kept by the send handle) and
+    the gathered per-sender histograms; one all-to-all delivers (slot, global index) pairs and the owner scatters them."""
+
+    def __init__(self, ctx, send, index_base, n_local, cell_to_rank, n_slots, comm):
+        self.ctx, self.send, self.base, self.n_local, self.c2r, self.n_slots, self.comm = ctx, send, int(index_base), int(n_local), cell_to_rank, int(n_slots), comm
+        self.value = None
+
+    def resolve(self):
+        if self.value is not None:
+            return self.value
+        import torch
+
+        dev, comm = self.comm.device, self.comm
+        ptr, n = self.ctx.shard_send_cells(self.send)
+        cells = (torch.as_tensor(_RawCuda(ptr, (max(n, 1),), "|u1"), device=dev)[:n] if n else torch.zeros(0, dtype=torch.uint8, device=dev)).to(torch.int64)
+        mine = torch.bincount(cells, minlength=64)
+        H = np.asarray(comm.all_gather_counts(mine.cpu().numpy()), np.int64).reshape(comm.world, 64)
+        T, c2r = H.sum(0), np.asarray(self.c2r, np.int64)
+        slot_start = np.zeros(64, np.int64)
+        for r in range(comm.world):
+            run = 0
+            for c in range(64):
+                if c2r[c] == r and T[c]:
+                    slot_start[c] = run
+                    run += int(T[c])
+        pre = H[: comm.rank].sum(0)
+        order = torch.argsort(cells, stable=True)
+        sc = cells[order]
+        first = torch.cumsum(mine, 0) - mine
+        base = torch.from_numpy(slot_start + pre).to(dev)
+        slot = base[sc] + (torch.arange(n, device=dev) - first[sc])
+        owner = torch.from_numpy(c2r).to(dev)[sc]
+        o2 = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=comm.world).cpu().numpy().astype(np.int64)
+        recv_counts = np.asarray(comm.all_gather_counts(send_counts), np.int64).reshape(comm.world, comm.world)[:, comm.rank]
+        sc_l, rc_l = [int(v) for v in send_counts], [int(v) for v in recv_counts]
+        got_slot = comm.all_to_all(slot[o2].contiguous(), sc_l, rc_l)
+        got_idx = comm.all_to_all((order[o2] + self.base).contiguous(), sc_l, rc_l)
+        assert int(got_slot.numel()) == self.n_slots, "slots received and slots owned disagree"
+        value = torch.full((self.n_slots,), -1, dtype=torch.int64, device=dev)
+        value[got_slot] = got_idx
+        assert self.n_slots == 0 or int(value.min()) >= 0, "a slot has no source"
+        self.value = value
+        return self.value
+
+    def numel(self):
+        return self.n_slots
+
+
 class ShardedOctree:
     """The result on one rank: `local` holds the sub-trees of this rank's cells (levels >= k) plus its collector
     content; `top` (rank 0 only) holds the nodes of levels < k.  The global octree is the union of every rank's
@@ -769,18 +820,22 @@ def build_octree_sharded_native(ctx, x, y, z, rgb, intensity, index_base, resolu
     comm = comm or TorchComm(x.device)
     cs = make_c_comm(comm)
     n = int(x.numel())
-    local, top, k, c2r, unit_nsub, send = ctx.build_octree_sharded(cs, x.data_ptr(), y.data_ptr(), z.data_ptr(), 1, rgb.data_ptr(),
-                                                                   intensity.data_ptr() if intensity is not None else None, n, resolution, bbox_min, bbox_max,
-                                                                   prefix_levels)
+    local, top, k, c2r, unit_nsub, n_recv, send = ctx.build_octree_sharded(cs, x.data_ptr(), y.data_ptr(), z.data_ptr(), 1, rgb.data_ptr(),
+                                                                           intensity.data_ptr() if intensity is not None else None, n, resolution, bbox_min,
+                                                                           bbox_max, prefix_levels)
     stats = ctx.last_build_stats()
-    # provenance, all on demand: count matrix from the per-point destinations, slots of the top pieces from the local tree
+    # provenance, all on demand: slots of the received points from the senders' per-point bytes, slots of the top pieces from
+    # the local tree
     import torch
 
-    ptr, nd = ctx.shard_send_dest(send)
-    dest = torch.as_tensor(_RawCuda(ptr, (max(nd, 1),), "|u1"), device=x.device)[:nd] if nd else torch.zeros(0, dtype=torch.uint8, device=x.device)
-    sc = torch.bincount(dest.to(torch.int64), minlength=comm.world).cpu().numpy().astype(np.int64)
-    M = np.asarray(comm.all_gather_counts(sc)).reshape(comm.world, comm.world)
-    r_idx = LazyIndex(ctx, send, index_base, n, M, comm)
+    if ctx.shard_send_cells(send) is not None:  # the fused exchange pass ran
+        r_idx = LazyCellIndex(ctx, send, index_base, n, c2r, n_recv, comm)
+    else:
+        ptr, nd = ctx.shard_send_dest(send)
+        dest = torch.as_tensor(_RawCuda(ptr, (max(nd, 1),), "|u1"), device=x.device)[:nd] if nd else torch.zeros(0, dtype=torch.uint8, device=x.device)
+        sc = torch.bincount(dest.to(torch.int64), minlength=comm.world).cpu().numpy().astype(np.int64)
+        M = np.asarray(comm.all_gather_counts(sc)).reshape(comm.world, comm.world)
+        r_idx = LazyIndex(ctx, send, index_base, n, M, comm)
     lazy_slots = {}
     meta = local.meta
     idx_mask = (1 << 60) - 1
@@ -798,6 +853,7 @@ def build_octree_sharded_native(ctx, x, y, z, rgb, intensity, index_base, resolu
     out = ShardedOctree(local, top, k, r_idx, {"mine": lazy_slots}, c2r, comm.rank, stats)
     out.send_handle = (ctx, send)
     out.recv_points = r_idx.numel()
+    out.phases_ms = ctx.sharded_phases()
     out.c_comm = cs  # keeps the callbacks alive as long as the tree (pcv_sharded_release takes the same struct)
     return out
 

@@ -1,10 +1,8 @@
-set -x
-timeout 900 python -m pytest tests/test_build_gpu.py tests/test_config2_parity_gpu.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --steps 5 --warmup 3 --roofline-only > gpurun_out/r2_p1.json 2> gpurun_out/r2_p1.err
-PCV_NO_POW2=1 timeout 600 python bench.py --steps 5 --warmup 3 --roofline-only > gpurun_out/r2_p1b.json 2>> gpurun_out/r2_p1.err
-python - <<'PY'
-import json
-for f in ('gpurun_out/r2_p1.json','gpurun_out/r2_p1b.json'):
-    d=json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, d['ms_per_step'], d['value'], d.get('library_event_ms_per_step'), {k:round(v['ms'],2) for k,v in d['roofline']['kernels'].items() if v['ms']>0})
-PY
+#!/bin/bash
+# 2-GPU box: native (C-orchestrated) sharded build tests + fused exchange pass + bench with phase timings
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_sharded_native_gpu.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/native_tests.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29741 scripts/sharded_check.py 1e6 20000 2 2>&1 | grep -E "OK|Error|error|assert" | tail -12 | tee gpurun_out/sharded_check2.log
+PCV_TIMING=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29742 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/r2_f2.json 2> gpurun_out/r2_f2.err
+tail -c 1500 gpurun_out/r2_f2.json
+grep -E "pcv sharded|pcv timing" gpurun_out/r2_f2.err | tail -12

@@ -36,8 +36,9 @@ class SoloComm:
         torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("kind_name,k", [("SYNTH_GAUSS_CLUSTERS", 2), ("SYNTH_SLAB_ECEF", 2), ("SYNTH_GAUSS_CLUSTERS", 1)])
-def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k):
+@pytest.mark.parametrize("kind_name,k,with_int,fused", [("SYNTH_GAUSS_CLUSTERS", 2, False, True), ("SYNTH_SLAB_ECEF", 2, True, True), ("SYNTH_GAUSS_CLUSTERS", 1, False, True),
+                                                     ("SYNTH_GAUSS_CLUSTERS", 2, True, False)])
+def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k, with_int, fused, monkeypatch):
     import torch
 
     import point_cloud_viewer_b200 as pcv
@@ -51,18 +52,24 @@ def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k):
     x, y, z = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
     rgb = torch.empty(n * 3, dtype=torch.uint8, device=dev)
     ctx.synth_points_device(kind, 11, 0, n, x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr())
-    single = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
+    inten = torch.rand(n, dtype=torch.float32, device=dev) if with_int else None
+    if not fused:  # the exchange of ingested records + the owner's full build (the fall-back of the fused exchange pass)
+        monkeypatch.setenv("PCV_NO_FUSED_PASS", "1")
+    single = ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, intensity=inten.data_ptr() if with_int else None, n=n, device=True)
     comm = SoloComm(dev)
     for _ in range(2):  # the second call reuses the cached slab
-        tree = D.build_octree_sharded_native(ctx, x, y, z, rgb, None, 0, res, bmin, bmax, prefix_levels=k, comm=comm)
+        tree = D.build_octree_sharded_native(ctx, x, y, z, rgb, inten, 0, res, bmin, bmax, prefix_levels=k, comm=comm)
+        assert (ctx.shard_send_cells(tree.send_handle[1]) is not None) == (fused and tree.k == 2)
         merged = tree.gather_all(comm)
         assert set(single.nodes) == set(merged)
         for name, m in single.nodes.items():
             g = merged[name]
             assert (g["num_points"], g["enc"], tuple(g["cube"])) == (m["num_points"], m["enc"], tuple(m["cube"])), name
             if m["num_points"]:
-                sx, sc, _, ss = single.node_data(name)
+                sx, sc, si, ss = single.node_data(name)
                 assert np.array_equal(sx, g["xyz"]) and np.array_equal(sc, g["rgb"]) and np.array_equal(ss, g["src"]), name
+                if with_int:
+                    assert np.array_equal(si, g["intensity"]), name
         cs = tree.c_comm
         tree.free()
     ctx.sharded_release(cs)
