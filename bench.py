@@ -45,7 +45,7 @@ def _peaks():
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region."""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index=0):
         self.p = None
@@ -58,6 +58,11 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def window(self, t0, t1):
+        """Only samples taken inside [t0, t1] (time.time()) count: the sampler is started before the warm-up so that nvidia-smi's
+        own start-up (it initialises NVML and takes driver locks for hundreds of milliseconds) stays out of the timed steps."""
+        self.t0, self.t1 = t0, t1
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -69,10 +74,20 @@ class ClockSampler:
             out = ""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
                 continue
+            if t0 is not None and len(f) >= 7:
+                try:
+                    ts = datetime.datetime.strptime(f[6], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 - 0.05 or ts > t1 + 0.05:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
@@ -81,6 +96,10 @@ class ClockSampler:
             for nm, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        if not sm and t0 is not None:  # a timed region shorter than the sampling period: fall back to every sample of the run
+            self.t0 = self.t1 = None
+            self.p = type("Done", (), {"terminate": lambda s: None, "communicate": lambda s, timeout=None: (out, ""), "kill": lambda s: None})()
+            return self.stop()
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -404,7 +423,7 @@ def run_ours(args):
         except Exception as e:
             out_extra["parity_check"] = {"equal": False, "error": str(e)[:300]}
 
-    x, y, z, rgb = make_input(n, rank * n)
+    x, y, z, rgb = make_input(n, rank * n + int(float(os.environ.get("PCV_FIRST_INDEX", "0"))))  # (diagnostic: another slice of the generator)
 
     if world > 1:
 
@@ -415,14 +434,15 @@ def run_ours(args):
         def step():
             return ctx.build_octree(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), res, bmin, bmax, n=n, device=True)
 
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("PCV_NO_SAMPLER"):  # (diagnostic switch: the clocks line is part of the contract)
+        sampler.start()  # before the warm-up: see ClockSampler.window
     for w in range(args.warmup):
         t = step()
         t.free()
-    sampler = ClockSampler(local)
     launches0 = ctx.kernel_launch_count()
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.time()
     dev_ms = 0.0
     wall_ms = 0.0
     lib_ms = 0.0
@@ -445,6 +465,14 @@ def run_ours(args):
         if world == 1:
             lib_ms += ctx.last_build_stats()["ms_total"]
         barrier()
+    if os.environ.get("PCV_RANK_KSTATS"):  # diagnostic: per-rank kernel times of one extra step
+        ctx.set_profiling(True)
+        t = step()
+        t.free()
+        ks = ctx.kernel_stats()
+        ctx.set_profiling(False)
+        print("[kstats r%d] " % rank + "  ".join("%s %.2f" % (k, v["ms"]) for k, v in ks.items() if v["ms"] > 0), file=sys.stderr, flush=True)
+    sampler.window(t_region0, time.time())
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launch_count() - launches0
     tm = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)

@@ -381,6 +381,10 @@ typedef struct pcv_build_stats {
                                                              ms_host_plan: host time spent planning passes (inside ms_total) */
     float ms_host_wait;                                   /* host time blocked on the per-pass histogram read-back       */
 } pcv_build_stats;
+/* Work buffers are recycled inside the context (by exact size, at most half of the device memory) and in the device's stream-ordered
+ * pool, so that repeated builds make no allocator calls.  This returns all of it to the driver (e.g. before another library needs
+ * the memory). */
+int pcv_release_cached_memory(pcv_ctx* ctx);
 int pcv_last_build_stats(pcv_ctx* ctx, pcv_build_stats* out);
 /* Optional per-kernel timing: CUDA events on the context's stream around every launch of the build kernels.
  * Off by default (the events serialise nothing but cost host time); turn on for a measurement build. */

@@ -250,6 +250,9 @@ class Context:
             return None
         return (ptr.value or 0), int(n.value)
 
+    def release_cached_memory(self):
+        N.check(N.lib().pcv_release_cached_memory(self.h))
+
     def sharded_phases(self):
         """Per-phase wall-clock milliseconds of the last build_octree_sharded on this context."""
         out = (C.c_double * 6)()

@@ -184,6 +184,7 @@ SYMBOLS = [
     ("pcv_build_octree_after_pass_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, _dp, _dp, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_shard_send_cells", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p]),
     ("pcv_sharded_release", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("pcv_release_cached_memory", C.c_int, [C.c_void_p]),
     ("pcv_sharded_phases", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     ("pcv_build_octree_sharded_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("pcv_octree_node_nsub", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _u64p]),

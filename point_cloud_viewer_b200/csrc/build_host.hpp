@@ -546,6 +546,8 @@ class BuildPlan {
         if (pts.n >= 0xFFFFFFFFull) throw BuildError(-6, "more than 2^32-2 points per context are not supported");
         BuildResult R;
         R.n = pts.n;
+        const auto t_run0 = std::chrono::steady_clock::now();
+        double ms_setup = 0;
         // Cube::bounding (aabb.rs:149-157)
         double E = std::fmax(std::fmax(bmax[0] - bmin[0], bmax[1] - bmin[1]), bmax[2] - bmin[2]);
         for (int a = 0; a < 3; ++a) R.root_min[a] = bmin[a];
@@ -661,6 +663,7 @@ class BuildPlan {
             for (uint32_t o = 0; o < nt0; o += kChunkTiles) c0.push_back(ChunkDesc{o, std::min(kChunkTiles, nt0 - o), 0u, o == 0 ? 1u : 0u});
             be.h2d(chk[0], c0.data(), c0.size() * sizeof(ChunkDesc));
 
+            ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count();
             be.mark(0);
             IngestArgs ia{};
             ia.pts = pts;
@@ -903,7 +906,7 @@ class BuildPlan {
         if (!fused) be.dfree(arena), be.dfree(col_arena);
         R.host_ms_plan += tms(ts0, ts5);
         if (dbg)
-            fprintf(stderr, "[pcv timing] passes %u  wait %.2f | plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", R.passes,
+            fprintf(stderr, "[pcv timing] setup %.2f  passes %u  wait %.2f | plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", ms_setup, R.passes,
                     R.host_ms_wait, tms(ts0, ts1), tms(ts1, ts2), tms(ts2, ts3), tms(ts3, ts4), tms(ts4, ts5), nodes.size(), (size_t)nplace_tiles);
         return R;
     }

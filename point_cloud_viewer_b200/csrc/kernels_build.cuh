@@ -15,7 +15,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <map>
 #include <type_traits>
+#include <unordered_map>
 
 #include "build_host.hpp"
 #include "chain_device.cuh"
@@ -1121,18 +1123,94 @@ struct CudaBackend : Backend {
         allow_smem_all();
     }
     ~CudaBackend() override {
+        cache_release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         if (pin) cudaFreeHost(pin);
         if (pin_back) cudaFreeHost(pin_back);
     }
+    // Large blocks are recycled by exact size inside the context before they go back to the stream-ordered pool: repeated builds
+    // of the same shape (a viewer re-building, the steps of the sharded build) make no allocator calls at all in steady state.
+    // Measured on the second rank of a 2-GPU sharded build, whose receive-side buffers (1.0004e9 points) are slightly larger than
+    // its send-side ones (1e9): the pool cannot reuse a freed block for a larger request, and a cudaMallocAsync that has to find
+    // 4 GB of new memory took 5 - 60 ms, every step.  Everything a context allocates is used on its one stream, so handing a
+    // block to the next user is stream-ordered exactly like cudaFreeAsync + cudaMallocAsync.  The cache is bounded (half of the
+    // device memory, oldest blocks leave first) and emptied when an allocation fails.
+    static constexpr size_t kCacheMin = (size_t)1 << 20;
+    struct CachedBlock {
+        void* p;
+        uint64_t seq;
+    };
+    std::unordered_map<void*, size_t> big_live;
+    std::multimap<size_t, CachedBlock> big_free;
+    size_t cached_bytes = 0, cache_cap = 0;
+    uint64_t cache_seq = 0;
+    void cache_release() {
+        for (auto& kv : big_free) cudaFreeAsync(kv.second.p, stream);
+        big_free.clear();
+        cached_bytes = 0;
+    }
+    void cache_evict_oldest() {
+        auto best = big_free.begin();
+        for (auto it = big_free.begin(); it != big_free.end(); ++it)
+            if (it->second.seq < best->second.seq) best = it;
+        cudaFreeAsync(best->second.p, stream);
+        cached_bytes -= best->first;
+        big_free.erase(best);
+    }
+    bool trace_alloc = std::getenv("PCV_TRACE_ALLOC") != nullptr;
     void* dmalloc(size_t bytes) override {
+        if (!trace_alloc) return dmalloc_impl(bytes);
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t nfree = big_free.size();
+        void* p = dmalloc_impl(bytes);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.2) {
+            int dev = -1;
+            cudaGetDevice(&dev);
+            fprintf(stderr, "[pcv dmalloc dev%d] %zu bytes: %.2f ms (cached blocks before %zu, after %zu)\n", dev, bytes, ms, nfree, big_free.size());
+        }
+        return p;
+    }
+    void* dmalloc_impl(size_t bytes) {
         void* p = nullptr;
-        PCV_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+        if (bytes >= kCacheMin) {
+            auto it = big_free.find(bytes);
+            if (it != big_free.end()) {
+                p = it->second.p;
+                big_free.erase(it);
+                cached_bytes -= bytes;
+                big_live[p] = bytes;
+                return p;
+            }
+        }
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+        if (e == cudaErrorMemoryAllocation && !big_free.empty()) {  // make room: everything cached goes back to the pool
+            cudaGetLastError();
+            cache_release();
+            e = cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+        }
+        PCV_CUDA_CHECK(e);
+        if (bytes >= kCacheMin) big_live[p] = bytes;
         return p;
     }
     void dfree(void* p) override {
-        if (p) cudaFreeAsync(p, stream);
+        if (!p) return;
+        auto it = big_live.find(p);
+        if (it == big_live.end()) {
+            cudaFreeAsync(p, stream);
+            return;
+        }
+        if (!cache_cap) {
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            cache_cap = tot / 2;
+        }
+        const size_t bytes = it->second;
+        big_live.erase(it);
+        big_free.emplace(bytes, CachedBlock{p, ++cache_seq});
+        cached_bytes += bytes;
+        while (cached_bytes > cache_cap && !big_free.empty()) cache_evict_oldest();
     }
     // Host -> device staging through a pinned ring so that descriptor uploads are truly asynchronous (a pageable
     // source would make cudaMemcpyAsync wait for all prior work of the stream).  The ring is recycled after a

@@ -342,6 +342,20 @@ int pcv_device_free(pcv_ctx* c, void* ptr) {
     return PCV_OK;
 }
 
+int pcv_release_cached_memory(pcv_ctx* c) {
+    if (!c) return fail(PCV_ERR_INVALID, "null context");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->be->cache_release();
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return PCV_OK;
+    API_CATCH
+}
+
 int pcv_last_build_stats(pcv_ctx* c, pcv_build_stats* out) {
     if (!c || !out) return fail(PCV_ERR_INVALID, "null argument");
     *out = c->stats;

@@ -341,6 +341,16 @@ int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution,
         sd->owned.push_back(p);
         return p;
     };
+    const char* tv = std::getenv("PCV_TIMING");
+    const bool fine = tv && tv[0] == '2';
+    auto tp0 = std::chrono::steady_clock::now();
+    double tms[5] = {0, 0, 0, 0, 0};
+    auto tmark = [&](int i) {
+        if (!fine) return;
+        const auto t = std::chrono::steady_clock::now();
+        tms[i] = std::chrono::duration<double, std::milli>(t - tp0).count();
+        tp0 = t;
+    };
     const size_t rec_bytes = sd->wide ? sizeof(RecW) : sizeof(RecN);
     const uint32_t nt = (uint32_t)((n + kTilePoints - 1) / kTilePoints), nch = (nt + kChunkTiles - 1) / kChunkTiles;
     sd->ntiles = nt;
@@ -359,7 +369,10 @@ int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution,
     ia.ntiles = nt;
     ia.lv = lv;
     for (int a = 0; a < 3; ++a) ia.root_min[a] = bmin[a];
+    tmark(0);
     be.ingest(ia);
+    if (fine) CU(cudaStreamSynchronize(c->stream));
+    tmark(1);
     // per-tile digit histogram + exclusive prefix over the tiles (one "node": all local points), as a partition pass would
     Scratch s(c);
     BuildState hs{};
@@ -392,9 +405,12 @@ int pcv_shard_ingest_device(pcv_ctx* c, const pcv_points* dp, double resolution,
     pa.cap_active = 1;
     pa.cap_chunks = nch;
     pa.cap_tiles = nt;
+    tmark(2);
     be.hist_scan(pa);
     std::vector<uint64_t> bins(64, 0);
     be.d2h(bins.data(), pa.node_bins, (size_t)sd->nbins * 8);
+    tmark(3);
+    if (fine) fprintf(stderr, "[pcv ingest dev%d] allocs %.2f  ingest kernel %.2f  uploads %.2f  hist+scan+readback %.2f ms\n", c->device, tms[0], tms[1], tms[2], tms[3]);
     const int shift = 3 * (sd->G0 - (int)k);  // digits carry G0 levels; the shard level may be shallower
     if (shift < 0) return fail(PCV_ERR_INVALID, "prefix levels exceed the levels of the first pass");
     for (int d = 0; d < sd->nbins; ++d) counts_out[d >> shift] += bins[(size_t)d];

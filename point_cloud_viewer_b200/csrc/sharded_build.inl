@@ -169,10 +169,22 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     std::vector<uint64_t> local_hist((size_t)1 << (3 * k), 0);
     PCVX(pcv_shard_ingest_device(c, dp, resolution, bmin, bmax, (uint32_t)k, local_hist.data(), &send));
     mark(0);
-    std::vector<uint64_t> counts_k = local_hist;
-    COMM(comm->allreduce_sum_u64(comm->user, counts_k.data(), counts_k.size()));
+    // one all-gather of the per-rank histograms carries everything the plan needs: the global counts (their sum), the count
+    // matrix (who sends how much to whom) and the per-sender cell counts of the fused exchange pass
+    std::vector<uint64_t> hist_all((size_t)R * local_hist.size());
+    COMM(comm->allgather(comm->user, local_hist.data(), (uint64_t)local_hist.size() * 8, hist_all.data()));
+    std::vector<uint64_t> counts_k(local_hist.size(), 0);
+    for (int s = 0; s < R; ++s)
+        for (size_t cell = 0; cell < counts_k.size(); ++cell) counts_k[cell] += hist_all[(size_t)s * counts_k.size() + cell];
     const int k2 = usable_prefix_levels(counts_k, k, E, resolution, c->cfg.max_points_per_node);
     if (k2 < k) {
+        std::vector<uint64_t> ha;
+        for (int s = 0; s < R; ++s) {
+            const std::vector<uint64_t> row(hist_all.begin() + (size_t)s * counts_k.size(), hist_all.begin() + (size_t)(s + 1) * counts_k.size());
+            const std::vector<uint64_t> red = level_counts_of(row, k, k2);
+            ha.insert(ha.end(), red.begin(), red.end());
+        }
+        hist_all.swap(ha);
         counts_k = level_counts_of(counts_k, k, k2);
         local_hist = level_counts_of(local_hist, k, k2);
         k = k2;
@@ -184,9 +196,9 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     }
     // (2) cells -> ranks, count matrix
     const std::vector<int32_t> c2r = assign_cells_lpt(counts_k, R);
-    std::vector<uint64_t> send_counts((size_t)R, 0), M((size_t)R * R);
-    for (size_t cell = 0; cell < local_hist.size(); ++cell) send_counts[(size_t)c2r[cell]] += local_hist[cell];
-    COMM(comm->allgather(comm->user, send_counts.data(), (uint64_t)R * 8, M.data()));  // M[s * R + d]
+    std::vector<uint64_t> M((size_t)R * R, 0);  // M[s * R + d]
+    for (int s = 0; s < R; ++s)
+        for (size_t cell = 0; cell < counts_k.size(); ++cell) M[(size_t)s * R + (size_t)c2r[cell]] += hist_all[(size_t)s * counts_k.size() + cell];
     uint64_t need = 0, n_recv = 0;
     for (int d = 0; d < R; ++d) {
         uint64_t t = 0;
@@ -204,8 +216,7 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     pcv_octree* local = nullptr;
     bool fused = k == 2 && !std::getenv("PCV_NO_FUSED_PASS");
     if (fused) {
-        std::vector<uint64_t> hist_all((size_t)R * 64), first_bins(64, 0), slots((size_t)R, 0);
-        COMM(comm->allgather(comm->user, local_hist.data(), 64 * 8, hist_all.data()));
+        std::vector<uint64_t> first_bins(64, 0), slots((size_t)R, 0);
         std::vector<pcv_shard_bufs> dst((size_t)R);
         for (int d = 0; d < R; ++d) dst[(size_t)d] = slab.bufs(d);
         COMM(comm->barrier(comm->user));  // no peer is still building out of its slab
@@ -334,8 +345,8 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
         std::lock_guard<std::mutex> g(g_slab_mu);
         g_phases[c] = ph;
     }
-    if (std::getenv("PCV_TIMING") && me == 0)
-        fprintf(stderr, "[pcv sharded C] ingest + histogram %.1f  all-reduce + plan %.1f  exchange%s %.1f  local build %.1f  top assembly %.1f ms\n", ph[0], ph[1],
+    if (const char* tv = std::getenv("PCV_TIMING"); tv && (me == 0 || tv[0] == '2'))
+        fprintf(stderr, "[pcv sharded C r%d] ingest + histogram %.1f  all-reduce + plan %.1f  exchange%s %.1f  local build %.1f  top assembly %.1f ms\n", me, ph[0], ph[1],
                 ph[5] != 0 ? " (fused pass)" : "", ph[2], ph[3], ph[4]);
     if (k_out) *k_out = (uint32_t)k;
     if (recv_points_out) *recv_points_out = n_recv;
