@@ -498,6 +498,7 @@ def run_ours(args):
         # full-size invariants of the sharded result, all-reduced: every point exactly once (count, sum and sum of squares of the
         # global source indices), and the per-phase breakdown of the last step
         try:
+            ctx.release_cached_memory()  # the library's recycled work buffers: the check below needs tens of GB for its own tensors
             out["full_size_check"] = full_size_check(last, D, torch, dist, world, n, dev)
         except Exception as e:
             out["full_size_check"] = {"ok": False, "error": str(e)[:300]}

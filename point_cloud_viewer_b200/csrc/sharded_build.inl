@@ -214,7 +214,11 @@ int pcv_build_octree_sharded(pcv_ctx* c, const pcv_comm* comm, const pcv_points*
     // (3a) fused exchange pass: every sender's first partition pass stores into the owners' buffers; the owner's build starts at
     // its second pass.  Falls back to (3b) when the layout does not allow it (same decision on every rank: same inputs).
     pcv_octree* local = nullptr;
-    bool fused = k == 2 && !std::getenv("PCV_NO_FUSED_PASS");
+    // Measured on 8 x B200 (1e9 points per GPU): with 56 of a sender's 64 buckets in peer memory the fused pass's short remote runs
+    // (28 records per bucket and tile) collapse the NVLink store rate (315 ms against 22 ms on two GPUs), while the exchange of
+    // ingested records - 7 long runs per tile - holds 515 GB/s per GPU (28.9 ms).  So the fused pass is the default up to two
+    // ranks; PCV_FUSED_PASS=1 forces it, PCV_NO_FUSED_PASS=1 disables it.
+    bool fused = k == 2 && !std::getenv("PCV_NO_FUSED_PASS") && (R <= 2 || std::getenv("PCV_FUSED_PASS"));
     if (fused) {
         std::vector<uint64_t> first_bins(64, 0), slots((size_t)R, 0);
         std::vector<pcv_shard_bufs> dst((size_t)R);

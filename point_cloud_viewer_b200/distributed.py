@@ -379,8 +379,9 @@ class LazyIndex:
     so the block a source rank wrote into this rank's slab holds, in order, exactly those of its points whose destination is
     this rank - each source lists their global indices from its per-point destination array and one all-to-all delivers them."""
 
-    def __init__(self, ctx, send, index_base, n_local, M, comm):
+    def __init__(self, ctx, send, index_base, n_local, M, comm, n_recv=None):
         self.ctx, self.send, self.base, self.n_local, self.M, self.comm = ctx, send, int(index_base), int(n_local), M, comm
+        self.n_recv = n_recv
         self.value = None
 
     def resolve(self):
@@ -392,6 +393,8 @@ class LazyIndex:
         ptr, n = self.ctx.shard_send_dest(self.send)
         dest = torch.as_tensor(_RawCuda(ptr, (max(n, 1),), "|u1"), device=dev)[:n] if n else torch.zeros(0, dtype=torch.uint8, device=dev)
         parts = [torch.nonzero(dest == d).flatten() + self.base for d in range(comm.world)]
+        if self.M is None:  # count matrix from the per-point destinations (collective)
+            self.M = np.asarray(comm.all_gather_counts(np.array([int(p.numel()) for p in parts], np.int64))).reshape(comm.world, comm.world)
         send = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
         sc, rc = [int(v) for v in self.M[comm.rank]], [int(v) for v in self.M[:, comm.rank]]
         assert [int(p.numel()) for p in parts] == sc, "destination array and count matrix disagree"
@@ -399,7 +402,7 @@ class LazyIndex:
         return self.value
 
     def numel(self):
-        return int(self.M[:, self.comm.rank].sum())
+        return int(self.n_recv) if self.M is None else int(self.M[:, self.comm.rank].sum())
 
 
 class LazyCellIndex(LazyIndex):
@@ -831,11 +834,7 @@ def build_octree_sharded_native(ctx, x, y, z, rgb, intensity, index_base, resolu
     if ctx.shard_send_cells(send) is not None:  # the fused exchange pass ran
         r_idx = LazyCellIndex(ctx, send, index_base, n, c2r, n_recv, comm)
     else:
-        ptr, nd = ctx.shard_send_dest(send)
-        dest = torch.as_tensor(_RawCuda(ptr, (max(nd, 1),), "|u1"), device=x.device)[:nd] if nd else torch.zeros(0, dtype=torch.uint8, device=x.device)
-        sc = torch.bincount(dest.to(torch.int64), minlength=comm.world).cpu().numpy().astype(np.int64)
-        M = np.asarray(comm.all_gather_counts(sc)).reshape(comm.world, comm.world)
-        r_idx = LazyIndex(ctx, send, index_base, n, M, comm)
+        r_idx = LazyIndex(ctx, send, index_base, n, None, comm, n_recv)  # the count matrix is derived on first use
     lazy_slots = {}
     meta = local.meta
     idx_mask = (1 << 60) - 1
