@@ -138,6 +138,9 @@ struct BuildState {
     int32_t plan_error, pad0;
     uint64_t arena_used;
     uint32_t deepest_level, pad;
+    // totals of the subsample plan (finish_layout): what the host needs to size the outputs and launch the placement
+    uint32_t nleaves, place_tiles;
+    uint64_t out_points, xyz_bytes, algo_xyz;
     PassState pass[kMaxPasses + 1];
 };
 enum : int32_t { kErrHistMismatch = 1, kErrTooDeep = 2, kErrCapacity = 3 };
@@ -210,6 +213,7 @@ struct PassArgs {
     BucketDesc* buckets;    // [active][nbins]
     PlanRun* plan_runs;  // [active] per-node demand, then bases (device backends that plan in several kernels)
     DevNode* nodes;
+    int32_t* children;  // [cap_nodes][8] index of every node's children, -1 if absent (read by the subsample plan); may be null
     uint32_t cap_active, cap_nodes, cap_tiles, cap_chunks;
     // split rule (generation.rs:128-150) + sharding
     uint64_t max_points;
@@ -324,7 +328,7 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
         if (EMIT) bk[nlocal] = bd;
         ++nlocal;
     };
-    auto emit_node = [&](uint32_t ni, uint64_t ihi, uint64_t ilo, int level, const double m[3], uint64_t cnt, bool leaf) {
+    auto emit_node = [&](uint32_t ni, uint32_t parent, uint64_t ihi, uint64_t ilo, int level, const double m[3], uint64_t cnt, bool leaf) {
         if (!EMIT || ni >= a.cap_nodes) return;
         DevNode& d = a.nodes[ni];
         d.index_hi = ihi;
@@ -333,9 +337,13 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
         d.count = cnt;
         d.arena_off = 0;
         d.level = level;
-        d.parent = (int32_t)act.node;
+        d.parent = (int32_t)parent;
         d.leaf = leaf ? 1 : 0;
         d.pad = 0;
+        if (a.children) {
+            for (int q = 0; q < 8; ++q) a.children[(size_t)ni * 8 + q] = -1;
+            a.children[(size_t)parent * 8 + (size_t)(ilo & 7u)] = (int32_t)ni;
+        }
     };
     // should_split_node (generation.rs:128-150); nodes of levels <= k of a sharded build decide on the global counts
     auto should_split = [&](int level, uint64_t ihi, uint64_t ilo, uint64_t cnt) {
@@ -357,7 +365,7 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
         const double m1[3] = {(k & 4) ? pn.m[0] + e1 : pn.m[0], (k & 2) ? pn.m[1] + e1 : pn.m[1], (k & 1) ? pn.m[2] + e1 : pn.m[2]};
         const bool split1 = should_split(l1, i1hi, i1lo, cnt1);
         const uint32_t c1 = run.nodes++;
-        emit_node(c1, i1hi, i1lo, l1, m1, cnt1, !split1);
+        emit_node(c1, act.node, i1hi, i1lo, l1, m1, cnt1, !split1);
         if (split1 && a.G == 2) {
             for (int k2 = 0; k2 < 8; ++k2) {
                 const uint64_t cnt2 = nb[k * 8 + k2];
@@ -368,8 +376,7 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
                 const double m2[3] = {(k2 & 4) ? m1[0] + e2 : m1[0], (k2 & 2) ? m1[1] + e2 : m1[1], (k2 & 1) ? m1[2] + e2 : m1[2]};
                 const bool split2 = should_split(l2, i2hi, i2lo, cnt2);
                 const uint32_t c2 = run.nodes++;
-                emit_node(c2, i2hi, i2lo, l2, m2, cnt2, !split2);
-                if (EMIT && c2 < a.cap_nodes) a.nodes[c2].parent = (int32_t)c1;
+                emit_node(c2, c1, i2hi, i2lo, l2, m2, cnt2, !split2);
                 route(c2, l2, m2, cnt2, split2, k * 8 + k2, k * 8 + k2 + 1, 2);
             }
         } else {
@@ -378,6 +385,92 @@ PCV_HD void plan_active(const PassArgs& a, uint32_t ai, PlanRun& run, int32_t& e
     }
     if (EMIT)
         for (int lb = (int)nlocal; lb < a.nbins; ++lb) bk[lb] = BucketDesc{};
+}
+
+// ---- subsample plan, on the device (closed form of generation.rs:195-253,335-387; see the header) ---------------------------------
+// Bottom-up over the levels: n(X) = size of X when it is subsampled into its parent (a leaf: its points; an inner node: the sum of
+// ceil(n(child) / 8) over its children in child order, which also gives every child its offset inside the parent), then one scan
+// over the nodes in creation order for the output layout and the leaf-tile index of the placement.
+struct FinishArgs {
+    BuildState* st;
+    const DevNode* nodes;
+    const int32_t* children;    // [nodes][8]
+    uint64_t* nsub;             // [nodes]
+    uint64_t* final_count;      // [nodes]
+    DNode* dn;                  // [nodes]
+    uint32_t* leaf_tile_begin;  // [nodes + 1]
+    uint32_t* leaf_node;        // [nodes]
+    int shard_k;
+    int level;                  // finish_node sweep: the level being processed
+    LevelTable lv;
+};
+PCV_HD void finish_node(const FinishArgs& f, uint32_t i) {
+    const DevNode& nd = f.nodes[i];
+    uint64_t ns;
+    if (nd.leaf) {
+        ns = nd.count;
+    } else {
+        uint64_t off = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int32_t c = f.children[(size_t)i * 8 + k];
+            if (c < 0) continue;
+            f.dn[c].off_in_parent = off;
+            off += (f.nsub[c] + 7) / 8;  // every 8th point by current index: ceil(n / 8)
+        }
+        ns = off;
+        if (f.shard_k && nd.level < f.shard_k - 1) ns = 0;  // above the collectors of a sharded build: assembled elsewhere
+    }
+    f.nsub[i] = ns;
+    const bool collector = f.shard_k && nd.level == f.shard_k - 1;
+    f.final_count[i] = (nd.parent < 0 || collector) ? ns : ns - (ns + 7) / 8;
+}
+// One node of the layout scan: the running offsets are the exclusive prefixes over the nodes before it (creation order).
+PCV_HD void finish_emit(const FinishArgs& f, uint32_t i, uint64_t point_off, uint64_t xyz_off, uint32_t leaf_ord, uint32_t tile_begin) {
+    const DevNode& nd = f.nodes[i];
+    DNode& d = f.dn[i];
+    d.m[0] = nd.m[0], d.m[1] = nd.m[1], d.m[2] = nd.m[2];
+    d.e = f.lv.edge[nd.level];
+    d.ry = f.lv.ry[nd.level];  // RN(1 / e)
+    if (nd.parent < 0) d.off_in_parent = 0;
+    d.out_point_off = point_off;
+    d.out_xyz_off = xyz_off;  // node .xyz blocks are 16-byte aligned inside the device array
+    d.arena_off = nd.arena_off;
+    d.count = nd.leaf ? nd.count : 0;
+    const bool collector = f.shard_k && nd.level == f.shard_k - 1;
+    d.parent = collector ? -1 : nd.parent;  // a collector ends the up-walk like the root does
+    d.enc = f.lv.enc[nd.level];
+    if (nd.leaf) {
+        f.leaf_tile_begin[leaf_ord] = tile_begin;
+        f.leaf_node[leaf_ord] = i;
+    }
+}
+PCV_HD uint64_t finish_xyz_bytes(const FinishArgs& f, uint32_t i) { return f.final_count[i] * 3 * (uint64_t)enc_bytes(f.lv.enc[f.nodes[i].level]); }
+// sequential form (test backend; the CUDA backend runs the same two functions from kernels)
+inline void finish_plan_seq(FinishArgs f, int last_level) {
+    const uint32_t n = f.st->nnodes;
+    for (int L = last_level; L >= 0; --L)
+        for (uint32_t i = 0; i < n; ++i)
+            if (f.nodes[i].level == L) finish_node(f, i);
+    uint64_t poff = 0, boff = 0, algo = 0, last_end = 0;
+    uint32_t nleaves = 0, tiles = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t b = finish_xyz_bytes(f, i);
+        finish_emit(f, i, poff, boff, nleaves, tiles);
+        if (f.nodes[i].leaf) {
+            ++nleaves;
+            tiles += (uint32_t)((f.nodes[i].count + kPlaceTile - 1) / kPlaceTile);
+        }
+        poff += f.final_count[i];
+        last_end = boff + b;
+        boff += (b + 15) & ~15ull;
+        algo += b;
+    }
+    f.leaf_tile_begin[nleaves] = tiles;
+    f.st->nleaves = nleaves;
+    f.st->place_tiles = tiles;
+    f.st->out_points = poff;
+    f.st->xyz_bytes = last_end;
+    f.st->algo_xyz = algo;
 }
 
 struct Backend {
@@ -391,6 +484,10 @@ struct Backend {
     virtual void pass(const PassArgs& a) = 0;       // digit histogram + scan + plan + partition of one pass (asynchronous)
     virtual void hist_scan(const PassArgs& a) {}    // only the digit histogram + scan of a pass (sharded build: the sender's side)
     virtual void plan(const PassArgs& a) {}         // only the planner of a pass (sharded build: the owner's side of the fused exchange pass)
+    virtual void finish_plan(const FinishArgs& f, int last_level) = 0;  // the subsample plan (asynchronous)
+    // asynchronous read-back into backend-owned host memory: valid after d2h_wait(); at most kReadSlots copies between two waits
+    virtual const void* d2h_begin(const void* d, size_t bytes) = 0;
+    virtual void d2h_wait() = 0;
     virtual void place(const PlaceArgs& a) = 0;
     virtual void mark(int what) {}  // timing hooks: 0 partition start, 1 partition end / place start, 2 place end
     virtual void pass_points(int pass, uint64_t npoints, uint64_t leaf_points) {}  // profiling: live point counts, known after the read-back
@@ -628,6 +725,12 @@ class BuildPlan {
             BucketDesc* buckets = (BucketDesc*)dalloc((size_t)cap_active * 64 * sizeof(BucketDesc));
             PlanRun* plan_runs = (PlanRun*)dalloc((size_t)cap_active * sizeof(PlanRun));
             DevNode* d_nodes = (DevNode*)dalloc((size_t)cap_nodes * sizeof(DevNode));
+            int32_t* d_children = (int32_t*)dalloc((size_t)cap_nodes * 8 * sizeof(int32_t));
+            uint64_t* d_nsub = (uint64_t*)dalloc((size_t)cap_nodes * 8);
+            uint64_t* d_final = (uint64_t*)dalloc((size_t)cap_nodes * 8);
+            DNode* d_dn = (DNode*)dalloc((size_t)cap_nodes * sizeof(DNode));
+            uint32_t* d_ltb = (uint32_t*)dalloc(((size_t)cap_nodes + 1) * 4);
+            uint32_t* d_leaf_node = (uint32_t*)dalloc((size_t)cap_nodes * 4);
             uint64_t* d_shard = nullptr;
             if (shard.k) {
                 const size_t ncount = ShardSpec::level_offset(shard.k + 1);
@@ -649,6 +752,8 @@ class BuildPlan {
             root.level = 0;
             root.parent = -1;
             be.h2d(d_nodes, &root, sizeof root);
+            const int32_t no_children[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+            be.h2d(d_children, no_children, sizeof no_children);
             ActiveDesc a0{};
             for (int a = 0; a < 3; ++a) a0.m[a] = bmin[a];
             a0.e = E;
@@ -711,6 +816,7 @@ class BuildPlan {
                 pa.buckets = buckets;
                 pa.plan_runs = plan_runs;
                 pa.nodes = d_nodes;
+                pa.children = d_children;
                 pa.cap_active = cap_active;
                 pa.cap_nodes = cap_nodes;
                 pa.cap_tiles = cap_tiles;
@@ -735,6 +841,19 @@ class BuildPlan {
                     if (hs.error || hs.pass[p + 1].nactive == 0) break;
                 }
             }
+            // ---- subsample plan on the device, enqueued behind the last pass: the host only reads totals before the placement ----
+            FinishArgs fa{};
+            fa.st = d_st;
+            fa.nodes = d_nodes;
+            fa.children = d_children;
+            fa.nsub = d_nsub;
+            fa.final_count = d_final;
+            fa.dn = d_dn;
+            fa.leaf_tile_begin = d_ltb;
+            fa.leaf_node = d_leaf_node;
+            fa.shard_k = shard.k;
+            fa.lv = lv;
+            be.finish_plan(fa, lv.last_level);
             be.mark(1);
             const auto tw0 = std::chrono::steady_clock::now();
             be.d2h(&hs, d_st, sizeof hs);
@@ -752,18 +871,68 @@ class BuildPlan {
                 }
                 throw BuildError(-2, "internal: the split phase lost points");
             }
+            if (hs.out_points != N) throw BuildError(-2, "internal: subsample plan does not conserve points");
             for (size_t p = 0; p < launched; ++p) {
                 if (hs.pass[p].nactive) R.passes++;
                 be.pass_points((int)p, hs.pass[p].npoints, hs.pass[p].npoints - hs.pass[p + 1].npoints);
             }
             R.deepest_level = hs.deepest_level;
-
-            const auto tp0 = std::chrono::steady_clock::now();
-            std::vector<DevNode> dv(hs.nnodes);
-            be.d2h(dv.data(), d_nodes, (size_t)hs.nnodes * sizeof(DevNode));
-            nodes.resize(hs.nnodes);
-            for (uint32_t i = 0; i < hs.nnodes; ++i) {
-                const DevNode& d = dv[i];
+            const auto ts0 = std::chrono::steady_clock::now();
+            // the ping-pong buffers and the planner's tables are dead now; the arena and the plan's tables live until the placement is done
+            auto keep = [&](void* q) {
+                return q == arena || q == (void*)col_arena || q == (void*)d_nodes || q == (void*)d_dn || q == (void*)d_nsub || q == (void*)d_final || q == (void*)d_ltb ||
+                       q == (void*)d_leaf_node;
+            };
+            for (auto& q : owned) {
+                if (q && !keep(q)) {  // (a fused build's arena is the caller's and not in `owned`)
+                    be.dfree(q);
+                    q = nullptr;
+                }
+            }
+            // node tables for the host-side octree object: their read-back is enqueued BEFORE the placement and consumed while it runs
+            const uint32_t nn = hs.nnodes;
+            const DevNode* hv = (const DevNode*)be.d2h_begin(d_nodes, (size_t)nn * sizeof(DevNode));
+            const DNode* hd = (const DNode*)be.d2h_begin(d_dn, (size_t)nn * sizeof(DNode));
+            const uint64_t* hns = (const uint64_t*)be.d2h_begin(d_nsub, (size_t)nn * 8);
+            const uint64_t* hfc = (const uint64_t*)be.d2h_begin(d_final, (size_t)nn * 8);
+            R.xyz_bytes = hs.xyz_bytes;
+            R.algorithmic_bytes = 27ull * pts.n + hs.algo_xyz + 3ull * pts.n + (pts.intensity ? 8ull * pts.n : 0ull);
+            R.d_xyz = (uint8_t*)be.dmalloc(hs.xyz_bytes + 32);  // + slack: the query kernels stage whole 16-byte granules
+            R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
+            R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);
+            R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
+            PlaceArgs pl{};
+            pl.wide = wide;
+            pl.pts = pts;
+            pl.arena = arena;
+            pl.col_arena = col_arena;
+            pl.fast = lv.fast;
+            pl.d_nodes = d_dn;
+            pl.d_leaf_tile_begin = d_ltb;
+            pl.d_leaf_node = d_leaf_node;
+            pl.nleaves = hs.nleaves;
+            pl.ntiles = hs.place_tiles;
+            pl.npoints = pts.n;
+            pl.xyz_bytes = hs.algo_xyz;
+            pl.out_xyz = R.d_xyz;
+            pl.out_rgb = R.d_rgb;
+            pl.out_intensity = R.d_intensity;
+            pl.out_src = R.d_src;
+            const auto ts1 = std::chrono::steady_clock::now();
+            be.place(pl);
+            be.mark(2);
+            // ---- host-side node table (while the placement runs) ----
+            be.d2h_wait();
+            const auto ts2 = std::chrono::steady_clock::now();
+            nodes.resize(nn);
+            struct SortKey {
+                uint64_t hi, lo;  // NodeId = level << 120 | index (node.rs:108-111)
+                uint32_t i;
+            };
+            std::vector<SortKey> keys(nn);
+            for (uint32_t i = 0; i < nn; ++i) {
+                const DevNode& d = hv[i];
+                keys[i] = SortKey{((uint64_t)d.level << 56) | d.index_hi, d.index_lo, i};
                 HNode& x = nodes[i];
                 x = HNode{};
                 x.index = ((u128)d.index_hi << 64) | d.index_lo;
@@ -776,138 +945,35 @@ class BuildPlan {
                 for (int a = 0; a < 3; ++a) x.m[a] = d.m[a];
                 x.e = lv.edge[d.level];
                 x.enc = lv.enc[d.level];
+                x.n_sub = hns[i];
+                x.off_in_parent = hd[i].off_in_parent;
+                x.final_count = hfc[i];
+                x.out_point_off = hd[i].out_point_off;
+                x.out_xyz_off = hd[i].out_xyz_off;
                 if (d.parent >= 0) nodes[d.parent].child[(int)(d.index_lo & 7)] = (int)i;
             }
-            R.host_ms_plan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
-            // the ping-pong buffers and the planner's tables are dead now; the arena lives until the placement is done
-            for (auto& p : owned) {
-                if (p && p != arena && p != (void*)col_arena) {  // (a fused build's arena is the caller's and not in `owned`)
-                    be.dfree(p);
-                    p = nullptr;
+            // nodes sorted by NodeId (level << 120 | index); the device arrays are laid out in node creation order
+            std::sort(keys.begin(), keys.end(), [](const SortKey& a, const SortKey& b) { return a.hi != b.hi ? a.hi < b.hi : a.lo < b.lo; });
+            R.sorted.resize(nn);
+            for (uint32_t i = 0; i < nn; ++i) R.sorted[i] = (int)keys[i].i;
+            const auto ts3 = std::chrono::steady_clock::now();
+            for (auto& q : owned) {
+                if (q) {
+                    be.dfree(q);
+                    q = nullptr;
                 }
             }
+            auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            R.host_ms_plan += tms(ts0, ts1) + tms(ts2, ts3);
+            if (std::getenv("PCV_TIMING"))
+                fprintf(stderr, "[pcv timing] setup %.2f  passes %u  wait %.2f | frees + output allocation %.2f  table read-back %.2f  host node table %.2f (overlaps the placement)  (nodes %zu, leaf tiles %u)\n",
+                        ms_setup, R.passes, R.host_ms_wait, tms(ts0, ts1), tms(ts1, ts2), tms(ts2, ts3), nodes.size(), hs.place_tiles);
         } catch (...) {
-            for (void* p : owned)
-                if (p) be.dfree(p);
+            for (void* q : owned)
+                if (q) be.dfree(q);
+            be.dfree(R.d_xyz), be.dfree(R.d_rgb), be.dfree(R.d_src), be.dfree(R.d_intensity);
             throw;
         }
-        owned.clear();
-
-        const bool dbg = std::getenv("PCV_TIMING") != nullptr;
-        auto tnow = []() { return std::chrono::steady_clock::now(); };
-        auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        const auto ts0 = tnow();
-        std::vector<void*> scratch;
-        auto free_scratch = [&]() {
-            for (void* p : scratch) be.dfree(p);
-            scratch.clear();
-        };
-        // ---- subsample plan: closed form of generation.rs:195-253,335-387 ----
-        for (size_t i = nodes.size(); i-- > 0;) {
-            HNode& x = nodes[i];
-            if (x.leaf) {
-                x.n_sub = x.count;
-            } else {
-                uint64_t off = 0;
-                for (int k = 0; k < 8; ++k) {
-                    if (x.child[k] < 0) continue;
-                    HNode& c = nodes[x.child[k]];
-                    c.off_in_parent = off;
-                    off += (c.n_sub + 7) / 8;  // every 8th point by current index: ceil(n/8)
-                }
-                x.n_sub = off;
-                if (shard.k && x.level < shard.k - 1) x.n_sub = 0;  // above the collectors: assembled elsewhere
-            }
-        }
-        auto is_collector = [&](const HNode& x) { return shard.k && x.level == shard.k - 1; };
-        for (auto& x : nodes) x.final_count = (x.parent < 0 || is_collector(x)) ? x.n_sub : x.n_sub - (x.n_sub + 7) / 8;
-
-        const auto ts1 = tnow();
-        // ---- output layout: nodes sorted by NodeId (level << 120 | index) ----
-        // (the device arrays are laid out in node creation order; the NodeId-sorted table is produced while the place
-        // kernel runs)
-        uint64_t poff = 0, boff = 0, algo_xyz = 0;
-        for (size_t i = 0; i < nodes.size(); ++i) {
-            HNode& x = nodes[i];
-            x.out_point_off = poff;
-            boff = (boff + 15) & ~15ull;  // node .xyz blocks are 16-byte aligned inside the device array
-            x.out_xyz_off = boff;
-            poff += x.final_count;
-            boff += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
-            algo_xyz += x.final_count * 3 * (uint64_t)enc_bytes(x.enc);
-        }
-        if (poff != pts.n) {
-            if (!fused) be.dfree(arena), be.dfree(col_arena);
-            throw BuildError(-2, "internal: subsample plan does not conserve points");
-        }
-        R.xyz_bytes = boff;
-        R.algorithmic_bytes = 27ull * pts.n + algo_xyz + 3ull * pts.n + (pts.intensity ? 8ull * pts.n : 0ull);
-
-        const auto ts2 = tnow();
-        // ---- place ----
-        std::vector<DNode> dn(nodes.size());
-        std::vector<uint32_t> leaf_tile_begin, leaf_node;
-        leaf_tile_begin.reserve(nodes.size() + 1);
-        leaf_node.reserve(nodes.size());
-        uint32_t nplace_tiles = 0;
-        for (size_t i = 0; i < nodes.size(); ++i) {
-            const HNode& x = nodes[i];
-            DNode& d = dn[i];
-            for (int a = 0; a < 3; ++a) d.m[a] = x.m[a];
-            d.e = x.e;
-            d.ry = 1.0 / x.e;
-            d.off_in_parent = x.off_in_parent;
-            d.out_point_off = x.out_point_off;
-            d.out_xyz_off = x.out_xyz_off;
-            d.arena_off = x.arena_off;
-            d.count = x.leaf ? x.count : 0;
-            d.parent = is_collector(x) ? -1 : x.parent;  // a collector ends the up-walk like the root does
-            d.enc = x.enc;
-            if (x.leaf) {
-                leaf_tile_begin.push_back(nplace_tiles);
-                leaf_node.push_back((uint32_t)i);
-                nplace_tiles += (uint32_t)((x.count + kPlaceTile - 1) / kPlaceTile);
-            }
-        }
-        leaf_tile_begin.push_back(nplace_tiles);
-        const auto ts3 = tnow();
-        R.d_xyz = (uint8_t*)be.dmalloc(boff + 32);  // + slack: the query kernels stage whole 16-byte granules
-        R.d_rgb = (uint8_t*)be.dmalloc((size_t)pts.n * 3);
-        R.d_src = (uint32_t*)be.dmalloc((size_t)pts.n * 4 + 64);
-        R.d_intensity = pts.intensity ? (float*)be.dmalloc((size_t)pts.n * 4) : nullptr;
-        const auto ts4 = tnow();
-        PlaceArgs pl{};
-        pl.wide = wide;
-        pl.pts = pts;
-        pl.arena = arena;
-        pl.col_arena = col_arena;
-        pl.fast = lv.fast;
-        pl.d_nodes = upload(dn, scratch);
-        pl.d_leaf_tile_begin = upload(leaf_tile_begin, scratch);
-        pl.d_leaf_node = upload(leaf_node, scratch);
-        pl.nleaves = (uint32_t)leaf_node.size();
-        pl.ntiles = nplace_tiles;
-        pl.npoints = pts.n;
-        pl.xyz_bytes = algo_xyz;
-        pl.out_xyz = R.d_xyz;
-        pl.out_rgb = R.d_rgb;
-        pl.out_intensity = R.d_intensity;
-        pl.out_src = R.d_src;
-        const auto ts5 = tnow();
-        be.place(pl);
-        be.mark(2);
-        R.sorted.resize(nodes.size());
-        for (size_t i = 0; i < nodes.size(); ++i) R.sorted[i] = (int)i;
-        std::sort(R.sorted.begin(), R.sorted.end(), [&](int a, int b) {
-            if (nodes[a].level != nodes[b].level) return nodes[a].level < nodes[b].level;
-            return nodes[a].index < nodes[b].index;
-        });
-        free_scratch();
-        if (!fused) be.dfree(arena), be.dfree(col_arena);
-        R.host_ms_plan += tms(ts0, ts5);
-        if (dbg)
-            fprintf(stderr, "[pcv timing] setup %.2f  passes %u  wait %.2f | plan %.2f  layout+sort %.2f  tables %.2f  alloc %.2f  upload %.2f  (nodes %zu, leaf tiles %zu)\n", ms_setup, R.passes,
-                    R.host_ms_wait, tms(ts0, ts1), tms(ts1, ts2), tms(ts2, ts3), tms(ts3, ts4), tms(ts4, ts5), nodes.size(), (size_t)nplace_tiles);
         return R;
     }
 };

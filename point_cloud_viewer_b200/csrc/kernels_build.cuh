@@ -532,6 +532,90 @@ __global__ void __launch_bounds__(kPlanNodeThreads) k_plan_emit(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// subsample plan (build_host.hpp finish_node / finish_emit): one small launch per level, bottom-up, then one block that scans
+// the nodes in creation order (output offsets, leaf ordinals, first placement tile of every leaf) and leaves the totals in the
+// build state
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sub_level(const __grid_constant__ FinishArgs f) {
+    const uint32_t n = f.st->nnodes;
+    if (f.st->error) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (f.nodes[i].level == f.level) finish_node(f, i);
+}
+// exclusive block scan of K values per thread at once (one set of barriers)
+template <int K>
+__device__ __forceinline__ void block_excl_scan_k(uint64_t (&v)[K], uint64_t (*sh)[33], uint64_t (&total)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        incl[q] = v[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, incl[q], o);
+            if (lane >= o) incl[q] += u;
+        }
+    }
+    __syncthreads();  // sh may still be read from the previous call
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) sh[q][warp] = incl[q];
+    }
+    __syncthreads();
+    if (warp < K) {
+        uint64_t w = sh[warp][lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        sh[warp][lane] = wi - w;
+        if (lane == 31) sh[warp][32] = wi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        total[q] = sh[q][32];
+        v[q] = incl[q] - v[q] + sh[q][warp];
+    }
+}
+
+__global__ void __launch_bounds__(kPlanThreads) k_sub_layout(const __grid_constant__ FinishArgs f) {
+    __shared__ uint64_t sh[5][33];
+    BuildState* st = f.st;
+    const uint32_t n = st->error ? 0u : st->nnodes;
+    uint64_t c_pts = 0, c_xyz = 0, c_leaf = 0, c_tile = 0, c_algo = 0;
+    for (uint32_t base = 0; base < n; base += kPlanThreads) {
+        const uint32_t i = base + threadIdx.x;
+        uint64_t fc = 0, b = 0, leaf = 0, tiles = 0;
+        if (i < n) {
+            fc = f.final_count[i];
+            b = finish_xyz_bytes(f, i);
+            if (f.nodes[i].leaf) {
+                leaf = 1;
+                tiles = (f.nodes[i].count + kPlaceTile - 1) / kPlaceTile;
+            }
+        }
+        uint64_t tot[5], v[5] = {fc, (b + 15) & ~15ull, leaf, tiles, b};
+        block_excl_scan_k<5>(v, sh, tot);
+        const uint64_t o_pts = c_pts + v[0], o_xyz = c_xyz + v[1], o_leaf = c_leaf + v[2], o_tile = c_tile + v[3];
+        if (i < n) {
+            finish_emit(f, i, o_pts, o_xyz, (uint32_t)o_leaf, (uint32_t)o_tile);
+            if (i == n - 1) st->xyz_bytes = o_xyz + b;
+        }
+        c_pts += tot[0], c_xyz += tot[1], c_leaf += tot[2], c_tile += tot[3], c_algo += tot[4];
+    }
+    if (threadIdx.x == 0) {
+        f.leaf_tile_begin[c_leaf] = (uint32_t)c_tile;
+        st->nleaves = (uint32_t)c_leaf;
+        st->place_tiles = (uint32_t)c_tile;
+        st->out_points = c_pts;
+        st->algo_xyz = c_algo;
+        if (n == 0) st->xyz_bytes = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pass: stable multi-way partition of every tile + the next pass's descent, in destination order
 // ------------------------------------------------------------------------------------------------
 // Persistent blocks of 8 warps, four per SM (independent barrier domains that cover each other's phases), tiles of 1792
@@ -1124,6 +1208,8 @@ struct CudaBackend : Backend {
     }
     ~CudaBackend() override {
         cache_release();
+        if (ev_back) cudaEventDestroy(ev_back);
+        for (auto& b : back_chunks) cudaFreeHost(b.p);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         if (pin) cudaFreeHost(pin);
@@ -1303,6 +1389,50 @@ struct CudaBackend : Backend {
         k_plan_scan<<<1, kPlanThreads, 0, stream>>>(a);
         k_plan_emit<<<pg, kPlanNodeThreads, 0, stream>>>(a);
         prof_end();
+    }
+    void finish_plan(const FinishArgs& f_in, int last_level) override {
+        FinishArgs f = f_in;
+        prof_begin(K_PLAN, 0);
+        for (int L = last_level; L >= 0; --L) {
+            f.level = L;
+            k_sub_level<<<sm_count() * 2, 256, 0, stream>>>(f);
+        }
+        k_sub_layout<<<1, kPlanThreads, 0, stream>>>(f);
+        prof_end();
+        launches += (uint64_t)last_level + 2;
+        PCV_CUDA_CHECK(cudaGetLastError());
+    }
+    // asynchronous read-backs into pinned chunks that never move (the caller keeps the returned pointers until d2h_wait)
+    struct BackChunk {
+        uint8_t* p;
+        size_t cap, off;
+    };
+    std::vector<BackChunk> back_chunks;
+    cudaEvent_t ev_back = nullptr;
+    const void* d2h_begin(const void* d, size_t bytes) override {
+        const size_t need = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+        BackChunk* c = nullptr;
+        for (auto& b : back_chunks)
+            if (b.off + need <= b.cap) {
+                c = &b;
+                break;
+            }
+        if (!c) {
+            BackChunk nb{nullptr, std::max<size_t>(need, (size_t)32 << 20), 0};
+            PCV_CUDA_CHECK(cudaMallocHost(&nb.p, nb.cap));
+            back_chunks.push_back(nb);
+            c = &back_chunks.back();
+        }
+        uint8_t* dst = c->p + c->off;
+        c->off += need;
+        if (bytes) PCV_CUDA_CHECK(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, stream));
+        if (!ev_back) PCV_CUDA_CHECK(cudaEventCreateWithFlags(&ev_back, cudaEventDisableTiming));
+        PCV_CUDA_CHECK(cudaEventRecord(ev_back, stream));
+        return dst;
+    }
+    void d2h_wait() override {
+        if (ev_back) PCV_CUDA_CHECK(cudaEventSynchronize(ev_back));
+        for (auto& b : back_chunks) b.off = 0;
     }
     void plan(const PassArgs& a) override {
         plan_launch(a);

@@ -19,6 +19,16 @@ struct CpuBackend : Backend {
     void dfree(void* p) override { std::free(p); }
     void h2d(void* d, const void* h, size_t b) override { std::memcpy(d, h, b); }
     void d2h(void* h, const void* d, size_t b) override { std::memcpy(h, d, b); }
+    // "device" memory is host memory here: the read-back is the buffer itself, kept alive by a private copy
+    std::vector<std::vector<uint8_t>> back;
+    const void* d2h_begin(const void* d, size_t b) override {
+        back.emplace_back((const uint8_t*)d, (const uint8_t*)d + b);
+        return back.back().data();
+    }
+    void d2h_wait() override {
+        if (back.size() > 16) back.erase(back.begin(), back.end() - 8);
+    }
+    void finish_plan(const FinishArgs& f, int last_level) override { finish_plan_seq(f, last_level); }
 
     static void load_rec(const void* base, uint64_t i, bool wide, uint64_t c[3], uint32_t& idx) {
         if (wide) {
