@@ -211,17 +211,29 @@ __device__ __forceinline__ void smem_load_rec(const unsigned char* srec, uint32_
 constexpr int kIngestThreads = 256;
 constexpr size_t kRgbStage = (size_t)kTilePoints * 3 + 32;
 
-template <bool WIDE, int FAST>
+// The coordinates of kIngestBatch points per thread are requested before the first of them is processed: the kernel is a
+// stream (27 B in, 21 B out per point) and lives on loads in flight, not on arithmetic.
+template <bool WIDE, int FAST, int kIngestBatch>
 __device__ __forceinline__ unsigned ingest_tile(const IngestArgs& a, uint64_t start, uint32_t count, const uint32_t* scol) {
     unsigned bad = 0;
     const double e0 = a.lv.edge[0], e1 = a.lv.edge[1], ry1 = a.lv.ry[1];
-    for (uint32_t i = threadIdx.x; i < count; i += kIngestThreads) {
+    for (uint32_t i0 = threadIdx.x; i0 < count; i0 += kIngestThreads * kIngestBatch) {
+      double qq[kIngestBatch][3];
+#pragma unroll
+      for (int u = 0; u < kIngestBatch; ++u) {
+          const uint32_t i = i0 + u * kIngestThreads;
+          const uint64_t g = start + (i < count ? i : i0);
+          // streamed once: bypass L1 (ld.global.cg)
+          qq[u][0] = __ldcg(a.pts.x + g * a.pts.stride);
+          qq[u][1] = __ldcg(a.pts.y + g * a.pts.stride);
+          qq[u][2] = __ldcg(a.pts.z + g * a.pts.stride);
+      }
+#pragma unroll
+      for (int u = 0; u < kIngestBatch; ++u) {
+        const uint32_t i = i0 + u * kIngestThreads;
+        if (i >= count) break;
         const uint64_t g = start + i;
-        double q[3], m[3] = {a.root_min[0], a.root_min[1], a.root_min[2]};
-        // streamed once: bypass L1 (ld.global.cg)
-        q[0] = __ldcg(a.pts.x + g * a.pts.stride);
-        q[1] = __ldcg(a.pts.y + g * a.pts.stride);
-        q[2] = __ldcg(a.pts.z + g * a.pts.stride);
+        double q[3] = {qq[u][0], qq[u][1], qq[u][2]}, m[3] = {a.root_min[0], a.root_min[1], a.root_min[2]};
         if (FAST == 2) bad |= input_bad(q[0]) | input_bad(q[1]) | input_bad(q[2]);
         typename std::conditional<WIDE, uint64_t, uint32_t>::type code[3];
         unsigned dig = 0;
@@ -235,11 +247,12 @@ __device__ __forceinline__ unsigned ingest_tile(const IngestArgs& a, uint64_t st
         store_rec<WIDE>(a.rec_out, g, c64, (uint32_t)g);
         a.col_out[g] = scol[i];
         a.dig_out[g] = (uint8_t)dig;
+      }
     }
     return bad;
 }
 
-template <bool WIDE>
+template <bool WIDE, int FASTMODE, int BATCH>  // FASTMODE = LevelTable::fast (a kernel per mode keeps the register budget for the loads in flight)
 __global__ void __launch_bounds__(kIngestThreads, 4) k_ingest(const __grid_constant__ IngestArgs a) {
     __shared__ __align__(16) uint8_t srgb[kRgbStage];
     __shared__ __align__(16) uint32_t scol[kTilePoints];
@@ -276,13 +289,13 @@ __global__ void __launch_bounds__(kIngestThreads, 4) k_ingest(const __grid_const
             }
             __syncthreads();
         }
-        if (a.lv.fast == 3) {
-            ingest_tile<WIDE, 3>(a, start, count, scol);  // power-of-two edges: exact for every input, nothing to repeat
-        } else if (a.lv.fast) {
-            const unsigned bad = a.lv.fast == 2 ? ingest_tile<WIDE, 2>(a, start, count, scol) : ingest_tile<WIDE, 1>(a, start, count, scol);
-            if (__syncthreads_or((int)bad)) ingest_tile<WIDE, 0>(a, start, count, scol);  // a numerator outside the proven range: IEEE operator (same stores)
+        if (FASTMODE == 3) {
+            ingest_tile<WIDE, 3, BATCH>(a, start, count, scol);  // power-of-two edges: exact for every input, nothing to repeat
+        } else if (FASTMODE) {
+            const unsigned bad = ingest_tile<WIDE, FASTMODE, BATCH>(a, start, count, scol);
+            if (__syncthreads_or((int)bad)) ingest_tile<WIDE, 0, BATCH>(a, start, count, scol);  // a numerator outside the proven range: IEEE operator (same stores)
         } else {
-            ingest_tile<WIDE, 0>(a, start, count, scol);
+            ingest_tile<WIDE, 0, BATCH>(a, start, count, scol);
         }
         __syncthreads();
     }
@@ -697,7 +710,15 @@ struct PassTile {  // descriptor of a staged tile (shared memory, 64 bytes)
 static_assert(sizeof(PassTile) == 64 && sizeof(ActiveDesc) == 64 && sizeof(PassBucket) == 32, "descriptor layout");
 
 // finish one record (see above).  All level constants are plain kernel parameters (PassArgs::e1 ...).
-template <bool WIDE, int FAST>
+// ENCU >= 0: every level the pass touches has this one encoding (the common case), so no switch per point
+#define PCV_ENC_SEL(encu, enc_value, ...)        \
+    if constexpr ((encu) >= 0) {                 \
+        constexpr int ENC = (encu);              \
+        __VA_ARGS__                              \
+    } else {                                     \
+        PCV_ENC_SWITCH(enc_value, __VA_ARGS__)   \
+    }
+template <bool WIDE, int FAST, int ENCU>
 __device__ __forceinline__ void finish_record(const PassArgs& a, const double pm[3], uint64_t c[3], unsigned dig, int keep, bool next, unsigned& dig_out,
                                               unsigned& bad) {
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type CodeT;
@@ -708,19 +729,19 @@ __device__ __forceinline__ void finish_record(const PassArgs& a, const double pm
     m[0] = (d1 & 4u) ? pm[0] + e1 : pm[0];
     m[1] = (d1 & 2u) ? pm[1] + e1 : pm[1];
     m[2] = (d1 & 1u) ? pm[2] + e1 : pm[2];
-    PCV_ENC_SWITCH(a.enc1, _Pragma("unroll") for (int k = 0; k < 3; ++k) q[k] = decode_axis<ENC>(c[k], m[k], e1);)
+    PCV_ENC_SEL(ENCU, a.enc1, _Pragma("unroll") for (int k = 0; k < 3; ++k) q[k] = decode_axis<ENC>(c[k], m[k], e1);)
     if (keep == 2) {
         const double e2 = a.e2, ry2 = a.ry2;
         m[0] = (d2 & 4u) ? m[0] + e2 : m[0];
         m[1] = (d2 & 2u) ? m[1] + e2 : m[1];
         m[2] = (d2 & 1u) ? m[2] + e2 : m[2];
         if (next) {
-            PCV_ENC_SWITCH(a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) {
+            PCV_ENC_SEL(ENCU, a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) {
                 c[k] = encode_axis<ENC, FAST>(q[k], m[k], e2, ry2, bad);
                 q[k] = decode_axis<ENC>(c[k], m[k], e2);
             })
         } else {
-            PCV_ENC_SWITCH(a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) c[k] = encode_axis<ENC, FAST>(q[k], m[k], e2, ry2, bad);)
+            PCV_ENC_SEL(ENCU, a.enc2, _Pragma("unroll") for (int k = 0; k < 3; ++k) c[k] = encode_axis<ENC, FAST>(q[k], m[k], e2, ry2, bad);)
             return;
         }
     }
@@ -730,16 +751,16 @@ __device__ __forceinline__ void finish_record(const PassArgs& a, const double pm
     CodeT code[3];
     unsigned d;
     if (a.Gn == 2) {
-        PCV_ENC_SWITCH(a.ench, d = level_step<ENC, FAST, true>(q, m, eb, eh, ryh, code, bad);)
+        PCV_ENC_SEL(ENCU, a.ench, d = level_step<ENC, FAST, true>(q, m, eb, eh, ryh, code, bad);)
         d = (d << 3) | level_digit(q, m, eh);
     } else {
-        PCV_ENC_SWITCH(a.ench, d = level_step<ENC, FAST, false>(q, m, eb, eh, ryh, code, bad);)
+        PCV_ENC_SEL(ENCU, a.ench, d = level_step<ENC, FAST, false>(q, m, eb, eh, ryh, code, bad);)
     }
     c[0] = (uint64_t)code[0], c[1] = (uint64_t)code[1], c[2] = (uint64_t)code[2];
     dig_out = d;
 }
 
-template <bool WIDE, int FAST, bool REMOTE>
+template <bool WIDE, int FAST, bool REMOTE, int ENCU>
 __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTile& pt, const unsigned char* srec, const uint32_t* scol, const uint8_t* sdig,
                                                 const uint32_t* perm, const PassBucket* bdst, const PassBucketExt* bext) {
     constexpr size_t recsz = PassSmem<WIDE>::rec_bytes;
@@ -762,7 +783,7 @@ __device__ __forceinline__ unsigned pass_finish(const PassArgs& a, const PassTil
             colour = scol[i];
         }
         unsigned dig_out = 0;
-        if (next || keep == 2) finish_record<WIDE, FAST>(a, pm, c, sdig[i], keep, next, dig_out, bad);
+        if (next || keep == 2) finish_record<WIDE, FAST, ENCU>(a, pm, c, sdig[i], keep, next, dig_out, bad);
         if (FAST == 1 && bad) continue;  // the block repeats the sweep with the IEEE operator
         if (REMOTE) {
             // The destination is the owner's memory.  A record that continues is stored in the wire format of the exchange
@@ -821,7 +842,9 @@ __device__ __forceinline__ void pass_make_desc(PassTile* desc, uint32_t tile, co
     desc->valid = 1;
 }
 
-template <bool WIDE, bool REMOTE>
+// FASTMODE = PassArgs::fast, ENCU = the pass's one encoding or -1 (mixed): a kernel per combination keeps the switches out of the
+// per-point code and the register budget on the work
+template <bool WIDE, bool REMOTE, int FASTMODE, int ENCU>
 __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_per_sm) k_pass(const __grid_constant__ PassArgs a) {
     constexpr int nbmax = kPassBins;
     constexpr int kThreads = PassCfg<WIDE>::threads, kWarps = PassCfg<WIDE>::warps, kWarpItems = PassCfg<WIDE>::warp_items, kSubRounds = PassCfg<WIDE>::sub_rounds;
@@ -1005,15 +1028,12 @@ __global__ void __launch_bounds__(PassCfg<WIDE>::threads, PassCfg<WIDE>::blocks_
         // (5) finish + store in destination order (speculatively through the reciprocal division; repeated with the IEEE
         // operator if any numerator of the block was outside the proven range - the stores are idempotent)
         mbar_wait(&mbar[2], it & 1u);  // records and colours: requested when the previous tile's sweep ended
-        if (a.fast == 3) {
-            pass_finish<WIDE, 3, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);  // power-of-two edges: exact scaling, nothing to repeat
-        } else if (a.fast == 2) {
-            pass_finish<WIDE, 2, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);  // no per-numerator checks: nothing to repeat
-        } else if (a.fast == 1) {
-            const unsigned bad = pass_finish<WIDE, 1, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
-            if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
+        if (FASTMODE == 1) {
+            const unsigned bad = pass_finish<WIDE, 1, REMOTE, ENCU>(a, pt, srec, scol, sdig, perm, bdst, bext);
+            if (__syncthreads_or((int)bad)) pass_finish<WIDE, 0, REMOTE, ENCU>(a, pt, srec, scol, sdig, perm, bdst, bext);
         } else {
-            pass_finish<WIDE, 0, REMOTE>(a, pt, srec, scol, sdig, perm, bdst, bext);
+            // 3: power-of-two edges, exact scaling; 2: no per-numerator checks; 0: IEEE division - nothing to repeat in any of them
+            pass_finish<WIDE, FASTMODE, REMOTE, ENCU>(a, pt, srec, scol, sdig, perm, bdst, bext);
         }
         __syncthreads();  // records, colours, perm and the tables are reused
         if (stage_next) pass_stage_big<WIDE>(a, descs[s ^ 1u], smem_raw, &mbar[2]);
@@ -1340,10 +1360,13 @@ struct CudaBackend : Backend {
         if (bytes) PCV_CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream));
     }
     static void allow_smem_all() {
-        cudaFuncSetAttribute(k_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
-        cudaFuncSetAttribute(k_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
-        cudaFuncSetAttribute(k_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<false>::bytes);
-        cudaFuncSetAttribute(k_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassSmem<true>::bytes);
+        for (int w = 0; w < 2; ++w)
+            for (int r = 0; r < 2; ++r)
+                for (int f = 0; f < 4; ++f)
+                    for (int e = -1; e <= ENC_F32; ++e) {
+                        const void* fn = pass_kernel(w != 0, r != 0, f, e);
+                        if (fn) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(w ? PassSmem<true>::bytes : PassSmem<false>::bytes));
+                    }
     }
     // prefetch distance = blocks resident at once (SMs x blocks per SM); 0 disables (PCV_NO_PREFETCH=1 for experiments)
     int sms = 0;
@@ -1363,10 +1386,23 @@ struct CudaBackend : Backend {
         const uint32_t grid = std::min<uint32_t>(a.ntiles, (uint32_t)sm_count() * 32u);
         const uint64_t rec = a.wide ? sizeof(RecW) : sizeof(RecN);
         prof_begin(K_INGEST, a.pts.n * (27 + rec + 4 + 1));
-        if (a.wide)
-            k_ingest<true><<<grid, kIngestThreads, 0, stream>>>(a);
-        else
-            k_ingest<false><<<grid, kIngestThreads, 0, stream>>>(a);
+        static const int batch = std::getenv("PCV_INGEST_BATCH") ? std::atoi(std::getenv("PCV_INGEST_BATCH")) : 2;  // 1: experiments
+#define PCV_INGEST(W, F)                                                 \
+    if (batch == 1)                                                      \
+        k_ingest<W, F, 1><<<grid, kIngestThreads, 0, stream>>>(a);      \
+    else                                                                 \
+        k_ingest<W, F, 2><<<grid, kIngestThreads, 0, stream>>>(a)
+        switch ((a.wide ? 4 : 0) + a.lv.fast) {
+            case 0: PCV_INGEST(false, 0); break;
+            case 1: PCV_INGEST(false, 1); break;
+            case 2: PCV_INGEST(false, 2); break;
+            case 3: PCV_INGEST(false, 3); break;
+            case 4: PCV_INGEST(true, 0); break;
+            case 5: PCV_INGEST(true, 1); break;
+            case 6: PCV_INGEST(true, 2); break;
+            default: PCV_INGEST(true, 3); break;
+        }
+#undef PCV_INGEST
         prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
@@ -1439,22 +1475,43 @@ struct CudaBackend : Backend {
         launches += 3;
         PCV_CUDA_CHECK(cudaGetLastError());
     }
+    // The instantiated partition kernels: wide records and the fused exchange pass only in the mixed-encoding form; narrow local
+    // passes also specialised for a single encoding (U8 / U16 / F32; ENC_* values 0..2).  Null: not instantiated.
+    template <bool W, bool R, int E>
+    static const void* pass_kernel_f(int fast) {
+        switch (fast) {
+            case 0: return (const void*)k_pass<W, R, 0, E>;
+            case 1: return (const void*)k_pass<W, R, 1, E>;
+            case 2: return (const void*)k_pass<W, R, 2, E>;
+            default: return (const void*)k_pass<W, R, 3, E>;
+        }
+    }
+    static const void* pass_kernel(bool wide, bool remote, int fast, int encu) {
+        if (wide) return encu >= 0 ? nullptr : (remote ? pass_kernel_f<true, true, -1>(fast) : pass_kernel_f<true, false, -1>(fast));
+        if (remote) return encu >= 0 ? nullptr : pass_kernel_f<false, true, -1>(fast);
+        switch (encu) {
+            case ENC_U8: return pass_kernel_f<false, false, ENC_U8>(fast);
+            case ENC_U16: return pass_kernel_f<false, false, ENC_U16>(fast);
+            case ENC_F32: return pass_kernel_f<false, false, ENC_F32>(fast);
+            default: return pass_kernel_f<false, false, -1>(fast);
+        }
+    }
     // the partition kernel of a pass; a.remote != null: the fused exchange pass of a sharded build (buckets in their owners' memory)
     void partition_launch(const PassArgs& a) {
         const int nsm = sm_count();
         prof_begin(K_PASS, 0, a.pass);
         const uint32_t gw = std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<true>::blocks_per_sm));
         const uint32_t gn = std::min<uint32_t>(a.cap_tiles, (uint32_t)(nsm * PassCfg<false>::blocks_per_sm));
-        if (a.remote) {
-            if (a.wide)
-                k_pass<true, true><<<gw, PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
-            else
-                k_pass<false, true><<<gn, PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
-        } else if (a.wide) {
-            k_pass<true, false><<<gw, PassCfg<true>::threads, PassSmem<true>::bytes, stream>>>(a);
-        } else {
-            k_pass<false, false><<<gn, PassCfg<false>::threads, PassSmem<false>::bytes, stream>>>(a);
-        }
+        // one encoding for every level this pass touches?  (level L+1, and L+2 / the next pass's first level when they are used)
+        int encu = a.enc1;
+        if (a.G == 2 && a.enc2 != encu) encu = -1;
+        if (a.Gn > 0 && a.ench != encu) encu = -1;
+        if (a.wide || a.remote || encu == ENC_F64 || std::getenv("PCV_PASS_GENERIC")) encu = -1;
+        const void* fn = pass_kernel(a.wide, a.remote != nullptr, a.fast, encu);
+        PassArgs arg = a;
+        void* params[1] = {&arg};
+        PCV_CUDA_CHECK(cudaLaunchKernel(fn, dim3(a.wide ? gw : gn), dim3(a.wide ? PassCfg<true>::threads : PassCfg<false>::threads), params,
+                                        a.wide ? PassSmem<true>::bytes : PassSmem<false>::bytes, stream));
         prof_end();
     }
     void partition(const PassArgs& a) {
