@@ -609,6 +609,8 @@ struct XrayArgs {
     const QTile* tiles;
     const uint8_t* xyz;
     double tmin[3], tdiag[3];
+    double rdiag[3];  // RN(1 / tdiag) for div_known (chain.h): the correctly rounded quotient without the division instruction
+    int div_ok;       // every tdiag is admissible for div_known (host check), else the IEEE operator
     double query_from_global[7];
     int has_q;
     uint32_t w, h;
@@ -616,6 +618,12 @@ struct XrayArgs {
     uint8_t* zover;    // w*h
     int* any;
 };
+
+// (p - tmin) / tdiag of one axis (process_point_data, generation.rs:108-127), bit-identical to the IEEE quotient
+__device__ __forceinline__ double xray_unit(const XrayArgs& a, int k, double p) {
+    const double d = p - a.tmin[k];
+    return a.div_ok ? div_known(d, a.tdiag[k], a.rdiag[k]) : d / a.tdiag[k];
+}
 
 // Rust `f64 as u32`: truncating, saturating, NaN -> 0.  cvt.rzi.u32.f64 saturates but returns 0x80000000 for NaN (measured).
 __device__ __forceinline__ uint32_t rust_as_u32_dev(double v) {
@@ -642,9 +650,9 @@ __global__ void __launch_bounds__(256) k_xray_accum(const __grid_constant__ Xray
             p[2] = q.z;
         }
         // process_point_data, generation.rs:108-127 (`as u32` saturates, NaN -> 0)
-        const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
-        const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
-        const uint32_t z = rust_as_u32_dev(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
+        const uint32_t x = rust_as_u32_dev(xray_unit(a, 0, p[0]) * (double)a.w);
+        const uint32_t y = rust_as_u32_dev((1. - xray_unit(a, 1, p[1])) * (double)a.h);
+        const uint32_t z = rust_as_u32_dev(xray_unit(a, 2, p[2]) * 1024.);
         if (x < a.w && y < a.h) {
             const size_t px = (size_t)y * a.w + x;
             if (z < 1024)
@@ -693,9 +701,9 @@ __global__ void __launch_bounds__(256) k_xray_bin(const __grid_constant__ XrayBi
                         p[0] = q.x, p[1] = q.y, p[2] = q.z;
                     }
                     // process_point_data, generation.rs:108-127 (`as u32` saturates, NaN -> 0)
-                    const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
-                    const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
-                    const uint32_t z = rust_as_u32_dev(((p[2] - a.tmin[2]) / a.tdiag[2]) * 1024.);
+                    const uint32_t x = rust_as_u32_dev(xray_unit(a, 0, p[0]) * (double)a.w);
+                    const uint32_t y = rust_as_u32_dev((1. - xray_unit(a, 1, p[1])) * (double)a.h);
+                    const uint32_t z = rust_as_u32_dev(xray_unit(a, 2, p[2]) * 1024.);
                     if (x < a.w && y < a.h) {
                         sub = (y / kXraySub) * b.sub_w + (x / kXraySub);
                         key = ((y % kXraySub) << 16) | ((x % kXraySub) << 11) | min(z, 1024u);
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(256) k_xray_bin(const __grid_constant__ XrayBi
     }
 }
 struct XraySubArgs {
-    const uint32_t* sub_id;     // [nsub_nonempty] sub-tile index
+    const uint32_t* sub_id;     // unused (every sub-tile has a block; empty ones leave at once)
     const uint32_t* sub_off;    // [nsub + 1] exclusive offsets into keys
     const uint32_t* keys;
     const uint8_t* grey;        // [1026]
@@ -731,20 +739,29 @@ struct XraySubArgs {
 __global__ void __launch_bounds__(512, 1) k_xray_subtile(const __grid_constant__ XraySubArgs b) {
     extern __shared__ __align__(16) uint32_t sbits[];  // [1024 pixels][32 words]
     __shared__ uint8_t sover[kXraySub * kXraySub];
-    const uint32_t sid = b.sub_id[blockIdx.x];
+    const uint32_t sid = blockIdx.x;
+    const uint32_t k0 = b.sub_off[sid], k1 = b.sub_off[sid + 1];
+    if (k1 == k0) return;  // no point falls into this sub-tile: its pixels stay transparent (the image is zero-initialised)
     const uint32_t px0 = (sid % b.sub_w) * kXraySub, py0 = (sid / b.sub_w) * kXraySub;
-    for (uint32_t i = threadIdx.x; i < kXraySub * kXraySub * 32; i += blockDim.x) sbits[i] = 0;
+    {
+        uint4* z4 = reinterpret_cast<uint4*>(sbits);
+        for (uint32_t i = threadIdx.x; i < kXraySub * kXraySub * 8; i += blockDim.x) z4[i] = make_uint4(0, 0, 0, 0);
+    }
     for (uint32_t i = threadIdx.x; i < kXraySub * kXraySub; i += blockDim.x) sover[i] = 0;
     __syncthreads();
-    const uint32_t k0 = b.sub_off[sid], k1 = b.sub_off[sid + 1];
-    for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-        const uint32_t key = __ldcs(b.keys + k);
+    auto put = [&](uint32_t key) {
         const uint32_t lp = (key >> 16) * kXraySub + ((key >> 11) & 31u), z = key & 2047u;
         if (z < 1024)
             atomicOr(&sbits[lp * 32 + (z >> 5)], 1u << (z & 31));
         else
             sover[lp] = 1;
+    };
+    uint32_t k = k0 + threadIdx.x;
+    for (; k + 3 * blockDim.x < k1; k += 4 * blockDim.x) {  // four independent loads in flight per thread
+        const uint32_t q0 = __ldcs(b.keys + k), q1 = __ldcs(b.keys + k + blockDim.x), q2 = __ldcs(b.keys + k + 2 * blockDim.x), q3 = __ldcs(b.keys + k + 3 * blockDim.x);
+        put(q0), put(q1), put(q2), put(q3);
     }
+    for (; k < k1; k += blockDim.x) put(__ldcs(b.keys + k));
     __syncthreads();
     // resolve: popcount of the pixel's bucket set -> grey (generation.rs:186-197)
     for (uint32_t lp = threadIdx.x; lp < kXraySub * kXraySub; lp += blockDim.x) {
@@ -819,8 +836,8 @@ __global__ void __launch_bounds__(256) k_xray_accum_attr(const __grid_constant__
             const V3 q = iso_apply(a.query_from_global, V3{p[0], p[1], p[2]});
             p[0] = q.x, p[1] = q.y, p[2] = q.z;
         }
-        const uint32_t x = rust_as_u32_dev(((p[0] - a.tmin[0]) / a.tdiag[0]) * (double)a.w);
-        const uint32_t y = rust_as_u32_dev((1. - ((p[1] - a.tmin[1]) / a.tdiag[1])) * (double)a.h);
+        const uint32_t x = rust_as_u32_dev(xray_unit(a, 0, p[0]) * (double)a.w);
+        const uint32_t y = rust_as_u32_dev((1. - xray_unit(a, 1, p[1])) * (double)a.h);
         if (!(x < a.w && y < a.h)) continue;
         const size_t px = (size_t)y * a.w + x;
         const uint64_t slot = nd.point_off + t.first + i;

@@ -674,7 +674,9 @@ static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const 
     for (int k = 0; k < 3; ++k) {
         a.tmin[k] = bmin[k];
         a.tdiag[k] = bmax[k] - bmin[k];
+        a.rdiag[k] = 1.0 / a.tdiag[k];
     }
+    a.div_ok = div_known_ok(a.tdiag[0]) && div_known_ok(a.tdiag[1]) && div_known_ok(a.tdiag[2]) ? 1 : 0;
     a.has_q = qfg ? 1 : 0;
     if (qfg) memcpy(a.query_from_global, qfg, sizeof(double) * 7);
     a.w = w;
@@ -746,23 +748,27 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
         k_xray_bin<1><<<grid, 256, 0, c->stream>>>(bin);
         c->be->launches += 3;
         CU(cudaGetLastError());
-        // the non-empty sub-tiles (host: 4 bytes per sub-tile)
-        std::vector<uint32_t> off((size_t)nsub + 1), ids;
-        c->be->d2h(off.data(), bin.sub_count, ((size_t)nsub + 1) * 4);
-        for (uint32_t i = 0; i < nsub; ++i)
-            if (off[i + 1] > off[i]) ids.push_back(i);
-        any = !ids.empty();
-        if (!ids.empty()) {
-            sb.sub_id = s.upload(ids.data(), ids.size());
-            sb.sub_off = bin.sub_count;
-            sb.keys = bin.keys;
-            const size_t sm = (size_t)kXraySub * kXraySub * 128;
+        // one block per sub-tile, enqueued without looking at the counts (an empty sub-tile's block leaves at once): no host
+        // round trip inside a tile
+        sb.sub_id = nullptr;
+        sb.sub_off = bin.sub_count;
+        sb.keys = bin.keys;
+        const size_t sm = (size_t)kXraySub * kXraySub * 128;
+        static bool attr_set[64] = {};
+        if (!attr_set[c->device & 63]) {
             CU(cudaFuncSetAttribute(k_xray_subtile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_xray_subtile<<<(uint32_t)ids.size(), 512, sm, c->stream>>>(sb);
-            c->be->launches++;
+            attr_set[c->device & 63] = true;
         }
+        k_xray_subtile<<<nsub, 512, sm, c->stream>>>(sb);
+        c->be->launches++;
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaGetLastError());
+        unsigned long long total = 0;
+        c->be->d2h(&total, dtot, 8);
+        any = total != 0;
+    } else {
+        CU(cudaEventRecord(e1, c->stream));
     }
-    CU(cudaEventRecord(e1, c->stream));
     CU(cudaGetLastError());
     c->be->d2h(rgba_out, sb.rgba, npix * 4);
     if (zbits_out) c->be->d2h(zbits_out, sb.zbits_out, npix * 128);
