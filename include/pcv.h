@@ -200,8 +200,9 @@ int pcv_xray_tile_attr(const pcv_octree* o, const double tile_min[3], const doub
 int pcv_prefix_histogram_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
                                 const double bbox_max[3], uint32_t k, uint64_t* counts_out /* 8^k, host */);
 /* The same histogram with find_bounding_box (generation.rs:256-270) of the local points folded into the one read of the
- * positions.  Both histogram calls keep the per-point cells on the context; a pack call over the same device arrays, box
- * and resolution reuses them instead of repeating the descent (the caller must not modify the points in between). */
+ * positions.  Both histogram calls keep the per-point cells on the context for exactly ONE following pack call over the same
+ * device arrays, box and resolution, which reuses them instead of repeating the descent and then drops them (the caller must not
+ * modify the points between the histogram and that pack; a pack without a fresh histogram recomputes the cells). */
 int pcv_prefix_histogram_bbox_device(pcv_ctx* ctx, const pcv_points* dev_points, double resolution, const double bbox_min[3],
                                      const double bbox_max[3], uint32_t k, uint64_t* counts_out, double data_min[3], double data_max[3]);
 int pcv_prefix_pack_device(pcv_ctx* ctx, const pcv_points* dev_points, const uint64_t* dev_global_index /* or NULL */,

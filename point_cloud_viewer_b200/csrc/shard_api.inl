@@ -92,6 +92,16 @@ static void attach_cells(pcv_ctx* c, PackArgs& a, double resolution, const doubl
     a.cells = c->shard_cells;
     a.cell_shift = 3 * (c->shard_cells_k - k);
 }
+// The cells of a histogram call serve exactly ONE pack: a caller that refills the same buffer (a caching allocator hands out the same
+// address and size every step) must not find the previous step's cells.  Called after the pack's kernels have been enqueued.
+static void release_cells(pcv_ctx* c) {
+    if (!c->shard_cells) return;
+    c->be->dfree(c->shard_cells);  // stream-ordered: the pack that reads them was enqueued before
+    c->shard_cells = nullptr;
+    c->shard_cells_x = nullptr;
+    c->shard_cells_n = 0;
+    c->shard_cells_k = 0;
+}
 
 int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgidx, uint64_t gidx_base, double resolution, const double bmin[3],
                            const double bmax[3], uint32_t k, const int32_t* cell_to_rank, uint32_t nranks, double* out_xyz, uint8_t* out_rgb,
@@ -131,6 +141,7 @@ int pcv_prefix_pack_device(pcv_ctx* c, const pcv_points* dp, const uint64_t* dgi
     k_pack_scatter<<<a.ntiles, 256, 0, c->stream>>>(a);
     c->be->launches += 3;
     CU(cudaGetLastError());
+    release_cells(c);
     // rank r's first slot = exclusive prefix at (r, tile 0); counts follow from consecutive starts
     std::vector<uint32_t> starts(nranks);
     for (uint32_t r = 0; r < nranks; ++r) c->be->d2h(&starts[r], a.counts + (size_t)r * a.ntiles, 4);
@@ -241,6 +252,7 @@ int pcv_prefix_pack_exchange_device(pcv_ctx* c, const pcv_points* dp, const uint
         k_pack_exchange_sorted<<<a.ntiles, 256, 0, c->stream>>>(a, d_pt);
     c->be->launches += 3;
     CU(cudaGetLastError());
+    release_cells(c);
     std::vector<uint32_t> starts(nranks);
     for (uint32_t r = 0; r < nranks; ++r) c->be->d2h(&starts[r], a.counts + (size_t)r * a.ntiles, 4);  // synchronises: the stores are out
     for (uint32_t r = 0; r < nranks; ++r) rank_counts_out[r] = (r + 1 < nranks ? starts[r + 1] : (uint32_t)n) - starts[r];
