@@ -36,9 +36,12 @@ class SoloComm:
         torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("kind_name,k,with_int,fused", [("SYNTH_GAUSS_CLUSTERS", 2, False, True), ("SYNTH_SLAB_ECEF", 2, True, True), ("SYNTH_GAUSS_CLUSTERS", 1, False, True),
-                                                     ("SYNTH_GAUSS_CLUSTERS", 2, True, False)])
-def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k, with_int, fused, monkeypatch):
+@pytest.mark.parametrize("kind_name,k,with_int,fused,res_override", [
+    ("SYNTH_GAUSS_CLUSTERS", 2, False, True, None), ("SYNTH_SLAB_ECEF", 2, True, True, None), ("SYNTH_GAUSS_CLUSTERS", 1, False, True, None),
+    ("SYNTH_GAUSS_CLUSTERS", 2, True, False, None),
+    # resolution 1e-6 over a 1024 m cube: the upper levels are Float64 encoded, i.e. wide (32-byte) records and separate colours
+    ("SYNTH_GAUSS_CLUSTERS", 2, True, True, 1e-6), ("SYNTH_GAUSS_CLUSTERS", 2, False, False, 1e-6)])
+def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k, with_int, fused, res_override, monkeypatch):
     import torch
 
     import point_cloud_viewer_b200 as pcv
@@ -48,6 +51,8 @@ def test_one_rank_native_sharded_build_equals_plain_build(kind_name, k, with_int
     n, maxpts = 600_000, 5000
     dev = torch.device("cuda", 0)
     bmin, bmax, res = pcv.synth_bbox(kind)
+    if res_override:
+        res = res_override
     ctx = pcv.Context(0, max_points_per_node=maxpts)
     x, y, z = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
     rgb = torch.empty(n * 3, dtype=torch.uint8, device=dev)
