@@ -1092,7 +1092,7 @@ __device__ __forceinline__ unsigned place_stayers(const PlaceArgs& a, const Leaf
 }
 
 // Points that move (every 8th by current rank, generation.rs:224-238): walk up re-encoding through every cube.
-template <bool WIDE, bool FASTDIV>
+template <bool WIDE>
 __device__ __forceinline__ void place_movers(const PlaceArgs& a, const LeafTile& lt, const DNode& leaf, bool all_points) {
     const uint32_t step = all_points ? 1u : 8u;
     for (uint32_t i = threadIdx.x * step; i < lt.count; i += blockDim.x * step) {
@@ -1106,7 +1106,7 @@ __device__ __forceinline__ void place_movers(const PlaceArgs& a, const LeafTile&
             const DNode P = a.d_nodes[nd.parent];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                if (FASTDIV) {
+                if (a.fast) {
                     const double q = decode1_fast(c[k], nd.m[k], nd.e, nd.enc);
                     c[k] = encode1_fast(q, P.m[k], P.e, P.ry, P.enc);
                 } else {
@@ -1121,7 +1121,7 @@ __device__ __forceinline__ void place_movers(const PlaceArgs& a, const LeafTile&
         if (nd.parent >= 0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                if (FASTDIV) {
+                if (a.fast) {
                     const double q = decode1_fast(c[k], nd.m[k], nd.e, nd.enc);
                     c[k] = encode1_fast(q, nd.m[k], nd.e, nd.ry, nd.enc);
                 } else {
@@ -1135,7 +1135,7 @@ __device__ __forceinline__ void place_movers(const PlaceArgs& a, const LeafTile&
     }
 }
 
-template <bool WIDE, int FASTMODE>  // FASTMODE = PlaceArgs::fast: a kernel per division mode
+template <bool WIDE>
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
     const LeafTile lt = leaf_tile_of(a, blockIdx.x);
     const DNode leaf = a.d_nodes[lt.node];
@@ -1151,19 +1151,25 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     // whose node ends the walk (root / collector), goes through the generic per-point path.
     const bool generic = leaf.parent < 0 || (lt.j0 & 7) != 0;
     if (generic) {
-        place_movers<WIDE, FASTMODE != 0>(a, lt, leaf, true);
+        place_movers<WIDE>(a, lt, leaf, true);
         return;
     }
-    if (FASTMODE == 1 || FASTMODE == 2) {
+    if (a.fast == 3) {
+        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 3>(a, lt, leaf);)
+    } else if (a.fast) {
         unsigned bad = 0;
-        PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, FASTMODE>(a, lt, leaf);)
+        if (a.fast == 2) {
+            PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, 2>(a, lt, leaf);)
+        } else {
+            PCV_ENC_SWITCH(leaf.enc, bad = place_stayers<WIDE, ENC, 1>(a, lt, leaf);)
+        }
         if (__syncthreads_or((int)bad)) {  // rare: redo the tile's stayers with the IEEE operator (idempotent stores)
             PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 0>(a, lt, leaf);)
         }
     } else {
-        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, FASTMODE>(a, lt, leaf);)  // 3: exact scaling, 0: IEEE division
+        PCV_ENC_SWITCH(leaf.enc, place_stayers<WIDE, ENC, 0>(a, lt, leaf);)
     }
-    place_movers<WIDE, FASTMODE != 0>(a, lt, leaf, false);
+    place_movers<WIDE>(a, lt, leaf, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1547,18 +1553,10 @@ struct CudaBackend : Backend {
         PlaceArgs a = a_in;
         a.prefetch_tiles = resident(4);
         prof_begin(K_PLACE, a.npoints * ((a.wide ? sizeof(RecW) : sizeof(RecN)) + 3 + 3 + 4 + (a.out_intensity ? 8 : 0)) + a.xyz_bytes);
-#define PCV_PLACE(W, F) k_place<W, F><<<a.ntiles, 256, 0, stream>>>(a)
-        switch ((a.wide ? 4 : 0) + a.fast) {
-            case 0: PCV_PLACE(false, 0); break;
-            case 1: PCV_PLACE(false, 1); break;
-            case 2: PCV_PLACE(false, 2); break;
-            case 3: PCV_PLACE(false, 3); break;
-            case 4: PCV_PLACE(true, 0); break;
-            case 5: PCV_PLACE(true, 1); break;
-            case 6: PCV_PLACE(true, 2); break;
-            default: PCV_PLACE(true, 3); break;
-        }
-#undef PCV_PLACE
+        if (a.wide)
+            k_place<true><<<a.ntiles, 256, 0, stream>>>(a);
+        else
+            k_place<false><<<a.ntiles, 256, 0, stream>>>(a);
         prof_end();
         ++launches;
         PCV_CUDA_CHECK(cudaGetLastError());
