@@ -88,6 +88,7 @@ int pcv_create(int device, const pcv_config* cfg, pcv_ctx** out) {
     c->be = new CudaBackend(c->stream);
     // per-device attribute (a second context on another GPU of the same process needs its own opt-in)
     CU(cudaFuncSetAttribute(k_ply_unpack, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_xray_subtile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kXraySub * kXraySub * 128)));
     *out = c;
     return PCV_OK;
     API_CATCH

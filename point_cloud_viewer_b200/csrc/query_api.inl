@@ -754,11 +754,6 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
         sb.sub_off = bin.sub_count;
         sb.keys = bin.keys;
         const size_t sm = (size_t)kXraySub * kXraySub * 128;
-        static bool attr_set[64] = {};
-        if (!attr_set[c->device & 63]) {
-            CU(cudaFuncSetAttribute(k_xray_subtile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            attr_set[c->device & 63] = true;
-        }
         k_xray_subtile<<<nsub, 512, sm, c->stream>>>(sb);
         c->be->launches++;
         CU(cudaEventRecord(e1, c->stream));
