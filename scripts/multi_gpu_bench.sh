@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: run15.sh N  - the sharded bench on N GPUs with per-rank phase timings
+# usage: multi_gpu_bench.sh N  (EXTRA_ENV="PCV_FUSED_PASS=1" ... for variants)  - the sharded bench on N GPUs with per-rank phase timings
 N=${1:-8}
 mkdir -p gpurun_out
 env PCV_TIMING=2 ${EXTRA_ENV} timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29742 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_n$N.json 2> gpurun_out/r2_n$N.err
