@@ -629,6 +629,19 @@ def run_ours(args):
             out["ply_ingest"] = bench_ply(ctx, pcv, int(args.ply_points), peak)
         except Exception as e:
             out["ply_ingest"] = {"error": str(e)[:200]}
+
+        # ---- the whole X-ray quadtree (leaves, background, Lanczos3 parents) - in a child process, last ----
+        try:
+            import subprocess
+
+            ctx.release_cached_memory()
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "xray_pyramid_bench.py"), "--points", str(int(args.cpu_points)), "--tile-px", str(int(args.xray_px)),
+                                "--peak", str(peak)], capture_output=True, text=True, timeout=420)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out["xray_quadtree"] = json.loads(line[-1]) if line else {"error": ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            out["xray_quadtree"] = {"error": str(e)[:300]}
     else:
         out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "e2e is measured at N=1 (without --no-extras)"}
         if last is not None:

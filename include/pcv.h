@@ -193,6 +193,56 @@ int pcv_xray_tile_attr(const pcv_octree* o, const double tile_min[3], const doub
                        const double* query_from_global /* 7 or NULL */, int strategy, float p0, float p1, int colormap, uint8_t* rgba_out,
                        int* any_out);
 
+/* Pixels no point falls into are TRANSPARENT.to_u8() = (255, 255, 255, 0) in every tile (src/color.rs:154-159,
+ * xray/src/generation.rs:506-511). */
+
+/* ---- f3: the rest of the X-ray pipeline (xray/src/generation.rs:129-157, 410-451, 515-759) ---- */
+/* Colored / ColoredWithIntensity with Binning = Some(("intensity", bin_size)) (:66-67, :129-157): per pixel and bin
+ * (bin = (intensity as f64 / bin_size) as i64) the mean colour / intensity, per pixel the mean of its bins' means
+ * (:276-290, :339-346).  Needs an octree with intensities ("Binning attribute needs to be available").  The reference sums
+ * in arrival / hash-map order: results are defined up to f32 rounding (+-1 per channel). */
+int pcv_xray_tile_attr_binned(const pcv_octree* o, const double tile_min[3], const double tile_max[3], uint32_t w, uint32_t h,
+                              const double* query_from_global /* 7 or NULL */, int strategy /* PCV_XRAY_COLORED | PCV_XRAY_INTENSITY */,
+                              float p0, float p1, double bin_size, uint8_t* rgba_out, int* any_out);
+/* assign_background (:695-720): every pixel with alpha < 128 becomes `background` (RGBA), in place (host buffer). */
+int pcv_xray_assign_background(pcv_ctx* ctx, uint8_t* rgba, uint64_t num_pixels, const uint8_t background[4]);
+/* build_node (:722-759) for one parent: build_parent's 2 x 2 mosaic of the four child images (:410-451; children[i] =
+ * child_px x child_px RGBA of quadtree child i or NULL -> background; child 1 top left, 0 bottom left, 3 top right, 2 bottom
+ * right) reduced to tile_px x tile_px with image 0.23's `imageops::resize(.., FilterType::Lanczos3)` (vertical pass into
+ * u8, then horizontal pass; f32 weights; round-to-nearest conversion - restated, the crate is not vendored).  Host buffers. */
+int pcv_xray_build_parent(pcv_ctx* ctx, const uint8_t* const children[4], uint32_t child_px, const uint8_t background[4],
+                          uint32_t tile_px, uint8_t* rgba_out /* tile_px * tile_px * 4 */);
+/* build_xray_quadtree (:560-622) as one call: bounding rect and levels (:515-533), every leaf tile at the deepest level
+ * (:535-551, :624-667) with the chosen strategy, assign_background on the created leaves, then level by level the parents
+ * (:669-693).  Every image stays in HBM until its parent is built; each finished tile is handed to `on_tile` (host
+ * pointer, valid during the call; return non-zero to cancel -> PCV_ERR_CANCELLED; must not call into the same context).
+ * What the reference writes as <id>.png and meta.pb is what on_tile receives plus `info`; PNG encoding stays on the host. */
+typedef struct pcv_xray_quadtree_params {
+    int32_t strategy;             /* 0 = XRay, or PCV_XRAY_COLORED / _INTENSITY / _HEIGHT_STDDEV                 */
+    float p0, p1;                 /* as in pcv_xray_tile_attr                                                     */
+    int32_t colormap;
+    double bin_size;              /* 0: Binning = None                                                            */
+    int32_t has_query_from_global;
+    double query_from_global[7];  /* tx,ty,tz, qi,qj,qk,qw                                                        */
+    uint8_t background[4];        /* tile_background_color: WHITE (255,255,255,255) or TRANSPARENT (255,255,255,0) */
+    uint32_t tile_size_px;
+    double pixel_size_m;
+    uint8_t root_level;           /* root_node_id (quadtree/src/lib.rs:143-150); NodeId::root() = (0, 0)          */
+    uint64_t root_index;
+} pcv_xray_quadtree_params;
+typedef struct pcv_xray_quadtree_info {
+    double rect_min_x, rect_min_y, rect_edge; /* Meta::bounding_rect = the (sub-)root node's rect                 */
+    uint8_t deepest_level;                    /* Meta::deepest_level                                              */
+    uint32_t tile_size_px;                    /* Meta::tile_size                                                  */
+    uint32_t num_nodes, num_leaves;           /* Meta::nodes = the ids on_tile received                           */
+    float ms_leaves, ms_parents;              /* CUDA events: leaf tiles + background; parent kernels             */
+    uint32_t kernel_launches;
+    uint64_t leaf_points;                     /* XRay strategy: points decoded for the leaf tiles                 */
+} pcv_xray_quadtree_info;
+typedef int (*pcv_xray_tile_fn)(void* user, uint8_t level, uint64_t index, const uint8_t* rgba, uint32_t tile_size_px);
+int pcv_xray_quadtree(const pcv_octree* o, const pcv_xray_quadtree_params* params, pcv_xray_tile_fn on_tile, void* user,
+                      pcv_xray_quadtree_info* info_out);
+
 /* ---- multi-GPU helpers (points shard by level-k path prefix) ------------------ */
 /* Per-point level-k cell (first k steps of the re-quantising descent on the raw positions) ->
  * 8^k histogram; then a stable pack of the points of each destination rank into contiguous send

@@ -7,6 +7,7 @@
 #include "oracle_disk.hpp"
 #include "oracle_ply.hpp"
 #include "oracle_query.hpp"
+#include "oracle_xray_pyramid.hpp"
 #include "../include/pcv_synth.h"  // input-data generators shared with the benchmark (no algorithm code)
 
 using namespace orc;
@@ -409,6 +410,104 @@ int orc_xray_tile_attr(void* hp, const double* bbox_min, const double* bbox_max,
     std::memcpy(rgba_out, rgba.data(), rgba.size());
     return any ? 1 : 0;
 }
+
+// ---- the rest of the X-ray pipeline (oracle_xray_pyramid.hpp) ----
+int orc_xray_tile_attr_binned(void* hp, const double* bbox_min, const double* bbox_max, uint32_t w, uint32_t hgt, const double* query_from_global7,
+                              int mode, float p0, float p1, double bin_size, uint8_t* rgba_out) {
+    Handle* h = (Handle*)hp;
+    Aabb bb = Aabb::make({bbox_min[0], bbox_min[1], bbox_min[2]}, {bbox_max[0], bbox_max[1], bbox_max[2]});
+    Iso3 q{};
+    if (query_from_global7) q = iso_from7(query_from_global7);
+    std::vector<uint8_t> rgba;
+    bool any = xray_tile_attr_binned(h->oct, bb, w, hgt, query_from_global7 != nullptr, q, mode, p0, p1, bin_size, rgba);
+    std::memcpy(rgba_out, rgba.data(), rgba.size());
+    return any ? 1 : 0;
+}
+void orc_resize_lanczos3(const uint8_t* src, uint32_t w, uint32_t hgt, uint32_t nw, uint32_t nh, uint8_t* out) {
+    Image im;
+    im.w = w;
+    im.h = hgt;
+    im.px.assign(src, src + (size_t)w * hgt * 4);
+    const Image r = resize_lanczos3(im, nw, nh);
+    std::memcpy(out, r.px.data(), r.px.size());
+}
+// build_node without the files: build_parent + resize to tile_px (children[i] may be null)
+void orc_build_parent_tile(const uint8_t* const children[4], uint32_t child_px, const uint8_t* bg4, uint32_t tile_px, uint8_t* out, uint8_t* mosaic_out) {
+    Image ch[4];
+    const Image* pc[4];
+    for (int k = 0; k < 4; ++k) {
+        pc[k] = nullptr;
+        if (children[k]) {
+            ch[k].w = ch[k].h = child_px;
+            ch[k].px.assign(children[k], children[k] + (size_t)child_px * child_px * 4);
+            pc[k] = &ch[k];
+        }
+    }
+    const Image large = build_parent(pc, bg4);
+    if (mosaic_out) std::memcpy(mosaic_out, large.px.data(), large.px.size());
+    const Image r = resize_lanczos3(large, tile_px, tile_px);
+    std::memcpy(out, r.px.data(), r.px.size());
+}
+void orc_assign_background(uint8_t* rgba, uint64_t npix, const uint8_t* bg4) {
+    Image im;
+    im.w = (uint32_t)npix;
+    im.h = 1;
+    im.px.assign(rgba, rgba + npix * 4);
+    assign_background(im, bg4);
+    std::memcpy(rgba, im.px.data(), npix * 4);
+}
+struct orc_xray_quadtree_params {
+    int32_t strategy;
+    float p0, p1;
+    int32_t colormap;
+    double bin_size;
+    int32_t has_query_from_global;
+    double query_from_global[7];
+    uint8_t background[4];
+    uint32_t tile_size_px;
+    double pixel_size_m;
+    uint8_t root_level;
+    uint64_t root_index;
+};
+void* orc_xray_quadtree_build(void* hp, const orc_xray_quadtree_params* p) {
+    Handle* h = (Handle*)hp;
+    XrayQuadtreeParams pr;
+    pr.strategy = p->strategy;
+    pr.p0 = p->p0;
+    pr.p1 = p->p1;
+    pr.colormap = p->colormap;
+    pr.bin_size = p->bin_size;
+    pr.has_q = p->has_query_from_global != 0;
+    if (pr.has_q) pr.query_from_global = iso_from7(p->query_from_global);
+    std::memcpy(pr.background, p->background, 4);
+    pr.tile_size_px = p->tile_size_px;
+    pr.pixel_size_m = p->pixel_size_m;
+    pr.root = QuadId{p->root_level, p->root_index};
+    XrayQuadtree* q = new XrayQuadtree();
+    if (!build_xray_quadtree(h->oct, pr, *q)) {
+        delete q;
+        return nullptr;
+    }
+    return q;
+}
+void orc_xray_quadtree_info(void* qp, double* rect3, int* deepest, uint64_t* ntiles) {
+    XrayQuadtree* q = (XrayQuadtree*)qp;
+    rect3[0] = q->bounding_rect.min_x, rect3[1] = q->bounding_rect.min_y, rect3[2] = q->bounding_rect.edge;
+    *deepest = q->deepest_level;
+    *ntiles = q->tiles.size();
+}
+void orc_xray_quadtree_ids(void* qp, uint8_t* levels, uint64_t* indices) {
+    size_t k = 0;
+    for (auto& kv : ((XrayQuadtree*)qp)->tiles) levels[k] = kv.first.level, indices[k] = kv.first.index, ++k;
+}
+int orc_xray_quadtree_tile(void* qp, uint8_t level, uint64_t index, uint8_t* rgba_out) {
+    XrayQuadtree* q = (XrayQuadtree*)qp;
+    auto it = q->tiles.find(QuadId{level, index});
+    if (it == q->tiles.end()) return -1;
+    std::memcpy(rgba_out, it->second.px.data(), it->second.px.size());
+    return 0;
+}
+void orc_xray_quadtree_free(void* qp) { delete (XrayQuadtree*)qp; }
 
 // ---- disk ----
 int orc_write_dir(void* hp, const char* dir) { return write_dir(((Handle*)hp)->oct, dir) ? 0 : -1; }

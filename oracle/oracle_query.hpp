@@ -445,6 +445,16 @@ inline void query_node(const Octree& oct, NodeId id, const Location& loc, const 
     }
 }
 
+// Pixels without a colour get `TRANSPARENT.to_u8()` = (255, 255, 255, 0): generation.rs:506-511, src/color.rs:154-159
+// (TRANSPARENT is white with alpha 0, not zero).
+inline void fill_transparent(std::vector<uint8_t>& rgba, size_t npix) {
+    rgba.resize(npix * 4);
+    for (size_t i = 0; i < npix; ++i) {
+        rgba[i * 4 + 0] = rgba[i * 4 + 1] = rgba[i * 4 + 2] = 255;
+        rgba[i * 4 + 3] = 0;
+    }
+}
+
 // xray/src/generation.rs:464-513 with the XRay strategy (:159-198) and process_point_data (:108-127).
 // `has_q` selects the OBB location + query_from_global transform (:471-477,493-497).
 inline bool xray_tile(const Octree& oct, const Aabb& bbox, uint32_t w, uint32_t h, bool has_q, const Iso3& query_from_global,
@@ -501,7 +511,7 @@ inline bool xray_tile(const Octree& oct, const Aabb& bbox, uint32_t w, uint32_t 
             }
         }
     }
-    rgba.assign((size_t)w * h * 4, 0);
+    fill_transparent(rgba, (size_t)w * h);
     if (!seen_any) return false;
     double max_sat = std::log(1024.);
     for (size_t px = 0; px < (size_t)w * h; ++px) {
@@ -631,7 +641,7 @@ inline bool xray_tile_attr(const Octree& oct, const Aabb& bbox, uint32_t w, uint
             }
         }
     }
-    rgba.assign(npix * 4, 0);
+    fill_transparent(rgba, npix);
     if (!seen_any) return false;
     for (size_t px = 0; px < npix; ++px) {
         if (count[px] == 0) continue;

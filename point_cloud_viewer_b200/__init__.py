@@ -554,6 +554,72 @@ class Octree:
         return bool(anyp.value), rgba
 
 
+    def xray_tile_attr_binned(self, tile_min, tile_max, w, h, strategy, bin_size, p0=0.0, p1=0.0, query_from_global=None):
+        """XRAY_COLORED / XRAY_INTENSITY with Binning = Some(("intensity", bin_size)) (xray/src/generation.rs:129-157)."""
+        rgba = np.zeros((h, w, 4), np.uint8)
+        anyp = C.c_int()
+        q = (C.c_double * 7)(*[float(v) for v in query_from_global]) if query_from_global is not None else None
+        N.check(N.lib().pcv_xray_tile_attr_binned(self.h, _d3(tile_min), _d3(tile_max), w, h, q, int(strategy), float(p0), float(p1), float(bin_size),
+                                                  _p(rgba), C.byref(anyp)))
+        return bool(anyp.value), rgba
+
+    def xray_quadtree(self, tile_size_px, pixel_size_m, strategy=0, p0=0.0, p1=0.0, colormap=0, bin_size=0.0, query_from_global=None,
+                      background=(255, 255, 255, 255), root=(0, 0), on_tile=None, keep_tiles=True):
+        """build_xray_quadtree (xray/src/generation.rs:560-622) on the GPU: returns (info dict, {(level, index): RGBA array}).
+        `on_tile(level, index, rgba)` is called for every finished tile (return a true value to cancel)."""
+        pr = N.XrayQuadtreeParams()
+        pr.strategy, pr.p0, pr.p1, pr.colormap, pr.bin_size = int(strategy), float(p0), float(p1), int(colormap), float(bin_size)
+        pr.has_query_from_global = 0 if query_from_global is None else 1
+        if query_from_global is not None:
+            pr.query_from_global = (C.c_double * 7)(*[float(v) for v in query_from_global])
+        pr.background = (C.c_uint8 * 4)(*[int(v) for v in background])
+        pr.tile_size_px, pr.pixel_size_m = int(tile_size_px), float(pixel_size_m)
+        pr.root_level, pr.root_index = int(root[0]), int(root[1])
+        tiles = {}
+
+        def cb(_user, level, index, ptr, tpx):
+            img = np.ctypeslib.as_array(ptr, shape=(tpx, tpx, 4))
+            if keep_tiles:
+                tiles[(int(level), int(index))] = img.copy()
+            return 1 if (on_tile is not None and on_tile(int(level), int(index), img)) else 0
+
+        info = N.XrayQuadtreeInfo()
+        N.check(N.lib().pcv_xray_quadtree(self.h, C.byref(pr), N.XRAY_TILE_FN(cb), None, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in N.XrayQuadtreeInfo._fields_}, tiles
+
+
+def xray_node_name(level, index):
+    """quadtree NodeId -> its name / PNG stem ("r", "r0", "r123323"; quadtree/src/lib.rs:216-233)."""
+    return "r" + "".join(str((int(index) >> (2 * l)) & 3) for l in reversed(range(int(level))))
+
+
+def xray_node_id(name):
+    """NodeId::from_str (quadtree/src/lib.rs:201-213): (level, index)."""
+    level = len(name) - 1
+    return level, (int(name[1:], 4) if level > 0 else 0)
+
+
+def xray_assign_background(ctx, rgba, background):
+    """assign_background (xray/src/generation.rs:695-720) in place on a C-contiguous (..., 4) uint8 array."""
+    bg = np.asarray(background, np.uint8)
+    assert rgba.dtype == np.uint8 and rgba.flags.c_contiguous and rgba.shape[-1] == 4 and bg.shape == (4,)
+    N.check(N.lib().pcv_xray_assign_background(ctx.h, _p(rgba), rgba.size // 4, _p(bg)))
+    return rgba
+
+
+def xray_build_parent(ctx, children, background, tile_px):
+    """build_parent + Lanczos3 reduction (xray/src/generation.rs:410-451, 722-759).  children: 4 x (N, N, 4) uint8 or None."""
+    child_px = next(c.shape[0] for c in children if c is not None)
+    keep = [np.ascontiguousarray(c, np.uint8) if c is not None else None for c in children]
+    for c in keep:
+        assert c is None or c.shape == (child_px, child_px, 4)
+    ptrs = (C.c_void_p * 4)(*[_p(c) for c in keep])
+    bg = np.asarray(background, np.uint8)
+    out = np.zeros((tile_px, tile_px, 4), np.uint8)
+    N.check(N.lib().pcv_xray_build_parent(ctx.h, ptrs, child_px, _p(bg), tile_px, _p(out)))
+    return out
+
+
 def ply_read_header(path):
     """parse_header + the property checks of PlyIterator::from_file (ply.rs:126-229, 327-450) -> pcv_ply_info."""
     info = N.PlyInfo()

@@ -109,6 +109,25 @@ class XrayStats(C.Structure):
     _fields_ = [("ms_device", C.c_float), ("kernel_launches", C.c_uint32), ("points", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
 
 
+class XrayQuadtreeParams(C.Structure):
+    """pcv_xray_quadtree_params (include/pcv.h)."""
+
+    _fields_ = [("strategy", C.c_int32), ("p0", C.c_float), ("p1", C.c_float), ("colormap", C.c_int32), ("bin_size", C.c_double),
+                ("has_query_from_global", C.c_int32), ("query_from_global", C.c_double * 7), ("background", C.c_uint8 * 4),
+                ("tile_size_px", C.c_uint32), ("pixel_size_m", C.c_double), ("root_level", C.c_uint8), ("root_index", C.c_uint64)]
+
+
+class XrayQuadtreeInfo(C.Structure):
+    """pcv_xray_quadtree_info (include/pcv.h)."""
+
+    _fields_ = [("rect_min_x", C.c_double), ("rect_min_y", C.c_double), ("rect_edge", C.c_double), ("deepest_level", C.c_uint8),
+                ("tile_size_px", C.c_uint32), ("num_nodes", C.c_uint32), ("num_leaves", C.c_uint32), ("ms_leaves", C.c_float),
+                ("ms_parents", C.c_float), ("kernel_launches", C.c_uint32), ("leaf_points", C.c_uint64)]
+
+
+XRAY_TILE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint8, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint32)
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64), ("ms", C.c_double)]
 
@@ -161,6 +180,10 @@ SYMBOLS = [
     ("pcv_last_xray_stats", C.c_int, [C.c_void_p, C.POINTER(XrayStats)]),
     ("pcv_xray_tile", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     ("pcv_xray_tile_attr", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    ("pcv_xray_tile_attr_binned", C.c_int, [C.c_void_p, _dp, _dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
+    ("pcv_xray_assign_background", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("pcv_xray_build_parent", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]),
+    ("pcv_xray_quadtree", C.c_int, [C.c_void_p, C.POINTER(XrayQuadtreeParams), XRAY_TILE_FN, C.c_void_p, C.POINTER(XrayQuadtreeInfo)]),
     ("pcv_prefix_histogram_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p]),
     ("pcv_prefix_histogram_bbox_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, _dp, _dp]),
     ("pcv_prefix_pack_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_uint64, C.c_double, _dp, _dp, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -20,6 +20,7 @@
 #include "ply_host.hpp"
 #include "kernels_shard.cuh"
 #include "query.cuh"
+#include "xray_pyramid.cuh"
 #include "synth.cuh"
 
 using namespace pcv;
@@ -661,6 +662,7 @@ int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* res
 }  // extern "C"
 
 #include "query_api.inl"
+#include "xray_api.inl"
 #include "ply_api.inl"
 #include "shard_api.inl"
 #include "sharded_build.inl"

@@ -603,6 +603,11 @@ __global__ void __launch_bounds__(256) k_cull_fused(const __grid_constant__ Cull
 }
 
 // ---- X-ray -----------------------------------------------------------------------------------------
+// Pixels no point falls into get TRANSPARENT.to_u8() = (255, 255, 255, 0) (src/color.rs:154-159, generation.rs:506-511).
+constexpr uint32_t kXrayTransparent = 0x00FFFFFFu;  // r | g << 8 | b << 16 | a << 24
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t* __restrict__ dst, uint32_t value, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = value;
+}
 struct XrayArgs {
     QueryGeom geom;
     const QNode* nodes;
@@ -741,7 +746,7 @@ __global__ void __launch_bounds__(512, 1) k_xray_subtile(const __grid_constant__
     __shared__ uint8_t sover[kXraySub * kXraySub];
     const uint32_t sid = blockIdx.x;
     const uint32_t k0 = b.sub_off[sid], k1 = b.sub_off[sid + 1];
-    if (k1 == k0) return;  // no point falls into this sub-tile: its pixels stay transparent (the image is zero-initialised)
+    if (k1 == k0) return;  // no point falls into this sub-tile: its pixels stay transparent (the image is pre-filled with TRANSPARENT)
     const uint32_t px0 = (sid % b.sub_w) * kXraySub, py0 = (sid / b.sub_w) * kXraySub;
     {
         uint4* z4 = reinterpret_cast<uint4*>(sbits);
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(256) k_xray_resolve(const uint32_t* __restrict
         const uint4 v = b[k];
         cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
     }
-    uchar4 o = make_uchar4(0, 0, 0, 0);
+    uchar4 o = make_uchar4(255, 255, 255, 0);  // TRANSPARENT.to_u8() (color.rs:154-159; generation.rs:506-511)
     if (cnt) {
         const uint8_t gval = grey[cnt];
         o = make_uchar4(gval, gval, gval, 255);
@@ -880,7 +885,7 @@ __global__ void __launch_bounds__(256) k_xray_resolve_attr(int mode, float p0, f
                                                            uint8_t* __restrict__ rgba) {
     const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= npix) return;
-    uchar4 o = make_uchar4(0, 0, 0, 0);
+    uchar4 o = make_uchar4(255, 255, 255, 0);  // TRANSPARENT.to_u8() (color.rs:154-159; generation.rs:506-511)
     const uint32_t n = count[px];
     if (n) {
         if (mode == 1) {

@@ -685,14 +685,12 @@ static void xray_prepare(pcv_octree* o, pcv_ctx* c, const double tmin[3], const 
     (void)c;
 }
 
-int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
-                  uint32_t* zbits_out, int* any_out) {
-    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
-    API_TRY
-    pcv_octree* o = const_cast<pcv_octree*>(oc);
+// The leaf tile with the XRay strategy.  The caller holds the context's lock and has selected its device.  The image goes to
+// `rgba_out` (host, optional) and / or stays in `d_rgba_ext` (device, w * h * 4 bytes, optional: the quadtree driver keeps
+// the tiles of a level resident for the parents).
+static int xray_tile_core(pcv_octree* o, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
+                          uint32_t* zbits_out, int* any_out, uint8_t* d_rgba_ext) {
     pcv_ctx* c = o->ctx;
-    std::lock_guard<std::mutex> g(c->mu);
-    CU(cudaSetDevice(c->device));
     ensure_tables(o);
     c->xstats = pcv_xray_stats{};
     const uint64_t l0 = c->be->launches;
@@ -726,7 +724,7 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     bin.keys = s.alloc<uint32_t>(std::max<uint64_t>(pts, 1));
     XraySubArgs sb{};
     sb.grey = s.upload(grey, 1026);
-    sb.rgba = s.alloc<uint8_t>(npix * 4);
+    sb.rgba = d_rgba_ext ? d_rgba_ext : s.alloc<uint8_t>(npix * 4);
     sb.zbits_out = zbits_out ? s.alloc<uint32_t>(npix * 32) : nullptr;
     sb.sub_w = sw;
     sb.w = w;
@@ -735,7 +733,8 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, c->stream));
-    CU(cudaMemsetAsync(sb.rgba, 0, npix * 4, c->stream));
+    k_fill_u32<<<(uint32_t)std::min<size_t>((npix + 255) / 256, (size_t)c->sm_count * 8), 256, 0, c->stream>>>((uint32_t*)sb.rgba, kXrayTransparent, npix);
+    c->be->launches++;
     CU(cudaMemsetAsync(bin.sub_count, 0, ((size_t)nsub + 1) * 4, c->stream));
     CU(cudaMemsetAsync(bin.sub_cursor, 0, ((size_t)nsub + 1) * 4, c->stream));
     if (sb.zbits_out) CU(cudaMemsetAsync(sb.zbits_out, 0, npix * 128, c->stream));
@@ -765,7 +764,10 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
         CU(cudaEventRecord(e1, c->stream));
     }
     CU(cudaGetLastError());
-    c->be->d2h(rgba_out, sb.rgba, npix * 4);
+    if (rgba_out)
+        c->be->d2h(rgba_out, sb.rgba, npix * 4);
+    else
+        CU(cudaStreamSynchronize(c->stream));  // the events below and the scratch buffers
     if (zbits_out) c->be->d2h(zbits_out, sb.zbits_out, npix * 128);
     if (any_out) *any_out = any;
     cudaEventElapsedTime(&c->xstats.ms_device, e0, e1);
@@ -775,35 +777,45 @@ int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[
     c->xstats.points = pts;
     c->xstats.algorithmic_bytes = bytes + 4ull * npix;
     return PCV_OK;
-    API_CATCH
 }
 
-}  // extern "C"
-
-// The other ColoringStrategyKinds of xray_from_points (xray/src/generation.rs:76-97, 200-405) with Binning = None.
-int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, int mode, float p0,
-                       float p1, int colormap, uint8_t* rgba_out, int* any_out) {
+int pcv_xray_tile(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, uint8_t* rgba_out,
+                  uint32_t* zbits_out, int* any_out) {
     if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
-    if (mode < PCV_XRAY_COLORED || mode > PCV_XRAY_HEIGHT_STDDEV) return fail(PCV_ERR_INVALID, "unknown colouring strategy %d", mode);
-    if (mode == PCV_XRAY_INTENSITY && !oc->d_intensity)
-        return fail(PCV_ERR_INVALID, "Coloring by intensity was requested, but point data without intensity found.");
     API_TRY
     pcv_octree* o = const_cast<pcv_octree*>(oc);
     pcv_ctx* c = o->ctx;
     std::lock_guard<std::mutex> g(c->mu);
     CU(cudaSetDevice(c->device));
+    return xray_tile_core(o, tmin, tmax, w, h, qfg, rgba_out, zbits_out, any_out, nullptr);
+    API_CATCH
+}
+
+}  // extern "C"
+
+// The other ColoringStrategyKinds of xray_from_points (xray/src/generation.rs:76-97, 200-405).  bin_size == 0: Binning = None;
+// bin_size > 0 (strategies Colored and ColoredWithIntensity): Binning = Some(("intensity", bin_size)), the columns are
+// aggregated per (pixel, bin) in two device hash tables (xray_pyramid.h) and the pixel is the mean of its bins' means.
+// Same contract as xray_tile_core for the lock and the two outputs.
+static int xray_tile_attr_core(pcv_octree* o, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, int mode, float p0,
+                               float p1, int colormap, double bin_size, uint8_t* rgba_out, int* any_out, uint8_t* d_rgba_ext) {
+    pcv_ctx* c = o->ctx;
     ensure_tables(o);
     Scratch s(c);
+    const bool binned = bin_size != 0.0;
+    XrayBinnedArgs bb{};
     XrayAttrArgs b{};
+    XrayArgs& xa = binned ? bb.x : b.x;
     size_t ntiles = 0;
-    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, b.x, nullptr, &ntiles);
+    std::vector<uint32_t> hit;
+    xray_prepare(o, c, tmin, tmax, w, h, qfg, s, xa, &hit, &ntiles);
     const size_t npix = (size_t)w * h;
-    b.x.any = s.alloc<int>(1);
+    xa.any = s.alloc<int>(1);
     b.rgb = o->d_rgb;
     b.intensity = o->d_intensity;
     b.count = s.alloc<uint32_t>(npix);
     b.z0 = (std::fmin(tmin[2], tmax[2]) + std::fmax(tmin[2], tmax[2])) * 0.5;
-    CU(cudaMemsetAsync(b.x.any, 0, 4, c->stream));
+    CU(cudaMemsetAsync(xa.any, 0, 4, c->stream));
     CU(cudaMemsetAsync(b.count, 0, npix * 4, c->stream));
     if (mode == PCV_XRAY_HEIGHT_STDDEV) {
         b.dsum = s.alloc<double>(npix * 2);
@@ -813,8 +825,9 @@ int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double 
         b.sum = s.alloc<float>(npix * per);
         CU(cudaMemsetAsync(b.sum, 0, npix * per * 4, c->stream));
     }
-    uint8_t* drgba = s.alloc<uint8_t>(npix * 4);
-    if (ntiles) {
+    uint8_t* drgba = d_rgba_ext ? d_rgba_ext : s.alloc<uint8_t>(npix * 4);
+    int* derr = nullptr;
+    if (ntiles && !binned) {
         if (mode == PCV_XRAY_COLORED)
             k_xray_accum_attr<1><<<(uint32_t)ntiles, 256, 0, c->stream>>>(b);
         else if (mode == PCV_XRAY_INTENSITY)
@@ -822,15 +835,72 @@ int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double 
         else
             k_xray_accum_attr<3><<<(uint32_t)ntiles, 256, 0, c->stream>>>(b);
         c->be->launches++;
+    } else if (ntiles) {
+        uint64_t pts = 0;
+        for (uint32_t k : hit) pts += (uint64_t)o->nodes[k].num_points;
+        BinnedTables& t = bb.t;
+        t.bin_cap = 1u << 20;
+        t.col_cap = 2 * pts + 1024;
+        t.ncomp = mode == PCV_XRAY_COLORED ? 3 : 1;
+        t.bin_keys = s.alloc<uint64_t>(t.bin_cap);
+        t.col_keys = s.alloc<uint64_t>(t.col_cap);
+        t.col_sum = s.alloc<float>(t.col_cap * (size_t)t.ncomp);
+        t.col_count = s.alloc<uint32_t>(t.col_cap);
+        t.err = derr = s.alloc<int>(1);
+        const uint32_t fgrid = (uint32_t)c->sm_count * 8;
+        k_fill_u64<<<fgrid, 256, 0, c->stream>>>(t.bin_keys, kBinEmpty, t.bin_cap);
+        k_fill_u64<<<fgrid, 256, 0, c->stream>>>(t.col_keys, kColEmpty, t.col_cap);
+        CU(cudaMemsetAsync(t.col_sum, 0, t.col_cap * (size_t)t.ncomp * 4, c->stream));
+        CU(cudaMemsetAsync(t.col_count, 0, t.col_cap * 4, c->stream));
+        CU(cudaMemsetAsync(t.err, 0, 4, c->stream));
+        bb.rgb = o->d_rgb;
+        bb.intensity = o->d_intensity;
+        bb.bin_size = bin_size;
+        if (mode == PCV_XRAY_COLORED)
+            k_xray_binned_insert<1><<<(uint32_t)ntiles, 256, 0, c->stream>>>(bb);
+        else
+            k_xray_binned_insert<2><<<(uint32_t)ntiles, 256, 0, c->stream>>>(bb);
+        // per (pixel, bin) mean -> the pixel's sum over bins and its number of bins, in the layout k_xray_resolve_attr reads
+        k_xray_binned_reduce<<<fgrid, 256, 0, c->stream>>>(t, b.sum, mode == PCV_XRAY_COLORED ? 4 : 1, b.count);
+        c->be->launches += 4;
     }
     k_xray_resolve_attr<<<(uint32_t)((npix + 255) / 256), 256, 0, c->stream>>>(mode, p0, p1, colormap, b.sum, b.dsum, b.count, (uint32_t)npix, drgba);
     c->be->launches++;
     CU(cudaGetLastError());
     int any = 0;
-    c->be->d2h(&any, b.x.any, 4);
-    c->be->d2h(rgba_out, drgba, npix * 4);
+    c->be->d2h(&any, xa.any, 4);
+    if (derr) {
+        int err = 0;
+        c->be->d2h(&err, derr, 4);
+        if (err) return fail(PCV_ERR_UNSUPPORTED, err == 1 ? "more than 2^20 distinct bins in one X-ray tile" : "X-ray column table full");
+    }
+    if (rgba_out) c->be->d2h(rgba_out, drgba, npix * 4);
     if (any_out) *any_out = any;
     return PCV_OK;
+}
+
+static int xray_attr_check(const pcv_octree* oc, int mode, double bin_size) {
+    if (mode < PCV_XRAY_COLORED || mode > PCV_XRAY_HEIGHT_STDDEV) return fail(PCV_ERR_INVALID, "unknown colouring strategy %d", mode);
+    if (mode == PCV_XRAY_INTENSITY && !oc->d_intensity)
+        return fail(PCV_ERR_INVALID, "Coloring by intensity was requested, but point data without intensity found.");
+    if (bin_size != 0.0) {
+        if (mode == PCV_XRAY_HEIGHT_STDDEV) return fail(PCV_ERR_INVALID, "the height-stddev strategy has no binning (xray/src/generation.rs:76-84)");
+        if (!(bin_size == bin_size)) return fail(PCV_ERR_INVALID, "bin size is NaN");
+        if (!oc->d_intensity) return fail(PCV_ERR_INVALID, "Binning attribute needs to be available in points batch.");
+    }
+    return PCV_OK;
+}
+
+int pcv_xray_tile_attr(const pcv_octree* oc, const double tmin[3], const double tmax[3], uint32_t w, uint32_t h, const double* qfg, int mode, float p0,
+                       float p1, int colormap, uint8_t* rgba_out, int* any_out) {
+    if (!oc || !tmin || !tmax || !rgba_out || w == 0 || h == 0) return fail(PCV_ERR_INVALID, "null argument or empty image");
+    if (int rc = xray_attr_check(oc, mode, 0.0)) return rc;
+    API_TRY
+    pcv_octree* o = const_cast<pcv_octree*>(oc);
+    pcv_ctx* c = o->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    return xray_tile_attr_core(o, tmin, tmax, w, h, qfg, mode, p0, p1, colormap, 0.0, rgba_out, any_out, nullptr);
     API_CATCH
 }
 

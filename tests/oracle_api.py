@@ -98,6 +98,16 @@ def lib():
         L.orc_query_batch_timed.argtypes = [C.c_void_p, LP, C.c_uint32, C.c_int, C.c_uint64, u64p, u64p, u64p]
         L.orc_xray_tile_attr.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]
         L.orc_xray_tile.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_xray_tile_attr_binned.argtypes = [C.c_void_p, dp, dp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_double, C.c_void_p]
+        L.orc_resize_lanczos3.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_build_parent_tile.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.orc_assign_background.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_xray_quadtree_build.restype = C.c_void_p
+        L.orc_xray_quadtree_build.argtypes = [C.c_void_p, C.POINTER(XrayQuadtreeParams)]
+        L.orc_xray_quadtree_info.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int), u64p]
+        L.orc_xray_quadtree_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_xray_quadtree_tile.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64, C.c_void_p]
+        L.orc_xray_quadtree_free.argtypes = [C.c_void_p]
         L.orc_write_dir.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_load_dir.restype = C.c_void_p
         L.orc_load_dir.argtypes = [C.c_char_p]
@@ -115,6 +125,39 @@ def lib():
 
 def _d(a):
     return (C.c_double * len(a))(*[float(v) for v in a])
+
+
+class XrayQuadtreeParams(C.Structure):  # orc_xray_quadtree_params (same layout as the product's pcv_xray_quadtree_params)
+    _fields_ = [("strategy", C.c_int32), ("p0", C.c_float), ("p1", C.c_float), ("colormap", C.c_int32), ("bin_size", C.c_double),
+                ("has_query_from_global", C.c_int32), ("query_from_global", C.c_double * 7), ("background", C.c_uint8 * 4),
+                ("tile_size_px", C.c_uint32), ("pixel_size_m", C.c_double), ("root_level", C.c_uint8), ("root_index", C.c_uint64)]
+
+
+def resize_lanczos3(img, nw, nh):
+    """image 0.23 imageops::resize(.., Lanczos3) restated (oracle_xray_pyramid.hpp).  img: (h, w, 4) uint8."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((nh, nw, 4), np.uint8)
+    lib().orc_resize_lanczos3(_ptr(img), img.shape[1], img.shape[0], nw, nh, _ptr(out))
+    return out
+
+
+def build_parent_tile(children, background, tile_px, want_mosaic=False):
+    """build_parent + resize (xray/src/generation.rs:410-451, 722-759).  children: 4 x (N, N, 4) uint8 or None."""
+    child_px = next(c.shape[0] for c in children if c is not None)
+    keep = [np.ascontiguousarray(c, np.uint8) if c is not None else None for c in children]
+    ptrs = (C.c_void_p * 4)(*[c.ctypes.data if c is not None else None for c in keep])
+    bg = np.asarray(background, np.uint8)
+    out = np.zeros((tile_px, tile_px, 4), np.uint8)
+    mosaic = np.zeros((2 * child_px, 2 * child_px, 4), np.uint8) if want_mosaic else None
+    lib().orc_build_parent_tile(ptrs, child_px, _ptr(bg), tile_px, _ptr(out), _ptr(mosaic))
+    return (out, mosaic) if want_mosaic else out
+
+
+def assign_background(rgba, background):
+    out = np.ascontiguousarray(rgba, np.uint8).copy()
+    bg = np.asarray(background, np.uint8)
+    lib().orc_assign_background(_ptr(out), out.size // 4, _ptr(bg))
+    return out
 
 
 def _ptr(a):
@@ -204,6 +247,42 @@ class OracleOctree:
         q = _d(query_from_global) if query_from_global is not None else None
         any_ = lib().orc_xray_tile_attr(self.h, _d(bmin), _d(bmax), w, h, q, mode, p0, p1, colormap, _ptr(rgba))
         return bool(any_), rgba
+
+    def xray_tile_attr_binned(self, bmin, bmax, w, h, mode, bin_size, p0=0.0, p1=0.0, query_from_global=None):
+        rgba = np.zeros((h, w, 4), np.uint8)
+        q = _d(query_from_global) if query_from_global is not None else None
+        any_ = lib().orc_xray_tile_attr_binned(self.h, _d(bmin), _d(bmax), w, h, q, mode, p0, p1, float(bin_size), _ptr(rgba))
+        return bool(any_), rgba
+
+    def xray_quadtree(self, tile_size_px, pixel_size_m, strategy=0, p0=0.0, p1=0.0, colormap=0, bin_size=0.0, query_from_global=None,
+                      background=(255, 255, 255, 255), root=(0, 0)):
+        """build_xray_quadtree restated: (info dict, {(level, index): RGBA}) or None when the root id is outside the quadtree."""
+        pr = XrayQuadtreeParams()
+        pr.strategy, pr.p0, pr.p1, pr.colormap, pr.bin_size = int(strategy), float(p0), float(p1), int(colormap), float(bin_size)
+        pr.has_query_from_global = 0 if query_from_global is None else 1
+        if query_from_global is not None:
+            pr.query_from_global = (C.c_double * 7)(*[float(v) for v in query_from_global])
+        pr.background = (C.c_uint8 * 4)(*[int(v) for v in background])
+        pr.tile_size_px, pr.pixel_size_m = int(tile_size_px), float(pixel_size_m)
+        pr.root_level, pr.root_index = int(root[0]), int(root[1])
+        q = lib().orc_xray_quadtree_build(self.h, C.byref(pr))
+        if not q:
+            return None
+        try:
+            rect = (C.c_double * 3)()
+            deepest, nt = C.c_int(), C.c_uint64()
+            lib().orc_xray_quadtree_info(q, rect, C.byref(deepest), C.byref(nt))
+            levels = np.zeros(nt.value, np.uint8)
+            idx = np.zeros(nt.value, np.uint64)
+            lib().orc_xray_quadtree_ids(q, _ptr(levels), _ptr(idx))
+            tiles = {}
+            for l, i in zip(levels, idx):
+                img = np.zeros((tile_size_px, tile_size_px, 4), np.uint8)
+                assert lib().orc_xray_quadtree_tile(q, int(l), int(i), _ptr(img)) == 0
+                tiles[(int(l), int(i))] = img
+            return dict(rect_min_x=rect[0], rect_min_y=rect[1], rect_edge=rect[2], deepest_level=deepest.value, num_nodes=int(nt.value)), tiles
+        finally:
+            lib().orc_xray_quadtree_free(q)
 
     def xray_tile(self, bmin, bmax, w, h, query_from_global=None):
         rgba = np.zeros((h, w, 4), np.uint8)
