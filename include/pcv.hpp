@@ -194,6 +194,29 @@ class Octree {
         check(pcv_xray_tile_attr(o_, tile.min.data(), tile.max.data(), w, h, query_from_global7, strategy, p0, p1, colormap, rgba.data(), &any));
         return any != 0;
     }
+    // ... with Binning = Some(("intensity", bin_size)) for the Colored / ColoredWithIntensity strategies (generation.rs:129-157)
+    bool xray_tile_attr_binned(const Aabb& tile, uint32_t w, uint32_t h, int strategy, float p0, float p1, double bin_size, std::vector<uint8_t>& rgba,
+                               const double* query_from_global7 = nullptr) const {
+        rgba.assign((size_t)w * h * 4, 0);
+        int any = 0;
+        check(pcv_xray_tile_attr_binned(o_, tile.min.data(), tile.max.data(), w, h, query_from_global7, strategy, p0, p1, bin_size, rgba.data(), &any));
+        return any != 0;
+    }
+    // build_xray_quadtree (xray/src/generation.rs:560-622): every tile of the quadtree, leaves to root, through `on_tile`
+    // (level, index, RGBA tile_size_px^2); returns what the reference writes into the quadtree's meta.pb.
+    template <class F>
+    pcv_xray_quadtree_info build_xray_quadtree(const pcv_xray_quadtree_params& params, F&& on_tile) const {
+        struct Thunk {
+            F* f;
+            static int call(void* user, uint8_t level, uint64_t index, const uint8_t* rgba, uint32_t tile_px) {
+                (*static_cast<Thunk*>(user)->f)(level, index, rgba, tile_px);
+                return 0;
+            }
+        } th{&on_tile};
+        pcv_xray_quadtree_info info{};
+        check(pcv_xray_quadtree(o_, &params, &Thunk::call, &th, &info));
+        return info;
+    }
     void write_to_directory(const std::string& dir) const { check(pcv_octree_write_dir(o_, dir.c_str())); }
     pcv_octree* raw() const { return o_; }
 

@@ -28,6 +28,30 @@ def test_struct_layouts_match_header():
     assert C.sizeof(N.PlyInfo) == 96 and N.PlyInfo.offset.offset == 72 and N.PlyInfo.off_intensity.offset == 64
 
 
+def test_xray_quadtree_structs_match_the_c_compiler(tmp_path):
+    """pcv_xray_quadtree_params / _info: ctypes sizes and field offsets equal gcc's for include/pcv.h."""
+    import subprocess
+
+    from point_cloud_viewer_b200 import _native as N
+
+    fields = {"pcv_xray_quadtree_params": [f for f, _ in N.XrayQuadtreeParams._fields_], "pcv_xray_quadtree_info": [f for f, _ in N.XrayQuadtreeInfo._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pcv.h"', "int main(void) {"]
+    for st, fs in fields.items():
+        src.append('printf("%s %%zu" "\\n", sizeof(%s));' % (st, st))
+        for f in fs:
+            src.append('printf("%s.%s %%zu" "\\n", offsetof(%s, %s));' % (st, f, st, f))
+    src.append("return 0; }")
+    c = tmp_path / "layout.c"
+    c.write_text(chr(10).join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(c)])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for st, cls in (("pcv_xray_quadtree_params", N.XrayQuadtreeParams), ("pcv_xray_quadtree_info", N.XrayQuadtreeInfo)):
+        assert int(got[st]) == C.sizeof(cls)
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (st, f)]) == getattr(cls, f).offset, (st, f)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the library refuses to create a context (there is no CPU path to fall back to)."""
     from point_cloud_viewer_b200 import _native as N
