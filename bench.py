@@ -342,6 +342,18 @@ def multi_gpu_parity_check(ctx, pcv, D, torch, dist, world, rank, dev, n_global,
     return verdict
 
 
+def _final_node_bytes(pcv, tree):
+    """Sum over the final nodes this rank holds of n (3 bpc + 3): local nodes at level >= k, plus the assembled top on rank 0."""
+
+    def part(octree, min_level):
+        return sum(int(m["num_points"]) * (3 * pcv.ENC_BYTES[int(m["enc"])] + 3) for name, m in octree.nodes.items() if len(name) - 1 >= min_level)
+
+    total = part(tree.local, tree.k)
+    if getattr(tree, "top", None) is not None:
+        total += part(tree.top, 0)
+    return total
+
+
 def full_size_check(tree, D, torch, dist, world, n, dev):
     """Size-independent invariants of the full-size sharded result, all-reduced over the ranks: every input point appears
     exactly once in the final nodes (count, sum and sum of squares of the global source indices, mod 2^64)."""
@@ -503,6 +515,23 @@ def run_ours(args):
         except Exception as e:
             out["full_size_check"] = {"ok": False, "error": str(e)[:300]}
         out["phases_ms"] = getattr(last, "phases_ms", None)
+        # whole-build HBM roofline of the sharded job (SURVEY 8d bytes: 27 per input point + every point once in its final
+        # encoding), per GPU.  One unconditional all-reduce: a rank whose local sum fails contributes a flag instead of hanging.
+        try:
+            final_bytes = float(_final_node_bytes(pcv, last))
+            bad = 0.0
+        except Exception:
+            final_bytes, bad = 0.0, 1.0
+        tb = torch.tensor([final_bytes, bad], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb)
+        if float(tb[1]) == 0.0:
+            peak, peak_src = _peaks()
+            algo = 27.0 * n * world + float(tb[0])
+            per_gpu = algo / world / (ms_per_step * 1e-3) / 1e9
+            out["roofline"] = {"bound": "hbm", "kernel": "whole sharded build (per GPU; every kernel + the exchange)", "achieved": per_gpu, "peak": peak, "unit": "GB/s",
+                               "frac": per_gpu / peak, "traffic": None, "peak_source": peak_src,
+                               "whole_build": {"algorithmic_bytes": int(algo), "achieved": per_gpu, "frac": per_gpu / peak},
+                               "note": "per-kernel rooflines are reported by the N = 1 run (same kernels); the exchange phase moves 17 B per point over NVLink (phases_ms.exchange)"}
 
     if world == 1 and not args.no_extras:
         peak, peak_src = _peaks()

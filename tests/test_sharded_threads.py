@@ -9,6 +9,8 @@ import pytest
 
 import oracle_api as O
 import tb_api
+import bench
+import point_cloud_viewer_b200 as pcv
 from point_cloud_viewer_b200 import distributed as D
 
 
@@ -82,6 +84,7 @@ def _run(world_size, P, rgb, inten, res, maxpts, k):
     n = len(P)
     world = ThreadWorld(world_size)
     results, errors = [None] * world_size, []
+    final_bytes = [0] * world_size
     cuts = np.linspace(0, n, world_size + 1).astype(int)
 
     def worker(rank):
@@ -91,6 +94,7 @@ def _run(world_size, P, rgb, inten, res, maxpts, k):
             ops = tb_api.TbOps(x, y, z, rgb[3 * lo:3 * hi].copy(), inten[lo:hi].copy(), res, P.min(0), P.max(0), maxpts)
             comm = ThreadComm(world, rank)
             tree = D.build_sharded(ops, comm, int(lo), prefix_levels=k, max_points_per_node=maxpts)
+            final_bytes[rank] = bench._final_node_bytes(pcv, tree)
             results[rank] = (tree.gather_all(comm), tree.k, tree.bbox_inside)
         except BaseException as e:  # noqa: BLE001 - release the other threads
             errors.append(e)
@@ -103,7 +107,7 @@ def _run(world_size, P, rgb, inten, res, maxpts, k):
         t.join()
     if errors:
         raise errors[0]
-    return results[0]
+    return results[0] + (sum(final_bytes),)
 
 
 CASES = [
@@ -116,11 +120,13 @@ CASES = [
 @pytest.mark.parametrize("world_size,kind,n,maxpts,k,res", CASES)
 def test_sharded_build_equals_single_build(world_size, kind, n, maxpts, k, res):
     P, rgb, inten = _cloud(kind, n, world_size * 1000 + n)
-    nodes, k_used, inside = _run(world_size, P, rgb, inten, res, maxpts, k)
+    nodes, k_used, inside, final_bytes = _run(world_size, P, rgb, inten, res, maxpts, k)
     assert inside and 1 <= k_used <= k
     x, y, z = [np.ascontiguousarray(P[:, i]) for i in range(3)]
     ref = O.build(x, y, z, rgb.reshape(-1, 3), res, P.min(0), P.max(0), intensity=inten, max_points_per_node=maxpts)
     assert set(nodes) == set(ref.nodes), sorted(set(nodes) ^ set(ref.nodes))[:10]
+    # bench.py's N > 1 roofline numerator: every final node exactly once over the ranks (sum of n (3 bpc + 3))
+    assert final_bytes == sum(m["num_points"] * (3 * pcv.ENC_BYTES[m["enc"]] + 3) for m in ref.nodes.values())
     for name, m in ref.nodes.items():
         g = nodes[name]
         assert (g["num_points"], g["enc"], tuple(g["cube"])) == (m["num_points"], m["enc"], tuple(m["cube"])), name
