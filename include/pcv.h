@@ -243,6 +243,36 @@ typedef int (*pcv_xray_tile_fn)(void* user, uint8_t level, uint64_t index, const
 int pcv_xray_quadtree(const pcv_octree* o, const pcv_xray_quadtree_params* params, pcv_xray_tile_fn on_tile, void* user,
                       pcv_xray_quadtree_info* info_out);
 
+/* ---- f4: the S2-cell point cloud (src/read_write/s2.rs, src/s2_cells/mod.rs, src/geometry/s2_cell_union.rs) ---- */
+/* Cell ids are the S2 library's 64-bit CellID values (face, Hilbert position, level marker bit); the arithmetic is the `s2`
+ * crate's, restated (csrc/s2.h): integer and IEEE +, *, /, sqrt only, identical on host and device. */
+/* CellID::from_point(p).parent(level) for every point (src/math/mod.rs:119-131). */
+int pcv_s2_cell_ids(pcv_ctx* ctx, const pcv_points* host_points, uint32_t level, uint64_t* ids_out);
+/* S2Splitter::write over the cloud + get_meta (read_write/s2.rs:52-125,165-173; DEFAULT_S2_SPLIT_LEVEL = 20): every point must
+ * be a valid ECEF point (|p| in [6 352 800, 6 384 400] m, else PCV_ERR_INVALID with the reference's message); points are grouped
+ * by cell - cells in id order, inside a cell in input order - as Plain-encoded f64 positions plus colour / intensity. */
+typedef struct pcv_s2cloud pcv_s2cloud;
+int pcv_s2_build(pcv_ctx* ctx, const pcv_points* host_points, uint32_t split_level, pcv_s2cloud** out);
+int pcv_s2_build_device(pcv_ctx* ctx, const pcv_points* dev_points, uint32_t split_level, pcv_s2cloud** out);
+void pcv_s2_free(pcv_s2cloud* cloud);
+/* S2Meta: cells + num_points (mod.rs:23-41), bounding box, attributes. */
+int pcv_s2_info(const pcv_s2cloud* cloud, uint64_t* num_cells, uint64_t* num_points, uint32_t* split_level, double bbox_min[3],
+                double bbox_max[3], int* has_color, int* has_intensity);
+int pcv_s2_cells(const pcv_s2cloud* cloud, uint64_t* ids_out, uint64_t* num_points_out);
+/* points_in_node (mod.rs:174-190): one cell's arrays; PCV_ERR_NOT_FOUND for an id the cloud does not hold. */
+int pcv_s2_cell_data(const pcv_s2cloud* cloud, uint64_t cell_id, double* xyz_out /* n*3 */, uint8_t* rgb_out, float* intensity_out,
+                     uint64_t* src_index_out);
+/* nodes_in_location for PointLocation::AllPoints (union_ids == NULL) and PointLocation::S2Cells (mod.rs:157-168, 233-241:
+ * the cells whose id range intersects the union's; the union is normalised first).  ids_out may be NULL to count. */
+int pcv_s2_cells_in_union(const pcv_s2cloud* cloud, const uint64_t* union_ids, uint32_t n_union, uint64_t* ids_out, uint64_t cap,
+                          uint64_t* n_out);
+/* The FilteredIterator over those cells with the CellUnion as PointCulling (s2_cell_union.rs:27-31): survivors in cell order,
+ * input order inside a cell.  n_out = number of survivors (may exceed cap: only cap are written). */
+int pcv_s2_query_union(const pcv_s2cloud* cloud, const uint64_t* union_ids, uint32_t n_union, double* xyz_out, uint8_t* rgb_out,
+                       float* intensity_out, uint64_t* src_index_out, uint64_t cap, uint64_t* n_out, uint64_t* tested_out);
+/* CellUnion::contains for arbitrary points: mask_out[i] = union.contains_cellid(CellID::from_point(p_i)). */
+int pcv_s2_union_contains(pcv_ctx* ctx, const pcv_points* host_points, const uint64_t* union_ids, uint32_t n_union, uint8_t* mask_out);
+
 /* ---- multi-GPU helpers (points shard by level-k path prefix) ------------------ */
 /* Per-point level-k cell (first k steps of the re-quantising descent on the raw positions) ->
  * 8^k histogram; then a stable pack of the points of each destination rank into contiguous send

@@ -8,6 +8,7 @@
 #include "oracle_ply.hpp"
 #include "oracle_query.hpp"
 #include "oracle_xray_pyramid.hpp"
+#include "oracle_s2.hpp"
 #include "../include/pcv_synth.h"  // input-data generators shared with the benchmark (no algorithm code)
 
 using namespace orc;
@@ -508,6 +509,55 @@ int orc_xray_quadtree_tile(void* qp, uint8_t level, uint64_t index, uint8_t* rgb
     return 0;
 }
 void orc_xray_quadtree_free(void* qp) { delete (XrayQuadtree*)qp; }
+
+// ---- S2 (oracle_s2.hpp) ----
+void orc_s2_cell_ids(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, int level, uint64_t* out) {
+    for (uint64_t k = 0; k < n; ++k) out[k] = s2::parent(s2::cell_id_from_point(x[k * stride], y[k * stride], z[k * stride]), level);
+}
+void orc_s2_face_ij(uint64_t id, int* f, int* i, int* j) { s2::face_ij(id, *f, *i, *j); }
+void orc_s2_centre(uint64_t id, double* out3) {
+    const s2::V3 c = s2::cell_centre_raw(id);
+    out3[0] = c.x, out3[1] = c.y, out3[2] = c.z;
+}
+uint64_t orc_s2_from_face_ij(int f, int i, int j) { return s2::from_face_ij(f, i, j); }
+uint64_t orc_s2_parent(uint64_t id, int level) { return s2::parent(id, level); }
+uint64_t orc_s2_next(uint64_t id) { return s2::next(id); }
+int orc_s2_level(uint64_t id) { return s2::level_of(id); }
+void orc_s2_token(uint64_t id, char* buf, int cap) { snprintf(buf, cap, "%s", s2::to_token(id).c_str()); }
+uint64_t orc_s2_normalize(uint64_t* ids, uint64_t n) {
+    std::vector<uint64_t> v(ids, ids + n);
+    s2::normalize(v);
+    std::copy(v.begin(), v.end(), ids);
+    return v.size();
+}
+void orc_s2_union_test(const uint64_t* cu, uint64_t ncu, const uint64_t* ids, uint64_t m, uint8_t* contains_out, uint8_t* intersects_out) {
+    const std::vector<uint64_t> v(cu, cu + ncu);
+    for (uint64_t k = 0; k < m; ++k) {
+        if (contains_out) contains_out[k] = s2::union_contains(v, ids[k]) ? 1 : 0;
+        if (intersects_out) intersects_out[k] = s2::union_intersects(v, ids[k]) ? 1 : 0;
+    }
+}
+void* orc_s2_split(uint64_t n, const double* x, const double* y, const double* z, uint64_t stride, int level) {
+    return new s2::SplitResult(s2::split(x, y, z, stride, n, level));
+}
+void orc_s2_split_info(void* hp, int* ok, uint64_t* bad_index, double* bbox6, uint64_t* ncells) {
+    auto* r = (s2::SplitResult*)hp;
+    *ok = r->ok ? 1 : 0;
+    *bad_index = r->bad_index;
+    for (int a = 0; a < 3; ++a) bbox6[a] = r->bmin[a], bbox6[3 + a] = r->bmax[a];
+    *ncells = r->cells.size();
+}
+void orc_s2_split_cells(void* hp, uint64_t* ids, uint64_t* counts, uint64_t* order) {
+    auto* r = (s2::SplitResult*)hp;
+    size_t c = 0, o = 0;
+    for (auto& kv : r->cells) {
+        ids[c] = kv.first;
+        counts[c] = kv.second.size();
+        ++c;
+        for (uint64_t i : kv.second) order[o++] = i;
+    }
+}
+void orc_s2_split_free(void* hp) { delete (s2::SplitResult*)hp; }
 
 // ---- disk ----
 int orc_write_dir(void* hp, const char* dir) { return write_dir(((Handle*)hp)->oct, dir) ? 0 : -1; }

@@ -95,6 +95,36 @@ class Context:
         del keep
         return Octree(self, out)
 
+    # -- S2-cell point cloud (src/read_write/s2.rs, src/s2_cells/mod.rs)
+    def s2_cell_ids(self, x, y, z, level, stride=1, n=None):
+        """CellID::from_point(p).parent(level) for host points."""
+        n = int(n if n is not None else len(x) // (1 if stride == 1 else 1))
+        pts = N.Points(_p(x), _p(y), _p(z), stride, None, None, n)
+        out = np.zeros(n, np.uint64)
+        N.check(N.lib().pcv_s2_cell_ids(self.h, C.byref(pts), int(level), _p(out)))
+        return out
+
+    def build_s2_cloud(self, x, y, z, rgb=None, intensity=None, split_level=20, stride=1, n=None, device=False):
+        """S2Splitter::write over the whole cloud + get_meta (read_write/s2.rs:52-125,165-173): an S2Cloud resident in HBM."""
+        if n is None:
+            n = len(x)
+        keep = (x, y, z, rgb, intensity)
+        pts = N.Points(_p(x), _p(y), _p(z), stride, _p(rgb), _p(intensity), int(n))
+        out = C.c_void_p()
+        fn = N.lib().pcv_s2_build_device if device else N.lib().pcv_s2_build
+        N.check(fn(self.h, C.byref(pts), int(split_level), C.byref(out)))
+        del keep
+        return S2Cloud(self, out)
+
+    def s2_union_contains(self, x, y, z, union_ids, stride=1, n=None):
+        """CellUnion as PointCulling (geometry/s2_cell_union.rs:27-31): boolean mask over host points."""
+        n = int(n if n is not None else len(x))
+        pts = N.Points(_p(x), _p(y), _p(z), stride, None, None, n)
+        u = np.ascontiguousarray(union_ids, np.uint64)
+        mask = np.zeros(n, np.uint8)
+        N.check(N.lib().pcv_s2_union_contains(self.h, C.byref(pts), _p(u), len(u), _p(mask)))
+        return mask.astype(bool)
+
     # -- PLY input (src/read_write/ply.rs, generation.rs:256-287)
     def load_ply(self, path):
         """PlyIterator + find_bounding_box in one pass: the file's points as device SoA arrays.  Returns a PlyPoints."""
@@ -586,6 +616,70 @@ class Octree:
         info = N.XrayQuadtreeInfo()
         N.check(N.lib().pcv_xray_quadtree(self.h, C.byref(pr), N.XRAY_TILE_FN(cb), None, C.byref(info)))
         return {k: getattr(info, k) for k, _ in N.XrayQuadtreeInfo._fields_}, tiles
+
+
+class S2Cloud:
+    """pcv_s2cloud: the S2-cell point cloud (S2Cells / S2Meta of src/s2_cells/mod.rs) resident in HBM."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        nc, npnt, lvl = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        hc, hi = C.c_int(), C.c_int()
+        N.check(N.lib().pcv_s2_info(self.h, C.byref(nc), C.byref(npnt), C.byref(lvl), mn, mx, C.byref(hc), C.byref(hi)))
+        self.num_cells, self.num_points, self.split_level = nc.value, npnt.value, lvl.value
+        self.bbox_min, self.bbox_max = np.array(mn), np.array(mx)
+        self.has_color, self.has_intensity = bool(hc.value), bool(hi.value)
+        self.cell_ids = np.zeros(self.num_cells, np.uint64)
+        self.cell_counts = np.zeros(self.num_cells, np.uint64)
+        N.check(N.lib().pcv_s2_cells(self.h, _p(self.cell_ids), _p(self.cell_counts)))
+
+    def free(self):
+        if self.h:
+            N.lib().pcv_s2_free(self.h)
+            self.h = None
+
+    def cell_data(self, cell_id):
+        """points_in_node: (xyz f64 (n, 3), rgb or None, intensity or None, source index)."""
+        k = int(np.searchsorted(self.cell_ids, np.uint64(cell_id)))
+        n = int(self.cell_counts[k]) if k < self.num_cells and int(self.cell_ids[k]) == int(cell_id) else 0
+        xyz = np.zeros((n, 3), np.float64)
+        rgb = np.zeros((n, 3), np.uint8) if self.has_color else None
+        inten = np.zeros(n, np.float32) if self.has_intensity else None
+        src = np.zeros(n, np.uint64)
+        N.check(N.lib().pcv_s2_cell_data(self.h, int(cell_id), _p(xyz), _p(rgb), _p(inten), _p(src)))
+        return xyz, rgb, inten, src
+
+    def cells_in_union(self, union_ids=None):
+        """nodes_in_location for AllPoints (None) / S2Cells(CellUnion)."""
+        u = None if union_ids is None else np.ascontiguousarray(union_ids, np.uint64)
+        out = np.zeros(self.num_cells, np.uint64)
+        n = C.c_uint64()
+        N.check(N.lib().pcv_s2_cells_in_union(self.h, _p(u), 0 if u is None else len(u), _p(out), len(out), C.byref(n)))
+        return out[: n.value]
+
+    def query_union(self, union_ids=None, cap=None):
+        """The filtered point stream of the location: dict(xyz, rgb, intensity, src, tested)."""
+        u = None if union_ids is None else np.ascontiguousarray(union_ids, np.uint64)
+        nu = 0 if u is None else len(u)
+        n, tested = C.c_uint64(), C.c_uint64()
+        if cap is None:
+            N.check(N.lib().pcv_s2_query_union(self.h, _p(u), nu, None, None, None, None, 0, C.byref(n), C.byref(tested)))
+            cap = n.value
+        xyz = np.zeros((cap, 3), np.float64)
+        rgb = np.zeros((cap, 3), np.uint8) if self.has_color else None
+        inten = np.zeros(cap, np.float32) if self.has_intensity else None
+        src = np.zeros(cap, np.uint64)
+        N.check(N.lib().pcv_s2_query_union(self.h, _p(u), nu, _p(xyz), _p(rgb), _p(inten), _p(src), cap, C.byref(n), C.byref(tested)))
+        m = min(cap, n.value)
+        return dict(xyz=xyz[:m], rgb=None if rgb is None else rgb[:m], intensity=None if inten is None else inten[:m], src=src[:m], total=n.value, tested=tested.value)
+
+
+def s2_token(cell_id):
+    """CellID::to_token: the per-cell file stem of the reference's S2 directory layout."""
+    if int(cell_id) == 0:
+        return "X"
+    return ("%016x" % int(cell_id)).rstrip("0")
 
 
 def xray_node_name(level, index):

@@ -21,6 +21,7 @@
 #include "kernels_shard.cuh"
 #include "query.cuh"
 #include "xray_pyramid.cuh"
+#include "s2.cuh"
 #include "synth.cuh"
 
 using namespace pcv;
@@ -663,6 +664,7 @@ int pcv_synth_bbox(int kind, double bbox_min[3], double bbox_max[3], double* res
 
 #include "query_api.inl"
 #include "xray_api.inl"
+#include "s2_api.inl"
 #include "ply_api.inl"
 #include "shard_api.inl"
 #include "sharded_build.inl"

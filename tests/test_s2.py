@@ -1,0 +1,150 @@
+"""S2 cell arithmetic without a GPU.  The `s2` crate is not vendored and the reference holds no S2 golden
+vector, so the oracle's restatement is checked against the structural invariants S2 publishes; the product's csrc/s2.h (a
+different formulation of the same curve) must then equal the oracle bit for bit."""
+import numpy as np
+import pytest
+
+import s2_api as S
+
+L = S.orc
+
+
+def _ecef(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    return v * rng.uniform(6352800.0, 6384400.0, (n, 1))
+
+
+def test_face_cells_and_tokens():
+    axes = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]], float)
+    ids = S.oracle_cell_ids(axes, 0)
+    assert [int(i) for i in ids] == [(f << 61) | (1 << 60) for f in range(6)]
+    assert [S.token(i) for i in ids] == ["1", "3", "5", "7", "9", "b"]
+    assert S.token(0) == "X"
+    # the leaf cell of (1, 0, 0): (i, j) = (2^29, 2^29) is the first leaf of the face centre's third child
+    assert int(S.oracle_cell_ids(axes[:1], 30)[0]) == 0x1000000000000001
+    assert S.token(0x1000000000000001) == "1000000000000001"
+
+
+def test_hierarchy():
+    P = _ecef(2000, 1)
+    leaf = S.oracle_cell_ids(P, 30)
+    prev = leaf
+    for level in range(29, -1, -1):
+        cur = S.oracle_cell_ids(P, level)
+        lsb = cur & (~cur + np.uint64(1))
+        assert (lsb == np.uint64(1) << np.uint64(2 * (30 - level))).all()
+        assert ((cur - (lsb - np.uint64(1)) <= prev) & (prev <= cur + (lsb - np.uint64(1)))).all()  # the parent's range holds the child
+        assert all(L().orc_s2_parent(int(p), level) == int(c) for p, c in zip(prev[:50], cur[:50]))
+        prev = cur
+
+
+@pytest.mark.parametrize("level", [1, 2, 5, 11, 20, 30])
+def test_hilbert_curve_is_continuous_inside_a_face(level):
+    """Consecutive cells along the curve share an edge: their (i, j) differ by one cell size in exactly one coordinate.  This
+    exercises both look-up tables (ij -> pos on the way in, pos -> ij on the way out) over whole 4-level chunks."""
+    rng = np.random.default_rng(level)
+    size = 1 << (30 - level)
+    for _ in range(300):
+        f = int(rng.integers(0, 6))
+        i, j = (int(v) for v in rng.integers(0, 1 << 30, 2))
+        c = L().orc_s2_parent(L().orc_s2_from_face_ij(f, i, j), level)
+        n = L().orc_s2_next(c)
+        if (n >> 61) != (c >> 61):
+            continue  # last cell of the face
+        f0, i0, j0 = S.face_ij(c)
+        f1, i1, j1 = S.face_ij(n)
+        a, b = abs((i0 & -size) - (i1 & -size)), abs((j0 & -size) - (j1 & -size))
+        assert f0 == f1 == f and sorted((a, b)) == [0, size], (hex(c), hex(n))
+        assert S.face_ij(L().orc_s2_from_face_ij(f, i, j)) == (f, i, j)  # the two tables are inverse to each other
+
+
+def test_curve_is_continuous_across_faces_and_centres_round_trip():
+    """The last cell of face f touches the first cell of face f + 1 (the face (u, v) frames are chosen for exactly that), and
+    the centre of a cell maps back to the cell: xyz -> face / uv and face / uv -> xyz agree in every face's sign conventions."""
+    for level in (3, 10, 18):
+        ang = 4.0 / (1 << level)  # well above one cell diagonal, far below a face
+        for f in range(6):
+            last = L().orc_s2_parent(((f + 1) << 61) - 1, level)
+            first = L().orc_s2_parent(((f + 1) % 6) << 61 | 1, level)
+            a, b = S.centre(last), S.centre(first)
+            a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+            assert np.arccos(np.clip(a @ b, -1, 1)) < ang, (level, f)
+    rng = np.random.default_rng(3)
+    for level in (0, 1, 7, 20, 30):
+        cells = [L().orc_s2_parent(L().orc_s2_from_face_ij(int(rng.integers(0, 6)), *(int(v) for v in rng.integers(0, 1 << 30, 2))), level) for _ in range(200)]
+        C = np.array([S.centre(c) for c in cells])
+        assert [int(v) for v in S.oracle_cell_ids(C * 6.37e6 / np.linalg.norm(C, axis=1)[:, None], level)] == cells
+        assert all(L().orc_s2_level(c) == level for c in cells)
+
+
+def test_product_cell_ids_equal_the_oracle():
+    P = np.concatenate([_ecef(200000, 5), _ecef(1000, 6) / 6.37e6, _ecef(1000, 7) * 1e-300,
+                        np.array([[1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1], [-1, -1, -1], [0, 0, 0], [1e308, 1e308, 1e308], [0.0, -0.0, 5.0]], float)])
+    for level in (30, 20, 12, 0):
+        got, valid = S.product_cell_ids(P, level)
+        assert np.array_equal(got, S.oracle_cell_ids(P, level)), level
+    with np.errstate(over="ignore"):
+        r = np.sqrt(P[:, 0] * P[:, 0] + P[:, 1] * P[:, 1] + P[:, 2] * P[:, 2])
+    assert np.array_equal(valid, ~((r > 6384400.0) | (r < 6352800.0))) and valid[:200000].all() and not valid[200000:].any()
+    rng = np.random.default_rng(8)
+    for _ in range(2000):
+        f, i, j = int(rng.integers(0, 6)), *(int(v) for v in rng.integers(0, 1 << 30, 2))
+        c = S.tb().tbs_from_face_ij(f, i, j)
+        assert c == L().orc_s2_from_face_ij(f, i, j) and S.tb().tbs_is_valid(c) and S.tb().tbs_level(c) == 30
+    for cid in (0, 1 << 60, 0x1000000000000001, 0x89c25a31c0000000, 0xb000000000000000):
+        assert S.token(cid, product=True) == S.token(cid)
+        back = S.C.c_uint64()
+        assert S.tb().tbs_from_token(S.token(cid).encode(), S.C.byref(back)) == 0 and back.value == cid
+    assert not S.tb().tbs_is_valid(0) and not S.tb().tbs_is_valid(0xc000000000000001) and not S.tb().tbs_is_valid(0x1000000000000002)
+
+
+def test_union_normalize_contains_intersects():
+    rng = np.random.default_rng(9)
+    P = _ecef(3000, 10)
+    leaves = S.oracle_cell_ids(P, 30)
+    # a messy union: cells of mixed levels, duplicates, children next to their parents, four siblings
+    base = [int(v) for v in S.oracle_cell_ids(P[:40], 12)] + [int(v) for v in S.oracle_cell_ids(P[:60], 16)] + [int(v) for v in S.oracle_cell_ids(P[40:50], 9)]
+    parent = int(S.oracle_cell_ids(P[100:101], 10)[0])
+    lsb = parent & -parent
+    kids = [parent - lsb + (lsb >> 2) * (2 * k + 1) // 1 for k in range(4)]  # the four children: parent.range_min + (2k+1) * child_lsb
+    kids = [(parent - (lsb - 1)) + (lsb >> 2) - 1 + k * (lsb >> 1) for k in range(4)]
+    assert all(L().orc_s2_parent(k, 10) == parent and L().orc_s2_level(k) == 11 for k in kids)
+    cu_in = np.array(base + base[:7] + kids, np.uint64)
+    cu = S.normalize(cu_in)
+    assert np.array_equal(cu, S.normalize(cu_in, product=True))
+    assert (np.diff(cu.astype(object)) > 0).all() and parent in [int(v) for v in cu] and not any(k in [int(v) for v in cu] for k in kids)
+    lo = cu - ((cu & (~cu + np.uint64(1))) - np.uint64(1))
+    hi = cu + ((cu & (~cu + np.uint64(1))) - np.uint64(1))
+    assert (lo[1:].astype(object) > hi[:-1].astype(object)).all()  # disjoint ranges
+    # every input cell is covered by the normalised union; brute-force membership agrees with the binary search
+    probe = np.concatenate([leaves, S.oracle_cell_ids(P, 14), S.oracle_cell_ids(P, 8), cu_in])
+    c, i = S.union_test(cu, probe)
+    plo = probe - ((probe & (~probe + np.uint64(1))) - np.uint64(1))
+    phi = probe + ((probe & (~probe + np.uint64(1))) - np.uint64(1))
+    want_c = np.array([bool(((lo <= p) & (p <= hi)).any()) for p in probe])
+    want_i = np.array([bool(((lo <= b) & (a <= hi)).any()) for a, b in zip(plo, phi)])
+    assert np.array_equal(c, want_c) and np.array_equal(i, want_i) and c[-len(cu_in):].all() and 0 < c[:3000].sum() < 3000
+    c2, i2 = S.union_test(cu, probe, product=True)
+    assert np.array_equal(c2, c) and np.array_equal(i2, i)
+    # the reference's own query shape (point_cloud_test/src/queries.rs:49-53): a cell and its successor
+    cell = int(S.oracle_cell_ids(P[:1], 20)[0])
+    pair = S.normalize(np.array([cell, L().orc_s2_next(cell)], np.uint64))
+    assert len(pair) in (1, 2) and S.union_test(pair, S.oracle_cell_ids(P[:1], 30))[0][0]
+
+
+def test_split_restatement():
+    P = _ecef(5000, 11)
+    P[100:200] = P[100]  # one crowded cell
+    r = S.split(P, 12)
+    ids = S.oracle_cell_ids(P, 12)
+    assert r["ok"] and np.array_equal(r["ids"], np.unique(ids)) and r["counts"].sum() == len(P)
+    assert np.array_equal(r["bmin"], P.min(0)) and np.array_equal(r["bmax"], P.max(0))
+    o = 0
+    for cid, cnt in zip(r["ids"], r["counts"]):
+        assert np.array_equal(r["order"][o:o + int(cnt)], np.nonzero(ids == cid)[0])  # input order inside every cell
+        o += int(cnt)
+    P[777] *= 1.01  # "is not a valid ECEF point"
+    bad = S.split(P, 12)
+    assert not bad["ok"] and bad["bad_index"] == 777
