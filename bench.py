@@ -659,7 +659,7 @@ def run_ours(args):
         except Exception as e:
             out["ply_ingest"] = {"error": str(e)[:200]}
 
-        # ---- the whole X-ray quadtree (leaves, background, Lanczos3 parents) - in a child process, last ----
+        # ---- SURVEY 8(f3, f4): the whole X-ray quadtree (leaves, background, Lanczos3 parents) and the S2-cell cloud split - in a child process, last ----
         try:
             import subprocess
 
@@ -668,7 +668,9 @@ def run_ours(args):
             r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "xray_pyramid_bench.py"), "--points", str(int(args.cpu_points)), "--tile-px", str(int(args.xray_px)),
                                 "--peak", str(peak)], capture_output=True, text=True, timeout=420)
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            out["xray_quadtree"] = json.loads(line[-1]) if line else {"error": ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-300:]}
+            extra = json.loads(line[-1]) if line else {"xray_quadtree": {"error": ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-300:]}}
+            out["xray_quadtree"] = extra.get("xray_quadtree")
+            out["s2_cloud"] = extra.get("s2_cloud")
         except Exception as e:
             out["xray_quadtree"] = {"error": str(e)[:300]}
     else:

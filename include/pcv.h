@@ -259,6 +259,9 @@ void pcv_s2_free(pcv_s2cloud* cloud);
 int pcv_s2_info(const pcv_s2cloud* cloud, uint64_t* num_cells, uint64_t* num_points, uint32_t* split_level, double bbox_min[3],
                 double bbox_max[3], int* has_color, int* has_intensity);
 int pcv_s2_cells(const pcv_s2cloud* cloud, uint64_t* ids_out, uint64_t* num_points_out);
+/* Device time of the build (CUDA events: keys, sort, run starts, gather; the bounding-box pass and the host reads between them
+ * included), kernel launches, and the compulsory bytes: every point read once and written once into its cell. */
+int pcv_s2_build_stats(const pcv_s2cloud* cloud, float* ms_device, uint32_t* kernel_launches, uint64_t* algorithmic_bytes);
 /* points_in_node (mod.rs:174-190): one cell's arrays; PCV_ERR_NOT_FOUND for an id the cloud does not hold. */
 int pcv_s2_cell_data(const pcv_s2cloud* cloud, uint64_t cell_id, double* xyz_out /* n*3 */, uint8_t* rgb_out, float* intensity_out,
                      uint64_t* src_index_out);

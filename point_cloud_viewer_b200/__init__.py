@@ -639,6 +639,11 @@ class S2Cloud:
             N.lib().pcv_s2_free(self.h)
             self.h = None
 
+    def build_stats(self):
+        ms, l, b = C.c_float(), C.c_uint32(), C.c_uint64()
+        N.check(N.lib().pcv_s2_build_stats(self.h, C.byref(ms), C.byref(l), C.byref(b)))
+        return dict(ms_device=ms.value, kernel_launches=l.value, algorithmic_bytes=b.value)
+
     def cell_data(self, cell_id):
         """points_in_node: (xyz f64 (n, 3), rgb or None, intensity or None, source index)."""
         k = int(np.searchsorted(self.cell_ids, np.uint64(cell_id)))

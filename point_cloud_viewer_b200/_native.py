@@ -190,6 +190,7 @@ SYMBOLS = [
     ("pcv_s2_free", None, [C.c_void_p]),
     ("pcv_s2_info", C.c_int, [C.c_void_p, _u64p, _u64p, C.POINTER(C.c_uint32), _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("pcv_s2_cells", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("pcv_s2_build_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32), _u64p]),
     ("pcv_s2_cell_data", C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("pcv_s2_cells_in_union", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, _u64p]),
     ("pcv_s2_query_union", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, _u64p, _u64p]),

@@ -23,6 +23,8 @@ struct pcv_s2cloud {
     uint8_t* d_rgb = nullptr;
     float* d_intensity = nullptr;
     uint32_t* d_src = nullptr;                  // input index of every slot
+    float ms_device = 0.f;                      // CUDA events around the build's kernels (keys ... gather)
+    uint32_t kernel_launches = 0;
 };
 
 namespace {
@@ -65,6 +67,16 @@ pcv_s2cloud* s2_build_core(pcv_ctx* c, const PointsView& v, uint32_t level) {
     unsigned long long* scal = sc.alloc<unsigned long long>(3);  // first bad index, run count, run cursor
     const unsigned long long init[3] = {~0ull, 0ull, 0ull};
     c->be->h2d(scal, init, sizeof init);
+    struct Ev {
+        cudaEvent_t e = nullptr;
+        ~Ev() {
+            if (e) cudaEventDestroy(e);
+        }
+    } ev0, ev1;
+    CU(cudaEventCreate(&ev0.e));
+    CU(cudaEventCreate(&ev1.e));
+    const uint64_t l0 = c->be->launches;
+    CU(cudaEventRecord(ev0.e, c->stream));
     k_s2_keys<<<s2_grid(c, n), 256, 0, c->stream>>>(v, (int)level, keys, idx, scal);
     c->be->launches++;
     CU(cudaGetLastError());
@@ -125,7 +137,10 @@ pcv_s2cloud* s2_build_core(pcv_ctx* c, const PointsView& v, uint32_t level) {
     k_s2_gather<<<s2_grid(c, n), 256, 0, c->stream>>>(g);
     c->be->launches++;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ev1.e, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&s->ms_device, ev0.e, ev1.e);
+    s->kernel_launches = (uint32_t)(c->be->launches - l0);
     s->d_xyz = g.xyz;
     s->d_rgb = g.rgb;
     s->d_intensity = g.intensity;
@@ -237,6 +252,15 @@ int pcv_s2_info(const pcv_s2cloud* s, uint64_t* num_cells, uint64_t* num_points,
     }
     if (has_color) *has_color = s->has_rgb ? 1 : 0;
     if (has_intensity) *has_intensity = s->has_intensity ? 1 : 0;
+    return PCV_OK;
+}
+
+int pcv_s2_build_stats(const pcv_s2cloud* s, float* ms_device, uint32_t* kernel_launches, uint64_t* algorithmic_bytes) {
+    if (!s) return fail(PCV_ERR_INVALID, "null argument");
+    if (ms_device) *ms_device = s->ms_device;
+    if (kernel_launches) *kernel_launches = s->kernel_launches;
+    // every input point read once (24 + 3 + 4 B) and written once into its cell (the same bytes)
+    if (algorithmic_bytes) *algorithmic_bytes = 2ull * s->n * (24ull + (s->has_rgb ? 3ull : 0ull) + (s->has_intensity ? 4ull : 0ull));
     return PCV_OK;
 }
 

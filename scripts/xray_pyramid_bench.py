@@ -1,5 +1,7 @@
-"""The X-ray quadtree (leaves -> background -> parents) on the GPU over a sample octree: parity against the oracle at a tile
-size the oracle finishes in seconds, then device timings at BASELINE config 5's tile size.  Prints ONE JSON object.
+"""SURVEY 8(f3) and 8(f4) legs.  The X-ray quadtree (leaves -> background -> parents) on the GPU over a sample octree: parity
+against the oracle at a tile size the oracle finishes in seconds, then device timings at BASELINE config 5's tile size; and
+the S2-cell cloud split of a synthetic ECEF slab: device time, HBM fraction, parity and the CPU port.  Prints ONE JSON object
+{"xray_quadtree": ..., "s2_cloud": ...}.
 bench.py runs this in a child process as its last leg (these entry points were added after the round's last GPU session; a
 child process keeps a failure here away from the benchmark's own line)."""
 import argparse
@@ -19,19 +21,36 @@ def main():
     ap.add_argument("--tile-px", type=int, default=4096)
     ap.add_argument("--parity-px", type=int, default=256)
     ap.add_argument("--peak", type=float, default=0.0, help="HBM peak in GB/s for the roofline fraction")
+    ap.add_argument("--s2-points", type=float, default=1e8)
     a = ap.parse_args()
     import numpy as np
 
     import oracle_api as O
     import point_cloud_viewer_b200 as pcv
 
+    cores = os.cpu_count() or 1
+    ctx = pcv.Context(0)
+    res_all = {}
+    try:
+        res_all["xray_quadtree"] = bench_quadtree(ctx, pcv, O, np, a, cores)
+    except Exception as e:  # noqa: BLE001
+        res_all["xray_quadtree"] = {"error": str(e)[:300]}
+    # ---- the S2-cell cloud of a synthetic ECEF slab (what point_cloud_test builds), split level 20 ----
+    try:
+        res_all["s2_cloud"] = bench_s2(ctx, pcv, O, np, int(a.s2_points), a.peak, cores)
+    except Exception as e:  # noqa: BLE001
+        res_all["s2_cloud"] = {"error": str(e)[:300]}
+    ctx.close()
+    print(json.dumps(res_all))
+
+
+def bench_quadtree(ctx, pcv, O, np, a, cores):
     out = {}
     n = int(a.points)
     cores = os.cpu_count() or 1
     kind = O.SYNTH_GAUSS_CLUSTERS
     x, y, z, rgb = O.synth_points(kind, 1, 0, n, num_threads=cores)
     bmin, bmax, res = O.synth_bbox(kind)
-    ctx = pcv.Context(0)
     tree = ctx.build_octree(x, y, z, rgb, res, bmin, bmax)
     ref = O.build(x, y, z, rgb.reshape(-1, 3), res, bmin, bmax, num_threads=cores)
     E = float(bmax[0] - bmin[0])
@@ -68,8 +87,48 @@ def main():
                                             "frac": (gbps / a.peak) if a.peak else None, "algorithmic_bytes": int(pbytes),
                                             "note": "children read once + the parent written once (the vertically reduced mosaic is intermediate traffic)"}}
     tree.free()
-    ctx.close()
-    print(json.dumps(out))
+    return out
+
+
+def bench_s2(ctx, pcv, O, np, n, peak, cores):
+    import s2_api as S
+
+    kind = pcv.SYNTH_SLAB_ECEF
+    bufs = [ctx.device_buffer((n,), "<f8") for _ in range(3)] + [ctx.device_buffer((3 * n,), "|u1")]
+    ctx.synth_points_device(kind, 80293751232, 0, n, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr)
+    best = None
+    for it in range(4):  # first call warms the pool up
+        cloud = ctx.build_s2_cloud(bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, None, split_level=20, n=n, device=True)
+        st = cloud.build_stats()
+        cells, pts = cloud.num_cells, cloud.num_points
+        cloud.free()
+        if it and (best is None or st["ms_device"] < best["ms_device"]):
+            best = st
+    gbps = best["algorithmic_bytes"] / (best["ms_device"] * 1e-3) / 1e9
+    out = {"points": int(pts), "cells": int(cells), "split_level": 20, "ms_device": best["ms_device"], "Mpoints_per_s": pts / (best["ms_device"] * 1e3),
+           "gpu_launches": int(best["kernel_launches"]),
+           "roofline": {"bound": "hbm", "kernel": "k_s2_keys + radix sort (cub) + k_s2_gather", "achieved": gbps, "peak": peak or None, "unit": "GB/s",
+                        "frac": (gbps / peak) if peak else None, "algorithmic_bytes": int(best["algorithmic_bytes"]),
+                        "note": "bytes = every point read once and written once into its cell (27 B each way); the sort's passes over (key, index) pairs are intermediate traffic"}}
+    # parity + CPU baseline on a bounded sample: the oracle's S2Splitter restatement (one thread, as the reference's writer is)
+    m = min(n, 2_000_000)
+    x, y, z, rgb = pcv.synth_points_host(kind, 80293751232, 0, m)
+    P = np.stack([x, y, z], 1)
+    t0 = time.perf_counter()
+    want = S.split(P, 20)
+    cpu_s = time.perf_counter() - t0
+    cloud = ctx.build_s2_cloud(x, y, z, rgb, None, split_level=20)
+    got_all = cloud.query_union(None)
+    equal = bool(np.array_equal(cloud.cell_ids, want["ids"]) and np.array_equal(cloud.cell_counts, want["counts"]) and np.array_equal(got_all["src"], want["order"])
+                 and np.array_equal(cloud.bbox_min, want["bmin"]) and np.array_equal(cloud.bbox_max, want["bmax"]))
+    cloud.free()
+    out["parity_check"] = {"equal": equal, "n": m, "cells": int(len(want["ids"])),
+                           "what": "pcv_s2_build == oracle S2Splitter restatement: cell ids, counts, bounding box, per-cell point order"}
+    out["cpu_baseline"] = {"value": m / cpu_s / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                           "sample": "first %d points of the same slab generator (oracle port of S2Splitter::write, one thread)" % m}
+    for b in bufs:
+        b.free()
+    return out
 
 
 if __name__ == "__main__":
