@@ -273,6 +273,12 @@ int pcv_s2_cells_in_union(const pcv_s2cloud* cloud, const uint64_t* union_ids, u
  * input order inside a cell.  n_out = number of survivors (may exceed cap: only cap are written). */
 int pcv_s2_query_union(const pcv_s2cloud* cloud, const uint64_t* union_ids, uint32_t n_union, double* xyz_out, uint8_t* rgb_out,
                        float* intensity_out, uint64_t* src_index_out, uint64_t cap, uint64_t* n_out, uint64_t* tested_out);
+/* The directory an S2Splitter<RawNodeWriter> leaves behind (read_write/s2.rs:127-145, raw.rs): per cell `<to_token()>.xyz`
+ * (f64 LE x, y, z), `.rgb`, `.intensity`, and meta.pb = Meta { version 13, bounding_box, s2 { cells, attributes } }
+ * (s2_cells/mod.rs:77-104); load = S2Cells::from_data_provider over such a directory (:106-147, :203-216; versions < 12 and
+ * octree metas are rejected with the reference's messages). */
+int pcv_s2_write_dir(const pcv_s2cloud* cloud, const char* directory);
+int pcv_s2_load_dir(pcv_ctx* ctx, const char* directory, pcv_s2cloud** out);
 /* CellUnion::contains for arbitrary points: mask_out[i] = union.contains_cellid(CellID::from_point(p_i)). */
 int pcv_s2_union_contains(pcv_ctx* ctx, const pcv_points* host_points, const uint64_t* union_ids, uint32_t n_union, uint8_t* mask_out);
 

@@ -116,6 +116,12 @@ class Context:
         del keep
         return S2Cloud(self, out)
 
+    def load_s2_dir(self, directory):
+        """S2Cells::from_data_provider over an on-disk S2 directory."""
+        out = C.c_void_p()
+        N.check(N.lib().pcv_s2_load_dir(self.h, os.fsencode(str(directory)), C.byref(out)))
+        return S2Cloud(self, out)
+
     def s2_union_contains(self, x, y, z, union_ids, stride=1, n=None):
         """CellUnion as PointCulling (geometry/s2_cell_union.rs:27-31): boolean mask over host points."""
         n = int(n if n is not None else len(x))
@@ -638,6 +644,10 @@ class S2Cloud:
         if self.h:
             N.lib().pcv_s2_free(self.h)
             self.h = None
+
+    def write_dir(self, directory):
+        """<token>.xyz / .rgb / .intensity per cell + meta.pb, as S2Splitter<RawNodeWriter> leaves them."""
+        N.check(N.lib().pcv_s2_write_dir(self.h, os.fsencode(str(directory))))
 
     def build_stats(self):
         ms, l, b = C.c_float(), C.c_uint32(), C.c_uint64()

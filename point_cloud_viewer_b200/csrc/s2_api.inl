@@ -12,6 +12,8 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include "s2_disk.hpp"
+
 struct pcv_s2cloud {
     pcv_ctx* ctx = nullptr;
     uint32_t level = 20;
@@ -411,6 +413,133 @@ int pcv_s2_query_union(const pcv_s2cloud* s, const uint64_t* union_ids, uint32_t
     if (rgb_out) c->be->d2h(rgb_out, e.rgb_out, emit * 3);
     if (intensity_out) c->be->d2h(intensity_out, e.intensity_out, emit * 4);
     if (src_index_out) c->be->d2h(src_index_out, e.src_out, emit * 8);
+    return PCV_OK;
+    API_CATCH
+}
+
+// What S2Splitter<RawNodeWriter> + S2Meta::to_proto leave in a directory (s2_disk.hpp).
+int pcv_s2_write_dir(const pcv_s2cloud* s, const char* dir) {
+    if (!s || !dir) return fail(PCV_ERR_INVALID, "null argument");
+    if (s->n == 0) return fail(PCV_ERR_INVALID, "an S2 cloud without points has no meta (S2Splitter::get_meta returns None)");
+    API_TRY
+    pcv_ctx* c = s->ctx;
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    mkdir(dir, 0777);
+    const std::string base = std::string(dir) + "/";
+    std::vector<uint8_t> buf;
+    for (size_t k = 0; k < s->ids.size(); ++k) {
+        const uint64_t st = s->starts[k], n = s->counts[k];
+        const std::string stem = base + s2_to_token(s->ids[k]);
+        buf.resize(n * 24);
+        c->be->d2h(buf.data(), s->d_xyz + 3 * st, n * 24);
+        if (!write_whole_file(stem + ".xyz", buf.data(), n * 24)) return fail(PCV_ERR_IO, "cannot write %s.xyz", stem.c_str());
+        if (s->d_rgb) {
+            c->be->d2h(buf.data(), s->d_rgb + 3 * st, n * 3);
+            if (!write_whole_file(stem + ".rgb", buf.data(), n * 3)) return fail(PCV_ERR_IO, "cannot write %s.rgb", stem.c_str());
+        }
+        if (s->d_intensity) {
+            c->be->d2h(buf.data(), s->d_intensity + st, n * 4);
+            if (!write_whole_file(stem + ".intensity", buf.data(), n * 4)) return fail(PCV_ERR_IO, "cannot write %s.intensity", stem.c_str());
+        }
+    }
+    S2MetaData m;
+    for (int a = 0; a < 3; ++a) m.bbox_min[a] = s->bmin[a], m.bbox_max[a] = s->bmax[a];
+    m.ids = s->ids;
+    m.counts = s->counts;
+    m.has_color = s->has_rgb;
+    m.has_intensity = s->has_intensity;
+    const std::string meta = encode_s2_meta(m);
+    if (!write_whole_file(base + "meta.pb", meta.data(), meta.size())) return fail(PCV_ERR_IO, "cannot write %smeta.pb", base.c_str());
+    return PCV_OK;
+    API_CATCH
+}
+
+// S2Cells::from_data_provider over an OnDiskDataProvider (s2_cells/mod.rs:203-216, data_provider/on_disk.rs).
+int pcv_s2_load_dir(pcv_ctx* c, const char* dir, pcv_s2cloud** out) {
+    if (!c || !dir || !out) return fail(PCV_ERR_INVALID, "null argument");
+    API_TRY
+    std::lock_guard<std::mutex> g(c->mu);
+    CU(cudaSetDevice(c->device));
+    const std::string base = std::string(dir) + "/";
+    std::string raw;
+    if (!read_whole_file(base + "meta.pb", raw)) return fail(PCV_ERR_IO, "cannot read %smeta.pb", base.c_str());
+    S2MetaData m;
+    int version = 0;
+    const std::string err = decode_s2_meta(raw, m, version);
+    if (!err.empty()) return fail(PCV_ERR_INVALID, "%s", err.c_str());
+    // cells in id order (the proto carries them in hash-map order)
+    std::vector<size_t> order(m.ids.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return m.ids[a] < m.ids[b]; });
+    std::unique_ptr<pcv_s2cloud> s(new pcv_s2cloud());
+    s->ctx = c;
+    s->has_rgb = m.has_color;
+    s->has_intensity = m.has_intensity;
+    for (int a = 0; a < 3; ++a) s->bmin[a] = m.bbox_min[a], s->bmax[a] = m.bbox_max[a];
+    uint64_t n = 0;
+    int level = -1;
+    for (size_t k : order) {
+        if (!s2_is_valid(m.ids[k])) return fail(PCV_ERR_INVALID, "invalid S2 cell id %llx in meta.pb", (unsigned long long)m.ids[k]);
+        if (!s->ids.empty() && s->ids.back() == m.ids[k]) return fail(PCV_ERR_INVALID, "cell %s is listed twice", s2_to_token(m.ids[k]).c_str());
+        s->ids.push_back(m.ids[k]);
+        s->counts.push_back(m.counts[k]);
+        s->starts.push_back(n);
+        n += m.counts[k];
+        level = std::max(level, s2_level(m.ids[k]));
+    }
+    if (n > 0xFFFFFFFEull) return fail(PCV_ERR_UNSUPPORTED, "more than 2^32-2 points per context");
+    s->n = n;
+    s->level = (uint32_t)std::max(level, 0);
+    if (n == 0) {
+        *out = s.release();
+        return PCV_OK;
+    }
+    struct Own {
+        pcv_ctx* c;
+        std::vector<void*> p;
+        ~Own() {
+            for (void* q : p) c->be->dfree(q);
+        }
+    } own{c, {}};
+    double* dx = (double*)c->be->dmalloc(n * 24);
+    own.p.push_back(dx);
+    uint8_t* dr = nullptr;
+    float* di = nullptr;
+    uint32_t* ds = (uint32_t*)c->be->dmalloc(n * 4);
+    own.p.push_back(ds);
+    if (m.has_color) {
+        dr = (uint8_t*)c->be->dmalloc(n * 3);
+        own.p.push_back(dr);
+    }
+    if (m.has_intensity) {
+        di = (float*)c->be->dmalloc(n * 4);
+        own.p.push_back(di);
+    }
+    std::string data;
+    std::vector<uint32_t> iota;
+    for (size_t k = 0; k < s->ids.size(); ++k) {
+        const uint64_t st = s->starts[k], cnt = s->counts[k];
+        const std::string stem = base + s2_to_token(s->ids[k]);
+        auto load = [&](const char* ext, void* dst, uint64_t bytes) -> bool {
+            if (!read_whole_file(stem + ext, data) || data.size() != bytes) return false;
+            if (bytes) c->be->h2d(dst, data.data(), bytes);
+            return true;
+        };
+        if (!load(".xyz", dx + 3 * st, cnt * 24)) return fail(PCV_ERR_NOT_FOUND, "Could not read %llu points of cell %s.xyz", (unsigned long long)cnt, stem.c_str());
+        if (dr && !load(".rgb", dr + 3 * st, cnt * 3)) return fail(PCV_ERR_NOT_FOUND, "Could not read cell %s.rgb", stem.c_str());
+        if (di && !load(".intensity", di + st, cnt * 4)) return fail(PCV_ERR_NOT_FOUND, "Could not read cell %s.intensity", stem.c_str());
+        iota.resize(cnt);
+        for (uint64_t i = 0; i < cnt; ++i) iota[i] = (uint32_t)(st + i);  // no provenance on disk: the slot number
+        if (cnt) c->be->h2d(ds + st, iota.data(), cnt * 4);
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    s->d_xyz = dx;
+    s->d_rgb = dr;
+    s->d_intensity = di;
+    s->d_src = ds;
+    own.p.clear();
+    *out = s.release();
     return PCV_OK;
     API_CATCH
 }

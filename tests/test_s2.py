@@ -148,3 +148,68 @@ def test_split_restatement():
     P[777] *= 1.01  # "is not a valid ECEF point"
     bad = S.split(P, 12)
     assert not bad["ok"] and bad["bad_index"] == 777
+
+
+# ---- meta.pb of an S2 cloud: the product's writer / reader against python-protobuf (descriptor restating proto.proto:58-149) --
+def _tbs_meta():
+    L = S.tb()
+    L.tbs_encode_s2_meta.restype = S.C.c_int64
+    L.tbs_encode_s2_meta.argtypes = [S.C.c_void_p, S.C.c_void_p, S.C.c_void_p, S.C.c_uint64, S.C.c_int, S.C.c_int, S.C.c_void_p, S.C.c_uint64]
+    L.tbs_decode_s2_meta.restype = S.C.c_int64
+    L.tbs_decode_s2_meta.argtypes = [S.C.c_void_p, S.C.c_uint64, S.C.c_void_p, S.C.c_void_p, S.C.c_void_p, S.C.c_uint64, S.C.POINTER(S.C.c_int), S.C.POINTER(S.C.c_int),
+                                     S.C.POINTER(S.C.c_int), S.C.c_char_p, S.C.c_int]
+    return L
+
+
+def _decode(buf, cap=8192):
+    L = _tbs_meta()
+    bb = np.zeros(6)
+    ids, counts = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    hc, hi, ver = S.C.c_int(), S.C.c_int(), S.C.c_int()
+    err = S.C.create_string_buffer(256)
+    raw = np.frombuffer(buf, np.uint8)
+    n = L.tbs_decode_s2_meta(raw.ctypes.data, len(raw), bb.ctypes.data, ids.ctypes.data, counts.ctypes.data, cap, S.C.byref(hc), S.C.byref(hi), S.C.byref(ver), err, 256)
+    return n, bb, ids[:max(n, 0)], counts[:max(n, 0)], bool(hc.value), bool(hi.value), ver.value, err.value.decode()
+
+
+def test_s2_meta_against_python_protobuf():
+    from proto_meta import Meta
+
+    P = _ecef(4000, 21)
+    r = S.split(P, 18)
+    bb = np.concatenate([r["bmin"], r["bmax"]])
+    L = _tbs_meta()
+    for hc, hi in ((1, 1), (1, 0), (0, 0)):
+        out = np.zeros(1 << 20, np.uint8)
+        n = L.tbs_encode_s2_meta(bb.ctypes.data, r["ids"].ctypes.data, r["counts"].ctypes.data, len(r["ids"]), hc, hi, out.ctypes.data, len(out))
+        assert n > 0
+        raw = out[:n].tobytes()
+        m = Meta.FromString(raw)  # an independent parser
+        assert m.version == 13 and m.WhichOneof("data") == "s2" and not m.HasField("octree")
+        assert [c.id for c in m.s2.cells] == [int(v) for v in r["ids"]] and [c.num_points for c in m.s2.cells] == [int(v) for v in r["counts"]]
+        assert [(a.name, a.data_type) for a in m.s2.attributes] == ([("color", 27)] if hc else []) + ([("intensity", 11)] if hi else [])
+        bbm = m.bounding_box
+        assert [bbm.min.x, bbm.min.y, bbm.min.z, bbm.max.x, bbm.max.y, bbm.max.z] == list(bb)
+        assert m.SerializeToString() == raw  # canonical field order, nothing unknown
+        k, bb2, ids, counts, c2, i2, ver, err = _decode(raw)
+        assert (k, ver, err, c2, i2) == (len(r["ids"]), 13, "", bool(hc), bool(hi)) and np.array_equal(ids, r["ids"]) and np.array_equal(counts, r["counts"]) and np.array_equal(bb2, bb)
+    # what python-protobuf serialises (cells in another order, attributes swapped) is read back; other metas are rejected
+    m = Meta()
+    m.version = 13
+    m.bounding_box.min.x, m.bounding_box.max.z = -1.5, 7.25
+    for cid, cnt in ((0x89c25a31c0000000, 7), (0x1000000000000001, 1)):
+        c = m.s2.cells.add()
+        c.id, c.num_points = cid, cnt
+    a = m.s2.attributes.add()
+    a.name, a.data_type = "intensity", 11
+    a = m.s2.attributes.add()
+    a.name, a.data_type = "color", 27
+    k, bb2, ids, counts, c2, i2, ver, err = _decode(m.SerializeToString())
+    assert k == 2 and [int(v) for v in ids] == [0x89c25a31c0000000, 0x1000000000000001] and [int(v) for v in counts] == [7, 1] and c2 and i2 and bb2[0] == -1.5 and bb2[5] == 7.25
+    m.version = 11
+    assert _decode(m.SerializeToString())[7] == "No S2 point cloud supported with version 11"
+    o = Meta()
+    o.version = 13
+    o.octree.resolution = 0.5
+    assert _decode(o.SerializeToString())[7] == "This meta does not describe S2 point clouds"
+    assert _decode(b"\\x0a\\xff\\xff")[0] == -1
