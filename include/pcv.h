@@ -243,6 +243,12 @@ typedef int (*pcv_xray_tile_fn)(void* user, uint8_t level, uint64_t index, const
 int pcv_xray_quadtree(const pcv_octree* o, const pcv_xray_quadtree_params* params, pcv_xray_tile_fn on_tile, void* user,
                       pcv_xray_quadtree_info* info_out);
 
+/* ... with the reference's outputs: <directory>/<node id>.png for every tile ("r", "r0", "r123323": quadtree/src/lib.rs:216-233;
+ * 8-bit RGBA, deflated on the host with zlib) and the quadtree's meta file (xray Meta, version 3: bounding_rect, deepest_level,
+ * tile_size, nodes; "meta.pb" for the root, "meta<digits>.pb" for a sub-root: xray/src/utils.rs:7-11, lib.rs:88-139). */
+int pcv_xray_quadtree_write_dir(const pcv_octree* o, const pcv_xray_quadtree_params* params, const char* directory,
+                                pcv_xray_quadtree_info* info_out);
+
 /* ---- f4: the S2-cell point cloud (src/read_write/s2.rs, src/s2_cells/mod.rs, src/geometry/s2_cell_union.rs) ---- */
 /* Cell ids are the S2 library's 64-bit CellID values (face, Hilbert position, level marker bit); the arithmetic is the `s2`
  * crate's, restated (csrc/s2.h): integer and IEEE +, *, /, sqrt only, identical on host and device. */

@@ -623,6 +623,14 @@ class Octree:
         N.check(N.lib().pcv_xray_quadtree(self.h, C.byref(pr), N.XRAY_TILE_FN(cb), None, C.byref(info)))
         return {k: getattr(info, k) for k, _ in N.XrayQuadtreeInfo._fields_}, tiles
 
+    def xray_quadtree_write_dir(self, directory, tile_size_px, pixel_size_m, strategy=0, p0=0.0, p1=0.0, colormap=0, bin_size=0.0, query_from_global=None,
+                                background=(255, 255, 255, 255), root=(0, 0)):
+        """build_xray_quadtree with the reference's outputs: <directory>/<node id>.png + the quadtree's meta file."""
+        pr = _xray_params(tile_size_px, pixel_size_m, strategy, p0, p1, colormap, bin_size, query_from_global, background, root)
+        info = N.XrayQuadtreeInfo()
+        N.check(N.lib().pcv_xray_quadtree_write_dir(self.h, C.byref(pr), os.fsencode(str(directory)), C.byref(info)))
+        return {k: getattr(info, k) for k, _ in N.XrayQuadtreeInfo._fields_}
+
 
 class S2Cloud:
     """pcv_s2cloud: the S2-cell point cloud (S2Cells / S2Meta of src/s2_cells/mod.rs) resident in HBM."""
@@ -706,6 +714,18 @@ def xray_node_id(name):
     """NodeId::from_str (quadtree/src/lib.rs:201-213): (level, index)."""
     level = len(name) - 1
     return level, (int(name[1:], 4) if level > 0 else 0)
+
+
+def _xray_params(tile_size_px, pixel_size_m, strategy, p0, p1, colormap, bin_size, query_from_global, background, root):
+    pr = N.XrayQuadtreeParams()
+    pr.strategy, pr.p0, pr.p1, pr.colormap, pr.bin_size = int(strategy), float(p0), float(p1), int(colormap), float(bin_size)
+    pr.has_query_from_global = 0 if query_from_global is None else 1
+    if query_from_global is not None:
+        pr.query_from_global = (C.c_double * 7)(*[float(v) for v in query_from_global])
+    pr.background = (C.c_uint8 * 4)(*[int(v) for v in background])
+    pr.tile_size_px, pr.pixel_size_m = int(tile_size_px), float(pixel_size_m)
+    pr.root_level, pr.root_index = int(root[0]), int(root[1])
+    return pr
 
 
 def xray_assign_background(ctx, rgba, background):

@@ -184,6 +184,7 @@ SYMBOLS = [
     ("pcv_xray_assign_background", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("pcv_xray_build_parent", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("pcv_xray_quadtree", C.c_int, [C.c_void_p, C.POINTER(XrayQuadtreeParams), XRAY_TILE_FN, C.c_void_p, C.POINTER(XrayQuadtreeInfo)]),
+    ("pcv_xray_quadtree_write_dir", C.c_int, [C.c_void_p, C.POINTER(XrayQuadtreeParams), C.c_char_p, C.POINTER(XrayQuadtreeInfo)]),
     ("pcv_s2_cell_ids", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_uint32, C.c_void_p]),
     ("pcv_s2_build", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_uint32, C.POINTER(C.c_void_p)]),
     ("pcv_s2_build_device", C.c_int, [C.c_void_p, C.POINTER(Points), C.c_uint32, C.POINTER(C.c_void_p)]),

@@ -7,6 +7,8 @@
 // :560-622 (build_xray_quadtree), :624-667 (create_leaf_nodes), :669-693 (create_non_leaf_nodes), :695-720
 // (assign_background), :722-759 (build_node).
 
+#include "xray_png.hpp"
+
 namespace {
 
 using namespace pcv;
@@ -267,6 +269,43 @@ int pcv_xray_quadtree(const pcv_octree* oc, const pcv_xray_quadtree_params* pr, 
     info->leaf_points = leaf_points;
     return PCV_OK;
     API_CATCH
+}
+
+// build_xray_quadtree with the reference's outputs: <directory>/<node id>.png for every tile and the quadtree's meta file
+// (generation.rs:560-622: create_dir, images, meta.to_disk(get_meta_pb_path(output_directory, root_node_id))).
+int pcv_xray_quadtree_write_dir(const pcv_octree* oc, const pcv_xray_quadtree_params* pr, const char* dir, pcv_xray_quadtree_info* info) {
+    if (!oc || !pr || !dir || !info) return fail(PCV_ERR_INVALID, "null argument");
+    mkdir(dir, 0777);  // "Ignore errors, maybe directory is already there." (:565-566)
+    struct State {
+        std::string base;
+        XrayMetaData meta;
+        std::string err;
+    } st;
+    st.base = std::string(dir) + "/";
+    auto on_tile = [](void* user, uint8_t level, uint64_t index, const uint8_t* rgba, uint32_t t) -> int {
+        State* s = (State*)user;
+        std::string png;
+        const std::string path = s->base + quad_node_name(level, index) + ".png";
+        if (!encode_png_rgba(rgba, t, t, png) || !write_whole_file(path, png.data(), png.size())) {
+            s->err = "cannot write " + path;
+            return 1;
+        }
+        s->meta.nodes.emplace_back((uint32_t)level, index);
+        return 0;
+    };
+    const int rc = pcv_xray_quadtree(oc, pr, on_tile, &st, info);
+    if (rc == PCV_ERR_CANCELLED && !st.err.empty()) return fail(PCV_ERR_IO, "%s", st.err.c_str());
+    if (rc != PCV_OK) return rc;
+    st.meta.min_x = info->rect_min_x;
+    st.meta.min_y = info->rect_min_y;
+    st.meta.edge = info->rect_edge;
+    st.meta.deepest_level = info->deepest_level;
+    st.meta.tile_size = info->tile_size_px;
+    const std::string name = quad_node_name(pr->root_level, pr->root_index);  // "r..." -> "meta..." (utils.rs:7-11)
+    const std::string path = st.base + "meta" + name.substr(1) + ".pb";
+    const std::string buf = encode_xray_meta(st.meta);
+    if (!write_whole_file(path, buf.data(), buf.size())) return fail(PCV_ERR_IO, "cannot write %s", path.c_str());
+    return PCV_OK;
 }
 
 }  // extern "C"

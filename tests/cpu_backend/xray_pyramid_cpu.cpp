@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../point_cloud_viewer_b200/csrc/xray_pyramid.h"
+#include "../../point_cloud_viewer_b200/csrc/xray_png.hpp"
 
 using namespace pcv;
 
@@ -66,4 +67,23 @@ int tbx_rect_and_levels(const double* bmin, const double* bmax, uint32_t tile_px
     *levels = l;
     return 0;
 }
+// host side of the quadtree's on-disk form (csrc/xray_png.hpp)
+int64_t tbx_encode_png(const uint8_t* rgba, uint32_t w, uint32_t h, uint8_t* out, uint64_t cap) {
+    std::string png;
+    if (!encode_png_rgba(rgba, w, h, png)) return -1;
+    if (png.size() > cap) return -(int64_t)png.size();
+    std::memcpy(out, png.data(), png.size());
+    return (int64_t)png.size();
+}
+int64_t tbx_encode_xray_meta(double min_x, double min_y, double edge, uint32_t deepest, uint32_t tile, const uint32_t* levels, const uint64_t* indices, uint64_t n,
+                             uint8_t* out, uint64_t cap) {
+    XrayMetaData m;
+    m.min_x = min_x, m.min_y = min_y, m.edge = edge, m.deepest_level = deepest, m.tile_size = tile;
+    for (uint64_t k = 0; k < n; ++k) m.nodes.emplace_back(levels[k], indices[k]);
+    const std::string b = encode_xray_meta(m);
+    if (b.size() > cap) return -(int64_t)b.size();
+    std::memcpy(out, b.data(), b.size());
+    return (int64_t)b.size();
+}
+void tbx_node_name(uint8_t level, uint64_t index, char* buf, int cap) { snprintf(buf, cap, "%s", quad_node_name(level, index).c_str()); }
 }

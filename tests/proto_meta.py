@@ -143,3 +143,52 @@ def serialize_meta(bbox_min, bbox_max, resolution, nodes, version=13):
         p = m.octree.nodes.add()
         p.id.high, p.id.low, p.num_points, p.position_encoding = int(hi), int(lo), int(n), int(enc)
     return m.SerializeToString()
+
+
+def _build_xray_pool():
+    """xray_proto_rust/src/proto.proto:20-56 (package xray.proto), restated as a descriptor."""
+    from google.protobuf import descriptor_pb2
+
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name = "xray_restated.proto"
+    fd.package = "xray.proto"
+    fd.syntax = "proto3"
+
+    def field(m, name, number, ftype, label=F.LABEL_OPTIONAL, type_name=None):
+        f = m.field.add()
+        f.name, f.number, f.type, f.label = name, number, ftype, label
+        if type_name:
+            f.type_name = ".xray.proto." + type_name
+
+    m = fd.message_type.add()
+    m.name = "Vector2f"
+    field(m, "x", 1, F.TYPE_FLOAT)
+    field(m, "y", 2, F.TYPE_FLOAT)
+    m = fd.message_type.add()
+    m.name = "Vector2d"
+    field(m, "x", 1, F.TYPE_DOUBLE)
+    field(m, "y", 2, F.TYPE_DOUBLE)
+    m = fd.message_type.add()
+    m.name = "Rect"
+    field(m, "min", 3, F.TYPE_MESSAGE, type_name="Vector2d")
+    field(m, "edge_length", 4, F.TYPE_DOUBLE)
+    field(m, "deprecated_min", 1, F.TYPE_MESSAGE, type_name="Vector2f")
+    field(m, "deprecated_edge_length", 2, F.TYPE_FLOAT)
+    m = fd.message_type.add()
+    m.name = "NodeId"
+    field(m, "level", 1, F.TYPE_UINT32)
+    field(m, "index", 2, F.TYPE_UINT64)
+    m = fd.message_type.add()
+    m.name = "Meta"
+    field(m, "version", 1, F.TYPE_INT32)
+    field(m, "bounding_rect", 2, F.TYPE_MESSAGE, type_name="Rect")
+    field(m, "deepest_level", 3, F.TYPE_UINT32)
+    field(m, "tile_size", 4, F.TYPE_UINT32)
+    field(m, "nodes", 5, F.TYPE_MESSAGE, label=F.LABEL_REPEATED, type_name="NodeId")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return pool
+
+
+XrayMeta = message_factory.GetMessageClass(_build_xray_pool().FindMessageTypeByName("xray.proto.Meta"))

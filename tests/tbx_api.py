@@ -22,8 +22,36 @@ def lib():
         L.tbx_bin_of.argtypes = [C.c_float, C.c_double]
         L.tbx_quad_rect_of.argtypes = [C.c_uint8, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.tbx_rect_and_levels.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.tbx_encode_png.restype = C.c_int64
+        L.tbx_encode_png.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.tbx_encode_xray_meta.restype = C.c_int64
+        L.tbx_encode_xray_meta.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.tbx_node_name.argtypes = [C.c_uint8, C.c_uint64, C.c_char_p, C.c_int]
         _lib = L
     return _lib
+
+
+def encode_png(rgba):
+    img = np.ascontiguousarray(rgba, np.uint8)
+    out = np.zeros(img.size + img.shape[0] + (1 << 16), np.uint8)
+    n = lib().tbx_encode_png(img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data, len(out))
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def encode_xray_meta(min_x, min_y, edge, deepest, tile, nodes):
+    lv = np.array([l for l, _ in nodes], np.uint32)
+    ix = np.array([i for _, i in nodes], np.uint64)
+    out = np.zeros(1 << 16, np.uint8)
+    n = lib().tbx_encode_xray_meta(min_x, min_y, edge, deepest, tile, lv.ctypes.data, ix.ctypes.data, len(nodes), out.ctypes.data, len(out))
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def node_name(level, index):
+    buf = C.create_string_buffer(80)
+    lib().tbx_node_name(level, index, buf, 80)
+    return buf.value.decode()
 
 
 def build_parent(children, background, tile_px):

@@ -221,3 +221,30 @@ def test_oracle_quadtree_structure(small_tree):
     assert (info2["rect_min_x"], info2["rect_min_y"], info2["rect_edge"]) == T.quad_rect_of(sub[0], sub[1], rect)
     assert all(np.array_equal(tiles2[k], tiles[k]) for k in tiles2)
     assert ref.xray_quadtree(T_px, px, root=(3, 0)) is None  # "Specified root node id is outside quadtree."
+
+
+# ---- the quadtree's on-disk form: PNG tiles and the meta file (host code, csrc/xray_png.hpp) --------------------------------
+def test_png_round_trip_through_pillow():
+    import io
+
+    Image = pytest.importorskip("PIL.Image")
+    for img in (_noise(37, 1), _smooth(64, 2), np.full((5, 9, 4), 255, np.uint8), np.zeros((1, 1, 4), np.uint8)):
+        raw = T.encode_png(img)
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+        back = Image.open(io.BytesIO(raw))
+        back.load()
+        assert back.mode == "RGBA" and back.size == (img.shape[1], img.shape[0])
+        assert np.array_equal(np.asarray(back), img)
+
+
+def test_xray_meta_against_python_protobuf():
+    from proto_meta import XrayMeta
+
+    nodes = [(0, 0), (1, 2), (2, 11), (3, int("301", 4))]
+    raw = T.encode_xray_meta(300000.125, -200000.5, 1024.0, 3, 4096, nodes)
+    m = XrayMeta.FromString(raw)
+    assert m.version == 3 and m.deepest_level == 3 and m.tile_size == 4096  # CURRENT_VERSION, xray/src/lib.rs:15
+    assert (m.bounding_rect.min.x, m.bounding_rect.min.y, m.bounding_rect.edge_length) == (300000.125, -200000.5, 1024.0)
+    assert [(n.level, n.index) for n in m.nodes] == nodes and not m.bounding_rect.HasField("deprecated_min")
+    assert m.SerializeToString() == raw
+    assert [T.node_name(l, i) for l, i in nodes] == ["r", "r2", "r23", "r301"] == [pcv.xray_node_name(l, i) for l, i in nodes]
