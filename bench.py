@@ -12,7 +12,10 @@ over NVLink (one fused rank + peer-store kernel, CUDA-IPC mapped receive slabs; 
 inputs resident in HBM; `e2e` = the same build through the C-ABI host entry point: pinned host buffers -> H2D -> build -> D2H
 of the node arrays, all inside the timed region.  Next to it (N = 1): per-kernel roofline from CUDA events on the library's
 stream, the frustum query and X-ray tile workloads (configs 3 and 5) with their own rooflines and CPU baselines, the reference's
-own bench sizes (config 1) and a parity verdict of the GPU octree against the oracle on a sample of the same generator.
+own bench sizes (config 1), a parity verdict of the GPU octree against the oracle on a sample of the same generator, and - last,
+in a child process (scripts/xray_pyramid_bench.py) - the whole X-ray quadtree and the S2-cell split, each
+with device time, HBM fraction, CPU port and parity verdict.  N > 1 lines carry parity and full-size checks, the phase
+breakdown and the whole-build roofline per GPU.
 
 The reference arm never loads the CUDA library: generator, in-memory and file-backed ("faithful") builds all come from oracle/.
 """

@@ -213,3 +213,21 @@ def test_s2_meta_against_python_protobuf():
     o.octree.resolution = 0.5
     assert _decode(o.SerializeToString())[7] == "This meta does not describe S2 point clouds"
     assert _decode(b"\\x0a\\xff\\xff")[0] == -1
+
+
+def test_fuzz_product_against_oracle():
+    """hypothesis: arbitrary finite vectors (any magnitude, signs, exact ties between components) - csrc/s2.h == oracle."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    comp = st.one_of(st.floats(allow_nan=False, allow_infinity=False, width=64), st.sampled_from([0.0, -0.0, 1.0, -1.0, 0.5, 6.37e6, -6.37e6, 1e-310, 1e300]))
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(st.lists(st.tuples(comp, comp, comp), min_size=1, max_size=40), st.integers(0, 30))
+    def run(pts, level):
+        P = np.array(pts, np.float64)
+        with np.errstate(all="ignore"):
+            got, _ = S.product_cell_ids(P, level)
+            assert np.array_equal(got, S.oracle_cell_ids(P, level))
+
+    run()
