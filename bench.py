@@ -664,8 +664,6 @@ def run_ours(args):
 
         # ---- SURVEY 8(f3, f4): the whole X-ray quadtree (leaves, background, Lanczos3 parents) and the S2-cell cloud split - in a child process, last ----
         try:
-            import subprocess
-
             ctx.release_cached_memory()
             torch.cuda.empty_cache()
             r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "xray_pyramid_bench.py"), "--points", str(int(args.cpu_points)), "--tile-px", str(int(args.xray_px)),
