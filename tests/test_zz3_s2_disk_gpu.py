@@ -64,3 +64,26 @@ def test_write_dir_and_load_dir(ctx, tmp_path):
     with pytest.raises(pcv._native.PcvError) as e:
         ctx.load_s2_dir(d)
     assert e.value.code == -4
+
+
+def test_split_two_million_points(ctx):
+    """More points than one wave of the grid-stride kernels covers: cells, counts, per-cell order and a union query == oracle."""
+    import point_cloud_viewer_b200 as pcv
+
+    n = 2_000_000
+    x, y, z, rgb = pcv.synth_points_host(pcv.SYNTH_SLAB_ECEF, 80293751232, 0, n)
+    P = np.stack([x, y, z], 1)
+    want = S.split(P, 22)
+    cloud = ctx.build_s2_cloud(x, y, z, rgb, None, split_level=22)
+    assert np.array_equal(cloud.cell_ids, want["ids"]) and np.array_equal(cloud.cell_counts, want["counts"])
+    allp = cloud.query_union(None)
+    assert np.array_equal(allp["src"], want["order"]) and np.array_equal(allp["rgb"], rgb.reshape(-1, 3)[want["order"].astype(np.int64)])
+    u = S.oracle_cell_ids(P[:5], 17)
+    inside = S.union_test(S.normalize(u), S.oracle_cell_ids(P, 30))[0]
+    keep = want["order"][inside[want["order"].astype(np.int64)]]
+    got = cloud.query_union(u)
+    assert got["total"] == len(keep) > 1000 and np.array_equal(got["src"], keep)
+    assert np.array_equal(ctx.s2_cell_ids(x, y, z, 22), S.oracle_cell_ids(P, 22))
+    st = cloud.build_stats()
+    assert st["ms_device"] > 0 and st["kernel_launches"] >= 5 and st["algorithmic_bytes"] == 2 * n * 27
+    cloud.free()

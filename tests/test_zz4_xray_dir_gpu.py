@@ -42,3 +42,17 @@ def test_quadtree_directory(ctx, tmp_path):
         assert (m.bounding_rect.min.x, m.bounding_rect.min.y, m.bounding_rect.edge_length) == (oinfo["rect_min_x"], oinfo["rect_min_y"], oinfo["rect_edge"])
         assert {(k.level, k.index) for k in m.nodes} == set(otiles_r) and len(m.nodes) == info["num_nodes"]
     tree.free()
+
+
+def test_full_size_parent_tile(ctx):
+    """A 2048 x 2048 parent from four 2048 x 2048 children (one missing): more blocks than one wave of the grid-stride kernels,
+    byte-identical to the oracle."""
+    import point_cloud_viewer_b200 as pcv
+
+    rng = np.random.default_rng(5)
+    T = 2048
+    ch = [rng.integers(0, 256, (T, T, 4), dtype=np.uint8) if k != 2 else None for k in range(4)]
+    got = pcv.xray_build_parent(ctx, ch, (255, 255, 255, 0), T)
+    assert np.array_equal(got, O.build_parent_tile(ch, (255, 255, 255, 0), T))
+    img = rng.integers(0, 256, (3000, 3000, 4), dtype=np.uint8)
+    assert np.array_equal(pcv.xray_assign_background(ctx, img.copy(), (1, 2, 3, 4)), O.assign_background(img, (1, 2, 3, 4)))
