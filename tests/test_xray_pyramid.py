@@ -248,3 +248,33 @@ def test_xray_meta_against_python_protobuf():
     assert [(n.level, n.index) for n in m.nodes] == nodes and not m.bounding_rect.HasField("deprecated_min")
     assert m.SerializeToString() == raw
     assert [T.node_name(l, i) for l, i in nodes] == ["r", "r2", "r23", "r301"] == [pcv.xray_node_name(l, i) for l, i in nodes]
+
+
+def test_fuzz_parent_tiles_and_binning():
+    """hypothesis: arbitrary child / tile sizes (up- and down-scaling ratios), missing children, backgrounds; arbitrary columns
+    for the binned aggregation - the product's shared code against the oracle / a dictionary."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.integers(1, 24), st.integers(1, 40), st.lists(st.booleans(), min_size=4, max_size=4), st.tuples(*[st.integers(0, 255)] * 4), st.integers(0, 2 ** 31))
+    def parents(child_px, tile_px, present, bg, seed):
+        hyp.assume(any(present))
+        ch = [_noise(child_px, seed + k) if present[k] else None for k in range(4)]
+        assert np.array_equal(T.build_parent(ch, bg, tile_px), O.build_parent_tile(ch, bg, tile_px))
+
+    parents()
+
+    vals = st.floats(-1e6, 1e6, allow_nan=False, width=32)
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.lists(st.tuples(st.integers(0, 15), vals, st.floats(0, 1, width=32)), min_size=1, max_size=200), st.sampled_from([0.5, 3.0, 1000.0, -7.0, 1e-3]))
+    def bins(rows, size):
+        pixel = np.array([r[0] for r in rows], np.uint32)
+        attr = np.array([r[1] for r in rows], np.float32)
+        value = np.array([[r[2]] for r in rows], np.float32)
+        err, pix_sum, nb = T.binned(pixel, attr, value, size, 16, 1, bin_cap=256)
+        want_sum, want_nb = _binned_reference(pixel, attr, value, size, 16)
+        assert err == 0 and np.array_equal(nb, want_nb) and np.allclose(pix_sum, want_sum, rtol=1e-5, atol=1e-5)
+
+    bins()
