@@ -7,6 +7,7 @@
 //   point_viewer::iterator::{PointQuery, PointLocation, ParallelIterator::try_for_each_batch}
 //                                                       src/iterator.rs:13-20,66-72,255    -> pcv::PointQuery, pcv::ParallelIterator
 //   point_viewer::{PointsBatch, NodeId}                 src/lib.rs:102-107, src/octree/node.rs:52-111
+//   point_viewer::s2_cells::S2Cells, read_write::S2Splitter   src/s2_cells/mod.rs, src/read_write/s2.rs  -> pcv::S2Cells, pcv::s2_split
 //
 // Error behaviour: the reference panics (unwrap) in build_octree / get_visible_nodes and returns Result elsewhere; here
 // every failure is a pcv::Error exception carrying the pcv_status and text (callers that want the panic semantics let it
@@ -281,6 +282,135 @@ inline Octree build_octree_from_file(Context& ctx, const std::string& output_dir
     Octree tree(o);
     if (!output_directory.empty()) tree.write_to_directory(output_directory);
     return tree;
+}
+
+// ---- the S2-cell point cloud: point_viewer::s2_cells::S2Cells + read_write::S2Splitter (src/s2_cells/mod.rs, src/read_write/s2.rs) ----
+using CellID = uint64_t;                 // s2::cellid::CellID(u64)
+using CellUnion = std::vector<CellID>;   // s2::cellunion::CellUnion(Vec<CellID>)
+
+// CellID::to_token (the per-cell file stem of the S2 directory layout)
+inline std::string cell_token(CellID id) {
+    if (id == 0) return "X";
+    static const char* hex = "0123456789abcdef";
+    std::string s;
+    for (int k = 15; k >= 0; --k) s.push_back(hex[(id >> (4 * k)) & 15]);
+    while (!s.empty() && s.back() == '0') s.pop_back();
+    return s;
+}
+
+class S2Cells {
+   public:
+    explicit S2Cells(pcv_s2cloud* s) : s_(s) {}
+    // S2Cells::from_data_provider over an on-disk directory (mod.rs:203-216)
+    static S2Cells from_directory(Context& ctx, const std::string& directory) {
+        pcv_s2cloud* s = nullptr;
+        check(pcv_s2_load_dir(ctx.raw(), directory.c_str(), &s));
+        return S2Cells(s);
+    }
+    ~S2Cells() {
+        if (s_) pcv_s2_free(s_);
+    }
+    S2Cells(S2Cells&& o) noexcept : s_(o.s_) { o.s_ = nullptr; }
+    S2Cells(const S2Cells&) = delete;
+    S2Cells& operator=(const S2Cells&) = delete;
+
+    uint64_t num_points() const {
+        uint64_t n = 0;
+        check(pcv_s2_info(s_, nullptr, &n, nullptr, nullptr, nullptr, nullptr, nullptr));
+        return n;
+    }
+    Aabb bounding_box() const {  // PointCloud::bounding_box (mod.rs:192-194)
+        std::array<double, 3> mn{}, mx{};
+        check(pcv_s2_info(s_, nullptr, nullptr, nullptr, mn.data(), mx.data(), nullptr, nullptr));
+        return Aabb(mn, mx);
+    }
+    // S2Meta::get_cells: (cell id, num_points), in id order
+    std::vector<std::pair<CellID, uint64_t>> cells() const {
+        uint64_t nc = 0;
+        check(pcv_s2_info(s_, &nc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        std::vector<uint64_t> ids(nc), cnt(nc);
+        check(pcv_s2_cells(s_, ids.data(), cnt.data()));
+        std::vector<std::pair<CellID, uint64_t>> out(nc);
+        for (uint64_t k = 0; k < nc; ++k) out[k] = {ids[k], cnt[k]};
+        return out;
+    }
+    // PointCloud::nodes_in_location for PointLocation::AllPoints (nullptr) and PointLocation::S2Cells (mod.rs:157-168)
+    std::vector<CellID> nodes_in_location(const CellUnion* cell_union) const {
+        uint64_t n = 0;
+        const uint64_t* u = cell_union ? cell_union->data() : nullptr;
+        const uint32_t nu = cell_union ? (uint32_t)cell_union->size() : 0;
+        check(pcv_s2_cells_in_union(s_, u, nu, nullptr, 0, &n));
+        std::vector<CellID> out(n);
+        check(pcv_s2_cells_in_union(s_, u, nu, out.data(), n, &n));
+        return out;
+    }
+    // points_in_node (mod.rs:174-190) as one batch
+    PointsBatch points_in_node(CellID id) const {
+        PointsBatch b;
+        for (auto& c : cells())
+            if (c.first == id) {
+                int hc = 0, hi = 0;
+                check(pcv_s2_info(s_, nullptr, nullptr, nullptr, nullptr, nullptr, &hc, &hi));
+                b.position.resize(c.second);
+                if (hc) b.color.resize(c.second);
+                if (hi) b.intensity.resize(c.second);
+                check(pcv_s2_cell_data(s_, id, c.second ? b.position[0].data() : nullptr, hc && c.second ? b.color[0].data() : nullptr,
+                                       hi && c.second ? b.intensity.data() : nullptr, nullptr));
+                return b;
+            }
+        throw Error(PCV_ERR_NOT_FOUND, "cell " + cell_token(id) + " not found");
+    }
+    // the filtered point stream of PointLocation::AllPoints / S2Cells (iterator.rs:96-119 with the CellUnion as PointCulling)
+    PointsBatch query(const CellUnion* cell_union) const {
+        const uint64_t* u = cell_union ? cell_union->data() : nullptr;
+        const uint32_t nu = cell_union ? (uint32_t)cell_union->size() : 0;
+        uint64_t n = 0;
+        check(pcv_s2_query_union(s_, u, nu, nullptr, nullptr, nullptr, nullptr, 0, &n, nullptr));
+        int hc = 0, hi = 0;
+        check(pcv_s2_info(s_, nullptr, nullptr, nullptr, nullptr, nullptr, &hc, &hi));
+        PointsBatch b;
+        b.position.resize(n);
+        if (hc) b.color.resize(n);
+        if (hi) b.intensity.resize(n);
+        if (n)
+            check(pcv_s2_query_union(s_, u, nu, b.position[0].data(), hc ? b.color[0].data() : nullptr, hi ? b.intensity.data() : nullptr, nullptr, n, &n,
+                                     nullptr));
+        return b;
+    }
+    void write_to_directory(const std::string& dir) const { check(pcv_s2_write_dir(s_, dir.c_str())); }
+    pcv_s2cloud* raw() const { return s_; }
+
+   private:
+    pcv_s2cloud* s_;
+};
+
+// S2Splitter::with_split_level(level, path, Encoding::Plain, ..) + write(batch)... + get_meta (read_write/s2.rs:33-50,59-125,165-173):
+// the batches of one cloud, split by S2 cell on the GPU; throws ("... is not a valid ECEF point") like the writer's Err.
+template <class BatchIterator>
+inline S2Cells s2_split(Context& ctx, const std::string& output_directory, BatchIterator begin, BatchIterator end, uint32_t split_level = 20) {
+    std::vector<std::array<double, 3>> pos;
+    std::vector<std::array<uint8_t, 3>> col;
+    std::vector<float> inten;
+    for (BatchIterator it = begin; it != end; ++it) {
+        const PointsBatch& b = *it;
+        pos.insert(pos.end(), b.position.begin(), b.position.end());
+        col.insert(col.end(), b.color.begin(), b.color.end());
+        inten.insert(inten.end(), b.intensity.begin(), b.intensity.end());
+    }
+    pcv_points pts{};
+    const double* base = pos.empty() ? nullptr : pos[0].data();
+    pts.x = base;
+    pts.y = base ? base + 1 : nullptr;
+    pts.z = base ? base + 2 : nullptr;
+    pts.stride = 3;
+    pts.rgb = col.size() == pos.size() && !col.empty() ? col[0].data() : nullptr;
+    pts.intensity = inten.size() == pos.size() && !inten.empty() ? inten.data() : nullptr;
+    pts.n = pos.size();
+    pcv_s2cloud* s = nullptr;
+    check(pcv_s2_build(ctx.raw(), &pts, split_level, &s));
+    S2Cells cloud(s);
+    if (!output_directory.empty()) cloud.write_to_directory(output_directory);
+    return cloud;
 }
 
 // ParallelIterator::new(point_clouds, query, batch_size, num_threads, buffer_size).try_for_each_batch(func) — iterator.rs:238-257.
