@@ -173,13 +173,13 @@ inline void s2_normalize(std::vector<uint64_t>& cells) {
     for (uint64_t id : cells) {
         if (!out.empty() && s2_range_min(out.back()) <= id && id <= s2_range_max(out.back())) continue;  // contained in the previous cell
         while (!out.empty() && s2_range_min(id) <= out.back() && out.back() <= s2_range_max(id)) out.pop_back();  // contains previous cells
-        while (out.size() >= 3) {  // the last three cells + id are the four children of one parent?
+        while (out.size() >= 3 && s2_level(id) != 0) {  // the last three cells + id: the four children of one parent?  (areSiblings)
             const size_t m = out.size();
             const uint64_t a = out[m - 3], b = out[m - 2], c = out[m - 1];
-            if ((a ^ b ^ c) != id) break;  // necessary condition (the libraries' fast reject)
-            const uint64_t mask = s2_lsb(id) << 1, m2 = ~(mask + (mask << 1));
-            const uint64_t idm = id & m2;
-            if ((a & m2) != idm || (b & m2) != idm || (c & m2) != idm || (id >> 61) != (a >> 61) || s2_level(id) == 0) break;
+            if ((a ^ b ^ c) != id) break;  // the libraries' fast reject: the XOR of four siblings is zero
+            const uint64_t two = s2_lsb(id) << 1, mask = ~(two + (two << 1));  // everything above the two bits that number the children
+            const uint64_t idm = id & mask;
+            if ((a & mask) != idm || (b & mask) != idm || (c & mask) != idm) break;
             out.resize(m - 3);
             id = s2_parent(id, s2_level(id) - 1);
         }

@@ -17,11 +17,9 @@ inline uint32_t pack_rgba(const uint8_t c[4]) { return (uint32_t)c[0] | ((uint32
 
 struct DevTaps {
     ResampleTaps t{};
-    uint32_t out = 0;
 };
 DevTaps upload_taps(Scratch& s, const ResampleTable& tb) {
     DevTaps d;
-    d.out = (uint32_t)tb.left.size();
     d.t.left = s.upload(tb.left.data(), tb.left.size());
     d.t.first = s.upload(tb.first.data(), tb.first.size());
     d.t.count = s.upload(tb.count.data(), tb.count.size());

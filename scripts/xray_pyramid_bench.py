@@ -47,7 +47,6 @@ def main():
 def bench_quadtree(ctx, pcv, O, np, a, cores):
     out = {}
     n = int(a.points)
-    cores = os.cpu_count() or 1
     kind = O.SYNTH_GAUSS_CLUSTERS
     x, y, z, rgb = O.synth_points(kind, 1, 0, n, num_threads=cores)
     bmin, bmax, res = O.synth_bbox(kind)
